@@ -1,0 +1,361 @@
+// Persistent warp-specialised bf16 GEMM on the 5th-gen tensor cores (sm_100a).
+//
+//   D[M,N] (+)= A . B,  fp32 accumulation in TMEM, bf16 output.
+//
+//  * operands staged global -> shared by TMA (cp.async.bulk.tensor, 128B swizzle)
+//    through a 4-stage full/empty mbarrier ring,
+//  * tcgen05.mma (128x256x16, kind::f16) issued by ONE thread, accumulators live
+//    in TMEM, double-buffered (2 x 256 columns) so the epilogue of tile i overlaps
+//    the mainloop of tile i+1,
+//  * epilogue warps: tcgen05.ld -> bf16 -> swizzled shared -> TMA store,
+//  * persistent grid (one CTA per SM) with grouped-M rasterisation for L2 reuse,
+//  * A and B may each be K-major or MN-major (UMMA descriptor major bits), so
+//    forward (x.W^T), dgrad (dy.W) and wgrad (dy^T.x) of a Linear layer all run
+//    without materialising transposes.
+//
+// This is the hot op behind every transformer GEMM the reference reaches through
+// `model(**batch)` / `accelerator.backward(loss)` (training.py:108-112).
+#include <mutex>
+#include <string>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tcgen05.cuh"
+
+namespace hb {
+
+namespace {
+
+using namespace sm100;
+
+constexpr int BM = 128;
+constexpr int BN = 256;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kAStage = BM * BK * 2;       // 16 KB
+constexpr int kBStage = BN * BK * 2;       // 32 KB
+constexpr int kEpiWarpBuf = 32 * 128;      // 32 rows x 64 bf16, per buffer
+constexpr int kEpiBytes = 4 * 2 * kEpiWarpBuf;
+constexpr int kTmemCols = 512;             // 2 accumulator stages x 256 fp32 columns
+constexpr int kGroupM = 16;
+constexpr int kThreads = 256;
+
+struct SmemLayout {
+  static constexpr int a_off = 0;
+  static constexpr int b_off = a_off + kStages * kAStage;
+  static constexpr int epi_off = b_off + kStages * kBStage;
+  static constexpr int bar_off = epi_off + kEpiBytes;
+  // barriers: full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], tmem_ptr
+  static constexpr int total = bar_off + (2 * kStages + 4) * 8 + 16;
+};
+constexpr int kSmemBytes = SmemLayout::total + 1024;  // slack for manual 1 KB alignment
+
+struct GemmParams {
+  int M, N, K;
+  int a_mn, b_mn;      // 1 => operand is MN-major
+  int accumulate;
+  const bf16* D;
+  int ldd;
+  int tiles_m, tiles_n, num_tiles;
+};
+
+__device__ __forceinline__ void tile_coords(int t, const GemmParams& p, int& tm, int& tn) {
+  const int per_group = kGroupM * p.tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * kGroupM;
+  const int gsz = min(p.tiles_m - first_m, kGroupM);
+  const int r = t - g * per_group;
+  tm = first_m + (r % gsz);
+  tn = r / gsz;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
+                         const __grid_constant__ CUtensorMap tma_b,
+                         const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t a_smem = smem_base + SmemLayout::a_off;
+  const uint32_t b_smem = smem_base + SmemLayout::b_off;
+  const uint32_t bars = smem_base + SmemLayout::bar_off;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages + 2 + s); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + SmemLayout::bar_off + 8 * (2 * kStages + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_kb = (p.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0 && lane == 0) {
+    // ============================ TMA producer ============================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      int tm, tn;
+      tile_coords(t, p, tm, tn);
+      const int m0 = tm * BM, n0 = tn * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_arrive_expect_tx(full_bar(stage), kAStage + kBStage);
+        const int k0 = kb * BK;
+        const uint32_t sa = a_smem + stage * kAStage;
+        const uint32_t sb = b_smem + stage * kBStage;
+        if (!p.a_mn) {
+          tma_load_2d(sa, &tma_a, full_bar(stage), k0, m0);  // box {64 k, 128 m}
+        } else {
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)                     // box {64 m, 64 k}
+            tma_load_2d(sa + i * (BK * 128), &tma_a, full_bar(stage), m0 + i * 64, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d(sb, &tma_b, full_bar(stage), k0, n0);  // box {64 k, 256 n}
+        } else {
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)                     // box {64 n, 64 k}
+            tma_load_2d(sb + i * (BK * 128), &tma_b, full_bar(stage), n0 + i * 64, k0);
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ============================ MMA issuer ==============================
+    const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+    // K-major : rows at 128 B pitch, 8-row groups 1024 B apart; advance 32 B per UMMA_K.
+    // MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k groups 1024 B apart;
+    //           advance 16 k-rows = 2048 B per UMMA_K.
+    const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+    const uint32_t a_kadv = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+    const uint32_t b_kadv = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = a_smem + stage * kAStage;
+        const uint32_t sb = b_smem + stage * kBStage;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ad = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024);
+          const uint64_t bd = umma_smem_desc(sb + k * b_kadv, b_lbo, 1024);
+          umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(stage));  // frees the smem slot when these MMAs retire
+        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar(acc));      // accumulator complete -> epilogue
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue ================================
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lanes [32*ew, 32*ew+32)
+    const uint32_t epi_smem = smem_base + SmemLayout::epi_off + ew * 2 * kEpiWarpBuf;
+    int it = 0;
+    int buf = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+      int tm, tn;
+      tile_coords(t, p, tm, tn);
+      const int m0 = tm * BM, n0 = tn * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const int row = m0 + ew * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_addr + c * 64, r0);
+        tmem_ld_32x32(t_addr + c * 64 + 32, r1);
+        tmem_ld_wait();
+        if (c == BN / 64 - 1) {
+          // all TMEM reads of this accumulator are done: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+        const int col0 = n0 + c * 64;
+        uint32_t packed[32];
+        if (p.accumulate) {
+          const bool row_ok = row < p.M;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 prev = make_uint4(0, 0, 0, 0);
+            if (row_ok && col0 + j * 8 + 8 <= p.N)
+              prev = *reinterpret_cast<const uint4*>(p.D + (size_t)row * p.ldd + col0 + j * 8);
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = j * 8 + e * 2;
+              const float2 o = __bfloat1622float2(pv[e]);
+              const float x0 = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]) + o.x;
+              const float x1 = __uint_as_float(i + 1 < 32 ? r0[(i + 1) & 31] : r1[(i + 1) & 31]) + o.y;
+              __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * i]),
+                                                      __uint_as_float(r0[2 * i + 1]));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * i]),
+                                                      __uint_as_float(r1[2 * i + 1]));
+            packed[i] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[16 + i] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        }
+        // the buffer we are about to overwrite was handed to TMA two chunks ago
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t sbuf = epi_smem + buf * kEpiWarpBuf;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(packed[4 * j]),
+                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (col0 < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_d, sbuf, col0, m0 + ew * 32);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+std::string g_err;
+EncodeTiledFn g_encode = nullptr;
+std::once_flag g_once;
+int g_num_sms = 0;
+
+void init_once() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) ==
+          cudaSuccess && q == cudaDriverEntryPointSuccess) {
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kSmemBytes);
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements.
+bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+               uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+const char* gemm_last_error() { return g_err.c_str(); }
+
+int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
+                      int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
+                      cudaStream_t s) {
+  std::call_once(g_once, init_once);
+  if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
+  if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(A) || !al16(B) || !al16(D) || (lda % 8) || (ldb % 8) || (ldd % 8) || (N % 8)) {
+    g_err = "operands must be 16-byte aligned with leading dimensions and N multiples of 8";
+    return 3;
+  }
+  if ((a_kmajor || b_kmajor) && (K % 8)) { g_err = "K must be a multiple of 8"; return 3; }
+  if (!a_kmajor && (M % 8)) { g_err = "MN-major A needs M % 8 == 0"; return 3; }
+
+  CUtensorMap ta, tb, td;
+  bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)
+                     : make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
+  ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN)
+                       : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK));
+  ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
+  if (!ok) return 4;
+
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_kmajor ? 0 : 1;
+  p.b_mn = b_kmajor ? 0 : 1;
+  p.accumulate = accumulate;
+  p.D = D; p.ldd = ldd;
+  p.tiles_m = (M + BM - 1) / BM;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+  gemm_bf16_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, p);
+  count_launch();
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }
+  return 0;
+}
+
+}  // namespace hb

@@ -1,0 +1,90 @@
+// Host-side launch API of the hypha_b200 sm_100a kernels (raw pointers +
+// stream; the Python layer validates dtype/shape/contiguity).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hb {
+using bf16 = __nv_bfloat16;
+
+// ---- normalisation / elementwise (elementwise.cu) ---------------------------
+void rmsnorm_fwd(const bf16* x, const bf16* res_in, bf16* res_out, const bf16* w, bf16* y,
+                 float* rstd, int rows, int cols, float eps, cudaStream_t s);
+int rmsnorm_bwd_num_partials(int rows);
+void rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd,
+                 const bf16* dres_in, bf16* dx, float* dw_partial, int rows, int cols,
+                 cudaStream_t s);
+void colsum_partials(const float* partial, int nparts, int cols, bf16* out, int accumulate,
+                     cudaStream_t s);
+void rope_inplace(bf16* qkv, const float* cos, const float* sin, int tokens, int seq_len,
+                  int n_rot_heads, int head_dim, int row_stride, int backward, cudaStream_t s);
+void swiglu_fwd(const bf16* gu, bf16* out, int rows, int inter, cudaStream_t s);
+void swiglu_bwd(const bf16* dout, const bf16* gu, bf16* dgu, int rows, int inter, cudaStream_t s);
+void cross_entropy_fwd_bwd(bf16* logits, const int64_t* targets, float* loss_rows, int rows,
+                           int vocab, int row_stride, float grad_scale, int64_t ignore_index,
+                           cudaStream_t s);
+void embedding_fwd(const int64_t* ids, const bf16* table, bf16* out, int tokens, int dim,
+                   cudaStream_t s);
+void embedding_bwd(const int64_t* ids, const bf16* dout, bf16* dtable, int tokens, int dim,
+                   cudaStream_t s);
+void add_f32_into_bf16(const float* src, bf16* dst, int64_t n, int accumulate, cudaStream_t s);
+
+// ---- optimizers (optim.cu) --------------------------------------------------
+void adamw_flat(bf16* p, const bf16* g, float* master, void* m, void* v, int state_bf16,
+                int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                float bias_corr1, float bias_corr2, float grad_scale, uint32_t seed,
+                cudaStream_t s);
+
+// ---- DiLoCo outer step (outer_step.cu) --------------------------------------
+// Local part: delta[i] = bf16(master[i] - float(anchor[i]))
+void diloco_make_delta(const float* master, const bf16* anchor, bf16* delta, int64_t n,
+                       cudaStream_t s);
+struct OuterStepArgs {
+  // per-rank symmetric buffers (device pointers valid on THIS rank)
+  const bf16* delta_peers[8];   // peer-mapped delta buffers, index = rank
+  bf16* param_peers[8];         // peer-mapped bf16 parameter buffers
+  bf16* anchor_peers[8];        // peer-mapped bf16 anchor (round-start weights)
+  uint32_t* flag_peers[8];      // peer-mapped barrier flag words [>= 64 u32 each]
+  float* master;                // local fp32 master weights (full)
+  float* theta_outer;           // local fp32 outer params, shard only
+  float* momentum;              // local fp32 outer momentum, shard only
+  int64_t n;                    // total elements
+  int64_t shard_begin;          // first element owned by this rank
+  int64_t shard_len;            // elements owned by this rank
+  int world;                    // participating ranks this round
+  int rank;                     // my index among participants
+  uint32_t member_mask;         // bit r set => rank r participates
+  uint32_t epoch;               // monotonically increasing round id
+  float lr, mu;
+  int first_round;              // momentum := g on the first round
+  float inv_world;              // 1 / number of contributing ranks
+};
+void diloco_outer_step_fused(const OuterStepArgs& a, int num_ctas, cudaStream_t s);
+// Local Nesterov step.  delta_sum == null: single worker, exact fp32
+// g = master_in - theta.  Otherwise g = delta_sum*inv_world + (anchor - theta)
+// on a shard whose bf16 delta has already been reduced (NCCL fallback path).
+void diloco_outer_local(const float* master_in, const bf16* delta_sum, const bf16* anchor,
+                        float* theta_outer, float* momentum, float* master_out, bf16* param_out,
+                        int64_t n, float lr, float mu, int first_round, float inv_world,
+                        cudaStream_t s);
+void set_outer_timeout_ms(uint64_t ms);
+int diloco_outer_step_status(unsigned int* missing_mask);
+// peer-memory broadcast: copy bf16 params from a live rank (pull over NVLink)
+void peer_pull_copy(const void* src_peer, void* dst_local, int64_t bytes, int num_ctas,
+                    cudaStream_t s);
+void bf16_to_master(const bf16* p, float* master, int64_t n, cudaStream_t s);
+
+// ---- tcgen05 GEMM (gemm_tcgen05.cu) ------------------------------------------
+// D[M,N] (+)= A * B with bf16 inputs, fp32 TMEM accumulation, bf16 output.
+//  a_kmajor: A stored [M,K] (K contiguous) else stored [K,M]
+//  b_kmajor: B stored [N,K] (K contiguous) else stored [K,N]
+// lda/ldb/ldd are row strides (elements) of the stored matrices.
+int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
+                      int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
+                      cudaStream_t s);
+const char* gemm_last_error();
+
+unsigned long long launch_count();
+void reset_launch_count();
+}  // namespace hb

@@ -1,0 +1,360 @@
+// DiLoCo outer step as ONE persistent sm_100a kernel over NVLink/NVSwitch peer
+// memory -- no NCCL on this path.
+//
+// Replaces the reference's parameter-server round trip
+//   worker:  delta = theta_local - theta_prev              (utils.py:118-123, on CPU)
+//   PS:      avg  = running (a+b)/2 over received files     (parameter_server.rs:182-211)
+//            m    = mu*m + avg  (m0 = avg)                  (parameter_server.rs:386-416)
+//            u    = lr*(mu*m + avg)                         (parameter_server.rs:418-446)
+//   worker:  theta = theta_prev + u                         (utils.py:105-115)
+// with a true 1/N mean (the reference's pairwise average is only right for N=2,
+// SURVEY appendix B Q1).
+//
+// Layout.  Every rank r owns shard r of the flat parameter vector and keeps the
+// fp32 outer parameters theta_outer[shard] and momentum[shard] (ZeRO-1 style).
+// Every rank also keeps `anchor` = the bf16 weights all ranks started the round
+// from.  Using  mean_r(master_r) - theta_outer = mean_r(master_r - anchor) +
+// (anchor - theta_outer)  only bf16 deltas relative to the common anchor cross
+// NVLink while the owner's fp32 theta_outer absorbs the exact update (error
+// feedback), so no precision is lost to the 16-bit wire format.
+//
+// Phases (all inside one cooperative launch per rank):
+//   A  local : delta = bf16(master - anchor)                 -> symmetric buffer
+//   -- cross-GPU flag barrier (st.release.sys / ld.acquire.sys, epoch-stamped) --
+//   B  owner : g = mean_r delta_r[shard] (P2P 16-byte loads from every peer)
+//              + (anchor - theta_outer); Nesterov; theta_outer += u;
+//              P2P-store bf16(theta_outer) into every member's parameter buffer
+//   -- cross-GPU flag barrier --
+//   C  local : master = float(param); anchor = param
+// Barriers carry a timeout: a dead peer yields status != 0 instead of a hang so
+// the host can shrink the membership and retry.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace hb {
+
+namespace {
+
+struct LocalSync {
+  unsigned int grid_bar;   // local grid-barrier counter (zeroed before launch)
+  unsigned int status;     // 0 ok, 1 = barrier-1 timeout, 2 = barrier-2 timeout
+  unsigned int missing;    // bitmask of ranks that never arrived
+  unsigned int pad;
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ uint4 ld_peer_16(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+  return r;
+}
+__device__ __forceinline__ void st_peer_16(void* p, const uint4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Local grid barrier over a monotonically increasing counter.
+__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int old = atomicAdd(bar, 1u);
+    const unsigned int target = (old / nblocks + 1u) * nblocks;
+    while (ld_acquire_gpu(bar) < target) { __nanosleep(32); }
+  }
+  __syncthreads();
+}
+
+// Cross-GPU barrier: CTA 0 / thread r signals every member, then waits for all.
+// `slot` separates the barrier instances of one launch; tokens are epoch-unique.
+__device__ void cross_gpu_barrier(const OuterStepArgs& a, LocalSync* ls, int slot,
+                                  uint32_t token, uint64_t timeout_ns, unsigned int err_code) {
+  grid_barrier(&ls->grid_bar, gridDim.x);
+  if (blockIdx.x == 0) {
+    if (threadIdx.x < 8 && ((a.member_mask >> threadIdx.x) & 1u)) {
+      const int peer = threadIdx.x;
+      st_release_sys(a.flag_peers[peer] + slot * 8 + a.rank, token);
+      const uint32_t* mine = a.flag_peers[a.rank] + slot * 8 + peer;
+      const uint64_t t0 = globaltimer_ns();
+      while ((int32_t)(ld_acquire_sys(mine) - token) < 0) {
+        __nanosleep(64);
+        if (globaltimer_ns() - t0 > timeout_ns) {
+          atomicExch(&ls->status, err_code);
+          atomicOr(&ls->missing, 1u << peer);
+          break;
+        }
+      }
+    }
+  }
+  grid_barrier(&ls->grid_bar, gridDim.x);
+}
+
+__global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs a,
+                                                                   LocalSync* ls,
+                                                                   uint64_t timeout_ns) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+
+  // ---- Phase A: local pseudo-gradient relative to the common anchor ---------
+  {
+    bf16* my_delta = const_cast<bf16*>(a.delta_peers[a.rank]);
+    const bf16* anchor = a.anchor_peers[a.rank];
+    const int64_t nvec = a.n >> 3;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      const int64_t off = i << 3;
+      float w[8], x[8];
+      *reinterpret_cast<float4*>(w) = ld_stream_f32x4(a.master + off);
+      *reinterpret_cast<float4*>(w + 4) = ld_stream_f32x4(a.master + off + 4);
+      unpack8(ld_stream_bf16x8(anchor + off), x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) w[e] -= x[e];
+      st_bf16x8(my_delta + off, pack8(w));
+    }
+  }
+  cross_gpu_barrier(a, ls, 0, a.epoch * 2u + 1u, timeout_ns, 1u);
+  if (ld_acquire_gpu(&ls->status) != 0u) return;
+
+  // ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast --------
+  {
+    const bf16* anchor = a.anchor_peers[a.rank];
+    const int64_t nvec = a.shard_len >> 3;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      const int64_t loc = i << 3;
+      const int64_t off = a.shard_begin + loc;
+      uint4 raw[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if ((a.member_mask >> r) & 1u) raw[r] = ld_peer_16(a.delta_peers[r] + off);
+      }
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if ((a.member_mask >> r) & 1u) {
+          float d[8];
+          unpack8(*reinterpret_cast<bf16x8*>(&raw[r]), d);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[e] += d[e];
+        }
+      }
+      float x[8], th[8], mo[8];
+      unpack8(ld_stream_bf16x8(anchor + off), x);
+      *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(a.theta_outer + loc);
+      *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(a.theta_outer + loc + 4);
+      *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(a.momentum + loc);
+      *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(a.momentum + loc + 4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float g = acc[e] * a.inv_world + (x[e] - th[e]);
+        mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
+        th[e] += a.lr * (a.mu * mo[e] + g);
+      }
+      *reinterpret_cast<float4*>(a.theta_outer + loc) = *reinterpret_cast<float4*>(th);
+      *reinterpret_cast<float4*>(a.theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
+      *reinterpret_cast<float4*>(a.momentum + loc) = *reinterpret_cast<float4*>(mo);
+      *reinterpret_cast<float4*>(a.momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
+      bf16x8 pn = pack8(th);
+      const uint4 pv = *reinterpret_cast<uint4*>(&pn);
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        if ((a.member_mask >> r) & 1u) st_peer_16(a.param_peers[r] + off, pv);
+      }
+    }
+  }
+  cross_gpu_barrier(a, ls, 1, a.epoch * 2u + 2u, timeout_ns, 2u);
+  if (ld_acquire_gpu(&ls->status) != 0u) return;
+
+  // ---- Phase C: adopt the new global weights locally -------------------------
+  {
+    const bf16* param = a.param_peers[a.rank];
+    bf16* anchor = a.anchor_peers[a.rank];
+    const int64_t nvec = a.n >> 3;
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      const int64_t off = i << 3;
+      const uint4 raw = ld_peer_16(param + off);  // written by remote owners: bypass L1
+      float w[8];
+      unpack8(*reinterpret_cast<const bf16x8*>(&raw), w);
+      *reinterpret_cast<float4*>(a.master + off) = *reinterpret_cast<float4*>(w);
+      *reinterpret_cast<float4*>(a.master + off + 4) = *reinterpret_cast<float4*>(w + 4);
+      *reinterpret_cast<uint4*>(anchor + off) = raw;
+    }
+  }
+}
+
+LocalSync* g_local_sync[16] = {nullptr};
+
+LocalSync* local_sync_for_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (g_local_sync[dev] == nullptr) {
+    cudaMalloc(&g_local_sync[dev], sizeof(LocalSync));
+    cudaMemset(g_local_sync[dev], 0, sizeof(LocalSync));
+  }
+  return g_local_sync[dev];
+}
+
+}  // namespace
+
+static uint64_t g_outer_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
+void set_outer_timeout_ms(uint64_t ms) { g_outer_timeout_ns = ms * 1000000ull; }
+
+int diloco_outer_step_status(unsigned int* missing_mask) {
+  LocalSync h;
+  cudaMemcpy(&h, local_sync_for_device(), sizeof(LocalSync), cudaMemcpyDeviceToHost);
+  if (missing_mask) *missing_mask = h.missing;
+  return (int)h.status;
+}
+
+void diloco_outer_step_fused(const OuterStepArgs& a, int num_ctas, cudaStream_t s) {
+  LocalSync* ls = local_sync_for_device();
+  cudaMemsetAsync(ls, 0, sizeof(LocalSync), s);
+  if (num_ctas <= 0 || num_ctas > kNumSMs) num_ctas = kNumSMs;
+  OuterStepArgs args = a;
+  uint64_t timeout = g_outer_timeout_ns;
+  void* params[] = {&args, &ls, &timeout};
+  cudaLaunchCooperativeKernel((void*)diloco_outer_step_kernel, dim3(num_ctas), dim3(512), params,
+                              0, s);
+  count_launch();
+}
+
+// -----------------------------------------------------------------------------
+// Local helpers
+// -----------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) make_delta_kernel(const float* __restrict__ master,
+                                                         const bf16* __restrict__ anchor,
+                                                         bf16* __restrict__ delta, int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t off = i << 3;
+    float w[8], x[8];
+    *reinterpret_cast<float4*>(w) = ld_stream_f32x4(master + off);
+    *reinterpret_cast<float4*>(w + 4) = ld_stream_f32x4(master + off + 4);
+    unpack8(ld_stream_bf16x8(anchor + off), x);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) w[e] -= x[e];
+    st_bf16x8(delta + off, pack8(w));
+  }
+}
+static int flat_grid(int64_t nvec) {
+  int64_t b = (nvec + 255) / 256;
+  const int64_t cap = (int64_t)kNumSMs * 8;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+void diloco_make_delta(const float* master, const bf16* anchor, bf16* delta, int64_t n,
+                       cudaStream_t s) {
+  make_delta_kernel<<<flat_grid(n / 8), 256, 0, s>>>(master, anchor, delta, n / 8);
+  count_launch();
+}
+
+// g = (delta_sum*inv_world + anchor - theta)   [delta_sum != null, shard of a reduced delta]
+//   or (master - theta)                         [delta_sum == null, single worker, exact fp32]
+__global__ void __launch_bounds__(256) outer_local_kernel(
+    const float* __restrict__ master_in, const bf16* __restrict__ delta_sum,
+    const bf16* __restrict__ anchor, float* __restrict__ theta, float* __restrict__ mom,
+    float* __restrict__ master_out, bf16* __restrict__ param_out, int64_t nvec, float lr,
+    float mu, int first_round, float inv_world) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t off = i << 3;
+    float th[8], mo[8], g[8];
+    *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta + off);
+    *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta + off + 4);
+    *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(mom + off);
+    *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(mom + off + 4);
+    if (delta_sum != nullptr) {
+      float d[8], x[8];
+      unpack8(ld_stream_bf16x8(delta_sum + off), d);
+      unpack8(ld_stream_bf16x8(anchor + off), x);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = d[e] * inv_world + (x[e] - th[e]);
+    } else {
+      float w[8];
+      *reinterpret_cast<float4*>(w) = ld_stream_f32x4(master_in + off);
+      *reinterpret_cast<float4*>(w + 4) = ld_stream_f32x4(master_in + off + 4);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) g[e] = w[e] - th[e];
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      mo[e] = first_round ? g[e] : (mu * mo[e] + g[e]);
+      th[e] += lr * (mu * mo[e] + g[e]);
+    }
+    *reinterpret_cast<float4*>(theta + off) = *reinterpret_cast<float4*>(th);
+    *reinterpret_cast<float4*>(theta + off + 4) = *reinterpret_cast<float4*>(th + 4);
+    *reinterpret_cast<float4*>(mom + off) = *reinterpret_cast<float4*>(mo);
+    *reinterpret_cast<float4*>(mom + off + 4) = *reinterpret_cast<float4*>(mo + 4);
+    if (master_out != nullptr) {
+      *reinterpret_cast<float4*>(master_out + off) = *reinterpret_cast<float4*>(th);
+      *reinterpret_cast<float4*>(master_out + off + 4) = *reinterpret_cast<float4*>(th + 4);
+    }
+    if (param_out != nullptr) st_bf16x8(param_out + off, pack8(th));
+  }
+}
+void diloco_outer_local(const float* master_in, const bf16* delta_sum, const bf16* anchor,
+                        float* theta_outer, float* momentum, float* master_out, bf16* param_out,
+                        int64_t n, float lr, float mu, int first_round, float inv_world,
+                        cudaStream_t s) {
+  outer_local_kernel<<<flat_grid(n / 8), 256, 0, s>>>(master_in, delta_sum, anchor, theta_outer,
+                                                      momentum, master_out, param_out, n / 8, lr,
+                                                      mu, first_round, inv_world);
+  count_launch();
+}
+
+__global__ void __launch_bounds__(512) peer_pull_kernel(const uint4* __restrict__ src,
+                                                        uint4* __restrict__ dst, int64_t nvec) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = tid;
+  for (; i + 3 * stride < nvec; i += 4 * stride) {  // 4 x 16 B in flight per thread
+    uint4 v0 = ld_peer_16(src + i), v1 = ld_peer_16(src + i + stride);
+    uint4 v2 = ld_peer_16(src + i + 2 * stride), v3 = ld_peer_16(src + i + 3 * stride);
+    dst[i] = v0; dst[i + stride] = v1; dst[i + 2 * stride] = v2; dst[i + 3 * stride] = v3;
+  }
+  for (; i < nvec; i += stride) dst[i] = ld_peer_16(src + i);
+}
+void peer_pull_copy(const void* src_peer, void* dst_local, int64_t bytes, int num_ctas,
+                    cudaStream_t s) {
+  if (num_ctas <= 0) num_ctas = kNumSMs * 2;
+  peer_pull_kernel<<<num_ctas, 512, 0, s>>>(reinterpret_cast<const uint4*>(src_peer),
+                                            reinterpret_cast<uint4*>(dst_local), bytes / 16);
+  count_launch();
+}
+
+__global__ void __launch_bounds__(256) bf16_to_master_kernel(const bf16* __restrict__ p,
+                                                             float* __restrict__ master,
+                                                             int64_t nvec) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float w[8];
+    unpack8(ld_stream_bf16x8(p + (i << 3)), w);
+    *reinterpret_cast<float4*>(master + (i << 3)) = *reinterpret_cast<float4*>(w);
+    *reinterpret_cast<float4*>(master + (i << 3) + 4) = *reinterpret_cast<float4*>(w + 4);
+  }
+}
+void bf16_to_master(const bf16* p, float* master, int64_t n, cudaStream_t s) {
+  bf16_to_master_kernel<<<flat_grid(n / 8), 256, 0, s>>>(p, master, n / 8);
+  count_launch();
+}
+
+}  // namespace hb
