@@ -1,0 +1,296 @@
+"""Llama-family causal LM built on the hypha_b200 sm_100a op library.
+
+Design points (B200-first, not a port of HF ``LlamaForCausalLM``):
+
+* all parameters are views into ONE flat bf16 buffer (``FlatParams``) with a
+  matching flat gradient buffer, so the fused AdamW and the DiLoCo outer step are
+  single launches over contiguous memory, and the buffer can be placed in
+  peer-mapped symmetric memory for the NVLink outer step;
+* q/k/v and gate/up projections are fused weights -> one tcgen05 GEMM each;
+* residual add is fused into the following RMSNorm; RoPE runs in place on the
+  fused qkv activation; the LM head is fused with the cross-entropy (chunked);
+* activations can be recomputed per layer (``recompute_layers``) to trade FLOPs
+  for HBM when the optimizer state of an 8B model shares one 192 GB GPU.
+
+The reference obtains its model from ``AutoModelForCausalLM.from_pretrained``
+(executors/accelerate/src/hypha/accelerate_executor/model.py:47-56); here the
+architecture is local and weights are random-init or loaded from safetensors.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import asdict, dataclass, field
+from typing import Dict, Iterator, List, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+@dataclass
+class LlamaConfig:
+    vocab_size: int = 128256
+    hidden_size: int = 4096
+    intermediate_size: int = 14336
+    num_layers: int = 32
+    num_heads: int = 32
+    num_kv_heads: int = 8
+    head_dim: int = 128
+    rope_theta: float = 500000.0
+    rms_eps: float = 1e-5
+    max_seq_len: int = 8192
+    init_std: float = 0.02
+    recompute_layers: int = 0          # first k layers recompute their activations in backward
+    ce_chunk: int = 4096               # rows per fused LM-head/CE chunk
+    name: str = "llama"
+
+    @property
+    def qkv_dim(self) -> int:
+        return (self.num_heads + 2 * self.num_kv_heads) * self.head_dim
+
+    def num_params(self) -> int:
+        h, i, v = self.hidden_size, self.intermediate_size, self.vocab_size
+        per_layer = self.qkv_dim * h + h * self.num_heads * self.head_dim + 2 * i * h + h * i + 2 * h
+        return 2 * v * h + h + self.num_layers * per_layer
+
+    def flops_per_token(self, seq_len: int) -> float:
+        """Training FLOPs per token (fwd+bwd = 3x fwd; causal attention counted at half)."""
+        h, i = self.hidden_size, self.intermediate_size
+        dense = self.qkv_dim * h + h * self.num_heads * self.head_dim + 3 * i * h
+        attn = 2 * self.num_heads * self.head_dim * seq_len / 2  # QK^T + PV, causal
+        fwd = 2 * (self.num_layers * (dense + attn) + self.vocab_size * h)
+        return 3.0 * fwd
+
+    def to_dict(self) -> dict:
+        return asdict(self)
+
+
+PRESETS: Dict[str, LlamaConfig] = {
+    "llama3-8b": LlamaConfig(name="llama3-8b"),
+    "llama3-1b": LlamaConfig(vocab_size=128256, hidden_size=2048, intermediate_size=8192,
+                             num_layers=16, num_heads=32, num_kv_heads=8, head_dim=64,
+                             name="llama3-1b"),
+    "llama-tiny": LlamaConfig(vocab_size=1024, hidden_size=256, intermediate_size=512,
+                              num_layers=2, num_heads=4, num_kv_heads=2, head_dim=64,
+                              max_seq_len=256, ce_chunk=128, name="llama-tiny"),
+    "llama-small": LlamaConfig(vocab_size=32000, hidden_size=1024, intermediate_size=4096,
+                               num_layers=4, num_heads=8, num_kv_heads=4, head_dim=128,
+                               max_seq_len=2048, ce_chunk=2048, name="llama-small"),
+}
+
+
+def get_config(name: str, **overrides) -> LlamaConfig:
+    cfg = PRESETS[name]
+    d = cfg.to_dict()
+    d.update(overrides)
+    return LlamaConfig(**d)
+
+
+class FlatParams:
+    """One flat bf16 parameter buffer + one flat bf16 gradient buffer.
+
+    ``alloc`` may be supplied to place the parameter buffer in peer-mapped
+    symmetric memory (see ``hypha_b200.parallel.peer_memory``)."""
+
+    ALIGN = 64  # elements; keeps every tensor 128-byte aligned for TMA
+
+    def __init__(self, shapes: List[Tuple[str, Tuple[int, ...]]], device, dtype=torch.bfloat16,
+                 alloc=None, grad_alloc=None, with_grad: bool = True):
+        self.layout: Dict[str, Tuple[int, Tuple[int, ...]]] = {}
+        off = 0
+        for name, shape in shapes:
+            n = math.prod(shape)
+            self.layout[name] = (off, shape)
+            off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = (off + 1023) // 1024 * 1024
+        if alloc is not None:
+            self.data = alloc(self.numel, dtype)
+        else:
+            self.data = torch.zeros(self.numel, dtype=dtype, device=device)
+        if not with_grad:
+            self.grad = None
+        elif grad_alloc is not None:
+            self.grad = grad_alloc(self.numel, dtype)
+        else:
+            self.grad = torch.zeros(self.numel, dtype=dtype, device=device)
+
+    def view(self, name: str, of: Optional[torch.Tensor] = None) -> torch.Tensor:
+        off, shape = self.layout[name]
+        base = self.data if of is None else of
+        return base[off: off + math.prod(shape)].view(shape)
+
+    def named_views(self) -> Iterator[Tuple[str, torch.Tensor]]:
+        for name in self.layout:
+            yield name, self.view(name)
+
+
+def _ckpt_run(fn, a, b):
+    return fn(a, b)
+
+
+class _CheckpointPair(torch.autograd.Function):
+    """Recompute-in-backward for a ``(delta, residual) -> (delta, residual)`` layer."""
+
+    @staticmethod
+    def forward(ctx, fn, delta, residual):
+        ctx.fn = fn
+        ctx.save_for_backward(delta, residual)
+        with torch.no_grad():
+            d, r = fn(delta, residual)
+        return d, r
+
+    @staticmethod
+    def backward(ctx, dd, dr):
+        delta, residual = ctx.saved_tensors
+        delta = delta.detach().requires_grad_(True)
+        residual = residual.detach().requires_grad_(True)
+        with torch.enable_grad():
+            d, r = ctx.fn(delta, residual)
+            torch.autograd.backward([d, r], [dd, dr])
+        return None, delta.grad, residual.grad
+
+
+class LlamaBlock(nn.Module):
+    def __init__(self, cfg: LlamaConfig, wqkv, wo, wgu, wdown, norm1, norm2):
+        super().__init__()
+        self.cfg = cfg
+        self.wqkv, self.wo, self.wgu, self.wdown = wqkv, wo, wgu, wdown
+        self.norm1, self.norm2 = norm1, norm2
+
+    def forward(self, delta, residual, cos, sin, batch: int, seq: int):
+        c = self.cfg
+        n1, res = ops.add_rmsnorm(delta, residual, self.norm1, c.rms_eps)
+        qkv = ops.linear(n1, self.wqkv)
+        qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim)
+        att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
+        o = ops.linear(att, self.wo)
+        n2, res = ops.add_rmsnorm(o, res, self.norm2, c.rms_eps)
+        gu = ops.linear(n2, self.wgu)
+        act = ops.swiglu(gu)
+        down = ops.linear(act, self.wdown)
+        return down, res
+
+
+class LlamaForCausalLM(nn.Module):
+    """Causal LM; ``forward(input_ids, labels)`` returns the mean token loss."""
+
+    def __init__(self, cfg: LlamaConfig, device="cuda", dtype=torch.bfloat16, alloc=None,
+                 grad_alloc=None, seed: int = 0, init: bool = True):
+        super().__init__()
+        self.cfg = cfg
+        h, i, v = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size
+        shapes: List[Tuple[str, Tuple[int, ...]]] = [("embed", (v, h))]
+        for l in range(cfg.num_layers):
+            shapes += [
+                (f"layers.{l}.norm1", (h,)),
+                (f"layers.{l}.wqkv", (cfg.qkv_dim, h)),
+                (f"layers.{l}.wo", (h, cfg.num_heads * cfg.head_dim)),
+                (f"layers.{l}.norm2", (h,)),
+                (f"layers.{l}.wgu", (2 * i, h)),
+                (f"layers.{l}.wdown", (h, i)),
+            ]
+        shapes += [("final_norm", (h,)), ("lm_head", (v, h))]
+        self.flat = FlatParams(shapes, device, dtype, alloc=alloc, grad_alloc=grad_alloc)
+        self._params: Dict[str, nn.Parameter] = {}
+        for name, view in self.flat.named_views():
+            p = nn.Parameter(view, requires_grad=True)
+            p.main_grad = self.flat.view(name, of=self.flat.grad)
+            p.grad_accumulate = False
+            self._params[name] = p
+            self.register_parameter(name.replace(".", "_"), p)
+        P = self._params
+        self.blocks = nn.ModuleList([
+            LlamaBlock(cfg, P[f"layers.{l}.wqkv"], P[f"layers.{l}.wo"], P[f"layers.{l}.wgu"],
+                       P[f"layers.{l}.wdown"], P[f"layers.{l}.norm1"], P[f"layers.{l}.norm2"])
+            for l in range(cfg.num_layers)
+        ])
+        self._rope_cache: Dict[Tuple[int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+        if init:
+            self.reset_parameters(seed)
+
+    # -- parameters ---------------------------------------------------------------------
+    @torch.no_grad()
+    def reset_parameters(self, seed: int = 0) -> None:
+        g = torch.Generator(device=self.flat.data.device)
+        g.manual_seed(seed)
+        cfg = self.cfg
+        for name, view in self.flat.named_views():
+            if "norm" in name:
+                view.fill_(1.0)
+            else:
+                std = cfg.init_std
+                if name.endswith("wo") or name.endswith("wdown"):
+                    std = cfg.init_std / math.sqrt(2 * cfg.num_layers)
+                view.normal_(0.0, std, generator=g)
+
+    def named_flat_parameters(self) -> Dict[str, nn.Parameter]:
+        return dict(self._params)
+
+    def set_grad_accumulate(self, flag: bool) -> None:
+        for p in self._params.values():
+            p.grad_accumulate = flag
+
+    def _rope(self, seq: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+        key = (seq, str(device))
+        if key not in self._rope_cache:
+            self._rope_cache[key] = ops.rope_tables(seq, self.cfg.head_dim, self.cfg.rope_theta, device)
+        return self._rope_cache[key]
+
+    # -- forward ------------------------------------------------------------------------
+    def forward(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None):
+        cfg = self.cfg
+        batch, seq = input_ids.shape
+        cos, sin = self._rope(seq, input_ids.device)
+        P = self._params
+        delta = ops.embedding(input_ids, P["embed"])
+        residual = torch.zeros_like(delta)
+        for l, blk in enumerate(self.blocks):
+            if l < cfg.recompute_layers and torch.is_grad_enabled():
+                fn = lambda d, r, blk=blk: blk(d, r, cos, sin, batch, seq)
+                delta, residual = _CheckpointPair.apply(fn, delta, residual)
+            else:
+                delta, residual = blk(delta, residual, cos, sin, batch, seq)
+        hN, _ = ops.add_rmsnorm(delta, residual, P["final_norm"], cfg.rms_eps)
+        if labels is None:
+            return ops.linear(hN, P["lm_head"]).view(batch, seq, -1)
+        return ops.linear_cross_entropy(hN, P["lm_head"], labels.reshape(-1), chunk=cfg.ce_chunk)
+
+    # -- HF interop -----------------------------------------------------------------------
+    @torch.no_grad()
+    def load_hf_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Load a HuggingFace ``LlamaForCausalLM`` state dict (fuses q/k/v and gate/up)."""
+        P = self._params
+        P["embed"].copy_(sd["model.embed_tokens.weight"])
+        P["final_norm"].copy_(sd["model.norm.weight"])
+        P["lm_head"].copy_(sd.get("lm_head.weight", sd["model.embed_tokens.weight"]))
+        for l in range(self.cfg.num_layers):
+            pre = f"model.layers.{l}."
+            P[f"layers.{l}.wqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.weight"],
+                                                   sd[pre + "self_attn.k_proj.weight"],
+                                                   sd[pre + "self_attn.v_proj.weight"]], 0))
+            P[f"layers.{l}.wo"].copy_(sd[pre + "self_attn.o_proj.weight"])
+            P[f"layers.{l}.wgu"].copy_(torch.cat([sd[pre + "mlp.gate_proj.weight"],
+                                                  sd[pre + "mlp.up_proj.weight"]], 0))
+            P[f"layers.{l}.wdown"].copy_(sd[pre + "mlp.down_proj.weight"])
+            P[f"layers.{l}.norm1"].copy_(sd[pre + "input_layernorm.weight"])
+            P[f"layers.{l}.norm2"].copy_(sd[pre + "post_attention_layernorm.weight"])
+
+    def to_hf_state_dict(self) -> Dict[str, torch.Tensor]:
+        c, P = self.cfg, self._params
+        qd, kd = c.num_heads * c.head_dim, c.num_kv_heads * c.head_dim
+        sd = {"model.embed_tokens.weight": P["embed"].detach(), "model.norm.weight": P["final_norm"].detach(),
+              "lm_head.weight": P["lm_head"].detach()}
+        for l in range(c.num_layers):
+            pre = f"model.layers.{l}."
+            wqkv, wgu = P[f"layers.{l}.wqkv"].detach(), P[f"layers.{l}.wgu"].detach()
+            sd[pre + "self_attn.q_proj.weight"] = wqkv[:qd]
+            sd[pre + "self_attn.k_proj.weight"] = wqkv[qd: qd + kd]
+            sd[pre + "self_attn.v_proj.weight"] = wqkv[qd + kd:]
+            sd[pre + "self_attn.o_proj.weight"] = P[f"layers.{l}.wo"].detach()
+            sd[pre + "mlp.gate_proj.weight"] = wgu[: c.intermediate_size]
+            sd[pre + "mlp.up_proj.weight"] = wgu[c.intermediate_size:]
+            sd[pre + "mlp.down_proj.weight"] = P[f"layers.{l}.wdown"].detach()
+            sd[pre + "input_layernorm.weight"] = P[f"layers.{l}.norm1"].detach()
+            sd[pre + "post_attention_layernorm.weight"] = P[f"layers.{l}.norm2"].detach()
+        return sd

@@ -1,0 +1,477 @@
+"""Differentiable front-ends of the sm_100a kernels.
+
+Every op has two implementations:
+
+* CUDA tensors  -> the hand-written kernels in ``hypha_b200/_C`` (bf16 I/O);
+* CPU tensors   -> a plain PyTorch implementation of the same math, used by the
+  CPU plumbing configuration (GPT-2 / gloo) and as the numerics reference in
+  ``tests/``.
+
+Weight gradients follow the Megatron ``main_grad`` convention: when a parameter
+carries a ``main_grad`` view (a slice of the model's flat gradient buffer) the
+backward kernels write into it directly -- the wgrad GEMM epilogue either
+overwrites or accumulates depending on ``param.grad_accumulate`` -- and autograd
+sees ``None``.  This is what lets one flat fused-AdamW launch update the model.
+
+Reference parity: these are the ops the reference reaches through
+``outputs = model(**batch)`` / ``accelerator.backward(loss)``
+(executors/accelerate/src/hypha/accelerate_executor/training.py:108-112).
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from .native import cuda_stream, load_C
+
+_GEMM_BACKEND = os.environ.get("HYPHA_GEMM", "tcgen05")
+
+
+def set_gemm_backend(name: str) -> None:
+    """``tcgen05`` (hand-written kernel, default) or ``cublas`` (torch.mm, baseline)."""
+    global _GEMM_BACKEND
+    if name not in ("tcgen05", "cublas"):
+        raise ValueError(name)
+    _GEMM_BACKEND = name
+
+
+def get_gemm_backend() -> str:
+    return _GEMM_BACKEND
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+# -----------------------------------------------------------------------------
+# GEMM
+# -----------------------------------------------------------------------------
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
+         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """``D[M,N] (+)= A . B`` without materialising transposes.
+
+    ``a_kmajor``: ``a`` is stored ``[M, K]`` else ``[K, M]``;
+    ``b_kmajor``: ``b`` is stored ``[N, K]`` else ``[K, N]`` (row-major, unit inner stride).
+    """
+    assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
+    M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
+    N, Kb = (b.shape[0], b.shape[1]) if b_kmajor else (b.shape[1], b.shape[0])
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
+        accumulate = False
+    assert out.shape == (M, N) and out.stride(1) == 1
+    use_native = (a.is_cuda and _GEMM_BACKEND == "tcgen05" and a.dtype == torch.bfloat16
+                  and b.dtype == torch.bfloat16 and out.dtype == torch.bfloat16
+                  and N % 8 == 0 and K % 8 == 0 and (a_kmajor or M % 8 == 0)
+                  and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and out.stride(0) % 8 == 0
+                  and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+                  and out.data_ptr() % 16 == 0)
+    if use_native:
+        load_C().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0),
+                           b.stride(0), out.stride(0), int(a_kmajor), int(b_kmajor),
+                           int(accumulate), cuda_stream())
+        return out
+    A = a if a_kmajor else a.t()
+    B = b.t() if b_kmajor else b
+    if accumulate:
+        out.addmm_(A, B)
+    else:
+        torch.mm(A, B, out=out)
+    return out
+
+
+def _wgrad_into(param: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor) -> Optional[torch.Tensor]:
+    """dW[N,K] = dy^T . x ; written into ``param.main_grad`` when present."""
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        gemm(dy2, x2, a_kmajor=False, b_kmajor=False, out=mg,
+             accumulate=bool(getattr(param, "grad_accumulate", False)))
+        return None
+    return gemm(dy2, x2, a_kmajor=False, b_kmajor=False)
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = gemm(x2, weight)
+        ctx.save_for_backward(x2, weight)
+        ctx.x_shape = x.shape
+        return y.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight = ctx.saved_tensors
+        dy2 = dy.reshape(-1, dy.shape[-1])
+        if dy2.stride(1) != 1 or dy2.stride(0) % 8 != 0:
+            dy2 = dy2.contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = gemm(dy2, weight, a_kmajor=True, b_kmajor=False).view(ctx.x_shape)
+        dw = _wgrad_into(weight, dy2, x2) if ctx.needs_input_grad[1] else None
+        return dx, dw
+
+
+def linear(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``y = x @ weight.T`` (no bias); fwd/dgrad/wgrad all on the tcgen05 GEMM."""
+    if not x.is_cuda:
+        return F.linear(x, weight)
+    return _Linear.apply(x, weight)
+
+
+# -----------------------------------------------------------------------------
+# RMSNorm (+ fused residual add)
+# -----------------------------------------------------------------------------
+def _rmsnorm_ref(x: torch.Tensor, weight: torch.Tensor, eps: float) -> torch.Tensor:
+    xf = x.float()
+    y = xf * torch.rsqrt(xf.pow(2).mean(-1, keepdim=True) + eps)
+    return (y * weight.float()).to(x.dtype)
+
+
+def _norm_wgrad(param: torch.Tensor, partial: torch.Tensor, nparts: int, cols: int):
+    C = load_C()
+    mg = getattr(param, "main_grad", None)
+    if mg is not None:
+        C.colsum_partials(partial.data_ptr(), nparts, cols, mg.data_ptr(),
+                          int(bool(getattr(param, "grad_accumulate", False))), cuda_stream())
+        return None
+    dw = torch.empty(cols, dtype=torch.bfloat16, device=partial.device)
+    C.colsum_partials(partial.data_ptr(), nparts, cols, dw.data_ptr(), 0, cuda_stream())
+    return dw.to(param.dtype)
+
+
+class _RMSNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        C = load_C()
+        cols = x.shape[-1]
+        x2 = x.reshape(-1, cols)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        C.rmsnorm_fwd(x2.data_ptr(), 0, 0, weight.data_ptr(), y.data_ptr(), rstd.data_ptr(), rows,
+                      cols, eps, cuda_stream())
+        ctx.save_for_backward(x2, weight, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        C = load_C()
+        x2, weight, rstd = ctx.saved_tensors
+        rows, cols = x2.shape
+        dy2 = dy.reshape(rows, cols).contiguous()
+        dx = torch.empty_like(x2)
+        nparts = C.rmsnorm_bwd_num_partials(rows)
+        partial = torch.empty((nparts, cols), dtype=torch.float32, device=x2.device)
+        C.rmsnorm_bwd(dy2.data_ptr(), x2.data_ptr(), weight.data_ptr(), rstd.data_ptr(), 0,
+                      dx.data_ptr(), partial.data_ptr(), rows, cols, cuda_stream())
+        dw = _norm_wgrad(weight, partial, nparts, cols)
+        return dx.view(ctx.shape), dw, None
+
+
+class _AddRMSNorm(torch.autograd.Function):
+    """h = x + residual ; y = rmsnorm(h) * w ; returns (y, h)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, weight, eps):
+        C = load_C()
+        cols = x.shape[-1]
+        x2 = x.reshape(-1, cols).contiguous()
+        r2 = residual.reshape(-1, cols).contiguous()
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        h = torch.empty_like(x2)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        C.rmsnorm_fwd(x2.data_ptr(), r2.data_ptr(), h.data_ptr(), weight.data_ptr(), y.data_ptr(),
+                      rstd.data_ptr(), rows, cols, eps, cuda_stream())
+        ctx.save_for_backward(h, weight, rstd)
+        ctx.shape = x.shape
+        return y.view(x.shape), h.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dh):
+        C = load_C()
+        h, weight, rstd = ctx.saved_tensors
+        rows, cols = h.shape
+        dy2 = dy.reshape(rows, cols).contiguous()
+        dh2 = dh.reshape(rows, cols).contiguous() if dh is not None else None
+        dx = torch.empty_like(h)
+        nparts = C.rmsnorm_bwd_num_partials(rows)
+        partial = torch.empty((nparts, cols), dtype=torch.float32, device=h.device)
+        C.rmsnorm_bwd(dy2.data_ptr(), h.data_ptr(), weight.data_ptr(), rstd.data_ptr(), _ptr(dh2),
+                      dx.data_ptr(), partial.data_ptr(), rows, cols, cuda_stream())
+        dw = _norm_wgrad(weight, partial, nparts, cols)
+        dxv = dx.view(ctx.shape)
+        return dxv, dxv, dw, None
+
+
+def rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    if not x.is_cuda:
+        return _rmsnorm_ref(x, weight, eps)
+    return _RMSNorm.apply(x, weight, eps)
+
+
+def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor,
+                eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fused ``h = x + residual; y = rmsnorm(h)``; returns ``(y, h)``."""
+    if not x.is_cuda:
+        h = (x.float() + residual.float()).to(x.dtype)
+        return _rmsnorm_ref(h, weight, eps), h
+    return _AddRMSNorm.apply(x, residual, weight, eps)
+
+
+# -----------------------------------------------------------------------------
+# RoPE
+# -----------------------------------------------------------------------------
+def rope_tables(seq_len: int, head_dim: int, theta: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
+    ang = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=device), inv)
+    return ang.cos().contiguous(), ang.sin().contiguous()
+
+
+def _rope_ref(qkv, cos, sin, seq_len, n_rot_heads, head_dim):
+    T = qkv.shape[0]
+    x = qkv.view(T, -1, head_dim)
+    rot, rest = x[:, :n_rot_heads].float(), x[:, n_rot_heads:]
+    pos = torch.arange(T, device=qkv.device) % seq_len
+    c, s = cos[pos][:, None, :], sin[pos][:, None, :]
+    x1, x2 = rot[..., : head_dim // 2], rot[..., head_dim // 2:]
+    out = torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(qkv.dtype)
+    return torch.cat([out, rest], dim=1).reshape(T, -1)
+
+
+class _RoPE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, cos, sin, seq_len, n_rot_heads, head_dim):
+        assert qkv.dim() == 2 and qkv.stride(1) == 1
+        load_C().rope_inplace(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), qkv.shape[0], seq_len,
+                              n_rot_heads, head_dim, qkv.stride(0), 0, cuda_stream())
+        ctx.mark_dirty(qkv)
+        ctx.save_for_backward(cos, sin)
+        ctx.args = (seq_len, n_rot_heads, head_dim)
+        return qkv
+
+    @staticmethod
+    def backward(ctx, dqkv):
+        cos, sin = ctx.saved_tensors
+        seq_len, n_rot_heads, head_dim = ctx.args
+        if not dqkv.is_contiguous():
+            dqkv = dqkv.contiguous()
+        load_C().rope_inplace(dqkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), dqkv.shape[0],
+                              seq_len, n_rot_heads, head_dim, dqkv.stride(0), 1, cuda_stream())
+        return dqkv, None, None, None, None, None
+
+
+def rope_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int,
+             n_rot_heads: int, head_dim: int) -> torch.Tensor:
+    """Rotate the q and k heads of a fused ``[tokens, (Hq+2Hkv)*D]`` activation in place."""
+    if not qkv.is_cuda:
+        return _rope_ref(qkv, cos, sin, seq_len, n_rot_heads, head_dim)
+    return _RoPE.apply(qkv, cos, sin, seq_len, n_rot_heads, head_dim)
+
+
+# -----------------------------------------------------------------------------
+# SwiGLU
+# -----------------------------------------------------------------------------
+class _SwiGLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, gu):
+        rows, two_i = gu.shape
+        out = torch.empty((rows, two_i // 2), dtype=gu.dtype, device=gu.device)
+        load_C().swiglu_fwd(gu.data_ptr(), out.data_ptr(), rows, two_i // 2, cuda_stream())
+        ctx.save_for_backward(gu)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (gu,) = ctx.saved_tensors
+        rows, two_i = gu.shape
+        dgu = torch.empty_like(gu)
+        load_C().swiglu_bwd(dout.contiguous().data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows,
+                            two_i // 2, cuda_stream())
+        return dgu
+
+
+def swiglu(gu: torch.Tensor) -> torch.Tensor:
+    """``silu(gate) * up`` on a fused ``[rows, 2*I]`` (gate | up) activation."""
+    if not gu.is_cuda:
+        g, u = gu.chunk(2, dim=-1)
+        return (F.silu(g.float()) * u.float()).to(gu.dtype)
+    assert gu.dim() == 2 and gu.is_contiguous()
+    return _SwiGLU.apply(gu)
+
+
+# -----------------------------------------------------------------------------
+# Attention (causal, GQA) on the fused qkv activation
+# -----------------------------------------------------------------------------
+def _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim):
+    T = batch * seq
+    q = qkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim).transpose(1, 2)
+    k = qkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim).transpose(1, 2)
+    v = qkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim).transpose(1, 2)
+    rep = n_heads // n_kv
+    k = k.repeat_interleave(rep, dim=1)
+    v = v.repeat_interleave(rep, dim=1)
+    o = F.scaled_dot_product_attention(q, k, v, is_causal=True)
+    return o.transpose(1, 2).reshape(T, n_heads * head_dim)
+
+
+class _FlashAttnQKV(torch.autograd.Function):
+    """Causal GQA attention reading q/k/v as strided views of the fused qkv buffer and
+    writing dq/dk/dv straight into one dqkv buffer (no concat / split copies)."""
+
+    @staticmethod
+    def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim):
+        from flash_attn.flash_attn_interface import _flash_attn_forward
+
+        q = qkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim)
+        k = qkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim)
+        v = qkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim)
+        scale = 1.0 / math.sqrt(head_dim)
+        out, lse, _, rng = _flash_attn_forward(q, k, v, 0.0, scale, True, -1, -1, 0.0, None, False)
+        ctx.save_for_backward(qkv, out, lse, rng)
+        ctx.dims = (batch, seq, n_heads, n_kv, head_dim, scale)
+        return out.view(batch * seq, n_heads * head_dim)
+
+    @staticmethod
+    def backward(ctx, dout):
+        from flash_attn.flash_attn_interface import _flash_attn_backward
+
+        qkv, out, lse, rng = ctx.saved_tensors
+        batch, seq, n_heads, n_kv, head_dim, scale = ctx.dims
+        q = qkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim)
+        k = qkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim)
+        v = qkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim)
+        dqkv = torch.empty_like(qkv)
+        dq = dqkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim)
+        dk = dqkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim)
+        dv = dqkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim)
+        do = dout.contiguous().view(batch, seq, n_heads, head_dim)
+        _flash_attn_backward(do, q, k, v, out, lse, dq, dk, dv, 0.0, scale, True, -1, -1, 0.0, None,
+                             False, rng)
+        return dqkv, None, None, None, None, None
+
+
+def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int,
+                  head_dim: int) -> torch.Tensor:
+    """Causal self-attention on a fused (already RoPE'd) qkv activation -> ``[tokens, Hq*D]``."""
+    if not qkv.is_cuda:
+        return _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim)
+    return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+
+
+# -----------------------------------------------------------------------------
+# Embedding
+# -----------------------------------------------------------------------------
+class _Embedding(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, table):
+        tokens = ids.numel()
+        dim = table.shape[1]
+        out = torch.empty((tokens, dim), dtype=table.dtype, device=table.device)
+        load_C().embedding_fwd(ids.data_ptr(), table.data_ptr(), out.data_ptr(), tokens, dim,
+                               cuda_stream())
+        ctx.save_for_backward(ids)
+        ctx.table = table
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (ids,) = ctx.saved_tensors
+        table = ctx.table
+        mg = getattr(table, "main_grad", None)
+        if mg is not None:
+            if not getattr(table, "grad_accumulate", False):
+                mg.zero_()
+            target, ret = mg, None
+        else:
+            target = torch.zeros_like(table)
+            ret = target
+        load_C().embedding_bwd(ids.data_ptr(), dout.contiguous().data_ptr(), target.data_ptr(),
+                               ids.numel(), table.shape[1], cuda_stream())
+        return None, ret
+
+
+def embedding(ids: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """Row gather ``table[ids]`` -> ``[tokens, dim]`` (ids flattened, int64)."""
+    if not table.is_cuda:
+        return F.embedding(ids.reshape(-1), table)
+    return _Embedding.apply(ids.reshape(-1).contiguous(), table)
+
+
+# -----------------------------------------------------------------------------
+# Fused LM head + softmax cross-entropy (chunked; logits are never kept)
+# -----------------------------------------------------------------------------
+class _LinearCrossEntropy(torch.autograd.Function):
+    """loss = mean CE(h @ W^T, targets).  The backward of logits is produced in place by the
+    CE kernel inside forward, immediately consumed by the dgrad/wgrad GEMMs, and dropped, so
+    peak memory is one ``[chunk, vocab]`` bf16 tile instead of ``[tokens, vocab]`` fp32."""
+
+    @staticmethod
+    def forward(ctx, h, weight, targets, chunk, ignore_index):
+        C = load_C()
+        T, K = h.shape
+        V = weight.shape[0]
+        if ignore_index is None:
+            n_valid, ignore_index = T, -100          # caller guarantees every target is valid
+        else:
+            n_valid = max(int((targets != ignore_index).sum().item()), 1)   # host sync
+        scale = 1.0 / n_valid
+        loss_rows = torch.empty(T, dtype=torch.float32, device=h.device)
+        dh = torch.empty_like(h)
+        logits = torch.empty((min(chunk, T), V), dtype=torch.bfloat16, device=h.device)
+        mg = getattr(weight, "main_grad", None)
+        dw = mg if mg is not None else torch.empty_like(weight)
+        accumulate = bool(getattr(weight, "grad_accumulate", False)) if mg is not None else False
+        for s in range(0, T, chunk):
+            e = min(s + chunk, T)
+            lg = logits[: e - s]
+            gemm(h[s:e], weight, out=lg)
+            C.cross_entropy_fwd_bwd(lg.data_ptr(), targets[s:e].data_ptr(), loss_rows[s:e].data_ptr(),
+                                    e - s, V, lg.stride(0), scale, ignore_index, cuda_stream())
+            gemm(lg, weight, a_kmajor=True, b_kmajor=False, out=dh[s:e])
+            gemm(lg, h[s:e], a_kmajor=False, b_kmajor=False, out=dw, accumulate=accumulate or s > 0)
+        ctx.save_for_backward(dh)
+        ctx.dw = None if mg is not None else dw
+        return loss_rows.sum() * scale
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dh,) = ctx.saved_tensors
+        # dloss is 1.0 for a plain `loss.backward()`; keep generality without a host sync.
+        dh = dh * dloss.to(dh.dtype)
+        dw = ctx.dw
+        if dw is not None:
+            dw = dw * dloss.to(dw.dtype)
+        return dh, dw, None, None, None
+
+
+def linear_cross_entropy(h: torch.Tensor, weight: torch.Tensor, targets: torch.Tensor,
+                         chunk: int = 4096, ignore_index: Optional[int] = None) -> torch.Tensor:
+    """Mean token cross-entropy of ``h @ weight.T`` against ``targets`` (LM head fused in).
+
+    ``ignore_index=None`` promises that every target is valid, which keeps the op free of
+    host synchronisation; pass an index (e.g. ``-100``) to mask padding tokens."""
+    if not h.is_cuda:
+        logits = F.linear(h, weight).float()
+        return F.cross_entropy(logits, targets.reshape(-1),
+                               ignore_index=-100 if ignore_index is None else ignore_index)
+    return _LinearCrossEntropy.apply(h, weight, targets.reshape(-1).contiguous(), chunk, ignore_index)
+
+
+def cross_entropy_inplace(logits: torch.Tensor, targets: torch.Tensor, grad_scale: float,
+                          ignore_index: int = -100) -> torch.Tensor:
+    """Raw kernel access: returns per-row losses and overwrites ``logits`` with d(loss)/d(logits)."""
+    rows, vocab = logits.shape
+    loss_rows = torch.empty(rows, dtype=torch.float32, device=logits.device)
+    load_C().cross_entropy_fwd_bwd(logits.data_ptr(), targets.data_ptr(), loss_rows.data_ptr(), rows,
+                                   vocab, logits.stride(0), grad_scale, ignore_index, cuda_stream())
+    return loss_rows

@@ -1,0 +1,6 @@
+"""Parallelism: DiLoCo (inner fused AdamW, outer fused NVLink step) + peer memory."""
+from .diloco import AdamWConfig, DiLoCoConfig, DiLoCoOuter, FlatAdamW, make_lr_lambda, shard_bounds
+from .peer_memory import BandwidthCounters, PeerGroup, SymmetricBuffer
+
+__all__ = ["AdamWConfig", "DiLoCoConfig", "DiLoCoOuter", "FlatAdamW", "make_lr_lambda",
+           "shard_bounds", "BandwidthCounters", "PeerGroup", "SymmetricBuffer"]

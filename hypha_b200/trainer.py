@@ -1,0 +1,137 @@
+"""DiLoCoTrainer: the public training API of hypha_b200 on one B200 (one rank).
+
+    trainer = DiLoCoTrainer.create("llama3-8b", group=PeerGroup.from_torch_distributed())
+    loss = trainer.step(input_ids_pinned_cpu, labels_pinned_cpu)   # one inner step (+ outer every H)
+
+A step = H2D copy of the batch on a side stream, forward + backward on the
+sm_100a kernels, ONE fused flat-AdamW launch, and -- every ``inner_steps`` steps --
+the fused NVLink outer step.  The loss stays on the device; ``loss.item()`` (or
+``trainer.read_loss()``) is the only device->host sync the caller pays, which
+removes the reference's per-step ``loss.cpu()`` + HTTP status round trip
+(training.py:115-125).
+"""
+from __future__ import annotations
+
+import os
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+
+from .models.llama import LlamaConfig, LlamaForCausalLM, get_config
+from .parallel.diloco import AdamWConfig, DiLoCoConfig, DiLoCoOuter, FlatAdamW, make_lr_lambda
+from .parallel.peer_memory import PeerGroup
+
+
+@dataclass
+class StepStats:
+    step: int
+    round: int
+    did_outer: bool
+
+
+class DiLoCoTrainer:
+    def __init__(self, model: LlamaForCausalLM, adamw: AdamWConfig, diloco: DiLoCoConfig,
+                 group: Optional[PeerGroup] = None, param_buf=None, grad_buf=None,
+                 scheduler: Optional[dict] = None, process_group=None):
+        self.model = model
+        self.device = model.flat.data.device
+        self.opt = FlatAdamW(model.flat.data, model.flat.grad, adamw, make_lr_lambda(scheduler))
+        self.outer = DiLoCoOuter(self.opt, diloco, group, param_buf, grad_buf, process_group)
+        self.diloco = diloco
+        self.global_step = 0
+        self._h2d_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        self.last_loss: Optional[torch.Tensor] = None
+        self.h2d_bytes = 0
+
+    # -- construction -------------------------------------------------------------------
+    @classmethod
+    def create(cls, model: str | LlamaConfig = "llama3-8b", *, adamw: Optional[AdamWConfig] = None,
+               diloco: Optional[DiLoCoConfig] = None, group: Optional[PeerGroup] = None,
+               device: Optional[int] = None, seed: int = 0, scheduler: Optional[dict] = None,
+               process_group=None, **model_overrides) -> "DiLoCoTrainer":
+        cfg = get_config(model, **model_overrides) if isinstance(model, str) else model
+        adamw = adamw or AdamWConfig()
+        diloco = diloco or DiLoCoConfig()
+        dev = torch.cuda.current_device() if device is None else device
+        torch.cuda.set_device(dev)
+        param_buf = grad_buf = None
+        want_fused = group is not None and group.world > 1 and diloco.backend in ("auto", "fused")
+        if want_fused:
+            holders = {}
+
+            def alloc(n, dt):
+                holders["p"] = group.alloc("model.params", n, dt)
+                return holders["p"].local
+
+            def galloc(n, dt):
+                holders["g"] = group.alloc("model.grads", n, dt)
+                return holders["g"].local
+
+            net = LlamaForCausalLM(cfg, device=f"cuda:{dev}", alloc=alloc, grad_alloc=galloc, seed=seed)
+            param_buf, grad_buf = holders["p"], holders["g"]
+        else:
+            net = LlamaForCausalLM(cfg, device=f"cuda:{dev}", seed=seed)
+        return cls(net, adamw, diloco, group, param_buf, grad_buf, scheduler, process_group)
+
+    # -- one inner step ---------------------------------------------------------------------
+    def _to_device(self, t: torch.Tensor) -> torch.Tensor:
+        if t.device == self.device:
+            return t
+        self.h2d_bytes += t.numel() * t.element_size()
+        with torch.cuda.stream(self._h2d_stream):
+            d = t.to(self.device, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(self._h2d_stream)
+        d.record_stream(torch.cuda.current_stream())
+        return d
+
+    def inner_step(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        ids = self._to_device(input_ids)
+        lab = self._to_device(labels)
+        self.model.set_grad_accumulate(False)
+        loss = self.model(ids, lab)
+        loss.backward()
+        self.opt.step()
+        self.last_loss = loss.detach()
+        return self.last_loss
+
+    def outer_step(self) -> None:
+        self.outer.step()
+
+    def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One DiLoCo inner step; runs the outer step when ``inner_steps`` are complete."""
+        if labels is None:
+            labels = torch.roll(input_ids, -1, dims=-1)
+        loss = self.inner_step(input_ids, labels)
+        self.global_step += 1
+        if self.global_step % self.diloco.inner_steps == 0:
+            self.outer_step()
+        return loss
+
+    def read_loss(self) -> float:
+        """Device->host read of the last loss (4 bytes)."""
+        return float(self.last_loss.item())
+
+    # -- checkpoint (absent in the reference; needed for rejoin) -------------------
+    def state_dict(self) -> Dict[str, torch.Tensor]:
+        sd = {"params": self.model.flat.data, "global_step": torch.tensor(self.global_step)}
+        sd.update({f"opt.{k}": v for k, v in self.opt.state_dict().items()})
+        sd.update({f"outer.{k}": v for k, v in self.outer.state_dict().items()})
+        return sd
+
+    def save_checkpoint(self, path: str) -> None:
+        from safetensors.torch import save_file
+
+        tmp = path + ".tmp"
+        save_file({k: v.detach().contiguous().cpu() for k, v in self.state_dict().items()}, tmp)
+        os.replace(tmp, path)
+
+    def load_checkpoint(self, path: str) -> None:
+        from safetensors.torch import load_file
+
+        sd = load_file(path, device=str(self.device))
+        self.model.flat.data.copy_(sd["params"])
+        self.global_step = int(sd["global_step"])
+        self.opt.load_state_dict({k[4:]: v for k, v in sd.items() if k.startswith("opt.")})
+        self.outer.load_state_dict({k[6:]: v for k, v in sd.items() if k.startswith("outer.")})

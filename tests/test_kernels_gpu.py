@@ -1,0 +1,315 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def C():
+    from hypha_b200.ops.native import load_C
+
+    return load_C()
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / (b.norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 264, 136), (1000, 1032, 520),
+                                   (2048, 4096, 4096)])
+def test_gemm_tcgen05(C, a_k, b_k, M, N, K):
+    from hypha_b200 import ops
+
+    if not a_k and M % 8:
+        pytest.skip("MN-major A needs M % 8 == 0")
+    torch.manual_seed(0)
+    dev = "cuda"
+    A = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+    B = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
+    a = A if a_k else A.t().contiguous()
+    b = B if b_k else B.t().contiguous()
+    ops.set_gemm_backend("tcgen05")
+    out = ops.gemm(a, b, a_kmajor=a_k, b_kmajor=b_k)
+    ref = A.float() @ B.float().t()
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 5e-3, f"rel err {_rel(out, ref)}"
+
+
+def test_gemm_accumulate(C):
+    from hypha_b200 import ops
+
+    torch.manual_seed(1)
+    M, N, K = 384, 520, 200
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    D0 = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    out = D0.clone()
+    ops.set_gemm_backend("tcgen05")
+    ops.gemm(A, B, out=out, accumulate=True)
+    ref = D0.float() + A.float() @ B.float().t()
+    assert _rel(out, ref) < 5e-3
+
+
+def test_gemm_strided_views(C):
+    """lda/ldb/ldd larger than the logical width (views into fused buffers)."""
+    from hypha_b200 import ops
+
+    torch.manual_seed(2)
+    big = torch.randn(512, 1024, device="cuda", dtype=torch.bfloat16)
+    A = big[:, 128:128 + 256]
+    W = torch.randn(384, 256, device="cuda", dtype=torch.bfloat16)
+    outbig = torch.zeros(512, 1024, device="cuda", dtype=torch.bfloat16)
+    out = outbig[:, 256:256 + 384]
+    ops.set_gemm_backend("tcgen05")
+    ops.gemm(A, W, out=out)
+    assert _rel(out, A.float() @ W.float().t()) < 5e-3
+    assert outbig[:, :256].abs().sum().item() == 0 and outbig[:, 640:].abs().sum().item() == 0
+
+
+@pytest.mark.parametrize("rows,cols", [(7, 256), (333, 768), (1024, 4096), (64, 8192)])
+def test_rmsnorm_fwd_bwd(C, rows, cols):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    x = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(rows, cols, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = (1 + 0.1 * torch.randn(cols, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    y, h = ops.add_rmsnorm(x, r, w, 1e-5)
+    dy = torch.randn_like(y)
+    dh = torch.randn_like(h)
+    torch.autograd.backward([y, h], [dy, dh])
+    xf, rf, wf = (t.detach().float().requires_grad_(True) for t in (x, r, w))
+    hs = xf + rf
+    hf = hs + (hs.to(torch.bfloat16).float() - hs).detach()  # bf16-rounded h, straight-through grad
+    yf = hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5) * wf
+    torch.autograd.backward([yf, hf], [dy.float(), dh.float()])
+    assert _rel(y, yf) < 1e-2 and _rel(h, hf) < 1e-2
+    assert _rel(x.grad, xf.grad) < 1e-2 and _rel(r.grad, rf.grad) < 1e-2
+    assert _rel(w.grad, wf.grad) < 2e-2
+    # plain (no residual)
+    x2 = x.detach().clone().requires_grad_(True)
+    w2 = w.detach().clone().requires_grad_(True)
+    y2 = ops.rmsnorm(x2, w2, 1e-5)
+    y2.backward(dy)
+    xf2, wf2 = x2.detach().float().requires_grad_(True), w2.detach().float().requires_grad_(True)
+    yf2 = xf2 * torch.rsqrt(xf2.pow(2).mean(-1, keepdim=True) + 1e-5) * wf2
+    yf2.backward(dy.float())
+    assert _rel(y2, yf2) < 1e-2 and _rel(x2.grad, xf2.grad) < 1e-2 and _rel(w2.grad, wf2.grad) < 2e-2
+
+
+def test_rope(C):
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _rope_ref
+
+    torch.manual_seed(0)
+    B, S, Hq, Hk, D = 2, 96, 8, 2, 128
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16)
+    cos, sin = ops.rope_tables(S, D, 500000.0, "cuda")
+    ref = _rope_ref(qkv.clone(), cos, sin, S, Hq + Hk, D)
+    x = qkv.clone().requires_grad_(True)
+    y = ops.rope_qkv(x * 1.0, cos, sin, S, Hq + Hk, D)
+    assert _rel(y, ref) < 1e-2
+    g = torch.randn_like(y)
+    y.backward(g)
+    xr = qkv.clone().float().requires_grad_(True)
+    yr = _rope_ref(xr, cos, sin, S, Hq + Hk, D)
+    yr.backward(g.float())
+    assert _rel(x.grad, xr.grad) < 1e-2
+
+
+def test_swiglu(C):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    gu = torch.randn(300, 2 * 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    out = ops.swiglu(gu)
+    d = torch.randn_like(out)
+    out.backward(d)
+    gf = gu.detach().float().requires_grad_(True)
+    g, u = gf.chunk(2, -1)
+    of = torch.nn.functional.silu(g) * u
+    of.backward(d.float())
+    assert _rel(out, of) < 1e-2 and _rel(gu.grad, gf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("rows,vocab", [(5, 1024), (64, 32000), (16, 128256)])
+def test_cross_entropy(C, rows, vocab):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    logits = (3 * torch.randn(rows, vocab, device="cuda")).to(torch.bfloat16)
+    tgt = torch.randint(0, vocab, (rows,), device="cuda")
+    tgt[0] = -100
+    lf = logits.float().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf, tgt, reduction="none", ignore_index=-100)
+    (ref.sum() * 0.25).backward()
+    z = logits.clone()
+    loss = ops.cross_entropy_inplace(z, tgt, 0.25, -100)
+    assert torch.allclose(loss, ref, atol=2e-2, rtol=1e-2)
+    assert _rel(z, lf.grad) < 2e-2
+
+
+def test_linear_cross_entropy(C):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    T, K, V = 300, 256, 1024
+    h = torch.randn(T, K, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    W = (0.05 * torch.randn(V, K, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    tgt = torch.randint(0, V, (T,), device="cuda")
+    loss = ops.linear_cross_entropy(h, W, tgt, chunk=128)
+    loss.backward()
+    hf, Wf = h.detach().float().requires_grad_(True), W.detach().float().requires_grad_(True)
+    lf = torch.nn.functional.cross_entropy(hf @ Wf.t(), tgt)
+    lf.backward()
+    assert abs(loss.item() - lf.item()) < 2e-2
+    assert _rel(h.grad, hf.grad) < 3e-2 and _rel(W.grad, Wf.grad) < 3e-2
+
+
+def test_embedding(C):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    table = torch.randn(1000, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    ids = torch.randint(0, 1000, (4, 64), device="cuda")
+    out = ops.embedding(ids, table)
+    assert torch.equal(out, table.detach()[ids.reshape(-1)])
+    d = torch.randn_like(out)
+    out.backward(d)
+    ref = torch.zeros(1000, 256, device="cuda")
+    ref.index_add_(0, ids.reshape(-1), d.float())
+    assert _rel(table.grad, ref) < 2e-2
+
+
+@pytest.mark.parametrize("state", ["fp32", "bf16"])
+def test_adamw_matches_torch(C, state):
+    from hypha_b200.parallel.diloco import AdamWConfig, FlatAdamW
+
+    torch.manual_seed(0)
+    n = 8192 * 3
+    p = torch.randn(n, device="cuda").to(torch.bfloat16)
+    g = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    opt = FlatAdamW(p, g, AdamWConfig(lr=1e-2, state_dtype=state))
+    ref_p = p.float().clone().requires_grad_(True)
+    ref = torch.optim.AdamW([ref_p], lr=1e-2)
+    for _ in range(5):
+        gr = torch.randn(n, device="cuda").to(torch.bfloat16)
+        g.copy_(gr)
+        opt.step()
+        ref_p.grad = gr.float()
+        ref.step()
+    tol = 1e-5 if state == "fp32" else 5e-3
+    assert _rel(opt.master, ref_p.detach()) < tol
+    assert torch.equal(p, opt.master.to(torch.bfloat16))
+
+
+def test_attention_matches_sdpa(C):
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _attention_ref
+
+    torch.manual_seed(0)
+    B, S, Hq, Hk, D = 2, 256, 8, 2, 128
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
+    d = torch.randn_like(out)
+    out.backward(d)
+    qf = qkv.detach().float().requires_grad_(True)
+    of = _attention_ref(qf, B, S, Hq, Hk, D)
+    of.backward(d.float())
+    assert _rel(out, of) < 2e-2 and _rel(qkv.grad, qf.grad) < 3e-2
+
+
+def test_outer_step_reference_vector(C):
+    """Nesterov vector from the reference's own test (parameter_server.rs:452-524):
+    lr=0.1 mu=0.7, g0=0.5 -> u0=0.085 ; g1=[.1..5] -> u1=[.0415,.0585,.0755,.0925,.1095]."""
+    n = 1024
+    s = torch.cuda.current_stream().cuda_stream
+    theta = torch.zeros(n, device="cuda")
+    mom = torch.zeros(n, device="cuda")
+    master = torch.full((n,), 0.5, device="cuda")
+    p = torch.zeros(n, device="cuda", dtype=torch.bfloat16)
+    C.diloco_outer_local(master.data_ptr(), 0, 0, theta.data_ptr(), mom.data_ptr(), master.data_ptr(),
+                         p.data_ptr(), n, 0.1, 0.7, 1, 1.0, s)
+    assert torch.allclose(theta, torch.full_like(theta, 0.085), atol=1e-6)
+    assert torch.allclose(master, theta)
+    g1 = torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5], device="cuda").repeat(n // 5 + 1)[:n]
+    master.copy_(theta + g1)
+    before = theta.clone()
+    C.diloco_outer_local(master.data_ptr(), 0, 0, theta.data_ptr(), mom.data_ptr(), master.data_ptr(),
+                         p.data_ptr(), n, 0.1, 0.7, 0, 1.0, s)
+    u1 = (theta - before)[:5]
+    assert torch.allclose(u1, torch.tensor([0.0415, 0.0585, 0.0755, 0.0925, 0.1095], device="cuda"), atol=1e-6)
+
+
+def test_fused_outer_step_single_rank(C):
+    """The fused peer-memory kernel with world=1 must equal the math of the local kernel."""
+    from hypha_b200.parallel.diloco import AdamWConfig, DiLoCoConfig, DiLoCoOuter, FlatAdamW
+    from hypha_b200.parallel.peer_memory import PeerGroup
+
+    torch.manual_seed(0)
+    n = 1024 * 64
+    grp = PeerGroup.solo()
+    pbuf = grp.alloc("p", n, torch.bfloat16)
+    gbuf = grp.alloc("g", n, torch.bfloat16)
+    pbuf.local.copy_(torch.randn(n, device="cuda"))
+    opt = FlatAdamW(pbuf.local, gbuf.local, AdamWConfig())
+    outer = DiLoCoOuter(opt, DiLoCoConfig(backend="fused", outer_lr=0.7, outer_momentum=0.9), grp, pbuf, gbuf)
+    theta0 = outer.theta_outer.clone()
+    anchor = outer.anchor_buf.local.float()
+    for rnd in range(2):
+        opt.master.add_(0.01 * torch.randn(n, device="cuda"))
+        m_before = opt.master.clone()
+        mom_before = outer.momentum.clone()
+        th_before = outer.theta_outer.clone()
+        anchor = outer.anchor_buf.local.float()
+        outer.step()
+        assert outer.check() == (0, 0)
+        delta = (m_before - anchor).to(torch.bfloat16).float()
+        g = delta + (anchor - th_before)
+        mom = g if rnd == 0 else 0.9 * mom_before + g
+        th = th_before + 0.7 * (0.9 * mom + g)
+        assert torch.allclose(outer.theta_outer, th, atol=1e-5, rtol=1e-5)
+        assert torch.equal(pbuf.local, th.to(torch.bfloat16))
+        assert torch.equal(opt.master, pbuf.local.float())
+        assert torch.equal(outer.anchor_buf.local, pbuf.local)
+    grp.close()
+
+
+def test_llama_tiny_trains(C):
+    from hypha_b200.parallel.diloco import AdamWConfig, DiLoCoConfig
+    from hypha_b200.trainer import DiLoCoTrainer
+
+    torch.manual_seed(0)
+    tr = DiLoCoTrainer.create("llama-tiny", adamw=AdamWConfig(lr=3e-3, state_dtype="fp32"),
+                              diloco=DiLoCoConfig(inner_steps=5))
+    ids = torch.randint(0, 1024, (4, 128)).pin_memory()
+    losses = [tr.step(ids).item() for _ in range(20)]
+    assert losses[0] > math.log(1024) - 1.0
+    assert losses[-1] < losses[0] - 1.0, losses
+    assert tr.outer.round == 4
+
+
+def test_llama_matches_reference_autograd(C):
+    """Loss + flat gradients of the kernel path vs the same model evaluated with stock fp32 ops."""
+    from hypha_b200.models.llama import LlamaForCausalLM, get_config
+
+    torch.manual_seed(0)
+    cfg = get_config("llama-tiny")
+    net = LlamaForCausalLM(cfg, device="cuda", seed=3)
+    ids = torch.randint(0, cfg.vocab_size, (2, 128), device="cuda")
+    lab = torch.roll(ids, -1, 1)
+    loss = net(ids, lab)
+    loss.backward()
+    ref = LlamaForCausalLM(cfg, device="cpu", dtype=torch.float32, seed=3)
+    ref.flat.data.copy_(net.flat.data.float().cpu())
+    lr = ref(ids.cpu(), lab.cpu())
+    lr.backward()
+    assert abs(loss.item() - lr.item()) < 3e-2
+    for name, p in ref.named_flat_parameters().items():
+        got = net.named_flat_parameters()[name].main_grad
+        assert _rel(got.cpu(), p.grad) < 6e-2, name
