@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
-        self._stop = threading.Event()
+        self._halt = threading.Event()
         self._nvml = None
         try:
             import pynvml
@@ -67,7 +67,7 @@ class ClockSampler(threading.Thread):
             self._nvml = None
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 if self._nvml is not None:
                     n = self._nvml
@@ -93,10 +93,10 @@ class ClockSampler(threading.Thread):
                             self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(self.period)
+            self._halt.wait(self.period)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=2)
         return {"sm_mhz": int(statistics.median(self.samples)) if self.samples else None,
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),

@@ -162,7 +162,7 @@ class LlamaBlock(nn.Module):
         c = self.cfg
         n1, res = ops.add_rmsnorm(delta, residual, self.norm1, c.rms_eps)
         qkv = ops.linear(n1, self.wqkv)
-        qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim)
+        qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim, grad_inplace=True)
         att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
         o = ops.linear(att, self.wo)
         n2, res = ops.add_rmsnorm(o, res, self.norm2, c.rms_eps)

@@ -102,7 +102,7 @@ class _Linear(torch.autograd.Function):
         y = gemm(x2, weight)
         ctx.save_for_backward(x2, weight)
         ctx.x_shape = x.shape
-        return y.view(*x.shape[:-1], weight.shape[0])
+        return y if x.dim() == 2 else y.view(*x.shape[:-1], weight.shape[0])
 
     @staticmethod
     def backward(ctx, dy):
@@ -160,7 +160,7 @@ class _RMSNorm(torch.autograd.Function):
                       cols, eps, cuda_stream())
         ctx.save_for_backward(x2, weight, rstd)
         ctx.shape = x.shape
-        return y.view(x.shape)
+        return y if x.dim() == 2 else y.view(x.shape)
 
     @staticmethod
     def backward(ctx, dy):
@@ -194,6 +194,8 @@ class _AddRMSNorm(torch.autograd.Function):
                       rstd.data_ptr(), rows, cols, eps, cuda_stream())
         ctx.save_for_backward(h, weight, rstd)
         ctx.shape = x.shape
+        if x.dim() == 2:
+            return y, h
         return y.view(x.shape), h.view(x.shape)
 
     @staticmethod
@@ -250,13 +252,14 @@ def _rope_ref(qkv, cos, sin, seq_len, n_rot_heads, head_dim):
 
 class _RoPE(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, cos, sin, seq_len, n_rot_heads, head_dim):
+    def forward(ctx, qkv, cos, sin, seq_len, n_rot_heads, head_dim, grad_inplace):
         assert qkv.dim() == 2 and qkv.stride(1) == 1
         load_C().rope_inplace(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), qkv.shape[0], seq_len,
                               n_rot_heads, head_dim, qkv.stride(0), 0, cuda_stream())
         ctx.mark_dirty(qkv)
         ctx.save_for_backward(cos, sin)
         ctx.args = (seq_len, n_rot_heads, head_dim)
+        ctx.grad_inplace = grad_inplace
         return qkv
 
     @staticmethod
@@ -265,17 +268,23 @@ class _RoPE(torch.autograd.Function):
         seq_len, n_rot_heads, head_dim = ctx.args
         if not dqkv.is_contiguous():
             dqkv = dqkv.contiguous()
+        elif not ctx.grad_inplace:
+            dqkv = dqkv.clone()   # autograd contract: never mutate an incoming gradient
         load_C().rope_inplace(dqkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), dqkv.shape[0],
                               seq_len, n_rot_heads, head_dim, dqkv.stride(0), 1, cuda_stream())
-        return dqkv, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
 def rope_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int,
-             n_rot_heads: int, head_dim: int) -> torch.Tensor:
-    """Rotate the q and k heads of a fused ``[tokens, (Hq+2Hkv)*D]`` activation in place."""
+             n_rot_heads: int, head_dim: int, grad_inplace: bool = False) -> torch.Tensor:
+    """Rotate the q and k heads of a fused ``[tokens, (Hq+2Hkv)*D]`` activation in place.
+
+    ``grad_inplace=True`` lets backward rotate the incoming gradient in place as well; only
+    safe when the caller knows that gradient has a single consumer (true for the dqkv tensor
+    our attention backward allocates)."""
     if not qkv.is_cuda:
         return _rope_ref(qkv, cos, sin, seq_len, n_rot_heads, head_dim)
-    return _RoPE.apply(qkv, cos, sin, seq_len, n_rot_heads, head_dim)
+    return _RoPE.apply(qkv, cos, sin, seq_len, n_rot_heads, head_dim, grad_inplace)
 
 
 # -----------------------------------------------------------------------------

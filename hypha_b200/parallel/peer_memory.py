@@ -18,6 +18,7 @@ from typing import Callable, Dict, List, Optional, Sequence
 import torch
 
 from ..ops.native import load_C
+from ..telemetry.bandwidth import BandwidthCounters
 
 _DT_SIZE = {torch.bfloat16: 2, torch.float16: 2, torch.float32: 4, torch.uint8: 1, torch.int32: 4,
             torch.uint32: 4, torch.int64: 8}
@@ -53,22 +54,6 @@ class SymmetricBuffer:
     @property
     def nbytes(self) -> int:
         return self.numel * _DT_SIZE[self.dtype]
-
-
-class BandwidthCounters:
-    """hypha.bandwidth.{inbound,outbound}.bytes, keyed by protocol label."""
-
-    def __init__(self) -> None:
-        self.inbound: Dict[str, int] = {}
-        self.outbound: Dict[str, int] = {}
-
-    def add(self, protocol: str, inbound: int = 0, outbound: int = 0) -> None:
-        self.inbound[protocol] = self.inbound.get(protocol, 0) + int(inbound)
-        self.outbound[protocol] = self.outbound.get(protocol, 0) + int(outbound)
-
-    def snapshot(self) -> Dict[str, Dict[str, int]]:
-        return {"hypha.bandwidth.inbound.bytes": dict(self.inbound),
-                "hypha.bandwidth.outbound.bytes": dict(self.outbound)}
 
 
 class PeerGroup:

@@ -274,7 +274,7 @@ def test_fused_outer_step_single_rank(C):
         mom = g if rnd == 0 else 0.9 * mom_before + g
         th = th_before + 0.7 * (0.9 * mom + g)
         assert torch.allclose(outer.theta_outer, th, atol=1e-5, rtol=1e-5)
-        assert torch.equal(pbuf.local, th.to(torch.bfloat16))
+        assert torch.equal(pbuf.local, outer.theta_outer.to(torch.bfloat16))
         assert torch.equal(opt.master, pbuf.local.float())
         assert torch.equal(outer.anchor_buf.local, pbuf.local)
     grp.close()

@@ -1,0 +1,283 @@
+"""Multi-node-without-a-cluster tests of the control-plane fabric (model: the reference's
+crates/network/tests/{gossipsub,kad,request_response}_test.rs, 2-3 in-memory nodes per test)."""
+import asyncio
+import os
+import tempfile
+
+import pytest
+
+from hypha_b200.transport import (AlreadyRegistered, DialError, Network, NoHandler, PublishError,
+                                  RecordNotFound, RequestFailed)
+
+
+def run(coro):
+    return asyncio.run(asyncio.wait_for(coro, 20))
+
+
+async def pair(kind="memory", tmp=None):
+    a, b = Network("A"), Network("B")
+    if kind == "memory":
+        addr = await a.listen(f"memory://{id(a)}")
+    elif kind == "unix":
+        addr = await a.listen(f"unix://{tmp}/a.sock")
+    else:
+        addr = await a.listen("tcp://127.0.0.1:0")
+    assert await b.dial(addr) == "A"
+    for _ in range(50):
+        if "B" in a.links:
+            break
+        await asyncio.sleep(0.01)
+    return a, b
+
+
+@pytest.mark.parametrize("kind", ["memory", "unix", "tcp"])
+def test_request_response_roundtrip(kind):
+    async def main():
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = await pair(kind, tmp)
+
+            async def h(peer, msg):
+                return {"echo": msg["x"], "from": peer}
+
+            a.on("/hypha-api/0.0.1", None, h)
+            r = await b.request("A", "/hypha-api/0.0.1", {"x": 7})
+            assert r == {"echo": 7, "from": "B"}
+            assert b.counters.total()["hypha.bandwidth.outbound.bytes"] > 0
+            assert a.counters.snapshot()["hypha.bandwidth.inbound.bytes"].get("/hypha-api/0.0.1", 0) > 0
+            await a.close(); await b.close()
+    run(main())
+
+
+def test_multiple_handlers_with_patterns_first_match_wins():
+    async def main():
+        a, b = await pair()
+
+        async def h1(p, m):
+            return "one"
+
+        async def h2(p, m):
+            return "two"
+
+        async def h3(p, m):
+            return "any"
+
+        a.on("/p", lambda m: m.get("k") == 1, h1)
+        a.on("/p", lambda m: m.get("k") == 2, h2)
+        a.on("/p", lambda m: True, h3)
+        a.on("/p", lambda m: m.get("k") == 2, h1)         # duplicate pattern registered later: never wins
+        assert await b.request("A", "/p", {"k": 1}) == "one"
+        assert await b.request("A", "/p", {"k": 2}) == "two"
+        assert await b.request("A", "/p", {"k": 3}) == "any"
+        await a.close(); await b.close()
+    run(main())
+
+
+def test_handler_unregistration_and_no_handler():
+    async def main():
+        a, b = await pair()
+
+        async def h(p, m):
+            return "ok"
+
+        reg = a.on("/p", None, h)
+        assert await b.request("A", "/p", {}) == "ok"
+        reg.unregister()
+        with pytest.raises(NoHandler):
+            await b.request("A", "/p", {})
+        with pytest.raises(NoHandler):
+            await b.request("A", "/other", {})
+        await a.close(); await b.close()
+    run(main())
+
+
+def test_handler_exception_is_failed_request():
+    async def main():
+        a, b = await pair()
+
+        async def h(p, m):
+            raise ValueError("boom")
+
+        a.on("/p", None, h)
+        with pytest.raises(RequestFailed):
+            await b.request("A", "/p", {})
+        await a.close(); await b.close()
+    run(main())
+
+
+def test_request_after_disconnect():
+    """request_response_test.rs:744-792: peer goes away -> Err(Request)."""
+    async def main():
+        a, b = await pair()
+
+        async def h(p, m):
+            return 1
+
+        a.on("/p", None, h)
+        assert await b.request("A", "/p", {}) == 1
+        await a.close()
+        with pytest.raises(RequestFailed):
+            await b.request("A", "/p", {}, timeout=1.0)
+        await b.close()
+    run(main())
+
+
+def test_dial_errors():
+    async def main():
+        n = Network("X")
+        with pytest.raises(DialError):
+            await n.dial("memory://nobody")
+        with pytest.raises(DialError):
+            await n.dial("tcp://127.0.0.1:1", timeout=1.0)
+        await n.close()
+    run(main())
+
+
+def test_gossip_single_and_multiple_subscribers():
+    async def main():
+        hub = Network("hub", relay_server=True, dht_server=True)
+        addr = await hub.listen(f"memory://hub-{id(hub)}")
+        pub, s1, s2 = Network("pub"), Network("s1"), Network("s2")
+        for n in (pub, s1, s2):
+            await n.dial(addr)
+        sub1 = await s1.subscribe("hypha/worker")
+        sub2 = await s2.subscribe("hypha/worker")
+        await pub.publish("hypha/worker", b"hello")
+        assert await sub1.get(2) == ("pub", b"hello")
+        assert await sub2.get(2) == ("pub", b"hello")
+        # publisher does not hear itself; unsubscribed peers stop receiving
+        await sub2.unsubscribe()
+        await pub.publish("hypha/worker", b"again")
+        assert (await sub1.get(2))[1] == b"again"
+        assert sub2.q.empty()
+        for n in (hub, pub, s1, s2):
+            await n.close()
+    run(main())
+
+
+def test_isolated_peer_publish_fails():
+    async def main():
+        n = Network("lonely")
+        with pytest.raises(PublishError):
+            await n.publish("hypha/worker", b"x")
+        await n.close()
+    run(main())
+
+
+def test_store_and_get_record_and_providers():
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        gw.enable_dht_handlers()
+        addr = await gw.listen(f"memory://gw-{id(gw)}")
+        data, sched = Network("data"), Network("sched")
+        await data.dial(addr)
+        await sched.dial(addr)
+        await sched.wait_for_bootstrap(1.0)
+        await data.put_record("mnist", b'{"num_slices": 7}')
+        val, publisher = await sched.get_record("mnist")
+        assert val == b'{"num_slices": 7}' and publisher == "data"
+        with pytest.raises(RecordNotFound):
+            await sched.get_record("missing")
+        await data.provide("mnist")
+        lonely = Network("p2")
+        await lonely.dial(addr)
+        await lonely.provide("mnist")
+        assert await sched.find_providers("mnist") == ["data", "p2"]
+        assert set(gw.closest_peers("mnist")) == {"data", "sched", "p2"}
+        for n in (gw, data, sched, lonely):
+            await n.close()
+    run(main())
+
+
+def test_wait_for_bootstrap_times_out_without_gateway():
+    async def main():
+        n = Network("n")
+        with pytest.raises(asyncio.TimeoutError):
+            await n.wait_for_bootstrap(0.1)
+        await n.close()
+    run(main())
+
+
+def test_relay_through_gateway():
+    """Two peers that only know the gateway can still talk (relay server)."""
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        addr = await gw.listen(f"memory://gw-{id(gw)}")
+        a, b = Network("a"), Network("b")
+        await a.dial(addr)
+        await b.dial(addr)
+
+        async def h(p, m):
+            return {"hi": p}
+
+        b.on("/p", None, h)
+        assert await a.request("b", "/p", {}) == {"hi": "a"}
+        await a.ping("b")
+        for n in (gw, a, b):
+            await n.close()
+    run(main())
+
+
+def test_direct_dial_via_gateway_peer_table():
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        gaddr = await gw.listen(f"memory://gw-{id(gw)}")
+        b = Network("b")
+        await b.listen(f"memory://b-{id(b)}")
+        await b.dial(gaddr)
+        a = Network("a")
+        await a.dial(gaddr)          # learns b's address from the gateway's hello
+
+        async def h(p, m):
+            return "direct"
+
+        b.on("/p", None, h)
+        assert await a.request("b", "/p", {}) == "direct"
+        assert "b" in a.links        # a direct link was established
+        for n in (gw, a, b):
+            await n.close()
+    run(main())
+
+
+@pytest.mark.parametrize("kind", ["memory", "tcp"])
+def test_push_stream_and_already_registered(kind):
+    async def main():
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = await pair(kind, tmp)
+            rx = a.streams_push()
+            with pytest.raises(AlreadyRegistered):
+                a.streams_push()
+            rx_job = a.streams_push(job_id="job-1")          # per-job receivers may coexist (Q15)
+            payload = os.urandom(3 * (1 << 20) + 17)
+            src = os.path.join(tmp, "src.bin")
+            open(src, "wb").write(payload)
+            t = asyncio.ensure_future(b.stream_push("A", src))
+            st = await rx.get()
+            dst = os.path.join(tmp, "dst.bin")
+            n = await st.save(dst)
+            assert await t == len(payload) == n and open(dst, "rb").read() == payload
+            assert oct(os.stat(dst).st_mode & 0o777) == "0o600" and st.peer == "B"
+            t = asyncio.ensure_future(b.stream_push("A", b"tiny", job_id="job-1"))
+            st2 = await rx_job.get()
+            assert await st2.read_all() == b"tiny" and st2.job_id == "job-1"
+            await t
+            await a.close(); await b.close()
+    run(main())
+
+
+def test_pull_stream():
+    async def main():
+        a, b = await pair()
+        blobs = {0: b"slice-zero" * 1000, 1: b"slice-one"}
+
+        async def serve(peer, header):
+            return blobs[header["index"]]
+
+        a.serve_pull(serve)
+        with pytest.raises(AlreadyRegistered):
+            a.serve_pull(serve)
+        st = await b.stream_pull("A", {"dataset": "d", "index": 0})
+        assert await st.read_all() == blobs[0]
+        st = await b.stream_pull("A", {"dataset": "d", "index": 1})
+        assert await st.read_all() == blobs[1]
+        await a.close(); await b.close()
+    run(main())
