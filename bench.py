@@ -13,6 +13,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+os.environ.setdefault("PYTORCH_CUDA_ALLOC_CONF", "expandable_segments:True")
 import statistics
 import subprocess
 import sys
@@ -38,6 +40,7 @@ def parse_args():
     ap.add_argument("--state-dtype", default=os.environ.get("HYPHA_BENCH_STATE", "bf16"))
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2"])
     return ap.parse_args()
 
 
@@ -135,6 +138,7 @@ def main():
     from hypha_b200.parallel.peer_memory import PeerGroup
     from hypha_b200.trainer import DiLoCoTrainer
 
+    ops.set_attention_backend(args.attn)
     if args.impl == "baseline":
         ops.set_gemm_backend("cublas")
     cfg = get_config(args.model)
@@ -236,6 +240,7 @@ def main():
                 "outer_backend": trainer.outer.backend,
                 "optimizer": f"fused flat AdamW, fp32 master, {args.state_dtype} moments",
                 "recompute_layers": recompute, "gemm_backend": ops.get_gemm_backend(),
+                "attention_backend": ops.get_attention_backend(),
                 "l2": "no flush needed: >16 GB of weights/activations streamed per step >> 126 MB L2",
             },
             "model_tflops_per_gpu": value / world * cfg.flops_per_token(S) / 1e12,

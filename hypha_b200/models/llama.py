@@ -125,30 +125,33 @@ class FlatParams:
             yield name, self.view(name)
 
 
-def _ckpt_run(fn, a, b):
-    return fn(a, b)
-
-
 class _CheckpointPair(torch.autograd.Function):
-    """Recompute-in-backward for a ``(delta, residual) -> (delta, residual)`` layer."""
+    """Recompute-in-backward for a ``(delta, residual) -> (delta, residual)`` layer
+    (``residual`` may be ``None`` for the first layer)."""
 
     @staticmethod
     def forward(ctx, fn, delta, residual):
         ctx.fn = fn
-        ctx.save_for_backward(delta, residual)
+        ctx.has_res = residual is not None
+        if ctx.has_res:
+            ctx.save_for_backward(delta, residual)
+        else:
+            ctx.save_for_backward(delta)
         with torch.no_grad():
             d, r = fn(delta, residual)
+        if r is delta:          # first layer: the residual stream IS the input; never alias outputs
+            r = r.clone()
         return d, r
 
     @staticmethod
     def backward(ctx, dd, dr):
-        delta, residual = ctx.saved_tensors
-        delta = delta.detach().requires_grad_(True)
-        residual = residual.detach().requires_grad_(True)
+        saved = ctx.saved_tensors
+        delta = saved[0].detach().requires_grad_(True)
+        residual = saved[1].detach().requires_grad_(True) if ctx.has_res else None
         with torch.enable_grad():
             d, r = ctx.fn(delta, residual)
             torch.autograd.backward([d, r], [dd, dr])
-        return None, delta.grad, residual.grad
+        return None, delta.grad, (residual.grad if ctx.has_res else None)
 
 
 class LlamaBlock(nn.Module):
@@ -160,15 +163,12 @@ class LlamaBlock(nn.Module):
 
     def forward(self, delta, residual, cos, sin, batch: int, seq: int):
         c = self.cfg
-        n1, res = ops.add_rmsnorm(delta, residual, self.norm1, c.rms_eps)
-        qkv = ops.linear(n1, self.wqkv)
+        qkv, res = ops.add_norm_linear(delta, residual, self.norm1, self.wqkv, c.rms_eps)
         qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim, grad_inplace=True)
         att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
         o = ops.linear(att, self.wo)
-        n2, res = ops.add_rmsnorm(o, res, self.norm2, c.rms_eps)
-        gu = ops.linear(n2, self.wgu)
-        act = ops.swiglu(gu)
-        down = ops.linear(act, self.wdown)
+        gu, res = ops.add_norm_linear(o, res, self.norm2, self.wgu, c.rms_eps)
+        down = ops.swiglu_linear(gu, self.wdown)
         return down, res
 
 
@@ -244,7 +244,7 @@ class LlamaForCausalLM(nn.Module):
         cos, sin = self._rope(seq, input_ids.device)
         P = self._params
         delta = ops.embedding(input_ids, P["embed"])
-        residual = torch.zeros_like(delta)
+        residual = None
         for l, blk in enumerate(self.blocks):
             if l < cfg.recompute_layers and torch.is_grad_enabled():
                 fn = lambda d, r, blk=blk: blk(d, r, cos, sin, batch, seq)

@@ -230,6 +230,129 @@ def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor,
     return _AddRMSNorm.apply(x, residual, weight, eps)
 
 
+def _norm_linear_fwd(x, residual, norm_w, weight, eps):
+    C = load_C()
+    rows, cols = x.shape
+    n = torch.empty_like(x)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    if residual is not None:
+        h = torch.empty_like(x)
+        C.rmsnorm_fwd(x.data_ptr(), residual.data_ptr(), h.data_ptr(), norm_w.data_ptr(), n.data_ptr(),
+                      rstd.data_ptr(), rows, cols, eps, cuda_stream())
+    else:
+        h = x
+        C.rmsnorm_fwd(x.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), rstd.data_ptr(), rows, cols, eps,
+                      cuda_stream())
+    return gemm(n, weight), h, rstd
+
+
+def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
+    C = load_C()
+    rows, cols = h.shape
+    s = cuda_stream()
+    n = torch.empty_like(h)
+    C.rmsnorm_fwd(h.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), 0, rows, cols, eps, s)
+    dy2 = dy if dy.is_contiguous() else dy.contiguous()
+    _wgrad_into(weight, dy2, n)
+    dn = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=n)            # reuse the buffer
+    dx = torch.empty_like(h)
+    nparts = C.rmsnorm_bwd_num_partials(rows)
+    partial = torch.empty((nparts, cols), dtype=torch.float32, device=h.device)
+    dh2 = None
+    if dh is not None:
+        dh2 = dh if dh.is_contiguous() else dh.contiguous()
+    C.rmsnorm_bwd(dn.data_ptr(), h.data_ptr(), norm_w.data_ptr(), rstd.data_ptr(), _ptr(dh2), dx.data_ptr(),
+                  partial.data_ptr(), rows, cols, s)
+    return dx, _norm_wgrad(norm_w, partial, nparts, cols)
+
+
+class _AddNormLinear(torch.autograd.Function):
+    """``h = x + residual; y = rmsnorm(h) @ W^T`` saving only ``h`` and ``rstd``.
+
+    The normalised activation (the GEMM's A operand) is NOT kept: backward re-derives it with one
+    extra rmsnorm_fwd launch (memory-bound, ~60 us) instead of holding ``tokens x hidden`` bf16 per
+    norm per layer.  Returns ``(y, h)``."""
+
+    @staticmethod
+    def forward(ctx, x, residual, norm_w, weight, eps):
+        y, h, rstd = _norm_linear_fwd(x, residual, norm_w, weight, eps)
+        ctx.save_for_backward(h, rstd, norm_w, weight)
+        ctx.eps = eps
+        return y, h
+
+    @staticmethod
+    def backward(ctx, dy, dh):
+        h, rstd, norm_w, weight = ctx.saved_tensors
+        dx, dnw = _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, ctx.eps)
+        return dx, dx, dnw, None, None
+
+
+class _NormLinear(torch.autograd.Function):
+    """``y = rmsnorm(x) @ W^T`` (no residual input); same recompute policy as ``_AddNormLinear``."""
+
+    @staticmethod
+    def forward(ctx, x, norm_w, weight, eps):
+        y, _, rstd = _norm_linear_fwd(x, None, norm_w, weight, eps)
+        ctx.save_for_backward(x, rstd, norm_w, weight)
+        ctx.eps = eps
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, rstd, norm_w, weight = ctx.saved_tensors
+        dx, dnw = _norm_linear_bwd(dy, None, x, rstd, norm_w, weight, ctx.eps)
+        return dx, dnw, None, None
+
+
+def add_norm_linear(x: torch.Tensor, residual: Optional[torch.Tensor], norm_w: torch.Tensor,
+                    weight: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``h = x + residual`` (or ``x``), ``y = rmsnorm(h) * norm_w @ weight.T``; returns ``(y, h)``."""
+    if not x.is_cuda:
+        h = x if residual is None else (x.float() + residual.float()).to(x.dtype)
+        return F.linear(_rmsnorm_ref(h, norm_w, eps), weight), h
+    assert x.dim() == 2 and x.is_contiguous()
+    if residual is None:
+        return _NormLinear.apply(x, norm_w, weight, eps), x
+    return _AddNormLinear.apply(x, residual, norm_w, weight, eps)
+
+
+class _SwiGLULinear(torch.autograd.Function):
+    """``y = (silu(g) * u) @ W^T`` on a fused gate|up activation, saving only ``gu``."""
+
+    @staticmethod
+    def forward(ctx, gu, weight):
+        rows, two_i = gu.shape
+        act = torch.empty((rows, two_i // 2), dtype=gu.dtype, device=gu.device)
+        load_C().swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, two_i // 2, cuda_stream())
+        y = gemm(act, weight)
+        ctx.save_for_backward(gu, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C = load_C()
+        gu, weight = ctx.saved_tensors
+        rows, two_i = gu.shape
+        inter = two_i // 2
+        s = cuda_stream()
+        act = torch.empty((rows, inter), dtype=gu.dtype, device=gu.device)
+        C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, inter, s)
+        dy2 = dy if dy.is_contiguous() else dy.contiguous()
+        _wgrad_into(weight, dy2, act)
+        dact = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=act)
+        dgu = torch.empty_like(gu)
+        C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
+        return dgu, None
+
+
+def swiglu_linear(gu: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """``(silu(gate) * up) @ weight.T`` with the activation recomputed in backward."""
+    if not gu.is_cuda:
+        return F.linear(swiglu(gu), weight)
+    assert gu.dim() == 2 and gu.is_contiguous()
+    return _SwiGLULinear.apply(gu, weight)
+
+
 # -----------------------------------------------------------------------------
 # RoPE
 # -----------------------------------------------------------------------------
@@ -369,11 +492,41 @@ class _FlashAttnQKV(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+_ATTN_BACKEND = os.environ.get("HYPHA_ATTN", "cudnn")
+
+
+def set_attention_backend(name: str) -> None:
+    """``cudnn`` (cuDNN fused attention through torch SDPA; library), ``flash2`` (flash-attn 2
+    mma.sync kernels; library) -- the hand-written tcgen05 attention replaces both."""
+    global _ATTN_BACKEND
+    if name not in ("cudnn", "flash2"):
+        raise ValueError(name)
+    _ATTN_BACKEND = name
+
+
+def get_attention_backend() -> str:
+    return _ATTN_BACKEND
+
+
+def _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim):
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    T = batch * seq
+    q = qkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim).transpose(1, 2)
+    k = qkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim).transpose(1, 2)
+    v = qkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim).transpose(1, 2)
+    with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION]):
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(n_kv != n_heads))
+    return o.transpose(1, 2).reshape(T, n_heads * head_dim)
+
+
 def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int,
                   head_dim: int) -> torch.Tensor:
     """Causal self-attention on a fused (already RoPE'd) qkv activation -> ``[tokens, Hq*D]``."""
     if not qkv.is_cuda:
         return _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim)
+    if _ATTN_BACKEND == "cudnn":
+        return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)
     return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
 
 

@@ -1,0 +1,316 @@
+"""The four long-running roles -- gateway, data node, worker, scheduler -- as asyncio programs.
+
+Reference main flows: crates/gateway/src/bin/hypha-gateway.rs:36-164,
+crates/data/src/bin/hypha-data.rs:33-233, crates/worker/src/bin/hypha-worker.rs:42-283,
+crates/scheduler/src/bin/hypha-scheduler.rs:54-432.  Common start-up sequence for every role:
+telemetry -> Network -> listen -> external addresses -> dial gateways -> DHT bootstrap ->
+health handler -> role logic -> graceful shutdown.
+
+Roles run either all in one process over ``memory://`` links (the north-star layout: the 8 GPUs
+of a box are the workers) or as separate processes over ``unix://`` / ``tcp://``.
+"""
+from __future__ import annotations
+
+import asyncio
+import json
+import math
+import os
+import time
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional
+
+from . import config as C
+from . import messages as M
+from .scheduler import (AimConnector, BatchSchedulerService, Connector as MetricsConnector, DataSchedulerService,
+                        GreedyWorkerAllocator, JsonlConnector, MetricsBridge, NoOpConnector, Task, WorkerHandle)
+from .telemetry import Telemetry
+from .transport import Network, NetworkError, RecordNotFound
+from .worker import Arbiter, Connector, JobManager
+
+ALLOCATION_PAUSE_S = 1.0          # hypha-scheduler.rs:241 (let losers' tentative leases expire)
+
+
+class RoleError(Exception):
+    pass
+
+
+@dataclass
+class Node:
+    """Started network + telemetry of one role."""
+
+    name: str
+    network: Network
+    telemetry: Telemetry
+    ready: asyncio.Event = field(default_factory=asyncio.Event)
+    stop: asyncio.Event = field(default_factory=asyncio.Event)
+
+    @property
+    def peer_id(self) -> str:
+        return self.network.peer_id
+
+    async def shutdown(self) -> None:
+        self.stop.set()
+        await self.network.close()
+        self.telemetry.shutdown()
+
+
+async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, relay_server: bool = False,
+                     dht_server: bool = False, need_bootstrap: bool = True) -> Node:
+    tel = Telemetry.from_config(f"hypha-{role}", cfg)
+    C.load_tls(cfg)                         # accepted for parity; loopback links do not use mTLS
+    net = Network(peer_id or f"{role}-{M.new_id()[:8]}", agent=f"hypha-{role}", relay_server=relay_server,
+                  dht_server=dht_server)
+    tel.register_bandwidth(net.counters)
+    node = Node(role, net, tel)
+    net.enable_dht_handlers()
+    for addr in cfg.listen_addresses:
+        await net.listen(addr)
+    for addr in getattr(cfg, "external_addresses", []) or []:
+        net.add_external_address(addr)
+
+    async def health(peer, msg):            # /hypha-health/0.0.1: healthy == ready
+        return M.HealthResponse(node.ready.is_set())
+
+    net.on(M.HEALTH_PROTOCOL, None, health)
+    gateways = getattr(cfg, "gateway_addresses", []) or []
+    dialed = 0
+    for addr in gateways:
+        try:
+            await net.dial(addr)
+            dialed += 1
+        except NetworkError as exc:
+            tel.logger.warning("dial gateway %s failed: %s", addr, exc)
+    if gateways and dialed == 0:
+        raise RoleError(f"{role}: none of the gateways {gateways} could be dialed")
+    if need_bootstrap and gateways:
+        await net.wait_for_bootstrap(10.0)
+    return node
+
+
+async def probe(addr: str, timeout: float = 5.0) -> bool:
+    """``probe <addr>``: dial, send ``health::Request``, true iff healthy
+    (hypha-scheduler.rs:494-535)."""
+    net = Network(f"probe-{M.new_id()[:8]}")
+    try:
+        peer = await net.dial(addr, timeout=timeout)
+        resp = await net.request(peer, M.HEALTH_PROTOCOL, M.HealthRequest(), timeout=timeout)
+        return bool(M.HealthResponse.from_wire(resp).healthy)
+    except NetworkError:
+        return False
+    finally:
+        await net.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# gateway
+# ---------------------------------------------------------------------------------------------
+async def run_gateway(cfg: C.GatewayConfig, *, peer_id: Optional[str] = None,
+                      started: Optional[asyncio.Future] = None) -> None:
+    node = await start_node("gateway", cfg, peer_id=peer_id, relay_server=True, dht_server=True,
+                            need_bootstrap=False)
+    node.ready.set()                        # gateway readiness == listening (hypha-gateway.rs:78,121)
+    node.telemetry.logger.info("gateway %s listening on %s", node.peer_id, node.network.listen_addrs)
+    if started is not None and not started.done():
+        started.set_result(node)
+    try:
+        await node.stop.wait()
+    finally:
+        await node.shutdown()
+
+
+# ---------------------------------------------------------------------------------------------
+# data node
+# ---------------------------------------------------------------------------------------------
+def dataset_files(path: str) -> List[str]:
+    """Slices of a dataset directory in SORTED order (the reference indexes ``read_dir()`` order,
+    which is unspecified: quirk Q5)."""
+    return sorted(os.path.join(path, f) for f in os.listdir(path) if os.path.isfile(os.path.join(path, f)))
+
+
+async def run_data(cfg: C.DataConfig, *, peer_id: Optional[str] = None,
+                   started: Optional[asyncio.Future] = None) -> None:
+    C.validate(cfg)
+    node = await start_node("data", cfg, peer_id=peer_id)
+    name = os.path.basename(os.path.normpath(cfg.dataset_path))
+    files = dataset_files(cfg.dataset_path)
+    if not files:
+        raise RoleError(f"dataset directory {cfg.dataset_path} is empty")
+
+    async def serve(peer: str, header: Any):
+        sl = M.DataSlice.from_wire(header)
+        if sl.dataset != name:
+            raise RoleError(f"unknown dataset {sl.dataset!r}")
+        if not (0 <= sl.index < len(files)):            # correct bounds (reference uses `>`: Q5)
+            raise RoleError(f"slice {sl.index} out of range 0..{len(files) - 1}")
+        return files[sl.index]
+
+    node.network.serve_pull(serve)
+    await node.network.put_record(name, json.dumps(M.DataRecord(len(files)).to_wire()).encode())
+    await node.network.provide(name)
+    node.ready.set()
+    node.telemetry.logger.info("data node %s announces %s (%d slices)", node.peer_id, name, len(files))
+    if started is not None and not started.done():
+        started.set_result(node)
+    try:
+        await node.stop.wait()
+    finally:
+        await node.shutdown()
+
+
+# ---------------------------------------------------------------------------------------------
+# worker
+# ---------------------------------------------------------------------------------------------
+async def run_worker(cfg: C.WorkerConfig, *, peer_id: Optional[str] = None,
+                     started: Optional[asyncio.Future] = None, log: Callable[[str], None] = print) -> None:
+    C.validate(cfg)
+    node = await start_node("worker", cfg, peer_id=peer_id)
+    net = node.network
+    connector = Connector(net)
+    jobs = JobManager(connector, net, cfg.work_dir, cfg.executors, log=log)
+    cap = M.Resources(gpu=cfg.resources.gpu, cpu=cfg.resources.cpu, storage=cfg.resources.storage,
+                      memory=cfg.resources.memory)
+    arbiter = Arbiter(net, cap, jobs, price=cfg.offer.price, floor=cfg.offer.floor,
+                      strategy=cfg.offer.strategy.type, log=log)
+    node.arbiter = arbiter  # type: ignore[attr-defined]
+    node.jobs = jobs  # type: ignore[attr-defined]
+    node.ready.set()                         # listening + bootstrapped (hypha-worker.rs:84-87,200)
+    if started is not None and not started.done():
+        started.set_result(node)
+    try:
+        await arbiter.run(node.stop)
+    finally:
+        await jobs.shutdown()
+        await node.shutdown()
+
+
+# ---------------------------------------------------------------------------------------------
+# scheduler
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class JobOutcome:
+    job_id: str
+    rounds: int
+    workers: List[str]
+    parameter_server: str
+    metrics: List[Dict[str, Any]]
+    finished: bool
+
+
+def worker_batch_size(offered_gpu: float, required_gpu: float, max_batch: Optional[int]) -> int:
+    """``floor(offered.gpu / required.gpu).min(max_batch_size)`` (hypha-scheduler.rs:320-322)."""
+    bs = int(math.floor(offered_gpu / required_gpu)) if required_gpu > 0 else 1
+    bs = max(bs, 1)
+    return min(bs, max_batch) if max_batch else bs
+
+
+async def get_data_provider(net: Network, dataset: str, retries: int = 20) -> tuple:
+    for _ in range(retries):
+        try:
+            value, publisher = await net.get_record(dataset)
+            return publisher, M.DataRecord.from_wire(json.loads(value))
+        except RecordNotFound:
+            await asyncio.sleep(0.25)
+    raise RoleError(f"dataset {dataset!r} is not announced by any data node")
+
+
+async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None,
+                        started: Optional[asyncio.Future] = None,
+                        metrics_connector: Optional[MetricsConnector] = None,
+                        allocation_pause_s: float = ALLOCATION_PAUSE_S) -> JobOutcome:
+    C.validate(cfg)
+    node = await start_node("scheduler", cfg, peer_id=peer_id)
+    net, log = node.network, node.telemetry.logger
+    job = cfg.scheduler.job
+    res = job.resources
+    node.ready.set()
+    if started is not None and not started.done():
+        started.set_result(node)
+    handles: List[WorkerHandle] = []
+    services: List[Any] = []
+    tasks: List[Task] = []
+    try:
+        allocator = GreedyWorkerAllocator(net)
+        to_res = lambda r: M.Resources(gpu=r.gpu, cpu=r.cpu, storage=r.storage, memory=r.memory)
+        wspec = M.WorkerSpec(to_res(res.worker), [M.ExecutorDescriptor("train", M.TRAIN_EXECUTOR_NAME)])
+        with node.telemetry.span("allocate.workers", num=res.num_workers):
+            workers = await allocator.request(wspec, res.worker_price.bid, res.worker_price.max, res.num_workers)
+        handles += workers
+        await asyncio.sleep(allocation_pause_s)
+        pspec = M.WorkerSpec(to_res(res.parameter_server), [M.ExecutorDescriptor("aggregate", M.AGGREGATE_EXECUTOR_NAME)])
+        with node.telemetry.span("allocate.parameter_server"):
+            ps_list = await allocator.request(pspec, res.parameter_server_price.bid, res.parameter_server_price.max, 1)
+        handles += ps_list
+        if len(workers) < res.num_workers or not ps_list:
+            raise RoleError(f"allocation incomplete: {len(workers)}/{res.num_workers} workers, {len(ps_list)} PS")
+        ps = ps_list[0]
+        provider, record = await get_data_provider(net, job.dataset.dataset)
+        data_svc = DataSchedulerService(net, job.dataset.dataset, provider, record.num_slices)
+        data_svc.start()
+        services.append(data_svc)
+
+        job_id = M.new_id()
+        batch = BatchSchedulerService(net, job_id, ps.peer_id, job.rounds.avg_samples_between_updates,
+                                      job.rounds.update_rounds)
+        batch.start()
+        services.append(batch)
+        worker_ids = [w.peer_id for w in workers]
+        model = M.Model(job.model.type, M.Fetch.huggingface(job.model.repository, job.model.revision,
+                                                            job.model.filenames, job.model.token),
+                        list(job.model.input_names))
+        pre = None
+        if job.preprocessor is not None:
+            p = job.preprocessor
+            pre = M.Preprocessor(p.type, M.Fetch.huggingface(p.repository, p.revision, p.filenames, p.token),
+                                 list(p.input_names))
+        adam = M.Adam(job.inner_optimizer.learning_rate,
+                      tuple(job.inner_optimizer.betas) if job.inner_optimizer.betas else None,
+                      job.inner_optimizer.epsilon)
+        for w in workers:
+            bs = worker_batch_size(w.resources.gpu, res.worker.gpu, job.rounds.max_batch_size)
+            batch.add_worker(w.peer_id, bs)
+            tcfg = M.TrainExecutorConfig(model=model, data=M.Fetch.scheduler(net.peer_id, job.dataset.dataset),
+                                         updates=M.Send.to_peers([ps.peer_id]), results=M.Receive.from_peers([ps.peer_id]),
+                                         optimizer=adam, batch_size=bs, preprocessor=pre)
+            spec = M.JobSpec(job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))
+            tasks.append(await Task.try_new(net, spec, [w]))
+        acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(worker_ids), results=M.Send.to_peers(worker_ids),
+                                         optimizer=M.Nesterov(job.outer_optimizer.learning_rate,
+                                                              job.outer_optimizer.momentum))
+        tasks.append(await Task.try_new(net, M.JobSpec(job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg)), [ps]))
+
+        collected: List[Dict[str, Any]] = []
+
+        class _Tee(MetricsConnector):
+            def __init__(self, inner):
+                self.inner = inner
+
+            async def send(self, worker_id, round, name, value):
+                collected.append({"worker_id": worker_id, "round": round, "metric_name": name, "value": value})
+                await self.inner.send(worker_id, round, name, value)
+
+        sink = metrics_connector or (AimConnector(cfg.status_bridge) if cfg.status_bridge else NoOpConnector())
+        bridge = MetricsBridge(_Tee(sink))
+        bridge.register_stream(batch.metrics)
+        bridge_task = asyncio.ensure_future(bridge.run())
+
+        # wait: job done | any lease lost | stop requested (hypha-scheduler.rs:396-412)
+        waiters = {asyncio.ensure_future(batch.done.wait()): "done", asyncio.ensure_future(node.stop.wait()): "stop"}
+        for h in handles:
+            if h.task is not None:
+                waiters[h.task] = f"lease:{h.peer_id}"
+        done, _ = await asyncio.wait(waiters.keys(), return_when=asyncio.FIRST_COMPLETED)
+        reason = waiters[next(iter(done))]
+        finished = batch.done.is_set()
+        if not finished:
+            log.warning("scheduler stopping before completion: %s", reason)
+        await asyncio.sleep(0.05)              # let the last metrics drain
+        bridge_task.cancel()
+        return JobOutcome(job_id, batch.round, worker_ids, ps.peer_id, collected, finished)
+    finally:
+        for t in tasks:
+            t.close()
+        for s in services:
+            s.stop()
+        for h in handles:
+            await h.release()
+        await node.shutdown()

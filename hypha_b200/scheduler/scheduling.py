@@ -1,0 +1,173 @@
+"""Batch scheduler (progress state machine), data scheduler (slice hand-out), metrics bridge.
+
+Reference: crates/scheduler/src/scheduling/batch_scheduler.rs:54-220,
+crates/scheduler/src/scheduling/data_scheduler.rs:28-103, crates/scheduler/src/metrics_bridge.rs:18-146.
+The state machine, the sync-point simulation and the slice tracker are the C++ core; these
+classes bind them to the request/response fabric.
+"""
+from __future__ import annotations
+
+import asyncio
+import json
+import time
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+from .. import messages as M
+from ..ops.native import load_core
+from ..transport import Network
+
+
+def _now_ms(t0: float) -> int:
+    return int((time.monotonic() - t0) * 1000)
+
+
+class BatchSchedulerService:
+    """Serves ``/hypha-progress/0.0.1`` for one job.
+
+    ``metrics`` receives ``(peer, Progress(kind='metrics'))``; ``done`` is set when every worker
+    acknowledged the final update (batch_scheduler.rs:140-161)."""
+
+    def __init__(self, network: Network, job_id: str, parameter_server: str, update_target: int,
+                 update_rounds: int, time_cap_ms: int = 10000, update_cap: int = 3):
+        self.core = load_core()
+        self.network, self.job_id = network, job_id
+        self._t0 = time.monotonic()
+        tracker = self.core.ProgressTracker(parameter_server, update_target, update_rounds, 0)
+        self.sched = self.core.BatchScheduler(tracker, time_cap_ms, update_cap)
+        self.metrics: asyncio.Queue = asyncio.Queue(256)
+        self.done = asyncio.Event()
+        self._lock = asyncio.Lock()
+        self._reg = None
+        self._kinds = {"status": self.core.ProgressKind.Status, "metrics": self.core.ProgressKind.Metrics,
+                       "update": self.core.ProgressKind.Update, "updated": self.core.ProgressKind.Updated,
+                       "update-received": self.core.ProgressKind.UpdateReceived}
+        self._resp = {self.core.ResponseKind.Ok: "Ok", self.core.ResponseKind.Continue: "Continue",
+                      self.core.ResponseKind.ScheduleUpdate: "ScheduleUpdate", self.core.ResponseKind.Done: "Done",
+                      self.core.ResponseKind.Error: "Error"}
+
+    def add_worker(self, peer: str, batch_size: int) -> None:
+        self.sched.tracker.worker_tracker.add_worker(peer, batch_size)
+
+    def remove_worker(self, peer: str) -> None:
+        self.sched.tracker.worker_tracker.remove_worker(peer)
+
+    @property
+    def round(self) -> int:
+        return self.sched.tracker.round()
+
+    async def handle(self, peer: str, progress: M.Progress) -> M.ProgressResponse:
+        async with self._lock:
+            if progress.kind == "metrics":
+                if self.metrics.full():
+                    self.metrics.get_nowait()
+                self.metrics.put_nowait((peer, progress))
+            r = self.sched.handle(peer, self._kinds[progress.kind], progress.batch_size, _now_ms(self._t0))
+            if r.all_done:
+                self.done.set()
+            return M.ProgressResponse(self._resp[r.kind], r.counter)
+
+    def start(self) -> None:
+        async def serve(peer, msg):
+            req = M.ProgressRequest.from_wire(msg)
+            return await self.handle(peer, req.progress)
+
+        self._reg = self.network.on(M.PROGRESS_PROTOCOL,
+                                    lambda m: isinstance(m, dict) and str(m.get("job_id")) == self.job_id, serve)
+
+    def stop(self) -> None:
+        if self._reg is not None:
+            self._reg.unregister()
+            self._reg = None
+
+
+class DataSchedulerService:
+    """Answers ``api::Request::Data{dataset}`` with ``(data_provider, slice index)``."""
+
+    def __init__(self, network: Network, dataset: str, data_provider: str, num_slices: int):
+        self.network, self.dataset, self.data_provider = network, dataset, data_provider
+        self.tracker = load_core().SliceTracker(num_slices)
+        self._reg = None
+
+    def start(self) -> None:
+        async def serve(peer, msg):
+            ds = msg["Data"]["dataset"]
+            if ds != self.dataset:
+                return M.ApiResponse.data_not_found()
+            return M.ApiResponse.data_success(self.data_provider, self.tracker.next(peer))
+
+        self._reg = self.network.on(M.API_PROTOCOL, lambda m: isinstance(m, dict) and "Data" in m, serve)
+
+    def remove_worker(self, peer: str) -> None:
+        self.tracker.remove_worker(peer)
+
+    def stop(self) -> None:
+        if self._reg is not None:
+            self._reg.unregister()
+            self._reg = None
+
+
+# -- metrics bridge -------------------------------------------------------------------------------
+class Connector:
+    async def send(self, worker_id: str, round: int, name: str, value: float) -> None:
+        raise NotImplementedError
+
+
+class NoOpConnector(Connector):
+    async def send(self, worker_id, round, name, value) -> None:
+        return None
+
+
+class MemoryConnector(Connector):
+    def __init__(self) -> None:
+        self.records: List[Dict[str, Any]] = []
+
+    async def send(self, worker_id, round, name, value) -> None:
+        self.records.append({"worker_id": worker_id, "round": round, "metric_name": name, "value": value})
+
+
+class JsonlConnector(Connector):
+    def __init__(self, path: str):
+        self.path = path
+
+    async def send(self, worker_id, round, name, value) -> None:
+        with open(self.path, "a") as f:
+            f.write(json.dumps({"worker_id": worker_id, "round": round, "metric_name": name, "value": value}) + "\n")
+
+
+class AimConnector(Connector):
+    """POST one JSON ``AimMetrics`` per metric to ``http://<status_bridge>/status``
+    (metrics_bridge.rs:18-24,126-145)."""
+
+    def __init__(self, status_bridge: str):
+        self.url = f"http://{status_bridge}/status"
+
+    async def send(self, worker_id, round, name, value) -> None:
+        import aiohttp
+
+        async with aiohttp.ClientSession() as s:
+            async with s.post(self.url, json={"worker_id": worker_id, "round": round, "metric_name": name,
+                                              "value": value}) as r:
+                r.raise_for_status()
+
+
+class MetricsBridge:
+    """Fan-in of ``(peer, Metrics)`` queues -> a connector."""
+
+    def __init__(self, connector: Connector):
+        self.connector = connector
+        self._queues: List[asyncio.Queue] = []
+
+    def register_stream(self, q: asyncio.Queue) -> None:
+        self._queues.append(q)
+
+    async def run(self) -> None:
+        async def pump(q: asyncio.Queue):
+            while True:
+                peer, progress = await q.get()
+                for name, value in progress.metrics.items():
+                    try:
+                        await self.connector.send(peer, progress.round, name, float(value))
+                    except Exception:      # a broken sink must not stop training
+                        pass
+
+        await asyncio.gather(*(pump(q) for q in self._queues))

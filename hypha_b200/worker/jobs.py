@@ -1,0 +1,330 @@
+"""Job execution on a worker: JobManager, the process executor, the parameter-server executor.
+
+Reference: crates/worker/src/job_manager.rs:36-211, crates/worker/src/executor/process.rs:77-205
+(work dir ``hypha-{uuid}``, ``bridge.sock``, placeholder substitution, SIGTERM -> 5 s -> SIGKILL,
+cleanup), crates/worker/src/executor/parameter_server.rs:73-446 (receive N updates, average,
+Nesterov, broadcast, ``Updated``).
+
+Differences by design: the parameter server takes a TRUE mean over the N updates (the reference's
+pairwise running average is only right for N=2), has a receive timeout with
+membership shrink instead of waiting forever (quirk Q8), and jobs are keyed by lease id (quirk
+Q7).  On an NVSwitch box the aggregate role is normally subsumed by the fused peer-memory outer
+step (hypha_b200/parallel/diloco.py); this executor keeps the file-based path for the CPU
+plumbing configuration and for API parity.
+"""
+from __future__ import annotations
+
+import asyncio
+import hashlib
+import json
+import os
+import shutil
+import signal
+import sys
+import uuid
+from dataclasses import dataclass, field
+from typing import Any, Callable, Dict, List, Optional
+
+from .. import messages as M
+from ..transport import Network, NetworkError
+from .bridge import Bridge, Connector
+
+KILL_GRACE_S = 5.0
+
+
+def substitute_placeholders(args: List[str], socket_path: str, work_dir: str, job_json: str) -> List[str]:
+    """``{SOCKET_PATH}`` / ``{WORK_DIR}`` / ``{JOB_JSON}`` (process.rs:201-205)."""
+    out = []
+    for a in args:
+        out.append(a.replace("{SOCKET_PATH}", socket_path).replace("{WORK_DIR}", work_dir)
+                   .replace("{JOB_JSON}", job_json))
+    return out
+
+
+class Execution:
+    """A running job: ``wait()`` for the exit status, ``cancel()`` to stop it."""
+
+    def __init__(self) -> None:
+        self.done = asyncio.Event()
+        self.status = M.JobStatus.RUNNING
+        self._cancel = asyncio.Event()
+
+    def cancel(self) -> None:
+        self._cancel.set()
+
+    async def wait(self) -> M.JobStatus:
+        await self.done.wait()
+        return self.status
+
+
+class ProcessExecutor:
+    """Runs the job as a subprocess supervised over a per-job bridge socket."""
+
+    def __init__(self, connector: Connector, network: Network, work_dir_base: str, cmd: str, args: List[str],
+                 env: Optional[Dict[str, str]] = None, log: Callable[[str], None] = print):
+        self.connector, self.network = connector, network
+        self.base, self.cmd, self.args, self.env, self.log = work_dir_base, cmd, args, env or {}, log
+
+    async def execute(self, spec: M.JobSpec, task_id: str, scheduler: str) -> Execution:
+        ex = Execution()
+        work_dir = os.path.join(self.base, f"hypha-{uuid.uuid4()}")
+        os.makedirs(work_dir, exist_ok=True)
+        sock = os.path.join(work_dir, "bridge.sock")
+        sock_dir = None
+        if len(sock.encode()) > 100:            # sun_path is 108 bytes; fall back to a short private dir
+            import tempfile
+
+            sock_dir = tempfile.mkdtemp(prefix="hb-", dir="/tmp")
+            os.chmod(sock_dir, 0o700)
+            sock = os.path.join(sock_dir, "bridge.sock")
+        bridge = Bridge(self.connector, self.network, work_dir, sock, spec.job_id, scheduler)
+        await bridge.start()
+        job_json = spec.to_json()
+        argv = substitute_placeholders(self.args, sock, work_dir, job_json)
+        cmd = sys.executable if self.cmd in ("python", "python3") else self.cmd
+        env = dict(os.environ)
+        env.update(self.env)
+        env.update({"SOCKET_PATH": sock, "WORK_DIR": work_dir, "JOB_JSON": job_json})
+        try:
+            proc = await asyncio.create_subprocess_exec(cmd, *argv, env=env, stdout=asyncio.subprocess.PIPE,
+                                                        stderr=asyncio.subprocess.STDOUT, start_new_session=True)
+        except OSError:
+            await bridge.stop()
+            shutil.rmtree(work_dir, ignore_errors=True)
+            if sock_dir:
+                shutil.rmtree(sock_dir, ignore_errors=True)
+            raise
+        ex.pid = proc.pid  # type: ignore[attr-defined]
+        ex.work_dir = work_dir  # type: ignore[attr-defined]
+
+        async def forward():
+            assert proc.stdout is not None
+            async for line in proc.stdout:
+                self.log(f"[job {spec.job_id[:8]}] {line.decode(errors='replace').rstrip()}")
+
+        async def supervise():
+            fwd = asyncio.ensure_future(forward())
+            waiter = asyncio.ensure_future(proc.wait())
+            canceller = asyncio.ensure_future(ex._cancel.wait())
+            try:
+                await asyncio.wait({waiter, canceller}, return_when=asyncio.FIRST_COMPLETED)
+                if not waiter.done():
+                    try:
+                        os.killpg(proc.pid, signal.SIGTERM)
+                    except ProcessLookupError:
+                        pass
+                    try:
+                        await asyncio.wait_for(asyncio.shield(waiter), KILL_GRACE_S)
+                    except asyncio.TimeoutError:
+                        try:
+                            os.killpg(proc.pid, signal.SIGKILL)
+                        except ProcessLookupError:
+                            pass
+                        await waiter
+                    ex.status = M.JobStatus.FAILED
+                else:
+                    ex.status = M.JobStatus.FINISHED if proc.returncode == 0 else M.JobStatus.FAILED
+            finally:
+                canceller.cancel()
+                try:
+                    await asyncio.wait_for(fwd, 1.0)
+                except (asyncio.TimeoutError, Exception):
+                    fwd.cancel()
+                await bridge.stop()
+                shutil.rmtree(work_dir, ignore_errors=True)
+                if sock_dir:
+                    shutil.rmtree(sock_dir, ignore_errors=True)
+                ex.done.set()
+
+        ex._task = asyncio.ensure_future(supervise())  # type: ignore[attr-defined]
+        return ex
+
+
+# ---------------------------------------------------------------------------------------------
+# parameter server
+# ---------------------------------------------------------------------------------------------
+def nesterov_step(avg: Dict[str, Any], momentum: Optional[Dict[str, Any]], lr: float, mu: float):
+    """``m = g`` (first round) else ``mu*m + g``; ``u = lr*(mu*m + g)``.
+    Vector (parameter_server.rs:452-524): lr=.1 mu=.7 g0=.5 -> u0=.085;
+    g1=[.1,.2,.3,.4,.5] -> u1=[.0415,.0585,.0755,.0925,.1095]."""
+    new_m, upd = {}, {}
+    for k, g in avg.items():
+        m = g.clone() if momentum is None else momentum[k] * mu + g
+        new_m[k] = m
+        upd[k] = (m * mu + g) * lr
+    return new_m, upd
+
+
+class ParameterServerExecutor:
+    def __init__(self, connector: Connector, network: Network, work_dir_base: str,
+                 receive_timeout_s: float = 600.0, log: Callable[[str], None] = print):
+        self.connector, self.network, self.base = connector, network, work_dir_base
+        self.receive_timeout_s, self.log = receive_timeout_s, log
+
+    async def execute(self, spec: M.JobSpec, task_id: str, scheduler: str) -> Execution:
+        cfg = spec.executor.config
+        assert isinstance(cfg, M.AggregateExecutorConfig)
+        ex = Execution()
+        work_dir = os.path.join(self.base, f"hypha-{uuid.uuid4()}")
+        os.makedirs(work_dir, exist_ok=True)
+        ex.work_dir = work_dir  # type: ignore[attr-defined]
+
+        async def run():
+            from safetensors.torch import load_file, save_file
+
+            workers = list(cfg.updates.get_peers())
+            momentum = None
+            rnd = 0
+            incoming = self.connector.receive(cfg.updates, job_id=spec.job_id)
+            try:
+                while True:
+                    got: Dict[str, str] = {}
+                    while len(got) < len(workers):
+                        try:
+                            st = await asyncio.wait_for(incoming.__anext__(), self.receive_timeout_s)
+                        except asyncio.TimeoutError:
+                            missing = [w for w in workers if w not in got]
+                            if not got:
+                                raise
+                            self.log(f"[ps {spec.job_id[:8]}] round {rnd}: timeout, dropping {missing}")
+                            workers = [w for w in workers if w in got]      # membership shrink (Q8)
+                            break
+                        path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
+                        await st.save(path)
+                        got[st.peer] = path
+                    # true mean, one tensor at a time
+                    files = [load_file(p) for p in got.values()]
+                    avg = {}
+                    for k in files[0].keys():
+                        acc = files[0][k].float().clone()
+                        for f in files[1:]:
+                            acc += f[k].float()
+                        avg[k] = acc / len(files)
+                    del files
+                    momentum, upd = nesterov_step(avg, momentum, cfg.optimizer.learning_rate, cfg.optimizer.momentum)
+                    out = os.path.join(work_dir, "gradient_update")
+                    save_file({k: v.contiguous() for k, v in upd.items()}, out)
+                    save_file({k: v.contiguous() for k, v in momentum.items()}, os.path.join(work_dir, "momentum"))
+                    send_ref = M.Send.to_peers([p for p in cfg.results.peers if p in got] or cfg.results.peers)
+                    await self.connector.send(send_ref, out, job_id=spec.job_id)
+                    for p in got.values():
+                        os.unlink(p)
+                    os.unlink(out)
+                    rnd += 1
+                    resp = await self.network.request(scheduler, M.PROGRESS_PROTOCOL,
+                                                      M.ProgressRequest(spec.job_id, M.Progress("updated")))
+                    if M.ProgressResponse.from_wire(resp).type == "Done":
+                        ex.status = M.JobStatus.FINISHED
+                        return
+            except asyncio.CancelledError:
+                ex.status = M.JobStatus.FAILED
+            except Exception as exc:
+                self.log(f"[ps {spec.job_id[:8]}] failed: {type(exc).__name__}: {exc}")
+                ex.status = M.JobStatus.FAILED
+            finally:
+                try:
+                    await incoming.aclose()
+                except Exception:
+                    pass
+                shutil.rmtree(work_dir, ignore_errors=True)
+                ex.done.set()
+
+        task = asyncio.ensure_future(run())
+
+        async def watch_cancel():
+            await ex._cancel.wait()
+            task.cancel()
+
+        ex._task = task  # type: ignore[attr-defined]
+        ex._watch = asyncio.ensure_future(watch_cancel())  # type: ignore[attr-defined]
+        return ex
+
+
+# ---------------------------------------------------------------------------------------------
+# job manager
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class Job:
+    id: str
+    lease_id: str
+    scheduler: str
+    spec: M.JobSpec
+    execution: Execution
+
+
+class JobManagerError(Exception):
+    pass
+
+
+class JobManager:
+    """Picks the executor for a dispatched job and tracks running jobs by id / lease."""
+
+    def __init__(self, connector: Connector, network: Network, work_dir: str, executor_configs: List[Any],
+                 log: Callable[[str], None] = print):
+        self.connector, self.network, self.work_dir, self.log = connector, network, work_dir, log
+        self.executor_configs = executor_configs
+        self.jobs: Dict[str, Job] = {}
+
+    def supported(self) -> List[M.ExecutorDescriptor]:
+        return [M.ExecutorDescriptor(e.cls, e.name) for e in self.executor_configs]
+
+    def _find(self, desc: M.ExecutorDescriptor):
+        for e in self.executor_configs:
+            if e.cls == desc.cls and e.name == desc.name:
+                return e
+        raise JobManagerError(f"no executor configured for {desc.cls}/{desc.name}")
+
+    async def execute(self, task_id: str, spec: M.JobSpec, lease_id: str, scheduler: str) -> Job:
+        ec = self._find(spec.executor.descriptor)
+        if ec.runtime == "process":
+            runner = ProcessExecutor(self.connector, self.network, self.work_dir, ec.cmd, list(ec.args), log=self.log)
+        elif ec.runtime == "parameter-server":
+            if spec.executor.descriptor.cls != "aggregate":
+                raise JobManagerError("parameter-server runtime only runs aggregate jobs")
+            runner = ParameterServerExecutor(self.connector, self.network, self.work_dir, log=self.log)
+        else:
+            raise JobManagerError(f"unknown runtime {ec.runtime!r}")
+        execution = await runner.execute(spec, task_id, scheduler)
+        job = Job(task_id, lease_id, scheduler, spec, execution)
+        self.jobs[task_id] = job
+        asyncio.ensure_future(self._report(job))
+        return job
+
+    async def _report(self, job: Job) -> None:
+        status = await job.execution.wait()
+        try:
+            await self.network.request(job.scheduler, M.API_PROTOCOL, M.ApiRequest.job_status(job.id, status),
+                                       timeout=5.0)
+        except NetworkError:
+            pass
+
+    def find_jobs_by_lease(self, lease_id: str) -> List[Job]:
+        return [j for j in self.jobs.values() if j.lease_id == lease_id]
+
+    def find_jobs_by_scheduler(self, scheduler: str) -> List[Job]:
+        return [j for j in self.jobs.values() if j.scheduler == scheduler]
+
+    def get_status(self, task_id: str) -> M.JobStatus:
+        j = self.jobs.get(task_id)
+        return j.execution.status if j else M.JobStatus.UNKNOWN
+
+    async def cancel(self, task_id: str) -> None:
+        j = self.jobs.get(task_id)
+        if j is not None:
+            j.execution.cancel()
+            await j.execution.wait()
+
+    def cleanup_finished_jobs(self) -> int:
+        gone = [k for k, j in self.jobs.items() if j.execution.done.is_set()]
+        for k in gone:
+            del self.jobs[k]
+        return len(gone)
+
+    async def shutdown(self) -> None:
+        for j in list(self.jobs.values()):
+            j.execution.cancel()
+        for j in list(self.jobs.values()):
+            try:
+                await asyncio.wait_for(j.execution.wait(), KILL_GRACE_S + 2)
+            except asyncio.TimeoutError:
+                pass

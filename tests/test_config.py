@@ -1,0 +1,125 @@
+"""Layered config tests (model: crates/config/src/lib.rs:642-910, worker/src/config.rs:618-651)."""
+import os
+import tomllib
+
+import pytest
+
+from hypha_b200 import config as C
+
+
+def test_defaults_and_documented_toml_roundtrip(tmp_path):
+    cfg = C.builder(C.WorkerConfig).build()
+    assert cfg.resources.gpu == 16.0 and cfg.offer.strategy.type == "flexible" and cfg.work_dir == "/tmp"
+    text = C.to_toml(cfg)
+    assert "# capacity offered to schedulers" in text and "[[executors]]" in text
+    parsed = tomllib.loads(text)
+    assert parsed["executors"][0]["class"] == "train"
+    p = tmp_path / "w.toml"
+    p.write_text(text)
+    again = C.builder(C.WorkerConfig).with_toml(str(p)).build()
+    assert C.to_dict(again) == C.to_dict(cfg)
+
+
+def test_precedence_toml_env_otel_cli(tmp_path):
+    p = tmp_path / "s.toml"
+    p.write_text('status_bridge = "file:1"\ngateway_addresses = ["tcp://1.2.3.4:1"]\ntelemetry_sampler = "always_off"\n')
+    env = {"HYPHA_STATUS_BRIDGE": "env:2", "OTEL_TRACES_SAMPLER": "always_on", "OTEL_TRACES_SAMPLER_ARG": "0.25",
+           "HYPHA_LISTEN_ADDRESSES": '["tcp://127.0.0.1:7"]', "UNRELATED": "x"}
+    cfg = C.builder(C.SchedulerConfig).with_toml(str(p)).with_env(env).build()
+    assert cfg.status_bridge == "env:2"                       # HYPHA_ beats file
+    assert cfg.telemetry_sampler == "always_on"               # OTEL_ beats file (alias traces_sampler)
+    assert cfg.telemetry_sample_ratio == 0.25
+    assert cfg.listen_addresses == ["tcp://127.0.0.1:7"]
+    assert cfg.gateway_addresses == ["tcp://1.2.3.4:1"]
+    cfg2 = C.builder(C.SchedulerConfig).with_toml(str(p)).with_env(env).with_overrides({"status_bridge": "cli:3"}).build()
+    assert cfg2.status_bridge == "cli:3"                      # CLI beats everything
+    assert cfg2._meta.source["status_bridge"] == "cli"
+
+
+def test_scheduler_job_defaults_match_reference():
+    job = C.builder(C.SchedulerConfig).build().scheduler.job
+    assert job.type == "diloco" and job.model.repository == "hypha-space/lenet"
+    assert job.rounds.update_rounds == 100 and job.rounds.avg_samples_between_updates == 1200
+    assert job.rounds.max_batch_size == 600
+    assert job.inner_optimizer.learning_rate == 1e-3 and job.outer_optimizer.learning_rate == 0.7
+    assert job.outer_optimizer.momentum == 0.9 and job.resources.num_workers == 2
+    assert job.resources.worker.gpu == 10.0 and job.resources.worker_price.bid == 100.0
+    d = C.to_dict(job)
+    assert "learning-rate" in d["inner_optimizer"]           # kebab-case on the wire (messages :652-658)
+
+
+def test_job_section_from_toml(tmp_path):
+    p = tmp_path / "s.toml"
+    p.write_text('''
+[scheduler.job]
+type = "diloco"
+[scheduler.job.model]
+repository = "local/llama3-8b"
+filenames = ["config.json"]
+type = "causal-lm"
+input_names = ["input_ids", "labels"]
+[scheduler.job.rounds]
+avg_samples_between_updates = 6400
+update_rounds = 3
+[scheduler.job.inner_optimizer]
+learning-rate = 0.0003
+[scheduler.job.resources]
+num_workers = 8
+''')
+    cfg = C.validate(C.builder(C.SchedulerConfig).with_toml(str(p)).build())
+    job = cfg.scheduler.job
+    assert job.model.type == "causal-lm" and job.resources.num_workers == 8
+    assert job.inner_optimizer.learning_rate == 3e-4 and job.rounds.max_batch_size == 600
+
+
+def test_unknown_key_and_type_errors_point_at_file(tmp_path):
+    p = tmp_path / "w.toml"
+    p.write_text('work_dir = "/tmp"\nbogus_key = 1\n')
+    with pytest.raises(C.ConfigError) as e:
+        C.builder(C.WorkerConfig).with_toml(str(p)).build()
+    assert "bogus_key" in str(e.value) and "w.toml:2" in str(e.value)
+    p.write_text('[resources]\ngpu = "many"\n')
+    with pytest.raises(C.ConfigError) as e:
+        C.builder(C.WorkerConfig).with_toml(str(p)).build()
+    assert "resources.gpu" in str(e.value)
+
+
+def test_gateway_in_excluded_cidr_is_rich_diagnostic(tmp_path):
+    p = tmp_path / "w.toml"
+    p.write_text('# worker\ngateway_addresses = ["tcp://10.1.2.3:4001"]\n')
+    cfg = C.builder(C.WorkerConfig).with_toml(str(p)).build()
+    with pytest.raises(C.ConfigError) as e:
+        C.validate(cfg)
+    msg = str(e.value)
+    assert "10.0.0.0/8" in msg and "w.toml:2" in msg and "gateway_addresses =" in msg
+    ok = C.builder(C.WorkerConfig).with_toml(str(p)).with_overrides({"exclude_cidr": []}).build()
+    C.validate(ok)
+
+
+def test_missing_file_and_bad_toml(tmp_path):
+    with pytest.raises(C.ConfigError):
+        C.builder(C.GatewayConfig).with_toml(str(tmp_path / "nope.toml")).build()
+    bad = tmp_path / "bad.toml"
+    bad.write_text("this is = = not toml")
+    with pytest.raises(C.ConfigError):
+        C.builder(C.GatewayConfig).with_toml(str(bad)).build()
+
+
+def test_worker_validation_rules():
+    cfg = C.builder(C.WorkerConfig).with_overrides({"offer": {"strategy": {"type": "greedy"}}}).build()
+    with pytest.raises(C.ConfigError):
+        C.validate(cfg)
+    cfg = C.builder(C.WorkerConfig).with_overrides(
+        {"executors": [{"class": "train", "name": "x", "runtime": "process"}]}).build()
+    with pytest.raises(C.ConfigError):
+        C.validate(cfg)
+
+
+def test_tls_loader(tmp_path):
+    cert = tmp_path / "c.pem"
+    cert.write_bytes(b"-----BEGIN CERTIFICATE-----\n")
+    cfg = C.builder(C.GatewayConfig).with_overrides({"cert_pem": str(cert)}).build()
+    assert C.load_tls(cfg)["cert_pem"].startswith(b"-----BEGIN")
+    cfg = C.builder(C.GatewayConfig).with_overrides({"key_pem": str(tmp_path / "missing.pem")}).build()
+    with pytest.raises(C.ConfigError):
+        C.load_tls(cfg)

@@ -102,6 +102,46 @@ def test_rmsnorm_fwd_bwd(C, rows, cols):
     assert _rel(y2, yf2) < 1e-2 and _rel(x2.grad, xf2.grad) < 1e-2 and _rel(w2.grad, wf2.grad) < 2e-2
 
 
+def test_add_norm_linear_and_swiglu_linear(C):
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _rmsnorm_ref
+
+    torch.manual_seed(0)
+    T, H, N, I = 200, 256, 384, 512
+    mk = lambda *s, sc=1.0: (sc * torch.randn(*s, device="cuda")).to(torch.bfloat16).requires_grad_(True)
+    x, r, nw, W = mk(T, H), mk(T, H), mk(H, sc=0.2), mk(N, H, sc=0.05)
+    y, h = ops.add_norm_linear(x, r, nw, W)
+    dy, dh = torch.randn_like(y), torch.randn_like(h)
+    torch.autograd.backward([y, h], [dy, dh])
+    xf, rf, nf, Wf = (t.detach().float().requires_grad_(True) for t in (x, r, nw, W))
+    hs = xf + rf
+    hf = hs + (hs.to(torch.bfloat16).float() - hs).detach()
+    nrm = hf * torch.rsqrt(hf.pow(2).mean(-1, keepdim=True) + 1e-5) * nf
+    yf = nrm @ Wf.t()
+    torch.autograd.backward([yf, hf], [dy.float(), dh.float()])
+    assert _rel(y, yf) < 2e-2 and _rel(x.grad, xf.grad) < 2e-2 and _rel(r.grad, rf.grad) < 2e-2
+    assert _rel(W.grad, Wf.grad) < 2e-2 and _rel(nw.grad, nf.grad) < 3e-2
+    # no-residual variant
+    x2, nw2, W2 = mk(T, H), mk(H, sc=0.2), mk(N, H, sc=0.05)
+    y2, h2 = ops.add_norm_linear(x2, None, nw2, W2)
+    assert h2 is x2
+    y2.backward(dy)
+    xf2, nf2, Wf2 = (t.detach().float().requires_grad_(True) for t in (x2, nw2, W2))
+    yf2 = (xf2 * torch.rsqrt(xf2.pow(2).mean(-1, keepdim=True) + 1e-5) * nf2) @ Wf2.t()
+    yf2.backward(dy.float())
+    assert _rel(y2, yf2) < 2e-2 and _rel(x2.grad, xf2.grad) < 2e-2 and _rel(W2.grad, Wf2.grad) < 2e-2
+    # swiglu + linear
+    gu, Wd = mk(T, 2 * I), mk(H, I, sc=0.05)
+    out = ops.swiglu_linear(gu, Wd)
+    do = torch.randn_like(out)
+    out.backward(do)
+    gf, Wdf = gu.detach().float().requires_grad_(True), Wd.detach().float().requires_grad_(True)
+    g, u = gf.chunk(2, -1)
+    of = (torch.nn.functional.silu(g) * u) @ Wdf.t()
+    of.backward(do.float())
+    assert _rel(out, of) < 2e-2 and _rel(gu.grad, gf.grad) < 2e-2 and _rel(Wd.grad, Wdf.grad) < 2e-2
+
+
 def test_rope(C):
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _rope_ref
@@ -208,10 +248,12 @@ def test_adamw_matches_torch(C, state):
     assert torch.equal(p, opt.master.to(torch.bfloat16))
 
 
-def test_attention_matches_sdpa(C):
+@pytest.mark.parametrize("backend", ["cudnn", "flash2"])
+def test_attention_matches_sdpa(C, backend):
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _attention_ref
 
+    ops.set_attention_backend(backend)
     torch.manual_seed(0)
     B, S, Hq, Hk, D = 2, 256, 8, 2, 128
     qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
