@@ -1,0 +1,40 @@
+"""``hypha-certutil {root,org,node}`` (crates/certutil/src/cli.rs:59-279)."""
+import argparse
+import sys
+
+from .. import certutil as cu
+
+
+def main(argv=None) -> int:
+    p = argparse.ArgumentParser(prog="hypha-certutil", description="development PKI for hypha nodes")
+    sub = p.add_subparsers(dest="command", required=True)
+    r = sub.add_parser("root")
+    r.add_argument("-o", "--organization", required=True)
+    r.add_argument("--country", default="US")
+    r.add_argument("-n", "--name", default=None)
+    r.add_argument("-d", "--dir", default=".")
+    o = sub.add_parser("org")
+    o.add_argument("--root-cert", required=True)
+    o.add_argument("--root-key", required=True)
+    o.add_argument("-o", "--organization", required=True)
+    o.add_argument("--country", default="US")
+    o.add_argument("-n", "--name", default=None)
+    o.add_argument("-d", "--dir", default=".")
+    n = sub.add_parser("node")
+    n.add_argument("--ca-cert", required=True)
+    n.add_argument("--ca-key", required=True)
+    n.add_argument("-n", "--name", required=True)
+    n.add_argument("-s", "--san", action="append", default=[])
+    n.add_argument("-d", "--dir", default=".")
+    a = p.parse_args(argv)
+    if a.command == "root":
+        print(*cu.make_root(a.organization, a.name, a.country, a.dir))
+    elif a.command == "org":
+        print(*cu.make_org(a.root_cert, a.root_key, a.organization, a.name, a.country, a.dir))
+    else:
+        print(*cu.make_node(a.ca_cert, a.ca_key, a.name, tuple(a.san), a.dir))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -253,7 +253,7 @@ def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
     n = torch.empty_like(h)
     C.rmsnorm_fwd(h.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), 0, rows, cols, eps, s)
     dy2 = dy if dy.is_contiguous() else dy.contiguous()
-    _wgrad_into(weight, dy2, n)
+    dw = _wgrad_into(weight, dy2, n)
     dn = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=n)            # reuse the buffer
     dx = torch.empty_like(h)
     nparts = C.rmsnorm_bwd_num_partials(rows)
@@ -263,7 +263,7 @@ def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
         dh2 = dh if dh.is_contiguous() else dh.contiguous()
     C.rmsnorm_bwd(dn.data_ptr(), h.data_ptr(), norm_w.data_ptr(), rstd.data_ptr(), _ptr(dh2), dx.data_ptr(),
                   partial.data_ptr(), rows, cols, s)
-    return dx, _norm_wgrad(norm_w, partial, nparts, cols)
+    return dx, _norm_wgrad(norm_w, partial, nparts, cols), dw
 
 
 class _AddNormLinear(torch.autograd.Function):
@@ -283,8 +283,8 @@ class _AddNormLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy, dh):
         h, rstd, norm_w, weight = ctx.saved_tensors
-        dx, dnw = _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, ctx.eps)
-        return dx, dx, dnw, None, None
+        dx, dnw, dw = _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, ctx.eps)
+        return dx, dx, dnw, dw, None
 
 
 class _NormLinear(torch.autograd.Function):
@@ -300,8 +300,8 @@ class _NormLinear(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         x, rstd, norm_w, weight = ctx.saved_tensors
-        dx, dnw = _norm_linear_bwd(dy, None, x, rstd, norm_w, weight, ctx.eps)
-        return dx, dnw, None, None
+        dx, dnw, dw = _norm_linear_bwd(dy, None, x, rstd, norm_w, weight, ctx.eps)
+        return dx, dnw, dw, None
 
 
 def add_norm_linear(x: torch.Tensor, residual: Optional[torch.Tensor], norm_w: torch.Tensor,
@@ -338,11 +338,11 @@ class _SwiGLULinear(torch.autograd.Function):
         act = torch.empty((rows, inter), dtype=gu.dtype, device=gu.device)
         C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, inter, s)
         dy2 = dy if dy.is_contiguous() else dy.contiguous()
-        _wgrad_into(weight, dy2, act)
+        dw = _wgrad_into(weight, dy2, act)
         dact = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=act)
         dgu = torch.empty_like(gu)
         C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
-        return dgu, None
+        return dgu, dw
 
 
 def swiglu_linear(gu: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:

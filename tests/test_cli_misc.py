@@ -1,0 +1,95 @@
+import asyncio
+import json
+import os
+import tomllib
+
+import pytest
+
+from hypha_b200 import certutil as cu
+from hypha_b200 import cli, config as C, roles
+from hypha_b200.cli import certutil as cu_cli
+from hypha_b200.worker import InvalidPath, nesterov_step, safe_join, substitute_placeholders
+
+
+def test_init_writes_documented_toml_and_job_injection(tmp_path):
+    out = tmp_path / "sched.toml"
+    job = {"rounds": {"update_rounds": 7}, "resources": {"num_workers": 8}}
+    assert cli.main("scheduler", ["init", "-o", str(out), "--job", json.dumps(job), "-n", "sched1"]) == 0
+    d = tomllib.loads(out.read_text())
+    assert d["scheduler"]["job"]["rounds"]["update_rounds"] == 7 and d["scheduler"]["job"]["resources"]["num_workers"] == 8
+    assert d["cert_pem"] == "sched1-cert.pem" and "# " in out.read_text()
+    for role in ("gateway", "worker", "data"):
+        p = tmp_path / f"{role}.toml"
+        assert cli.main(role, ["init", "-o", str(p)]) == 0 and tomllib.loads(p.read_text())
+        assert "## hypha-%s run" % role in cli.cli_markdown(role)
+
+
+def test_run_rejects_bad_config(tmp_path, capsys):
+    p = tmp_path / "w.toml"
+    p.write_text('gateway_addresses = ["tcp://10.0.0.1:1"]\n')
+    assert cli.main("worker", ["run", "-c", str(p)]) == 2
+    assert "excluded range" in capsys.readouterr().err
+
+
+def test_probe_healthy_and_unreachable():
+    async def main():
+        gw_cfg = C.builder(C.GatewayConfig).with_overrides({"listen_addresses": ["tcp://127.0.0.1:0"]}).build()
+        fut = asyncio.get_event_loop().create_future()
+        t = asyncio.ensure_future(roles.run_gateway(gw_cfg, started=fut))
+        node = await fut
+        addr = node.network.listen_addrs[0]
+        assert await roles.probe(addr)
+        node.stop.set()
+        await t
+        assert not await roles.probe(addr, timeout=0.5)
+    asyncio.run(main())
+
+
+def test_certutil_chain(tmp_path):
+    d = str(tmp_path)
+    assert cu_cli.main(["root", "-o", "acme", "-d", d]) == 0
+    assert cu_cli.main(["org", "--root-cert", f"{d}/acme-root-cert.pem", "--root-key", f"{d}/acme-root-key.pem",
+                        "-o", "acme", "-d", d]) == 0
+    assert cu_cli.main(["node", "--ca-cert", f"{d}/acme-ca-cert.pem", "--ca-key", f"{d}/acme-ca-key.pem",
+                        "-n", "worker-1", "-d", d]) == 0
+    assert cu.verify_chain(f"{d}/worker-1-cert.pem")
+    assert oct(os.stat(f"{d}/worker-1-key.pem").st_mode & 0o777) == "0o600"
+    assert b"PRIVATE KEY" in open(f"{d}/worker-1-key.pem", "rb").read()
+    cfg = C.builder(C.WorkerConfig).with_overrides({"cert_pem": f"{d}/worker-1-cert.pem", "key_pem": f"{d}/worker-1-key.pem",
+                                                    "trust_pem": f"{d}/worker-1-trust.pem"}).build()
+    assert C.load_tls(cfg)["trust_pem"].startswith(b"-----BEGIN CERTIFICATE")
+
+
+def test_substitutes_all_known_tokens():   # executor/process.rs:207-241
+    out = substitute_placeholders(["--socket", "{SOCKET_PATH}", "--work-dir={WORK_DIR}", "{JOB_JSON}", "{UNKNOWN}"],
+                                  "/s.sock", "/w", '{"a":1}')
+    assert out == ["--socket", "/s.sock", "--work-dir=/w", '{"a":1}', "{UNKNOWN}"]
+
+
+def test_safe_join_rules():                # bridge.rs:330-346
+    assert safe_join("/work", "artifacts/x.bin") == "/work/artifacts/x.bin"
+    for bad in ("/etc/passwd", "../x", "a/../../x", ""):
+        with pytest.raises(InvalidPath):
+            safe_join("/work", bad)
+
+
+def test_nesterov_reference_vector():      # parameter_server.rs:452-524
+    import torch
+
+    m, u = nesterov_step({"w": torch.full((5,), 0.5)}, None, 0.1, 0.7)
+    assert torch.allclose(u["w"], torch.full((5,), 0.085))
+    m, u = nesterov_step({"w": torch.tensor([0.1, 0.2, 0.3, 0.4, 0.5])}, m, 0.1, 0.7)
+    assert torch.allclose(u["w"], torch.tensor([0.0415, 0.0585, 0.0755, 0.0925, 0.1095]), atol=1e-7)
+
+
+def test_aim_driver_jsonl_fallback(tmp_path, monkeypatch):
+    from fastapi.testclient import TestClient
+
+    import hypha_b200.drivers.aim_driver as drv
+
+    monkeypatch.setattr(drv, "JSONL", str(tmp_path / "m.jsonl"))
+    c = TestClient(drv.app)
+    r = c.post("/status", json={"worker_id": "w1", "round": 3, "metric_name": "loss", "value": 1.5})
+    assert r.status_code == 200
+    assert json.loads((tmp_path / "m.jsonl").read_text())["value"] == 1.5
+    assert c.post("/status", json={"worker_id": "w1"}).status_code == 422
