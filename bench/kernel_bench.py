@@ -47,8 +47,10 @@ def gemm_case(name, M, N, K, a_k, b_k, results, hbm, tf):
     Bs = [torch.randn((N, K) if b_k else (K, N), device=dev, dtype=torch.bfloat16) for _ in range(nvar)]
     out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
     row = {"name": name, "M": M, "N": N, "K": K, "a_kmajor": a_k, "b_kmajor": b_k}
-    for backend in ("tcgen05", "cublas"):
-        ops.set_gemm_backend(backend)
+    C = load_C()
+    for backend in ("tcgen05", "tcgen05_2cta", "cublas"):
+        ops.set_gemm_backend("cublas" if backend == "cublas" else "tcgen05")
+        C.gemm_set_cta_mode(2 if backend == "tcgen05_2cta" else 1)
         try:
             ms = time_fn(lambda i: ops.gemm(As[i], Bs[i], a_kmajor=a_k, b_kmajor=b_k, out=out),
                          variants=nvar)
@@ -57,12 +59,15 @@ def gemm_case(name, M, N, K, a_k, b_k, results, hbm, tf):
         except Exception as exc:  # keep going: one broken layout must not hide the others
             row[backend] = {"error": repr(exc)}
     # correctness spot check
-    ops.set_gemm_backend("tcgen05")
     try:
-        got = ops.gemm(As[0], Bs[0], a_kmajor=a_k, b_kmajor=b_k).float()
         ops.set_gemm_backend("cublas")
         ref = ops.gemm(As[0], Bs[0], a_kmajor=a_k, b_kmajor=b_k).float()
-        row["rel_err_vs_cublas"] = ((got - ref).norm() / ref.norm()).item()
+        ops.set_gemm_backend("tcgen05")
+        for mode, key in ((1, "rel_err_vs_cublas"), (2, "rel_err_2cta_vs_cublas")):
+            C.gemm_set_cta_mode(mode)
+            got = ops.gemm(As[0], Bs[0], a_kmajor=a_k, b_kmajor=b_k).float()
+            row[key] = ((got - ref).norm() / ref.norm()).item()
+        C.gemm_set_cta_mode(1)
     except Exception as exc:
         row["rel_err_vs_cublas"] = repr(exc)
     results.append(row)

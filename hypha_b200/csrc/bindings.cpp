@@ -152,6 +152,9 @@ PYBIND11_MODULE(_C, m) {
     if (rc != 0) throw std::runtime_error(std::string("gemm_bf16_tcgen05: ") + hb::gemm_last_error());
   });
 
+  m.def("gemm_set_cta_mode", &hb::gemm_set_cta_mode);
+  m.def("gemm_get_cta_mode", &hb::gemm_get_cta_mode);
+
   // ---- peer memory ------------------------------------------------------------
   m.def("sym_alloc", &hb::comm::sym_alloc, py::arg("bytes"), py::arg("zero") = true);
   m.def("sym_free", &hb::comm::sym_free);

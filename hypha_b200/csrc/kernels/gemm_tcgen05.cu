@@ -270,6 +270,238 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
   }
 }
 
+
+// =====================================================================================
+// 2-CTA variant: a cluster of two CTAs (one SM pair) computes a 256x256 tile with
+// tcgen05.mma.cta_group::2 (UMMA M = 256).  Each CTA stages ITS half of A (128 rows) and
+// its half of B (128 of the 256 N rows), so per-SM shared-memory fill traffic for B is
+// halved and 6 pipeline stages fit.  The leader CTA (rank 0) issues the MMAs and owns the
+// barriers the MMA thread waits on (full / tmem_empty); MMA completion is multicast to both
+// CTAs' empty / tmem_full barriers; each CTA's epilogue drains its own 128 TMEM lanes.
+// =====================================================================================
+constexpr int kStages2 = 6;
+constexpr int kAStage2 = 128 * BK * 2;  // 16 KB: this CTA's 128 rows of A
+constexpr int kBStage2 = 128 * BK * 2;  // 16 KB: this CTA's 128 rows of B (half of N = 256)
+constexpr int kGroupM2 = 8;
+
+struct SmemLayout2 {
+  static constexpr int a_off = 0;
+  static constexpr int b_off = a_off + kStages2 * kAStage2;
+  static constexpr int epi_off = b_off + kStages2 * kBStage2;
+  static constexpr int bar_off = epi_off + kEpiBytes;
+  static constexpr int total = bar_off + (2 * kStages2 + 4) * 8 + 16;
+};
+constexpr int kSmemBytes2 = SmemLayout2::total + 1024;
+
+__device__ __forceinline__ void tile_coords2(int t, const GemmParams& p, int& tm, int& tn) {
+  const int per_group = kGroupM2 * p.tiles_n;
+  const int g = t / per_group;
+  const int first_m = g * kGroupM2;
+  const int gsz = min(p.tiles_m - first_m, kGroupM2);
+  const int r = t - g * per_group;
+  tm = first_m + (r % gsz);
+  tn = r / gsz;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
+                              const __grid_constant__ CUtensorMap tma_b,
+                              const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  const uint32_t a_smem = smem_base + SmemLayout2::a_off;
+  const uint32_t b_smem = smem_base + SmemLayout2::b_off;
+  const uint32_t bars = smem_base + SmemLayout2::bar_off;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (kStages2 + s); };
+  auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages2 + s); };
+  auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 2 + s); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages2 + 4);
+  volatile uint32_t* tmem_ptr_gen =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + SmemLayout2::bar_off + 8 * (2 * kStages2 + 4));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+  const int num_kb = (p.K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_d);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kStages2; ++s) {
+      mbar_init(full_bar(s), 1);    // leader's arrive.expect_tx (bytes of BOTH CTAs land here)
+      mbar_init(empty_bar(s), 1);   // one multicast tcgen05.commit per phase
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar(s), 1);
+      mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2cta(tmem_ptr_smem, kTmemCols);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp == 0 && lane == 0) {
+    // ============================ TMA producer (both CTAs) =================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+      int tm, tn;
+      tile_coords2(t, p, tm, tn);
+      const int m0 = tm * 256 + (int)cta_rank * 128;
+      const int n0 = tn * 256 + (int)cta_rank * 128;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * (kAStage2 + kBStage2));
+        const uint32_t lbar = mapa_shared(full_bar(stage), 0);   // the leader's barrier
+        const int k0 = kb * BK;
+        const uint32_t sa = a_smem + stage * kAStage2;
+        const uint32_t sb = b_smem + stage * kBStage2;
+        if (!p.a_mn) {
+          tma_load_2d_2cta(sa, &tma_a, lbar, k0, m0);            // box {64 k, 128 m}
+        } else {
+          tma_load_2d_2cta(sa, &tma_a, lbar, m0, k0);            // box {64 m, 64 k} x 2
+          tma_load_2d_2cta(sa + BK * 128, &tma_a, lbar, m0 + 64, k0);
+        }
+        if (!p.b_mn) {
+          tma_load_2d_2cta(sb, &tma_b, lbar, k0, n0);            // box {64 k, 128 n}
+        } else {
+          tma_load_2d_2cta(sb, &tma_b, lbar, n0, k0);
+          tma_load_2d_2cta(sb + BK * 128, &tma_b, lbar, n0 + 64, k0);
+        }
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1 && lane == 0 && leader) {
+    // ============================ MMA issuer (leader CTA) ==================
+    const uint32_t idesc = umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);
+    const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
+    const uint32_t a_kadv = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
+    const uint32_t b_kadv = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = a_smem + stage * kAStage2;
+        const uint32_t sb = b_smem + stage * kBStage2;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t ad = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024);
+          const uint64_t bd = umma_smem_desc(sb + k * b_kadv, b_lbo, 1024);
+          umma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit_2cta(empty_bar(stage), 0x3);   // frees the slot in BOTH CTAs
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit_2cta(tfull_bar(acc), 0x3);       // accumulators ready in BOTH CTAs
+    }
+  } else if (warp >= 4) {
+    // ============================ epilogue (both CTAs) =====================
+    const int ew = warp - 4;
+    const uint32_t epi_smem = smem_base + SmemLayout2::epi_off + ew * 2 * kEpiWarpBuf;
+    int it = 0;
+    int buf = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++it) {
+      int tm, tn;
+      tile_coords2(t, p, tm, tn);
+      const int m0 = tm * 256 + (int)cta_rank * 128, n0 = tn * 256;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const int row = m0 + ew * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(t_addr + c * 64, r0);
+        tmem_ld_32x32(t_addr + c * 64 + 32, r1);
+        tmem_ld_wait();
+        if (c == BN / 64 - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(tempty_bar(acc), 0));
+        }
+        const int col0 = n0 + c * 64;
+        uint32_t packed[32];
+        if (p.accumulate) {
+          const bool row_ok = row < p.M;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 prev = make_uint4(0, 0, 0, 0);
+            if (row_ok && col0 + j * 8 + 8 <= p.N)
+              prev = *reinterpret_cast<const uint4*>(p.D + (size_t)row * p.ldd + col0 + j * 8);
+            const __nv_bfloat162* pv = reinterpret_cast<const __nv_bfloat162*>(&prev);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = j * 8 + e * 2;
+              const float2 o = __bfloat1622float2(pv[e]);
+              const float x0 = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]) + o.x;
+              const float x1 = __uint_as_float(i + 1 < 32 ? r0[(i + 1) & 31] : r1[(i + 1) & 31]) + o.y;
+              __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
+              packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * i]),
+                                                      __uint_as_float(r0[2 * i + 1]));
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * i]),
+                                                      __uint_as_float(r1[2 * i + 1]));
+            packed[i] = *reinterpret_cast<uint32_t*>(&h0);
+            packed[16 + i] = *reinterpret_cast<uint32_t*>(&h1);
+          }
+        }
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        const uint32_t sbuf = epi_smem + buf * kEpiWarpBuf;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(packed[4 * j]),
+                       "r"(packed[4 * j + 1]), "r"(packed[4 * j + 2]), "r"(packed[4 * j + 3])
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (col0 < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_d, sbuf, col0, m0 + ew * 32);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2cta(tmem_base, kTmemCols);
+  }
+}
+
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
@@ -279,6 +511,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 std::string g_err;
+int g_mode = 1;   // 1 = single-CTA kernel (default), 2 = cta_group::2 CTA-pair kernel
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 int g_num_sms = 0;
@@ -295,6 +528,9 @@ void init_once() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        kSmemBytes);
+  cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kSmemBytes2);
+  if (const char* e = getenv("HYPHA_GEMM_CTAS")) g_mode = (e[0] == '1') ? 1 : 2;
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements.
@@ -318,6 +554,8 @@ bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, 
 }  // namespace
 
 const char* gemm_last_error() { return g_err.c_str(); }
+void gemm_set_cta_mode(int mode) { std::call_once(g_once, init_once); g_mode = (mode == 1) ? 1 : 2; }
+int gemm_get_cta_mode() { std::call_once(g_once, init_once); return g_mode; }
 
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
@@ -333,10 +571,12 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   if ((a_kmajor || b_kmajor) && (K % 8)) { g_err = "K must be a multiple of 8"; return 3; }
   if (!a_kmajor && (M % 8)) { g_err = "MN-major A needs M % 8 == 0"; return 3; }
 
+  const bool two = (g_mode == 2);
+  const uint32_t b_rows = two ? 128 : BN;       // rows of the K-major B box each CTA loads
   CUtensorMap ta, tb, td;
   bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)
                      : make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
-  ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, BN)
+  ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, b_rows)
                        : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK));
   ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
   if (!ok) return 4;
@@ -347,11 +587,19 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   p.b_mn = b_kmajor ? 0 : 1;
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
-  p.tiles_m = (M + BM - 1) / BM;
   p.tiles_n = (N + BN - 1) / BN;
-  p.num_tiles = p.tiles_m * p.tiles_n;
-  const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
-  gemm_bf16_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, p);
+  if (two) {
+    p.tiles_m = (M + 255) / 256;
+    p.num_tiles = p.tiles_m * p.tiles_n;
+    int clusters = g_num_sms / 2;
+    if (p.num_tiles < clusters) clusters = p.num_tiles;
+    gemm_bf16_tcgen05_2cta_kernel<<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
+  } else {
+    p.tiles_m = (M + BM - 1) / BM;
+    p.num_tiles = p.tiles_m * p.tiles_n;
+    const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
+    gemm_bf16_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, p);
+  }
   count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }

@@ -84,6 +84,8 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
                       cudaStream_t s);
 const char* gemm_last_error();
+void gemm_set_cta_mode(int mode);   // 1 = single-CTA tiles, 2 = cta_group::2 CTA pairs
+int gemm_get_cta_mode();
 
 unsigned long long launch_count();
 void reset_launch_count();

@@ -19,14 +19,16 @@ def _rel(a, b):
     return ((a - b).norm() / (b.norm() + 1e-12)).item()
 
 
+@pytest.mark.parametrize("ctas", [1, 2])
 @pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 256), (384, 264, 136), (1000, 1032, 520),
                                    (2048, 4096, 4096)])
-def test_gemm_tcgen05(C, a_k, b_k, M, N, K):
+def test_gemm_tcgen05(C, a_k, b_k, M, N, K, ctas):
     from hypha_b200 import ops
 
     if not a_k and M % 8:
         pytest.skip("MN-major A needs M % 8 == 0")
+    C.gemm_set_cta_mode(ctas)
     torch.manual_seed(0)
     dev = "cuda"
     A = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
@@ -37,6 +39,7 @@ def test_gemm_tcgen05(C, a_k, b_k, M, N, K):
     out = ops.gemm(a, b, a_kmajor=a_k, b_kmajor=b_k)
     ref = A.float() @ B.float().t()
     torch.cuda.synchronize()
+    C.gemm_set_cta_mode(1)
     assert _rel(out, ref) < 5e-3, f"rel err {_rel(out, ref)}"
 
 

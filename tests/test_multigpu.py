@@ -1,0 +1,29 @@
+"""Multi-GPU tests (need >= 2 CUDA devices): fused outer step over peer memory vs NCCL."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.timeout(600)
+def test_fused_outer_step_matches_nccl_reference():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(_ngpu(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_outer_check.py"), "--numel",
+           str(16 * 1024 * 1024)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"correct": true' in r.stdout
