@@ -107,11 +107,15 @@ PYBIND11_MODULE(_C, m) {
   });
   m.def("diloco_outer_step_fused",
         [](std::vector<u64> delta_peers, std::vector<u64> param_peers, std::vector<u64> anchor_peers,
-           std::vector<u64> flag_peers, u64 master, u64 theta, u64 mom, int64_t n,
-           int64_t shard_begin, int64_t shard_len, int rank, uint32_t member_mask, uint32_t epoch,
-           float lr, float mu, int first_round, int num_ctas, u64 s) {
+           std::vector<u64> flag_peers, u64 master, std::vector<int64_t> seg_begin,
+           std::vector<int64_t> seg_len, std::vector<u64> seg_theta, std::vector<u64> seg_mom, int64_t n,
+           int rank, uint32_t member_mask, uint32_t epoch, float lr, float mu, int first_round,
+           int num_ctas, u64 s) {
           hb::OuterStepArgs a{};
           if (delta_peers.size() > 8) throw std::runtime_error("at most 8 ranks per NVSwitch box");
+          if (seg_begin.size() > 8 || seg_begin.size() != seg_len.size() ||
+              seg_begin.size() != seg_theta.size() || seg_begin.size() != seg_mom.size())
+            throw std::runtime_error("bad segment lists");
           int world = 0;
           for (size_t r = 0; r < delta_peers.size(); ++r) {
             a.delta_peers[r] = P<const bf16>(delta_peers[r]);
@@ -121,9 +125,14 @@ PYBIND11_MODULE(_C, m) {
             if ((member_mask >> r) & 1u) ++world;
           }
           a.master = P<float>(master);
-          a.theta_outer = P<float>(theta);
-          a.momentum = P<float>(mom);
-          a.n = n; a.shard_begin = shard_begin; a.shard_len = shard_len;
+          a.num_segs = (int)seg_begin.size();
+          for (size_t i = 0; i < seg_begin.size(); ++i) {
+            a.seg_begin[i] = seg_begin[i];
+            a.seg_len[i] = seg_len[i];
+            a.seg_theta[i] = P<float>(seg_theta[i]);
+            a.seg_mom[i] = P<float>(seg_mom[i]);
+          }
+          a.n = n;
           a.world = world; a.rank = rank; a.member_mask = member_mask; a.epoch = epoch;
           a.lr = lr; a.mu = mu; a.first_round = first_round;
           a.inv_world = 1.0f / (float)(world > 0 ? world : 1);

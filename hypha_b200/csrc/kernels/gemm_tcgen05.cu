@@ -511,7 +511,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 std::string g_err;
-int g_mode = 1;   // 1 = single-CTA kernel (default), 2 = cta_group::2 CTA-pair kernel
+int g_mode = 2;   // 2 = cta_group::2 CTA-pair kernel (default, faster), 1 = single-CTA kernel
 EncodeTiledFn g_encode = nullptr;
 std::once_flag g_once;
 int g_num_sms = 0;

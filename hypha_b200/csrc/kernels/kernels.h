@@ -47,11 +47,14 @@ struct OuterStepArgs {
   bf16* anchor_peers[8];        // peer-mapped bf16 anchor (round-start weights)
   uint32_t* flag_peers[8];      // peer-mapped barrier flag words [>= 64 u32 each]
   float* master;                // local fp32 master weights (full)
-  float* theta_outer;           // local fp32 outer params, shard only
-  float* momentum;              // local fp32 outer momentum, shard only
+  // Segments of the parameter vector this rank currently owns: its own shard plus any
+  // orphaned shards adopted from ranks that dropped out (fault tolerance).
+  int num_segs;
+  int64_t seg_begin[8];         // first element of the segment
+  int64_t seg_len[8];           // elements in the segment
+  float* seg_theta[8];          // fp32 outer params of the segment
+  float* seg_mom[8];            // fp32 outer momentum of the segment
   int64_t n;                    // total elements
-  int64_t shard_begin;          // first element owned by this rank
-  int64_t shard_len;            // elements owned by this rank
   int world;                    // participating ranks this round
   int rank;                     // my index among participants
   uint32_t member_mask;         // bit r set => rank r participates

@@ -135,12 +135,15 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
   if (ld_acquire_gpu(&ls->status) != 0u) return;
 
   // ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast --------
-  {
+  for (int seg = 0; seg < a.num_segs; ++seg) {
     const bf16* anchor = a.anchor_peers[a.rank];
-    const int64_t nvec = a.shard_len >> 3;
+    float* theta_outer = a.seg_theta[seg];
+    float* momentum = a.seg_mom[seg];
+    const int64_t seg_begin = a.seg_begin[seg];
+    const int64_t nvec = a.seg_len[seg] >> 3;
     for (int64_t i = tid; i < nvec; i += nthreads) {
       const int64_t loc = i << 3;
-      const int64_t off = a.shard_begin + loc;
+      const int64_t off = seg_begin + loc;
       uint4 raw[8];
 #pragma unroll
       for (int r = 0; r < 8; ++r) {
@@ -160,20 +163,20 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
       }
       float x[8], th[8], mo[8];
       unpack8(ld_stream_bf16x8(anchor + off), x);
-      *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(a.theta_outer + loc);
-      *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(a.theta_outer + loc + 4);
-      *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(a.momentum + loc);
-      *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(a.momentum + loc + 4);
+      *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
+      *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
+      *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
+      *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(momentum + loc + 4);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const float g = acc[e] * a.inv_world + (x[e] - th[e]);
         mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
         th[e] += a.lr * (a.mu * mo[e] + g);
       }
-      *reinterpret_cast<float4*>(a.theta_outer + loc) = *reinterpret_cast<float4*>(th);
-      *reinterpret_cast<float4*>(a.theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
-      *reinterpret_cast<float4*>(a.momentum + loc) = *reinterpret_cast<float4*>(mo);
-      *reinterpret_cast<float4*>(a.momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
+      *reinterpret_cast<float4*>(theta_outer + loc) = *reinterpret_cast<float4*>(th);
+      *reinterpret_cast<float4*>(theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
+      *reinterpret_cast<float4*>(momentum + loc) = *reinterpret_cast<float4*>(mo);
+      *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
       bf16x8 pn = pack8(th);
       const uint4 pv = *reinterpret_cast<uint4*>(&pn);
 #pragma unroll

@@ -198,6 +198,9 @@ class DiLoCoOuter:
             sl = slice(self.shard_begin, self.shard_begin + self.shard_len)
             self.theta_outer = opt.master[sl].clone()
             self.momentum = torch.zeros(self.shard_len, dtype=torch.float32, device=dev)
+            # segments owned by this rank: its shard + shards adopted from dropped ranks
+            self.segments = {self.rank: (self.shard_begin, self.shard_len, self.theta_outer, self.momentum)}
+            self.attempt = 0
             load_C().set_outer_timeout_ms(int(cfg.timeout_ms))
         elif backend == "nccl":
             # baseline: replicated outer state, stock collectives + unfused torch ops
@@ -226,16 +229,17 @@ class DiLoCoOuter:
                                  opt.params.data_ptr(), self.n, cfg.outer_lr, cfg.outer_momentum,
                                  first, 1.0, s)
         elif self.backend == "fused":
-            self.round_epoch = self.round + 1
+            self.attempt += 1                      # flag tokens must be unique per launch
+            segs = [self.segments[k] for k in sorted(self.segments)]
             C.diloco_outer_step_fused(self.delta_buf.peer_ptrs, self.param_buf.peer_ptrs,
                                       self.anchor_buf.peer_ptrs, self.flag_buf.peer_ptrs,
-                                      opt.master.data_ptr(), self.theta_outer.data_ptr(),
-                                      self.momentum.data_ptr(), self.n, self.shard_begin,
-                                      self.shard_len, self.rank, self.member_mask,
-                                      self.round_epoch, cfg.outer_lr, cfg.outer_momentum, first,
-                                      cfg.num_ctas, s)
+                                      opt.master.data_ptr(), [b for b, _, _, _ in segs],
+                                      [l for _, l, _, _ in segs], [t.data_ptr() for _, _, t, _ in segs],
+                                      [m.data_ptr() for _, _, _, m in segs], self.n, self.rank,
+                                      self.member_mask, self.attempt, cfg.outer_lr, cfg.outer_momentum,
+                                      first, cfg.num_ctas, s)
             nmem = bin(self.member_mask).count("1")
-            wire = 2 * self.shard_len * (nmem - 1)
+            wire = 2 * sum(l for _, l, _, _ in segs) * (nmem - 1)
             self.group.counters.add("/hypha-peer-memory/outer-step", inbound=wire, outbound=wire)
         else:
             import torch.distributed as dist
@@ -252,6 +256,71 @@ class DiLoCoOuter:
             opt.master.copy_(self.theta_outer)
             opt.params.copy_(self.theta_outer)
         self.round += 1
+
+    # -- fault tolerance ------------------------------------------------------------------------
+    def members(self) -> List[int]:
+        return [r for r in range(self.world) if (self.member_mask >> r) & 1]
+
+    def adopter_of(self, dead: int, members: List[int]) -> int:
+        """Deterministic adopter of an orphaned shard: the next live rank in cyclic order."""
+        for d in range(1, self.world + 1):
+            c = (dead + d) % self.world
+            if c in members:
+                return c
+        raise RuntimeError("no live rank left")
+
+    def drop_ranks(self, dead: List[int]) -> None:
+        """Shrink the membership; orphaned shards are adopted with theta_outer re-derived from the
+        common bf16 anchor (every rank holds it) and zero momentum."""
+        live = [r for r in self.members() if r not in dead]
+        self.set_members(live)
+        for k in dead:
+            if self.adopter_of(k, live) == self.rank and k not in self.segments:
+                b, l = shard_bounds(self.n, self.world, k)
+                theta = self.anchor_buf.local[b:b + l].float()
+                self.segments[k] = (b, l, theta, torch.zeros_like(theta))
+
+    def readmit(self, rank: int) -> None:
+        """A (re)joined rank takes its shard back at a round boundary."""
+        if rank != self.rank:
+            self.segments.pop(rank, None)
+        self.set_members(sorted(set(self.members()) | {rank}))
+
+    def sync_epoch(self) -> None:
+        """Agree on the flag-token epoch across the group (control-plane all-gather).  Needed when a
+        rank that missed launches (re)joins: stale flag words must never satisfy a new barrier."""
+        vals = self.group._exchange(int(self.attempt))
+        self.attempt = max(int(v) for v in vals)
+
+    def reseed_from(self, src_rank: int) -> None:
+        """(Re)join: pull the current global weights from a live rank over peer memory and rebuild
+        every piece of local state that derives from them."""
+        self.group.pull(src_rank, self.param_buf.name)
+        C = load_C()
+        C.bf16_to_master(self.opt.params.data_ptr(), self.opt.master.data_ptr(), self.n, cuda_stream())
+        self.anchor_buf.local.copy_(self.opt.params)
+        sl = slice(self.shard_begin, self.shard_begin + self.shard_len)
+        self.theta_outer.copy_(self.opt.master[sl])
+        self.momentum.zero_()
+        self.opt.m.zero_()
+        self.opt.v.zero_()
+
+    def step_resilient(self, max_retries: int = 2) -> tuple:
+        """``step()`` that survives ranks that never show up: on a barrier-1 timeout the missing
+        ranks are dropped, their shards adopted, and the step is retried with the survivors."""
+        for _ in range(max_retries + 1):
+            rnd = self.round
+            self.step()
+            st, missing = self.check()
+            if st == 0:
+                return (0, 0)
+            self.round = rnd                       # the failed attempt did not advance the round
+            if st != 1:
+                raise RuntimeError(f"outer step failed mid-broadcast (status {st}, missing mask {missing:#x}); "
+                                   f"restore from the last checkpoint")
+            dead = [r for r in range(self.world) if (missing >> r) & 1]
+            self.drop_ranks(dead)
+        raise RuntimeError("outer step kept timing out")
 
     def check(self) -> tuple:
         """Host-side status of the last fused step: (status, missing_rank_mask)."""

@@ -27,3 +27,15 @@ def test_fused_outer_step_matches_nccl_reference():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"correct": true' in r.stdout
+
+
+@pytest.mark.timeout(600)
+def test_kill_and_rejoin_over_peer_memory():
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(_ngpu(), 4)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "tests", "mgpu_fault_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"correct": true' in r.stdout
