@@ -40,6 +40,7 @@ def parse_args():
     ap.add_argument("--state-dtype", default=os.environ.get("HYPHA_BENCH_STATE", "bf16"))
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
     ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2"])
     return ap.parse_args()
 
@@ -139,6 +140,7 @@ def main():
     from hypha_b200.trainer import DiLoCoTrainer
 
     ops.set_attention_backend(args.attn)
+    ops.set_fp8(args.fp8)
     if args.impl == "baseline":
         ops.set_gemm_backend("cublas")
     cfg = get_config(args.model)
@@ -230,7 +232,8 @@ def main():
             "metric": "tokens/sec (whole box, device-timed, max over ranks) Llama-3-8B DiLoCo H=100",
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp8 GEMMs (e4m3 fwd / e5m2 grad, per-tensor scaling), bf16 elsewhere" if args.fp8 else "bf16",
             "data": "synthetic tokens, random-init weights", "impl": args.impl,
             "config": {
                 "model": cfg.name, "params": cfg.num_params(), "global_batch": B * world,

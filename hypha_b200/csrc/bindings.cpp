@@ -161,6 +161,21 @@ PYBIND11_MODULE(_C, m) {
     if (rc != 0) throw std::runtime_error(std::string("gemm_bf16_tcgen05: ") + hb::gemm_last_error());
   });
 
+  m.def("gemm_fp8", [](u64 A, u64 B, u64 D, int M, int N, int K, int lda, int ldb, int ldd, int a_kmajor,
+                       int b_kmajor, int a_fmt, int b_fmt, u64 dq_a, u64 dq_b, int accumulate, u64 s) {
+    int rc = hb::gemm_fp8_tcgen05(P<const uint8_t>(A), P<const uint8_t>(B), P<bf16>(D), M, N, K, lda, ldb, ldd,
+                                  a_kmajor, b_kmajor, a_fmt, b_fmt, P<const float>(dq_a), P<const float>(dq_b),
+                                  accumulate, S(s));
+    if (rc != 0) throw std::runtime_error(std::string("gemm_fp8_tcgen05: ") + hb::gemm_last_error());
+  });
+  m.def("amax_bf16", [](u64 x, int64_t n, u64 amax, u64 s) {
+    hb::amax_bf16(P<const bf16>(x), n, P<float>(amax), S(s));
+    check_last("amax_bf16");
+  });
+  m.def("quantize_fp8", [](u64 x, u64 out, int64_t n, u64 amax, u64 dequant, int fmt, u64 s) {
+    hb::quantize_fp8(P<const bf16>(x), P<uint8_t>(out), n, P<const float>(amax), P<float>(dequant), fmt, S(s));
+    check_last("quantize_fp8");
+  });
   m.def("gemm_set_cta_mode", &hb::gemm_set_cta_mode);
   m.def("gemm_get_cta_mode", &hb::gemm_get_cta_mode);
 

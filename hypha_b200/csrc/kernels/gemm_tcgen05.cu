@@ -58,6 +58,9 @@ struct GemmParams {
   const bf16* D;
   int ldd;
   int tiles_m, tiles_n, num_tiles;
+  int a_fmt, b_fmt;        // fp8 only: 0 = e4m3, 1 = e5m2
+  const float* scale;      // fp8 only: device dequantisation factor of A
+  const float* scale_b;    // fp8 only: device dequantisation factor of B
 };
 
 __device__ __forceinline__ void tile_coords(int t, const GemmParams& p, int& tm, int& tn) {
@@ -303,8 +306,12 @@ __device__ __forceinline__ void tile_coords2(int t, const GemmParams& p, int& tm
   tn = r / gsz;
 }
 
+// kFp8 = false: bf16 operands (kind::f16, 64-element K blocks, UMMA_K = 16)
+// kFp8 = true : fp8 e4m3/e5m2 operands (kind::f8f6f4, 128-element K blocks, UMMA_K = 32), the
+//               fp32 accumulator is multiplied by *p.scale (dequantisation) in the epilogue.
+template <bool kFp8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
+gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                               const __grid_constant__ CUtensorMap tma_b,
                               const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -326,7 +333,12 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
-  const int num_kb = (p.K + BK - 1) / BK;
+  constexpr int kElem = kFp8 ? 1 : 2;            // bytes per operand element
+  constexpr int BKE = 128 / kElem;               // K elements per 128-byte swizzle row
+  constexpr int UK = 32 / kElem;                 // K elements per tcgen05.mma
+  constexpr int kChunk = BKE * 128;              // bytes of one MN-major chunk (BKE k-rows x 128 B)
+  constexpr int kMnPerChunk = 128 / kElem;       // MN elements per 128-byte row
+  const int num_kb = (p.K + BKE - 1) / BKE;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
 
@@ -365,30 +377,33 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         mbar_wait(empty_bar(stage), phase ^ 1u);
         if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * (kAStage2 + kBStage2));
         const uint32_t lbar = mapa_shared(full_bar(stage), 0);   // the leader's barrier
-        const int k0 = kb * BK;
+        const int k0 = kb * BKE;
         const uint32_t sa = a_smem + stage * kAStage2;
         const uint32_t sb = b_smem + stage * kBStage2;
         if (!p.a_mn) {
-          tma_load_2d_2cta(sa, &tma_a, lbar, k0, m0);            // box {64 k, 128 m}
+          tma_load_2d_2cta(sa, &tma_a, lbar, k0, m0);            // box {128 B of k, 128 m}
         } else {
-          tma_load_2d_2cta(sa, &tma_a, lbar, m0, k0);            // box {64 m, 64 k} x 2
-          tma_load_2d_2cta(sa + BK * 128, &tma_a, lbar, m0 + 64, k0);
+#pragma unroll
+          for (int i = 0; i < 128 / kMnPerChunk; ++i)            // box {128 B of m, BKE k}
+            tma_load_2d_2cta(sa + i * kChunk, &tma_a, lbar, m0 + i * kMnPerChunk, k0);
         }
         if (!p.b_mn) {
-          tma_load_2d_2cta(sb, &tma_b, lbar, k0, n0);            // box {64 k, 128 n}
+          tma_load_2d_2cta(sb, &tma_b, lbar, k0, n0);            // box {128 B of k, 128 n}
         } else {
-          tma_load_2d_2cta(sb, &tma_b, lbar, n0, k0);
-          tma_load_2d_2cta(sb + BK * 128, &tma_b, lbar, n0 + 64, k0);
+#pragma unroll
+          for (int i = 0; i < 128 / kMnPerChunk; ++i)
+            tma_load_2d_2cta(sb + i * kChunk, &tma_b, lbar, n0 + i * kMnPerChunk, k0);
         }
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ============================ MMA issuer (leader CTA) ==================
-    const uint32_t idesc = umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);
-    const uint32_t a_lbo = p.a_mn ? BK * 128 : 16, b_lbo = p.b_mn ? BK * 128 : 16;
-    const uint32_t a_kadv = p.a_mn ? UMMA_K * 128 : UMMA_K * 2;
-    const uint32_t b_kadv = p.b_mn ? UMMA_K * 128 : UMMA_K * 2;
+    const uint32_t idesc = kFp8 ? umma_idesc_fp8(256, BN, p.a_mn, p.b_mn, p.a_fmt, p.b_fmt)
+                                : umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);
+    const uint32_t a_lbo = p.a_mn ? kChunk : 16, b_lbo = p.b_mn ? kChunk : 16;
+    const uint32_t a_kadv = p.a_mn ? UK * 128 : 32;   // MN-major: UK k-rows of 128 B; K-major: 32 B
+    const uint32_t b_kadv = p.b_mn ? UK * 128 : 32;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -404,10 +419,11 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         const uint32_t sa = a_smem + stage * kAStage2;
         const uint32_t sb = b_smem + stage * kBStage2;
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
+        for (int k = 0; k < BKE / UK; ++k) {
           const uint64_t ad = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024);
           const uint64_t bd = umma_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-          umma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (kFp8) umma_fp8_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          else umma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit_2cta(empty_bar(stage), 0x3);   // frees the slot in BOTH CTAs
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
@@ -418,6 +434,7 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     // ============================ epilogue (both CTAs) =====================
     const int ew = warp - 4;
     const uint32_t epi_smem = smem_base + SmemLayout2::epi_off + ew * 2 * kEpiWarpBuf;
+    const float out_scale = (kFp8 && p.scale != nullptr) ? __ldg(p.scale) * __ldg(p.scale_b) : 1.f;
     int it = 0;
     int buf = 0;
     for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++it) {
@@ -455,8 +472,8 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
             for (int e = 0; e < 4; ++e) {
               const int i = j * 8 + e * 2;
               const float2 o = __bfloat1622float2(pv[e]);
-              const float x0 = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]) + o.x;
-              const float x1 = __uint_as_float(i + 1 < 32 ? r0[(i + 1) & 31] : r1[(i + 1) & 31]) + o.y;
+              const float x0 = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]) * out_scale + o.x;
+              const float x1 = __uint_as_float(i + 1 < 32 ? r0[(i + 1) & 31] : r1[(i + 1) & 31]) * out_scale + o.y;
               __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);
               packed[i >> 1] = *reinterpret_cast<uint32_t*>(&h);
             }
@@ -464,10 +481,10 @@ gemm_bf16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         } else {
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * i]),
-                                                      __uint_as_float(r0[2 * i + 1]));
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * i]),
-                                                      __uint_as_float(r1[2 * i + 1]));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(__uint_as_float(r0[2 * i]) * out_scale,
+                                                      __uint_as_float(r0[2 * i + 1]) * out_scale);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(__uint_as_float(r1[2 * i]) * out_scale,
+                                                      __uint_as_float(r1[2 * i + 1]) * out_scale);
             packed[i] = *reinterpret_cast<uint32_t*>(&h0);
             packed[16 + i] = *reinterpret_cast<uint32_t*>(&h1);
           }
@@ -528,19 +545,22 @@ void init_once() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        kSmemBytes);
-  cudaFuncSetAttribute(gemm_bf16_tcgen05_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kSmemBytes2);
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        kSmemBytes2);
   if (const char* e = getenv("HYPHA_GEMM_CTAS")) g_mode = (e[0] == '1') ? 1 : 2;
 }
 
 // 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of `ld` elements.
 bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
-               uint32_t box_inner, uint32_t box_outer) {
+               uint32_t box_inner, uint32_t box_outer, int elem_bytes = 2) {
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {ld * sizeof(bf16)};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims,
+  CUresult r = g_encode(m, elem_bytes == 1 ? CU_TENSOR_MAP_DATA_TYPE_UINT8 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                        2, const_cast<void*>(ptr), dims,
                         strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -587,19 +607,60 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   p.b_mn = b_kmajor ? 0 : 1;
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
+  p.a_fmt = p.b_fmt = 0; p.scale = nullptr; p.scale_b = nullptr;
   p.tiles_n = (N + BN - 1) / BN;
   if (two) {
     p.tiles_m = (M + 255) / 256;
     p.num_tiles = p.tiles_m * p.tiles_n;
     int clusters = g_num_sms / 2;
     if (p.num_tiles < clusters) clusters = p.num_tiles;
-    gemm_bf16_tcgen05_2cta_kernel<<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
+    gemm_tcgen05_2cta_kernel<false><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
   } else {
     p.tiles_m = (M + BM - 1) / BM;
     p.num_tiles = p.tiles_m * p.tiles_n;
     const int grid = p.num_tiles < g_num_sms ? p.num_tiles : g_num_sms;
     gemm_bf16_tcgen05_kernel<<<grid, kThreads, kSmemBytes, s>>>(ta, tb, td, p);
   }
+  count_launch();
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }
+  return 0;
+}
+
+
+// D[M,N] (+)= scale * (A . B) with fp8 (e4m3 / e5m2) operands, fp32 accumulation, bf16 output.
+int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, int K, int lda,
+                     int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,
+                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s) {
+  std::call_once(g_once, init_once);
+  if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
+  if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(A) || !al16(B) || !al16(D) || (lda % 16) || (ldb % 16) || (ldd % 8) || (N % 16) ||
+      (K % 16) || (!a_kmajor && (M % 16))) {
+    g_err = "fp8 operands need 16-byte aligned pointers / leading dimensions and M,N,K % 16 == 0";
+    return 3;
+  }
+  CUtensorMap ta, tb, td;
+  bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 128, 128, 1)
+                     : make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 128, 1);
+  ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 128, 128, 1)
+                       : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, 128, 1));
+  ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
+  if (!ok) return 4;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = a_kmajor ? 0 : 1;
+  p.b_mn = b_kmajor ? 0 : 1;
+  p.accumulate = accumulate;
+  p.D = D; p.ldd = ldd;
+  p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = dequant_a; p.scale_b = dequant_b;
+  p.tiles_n = (N + BN - 1) / BN;
+  p.tiles_m = (M + 255) / 256;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  int clusters = g_num_sms / 2;
+  if (p.num_tiles < clusters) clusters = p.num_tiles;
+  gemm_tcgen05_2cta_kernel<true><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
   count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }

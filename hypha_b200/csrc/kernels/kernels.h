@@ -86,6 +86,13 @@ void bf16_to_master(const bf16* p, float* master, int64_t n, cudaStream_t s);
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
                       cudaStream_t s);
+// fp8 (kind::f8f6f4): D (+)= (*dequant_a * *dequant_b) * (A . B); formats 0 = e4m3, 1 = e5m2.
+int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, int K, int lda,
+                     int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,
+                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s);
+void amax_bf16(const bf16* x, int64_t n, float* amax, cudaStream_t s);
+void quantize_fp8(const bf16* x, uint8_t* out, int64_t n, const float* amax, float* dequant, int fmt,
+                  cudaStream_t s);
 const char* gemm_last_error();
 void gemm_set_cta_mode(int mode);   // 1 = single-CTA tiles, 2 = cta_group::2 CTA pairs
 int gemm_get_cta_mode();

@@ -200,6 +200,21 @@ __device__ __forceinline__ void umma_bf16_ss_2cta(uint32_t d_tmem, uint64_t a_de
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// kind::f8f6f4 instruction descriptor: fp8 inputs (0 = e4m3, 1 = e5m2), fp32 accumulate.
+__host__ __device__ constexpr uint32_t umma_idesc_fp8(int m, int n, int a_mn_major, int b_mn_major,
+                                                      int a_fmt, int b_fmt) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_fp8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // Arrive (once) on the same-offset mbarrier of every CTA in `cta_mask` when prior MMAs retire.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile(

@@ -1,11 +1,13 @@
 """sm_100a op library: differentiable wrappers (functional) + native loader."""
-from .functional import (add_norm_linear, add_rmsnorm, attention_qkv, get_attention_backend,
+from .functional import (E4M3, E5M2, bump_fp8_weight_version, fp8_enabled, gemm_fp8, quantize_fp8, set_fp8,
+                         add_norm_linear, add_rmsnorm, attention_qkv, get_attention_backend,
                          set_attention_backend, swiglu_linear, cross_entropy_inplace, embedding, gemm,
                          get_gemm_backend, linear, linear_cross_entropy, rmsnorm, rope_qkv,
                          rope_tables, set_gemm_backend, swiglu)
 from .native import launch_count, load_C, load_core, reset_launch_count
 
 __all__ = [
+    "E4M3", "E5M2", "bump_fp8_weight_version", "fp8_enabled", "gemm_fp8", "quantize_fp8", "set_fp8",
     "add_norm_linear", "add_rmsnorm", "attention_qkv", "get_attention_backend", "set_attention_backend",
     "swiglu_linear", "cross_entropy_inplace", "embedding", "gemm",
     "get_gemm_backend", "linear", "linear_cross_entropy", "rmsnorm", "rope_qkv", "rope_tables",

@@ -85,6 +85,103 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
     return out
 
 
+# -----------------------------------------------------------------------------
+# fp8 (kind::f8f6f4) path: per-tensor current scaling, e4m3 forward operands, e5m2 gradients
+# -----------------------------------------------------------------------------
+_FP8 = os.environ.get("HYPHA_FP8", "0") == "1"
+_FP8_WEIGHT_VERSION = 0
+E4M3, E5M2 = 0, 1
+
+
+def set_fp8(enabled: bool) -> None:
+    """Run Linear-layer GEMMs (fwd, dgrad, wgrad) in fp8 on the tcgen05 ``kind::f8f6f4`` kernel.
+    Master weights, gradients written to ``main_grad``, the optimizer and the DiLoCo outer step stay
+    bf16/fp32 (BASELINE config 3: fp8 inner steps, bf16 outer all-reduce)."""
+    global _FP8
+    _FP8 = bool(enabled)
+
+
+def fp8_enabled() -> bool:
+    return _FP8
+
+
+def bump_fp8_weight_version() -> None:
+    """Called by the optimizer after it rewrote the bf16 weights: cached fp8 copies are stale."""
+    global _FP8_WEIGHT_VERSION
+    _FP8_WEIGHT_VERSION += 1
+
+
+def quantize_fp8(x: torch.Tensor, fmt: int = E4M3) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(q, dequant)``: ``q = fp8(x * fmax/amax(x))`` as uint8, ``dequant = amax/fmax`` (device fp32[1])."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
+    C = load_C()
+    s = cuda_stream()
+    st = torch.empty(2, dtype=torch.float32, device=x.device)
+    q = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    C.amax_bf16(x.data_ptr(), x.numel(), st.data_ptr(), s)
+    C.quantize_fp8(x.data_ptr(), q.data_ptr(), x.numel(), st.data_ptr(), st.data_ptr() + 4, fmt, s)
+    return q, st[1:2]
+
+
+def _weight_fp8(weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    cache = getattr(weight, "_fp8_cache", None)
+    if cache is not None and cache[0] == _FP8_WEIGHT_VERSION:
+        return cache[1], cache[2]
+    q, dq = quantize_fp8(weight.detach(), E4M3)
+    weight._fp8_cache = (_FP8_WEIGHT_VERSION, q, dq)
+    return q, dq
+
+
+def gemm_fp8(aq: torch.Tensor, a_dq: torch.Tensor, bq: torch.Tensor, b_dq: torch.Tensor, *, a_kmajor: bool = True,
+             b_kmajor: bool = True, a_fmt: int = E4M3, b_fmt: int = E4M3, out: Optional[torch.Tensor] = None,
+             accumulate: bool = False) -> torch.Tensor:
+    """``D (+)= dq_a*dq_b * (A . B)`` with uint8-stored fp8 operands -> bf16."""
+    M, K = (aq.shape[0], aq.shape[1]) if a_kmajor else (aq.shape[1], aq.shape[0])
+    N, Kb = (bq.shape[0], bq.shape[1]) if b_kmajor else (bq.shape[1], bq.shape[0])
+    assert K == Kb
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=aq.device)
+        accumulate = False
+    load_C().gemm_fp8(aq.data_ptr(), bq.data_ptr(), out.data_ptr(), M, N, K, aq.stride(0), bq.stride(0),
+                      out.stride(0), int(a_kmajor), int(b_kmajor), a_fmt, b_fmt, a_dq.data_ptr(), b_dq.data_ptr(),
+                      int(accumulate), cuda_stream())
+    return out
+
+
+def _fp8_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (_FP8 and x2.is_cuda and x2.dtype == torch.bfloat16 and x2.shape[0] % 16 == 0
+            and x2.shape[1] % 16 == 0 and weight.shape[0] % 16 == 0)
+
+
+def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """y = x2 @ weight.T on the bf16 or fp8 tensor-core path."""
+    if _fp8_ok(x2, weight):
+        xq, xdq = quantize_fp8(x2, E4M3)
+        wq, wdq = _weight_fp8(weight)
+        return gemm_fp8(xq, xdq, wq, wdq)
+    return gemm(x2, weight)
+
+
+def _mm_bwd(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor, need_dx: bool = True,
+            dx_out: Optional[torch.Tensor] = None):
+    """(dx, dW) for y = x2 @ weight.T.  dW goes to ``weight.main_grad`` when present (returns None)."""
+    mg = getattr(weight, "main_grad", None)
+    acc = bool(getattr(weight, "grad_accumulate", False)) if mg is not None else False
+    if _fp8_ok(x2, weight) and dy2.shape[1] % 16 == 0:
+        dyq, dydq = quantize_fp8(dy2, E5M2)
+        xq, xdq = quantize_fp8(x2, E4M3)
+        dw = gemm_fp8(dyq, dydq, xq, xdq, a_kmajor=False, b_kmajor=False, a_fmt=E5M2, b_fmt=E4M3, out=mg,
+                      accumulate=acc)
+        dx = None
+        if need_dx:
+            wq, wdq = _weight_fp8(weight)
+            dx = gemm_fp8(dyq, dydq, wq, wdq, a_kmajor=True, b_kmajor=False, a_fmt=E5M2, b_fmt=E4M3, out=dx_out)
+        return dx, (None if mg is not None else dw)
+    dw = _wgrad_into(weight, dy2, x2)
+    dx = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=dx_out) if need_dx else None
+    return dx, dw
+
+
 def _wgrad_into(param: torch.Tensor, dy2: torch.Tensor, x2: torch.Tensor) -> Optional[torch.Tensor]:
     """dW[N,K] = dy^T . x ; written into ``param.main_grad`` when present."""
     mg = getattr(param, "main_grad", None)
@@ -99,7 +196,7 @@ class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight):
         x2 = x.reshape(-1, x.shape[-1])
-        y = gemm(x2, weight)
+        y = _mm_fwd(x2, weight)
         ctx.save_for_backward(x2, weight)
         ctx.x_shape = x.shape
         return y if x.dim() == 2 else y.view(*x.shape[:-1], weight.shape[0])
@@ -110,10 +207,9 @@ class _Linear(torch.autograd.Function):
         dy2 = dy.reshape(-1, dy.shape[-1])
         if dy2.stride(1) != 1 or dy2.stride(0) % 8 != 0:
             dy2 = dy2.contiguous()
-        dx = None
-        if ctx.needs_input_grad[0]:
-            dx = gemm(dy2, weight, a_kmajor=True, b_kmajor=False).view(ctx.x_shape)
-        dw = _wgrad_into(weight, dy2, x2) if ctx.needs_input_grad[1] else None
+        dx, dw = _mm_bwd(dy2, x2, weight, need_dx=ctx.needs_input_grad[0])
+        if dx is not None:
+            dx = dx.view(ctx.x_shape)
         return dx, dw
 
 
@@ -243,7 +339,7 @@ def _norm_linear_fwd(x, residual, norm_w, weight, eps):
         h = x
         C.rmsnorm_fwd(x.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), rstd.data_ptr(), rows, cols, eps,
                       cuda_stream())
-    return gemm(n, weight), h, rstd
+    return _mm_fwd(n, weight), h, rstd
 
 
 def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
@@ -253,8 +349,10 @@ def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
     n = torch.empty_like(h)
     C.rmsnorm_fwd(h.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), 0, rows, cols, eps, s)
     dy2 = dy if dy.is_contiguous() else dy.contiguous()
-    dw = _wgrad_into(weight, dy2, n)
-    dn = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=n)            # reuse the buffer
+    if _fp8_ok(n, weight):
+        dn, dw = _mm_bwd(dy2, n, weight)
+    else:
+        dn, dw = _mm_bwd(dy2, n, weight, dx_out=n)                           # reuse the buffer
     dx = torch.empty_like(h)
     nparts = C.rmsnorm_bwd_num_partials(rows)
     partial = torch.empty((nparts, cols), dtype=torch.float32, device=h.device)
@@ -324,7 +422,7 @@ class _SwiGLULinear(torch.autograd.Function):
         rows, two_i = gu.shape
         act = torch.empty((rows, two_i // 2), dtype=gu.dtype, device=gu.device)
         load_C().swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, two_i // 2, cuda_stream())
-        y = gemm(act, weight)
+        y = _mm_fwd(act, weight)
         ctx.save_for_backward(gu, weight)
         return y
 
@@ -338,8 +436,10 @@ class _SwiGLULinear(torch.autograd.Function):
         act = torch.empty((rows, inter), dtype=gu.dtype, device=gu.device)
         C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, inter, s)
         dy2 = dy if dy.is_contiguous() else dy.contiguous()
-        dw = _wgrad_into(weight, dy2, act)
-        dact = gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=act)
+        if _fp8_ok(act, weight):
+            dact, dw = _mm_bwd(dy2, act, weight)
+        else:
+            dact, dw = _mm_bwd(dy2, act, weight, dx_out=act)
         dgu = torch.empty_like(gu)
         C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
         return dgu, dw

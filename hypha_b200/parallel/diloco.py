@@ -140,6 +140,9 @@ class FlatAdamW:
                             self.m.data_ptr(), self.v.data_ptr(), int(c.state_dtype == "bf16"),
                             self.params.numel(), lr, c.betas[0], c.betas[1], c.eps, c.weight_decay,
                             bc1, bc2, grad_scale, (t * 2654435761) & 0xFFFFFFFF, cuda_stream())
+        from ..ops.functional import bump_fp8_weight_version
+
+        bump_fp8_weight_version()           # cached fp8 weight copies are stale now
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {"master": self.master, "m": self.m, "v": self.v,
@@ -256,6 +259,9 @@ class DiLoCoOuter:
             opt.master.copy_(self.theta_outer)
             opt.params.copy_(self.theta_outer)
         self.round += 1
+        from ..ops.functional import bump_fp8_weight_version
+
+        bump_fp8_weight_version()
 
     # -- fault tolerance ------------------------------------------------------------------------
     def members(self) -> List[int]:

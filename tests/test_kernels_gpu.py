@@ -358,3 +358,64 @@ def test_llama_matches_reference_autograd(C):
     for name, p in ref.named_flat_parameters().items():
         got = net.named_flat_parameters()[name].main_grad
         assert _rel(got.cpu(), p.grad) < 6e-2, name
+
+
+@pytest.mark.parametrize("a_k,b_k", [(True, True), (True, False), (False, False), (False, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (512, 1024, 384), (1008, 528, 272), (2048, 4096, 4096)])
+def test_gemm_fp8(C, a_k, b_k, M, N, K):
+    """kind::f8f6f4 GEMM vs an fp32 matmul of the SAME quantised operands (exact up to fp32
+    accumulation order), plus an end-to-end error bound vs the unquantised product."""
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    a = A if a_k else A.t().contiguous()
+    b = B if b_k else B.t().contiguous()
+    aq, adq = ops.quantize_fp8(a, ops.E5M2)
+    bq, bdq = ops.quantize_fp8(b, ops.E4M3)
+    out = ops.gemm_fp8(aq, adq, bq, bdq, a_kmajor=a_k, b_kmajor=b_k, a_fmt=ops.E5M2, b_fmt=ops.E4M3)
+    af = aq.view(torch.float8_e5m2).float() * adq
+    bf = bq.view(torch.float8_e4m3fn).float() * bdq
+    Af = af if a_k else af.t()
+    Bf = bf if b_k else bf.t()
+    ref_q = Af @ Bf.t()
+    assert _rel(out, ref_q) < 5e-3, _rel(out, ref_q)
+    assert _rel(out, A.float() @ B.float().t()) < 0.12
+    # accumulate into an existing bf16 output
+    D0 = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    o2 = D0.clone()
+    ops.gemm_fp8(aq, adq, bq, bdq, a_kmajor=a_k, b_kmajor=b_k, a_fmt=ops.E5M2, b_fmt=ops.E4M3, out=o2, accumulate=True)
+    assert _rel(o2, D0.float() + ref_q) < 5e-3
+
+
+def test_quantize_fp8_roundtrip(C):
+    from hypha_b200 import ops
+
+    x = (torch.randn(4096, 512, device="cuda") * 3).to(torch.bfloat16)
+    for fmt, dt, tol in ((ops.E4M3, torch.float8_e4m3fn, 0.04), (ops.E5M2, torch.float8_e5m2, 0.08)):
+        q, dq = ops.quantize_fp8(x, fmt)
+        back = q.view(dt).float() * dq
+        assert _rel(back, x) < tol
+        assert abs(dq.item() - x.abs().max().item() / (448.0 if fmt == ops.E4M3 else 57344.0)) < 1e-6 * max(1, dq.item())
+
+
+def test_llama_fp8_step_close_to_bf16(C):
+    from hypha_b200 import ops
+    from hypha_b200.models.llama import LlamaForCausalLM, get_config
+
+    torch.manual_seed(0)
+    cfg = get_config("llama-tiny")
+    ids = torch.randint(0, cfg.vocab_size, (2, 128), device="cuda")
+    lab = torch.roll(ids, -1, 1)
+    losses, grads = [], []
+    for fp8 in (False, True):
+        ops.set_fp8(fp8)
+        net = LlamaForCausalLM(cfg, device="cuda", seed=5)
+        loss = net(ids, lab)
+        loss.backward()
+        losses.append(loss.item())
+        grads.append(net.flat.grad.float().clone())
+    ops.set_fp8(False)
+    assert abs(losses[0] - losses[1]) < 0.05, losses
+    assert _rel(grads[1], grads[0]) < 0.2
