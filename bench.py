@@ -41,7 +41,7 @@ def parse_args():
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
-    ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2"])
+    ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2", "tcgen05"])
     return ap.parse_args()
 
 

@@ -97,6 +97,11 @@ const char* gemm_last_error();
 void gemm_set_cta_mode(int mode);   // 1 = single-CTA tiles, 2 = cta_group::2 CTA pairs
 int gemm_get_cta_mode();
 
+// ---- tcgen05 flash-attention forward (attention_tcgen05.cu) ------------------------------------
+int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int batch, int seq, int n_heads, int n_kv,
+                          int head_dim, int qkv_stride, int out_stride, float scale, cudaStream_t s);
+const char* attention_last_error();
+
 unsigned long long launch_count();
 void reset_launch_count();
 }  // namespace hb

@@ -123,7 +123,14 @@ def quantize_fp8(x: torch.Tensor, fmt: int = E4M3) -> Tuple[torch.Tensor, torch.
     return q, st[1:2]
 
 
+_FP8_CACHE_WEIGHTS = os.environ.get("HYPHA_FP8_CACHE", "1") == "1"
+
+
 def _weight_fp8(weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """fp8 copy of a weight; cached until the optimizer rewrites the weights (costs 1 byte/param;
+    HYPHA_FP8_CACHE=0 re-quantises on every use instead)."""
+    if not _FP8_CACHE_WEIGHTS:
+        return quantize_fp8(weight.detach(), E4M3)
     cache = getattr(weight, "_fp8_cache", None)
     if cache is not None and cache[0] == _FP8_WEIGHT_VERSION:
         return cache[1], cache[2]
@@ -592,6 +599,48 @@ class _FlashAttnQKV(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+class _TcgenAttnQKV(torch.autograd.Function):
+    """Forward on the hand-written tcgen05 flash-attention kernel (reads q/k/v straight out of the
+    fused qkv activation through TMA, emits O and log-sum-exp); backward through flash-attn 2's
+    kernel, which consumes exactly (q, k, v, O, lse, dO)."""
+
+    @staticmethod
+    def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim):
+        scale = 1.0 / math.sqrt(head_dim)
+        out = torch.empty((batch * seq, n_heads * head_dim), dtype=qkv.dtype, device=qkv.device)
+        lse = torch.empty((batch, n_heads, seq), dtype=torch.float32, device=qkv.device)
+        load_C().attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), batch, seq, n_heads, n_kv, head_dim,
+                               qkv.stride(0), out.stride(0), scale, cuda_stream())
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.dims = (batch, seq, n_heads, n_kv, head_dim, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from flash_attn.flash_attn_interface import _flash_attn_backward
+
+        qkv, out, lse = ctx.saved_tensors
+        batch, seq, n_heads, n_kv, head_dim, scale = ctx.dims
+        sl = lambda t, a, b, hh: t[:, a * head_dim: b * head_dim].view(batch, seq, hh, head_dim)
+        q, k, v = sl(qkv, 0, n_heads, n_heads), sl(qkv, n_heads, n_heads + n_kv, n_kv), sl(qkv, n_heads + n_kv, n_heads + 2 * n_kv, n_kv)
+        dqkv = torch.empty_like(qkv)
+        dq, dk, dv = sl(dqkv, 0, n_heads, n_heads), sl(dqkv, n_heads, n_heads + n_kv, n_kv), sl(dqkv, n_heads + n_kv, n_heads + 2 * n_kv, n_kv)
+        do = dout.contiguous().view(batch, seq, n_heads, head_dim)
+        rng = torch.zeros(2, dtype=torch.int64, device=qkv.device)
+        _flash_attn_backward(do, q, k, v, out.view(batch, seq, n_heads, head_dim), lse, dq, dk, dv, 0.0, scale, True,
+                             -1, -1, 0.0, None, False, rng)
+        return dqkv, None, None, None, None, None
+
+
+def attention_fwd_tcgen05(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int):
+    """Raw forward: returns ``(out [tokens, Hq*D], lse [B, Hq, S])``."""
+    out = torch.empty((batch * seq, n_heads * head_dim), dtype=qkv.dtype, device=qkv.device)
+    lse = torch.empty((batch, n_heads, seq), dtype=torch.float32, device=qkv.device)
+    load_C().attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), batch, seq, n_heads, n_kv, head_dim,
+                           qkv.stride(0), out.stride(0), 1.0 / math.sqrt(head_dim), cuda_stream())
+    return out, lse
+
+
 _ATTN_BACKEND = os.environ.get("HYPHA_ATTN", "cudnn")
 
 
@@ -599,7 +648,7 @@ def set_attention_backend(name: str) -> None:
     """``cudnn`` (cuDNN fused attention through torch SDPA; library), ``flash2`` (flash-attn 2
     mma.sync kernels; library) -- the hand-written tcgen05 attention replaces both."""
     global _ATTN_BACKEND
-    if name not in ("cudnn", "flash2"):
+    if name not in ("cudnn", "flash2", "tcgen05"):
         raise ValueError(name)
     _ATTN_BACKEND = name
 
@@ -627,6 +676,8 @@ def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: i
         return _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "cudnn":
         return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)
+    if _ATTN_BACKEND == "tcgen05" and head_dim == 128 and seq % 128 == 0:
+        return _TcgenAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
     return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
 
 

@@ -419,3 +419,40 @@ def test_llama_fp8_step_close_to_bf16(C):
     ops.set_fp8(False)
     assert abs(losses[0] - losses[1]) < 0.05, losses
     assert _rel(grads[1], grads[0]) < 0.2
+
+
+@pytest.mark.parametrize("B,S,Hq,Hk", [(1, 128, 2, 1), (2, 512, 8, 2), (1, 1024, 4, 4)])
+def test_attention_fwd_tcgen05(C, B, S, Hq, Hk):
+    """Hand-written tcgen05 flash-attention forward vs fp32 SDPA reference (output and lse)."""
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _attention_ref
+
+    torch.manual_seed(0)
+    D = 128
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16)
+    out, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
+    ref = _attention_ref(qkv.float(), B, S, Hq, Hk, D)
+    assert _rel(out, ref) < 2e-2, _rel(out, ref)
+    q = qkv[:, : Hq * D].view(B, S, Hq, D).transpose(1, 2).float()
+    k = qkv[:, Hq * D: (Hq + Hk) * D].view(B, S, Hk, D).transpose(1, 2).float().repeat_interleave(Hq // Hk, 1)
+    sc = (q @ k.transpose(-1, -2)) / math.sqrt(D)
+    sc = sc.masked_fill(torch.triu(torch.ones(S, S, device="cuda", dtype=torch.bool), 1), float("-inf"))
+    assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2, rtol=1e-2)
+
+
+def test_attention_tcgen05_backend_grad(C):
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _attention_ref
+
+    ops.set_attention_backend("tcgen05")
+    torch.manual_seed(0)
+    B, S, Hq, Hk, D = 2, 256, 8, 2, 128
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
+    d = torch.randn_like(out)
+    out.backward(d)
+    ops.set_attention_backend("cudnn")
+    qf = qkv.detach().float().requires_grad_(True)
+    of = _attention_ref(qf, B, S, Hq, Hk, D)
+    of.backward(d.float())
+    assert _rel(out, of) < 2e-2 and _rel(qkv.grad, qf.grad) < 3e-2
