@@ -143,25 +143,61 @@ def main():
     ops.set_fp8(args.fp8)
     if args.impl == "baseline":
         ops.set_gemm_backend("cublas")
-    cfg = get_config(args.model)
-    recompute = args.recompute_layers
-    if recompute < 0:
-        recompute = cfg.num_layers if cfg.num_params() > 4e9 else 0
-    cfg = get_config(args.model, recompute_layers=recompute, max_seq_len=max(args.seq_len, 8))
+    base_cfg = get_config(args.model)
     group = PeerGroup.from_torch_distributed(local_rank) if world > 1 else None
     outer_backend = args.outer_backend
     if args.impl == "baseline" and world > 1:
         outer_backend = "nccl"
-    trainer = DiLoCoTrainer.create(
-        cfg, adamw=AdamWConfig(lr=1e-4, state_dtype=args.state_dtype),
-        diloco=DiLoCoConfig(inner_steps=args.inner_steps, backend=outer_backend), group=group,
-        device=local_rank, seed=1234)
-
     B, S = args.micro_batch, args.seq_len
-    tokens_per_step = B * S * world
-    g = torch.Generator().manual_seed(1000 + rank)
-    pool = [torch.randint(0, cfg.vocab_size, (B, S), generator=g).pin_memory() for _ in range(4)]
+    g0 = torch.Generator().manual_seed(1000 + rank)
+    pool = [torch.randint(0, base_cfg.vocab_size, (B, S), generator=g0).pin_memory() for _ in range(4)]
     lab_pool = [torch.roll(t, -1, 1).pin_memory() for t in pool]
+
+    def make_trainer(recompute):
+        c = get_config(args.model, recompute_layers=recompute, max_seq_len=max(args.seq_len, 8))
+        return c, DiLoCoTrainer.create(
+            c, adamw=AdamWConfig(lr=1e-4, state_dtype=args.state_dtype),
+            diloco=DiLoCoConfig(inner_steps=args.inner_steps, backend=outer_backend), group=group,
+            device=local_rank, seed=1234)
+
+    # Memory plan: no layer recomputation if it fits; otherwise recompute just enough layers.  Every
+    # rank must agree, so an OOM on any rank moves all ranks to the next candidate.
+    if args.recompute_layers >= 0:
+        candidates = [args.recompute_layers]
+    elif base_cfg.num_params() > 4e9:
+        candidates = [0, 4, 8, 16, base_cfg.num_layers]
+    else:
+        candidates = [0]
+    trainer = cfg = None
+    for recompute in candidates:
+        ok = 1
+        try:
+            cfg, trainer = make_trainer(recompute)
+            for i in range(2):
+                trainer.step(pool[i % 4], lab_pool[i % 4])
+            trainer.read_loss()
+        except torch.OutOfMemoryError:
+            ok = 0
+        if world > 1:
+            t = torch.tensor([ok], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = int(t.item())
+        if ok:
+            break
+        if rank == 0:
+            print(f"[bench] recompute_layers={recompute} does not fit, trying the next setting", file=sys.stderr)
+        trainer = None
+        if group is not None:
+            group.close()
+            group = PeerGroup.from_torch_distributed(local_rank)
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+    if trainer is None:
+        raise SystemExit("no memory configuration fits")
+
+    tokens_per_step = B * S * world
     dev_pool = [(a.to(dev), b.to(dev)) for a, b in zip(pool, lab_pool)]
 
     def barrier():

@@ -657,16 +657,54 @@ def get_attention_backend() -> str:
     return _ATTN_BACKEND
 
 
-def _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim):
-    from torch.nn.attention import SDPBackend, sdpa_kernel
-
-    T = batch * seq
+def _sdpa_views(qkv, batch, seq, n_heads, n_kv, head_dim):
     q = qkv[:, : n_heads * head_dim].view(batch, seq, n_heads, head_dim).transpose(1, 2)
     k = qkv[:, n_heads * head_dim: (n_heads + n_kv) * head_dim].view(batch, seq, n_kv, head_dim).transpose(1, 2)
     v = qkv[:, (n_heads + n_kv) * head_dim:].view(batch, seq, n_kv, head_dim).transpose(1, 2)
+    return q, k, v
+
+
+def _sdpa_call(q, k, v, gqa: bool):
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
     with sdpa_kernel([SDPBackend.CUDNN_ATTENTION, SDPBackend.FLASH_ATTENTION]):
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=(n_kv != n_heads))
-    return o.transpose(1, 2).reshape(T, n_heads * head_dim)
+        return F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=gqa)
+
+
+class _CudnnAttnQKV(torch.autograd.Function):
+    """cuDNN fused attention (library) on views of the fused qkv activation.  The inner SDPA graph is
+    kept private so backward receives dq/dk/dv as three tensors and assembles ``dqkv`` with ONE
+    concatenation instead of autograd's three zero-fills + three slice copies + two adds."""
+
+    @staticmethod
+    def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim):
+        with torch.enable_grad():
+            base = qkv.detach()
+            q, k, v = (t.requires_grad_() for t in _sdpa_views(base, batch, seq, n_heads, n_kv, head_dim))
+            o = _sdpa_call(q, k, v, n_kv != n_heads)
+        ctx.inner = (q, k, v, o)
+        ctx.dims = (batch, seq, n_heads, n_kv, head_dim)
+        return o.detach().transpose(1, 2).reshape(batch * seq, n_heads * head_dim)
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, o = ctx.inner
+        ctx.inner = None
+        batch, seq, n_heads, n_kv, head_dim = ctx.dims
+        do = dout.view(batch, seq, n_heads, head_dim).transpose(1, 2)
+        dq, dk, dv = torch.autograd.grad(o, (q, k, v), do)
+        T = batch * seq
+        dqkv = torch.cat([dq.transpose(1, 2).reshape(T, -1), dk.transpose(1, 2).reshape(T, -1),
+                          dv.transpose(1, 2).reshape(T, -1)], dim=1)
+        return dqkv, None, None, None, None, None
+
+
+def _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim):
+    if torch.is_grad_enabled() and qkv.requires_grad:
+        return _CudnnAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+    q, k, v = _sdpa_views(qkv, batch, seq, n_heads, n_kv, head_dim)
+    o = _sdpa_call(q, k, v, n_kv != n_heads)
+    return o.transpose(1, 2).reshape(batch * seq, n_heads * head_dim)
 
 
 def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int,

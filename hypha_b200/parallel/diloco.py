@@ -247,17 +247,23 @@ class DiLoCoOuter:
         else:
             import torch.distributed as dist
 
-            delta = (opt.master - self.theta_outer).to(torch.bfloat16)
+            CH = 1 << 28                       # chunked so the unfused baseline fits next to an 8B model
+            delta = torch.empty(self.n, dtype=torch.bfloat16, device=opt.master.device)
+            for a in range(0, self.n, CH):
+                b = min(self.n, a + CH)
+                delta[a:b] = (opt.master[a:b] - self.theta_outer[a:b]).to(torch.bfloat16)
             dist.all_reduce(delta, group=self.process_group)
-            g = delta.float().div_(self.world)
-            if first:
-                self.momentum.copy_(g)
-            else:
-                self.momentum.mul_(cfg.outer_momentum).add_(g)
-            upd = (self.momentum * cfg.outer_momentum).add_(g).mul_(cfg.outer_lr)
-            self.theta_outer.add_(upd)
-            opt.master.copy_(self.theta_outer)
-            opt.params.copy_(self.theta_outer)
+            for a in range(0, self.n, CH):
+                b = min(self.n, a + CH)
+                g = delta[a:b].float().div_(self.world)
+                if first:
+                    self.momentum[a:b].copy_(g)
+                else:
+                    self.momentum[a:b].mul_(cfg.outer_momentum).add_(g)
+                self.theta_outer[a:b].add_((self.momentum[a:b] * cfg.outer_momentum).add_(g).mul_(cfg.outer_lr))
+                opt.master[a:b].copy_(self.theta_outer[a:b])
+                opt.params[a:b].copy_(self.theta_outer[a:b])
+            del delta
         self.round += 1
         from ..ops.functional import bump_fp8_weight_version
 
