@@ -19,8 +19,8 @@ void reset_launch_count() { g_launch_count = 0; }
 //   h = x (+ res_in) ; res_out = h ; y = h * rsqrt(mean(h^2)+eps) * w
 // One CTA per row; the row stays in registers between the two passes.
 // =============================================================================
-template <int kMaxVec>
-__global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(
+template <int kThr, int kMaxVec>
+__global__ void __launch_bounds__(kThr) rmsnorm_fwd_kernel(
     const bf16* __restrict__ x, const bf16* __restrict__ res_in, bf16* __restrict__ res_out,
     const bf16* __restrict__ w, bf16* __restrict__ y, float* __restrict__ rstd_out, int cols,
     float eps) {
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(
   float ss = 0.f;
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j) {
-    const int i = threadIdx.x + j * 256;
+    const int i = threadIdx.x + j * kThr;
     if (i < nvec) {
       bf16x8 v = ld_bf16x8(x + base + (size_t)i * 8);
       unpack8(v, h[j]);
@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(256) rmsnorm_fwd_kernel(
   if (threadIdx.x == 0 && rstd_out != nullptr) rstd_out[row] = rstd;
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j) {
-    const int i = threadIdx.x + j * 256;
+    const int i = threadIdx.x + j * kThr;
     if (i < nvec) {
       float wv[8], o[8];
       unpack8(ld_bf16x8(w + (size_t)i * 8), wv);
@@ -69,12 +69,15 @@ void rmsnorm_fwd(const bf16* x, const bf16* res_in, bf16* res_out, const bf16* w
                  float* rstd, int rows, int cols, float eps, cudaStream_t s) {
   if (rows == 0) return;
   const int nvec = cols / 8;
+  // one 16-byte vector per thread whenever possible: small register footprint -> full occupancy
   if (nvec <= 256) {
-    rmsnorm_fwd_kernel<1><<<rows, 256, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
+    rmsnorm_fwd_kernel<256, 1><<<rows, 256, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
   } else if (nvec <= 512) {
-    rmsnorm_fwd_kernel<2><<<rows, 256, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
+    rmsnorm_fwd_kernel<512, 1><<<rows, 512, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
+  } else if (nvec <= 1024) {
+    rmsnorm_fwd_kernel<512, 2><<<rows, 512, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
   } else {
-    rmsnorm_fwd_kernel<4><<<rows, 256, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
+    rmsnorm_fwd_kernel<512, 4><<<rows, 512, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
   }
   count_launch();
 }
@@ -86,8 +89,8 @@ void rmsnorm_fwd(const bf16* x, const bf16* res_in, bf16* res_out, const bf16* w
 //   xhat = x*rstd ; g = dy*w ; c = mean(g*xhat)
 //   dx = rstd*(g - xhat*c) (+ dres_in) ; dW += dy*xhat
 // =============================================================================
-template <int kMaxVec>
-__global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(
+template <int kThr, int kMaxVec>
+__global__ void __launch_bounds__(kThr) rmsnorm_bwd_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
     const float* __restrict__ rstd, const bf16* __restrict__ dres_in, bf16* __restrict__ dx,
     float* __restrict__ dw_partial, int rows, int cols) {
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(
   float wv[kMaxVec][8], dwacc[kMaxVec][8];
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j) {
-    const int i = threadIdx.x + j * 256;
+    const int i = threadIdx.x + j * kThr;
 #pragma unroll
     for (int e = 0; e < 8; ++e) { dwacc[j][e] = 0.f; wv[j][e] = 0.f; }
     if (i < nvec) unpack8(ld_bf16x8(w + (size_t)i * 8), wv[j]);
@@ -108,7 +111,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(
     float dot = 0.f;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
-      const int i = threadIdx.x + j * 256;
+      const int i = threadIdx.x + j * kThr;
       if (i < nvec) {
         float dyv[8], xv[8];
         unpack8(ld_stream_bf16x8(dy + base + (size_t)i * 8), dyv);
@@ -126,7 +129,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(
     const float c = dot / (float)cols;
 #pragma unroll
     for (int j = 0; j < kMaxVec; ++j) {
-      const int i = threadIdx.x + j * 256;
+      const int i = threadIdx.x + j * kThr;
       if (i < nvec) {
         float o[8];
 #pragma unroll
@@ -144,7 +147,7 @@ __global__ void __launch_bounds__(256) rmsnorm_bwd_kernel(
   float* out = dw_partial + (size_t)blockIdx.x * cols;
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j) {
-    const int i = threadIdx.x + j * 256;
+    const int i = threadIdx.x + j * kThr;
     if (i < nvec) {
       *reinterpret_cast<float4*>(out + (size_t)i * 8) =
           make_float4(dwacc[j][0], dwacc[j][1], dwacc[j][2], dwacc[j][3]);
@@ -165,11 +168,13 @@ void rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd
   const int grid = rmsnorm_bwd_num_partials(rows);
   const int nvec = cols / 8;
   if (nvec <= 256) {
-    rmsnorm_bwd_kernel<1><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<256, 1><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else if (nvec <= 512) {
-    rmsnorm_bwd_kernel<2><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<512, 1><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+  } else if (nvec <= 1024) {
+    rmsnorm_bwd_kernel<512, 2><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else {
-    rmsnorm_bwd_kernel<4><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   }
   count_launch();
 }
@@ -250,22 +255,21 @@ void rope_inplace(bf16* qkv, const float* cos, const float* sin, int tokens, int
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ gu,
                                                          bf16* __restrict__ out, int rows,
                                                          int inter) {
+  // grid.y strides over rows, grid.x over 8-element vectors of a row: no per-element div/mod
   const int vec_per_row = inter >> 3;
-  const int64_t total = (int64_t)rows * vec_per_row;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / vec_per_row;
-    const int v = (int)(idx % vec_per_row);
-    const bf16* gp = gu + r * 2 * inter + (int64_t)v * 8;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= vec_per_row) return;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const bf16* gp = gu + (int64_t)r * 2 * inter + (int64_t)v * 8;
     float g[8], u[8], o[8];
     unpack8(ld_stream_bf16x8(gp), g);
     unpack8(ld_stream_bf16x8(gp + inter), u);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float sg = 1.f / (1.f + __expf(-g[e]));
+      const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
       o[e] = g[e] * sg * u[e];
     }
-    st_bf16x8(out + r * inter + (int64_t)v * 8, pack8(o));
+    st_bf16x8(out + (int64_t)r * inter + (int64_t)v * 8, pack8(o));
   }
 }
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dout,
@@ -273,24 +277,22 @@ __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict_
                                                          bf16* __restrict__ dgu, int rows,
                                                          int inter) {
   const int vec_per_row = inter >> 3;
-  const int64_t total = (int64_t)rows * vec_per_row;
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t r = idx / vec_per_row;
-    const int v = (int)(idx % vec_per_row);
-    const bf16* gp = gu + r * 2 * inter + (int64_t)v * 8;
+  const int v = blockIdx.x * 256 + threadIdx.x;
+  if (v >= vec_per_row) return;
+  for (int r = blockIdx.y; r < rows; r += gridDim.y) {
+    const bf16* gp = gu + (int64_t)r * 2 * inter + (int64_t)v * 8;
     float g[8], u[8], d[8], dg[8], du[8];
     unpack8(ld_stream_bf16x8(gp), g);
     unpack8(ld_stream_bf16x8(gp + inter), u);
-    unpack8(ld_stream_bf16x8(dout + r * inter + (int64_t)v * 8), d);
+    unpack8(ld_stream_bf16x8(dout + (int64_t)r * inter + (int64_t)v * 8), d);
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      const float sg = 1.f / (1.f + __expf(-g[e]));
+      const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
       const float silu = g[e] * sg;
       du[e] = d[e] * silu;
       dg[e] = d[e] * u[e] * (sg + silu * (1.f - sg));
     }
-    bf16* op = dgu + r * 2 * inter + (int64_t)v * 8;
+    bf16* op = dgu + (int64_t)r * 2 * inter + (int64_t)v * 8;
     st_bf16x8(op, pack8(dg));
     st_bf16x8(op + inter, pack8(du));
   }
@@ -300,13 +302,19 @@ static int ew_grid(int64_t total) {
   const int64_t cap = (int64_t)kNumSMs * 16;
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
+static dim3 swiglu_grid(int rows, int inter) {
+  const int gx = (inter / 8 + 255) / 256;
+  int gy = rows < 8192 ? rows : 8192;
+  if (gy < 1) gy = 1;
+  return dim3(gx, gy);
+}
 void swiglu_fwd(const bf16* gu, bf16* out, int rows, int inter, cudaStream_t s) {
-  swiglu_fwd_kernel<<<ew_grid((int64_t)rows * (inter / 8)), 256, 0, s>>>(gu, out, rows, inter);
+  swiglu_fwd_kernel<<<swiglu_grid(rows, inter), 256, 0, s>>>(gu, out, rows, inter);
   count_launch();
 }
 void swiglu_bwd(const bf16* dout, const bf16* gu, bf16* dgu, int rows, int inter,
                 cudaStream_t s) {
-  swiglu_bwd_kernel<<<ew_grid((int64_t)rows * (inter / 8)), 256, 0, s>>>(dout, gu, dgu, rows, inter);
+  swiglu_bwd_kernel<<<swiglu_grid(rows, inter), 256, 0, s>>>(dout, gu, dgu, rows, inter);
   count_launch();
 }
 

@@ -58,6 +58,10 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
                      dht_server: bool = False, need_bootstrap: bool = True) -> Node:
     tel = Telemetry.from_config(f"hypha-{role}", cfg)
     C.load_tls(cfg)                         # accepted for parity; loopback links do not use mTLS
+    if peer_id is None and getattr(cfg, "key_pem", ""):
+        from .transport.utils import peer_id_from_key_pem
+
+        peer_id = peer_id_from_key_pem(cfg.key_pem)      # identity = public key, like the reference
     net = Network(peer_id or f"{role}-{M.new_id()[:8]}", agent=f"hypha-{role}", relay_server=relay_server,
                   dht_server=dht_server)
     tel.register_bandwidth(net.counters)

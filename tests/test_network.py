@@ -281,3 +281,48 @@ def test_pull_stream():
         assert await st.read_all() == blobs[1]
         await a.close(); await b.close()
     run(main())
+
+
+def test_batched_count_and_time_windows():
+    from hypha_b200.transport.utils import Batched
+
+    async def main():
+        q: asyncio.Queue = asyncio.Queue()
+
+        async def src():
+            while True:
+                x = await q.get()
+                if x is None:
+                    return
+                yield x
+
+        out = []
+
+        async def consume():
+            async for b in Batched(src(), 3, 0.1):
+                out.append(b)
+
+        t = asyncio.ensure_future(consume())
+        for i in range(4):
+            q.put_nowait(i)                      # 3 -> full batch, 1 left pending
+        await asyncio.sleep(0.25)                # window elapses -> partial batch flushed
+        q.put_nowait(9)
+        q.put_nowait(None)
+        await t
+        assert out == [[0, 1, 2], [3], [9]]
+    run(main())
+
+
+def test_cidr_helpers_and_identity(tmp_path):
+    from hypha_b200 import certutil as cu
+    from hypha_b200.transport.utils import RESERVED_IPV4, find_containing_cidr, is_excluded, peer_id_from_key_pem
+
+    assert find_containing_cidr("10.1.2.3", RESERVED_IPV4) == "10.0.0.0/8"
+    assert find_containing_cidr("8.8.8.8", RESERVED_IPV4) is None and not is_excluded("not-an-ip", RESERVED_IPV4)
+    assert is_excluded("::1", ["::1/128"])
+    d = str(tmp_path)
+    cu.make_root("o", out_dir=d)
+    cu.make_org(f"{d}/o-root-cert.pem", f"{d}/o-root-key.pem", "o", out_dir=d)
+    cu.make_node(f"{d}/o-ca-cert.pem", f"{d}/o-ca-key.pem", "n1", out_dir=d)
+    a, b = peer_id_from_key_pem(f"{d}/n1-key.pem"), peer_id_from_key_pem(f"{d}/n1-key.pem")
+    assert a == b and a.startswith("12D3Koo") and a != peer_id_from_key_pem(f"{d}/o-ca-key.pem")
