@@ -77,8 +77,12 @@ def main():
         fused = timed(outer.step, iters)
         st = outer.check()
         ar = timed(lambda: dist.all_reduce(g), iters)
-        th, mo = _Opt.master.clone(), torch.zeros(n, device=dev)
         CH = 1 << 28
+        try:
+            th, mo = _Opt.master.clone(), torch.zeros(n, device=dev)
+        except torch.OutOfMemoryError:
+            th = mo = None
+            torch.cuda.empty_cache()
 
         def nccl_full():
             d = torch.empty(n, device=dev, dtype=torch.bfloat16)
@@ -95,7 +99,7 @@ def main():
                 p[s:e].copy_(th[s:e])
 
         try:
-            full = timed(nccl_full, max(2, iters // 2))
+            full = timed(nccl_full, max(2, iters // 2)) if th is not None else None
         except torch.OutOfMemoryError:      # the unfused baseline needs ~10 more bytes/element
             full = None
             torch.cuda.empty_cache()

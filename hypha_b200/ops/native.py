@@ -38,6 +38,16 @@ def load_C():
 
 @lru_cache(maxsize=None)
 def load_core():
+    override = os.environ.get("HYPHA_CORE_OVERRIDE")        # e.g. the ASAN build from tools/sanitize.sh
+    if override:
+        import importlib.util
+        import glob
+
+        path = glob.glob(os.path.join(override, "_core*.so"))[0]
+        spec = importlib.util.spec_from_file_location("hypha_b200._core", path)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
     try:
         return importlib.import_module("hypha_b200._core")
     except ImportError as first:
