@@ -13,7 +13,7 @@
 //               MMA -> tcgen05.ld O_j and fold it into the fp32 register accumulator with the
 //               running rescale -> final normalise + store O and log-sum-exp
 // S_{j+1} is issued as soon as S_j has been read out of TMEM, so the QK^T of the next tile
-// overlaps the exponentials of the current one; two CTAs are co-resident per SM (112 KB smem,
+// overlaps the exponentials of the current one; two CTAs are co-resident per SM (96 KB smem,
 // 256 TMEM columns each) so one CTA's softmax hides under the other's MMAs.  `setmaxnreg`
 // moves registers from the producer/MMA warpgroup to the softmax warpgroup (128-float O row).
 //
@@ -33,7 +33,8 @@ using namespace sm100;
 constexpr int kD = 128;          // head dim
 constexpr int kBM = 128;         // q rows per CTA
 constexpr int kBN = 64;          // keys per tile
-constexpr int kKVStages = 2;
+constexpr int kKVStages = 2;         // K ring depth
+constexpr int kVStages = 1;          // V is single-buffered: 2 CTAs/SM must fit in 227 KB of smem
 constexpr int kQBytes = kBM * kD * 2;          // 32 KB (two 64-column swizzle atoms)
 constexpr int kKBytes = kBN * kD * 2;          // 16 KB
 constexpr int kVBytes = kBN * kD * 2;          // 16 KB
@@ -45,12 +46,18 @@ struct AttnSmem {
   static constexpr int q_off = 0;
   static constexpr int k_off = q_off + kQBytes;
   static constexpr int v_off = k_off + kKVStages * kKBytes;
-  static constexpr int p_off = v_off + kKVStages * kVBytes;
+  static constexpr int p_off = v_off + kVStages * kVBytes;
   static constexpr int bar_off = p_off + kPBytes;
   // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full, o_full, o_free, tmem ptr
   static constexpr int total = bar_off + 16 * 8;
 };
 constexpr int kAttnSmemBytes = AttnSmem::total + 1024;
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // one MUFU op; exp2f() adds range fix-ups
+  return y;
+}
 
 struct AttnParams {
   int batch, seq, n_heads, n_kv, q_tiles;
@@ -119,18 +126,22 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
       mbar_arrive_expect_tx(q_full, kQBytes);
       tma_load_2d(q_smem, &tma_q, q_full, q_col, row0);
       tma_load_2d(q_smem + kBM * 128, &tma_q, q_full, q_col + 64, row0);
-      for (int j = 0; j < n_tiles; ++j) {
+      auto load_k = [&](int j) {
         const int st = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         const int krow = b * p.seq + j * kBN;
-        mbar_wait(k_empty(st), ph ^ 1u);
+        mbar_wait(k_empty(st), ((uint32_t)(j >> 1) & 1u) ^ 1u);
         mbar_arrive_expect_tx(k_full(st), kKBytes);
         tma_load_2d(k_smem + st * kKBytes, &tma_kv, k_full(st), k_col, krow);
         tma_load_2d(k_smem + st * kKBytes + kBN * 128, &tma_kv, k_full(st), k_col + 64, krow);
-        mbar_wait(v_empty(st), ph ^ 1u);
-        mbar_arrive_expect_tx(v_full(st), kVBytes);
-        tma_load_2d(v_smem + st * kVBytes, &tma_kv, v_full(st), v_col, krow);
-        tma_load_2d(v_smem + st * kVBytes + kBN * 128, &tma_kv, v_full(st), v_col + 64, krow);
+      };
+      load_k(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        if (j + 1 < n_tiles) load_k(j + 1);                          // K runs one tile ahead of V
+        const int krow = b * p.seq + j * kBN;
+        mbar_wait(v_empty(0), ((uint32_t)j & 1u) ^ 1u);               // PV_{j-1} has consumed V
+        mbar_arrive_expect_tx(v_full(0), kVBytes);
+        tma_load_2d(v_smem, &tma_kv, v_full(0), v_col, krow);
+        tma_load_2d(v_smem + kBN * 128, &tma_kv, v_full(0), v_col + 64, krow);
       }
     } else if (warp == 1 && lane == 0) {
       // ====================== MMA issuer ========================
@@ -157,10 +168,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
         if (j + 1 < n_tiles) issue_s(j + 1);                        // overlaps softmax_j
         const int st = j & 1;
         mbar_wait(p_full, (uint32_t)j & 1u);
-        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
+        mbar_wait(v_full(0), (uint32_t)j & 1u);
         if (j > 0) mbar_wait(o_free, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
-        const uint32_t vb = v_smem + st * kVBytes;
+        const uint32_t vb = v_smem;
 #pragma unroll
         for (int kk = 0; kk < kBN / 16; ++kk) {
           const uint64_t ad = umma_smem_desc(p_smem + kk * 32, 16, 1024);                 // P: K-major, one atom
@@ -168,7 +179,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
           umma_bf16_ss(tmem_o, ad, bd, idesc_o, kk != 0 ? 1u : 0u);
         }
         umma_commit(o_full);
-        umma_commit(v_empty(st));
+        umma_commit(v_empty(0));
       }
     }
   } else {
@@ -205,12 +216,12 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
       }
       const float m_new = fmaxf(m_run, mx);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = exp2f(m_run - m_use);
+      const float alpha = fast_exp2(m_run - m_use);
       float sum = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        const float p0 = exp2f(x[c] - m_use), p1 = exp2f(x[c + 1] - m_use);
+        const float p0 = fast_exp2(x[c] - m_use), p1 = fast_exp2(x[c + 1] - m_use);
         sum += p0 + p1;
         __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
         pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh);

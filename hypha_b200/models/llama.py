@@ -206,6 +206,14 @@ class LlamaForCausalLM(nn.Module):
             for l in range(cfg.num_layers)
         ])
         self._rope_cache: Dict[Tuple[int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
+        # set by the trainer: callable(begin, end) invoked from backward as soon as the gradients of
+        # the flat parameter range [begin, end) are complete (optimizer-in-backward overlap)
+        self.grad_ready_hook = None
+        L = self.flat.layout
+        starts = [L[f"layers.{l}.norm1"][0] for l in range(cfg.num_layers)] + [L["final_norm"][0]]
+        self.layer_ranges = [(starts[l], starts[l + 1]) for l in range(cfg.num_layers)]
+        self.head_range = (L["final_norm"][0], self.flat.numel)
+        self.embed_range = (0, starts[0])
         if init:
             self.reset_parameters(seed)
 
@@ -245,12 +253,18 @@ class LlamaForCausalLM(nn.Module):
         P = self._params
         delta = ops.embedding(input_ids, P["embed"])
         residual = None
+        hook = self.grad_ready_hook if torch.is_grad_enabled() else None
         for l, blk in enumerate(self.blocks):
+            if hook is not None and delta.requires_grad:
+                rng = self.layer_ranges[l]
+                delta.register_hook(lambda g, rng=rng: hook(*rng))      # fires when layer l's backward is done
             if l < cfg.recompute_layers and torch.is_grad_enabled():
                 fn = lambda d, r, blk=blk: blk(d, r, cos, sin, batch, seq)
                 delta, residual = _CheckpointPair.apply(fn, delta, residual)
             else:
                 delta, residual = blk(delta, residual, cos, sin, batch, seq)
+        if hook is not None and delta.requires_grad:
+            delta.register_hook(lambda g: hook(*self.head_range))       # final norm + LM head grads complete
         hN, _ = ops.add_rmsnorm(delta, residual, P["final_norm"], cfg.rms_eps)
         if labels is None:
             return ops.linear(hN, P["lm_head"]).view(batch, seq, -1)

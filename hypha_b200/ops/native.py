@@ -8,6 +8,7 @@ loaded).
 from __future__ import annotations
 
 import importlib
+import importlib.util
 import os
 from functools import lru_cache
 
@@ -40,7 +41,6 @@ def load_C():
 def load_core():
     override = os.environ.get("HYPHA_CORE_OVERRIDE")        # e.g. the ASAN build from tools/sanitize.sh
     if override:
-        import importlib.util
         import glob
 
         path = glob.glob(os.path.join(override, "_core*.so"))[0]

@@ -129,20 +129,40 @@ class FlatAdamW:
     def lr(self) -> float:
         return self.cfg.lr * self.lr_lambda(self.step_count)
 
-    def step(self, grad_scale: float = 1.0) -> None:
+    def begin_step(self) -> None:
+        """Advance the step counter and fix this step's scalars (lr, bias corrections, SR seed)."""
         c = self.cfg
-        lr = self.lr
+        self._lr = self.lr
         self.step_count += 1
         t = self.step_count
-        bc1 = 1.0 - c.betas[0] ** t
-        bc2 = 1.0 - c.betas[1] ** t
-        load_C().adamw_flat(self.params.data_ptr(), self.grads.data_ptr(), self.master.data_ptr(),
-                            self.m.data_ptr(), self.v.data_ptr(), int(c.state_dtype == "bf16"),
-                            self.params.numel(), lr, c.betas[0], c.betas[1], c.eps, c.weight_decay,
-                            bc1, bc2, grad_scale, (t * 2654435761) & 0xFFFFFFFF, cuda_stream())
+        self._bc1 = 1.0 - c.betas[0] ** t
+        self._bc2 = 1.0 - c.betas[1] ** t
+        self._seed = (t * 2654435761) & 0xFFFFFFFF
+
+    def step_range(self, begin: int, end: int, grad_scale: float = 1.0) -> None:
+        """AdamW on the flat slice ``[begin, end)`` (multiples of 8) on the CURRENT stream.  Lets the
+        trainer update a layer as soon as its gradients exist, overlapped with the rest of backward."""
+        c = self.cfg
+        n = end - begin
+        if n <= 0:
+            return
+        assert begin % 8 == 0 and n % 8 == 0
+        es = 2 if c.state_dtype == "bf16" else 4
+        load_C().adamw_flat(self.params.data_ptr() + 2 * begin, self.grads.data_ptr() + 2 * begin,
+                            self.master.data_ptr() + 4 * begin, self.m.data_ptr() + es * begin,
+                            self.v.data_ptr() + es * begin, int(c.state_dtype == "bf16"), n, self._lr,
+                            c.betas[0], c.betas[1], c.eps, c.weight_decay, self._bc1, self._bc2, grad_scale,
+                            (self._seed + begin) & 0xFFFFFFFF, cuda_stream())
+
+    def finish_step(self) -> None:
         from ..ops.functional import bump_fp8_weight_version
 
         bump_fp8_weight_version()           # cached fp8 weight copies are stale now
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        self.begin_step()
+        self.step_range(0, self.params.numel(), grad_scale)
+        self.finish_step()
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         return {"master": self.master, "m": self.m, "v": self.v,

@@ -42,6 +42,13 @@ class DiLoCoTrainer:
         self.diloco = diloco
         self.global_step = 0
         self._h2d_stream = torch.cuda.Stream(device=self.device) if self.device.type == "cuda" else None
+        # optimizer-in-backward: each layer's AdamW slice runs on a side stream as soon as that layer's
+        # gradients exist, hidden under the remaining backward GEMMs (HBM-bound vs tensor-bound work)
+        self.overlap_optimizer = os.environ.get("HYPHA_OVERLAP_OPT", "1") == "1" and self.device.type == "cuda"
+        self._opt_stream = torch.cuda.Stream(device=self.device) if self.overlap_optimizer else None
+        self._opt_done: list = []
+        if self.overlap_optimizer:
+            model.grad_ready_hook = self._on_grad_ready
         self.last_loss: Optional[torch.Tensor] = None
         self.h2d_bytes = 0
 
@@ -86,13 +93,41 @@ class DiLoCoTrainer:
         d.record_stream(torch.cuda.current_stream())
         return d
 
+    def _on_grad_ready(self, begin: int, end: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._opt_stream.wait_event(ev)
+        with torch.cuda.stream(self._opt_stream):
+            self.opt.step_range(begin, end)
+        self._opt_done.append((begin, end))
+
     def inner_step(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         ids = self._to_device(input_ids)
         lab = self._to_device(labels)
         self.model.set_grad_accumulate(False)
-        loss = self.model(ids, lab)
-        loss.backward()
-        self.opt.step()
+        if not self.overlap_optimizer:
+            loss = self.model(ids, lab)
+            loss.backward()
+            self.opt.step()
+        else:
+            self.opt.begin_step()
+            self._opt_done.clear()
+            loss = self.model(ids, lab)
+            loss.backward()
+            # whatever backward did not cover (the embedding table, or everything if no hook fired)
+            done = sorted(self._opt_done)
+            cur, n = 0, self.opt.params.numel()
+            gaps = []
+            for b, e in done:
+                if b > cur:
+                    gaps.append((cur, b))
+                cur = max(cur, e)
+            if cur < n:
+                gaps.append((cur, n))
+            for b, e in gaps:
+                self._on_grad_ready(b, e)
+            torch.cuda.current_stream().wait_stream(self._opt_stream)
+            self.opt.finish_step()
         self.last_loss = loss.detach()
         return self.last_loss
 
