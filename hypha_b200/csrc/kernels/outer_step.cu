@@ -116,72 +116,95 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
 
   // ---- Phase A: local pseudo-gradient relative to the common anchor ---------
+  // (two 16-byte vectors per thread per trip: all loads are issued before the first use)
   {
     bf16* my_delta = const_cast<bf16*>(a.delta_peers[a.rank]);
     const bf16* anchor = a.anchor_peers[a.rank];
     const int64_t nvec = a.n >> 3;
-    for (int64_t i = tid; i < nvec; i += nthreads) {
-      const int64_t off = i << 3;
-      float w[8], x[8];
-      *reinterpret_cast<float4*>(w) = ld_stream_f32x4(a.master + off);
-      *reinterpret_cast<float4*>(w + 4) = ld_stream_f32x4(a.master + off + 4);
-      unpack8(ld_stream_bf16x8(anchor + off), x);
+    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
+      const int64_t i1 = i + nthreads;
+      const bool two = i1 < nvec;
+      const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
+      float w0[8], w1[8], x0[8], x1[8];
+      *reinterpret_cast<float4*>(w0) = ld_stream_f32x4(a.master + off0);
+      *reinterpret_cast<float4*>(w0 + 4) = ld_stream_f32x4(a.master + off0 + 4);
+      *reinterpret_cast<float4*>(w1) = ld_stream_f32x4(a.master + off1);
+      *reinterpret_cast<float4*>(w1 + 4) = ld_stream_f32x4(a.master + off1 + 4);
+      const bf16x8 a0 = ld_stream_bf16x8(anchor + off0), a1 = ld_stream_bf16x8(anchor + off1);
+      unpack8(a0, x0);
+      unpack8(a1, x1);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) w[e] -= x[e];
-      st_bf16x8(my_delta + off, pack8(w));
+      for (int e = 0; e < 8; ++e) { w0[e] -= x0[e]; w1[e] -= x1[e]; }
+      st_bf16x8(my_delta + off0, pack8(w0));
+      if (two) st_bf16x8(my_delta + off1, pack8(w1));
     }
   }
   cross_gpu_barrier(a, ls, 0, a.epoch * 2u + 1u, timeout_ns, 1u);
   if (ld_acquire_gpu(&ls->status) != 0u) return;
 
   // ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast --------
+  // Two vectors per thread per trip: up to 16 peer loads of 16 B are in flight per thread before
+  // the first one is consumed (NVLink latency ~2 us needs deep memory-level parallelism).
   for (int seg = 0; seg < a.num_segs; ++seg) {
     const bf16* anchor = a.anchor_peers[a.rank];
     float* theta_outer = a.seg_theta[seg];
     float* momentum = a.seg_mom[seg];
     const int64_t seg_begin = a.seg_begin[seg];
     const int64_t nvec = a.seg_len[seg] >> 3;
-    for (int64_t i = tid; i < nvec; i += nthreads) {
-      const int64_t loc = i << 3;
-      const int64_t off = seg_begin + loc;
-      uint4 raw[8];
+    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
+      const int64_t iv[2] = {i, i + nthreads};
+      const int cnt = iv[1] < nvec ? 2 : 1;
+      uint4 raw[2][8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if ((a.member_mask >> r) & 1u) raw[r] = ld_peer_16(a.delta_peers[r] + off);
-      }
-      float acc[8];
+      for (int u = 0; u < 2; ++u) {
+        if (u < cnt) {
+          const int64_t off = seg_begin + (iv[u] << 3);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) acc[e] = 0.f;
-#pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if ((a.member_mask >> r) & 1u) {
-          float d[8];
-          unpack8(*reinterpret_cast<bf16x8*>(&raw[r]), d);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc[e] += d[e];
+          for (int r = 0; r < 8; ++r) {
+            if ((a.member_mask >> r) & 1u) raw[u][r] = ld_peer_16(a.delta_peers[r] + off);
+          }
         }
       }
-      float x[8], th[8], mo[8];
-      unpack8(ld_stream_bf16x8(anchor + off), x);
-      *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
-      *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
-      *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
-      *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(momentum + loc + 4);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float g = acc[e] * a.inv_world + (x[e] - th[e]);
-        mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
-        th[e] += a.lr * (a.mu * mo[e] + g);
-      }
-      *reinterpret_cast<float4*>(theta_outer + loc) = *reinterpret_cast<float4*>(th);
-      *reinterpret_cast<float4*>(theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
-      *reinterpret_cast<float4*>(momentum + loc) = *reinterpret_cast<float4*>(mo);
-      *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
-      bf16x8 pn = pack8(th);
-      const uint4 pv = *reinterpret_cast<uint4*>(&pn);
+      for (int u = 0; u < 2; ++u) {
+        if (u < cnt) {
+          const int64_t loc = iv[u] << 3;
+          const int64_t off = seg_begin + loc;
+          float acc[8];
 #pragma unroll
-      for (int r = 0; r < 8; ++r) {
-        if ((a.member_mask >> r) & 1u) st_peer_16(a.param_peers[r] + off, pv);
+          for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if ((a.member_mask >> r) & 1u) {
+              float d[8];
+              unpack8(*reinterpret_cast<bf16x8*>(&raw[u][r]), d);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[e] += d[e];
+            }
+          }
+          float x[8], th[8], mo[8];
+          unpack8(ld_stream_bf16x8(anchor + off), x);
+          *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
+          *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
+          *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
+          *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(momentum + loc + 4);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g = acc[e] * a.inv_world + (x[e] - th[e]);
+            mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
+            th[e] += a.lr * (a.mu * mo[e] + g);
+          }
+          *reinterpret_cast<float4*>(theta_outer + loc) = *reinterpret_cast<float4*>(th);
+          *reinterpret_cast<float4*>(theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
+          *reinterpret_cast<float4*>(momentum + loc) = *reinterpret_cast<float4*>(mo);
+          *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
+          bf16x8 pn = pack8(th);
+          const uint4 pv = *reinterpret_cast<uint4*>(&pn);
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            if ((a.member_mask >> r) & 1u) st_peer_16(a.param_peers[r] + off, pv);
+          }
+        }
       }
     }
   }
@@ -193,14 +216,23 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
     const bf16* param = a.param_peers[a.rank];
     bf16* anchor = a.anchor_peers[a.rank];
     const int64_t nvec = a.n >> 3;
-    for (int64_t i = tid; i < nvec; i += nthreads) {
-      const int64_t off = i << 3;
-      const uint4 raw = ld_peer_16(param + off);  // written by remote owners: bypass L1
+    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
+      const int64_t i1 = i + nthreads;
+      const bool two = i1 < nvec;
+      const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
+      const uint4 r0 = ld_peer_16(param + off0);   // written by remote owners: bypass L1
+      const uint4 r1 = ld_peer_16(param + off1);
       float w[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(&raw), w);
-      *reinterpret_cast<float4*>(a.master + off) = *reinterpret_cast<float4*>(w);
-      *reinterpret_cast<float4*>(a.master + off + 4) = *reinterpret_cast<float4*>(w + 4);
-      *reinterpret_cast<uint4*>(anchor + off) = raw;
+      unpack8(*reinterpret_cast<const bf16x8*>(&r0), w);
+      *reinterpret_cast<float4*>(a.master + off0) = *reinterpret_cast<float4*>(w);
+      *reinterpret_cast<float4*>(a.master + off0 + 4) = *reinterpret_cast<float4*>(w + 4);
+      *reinterpret_cast<uint4*>(anchor + off0) = r0;
+      if (two) {
+        unpack8(*reinterpret_cast<const bf16x8*>(&r1), w);
+        *reinterpret_cast<float4*>(a.master + off1) = *reinterpret_cast<float4*>(w);
+        *reinterpret_cast<float4*>(a.master + off1 + 4) = *reinterpret_cast<float4*>(w + 4);
+        *reinterpret_cast<uint4*>(anchor + off1) = r1;
+      }
     }
   }
 }
