@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--batch", type=int, default=2)
     ap.add_argument("--inner-steps", type=int, default=10)
     ap.add_argument("--tiny", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     cfg = GPT2Config.tiny() if a.tiny else GPT2Config.small()
     job = {
@@ -41,7 +42,8 @@ def main():
         outcome, sink, logs, _ = asyncio.run(run_loopback_job(
             tmp, repo="local/gpt2", write_model_config=lambda p: cfg.to_json(p), job=job,
             write_dataset=lambda d: write_synthetic_token_slices(d, 8, 32, a.seq_len, cfg.vocab_size),
-            timeout_s=3600, omp_threads=max(1, (os.cpu_count() or 4) // 2)))
+            timeout_s=3600, omp_threads=max(1, (os.cpu_count() or 4) // 2),
+            log=(lambda m: print(m, flush=True)) if a.verbose else None))
         wall = time.time() - t0
     losses = {}
     for r in sink.records:

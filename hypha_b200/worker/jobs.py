@@ -192,27 +192,40 @@ class ParameterServerExecutor:
                         path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
                         await st.save(path)
                         got[st.peer] = path
-                    # true mean, one tensor at a time
-                    files = [load_file(p) for p in got.values()]
-                    avg = {}
-                    for k in files[0].keys():
-                        acc = files[0][k].float().clone()
-                        for f in files[1:]:
-                            acc += f[k].float()
-                        avg[k] = acc / len(files)
-                    del files
-                    momentum, upd = nesterov_step(avg, momentum, cfg.optimizer.learning_rate, cfg.optimizer.momentum)
+                    # true mean + Nesterov, one tensor at a time, OFF the event loop: the worker must
+                    # keep answering RenewLease / health RPCs while hundreds of MB are being reduced
                     out = os.path.join(work_dir, "gradient_update")
-                    save_file({k: v.contiguous() for k, v in upd.items()}, out)
-                    save_file({k: v.contiguous() for k, v in momentum.items()}, os.path.join(work_dir, "momentum"))
+                    paths = list(got.values())
+                    prev_momentum = momentum
+
+                    def reduce_and_step():
+                        files = [load_file(p) for p in paths]
+                        avg = {}
+                        for k in files[0].keys():
+                            acc = files[0][k].float().clone()
+                            for f in files[1:]:
+                                acc += f[k].float()
+                            avg[k] = acc / len(files)
+                        del files
+                        new_m, upd = nesterov_step(avg, prev_momentum, cfg.optimizer.learning_rate,
+                                                   cfg.optimizer.momentum)
+                        save_file({k: v.contiguous() for k, v in upd.items()}, out)
+                        save_file({k: v.contiguous() for k, v in new_m.items()}, os.path.join(work_dir, "momentum"))
+                        return new_m
+
+                    momentum = await asyncio.get_event_loop().run_in_executor(None, reduce_and_step)
+                    # Tell the scheduler the round is complete BEFORE distributing the result: a worker
+                    # that gets its file early would otherwise ack ("update-received") against the old
+                    # round number and be told to continue (the reference sends results first,
+                    # parameter_server.rs:232-282, and has this race).
+                    resp = await self.network.request(scheduler, M.PROGRESS_PROTOCOL,
+                                                      M.ProgressRequest(spec.job_id, M.Progress("updated")))
                     send_ref = M.Send.to_peers([p for p in cfg.results.peers if p in got] or cfg.results.peers)
                     await self.connector.send(send_ref, out, job_id=spec.job_id)
                     for p in got.values():
                         os.unlink(p)
                     os.unlink(out)
                     rnd += 1
-                    resp = await self.network.request(scheduler, M.PROGRESS_PROTOCOL,
-                                                      M.ProgressRequest(spec.job_id, M.Progress("updated")))
                     if M.ProgressResponse.from_wire(resp).type == "Done":
                         ex.status = M.JobStatus.FINISHED
                         return

@@ -1,0 +1,134 @@
+"""Allocation protocol end to end over in-memory links: gossip ad -> priced offers -> lease
+acceptance by renewal -> dispatch guard -> expiry.  (The reference has no tests for the arbiter /
+allocator / lease manager: SURVEY section 4 "not tested at all".)"""
+import asyncio
+import time
+
+import pytest
+
+from hypha_b200 import messages as M
+from hypha_b200.scheduler import GreedyWorkerAllocator, NoOffersReceived
+from hypha_b200.transport import Network
+from hypha_b200.worker import Arbiter, Connector, JobManager
+from hypha_b200.worker import arbiter as arb_mod
+
+
+class _Exec:
+    def __init__(self, cls, name, runtime="parameter-server"):
+        self.cls, self.name, self.runtime, self.cmd, self.args = cls, name, runtime, None, []
+
+
+async def _cluster(worker_specs):
+    """worker_specs: [(peer_id, gpu, price, floor, strategy)] -> (gateway, scheduler net, workers)"""
+    gw = Network("gw", relay_server=True, dht_server=True)
+    addr = await gw.listen(f"memory://alloc-{id(gw)}")
+    sched = Network("sched")
+    await sched.dial(addr)
+    workers = []
+    for pid, gpu, price, floor, strategy in worker_specs:
+        net = Network(pid)
+        await net.listen(f"memory://{pid}-{id(net)}")
+        await net.dial(addr)
+        jobs = JobManager(Connector(net), net, "/tmp", [_Exec("train", M.TRAIN_EXECUTOR_NAME), _Exec("aggregate", M.AGGREGATE_EXECUTOR_NAME)],
+                          log=lambda m: None)
+        a = Arbiter(net, M.Resources(gpu=gpu, cpu=8, storage=100, memory=64), jobs, price=price, floor=floor,
+                    strategy=strategy, log=lambda m: None)
+        stop = asyncio.Event()
+        task = asyncio.ensure_future(a.run(stop))
+        workers.append((net, a, stop, task))
+    await asyncio.sleep(0.05)          # subscriptions propagate
+    return gw, sched, workers
+
+
+async def _teardown(gw, sched, workers):
+    for net, a, stop, task in workers:
+        stop.set()
+    await asyncio.gather(*(w[3] for w in workers), return_exceptions=True)
+    for n in [gw, sched] + [w[0] for w in workers]:
+        await n.close()
+
+
+SPEC = M.WorkerSpec(M.Resources(gpu=1, cpu=1, storage=0, memory=1), [M.ExecutorDescriptor("train", M.TRAIN_EXECUTOR_NAME)])
+
+
+def test_cheapest_offers_win_with_diversity_and_leases_are_renewed():
+    async def main():
+        gw, sched, workers = await _cluster([("w-cheap", 4, 10.0, 1.0, "whole"), ("w-mid", 4, 20.0, 1.0, "whole"),
+                                             ("w-dear", 4, 90.0, 1.0, "whole")])
+        alloc = GreedyWorkerAllocator(sched)
+        handles = await alloc.request(SPEC, bid=5.0, max_price=50.0, num=2, deadline_s=2.0)
+        assert sorted(h.peer_id for h in handles) == ["w-cheap", "w-mid"]      # 90 > max price, best two kept
+        assert all(h.renewals >= 1 for h in handles)                            # accepted by renewing
+        for h in handles:
+            assert h.timeout - time.time() > 8.0                                # 10 s lease after acceptance
+            assert h.resources.gpu == 4                                         # "whole" strategy offers everything
+        by = {w[0].peer_id: w[1] for w in workers}
+        assert by["w-cheap"].leases.available().gpu == 0
+        await asyncio.sleep(arb_mod.OFFER_TIMEOUT_S + 2 * arb_mod.PRUNE_INTERVAL_S + 0.2)
+        assert by["w-dear"].leases.available().gpu == 4                         # loser's tentative lease expired
+        assert by["w-cheap"].leases.available().gpu == 0                        # winner's lease still held
+        for h in handles:
+            await h.release()
+        await _teardown(gw, sched, workers)
+    asyncio.run(main())
+
+
+def test_floor_unsupported_executor_and_capacity_filters():
+    async def main():
+        gw, sched, workers = await _cluster([("w1", 2, 10.0, 50.0, "flexible")])
+        alloc = GreedyWorkerAllocator(sched)
+        with pytest.raises(NoOffersReceived):                                   # bid below the worker's floor
+            await alloc.request(SPEC, bid=5.0, max_price=100.0, num=1, deadline_s=0.6)
+        bad = M.WorkerSpec(SPEC.resources, [M.ExecutorDescriptor("train", "unknown-executor")])
+        with pytest.raises(NoOffersReceived):
+            await alloc.request(bad, bid=60.0, max_price=100.0, num=1, deadline_s=0.6)
+        big = M.WorkerSpec(M.Resources(gpu=64, cpu=64, storage=1000, memory=1000), SPEC.executor)
+        with pytest.raises(NoOffersReceived):                                   # strictly greater than capacity
+            await alloc.request(big, bid=60.0, max_price=100.0, num=1, deadline_s=0.6)
+        ok = await alloc.request(SPEC, bid=60.0, max_price=100.0, num=1, deadline_s=2.0)
+        assert ok[0].peer_id == "w1" and ok[0].price == 60.0 and ok[0].resources.gpu == 1    # flexible mirrors the ask
+        await ok[0].release()
+        await _teardown(gw, sched, workers)
+    asyncio.run(main())
+
+
+def test_renew_by_non_owner_fails_and_dispatch_needs_a_lease():
+    async def main():
+        gw, sched, workers = await _cluster([("w1", 2, 10.0, 1.0, "flexible")])
+        intruder = Network("intruder")
+        await intruder.dial(gw.listen_addrs[0])
+        alloc = GreedyWorkerAllocator(sched)
+        (h,) = await alloc.request(SPEC, bid=20.0, max_price=100.0, num=1, deadline_s=2.0)
+        resp = M.ApiResponse.from_wire(await intruder.request("w1", M.API_PROTOCOL, M.ApiRequest.renew_lease(h.lease_id)))
+        assert resp.variant()[0] == "Failed"
+        spec = M.JobSpec(M.new_id(), M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, M.AggregateExecutorConfig(
+            M.Receive.from_peers(["x"]), M.Send.to_peers(["x"]), M.Nesterov(0.7, 0.9))))
+        resp = M.ApiResponse.from_wire(await intruder.request("w1", M.API_PROTOCOL, M.ApiRequest.dispatch_job(M.new_id(), spec)))
+        assert resp.variant()[0] == "Failed"                                    # no lease for this peer
+        resp = M.ApiResponse.from_wire(await sched.request("w1", M.API_PROTOCOL, M.ApiRequest.renew_lease("no-such-lease")))
+        assert resp.variant()[0] == "Failed"
+        await h.release()
+        await intruder.close()
+        await _teardown(gw, sched, workers)
+    asyncio.run(main())
+
+
+def test_lease_expiry_cancels_the_job_and_fails_the_handle(monkeypatch):
+    async def main():
+        monkeypatch.setattr(arb_mod, "LEASE_DURATION_S", 0.6)
+        gw, sched, workers = await _cluster([("w1", 2, 10.0, 1.0, "flexible")])
+        net, a, stop, task = workers[0]
+        alloc = GreedyWorkerAllocator(sched)
+        aspec = M.WorkerSpec(SPEC.resources, [M.ExecutorDescriptor("aggregate", M.AGGREGATE_EXECUTOR_NAME)])
+        (h,) = await alloc.request(aspec, bid=20.0, max_price=100.0, num=1, deadline_s=2.0)
+        spec = M.JobSpec(M.new_id(), M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, M.AggregateExecutorConfig(
+            M.Receive.from_peers(["nobody"]), M.Send.to_peers(["nobody"]), M.Nesterov(0.7, 0.9))))
+        tid = M.new_id()
+        resp = M.ApiResponse.from_wire(await sched.request("w1", M.API_PROTOCOL, M.ApiRequest.dispatch_job(tid, spec)))
+        assert resp.variant()[0] == "Dispatched"
+        job = a.jobs.jobs[tid]
+        await h.release()                               # scheduler stops renewing -> lease runs out
+        await asyncio.wait_for(job.execution.wait(), 5.0)
+        assert job.execution.status == M.JobStatus.FAILED and a.leases.available().gpu == 2
+        await _teardown(gw, sched, workers)
+    asyncio.run(main())
