@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--max-mb", type=float, default=16384)
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--nvls", action="store_true", help="also time the NVSwitch-multicast (multimem) variant")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -42,8 +43,14 @@ def main():
     grp = PeerGroup.from_torch_distributed(local)
     nmax = int(a.max_mb * 1024 * 1024 / 2)
     nmax = (nmax + 8191) // 8192 * 8192
-    pbuf = grp.alloc("params", nmax, torch.bfloat16)
-    gbuf = grp.alloc("grads", nmax, torch.bfloat16)
+    if a.nvls:
+        from hypha_b200.parallel.nvls import alloc_nvls
+
+        pbuf = alloc_nvls(grp, "params", nmax, torch.bfloat16)
+        gbuf = alloc_nvls(grp, "grads", nmax, torch.bfloat16)
+    else:
+        pbuf = grp.alloc("params", nmax, torch.bfloat16)
+        gbuf = grp.alloc("grads", nmax, torch.bfloat16)
     master_full = torch.zeros(nmax, device=dev)
 
     def timed(fn, iters):
@@ -70,12 +77,19 @@ def main():
         class _Opt:                      # the pieces of FlatAdamW the outer step touches
             params, grads, master = p, g, master_full[:n]
 
-        sub_p = type(pbuf)(pbuf.name, n, pbuf.dtype, p, pbuf.peer_ptrs)
-        sub_g = type(gbuf)(gbuf.name, n, gbuf.dtype, g, gbuf.peer_ptrs)
+        kw = (lambda b: {"mc_ptr": b.mc_ptr}) if a.nvls else (lambda b: {})
+        sub_p = type(pbuf)(pbuf.name, n, pbuf.dtype, p, pbuf.peer_ptrs, **kw(pbuf))
+        sub_g = type(gbuf)(gbuf.name, n, gbuf.dtype, g, gbuf.peer_ptrs, **kw(gbuf))
         outer = DiLoCoOuter(_Opt, DiLoCoConfig(backend="fused"), grp, sub_p, sub_g)
         iters = a.iters if mb >= 64 else 20
+        outer.use_nvls = False
         fused = timed(outer.step, iters)
         st = outer.check()
+        nvls_ms = None
+        if a.nvls:
+            outer.use_nvls = True
+            nvls_ms = timed(outer.step, iters)
+            st = tuple(max(x, y) for x, y in zip(st, outer.check()))
         ar = timed(lambda: dist.all_reduce(g), iters)
         CH = 1 << 28
         try:
@@ -107,7 +121,8 @@ def main():
         S = 2 * n
         bus = lambda ms: S * 2 * (world - 1) / world / ms / 1e6
         row = {"delta_mb": S / 2 ** 20, "numel": n, "status": list(st), "fused_ms": fused, "nccl_allreduce_ms": ar,
-               "nccl_full_outer_ms": full, "fused_busbw_gbs": bus(fused), "nccl_allreduce_busbw_gbs": bus(ar),
+               "nccl_full_outer_ms": full, "fused_busbw_gbs": bus(fused),
+               "fused_nvls_ms": nvls_ms, "fused_nvls_busbw_gbs": bus(nvls_ms) if nvls_ms else None, "nccl_allreduce_busbw_gbs": bus(ar),
                "fused_frac_of_770": bus(fused) / PEER_COPY_GBS, "fused_frac_of_900": bus(fused) / NVLINK_NOMINAL_GBS,
                "speedup_vs_nccl_full": (full / fused) if full else None}
         rows.append(row)

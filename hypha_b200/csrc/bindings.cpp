@@ -110,7 +110,7 @@ PYBIND11_MODULE(_C, m) {
            std::vector<u64> flag_peers, u64 master, std::vector<int64_t> seg_begin,
            std::vector<int64_t> seg_len, std::vector<u64> seg_theta, std::vector<u64> seg_mom, int64_t n,
            int rank, uint32_t member_mask, uint32_t epoch, float lr, float mu, int first_round,
-           int num_ctas, u64 s) {
+           int num_ctas, u64 mc_delta, u64 mc_param, u64 s) {
           hb::OuterStepArgs a{};
           if (delta_peers.size() > 8) throw std::runtime_error("at most 8 ranks per NVSwitch box");
           if (seg_begin.size() > 8 || seg_begin.size() != seg_len.size() ||
@@ -136,6 +136,8 @@ PYBIND11_MODULE(_C, m) {
           a.world = world; a.rank = rank; a.member_mask = member_mask; a.epoch = epoch;
           a.lr = lr; a.mu = mu; a.first_round = first_round;
           a.inv_world = 1.0f / (float)(world > 0 ? world : 1);
+          a.mc_delta = P<const bf16>(mc_delta);
+          a.mc_param = P<bf16>(mc_param);
           hb::diloco_outer_step_fused(a, num_ctas, S(s));
           check_last("diloco_outer_step_fused");
         });

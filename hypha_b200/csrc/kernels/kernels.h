@@ -62,6 +62,10 @@ struct OuterStepArgs {
   float lr, mu;
   int first_round;              // momentum := g on the first round
   float inv_world;              // 1 / number of contributing ranks
+  // NVLS (NVSwitch multicast) path: multicast addresses of the delta and parameter buffers.
+  // When set and every rank participates, phase B uses multimem.ld_reduce / multimem.st.
+  const bf16* mc_delta;
+  bf16* mc_param;
 };
 void diloco_outer_step_fused(const OuterStepArgs& a, int num_ctas, cudaStream_t s);
 // Local Nesterov step.  delta_sum == null: single worker, exact fp32

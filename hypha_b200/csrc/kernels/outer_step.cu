@@ -73,6 +73,20 @@ __device__ __forceinline__ void st_peer_16(void* p, const uint4& v) {
                "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+// NVSwitch in-fabric reduction: one 16-byte load returns the SUM over all devices bound to the
+// multicast object (8 bf16 lanes, accumulated in fp32 inside the switch).
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16x8(const void* mc) {
+  uint4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(mc) : "memory");
+  return r;
+}
+// One 16-byte store replicated by the switch into every device's copy.
+__device__ __forceinline__ void multimem_st_bf16x8(void* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1,%2,%3,%4};" ::"l"(mc), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 // Local grid barrier over a monotonically increasing counter.
 __device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
   __threadfence_system();
@@ -145,7 +159,50 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
   // ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast --------
   // Two vectors per thread per trip: up to 16 peer loads of 16 B are in flight per thread before
   // the first one is consumed (NVLink latency ~2 us needs deep memory-level parallelism).
-  for (int seg = 0; seg < a.num_segs; ++seg) {
+  const bool nvls = a.mc_delta != nullptr && a.mc_param != nullptr;
+  for (int seg = 0; nvls && seg < a.num_segs; ++seg) {
+    // ---- NVLS variant: the switch reduces the N deltas and replicates the new weights ----
+    const bf16* anchor = a.anchor_peers[a.rank];
+    float* theta_outer = a.seg_theta[seg];
+    float* momentum = a.seg_mom[seg];
+    const int64_t seg_begin = a.seg_begin[seg];
+    const int64_t nvec = a.seg_len[seg] >> 3;
+    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
+      const int64_t iv[2] = {i, i + nthreads};
+      const int cnt = iv[1] < nvec ? 2 : 1;
+      uint4 red[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (u < cnt) red[u] = multimem_ld_reduce_bf16x8(a.mc_delta + seg_begin + (iv[u] << 3));
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        if (u < cnt) {
+          const int64_t loc = iv[u] << 3;
+          const int64_t off = seg_begin + loc;
+          float acc[8], x[8], th[8], mo[8];
+          unpack8(*reinterpret_cast<bf16x8*>(&red[u]), acc);
+          unpack8(ld_stream_bf16x8(anchor + off), x);
+          *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
+          *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
+          *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
+          *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(momentum + loc + 4);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float g = acc[e] * a.inv_world + (x[e] - th[e]);
+            mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
+            th[e] += a.lr * (a.mu * mo[e] + g);
+          }
+          *reinterpret_cast<float4*>(theta_outer + loc) = *reinterpret_cast<float4*>(th);
+          *reinterpret_cast<float4*>(theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
+          *reinterpret_cast<float4*>(momentum + loc) = *reinterpret_cast<float4*>(mo);
+          *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
+          bf16x8 pn = pack8(th);
+          multimem_st_bf16x8(a.mc_param + off, *reinterpret_cast<uint4*>(&pn));
+        }
+      }
+    }
+  }
+  for (int seg = 0; !nvls && seg < a.num_segs; ++seg) {
     const bf16* anchor = a.anchor_peers[a.rank];
     float* theta_outer = a.seg_theta[seg];
     float* momentum = a.seg_mom[seg];

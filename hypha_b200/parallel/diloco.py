@@ -224,6 +224,7 @@ class DiLoCoOuter:
             # segments owned by this rank: its shard + shards adopted from dropped ranks
             self.segments = {self.rank: (self.shard_begin, self.shard_len, self.theta_outer, self.momentum)}
             self.attempt = 0
+            self.use_nvls = True                    # used when the buffers carry a multicast address
             load_C().set_outer_timeout_ms(int(cfg.timeout_ms))
         elif backend == "nccl":
             # baseline: replicated outer state, stock collectives + unfused torch ops
@@ -260,7 +261,7 @@ class DiLoCoOuter:
                                       [l for _, l, _, _ in segs], [t.data_ptr() for _, _, t, _ in segs],
                                       [m.data_ptr() for _, _, _, m in segs], self.n, self.rank,
                                       self.member_mask, self.attempt, cfg.outer_lr, cfg.outer_momentum,
-                                      first, cfg.num_ctas, s)
+                                      first, cfg.num_ctas, *self._multicast_ptrs(), s)
             nmem = bin(self.member_mask).count("1")
             wire = 2 * sum(l for _, l, _, _ in segs) * (nmem - 1)
             self.group.counters.add("/hypha-peer-memory/outer-step", inbound=wire, outbound=wire)
@@ -353,6 +354,16 @@ class DiLoCoOuter:
             dead = [r for r in range(self.world) if (missing >> r) & 1]
             self.drop_ranks(dead)
         raise RuntimeError("outer step kept timing out")
+
+    def _multicast_ptrs(self) -> tuple:
+        """(mc_delta, mc_param) when both buffers are NVLS-bound and every rank participates; the
+        switch cannot skip a member, so a shrunk membership falls back to P2P loads/stores."""
+        full = self.member_mask == (1 << self.world) - 1
+        md = getattr(self.delta_buf, "mc_ptr", 0)
+        mp = getattr(self.param_buf, "mc_ptr", 0)
+        if full and md and mp and self.use_nvls:
+            return (md, mp)
+        return (0, 0)
 
     def check(self) -> tuple:
         """Host-side status of the last fused step: (status, missing_rank_mask)."""

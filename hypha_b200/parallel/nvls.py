@@ -1,0 +1,200 @@
+"""NVLS symmetric memory: VMM allocations that are (a) local HBM, (b) mapped on every peer for
+plain P2P loads/stores and (c) bound to an NVSwitch *multicast object*, so a kernel can issue
+``multimem.ld_reduce`` (the switch sums the N copies in flight) and ``multimem.st`` (the switch
+replicates one store to all N copies).
+
+Set-up (driver API through ``cuda.bindings``; no NCCL, no torch symmetric-memory):
+  1. ``cuMemCreate`` a POSIX-fd-exportable physical allocation per rank,
+  2. swap the fds between the rank processes over AF_UNIX sockets (``SCM_RIGHTS``),
+  3. import + ``cuMemMap`` every peer's allocation (unicast view, for flags / fallback P2P),
+  4. rank 0 ``cuMulticastCreate``s the multicast object and shares its fd, every rank
+     ``cuMulticastAddDevice`` + ``cuMulticastBindMem``s its allocation and maps the multicast VA.
+
+This is the B200-native replacement of the reference's parameter-server fan-in / fan-out
+(crates/worker/src/executor/parameter_server.rs:101-283) at the transport level.
+"""
+from __future__ import annotations
+
+import array
+import os
+import socket
+import tempfile
+import time
+from dataclasses import dataclass
+from typing import Callable, List, Optional
+
+import torch
+
+from .peer_memory import _DT_SIZE, PeerGroup, SymmetricBuffer, tensor_from_ptr
+
+
+class NvlsUnavailable(RuntimeError):
+    pass
+
+
+def _cu():
+    try:
+        from cuda.bindings import driver as cu
+    except ImportError:  # older cuda-python
+        from cuda import cuda as cu
+    return cu
+
+
+def _ck(res, what: str):
+    cu = _cu()
+    err, *rest = res if isinstance(res, tuple) else (res,)
+    if err != cu.CUresult.CUDA_SUCCESS:
+        raise NvlsUnavailable(f"{what} failed: {err}")
+    return rest[0] if len(rest) == 1 else (tuple(rest) if rest else None)
+
+
+def _send_fds(path: str, rank: int, fds: List[int]) -> None:
+    deadline = time.time() + 30
+    while True:
+        try:
+            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+            s.connect(path)
+            break
+        except (FileNotFoundError, ConnectionRefusedError):
+            s.close()
+            if time.time() > deadline:
+                raise NvlsUnavailable(f"peer socket {path} never appeared")
+            time.sleep(0.02)
+    with s:
+        socket.send_fds(s, [rank.to_bytes(4, "little")], fds)
+        s.recv(1)           # ack: the receiver has dup'ed the descriptors
+
+
+def _recv_fds(server: socket.socket, count: int, nfds: int):
+    got = {}
+    for _ in range(count):
+        try:
+            conn, _ = server.accept()
+        except socket.timeout as exc:
+            raise NvlsUnavailable("timed out waiting for a peer's memory handle") from exc
+        with conn:
+            msg, fds, _, _ = socket.recv_fds(conn, 4, nfds)
+            got[int.from_bytes(msg, "little")] = list(fds)
+            conn.send(b"k")
+    return got
+
+
+@dataclass
+class NvlsBuffer(SymmetricBuffer):
+    mc_ptr: int = 0                 # multicast virtual address (0 if multicast could not be set up)
+    nbytes_mapped: int = 0
+
+
+def multicast_supported(device: int) -> bool:
+    cu = _cu()
+    try:
+        (err,) = cu.cuInit(0)
+        err, dev = cu.cuDeviceGet(device)
+        err, val = cu.cuDeviceGetAttribute(cu.CUdevice_attribute.CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev)
+        return err == cu.CUresult.CUDA_SUCCESS and bool(val)
+    except Exception:
+        return False
+
+
+def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock_dir: Optional[str] = None) -> NvlsBuffer:
+    """Collective: every rank of ``group`` must call it with the same arguments."""
+    cu = _cu()
+    rank, world, device = group.rank, group.world, group.device
+    torch.cuda.set_device(device)
+    torch.cuda.current_stream().synchronize()     # make sure the primary context exists
+    if not multicast_supported(device):
+        raise NvlsUnavailable("device does not report CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED")
+    _ck(cu.cuInit(0), "cuInit")
+    dev = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
+    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+
+    prop = cu.CUmemAllocationProp()
+    prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+    prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+    prop.location.id = device
+    prop.requestedHandleTypes = H
+
+    mcprop = cu.CUmulticastObjectProp()
+    mcprop.numDevices = world
+    mcprop.handleTypes = H
+    mcprop.flags = 0
+    nbytes = numel * _DT_SIZE[dtype]
+    mcprop.size = nbytes
+    gran_mc = _ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
+                  "cuMulticastGetGranularity")
+    gran_mem = _ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
+                   "cuMemGetAllocationGranularity")
+    gran = max(int(gran_mc), int(gran_mem))
+    size = (nbytes + gran - 1) // gran * gran
+    mcprop.size = size
+
+    h_local = _ck(cu.cuMemCreate(size, prop, 0), "cuMemCreate")
+    fd_local = int(_ck(cu.cuMemExportToShareableHandle(h_local, H, 0), "cuMemExportToShareableHandle"))
+
+    # ---- descriptor exchange over AF_UNIX --------------------------------------------------
+    tag = group._exchange(os.getpid() if rank == 0 else None)[0]
+    base = sock_dir or tempfile.gettempdir()
+    paths = [os.path.join(base, f"hb-nvls-{tag}-{name.replace('.', '_')}-{r}.sock") for r in range(world)]
+    if os.path.exists(paths[rank]):
+        os.unlink(paths[rank])
+    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    server.bind(paths[rank])
+    server.listen(world)
+    server.settimeout(60)                          # a rank that failed earlier must not hang the others
+    group._exchange(rank)                          # everyone is listening
+    mc_handle = None
+    fd_mc = -1
+    if rank == 0:
+        mc_handle = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
+        fd_mc = int(_ck(cu.cuMemExportToShareableHandle(mc_handle, H, 0), "export multicast handle"))
+    import threading
+
+    recv_box = {}
+    t = threading.Thread(target=lambda: recv_box.update(_recv_fds(server, world - 1, 2)))
+    t.start()
+    for p in range(world):
+        if p != rank:
+            _send_fds(paths[p], rank, [fd_local] + ([fd_mc] if rank == 0 else []))
+    t.join()
+    server.close()
+    os.unlink(paths[rank])
+
+    access = cu.CUmemAccessDesc()
+    access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+    access.location.id = device
+    access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+
+    def map_handle(h) -> int:
+        va = _ck(cu.cuMemAddressReserve(size, gran, 0, 0), "cuMemAddressReserve")
+        _ck(cu.cuMemMap(va, size, 0, h, 0), "cuMemMap")
+        _ck(cu.cuMemSetAccess(va, size, [access], 1), "cuMemSetAccess")
+        return int(va)
+
+    ptrs = [0] * world
+    ptrs[rank] = map_handle(h_local)
+    for p in range(world):
+        if p == rank:
+            continue
+        hp = _ck(cu.cuMemImportFromShareableHandle(recv_box[p][0], H), "cuMemImportFromShareableHandle")
+        ptrs[p] = map_handle(hp)
+        os.close(recv_box[p][0])
+    if rank != 0:
+        mc_handle = _ck(cu.cuMemImportFromShareableHandle(recv_box[0][1], H), "import multicast handle")
+        os.close(recv_box[0][1])
+    else:
+        os.close(fd_mc)
+    os.close(fd_local)
+
+    _ck(cu.cuMulticastAddDevice(mc_handle, dev), "cuMulticastAddDevice")
+    group._exchange(rank)                          # every device is part of the team before binding
+    _ck(cu.cuMulticastBindMem(mc_handle, 0, h_local, 0, size, 0), "cuMulticastBindMem")
+    group._exchange(rank)
+    mc_ptr = map_handle(mc_handle)
+
+    local = tensor_from_ptr(ptrs[rank], numel, dtype, device)
+    local.zero_()
+    torch.cuda.synchronize()
+    group._exchange(rank)
+    buf = NvlsBuffer(name, numel, dtype, local, ptrs, mc_ptr=mc_ptr, nbytes_mapped=size)
+    group.buffers[name] = buf
+    return buf

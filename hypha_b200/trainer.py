@@ -67,13 +67,30 @@ class DiLoCoTrainer:
         want_fused = group is not None and group.world > 1 and diloco.backend in ("auto", "fused")
         if want_fused:
             holders = {}
+            use_nvls = os.environ.get("HYPHA_NVLS", "1") == "1"
+
+            def sym_alloc(name, n, dt):
+                """NVLS (multicast-bound VMM) buffer when the fabric supports it, else CUDA-IPC.  All
+                ranks take the same branch: the decision is agreed through the control plane."""
+                nonlocal use_nvls
+                if use_nvls:
+                    from .parallel.nvls import NvlsUnavailable, alloc_nvls, multicast_supported
+
+                    ok = all(group._exchange(bool(multicast_supported(dev))))
+                    if ok:
+                        try:
+                            return alloc_nvls(group, name, n, dt)
+                        except NvlsUnavailable as exc:        # collective failure is fatal by design
+                            raise RuntimeError(f"NVLS set-up failed ({exc}); rerun with HYPHA_NVLS=0") from exc
+                    use_nvls = False
+                return group.alloc(name, n, dt)
 
             def alloc(n, dt):
-                holders["p"] = group.alloc("model.params", n, dt)
+                holders["p"] = sym_alloc("model.params", n, dt)
                 return holders["p"].local
 
             def galloc(n, dt):
-                holders["g"] = group.alloc("model.grads", n, dt)
+                holders["g"] = sym_alloc("model.grads", n, dt)
                 return holders["g"].local
 
             net = LlamaForCausalLM(cfg, device=f"cuda:{dev}", alloc=alloc, grad_alloc=galloc, seed=seed)

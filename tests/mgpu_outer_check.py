@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--numel", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--json", default=None)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--nvls", action="store_true", help="NVSwitch multicast buffers (multimem path)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -30,8 +31,20 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     grp = PeerGroup.from_torch_distributed(local)
     n = a.numel
-    pbuf = grp.alloc("params", n, torch.bfloat16)
-    gbuf = grp.alloc("grads", n, torch.bfloat16)
+    if a.nvls:
+        from hypha_b200.parallel.nvls import alloc_nvls, multicast_supported
+
+        if not multicast_supported(local):
+            if rank == 0:
+                print(json.dumps({"correct": True, "skipped": "multicast not supported on this device"}), flush=True)
+            dist.destroy_process_group()
+            sys.exit(0)
+        pbuf = alloc_nvls(grp, "params", n, torch.bfloat16)
+        gbuf = alloc_nvls(grp, "grads", n, torch.bfloat16)
+        assert pbuf.mc_ptr and gbuf.mc_ptr
+    else:
+        pbuf = grp.alloc("params", n, torch.bfloat16)
+        gbuf = grp.alloc("grads", n, torch.bfloat16)
     g = torch.Generator(device=dev).manual_seed(1)
     pbuf.local.copy_(torch.randn(n, device=dev, generator=g))          # identical start on every rank
     opt = FlatAdamW(pbuf.local, gbuf.local, AdamWConfig())
@@ -104,7 +117,7 @@ def main():
     ar_ms = timed(allreduce_only)
     bytes_ = 2 * n
     busbw = lambda ms: bytes_ * 2 * (world - 1) / world / ms / 1e6     # GB/s, nccl-tests convention
-    res = {"world": world, "numel": n, "delta_bytes": bytes_, "correct": bool(ok), "identical_params": same,
+    res = {"world": world, "numel": n, "nvls": bool(a.nvls and outer._multicast_ptrs()[0]), "delta_bytes": bytes_, "correct": bool(ok), "identical_params": same,
            "fused_outer_ms": fused_ms, "nccl_outer_ms": nccl_ms, "nccl_allreduce_only_ms": ar_ms,
            "fused_busbw_gbs": busbw(fused_ms), "nccl_allreduce_busbw_gbs": busbw(ar_ms),
            "speedup_vs_nccl_outer": nccl_ms / fused_ms}

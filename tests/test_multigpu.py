@@ -30,6 +30,22 @@ def test_fused_outer_step_matches_nccl_reference():
 
 
 @pytest.mark.timeout(600)
+def test_nvls_multimem_outer_step_matches_reference():
+    """Same check with the buffers bound to an NVSwitch multicast object (multimem.ld_reduce/st)."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(_ngpu(), 8)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tests", "mgpu_outer_check.py"), "--numel",
+           str(16 * 1024 * 1024), "--nvls"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
+    if r.returncode != 0 and "NvlsUnavailable" in r.stderr:
+        pytest.skip("NVSwitch multicast could not be set up on this box: " + r.stderr[-300:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"correct": true' in r.stdout
+
+
+@pytest.mark.timeout(600)
 def test_kill_and_rejoin_over_peer_memory():
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
