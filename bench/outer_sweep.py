@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--iters", type=int, default=5)
     ap.add_argument("--json", default=None)
     ap.add_argument("--nvls", action="store_true", help="also time the NVSwitch-multicast (multimem) variant")
+    ap.add_argument("--tune-mb", type=float, default=0, help="at this size also sweep chunks x link CTAs")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
@@ -82,14 +83,35 @@ def main():
         sub_g = type(gbuf)(gbuf.name, n, gbuf.dtype, g, gbuf.peer_ptrs, **kw(gbuf))
         outer = DiLoCoOuter(_Opt, DiLoCoConfig(backend="fused"), grp, sub_p, sub_g)
         iters = a.iters if mb >= 64 else 20
-        outer.use_nvls = False
-        fused = timed(outer.step, iters)
-        st = outer.check()
-        nvls_ms = None
-        if a.nvls:
-            outer.use_nvls = True
-            nvls_ms = timed(outer.step, iters)
+        st = (0, 0)
+
+        def variant(nvls, chunks, link_ctas=0):
+            nonlocal st
+            outer.use_nvls = nvls
+            os.environ["HYPHA_OUTER_CHUNKS"] = str(chunks)
+            os.environ["HYPHA_OUTER_LINK_CTAS"] = str(link_ctas)
+            ms = timed(outer.step, iters)
             st = tuple(max(x, y) for x, y in zip(st, outer.check()))
+            return ms
+
+        plain = variant(False, 1)                       # A | B | C, P2P loads/stores
+        piped = variant(False, 0)                       # auto-chunked software pipeline
+        fused = min(plain, piped)
+        nvls_ms = nvls_plain = nvls_piped = None
+        if a.nvls:
+            nvls_plain = variant(True, 1)
+            nvls_piped = variant(True, 0)
+            nvls_ms = min(nvls_plain, nvls_piped)
+        tune = None
+        if a.tune_mb and abs(mb - a.tune_mb) < 1e-6:
+            tune = []
+            for nv in ([False, True] if a.nvls else [False]):
+                for k in (2, 4, 8, 16):
+                    for b in (16, 32, 48, 72, 100):
+                        tune.append({"nvls": nv, "chunks": k, "link_ctas": b, "ms": variant(nv, k, b)})
+            if rank == 0:
+                best = min(tune, key=lambda t: t["ms"])
+                print("tune best:", json.dumps(best), flush=True)
         ar = timed(lambda: dist.all_reduce(g), iters)
         CH = 1 << 28
         try:
@@ -122,7 +144,9 @@ def main():
         bus = lambda ms: S * 2 * (world - 1) / world / ms / 1e6
         row = {"delta_mb": S / 2 ** 20, "numel": n, "status": list(st), "fused_ms": fused, "nccl_allreduce_ms": ar,
                "nccl_full_outer_ms": full, "fused_busbw_gbs": bus(fused),
-               "fused_nvls_ms": nvls_ms, "fused_nvls_busbw_gbs": bus(nvls_ms) if nvls_ms else None, "nccl_allreduce_busbw_gbs": bus(ar),
+               "fused_plain_ms": plain, "fused_pipelined_ms": piped, "pipeline_shape": list(outer._pipeline_shape()),
+               "fused_nvls_ms": nvls_ms, "fused_nvls_busbw_gbs": bus(nvls_ms) if nvls_ms else None,
+               "nvls_plain_ms": nvls_plain, "nvls_pipelined_ms": nvls_piped, "tune": tune, "nccl_allreduce_busbw_gbs": bus(ar),
                "fused_frac_of_770": bus(fused) / PEER_COPY_GBS, "fused_frac_of_900": bus(fused) / NVLINK_NOMINAL_GBS,
                "speedup_vs_nccl_full": (full / fused) if full else None}
         rows.append(row)

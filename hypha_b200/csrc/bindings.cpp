@@ -110,7 +110,8 @@ PYBIND11_MODULE(_C, m) {
            std::vector<u64> flag_peers, u64 master, std::vector<int64_t> seg_begin,
            std::vector<int64_t> seg_len, std::vector<u64> seg_theta, std::vector<u64> seg_mom, int64_t n,
            int rank, uint32_t member_mask, uint32_t epoch, float lr, float mu, int first_round,
-           int num_ctas, u64 mc_delta, u64 mc_param, u64 s) {
+           int num_ctas, u64 mc_delta, u64 mc_param, std::vector<int64_t> lay_begin,
+           std::vector<int64_t> lay_len, int num_chunks, int b_ctas, u64 s) {
           hb::OuterStepArgs a{};
           if (delta_peers.size() > 8) throw std::runtime_error("at most 8 ranks per NVSwitch box");
           if (seg_begin.size() > 8 || seg_begin.size() != seg_len.size() ||
@@ -138,6 +139,15 @@ PYBIND11_MODULE(_C, m) {
           a.inv_world = 1.0f / (float)(world > 0 ? world : 1);
           a.mc_delta = P<const bf16>(mc_delta);
           a.mc_param = P<bf16>(mc_param);
+          if (lay_begin.empty()) { lay_begin = {0}; lay_len = {n}; }
+          if (lay_begin.size() > 8 || lay_begin.size() != lay_len.size())
+            throw std::runtime_error("bad shard layout");
+          a.lay_n = (int)lay_begin.size();
+          for (size_t i = 0; i < lay_begin.size(); ++i) { a.lay_begin[i] = lay_begin[i]; a.lay_len[i] = lay_len[i]; }
+          if (num_chunks < 1) num_chunks = 1;
+          if (num_chunks > 30) num_chunks = 30;   // barrier tokens: epoch*32 + stage + 1
+          a.num_chunks = num_chunks;
+          a.b_ctas = b_ctas;
           hb::diloco_outer_step_fused(a, num_ctas, S(s));
           check_last("diloco_outer_step_fused");
         });

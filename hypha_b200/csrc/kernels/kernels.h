@@ -66,6 +66,13 @@ struct OuterStepArgs {
   // When set and every rank participates, phase B uses multimem.ld_reduce / multimem.st.
   const bf16* mc_delta;
   bf16* mc_param;
+  // Shard layout of the whole vector (independent of who currently owns which shard) and the
+  // software-pipeline shape: chunk c = the c-th 1/num_chunks slice of every shard.
+  int lay_n;
+  int64_t lay_begin[8];
+  int64_t lay_len[8];
+  int num_chunks;               // 1 = plain A | B | C
+  int b_ctas;                   // CTAs that drive NVLink (phase B) while the rest stream HBM
 };
 void diloco_outer_step_fused(const OuterStepArgs& a, int num_ctas, cudaStream_t s);
 // Local Nesterov step.  delta_sum == null: single worker, exact fp32

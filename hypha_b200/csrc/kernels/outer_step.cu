@@ -18,7 +18,7 @@
 // NVLink while the owner's fp32 theta_outer absorbs the exact update (error
 // feedback), so no precision is lost to the 16-bit wire format.
 //
-// Phases (all inside one cooperative launch per rank):
+// Phases (all inside one cooperative launch per rank; software-pipelined over chunks for large n):
 //   A  local : delta = bf16(master - anchor)                 -> symmetric buffer
 //   -- cross-GPU flag barrier (st.release.sys / ld.acquire.sys, epoch-stamped) --
 //   B  owner : g = mean_r delta_r[shard] (P2P 16-byte loads from every peer)
@@ -123,53 +123,98 @@ __device__ void cross_gpu_barrier(const OuterStepArgs& a, LocalSync* ls, int slo
   grid_barrier(&ls->grid_bar, gridDim.x);
 }
 
-__global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs a,
-                                                                   LocalSync* ls,
-                                                                   uint64_t timeout_ns) {
-  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-
-  // ---- Phase A: local pseudo-gradient relative to the common anchor ---------
-  // (two 16-byte vectors per thread per trip: all loads are issued before the first use)
-  {
-    bf16* my_delta = const_cast<bf16*>(a.delta_peers[a.rank]);
-    const bf16* anchor = a.anchor_peers[a.rank];
-    const int64_t nvec = a.n >> 3;
-    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
-      const int64_t i1 = i + nthreads;
-      const bool two = i1 < nvec;
-      const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
-      float w0[8], w1[8], x0[8], x1[8];
-      *reinterpret_cast<float4*>(w0) = ld_stream_f32x4(a.master + off0);
-      *reinterpret_cast<float4*>(w0 + 4) = ld_stream_f32x4(a.master + off0 + 4);
-      *reinterpret_cast<float4*>(w1) = ld_stream_f32x4(a.master + off1);
-      *reinterpret_cast<float4*>(w1 + 4) = ld_stream_f32x4(a.master + off1 + 4);
-      const bf16x8 a0 = ld_stream_bf16x8(anchor + off0), a1 = ld_stream_bf16x8(anchor + off1);
-      unpack8(a0, x0);
-      unpack8(a1, x1);
+// ---- Phase A: local pseudo-gradient relative to the common anchor, elements [base+8*lo, base+8*hi)
+// (two 16-byte vectors per thread per trip: all loads are issued before the first use)
+__device__ __forceinline__ void phase_a(const OuterStepArgs& a, int64_t base, int64_t lo, int64_t hi,
+                                        int64_t tid, int64_t nthreads) {
+  bf16* my_delta = const_cast<bf16*>(a.delta_peers[a.rank]) + base;
+  const bf16* anchor = a.anchor_peers[a.rank] + base;
+  const float* master = a.master + base;
+  for (int64_t i = lo + tid; i < hi; i += 2 * nthreads) {
+    const int64_t i1 = i + nthreads;
+    const bool two = i1 < hi;
+    const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
+    float w0[8], w1[8], x0[8], x1[8];
+    *reinterpret_cast<float4*>(w0) = ld_stream_f32x4(master + off0);
+    *reinterpret_cast<float4*>(w0 + 4) = ld_stream_f32x4(master + off0 + 4);
+    *reinterpret_cast<float4*>(w1) = ld_stream_f32x4(master + off1);
+    *reinterpret_cast<float4*>(w1 + 4) = ld_stream_f32x4(master + off1 + 4);
+    const bf16x8 a0 = ld_stream_bf16x8(anchor + off0), a1 = ld_stream_bf16x8(anchor + off1);
+    unpack8(a0, x0);
+    unpack8(a1, x1);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) { w0[e] -= x0[e]; w1[e] -= x1[e]; }
-      st_bf16x8(my_delta + off0, pack8(w0));
-      if (two) st_bf16x8(my_delta + off1, pack8(w1));
+    for (int e = 0; e < 8; ++e) { w0[e] -= x0[e]; w1[e] -= x1[e]; }
+    st_bf16x8(my_delta + off0, pack8(w0));
+    if (two) st_bf16x8(my_delta + off1, pack8(w1));
+  }
+}
+
+// ---- Phase C: adopt the new global weights locally -------------------------------------------
+__device__ __forceinline__ void phase_c(const OuterStepArgs& a, int64_t base, int64_t lo, int64_t hi,
+                                        int64_t tid, int64_t nthreads) {
+  const bf16* param = a.param_peers[a.rank] + base;
+  bf16* anchor = a.anchor_peers[a.rank] + base;
+  float* master = a.master + base;
+  for (int64_t i = lo + tid; i < hi; i += 2 * nthreads) {
+    const int64_t i1 = i + nthreads;
+    const bool two = i1 < hi;
+    const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
+    const uint4 r0 = ld_peer_16(param + off0);   // written by remote owners: bypass L1
+    const uint4 r1 = ld_peer_16(param + off1);
+    float w[8];
+    unpack8(*reinterpret_cast<const bf16x8*>(&r0), w);
+    *reinterpret_cast<float4*>(master + off0) = *reinterpret_cast<float4*>(w);
+    *reinterpret_cast<float4*>(master + off0 + 4) = *reinterpret_cast<float4*>(w + 4);
+    *reinterpret_cast<uint4*>(anchor + off0) = r0;
+    if (two) {
+      unpack8(*reinterpret_cast<const bf16x8*>(&r1), w);
+      *reinterpret_cast<float4*>(master + off1) = *reinterpret_cast<float4*>(w);
+      *reinterpret_cast<float4*>(master + off1 + 4) = *reinterpret_cast<float4*>(w + 4);
+      *reinterpret_cast<uint4*>(anchor + off1) = r1;
     }
   }
-  cross_gpu_barrier(a, ls, 0, a.epoch * 2u + 1u, timeout_ns, 1u);
-  if (ld_acquire_gpu(&ls->status) != 0u) return;
+}
 
-  // ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast --------
-  // Two vectors per thread per trip: up to 16 peer loads of 16 B are in flight per thread before
-  // the first one is consumed (NVLink latency ~2 us needs deep memory-level parallelism).
-  const bool nvls = a.mc_delta != nullptr && a.mc_param != nullptr;
-  for (int seg = 0; nvls && seg < a.num_segs; ++seg) {
-    // ---- NVLS variant: the switch reduces the N deltas and replicates the new weights ----
-    const bf16* anchor = a.anchor_peers[a.rank];
-    float* theta_outer = a.seg_theta[seg];
-    float* momentum = a.seg_mom[seg];
-    const int64_t seg_begin = a.seg_begin[seg];
-    const int64_t nvec = a.seg_len[seg] >> 3;
-    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
-      const int64_t iv[2] = {i, i + nthreads};
-      const int cnt = iv[1] < nvec ? 2 : 1;
+// Nesterov on 8 lanes given the summed delta; returns the packed bf16 weights.
+__device__ __forceinline__ uint4 nesterov8(const OuterStepArgs& a, const uint4& sum_raw,
+                                           const bf16* anchor_at, float* theta_at, float* mom_at) {
+  float acc[8], x[8], th[8], mo[8];
+  unpack8(*reinterpret_cast<const bf16x8*>(&sum_raw), acc);
+  unpack8(ld_stream_bf16x8(anchor_at), x);
+  *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_at);
+  *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_at + 4);
+  *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(mom_at);
+  *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(mom_at + 4);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const float g = acc[e] * a.inv_world + (x[e] - th[e]);
+    mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
+    th[e] += a.lr * (a.mu * mo[e] + g);
+  }
+  *reinterpret_cast<float4*>(theta_at) = *reinterpret_cast<float4*>(th);
+  *reinterpret_cast<float4*>(theta_at + 4) = *reinterpret_cast<float4*>(th + 4);
+  *reinterpret_cast<float4*>(mom_at) = *reinterpret_cast<float4*>(mo);
+  *reinterpret_cast<float4*>(mom_at + 4) = *reinterpret_cast<float4*>(mo + 4);
+  bf16x8 pn = pack8(th);
+  return *reinterpret_cast<uint4*>(&pn);
+}
+
+// ---- Phase B: owner-shard reduce over peers + Nesterov + broadcast, vectors [lo,hi) of a segment
+// P2P variant: two vectors per thread per trip, i.e. up to 16 peer loads of 16 B in flight per
+// thread before the first one is consumed (NVLink latency ~2 us needs deep memory-level
+// parallelism).  NVLS variant: the switch reduces the N deltas (multimem.ld_reduce) and replicates
+// the new weights (multimem.st), so each byte crosses this GPU's links once per direction.
+template <bool kNvls>
+__device__ __forceinline__ void phase_b(const OuterStepArgs& a, int seg, int64_t lo, int64_t hi,
+                                        int64_t tid, int64_t nthreads) {
+  const int64_t seg_begin = a.seg_begin[seg];
+  const bf16* anchor = a.anchor_peers[a.rank] + seg_begin;
+  float* theta_outer = a.seg_theta[seg];
+  float* momentum = a.seg_mom[seg];
+  for (int64_t i = lo + tid; i < hi; i += 2 * nthreads) {
+    const int64_t iv[2] = {i, i + nthreads};
+    const int cnt = iv[1] < hi ? 2 : 1;
+    if constexpr (kNvls) {
       uint4 red[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u)
@@ -178,39 +223,11 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
       for (int u = 0; u < 2; ++u) {
         if (u < cnt) {
           const int64_t loc = iv[u] << 3;
-          const int64_t off = seg_begin + loc;
-          float acc[8], x[8], th[8], mo[8];
-          unpack8(*reinterpret_cast<bf16x8*>(&red[u]), acc);
-          unpack8(ld_stream_bf16x8(anchor + off), x);
-          *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
-          *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
-          *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
-          *reinterpret_cast<float4*>(mo + 4) = *reinterpret_cast<const float4*>(momentum + loc + 4);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const float g = acc[e] * a.inv_world + (x[e] - th[e]);
-            mo[e] = a.first_round ? g : (a.mu * mo[e] + g);
-            th[e] += a.lr * (a.mu * mo[e] + g);
-          }
-          *reinterpret_cast<float4*>(theta_outer + loc) = *reinterpret_cast<float4*>(th);
-          *reinterpret_cast<float4*>(theta_outer + loc + 4) = *reinterpret_cast<float4*>(th + 4);
-          *reinterpret_cast<float4*>(momentum + loc) = *reinterpret_cast<float4*>(mo);
-          *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
-          bf16x8 pn = pack8(th);
-          multimem_st_bf16x8(a.mc_param + off, *reinterpret_cast<uint4*>(&pn));
+          const uint4 pv = nesterov8(a, red[u], anchor + loc, theta_outer + loc, momentum + loc);
+          multimem_st_bf16x8(a.mc_param + seg_begin + loc, pv);
         }
       }
-    }
-  }
-  for (int seg = 0; !nvls && seg < a.num_segs; ++seg) {
-    const bf16* anchor = a.anchor_peers[a.rank];
-    float* theta_outer = a.seg_theta[seg];
-    float* momentum = a.seg_mom[seg];
-    const int64_t seg_begin = a.seg_begin[seg];
-    const int64_t nvec = a.seg_len[seg] >> 3;
-    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
-      const int64_t iv[2] = {i, i + nthreads};
-      const int cnt = iv[1] < nvec ? 2 : 1;
+    } else {
       uint4 raw[2][8];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -226,7 +243,6 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
       for (int u = 0; u < 2; ++u) {
         if (u < cnt) {
           const int64_t loc = iv[u] << 3;
-          const int64_t off = seg_begin + loc;
           float acc[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -239,8 +255,9 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
               for (int e = 0; e < 8; ++e) acc[e] += d[e];
             }
           }
+          // the fp32 sum is handed over exactly: nesterov8 takes the sum in bf16 only for NVLS
           float x[8], th[8], mo[8];
-          unpack8(ld_stream_bf16x8(anchor + off), x);
+          unpack8(ld_stream_bf16x8(anchor + loc), x);
           *reinterpret_cast<float4*>(th) = *reinterpret_cast<const float4*>(theta_outer + loc);
           *reinterpret_cast<float4*>(th + 4) = *reinterpret_cast<const float4*>(theta_outer + loc + 4);
           *reinterpret_cast<float4*>(mo) = *reinterpret_cast<const float4*>(momentum + loc);
@@ -257,6 +274,7 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
           *reinterpret_cast<float4*>(momentum + loc + 4) = *reinterpret_cast<float4*>(mo + 4);
           bf16x8 pn = pack8(th);
           const uint4 pv = *reinterpret_cast<uint4*>(&pn);
+          const int64_t off = seg_begin + loc;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
             if ((a.member_mask >> r) & 1u) st_peer_16(a.param_peers[r] + off, pv);
@@ -265,31 +283,60 @@ __global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs
       }
     }
   }
-  cross_gpu_barrier(a, ls, 1, a.epoch * 2u + 2u, timeout_ns, 2u);
-  if (ld_acquire_gpu(&ls->status) != 0u) return;
+}
 
-  // ---- Phase C: adopt the new global weights locally -------------------------
-  {
-    const bf16* param = a.param_peers[a.rank];
-    bf16* anchor = a.anchor_peers[a.rank];
-    const int64_t nvec = a.n >> 3;
-    for (int64_t i = tid; i < nvec; i += 2 * nthreads) {
-      const int64_t i1 = i + nthreads;
-      const bool two = i1 < nvec;
-      const int64_t off0 = i << 3, off1 = (two ? i1 : i) << 3;
-      const uint4 r0 = ld_peer_16(param + off0);   // written by remote owners: bypass L1
-      const uint4 r1 = ld_peer_16(param + off1);
-      float w[8];
-      unpack8(*reinterpret_cast<const bf16x8*>(&r0), w);
-      *reinterpret_cast<float4*>(a.master + off0) = *reinterpret_cast<float4*>(w);
-      *reinterpret_cast<float4*>(a.master + off0 + 4) = *reinterpret_cast<float4*>(w + 4);
-      *reinterpret_cast<uint4*>(anchor + off0) = r0;
-      if (two) {
-        unpack8(*reinterpret_cast<const bf16x8*>(&r1), w);
-        *reinterpret_cast<float4*>(a.master + off1) = *reinterpret_cast<float4*>(w);
-        *reinterpret_cast<float4*>(a.master + off1 + 4) = *reinterpret_cast<float4*>(w + 4);
-        *reinterpret_cast<uint4*>(anchor + off1) = r1;
+// Vector range [lo,hi) of chunk c out of K of a shard of `len` elements.
+__device__ __forceinline__ void chunk_slice(int64_t len, int K, int c, int64_t& lo, int64_t& hi) {
+  const int64_t nv = len >> 3;
+  const int64_t per = (nv + K - 1) / K;
+  lo = c * per < nv ? c * per : nv;
+  hi = lo + per < nv ? lo + per : nv;
+}
+
+// Software pipeline over K chunks (chunk c = the c-th 1/K slice of EVERY owner's shard):
+//   stage s :  A(chunk s)  |  B(chunk s-1)  |  C(chunk s-2)        -- cross-GPU barrier --
+// A and C are local HBM streams, B is NVLink traffic, so within a stage the CTAs are split by role
+// (`b_ctas` CTAs drive the links, the rest stream HBM) and the two resources are busy at the same
+// time.  K = 1 degenerates to the plain A | B | C schedule with two barriers.
+__global__ void __launch_bounds__(512, 1) diloco_outer_step_kernel(OuterStepArgs a,
+                                                                   LocalSync* ls,
+                                                                   uint64_t timeout_ns) {
+  const bool nvls = a.mc_delta != nullptr && a.mc_param != nullptr;
+  const int K = a.num_chunks < 1 ? 1 : a.num_chunks;
+  for (int stage = 0; stage < K + 2; ++stage) {
+    const bool has_a = stage < K, has_b = stage >= 1 && stage <= K, has_c = stage >= 2;
+    const bool has_local = has_a || has_c;
+    int nb = 0;                                   // CTAs [0, nb) drive phase B in this stage
+    if (has_b) nb = has_local ? min(max(a.b_ctas, 1), (int)gridDim.x - 1) : (int)gridDim.x;
+    if ((int)blockIdx.x < nb) {
+      const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+      const int64_t nthreads = (int64_t)nb * blockDim.x;
+      for (int seg = 0; seg < a.num_segs; ++seg) {
+        int64_t lo, hi;
+        chunk_slice(a.seg_len[seg], K, stage - 1, lo, hi);
+        if (nvls) phase_b<true>(a, seg, lo, hi, tid, nthreads);
+        else phase_b<false>(a, seg, lo, hi, tid, nthreads);
       }
+    } else {
+      const int64_t tid = (int64_t)(blockIdx.x - nb) * blockDim.x + threadIdx.x;
+      const int64_t nthreads = (int64_t)(gridDim.x - nb) * blockDim.x;
+      for (int r = 0; r < a.lay_n; ++r) {
+        int64_t lo, hi;
+        if (has_a) {
+          chunk_slice(a.lay_len[r], K, stage, lo, hi);
+          phase_a(a, a.lay_begin[r], lo, hi, tid, nthreads);
+        }
+        if (has_c) {
+          chunk_slice(a.lay_len[r], K, stage - 2, lo, hi);
+          phase_c(a, a.lay_begin[r], lo, hi, tid, nthreads);
+        }
+      }
+    }
+    if (stage < K + 1) {
+      // a peer that never shows up is detected at the first barrier, before any state changed
+      cross_gpu_barrier(a, ls, stage & 1, a.epoch * 32u + (uint32_t)stage + 1u, timeout_ns,
+                        stage == 0 ? 1u : 2u);
+      if (ld_acquire_gpu(&ls->status) != 0u) return;
     }
   }
 }

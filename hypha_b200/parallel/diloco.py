@@ -48,6 +48,8 @@ class DiLoCoConfig:
     outer_momentum: float = 0.9
     backend: str = "auto"               # auto | fused | nccl | local
     num_ctas: int = 0                   # 0 = one CTA per SM
+    pipeline_chunks: int = 0            # fused backend: 0 = auto (by size), 1 = plain A|B|C, K = K-deep pipeline
+    link_ctas: int = 0                  # CTAs driving NVLink while the others stream HBM (0 = auto)
     timeout_ms: int = 30000
 
 
@@ -223,6 +225,7 @@ class DiLoCoOuter:
             self.momentum = torch.zeros(self.shard_len, dtype=torch.float32, device=dev)
             # segments owned by this rank: its shard + shards adopted from dropped ranks
             self.segments = {self.rank: (self.shard_begin, self.shard_len, self.theta_outer, self.momentum)}
+            self.layout = [shard_bounds(self.n, world, r) for r in range(world)]
             self.attempt = 0
             self.use_nvls = True                    # used when the buffers carry a multicast address
             load_C().set_outer_timeout_ms(int(cfg.timeout_ms))
@@ -261,7 +264,9 @@ class DiLoCoOuter:
                                       [l for _, l, _, _ in segs], [t.data_ptr() for _, _, t, _ in segs],
                                       [m.data_ptr() for _, _, _, m in segs], self.n, self.rank,
                                       self.member_mask, self.attempt, cfg.outer_lr, cfg.outer_momentum,
-                                      first, cfg.num_ctas, *self._multicast_ptrs(), s)
+                                      first, cfg.num_ctas, *self._multicast_ptrs(),
+                                      [b for b, _ in self.layout], [l for _, l in self.layout],
+                                      *self._pipeline_shape(), s)
             nmem = bin(self.member_mask).count("1")
             wire = 2 * sum(l for _, l, _, _ in segs) * (nmem - 1)
             self.group.counters.add("/hypha-peer-memory/outer-step", inbound=wire, outbound=wire)
@@ -354,6 +359,19 @@ class DiLoCoOuter:
             dead = [r for r in range(self.world) if (missing >> r) & 1]
             self.drop_ranks(dead)
         raise RuntimeError("outer step kept timing out")
+
+    def _pipeline_shape(self) -> tuple:
+        """(num_chunks, link_ctas).  Pipelining pays once a chunk's HBM/NVLink time dwarfs the extra
+        cross-GPU barriers (~15 us each): one chunk per 128 MB of delta, at most 8."""
+        import os
+
+        k = int(os.environ.get("HYPHA_OUTER_CHUNKS", self.cfg.pipeline_chunks))
+        if k <= 0:
+            k = max(1, min(8, (2 * self.n) // (128 << 20)))
+        b = int(os.environ.get("HYPHA_OUTER_LINK_CTAS", self.cfg.link_ctas))
+        if b <= 0:
+            b = 48
+        return (k, b)
 
     def _multicast_ptrs(self) -> tuple:
         """(mc_delta, mc_param) when both buffers are NVLS-bound and every rank participates; the

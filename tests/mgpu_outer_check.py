@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--numel", type=int, default=64 * 1024 * 1024)
     ap.add_argument("--json", default=None)
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--chunks", type=int, default=0, help="software-pipeline depth of the fused kernel (0 = auto)")
     ap.add_argument("--nvls", action="store_true", help="NVSwitch multicast buffers (multimem path)")
     a = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -48,7 +49,7 @@ def main():
     g = torch.Generator(device=dev).manual_seed(1)
     pbuf.local.copy_(torch.randn(n, device=dev, generator=g))          # identical start on every rank
     opt = FlatAdamW(pbuf.local, gbuf.local, AdamWConfig())
-    cfg = DiLoCoConfig(backend="fused", outer_lr=0.7, outer_momentum=0.9)
+    cfg = DiLoCoConfig(backend="fused", outer_lr=0.7, outer_momentum=0.9, pipeline_chunks=a.chunks, link_ctas=40)
     outer = DiLoCoOuter(opt, cfg, grp, pbuf, gbuf)
     ok = True
     gr = torch.Generator(device=dev).manual_seed(100 + rank)
@@ -59,6 +60,10 @@ def main():
         anchor = outer.anchor_buf.local.float()
         delta = (opt.master - anchor).to(torch.bfloat16).float()
         dist.all_reduce(delta)
+        if a.nvls:
+            # the switch accumulates in fp32 but returns the N-way sum as bf16 (the precision of a bf16
+            # NCCL all-reduce); the P2P path keeps the fp32 sum
+            delta = delta.to(torch.bfloat16).float()
         gmean = delta / world + (anchor - th_full)
         mom_full = gmean.clone() if rnd == 0 else 0.9 * mom_full + gmean
         th_full = th_full + 0.7 * (0.9 * mom_full + gmean)

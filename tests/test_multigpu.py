@@ -17,13 +17,15 @@ def _ngpu():
 
 
 @pytest.mark.timeout(600)
-def test_fused_outer_step_matches_nccl_reference():
+@pytest.mark.parametrize("chunks", [1, 4])
+def test_fused_outer_step_matches_nccl_reference(chunks):
+    """chunks=1: plain A|B|C schedule; chunks=4: software-pipelined schedule with role-split CTAs."""
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs")
     n = min(_ngpu(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_outer_check.py"), "--numel",
-           str(16 * 1024 * 1024)]
+           str(16 * 1024 * 1024), "--chunks", str(chunks)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"correct": true' in r.stdout
@@ -37,7 +39,7 @@ def test_nvls_multimem_outer_step_matches_reference():
     n = min(_ngpu(), 8)
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
            "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tests", "mgpu_outer_check.py"), "--numel",
-           str(16 * 1024 * 1024), "--nvls"]
+           str(16 * 1024 * 1024), "--nvls", "--chunks", "3"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
     if r.returncode != 0 and "NvlsUnavailable" in r.stderr:
         pytest.skip("NVSwitch multicast could not be set up on this box: " + r.stderr[-300:])
