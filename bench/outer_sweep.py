@@ -112,6 +112,7 @@ def main():
             if rank == 0:
                 best = min(tune, key=lambda t: t["ms"])
                 print("tune best:", json.dumps(best), flush=True)
+            os.environ["HYPHA_OUTER_CHUNKS"] = os.environ["HYPHA_OUTER_LINK_CTAS"] = "0"
         ar = timed(lambda: dist.all_reduce(g), iters)
         CH = 1 << 28
         try:

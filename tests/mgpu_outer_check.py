@@ -76,7 +76,10 @@ def main():
         mism = (pbuf.local != want_p).float().mean().item()           # bf16 ties may round differently
         e3 = (opt.master - pbuf.local.float()).abs().max().item()
         e4 = (outer.anchor_buf.local != pbuf.local).sum().item()
-        good = st == (0, 0) and e1 < 1e-4 and mism < 1e-3 and e3 == 0 and e4 == 0
+        # NVLS: the in-switch reduction returns a bf16 sum (rounding mode unspecified) -> 1 bf16 ulp of
+        # the largest |sum| (~0.1) times lr*(1+mu)/N; replicas must still agree bit-for-bit (checked below)
+        tol_t, tol_p = (1e-3, 5e-2) if a.nvls else (1e-4, 1e-3)
+        good = st == (0, 0) and e1 < tol_t and mism < tol_p and e3 == 0 and e4 == 0
         ok = ok and good
         if rank == 0:
             print(f"round {rnd}: status={st} |theta-ref|max={e1:.2e} param-mismatch-frac={mism:.2e} "
