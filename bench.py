@@ -263,6 +263,19 @@ def main():
                "h2d_bytes_per_step": (trainer.h2d_bytes - h2d0) // args.steps,
                "d2h_bytes_per_step": 4, "ms_per_step": wall * 1e3 / args.steps}
 
+    # ---- outer-step wall time (BASELINE metric 2), device-timed on its own -------------------
+    outer_ms = None
+    if world > 1:
+        trainer.outer_step()
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        trainer.outer_step()
+        trainer.outer_step()
+        o1.record()
+        barrier()
+        outer_ms = max_over_ranks(o0.elapsed_time(o1)) / 2
+
     if rank == 0:
         out = {
             "metric": "tokens/sec (whole box, device-timed, max over ranks) Llama-3-8B DiLoCo H=100",
@@ -277,13 +290,15 @@ def main():
                 "parallelism": f"diloco-dp{world}", "inner_steps_H": args.inner_steps,
                 "outer_steps_in_timed_region": outer_in_region,
                 "outer_backend": trainer.outer.backend,
+                "outer_nvls": bool(trainer.outer.backend == "fused" and trainer.outer._multicast_ptrs()[0]),
+                "outer_pipeline": list(trainer.outer._pipeline_shape()) if trainer.outer.backend == "fused" else None,
                 "optimizer": f"fused flat AdamW, fp32 master, {args.state_dtype} moments",
                 "recompute_layers": recompute, "gemm_backend": ops.get_gemm_backend(),
                 "attention_backend": ops.get_attention_backend(),
                 "l2": "no flush needed: >16 GB of weights/activations streamed per step >> 126 MB L2",
             },
             "model_tflops_per_gpu": value / world * cfg.flops_per_token(S) / 1e12,
-            "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "outer_step_ms": outer_ms, "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
         print(json.dumps(out))
     if world > 1:

@@ -370,7 +370,10 @@ class DiLoCoOuter:
             k = max(1, min(8, (2 * self.n) // (128 << 20)))
         b = int(os.environ.get("HYPHA_OUTER_LINK_CTAS", self.cfg.link_ctas))
         if b <= 0:
-            b = 48
+            # share of the SMs that phase B needs to keep up with phases A+C: at N=2 B is itself
+            # HBM-heavy (~45 % of the bytes); from N=4 on it is NVLink-latency-bound and 48 CTAs of
+            # 16-byte loads (2 x 8 in flight per thread) cover the bandwidth-delay product
+            b = 66 if self.world <= 2 else 48
         return (k, b)
 
     def _multicast_ptrs(self) -> tuple:
