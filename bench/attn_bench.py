@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Attention forward micro-benchmark at the Llama-3-8B shape (B=2, S=4096, 32 q / 8 kv heads,
+"""Attention forward + backward micro-benchmark at the Llama-3-8B shape (B=2, S=4096, 32 q / 8 kv heads,
 D=128, causal): hand-written tcgen05 kernel vs cuDNN (torch SDPA) vs flash-attn 2.
 FLOPs counted as 4*B*H*S^2*D/2 (causal).  -> gpurun_out/attn_bench.json"""
 import json
@@ -42,9 +42,27 @@ def main():
                     row[name] = {"ms": ms, "tflops": flops / ms / 1e9}
                 except Exception as exc:
                     row[name] = {"error": repr(exc)[:200]}
-            a, _ = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
+            a, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
             b = _attention_sdpa(qkv, B, S, Hq, Hk, D)
             row["rel_err_vs_cudnn"] = ((a.float() - b.float()).norm() / b.float().norm()).item()
+            # ---- backward (2.5x the forward FLOPs): hand-written tcgen05 vs library fwd+bwd minus fwd
+            dout = torch.randn_like(a)
+            try:
+                ms = timeit(lambda: ops.attention_bwd_tcgen05(qkv, a, dout, lse, B, S, Hq, Hk, D))
+                row["bwd_tcgen05"] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
+            except Exception as exc:
+                row["bwd_tcgen05"] = {"error": repr(exc)[:200]}
+        for name in ("cudnn", "flash2"):
+            try:
+                ops.set_attention_backend(name)
+                q = qkv.clone().requires_grad_(True)
+                o = ops.attention_qkv(q, B, S, Hq, Hk, D)
+                g = torch.randn_like(o)
+                ms = timeit(lambda: torch.autograd.grad(o, q, g, retain_graph=True))
+                row["bwd_" + name] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
+            except Exception as exc:
+                row["bwd_" + name] = {"error": repr(exc)[:200]}
+        ops.set_attention_backend("cudnn")
         res.append(row)
         print(json.dumps(row), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)

@@ -600,9 +600,10 @@ class _FlashAttnQKV(torch.autograd.Function):
 
 
 class _TcgenAttnQKV(torch.autograd.Function):
-    """Forward on the hand-written tcgen05 flash-attention kernel (reads q/k/v straight out of the
-    fused qkv activation through TMA, emits O and log-sum-exp); backward through flash-attn 2's
-    kernel, which consumes exactly (q, k, v, O, lse, dO)."""
+    """Hand-written tcgen05 flash attention, forward AND backward (csrc/kernels/attention_tcgen05.cu,
+    attention_bwd_tcgen05.cu).  Reads q/k/v straight out of the fused qkv activation through TMA and
+    writes dq/dk/dv straight into the fused d(qkv) the qkv projection's backward consumes.
+    ``HYPHA_ATTN_BWD=flash2`` routes the backward through flash-attn 2 (library) for A/B runs."""
 
     @staticmethod
     def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim):
@@ -617,19 +618,35 @@ class _TcgenAttnQKV(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
-        from flash_attn.flash_attn_interface import _flash_attn_backward
-
         qkv, out, lse = ctx.saved_tensors
         batch, seq, n_heads, n_kv, head_dim, scale = ctx.dims
+        dqkv = torch.empty_like(qkv)
+        if os.environ.get("HYPHA_ATTN_BWD", "tcgen05") == "tcgen05":
+            dout = dout if dout.stride(-1) == 1 and dout.stride(0) % 8 == 0 else dout.contiguous()
+            return attention_bwd_tcgen05(qkv, out, dout, lse, batch, seq, n_heads, n_kv, head_dim, dqkv), \
+                None, None, None, None, None
+        from flash_attn.flash_attn_interface import _flash_attn_backward
+
         sl = lambda t, a, b, hh: t[:, a * head_dim: b * head_dim].view(batch, seq, hh, head_dim)
         q, k, v = sl(qkv, 0, n_heads, n_heads), sl(qkv, n_heads, n_heads + n_kv, n_kv), sl(qkv, n_heads + n_kv, n_heads + 2 * n_kv, n_kv)
-        dqkv = torch.empty_like(qkv)
         dq, dk, dv = sl(dqkv, 0, n_heads, n_heads), sl(dqkv, n_heads, n_heads + n_kv, n_kv), sl(dqkv, n_heads + n_kv, n_heads + 2 * n_kv, n_kv)
         do = dout.contiguous().view(batch, seq, n_heads, head_dim)
         rng = torch.zeros(2, dtype=torch.int64, device=qkv.device)
         _flash_attn_backward(do, q, k, v, out.view(batch, seq, n_heads, head_dim), lse, dq, dk, dv, 0.0, scale, True,
                              -1, -1, 0.0, None, False, rng)
         return dqkv, None, None, None, None, None
+
+
+def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int,
+                          dqkv: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw backward: returns ``dqkv [tokens, (Hq+2Hkv)*D]`` given the forward's (qkv, out, lse) and dout."""
+    if dqkv is None:
+        dqkv = torch.empty_like(qkv)
+    ws = torch.empty(2 * batch * n_heads * seq, dtype=torch.float32, device=qkv.device)
+    load_C().attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                           ws.data_ptr(), batch, seq, n_heads, n_kv, head_dim, qkv.stride(0), out.stride(0),
+                           dout.stride(0), dqkv.stride(0), 1.0 / math.sqrt(head_dim), cuda_stream())
+    return dqkv
 
 
 def attention_fwd_tcgen05(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int):

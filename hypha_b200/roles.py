@@ -57,13 +57,16 @@ class Node:
 async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, relay_server: bool = False,
                      dht_server: bool = False, need_bootstrap: bool = True) -> Node:
     tel = Telemetry.from_config(f"hypha-{role}", cfg)
-    C.load_tls(cfg)                         # accepted for parity; loopback links do not use mTLS
+    C.load_tls(cfg)                         # validates that the configured PEM files are readable
+    tls = {k: getattr(cfg, k, "") for k in ("cert_pem", "key_pem", "trust_pem", "crls_pem")}
     if peer_id is None and getattr(cfg, "key_pem", ""):
         from .transport.utils import peer_id_from_key_pem
 
         peer_id = peer_id_from_key_pem(cfg.key_pem)      # identity = public key, like the reference
     net = Network(peer_id or f"{role}-{M.new_id()[:8]}", agent=f"hypha-{role}", relay_server=relay_server,
-                  dht_server=dht_server)
+                  dht_server=dht_server, tls=tls)          # mTLS applies to tcp:// links only
+    if any(a.startswith("tcp://") for a in cfg.listen_addresses) and net.tls is None:
+        tel.logger.warning("tcp:// listener without cert_pem/key_pem/trust_pem: the link is NOT encrypted")
     tel.register_bandwidth(net.counters)
     node = Node(role, net, tel)
     net.enable_dht_handlers()
@@ -91,10 +94,10 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
     return node
 
 
-async def probe(addr: str, timeout: float = 5.0) -> bool:
+async def probe(addr: str, timeout: float = 5.0, tls: Optional[dict] = None) -> bool:
     """``probe <addr>``: dial, send ``health::Request``, true iff healthy
     (hypha-scheduler.rs:494-535)."""
-    net = Network(f"probe-{M.new_id()[:8]}")
+    net = Network(f"probe-{M.new_id()[:8]}", tls=tls)
     try:
         peer = await net.dial(addr, timeout=timeout)
         resp = await net.request(peer, M.HEALTH_PROTOCOL, M.HealthRequest(), timeout=timeout)

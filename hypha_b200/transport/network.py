@@ -195,8 +195,12 @@ class Network:
     """Per-role network handle (what the reference calls ``Network`` + ``NetworkDriver``)."""
 
     def __init__(self, peer_id: Optional[str] = None, *, agent: str = "hypha-b200",
-                 relay_server: bool = False, dht_server: bool = False):
+                 relay_server: bool = False, dht_server: bool = False, tls: Optional[Dict[str, str]] = None):
         self.peer_id = peer_id or new_peer_id()
+        # mutual TLS on tcp:// links (the reference's mTLS, crates/network/src/cert.rs:30-80,
+        # rfc/2025-05-30_mtls.md): {"cert_pem": chain file, "key_pem": key file, "trust_pem": CA file,
+        # "crls_pem": optional}.  memory:// and unix:// links rely on process / file-system isolation.
+        self.tls = tls if tls and tls.get("cert_pem") and tls.get("key_pem") and tls.get("trust_pem") else None
         self.agent = agent
         self.relay_server = relay_server
         self.dht_server = dht_server
@@ -228,6 +232,22 @@ class Network:
         t.add_done_callback(self._tasks.discard)
         return t
 
+    def _ssl_context(self, server: bool):
+        if self.tls is None:
+            return None
+        import ssl
+
+        ctx = ssl.SSLContext(ssl.PROTOCOL_TLS_SERVER if server else ssl.PROTOCOL_TLS_CLIENT)
+        ctx.minimum_version = ssl.TLSVersion.TLSv1_3
+        ctx.load_cert_chain(self.tls["cert_pem"], self.tls["key_pem"])
+        ctx.load_verify_locations(self.tls["trust_pem"])
+        if self.tls.get("crls_pem"):
+            ctx.load_verify_locations(self.tls["crls_pem"])
+            ctx.verify_flags |= ssl.VERIFY_CRL_CHECK_LEAF
+        ctx.check_hostname = False            # peers are identified by certificate, not by DNS name
+        ctx.verify_mode = ssl.CERT_REQUIRED   # both directions: the server demands a client certificate
+        return ctx
+
     async def _send(self, link: Link, frame: dict, protocol: str) -> None:
         n = await link.send(frame)
         self.counters.add(protocol, outbound=n)
@@ -251,7 +271,7 @@ class Network:
             self._servers.append(srv)
         elif addr.startswith("tcp://"):
             host, port = addr[len("tcp://"):].rsplit(":", 1)
-            srv = await asyncio.start_server(self._on_socket, host=host, port=int(port))
+            srv = await asyncio.start_server(self._on_socket, host=host, port=int(port), ssl=self._ssl_context(True))
             port = srv.sockets[0].getsockname()[1]
             addr = f"tcp://{host}:{port}"
             self._servers.append(srv)
@@ -308,12 +328,13 @@ class Network:
                 self._spawn(self._socket_loop(link))
             elif addr.startswith("tcp://"):
                 host, port = addr[len("tcp://"):].rsplit(":", 1)
-                r, w = await asyncio.wait_for(asyncio.open_connection(host, int(port)), timeout)
+                r, w = await asyncio.wait_for(asyncio.open_connection(host, int(port), ssl=self._ssl_context(False)),
+                                              timeout)
                 link = SocketLink(r, w)
                 self._spawn(self._socket_loop(link))
             else:
                 raise DialError(f"unsupported address {addr!r}")
-        except (OSError, asyncio.TimeoutError) as exc:
+        except (OSError, asyncio.TimeoutError) as exc:       # ssl.SSLError is an OSError
             raise DialError(f"dial {addr} failed: {exc}") from exc
         fut = asyncio.get_event_loop().create_future()
         link._hello_fut = fut  # type: ignore[attr-defined]

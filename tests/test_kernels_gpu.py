@@ -440,6 +440,27 @@ def test_attention_fwd_tcgen05(C, B, S, Hq, Hk):
     assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("B,S,Hq,Hk", [(1, 128, 2, 1), (2, 512, 8, 2), (1, 1024, 4, 4), (1, 384, 4, 1)])
+def test_attention_bwd_tcgen05(C, B, S, Hq, Hk):
+    """Hand-written tcgen05 flash-attention backward (dQ, dK, dV written into the fused d(qkv)) vs
+    autograd through the fp32 reference."""
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _attention_ref
+
+    torch.manual_seed(1)
+    D = 128
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16)
+    out, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
+    dout = torch.randn_like(out)
+    dqkv = ops.attention_bwd_tcgen05(qkv, out, dout, lse, B, S, Hq, Hk, D)
+    qf = qkv.float().requires_grad_(True)
+    _attention_ref(qf, B, S, Hq, Hk, D).backward(dout.float())
+    ref = qf.grad
+    parts = {"dq": slice(0, Hq * D), "dk": slice(Hq * D, (Hq + Hk) * D), "dv": slice((Hq + Hk) * D, (Hq + 2 * Hk) * D)}
+    errs = {k: _rel(dqkv[:, sl], ref[:, sl]) for k, sl in parts.items()}
+    assert all(e < 2e-2 for e in errs.values()), errs
+
+
 def test_attention_tcgen05_backend_grad(C):
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _attention_ref

@@ -326,3 +326,49 @@ def test_cidr_helpers_and_identity(tmp_path):
     cu.make_node(f"{d}/o-ca-cert.pem", f"{d}/o-ca-key.pem", "n1", out_dir=d)
     a, b = peer_id_from_key_pem(f"{d}/n1-key.pem"), peer_id_from_key_pem(f"{d}/n1-key.pem")
     assert a == b and a.startswith("12D3Koo") and a != peer_id_from_key_pem(f"{d}/o-ca-key.pem")
+
+
+def test_tcp_links_use_mutual_tls(tmp_path):
+    """tcp:// links run TLS 1.3 with client-certificate verification when the PKI files are
+    configured; a peer without a certificate from the trusted chain cannot connect."""
+    from hypha_b200 import certutil
+    from hypha_b200.transport.network import DialError, Network
+
+    d = str(tmp_path)
+    rc, rk = certutil.make_root("Acme", out_dir=d)
+    oc, ok = certutil.make_org(rc, rk, "Acme", name="acme-org", out_dir=d)
+    paths = {}
+    for n in ("alpha", "beta"):
+        c, k, t = certutil.make_node(oc, ok, n, sans=("127.0.0.1",), out_dir=d)
+        paths[n] = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+    # an unrelated PKI
+    d2 = str(tmp_path / "evil")
+    import os
+    os.makedirs(d2)
+    rc2, rk2 = certutil.make_root("Evil", out_dir=d2)
+    oc2, ok2 = certutil.make_org(rc2, rk2, "Evil", name="evil-org", out_dir=d2)
+    c, k, t = certutil.make_node(oc2, ok2, "mallory", out_dir=d2)
+    evil = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+
+    async def main():
+        a = Network("alpha", tls=paths["alpha"])
+        b = Network("beta", tls=paths["beta"])
+        m = Network("mallory", tls=evil)
+        plain = Network("plain")
+        addr = await a.listen("tcp://127.0.0.1:0")
+
+        async def echo(peer, msg):
+            return {"echo": msg, "from": peer}
+
+        a.on("/test/echo", None, echo)
+        peer = await b.dial(addr)
+        assert peer == "alpha"
+        resp = await b.request("alpha", "/test/echo", {"x": 1})
+        assert resp == {"echo": {"x": 1}, "from": "beta"}
+        for bad in (m, plain):
+            with pytest.raises(DialError):
+                await bad.dial(addr, timeout=2.0)
+        for n in (a, b, m, plain):
+            await n.close()
+
+    asyncio.run(main())
