@@ -88,6 +88,8 @@ def main():
         def variant(nvls, chunks, link_ctas=0):
             nonlocal st
             outer.use_nvls = nvls
+            if chunks == 0 and world <= 2:
+                chunks = max(1, min(16, (2 * n) // (128 << 20)))     # force the pipeline for the comparison
             os.environ["HYPHA_OUTER_CHUNKS"] = str(chunks)
             os.environ["HYPHA_OUTER_LINK_CTAS"] = str(link_ctas)
             ms = timed(outer.step, iters)

@@ -227,7 +227,9 @@ class DiLoCoOuter:
             self.segments = {self.rank: (self.shard_begin, self.shard_len, self.theta_outer, self.momentum)}
             self.layout = [shard_bounds(self.n, world, r) for r in range(world)]
             self.attempt = 0
-            self.use_nvls = True                    # used when the buffers carry a multicast address
+            # multimem path when the buffers carry a multicast address; measured slower than P2P at
+            # N=2 (nothing to save: one peer) and 12-19 % faster at N=8
+            self.use_nvls = world >= 4
             load_C().set_outer_timeout_ms(int(cfg.timeout_ms))
         elif backend == "nccl":
             # baseline: replicated outer state, stock collectives + unfused torch ops
@@ -361,19 +363,20 @@ class DiLoCoOuter:
         raise RuntimeError("outer step kept timing out")
 
     def _pipeline_shape(self) -> tuple:
-        """(num_chunks, link_ctas).  Pipelining pays once a chunk's HBM/NVLink time dwarfs the extra
-        cross-GPU barriers (~15 us each): one chunk per 128 MB of delta, at most 8."""
+        """(num_chunks, link_ctas), tuned on 8xB200 (profiles/outer_sweep_n8_v2.json).  Pipelining
+        pays once a chunk's HBM/NVLink time dwarfs the extra cross-GPU barriers (~15 us each): one
+        chunk per 128 MB of delta, at most 16.  At N=2 phase B is itself HBM-bound, so splitting the
+        SMs by role does not help and the plain A|B|C schedule is kept."""
         import os
 
         k = int(os.environ.get("HYPHA_OUTER_CHUNKS", self.cfg.pipeline_chunks))
         if k <= 0:
-            k = max(1, min(8, (2 * self.n) // (128 << 20)))
+            k = 1 if self.world <= 2 else max(1, min(16, (2 * self.n) // (128 << 20)))
         b = int(os.environ.get("HYPHA_OUTER_LINK_CTAS", self.cfg.link_ctas))
         if b <= 0:
-            # share of the SMs that phase B needs to keep up with phases A+C: at N=2 B is itself
-            # HBM-heavy (~45 % of the bytes); from N=4 on it is NVLink-latency-bound and 48 CTAs of
-            # 16-byte loads (2 x 8 in flight per thread) cover the bandwidth-delay product
-            b = 66 if self.world <= 2 else 48
+            # CTAs that keep NVLink busy while the rest stream HBM: the multimem path needs fewer
+            # requests in flight (one load returns the reduced value) than 8 P2P loads per vector
+            b = 66 if self.world <= 2 else (32 if self._multicast_ptrs()[0] else 48)
         return (k, b)
 
     def _multicast_ptrs(self) -> tuple:

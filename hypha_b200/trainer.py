@@ -67,7 +67,7 @@ class DiLoCoTrainer:
         want_fused = group is not None and group.world > 1 and diloco.backend in ("auto", "fused")
         if want_fused:
             holders = {}
-            use_nvls = os.environ.get("HYPHA_NVLS", "1") == "1"
+            use_nvls = os.environ.get("HYPHA_NVLS", "1") == "1" and group.world >= 4
 
             def sym_alloc(name, n, dt):
                 """NVLS (multicast-bound VMM) buffer when the fabric supports it, else CUDA-IPC.  All
