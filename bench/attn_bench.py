@@ -52,16 +52,24 @@ def main():
                 row["bwd_tcgen05"] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
             except Exception as exc:
                 row["bwd_tcgen05"] = {"error": repr(exc)[:200]}
-        for name in ("cudnn", "flash2"):
+        for name in ("cudnn", "flash2", "tcgen05"):
+            # library backward = (forward + backward through the autograd Function) - forward
             try:
                 ops.set_attention_backend(name)
                 q = qkv.clone().requires_grad_(True)
-                o = ops.attention_qkv(q, B, S, Hq, Hk, D)
-                g = torch.randn_like(o)
-                ms = timeit(lambda: torch.autograd.grad(o, q, g, retain_graph=True))
-                row["bwd_" + name] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
+                g = torch.randn(B * S, Hq * D, device="cuda", dtype=torch.bfloat16)
+
+                def fb():
+                    q.grad = None
+                    ops.attention_qkv(q, B, S, Hq, Hk, D).backward(g)
+
+                ms = timeit(fb)
+                row["fwd+bwd_" + name] = {"ms": ms, "tflops": 3.5 * flops / ms / 1e9}
+                if name != "tcgen05" and "ms" in row.get(name, {}):
+                    bms = ms - row[name]["ms"]
+                    row["bwd_" + name] = {"ms": bms, "tflops": 2.5 * flops / bms / 1e9}
             except Exception as exc:
-                row["bwd_" + name] = {"error": repr(exc)[:200]}
+                row["fwd+bwd_" + name] = {"error": repr(exc)[:200]}
         ops.set_attention_backend("cudnn")
         res.append(row)
         print(json.dumps(row), flush=True)

@@ -10,8 +10,9 @@
 //                                    MN-major B operand so no transpose is ever made
 //   warps 4-7   softmax warpgroup: thread t owns row t; tcgen05.ld S -> scale/mask/exp2 ->
 //               running (max, sum) -> P (bf16) into swizzled smem as the A operand of the PV
-//               MMA -> tcgen05.ld O_j and fold it into the fp32 register accumulator with the
-//               running rescale -> final normalise + store O and log-sum-exp
+//               MMA; O accumulates in TMEM across tiles and is rescaled in place (tcgen05.ld ->
+//               scale -> tcgen05.st) only when the row max grew by more than 2^8 (lazy rescale)
+//               -> final tcgen05.ld, normalise, store O and log-sum-exp
 // S_{j+1} is issued as soon as S_j has been read out of TMEM, so the QK^T of the next tile
 // overlaps the exponentials of the current one; two CTAs are co-resident per SM (96 KB smem,
 // 256 TMEM columns each) so one CTA's softmax hides under the other's MMAs.  `setmaxnreg`
@@ -167,16 +168,15 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) issue_s(j + 1);                        // overlaps softmax_j
         const int st = j & 1;
-        mbar_wait(p_full, (uint32_t)j & 1u);
+        mbar_wait(p_full, (uint32_t)j & 1u);          // also orders any rescale of O before this MMA
         mbar_wait(v_full(0), (uint32_t)j & 1u);
-        if (j > 0) mbar_wait(o_free, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
         const uint32_t vb = v_smem;
 #pragma unroll
         for (int kk = 0; kk < kBN / 16; ++kk) {
           const uint64_t ad = umma_smem_desc(p_smem + kk * 32, 16, 1024);                 // P: K-major, one atom
           const uint64_t bd = umma_smem_desc(vb + kk * (16 * 128), kBN * 128, 1024);     // V: MN-major, 2 chunks
-          umma_bf16_ss(tmem_o, ad, bd, idesc_o, kk != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_o, ad, bd, idesc_o, (j != 0 || kk != 0) ? 1u : 0u);          // O accumulates in TMEM
         }
         umma_commit(o_full);
         umma_commit(v_empty(0));
@@ -189,10 +189,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
     const int r_local = q4 * 32 + lane;                             // row inside the q tile
     const int q_pos = qt * kBM + r_local;                           // position in the sequence
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
-    float m_run = -INFINITY, l_run = 0.f;
-    float o[kD];
-#pragma unroll
-    for (int i = 0; i < kD; ++i) o[i] = 0.f;
+    // O stays in TMEM for the whole KV loop.  The running max used for the exponentials (m_used) is
+    // only advanced when the true max has grown by more than 2^8 since the last advance (lazy
+    // rescale): P <= 256 is harmless in bf16 / fp32 accumulation, and the TMEM read-modify-write of
+    // the 128-column O row then happens a handful of times per row instead of once per tile.
+    float m_used = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_tiles; ++j) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
@@ -214,21 +215,38 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
         x[c] = v;
         mx = fmaxf(mx, v);
       }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha = fast_exp2(m_run - m_use);
+      const bool need = mx > m_used + 8.f;                          // true on the first tile (m_used = -inf)
+      const float m_next = need ? mx : m_used;
+      const float alpha = need ? fast_exp2(m_used - m_next) : 1.f;  // 0 on the first tile
+      const float m_safe = (m_next == -INFINITY) ? 0.f : m_next;
       float sum = 0.f;
       uint32_t pk[32];
 #pragma unroll
       for (int c = 0; c < 64; c += 2) {
-        const float p0 = fast_exp2(x[c] - m_use), p1 = fast_exp2(x[c + 1] - m_use);
+        const float p0 = fast_exp2(x[c] - m_safe), p1 = fast_exp2(x[c + 1] - m_safe);
         sum += p0 + p1;
         __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
         pk[c >> 1] = *reinterpret_cast<uint32_t*>(&hh);
       }
       l_run = l_run * alpha + sum;
-      m_run = m_new;
-      // P_{j-1}'s MMA finished (we waited o_full last iteration) -> the P buffer is free
+      m_used = m_next;
+      // PV_{j-1} must have finished before P is overwritten or O is rescaled
+      if (j > 0) {
+        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+        if (__any_sync(0xffffffffu, need)) {
+#pragma unroll
+          for (int c = 0; c < kD / 32; ++c) {
+            uint32_t t[32];
+            tmem_ld_32x32(tmem_o + lane_addr + c * 32, t);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t[i] = __float_as_uint(__uint_as_float(t[i]) * alpha);
+            tmem_st_32x32(tmem_o + lane_addr + c * 32, t);
+          }
+          tmem_st_wait();
+        }
+      }
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch) {
         const uint32_t dst = p_smem + r_local * 128 + ((ch ^ (r_local & 7)) << 4);
@@ -236,30 +254,27 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
                      "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3]) : "memory");
       }
       fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      mbar_wait(o_full, (uint32_t)j & 1u);
-      tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kD / 32; ++c) {
-        uint32_t t[32];
-        tmem_ld_32x32(tmem_o + lane_addr + c * 32, t);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = fmaf(o[c * 32 + i], alpha, __uint_as_float(t[i]));
-      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
+      if (lane == 0) mbar_arrive(p_full);
     }
+    mbar_wait(o_full, (uint32_t)(n_tiles - 1) & 1u);
+    tc_fence_after();
     const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    const float m_run = m_used;
     bf16* orow = p.out + (size_t)(row0 + r_local) * p.out_stride + h * kD;
 #pragma unroll
-    for (int c = 0; c < kD; c += 8) {
-      float f[8];
+    for (int c = 0; c < kD / 32; ++c) {
+      uint32_t t[32];
+      tmem_ld_32x32(tmem_o + lane_addr + c * 32, t);
+      tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = o[c + e] * inv;
-      st_bf16x8(orow + c, pack8(f));
+      for (int e = 0; e < 32; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(t[e + i]) * inv;
+        st_bf16x8(orow + c * 32 + e, pack8(f));
+      }
     }
     p.lse[((size_t)b * p.n_heads + h) * p.seq + q_pos] =
         (l_run > 0.f) ? (m_run + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
