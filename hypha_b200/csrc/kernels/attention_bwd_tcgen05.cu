@@ -15,9 +15,13 @@
 //                            MN-major B operands, so no transposed copy of anything is ever made)
 //   attn_bwd_dq_kernel     one CTA = one 128-row Q tile of one (batch, head); streams 64-key K_j/V_j:
 //                            S = Q K_j^T, dP = dO V_j^T -> dS (thread = q row) -> dQ += dS K_j (TMEM)
-// Roles per CTA as in the forward kernel: warp 0 = TMA producer, warp 1 = MMA issuer, warps 4-7 =
-// softmax warpgroup (`setmaxnreg` moves registers to it).  The S/dP MMAs of tile i+1 are issued before
-// the dV/dK (dQ) MMAs of tile i, so the tensor pipe works under the exponentials.
+// Roles per CTA: warp 0 = TMA producer, warp 1 = MMA issuer, warps 4-19 = FOUR softmax warpgroups.
+// The backward needs no row reductions (LSE and D are inputs), so the 64 columns of every S/dP tile
+// are split 16 per warpgroup: all four read the same TMEM lanes (lane = warp%4 quarter) at different
+// column offsets, which cuts the exp/convert latency that sits between the two MMA groups of a tile
+// by 4x (ncu on the 1-warpgroup version: tensor pipe 25-30 %, issue slots 24 % busy -> latency-bound).
+// The S/dP MMAs of tile i+1 are issued before the dV/dK (dQ) MMAs of tile i, so the tensor pipe works
+// under the exponentials.
 // Results are written straight into the fused d(qkv) activation gradient that the qkv projection's
 // dgrad/wgrad GEMMs consume.
 //
@@ -35,7 +39,9 @@ namespace {
 using namespace sm100;
 
 constexpr int kD = 128;
-constexpr int kThreads = 256;
+constexpr int kWG = 4;                       // softmax warpgroups; each owns 64 / kWG columns of a tile
+constexpr int kColsPerWG = 64 / kWG;         // 16
+constexpr int kThreads = 128 + 128 * kWG;    // 640
 constexpr int kTmemCols = 512;
 
 __device__ __forceinline__ float ex2(float x) {
@@ -129,7 +135,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128,    // qkv, b
   const uint32_t k_smem = smem_base + DkvSmem::k_off, v_smem = smem_base + DkvSmem::v_off;
   const uint32_t q_smem = smem_base + DkvSmem::q_off, do_smem = smem_base + DkvSmem::do_off;
   const uint32_t pt_smem = smem_base + DkvSmem::pt_off, ds_smem = smem_base + DkvSmem::ds_off;
-  float* vec_gen = reinterpret_cast<float*>(smem_gen + DkvSmem::vec_off);
+  const float* vec_gen = reinterpret_cast<const float*>(smem_gen + DkvSmem::vec_off);
+  const uint32_t vec_smem = smem_base + DkvSmem::vec_off;
   const uint32_t bars = smem_base + DkvSmem::bar_off;
   const uint32_t kv_full = bars;
   auto qdo_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -161,9 +168,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128,    // qkv, b
     mbar_init(kv_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(qdo_full(s), 1); mbar_init(qdo_empty(s), 1);
-      mbar_init(sdp_full(s), 1); mbar_init(sdp_free(s), 4);
+      mbar_init(sdp_full(s), 1); mbar_init(sdp_free(s), 4 * kWG);
     }
-    mbar_init(pds_full, 4); mbar_init(pds_free, 1); mbar_init(acc_full, 1);
+    mbar_init(pds_full, 4 * kWG); mbar_init(pds_free, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
@@ -176,7 +183,6 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128,    // qkv, b
   const uint32_t tmem_dv = tmem_base + 256, tmem_dk = tmem_base + 384;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // ====================== TMA producer ======================
       mbar_arrive_expect_tx(kv_full, 2 * kKVTileBytes);
@@ -189,7 +195,12 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128,    // qkv, b
         const int h = hk * G + it / n_q, i = i0 + it % n_q;
         const int qrow = b * p.seq + i * kBQ;
         mbar_wait(qdo_empty(st), ((uint32_t)(it >> 1) & 1u) ^ 1u);
-        mbar_arrive_expect_tx(qdo_full(st), 2 * kQTileBytes);
+        mbar_arrive_expect_tx(qdo_full(st), 2 * kQTileBytes + 2 * kBQ * 4);
+        {  // lse2 and D of the 64 q rows ride on the same barrier
+          const size_t vbase = ((size_t)b * p.n_heads + h) * p.seq + (size_t)i * kBQ;
+          bulk_load_1d(vec_smem + st * 512, p.lse2 + vbase, kBQ * 4, qdo_full(st));
+          bulk_load_1d(vec_smem + st * 512 + 256, p.delta + vbase, kBQ * 4, qdo_full(st));
+        }
         tma_load_2d(q_smem + st * kQTileBytes, &tma_qkv64, qdo_full(st), h * kD, qrow);
         tma_load_2d(q_smem + st * kQTileBytes + kBQ * 128, &tma_qkv64, qdo_full(st), h * kD + 64, qrow);
         tma_load_2d(do_smem + st * kQTileBytes, &tma_do64, qdo_full(st), h * kD, qrow);
@@ -245,85 +256,73 @@ attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tma_qkv128,    // qkv, b
       }
     }
   } else {
-    // ====================== softmax warpgroup: thread = key row ======================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ====================== softmax warpgroups: thread = key row, 16 q columns each ==========
     const int q4 = warp & 3;
+    const int wg = (warp - 4) >> 2;
     const int r_local = q4 * 32 + lane;                             // key row inside the tile == TMEM lane
-    const int wg_tid = threadIdx.x - 128;
     const int k_pos = j * kKV + r_local;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int col0 = wg * kColsPerWG;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
-      const int h = hk * G + it / n_q, i = i0 + it % n_q;
-      {  // stage lse2 (threads 0..63) and D (threads 64..127) of the 64 q rows
-        const size_t base = ((size_t)b * p.n_heads + h) * p.seq + (size_t)i * kBQ;
-        const float v = wg_tid < 64 ? p.lse2[base + wg_tid] : p.delta[base + wg_tid - 64];
-        vec_gen[st * 128 + wg_tid] = v;
-      }
-      named_bar_sync(1, 128);
+      const int i = i0 + it % n_q;
       const float* lse_s = vec_gen + st * 128;
       const float* d_s = lse_s + 64;
+      mbar_wait(qdo_full(st), (uint32_t)(it >> 1) & 1u);            // lse2 / D staged by the producer
       mbar_wait(sdp_full(st), (uint32_t)(it >> 1) & 1u);
       tc_fence_after();
       const bool diag = i * kBQ < j * kKV + kKV;                    // some (key, q) pairs are masked
       const int q_pos0 = i * kBQ;
+      uint32_t sv[16], dp[16];
+      tmem_ld_32x16(tmem_s(st) + lane_addr + col0, sv);
+      tmem_ld_32x16(tmem_dp(st) + lane_addr + col0, dp);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free(st));
+      uint32_t pk[8], dk[8];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(tmem_s(st) + lane_addr + half * 32, s);
-        tmem_ld_32x32(tmem_dp(st) + lane_addr + half * 32, dp);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_free(st));
+      for (int c = 0; c < 16; c += 2) {
+        float pv[2], dsv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = col0 + c + e;
+          float pe = ex2(fmaf(__uint_as_float(sv[c + e]), p.scale_log2, -lse_s[col]));
+          if (diag && k_pos > q_pos0 + col) pe = 0.f;
+          pv[e] = pe;
+          dsv[e] = pe * (__uint_as_float(dp[c + e]) - d_s[col]) * p.scale;
         }
-        uint32_t pk[16], dk[16];
+        pk[c >> 1] = pack_bf16x2(pv[0], pv[1]);
+        dk[c >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+      }
+      if (it > 0) mbar_wait(pds_free, (uint32_t)(it - 1) & 1u);     // dV/dK MMAs of tile it-1 done
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pv[2], dsv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = half * 32 + c + e;
-            float pe = ex2(__uint_as_float(s[c + e]) * p.scale_log2 - lse_s[col]);
-            if (diag && k_pos > q_pos0 + col) pe = 0.f;
-            pv[e] = pe;
-            dsv[e] = pe * (__uint_as_float(dp[c + e]) - d_s[col]) * p.scale;
-          }
-          pk[c >> 1] = pack_bf16x2(pv[0], pv[1]);
-          dk[c >> 1] = pack_bf16x2(dsv[0], dsv[1]);
-        }
-        if (half == 0 && it > 0) mbar_wait(pds_free, (uint32_t)(it - 1) & 1u);   // dV/dK MMAs of tile it-1 done
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t sw = (uint32_t)(((half * 4 + ch) ^ (r_local & 7)) << 4);
-          st_shared_16(pt_smem + r_local * 128 + sw, pk + 4 * ch);
-          st_shared_16(ds_smem + r_local * 128 + sw, dk + 4 * ch);
-        }
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t sw = (uint32_t)(((wg * 2 + ch) ^ (r_local & 7)) << 4);
+        st_shared_16(pt_smem + r_local * 128 + sw, pk + 4 * ch);
+        st_shared_16(ds_smem + r_local * 128 + sw, dk + 4 * ch);
       }
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
     }
-    // ---- epilogue: dV, dK -> bf16 -> d(qkv) ----
+    // ---- epilogue: dV, dK -> bf16 -> d(qkv); warpgroup g owns columns [32g, 32g+32) of both ----
     mbar_wait(acc_full, 0);
     tc_fence_after();
     bf16* row = p.dqkv + (size_t)(krow0 + r_local) * p.dqkv_stride;
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
-      bf16* dst = row + (which == 0 ? v_col : k_col);
-      const uint32_t src = (which == 0 ? tmem_dv : tmem_dk) + lane_addr;
-#pragma unroll
-      for (int c = 0; c < kD / 32; ++c) {
+      for (int c = wg; c < kD / 32; c += kWG) {
+        bf16* dst = row + (which == 0 ? v_col : k_col) + c * 32;
         uint32_t t[32];
-        tmem_ld_32x32(src + c * 32, t);
+        tmem_ld_32x32((which == 0 ? tmem_dv : tmem_dk) + lane_addr + c * 32, t);
         tmem_ld_wait();
 #pragma unroll
         for (int e = 0; e < 32; e += 8) {
           float f[8];
 #pragma unroll
           for (int x = 0; x < 8; ++x) f[x] = __uint_as_float(t[e + x]);
-          st_bf16x8(dst + c * 32 + e, pack8(f));
+          st_bf16x8(dst + e, pack8(f));
         }
       }
     }
@@ -396,9 +395,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
     mbar_init(qdo_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1);
-      mbar_init(sdp_full(s), 1); mbar_init(sdp_free(s), 4);
+      mbar_init(sdp_full(s), 1); mbar_init(sdp_free(s), 4 * kWG);
     }
-    mbar_init(ds_full, 4); mbar_init(ds_free, 1); mbar_init(acc_full, 1);
+    mbar_init(ds_full, 4 * kWG); mbar_init(ds_free, 1); mbar_init(acc_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, kTmemCols);
@@ -411,7 +410,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
   const uint32_t tmem_dq = tmem_base + 256;
 
   if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
       // ====================== TMA producer ======================
       mbar_arrive_expect_tx(qdo_full, 2 * kQBytes);
@@ -473,12 +471,13 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
       }
     }
   } else {
-    // ====================== softmax warpgroup: thread = q row ======================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    // ====================== softmax warpgroups: thread = q row, 16 key columns each ==========
     const int q4 = warp & 3;
+    const int wg = (warp - 4) >> 2;
     const int r_local = q4 * 32 + lane;
     const int q_pos = qt * kBM + r_local;
     const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const int col0 = wg * kColsPerWG;
     const size_t vidx = ((size_t)b * p.n_heads + h) * p.seq + q_pos;
     const float lse_r = p.lse2[vidx], d_r = p.delta[vidx];
     for (int jj = 0; jj < n_tiles; ++jj) {
@@ -487,36 +486,31 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
       tc_fence_after();
       const int key0 = jj * kBN;
       const bool diag = key0 + kBN - 1 > qt * kBM;
+      uint32_t sv[16], dp[16];
+      tmem_ld_32x16(tmem_s(st) + lane_addr + col0, sv);
+      tmem_ld_32x16(tmem_dp(st) + lane_addr + col0, dp);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(sdp_free(st));
+      uint32_t dk[8];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t s[32], dp[32];
-        tmem_ld_32x32(tmem_s(st) + lane_addr + half * 32, s);
-        tmem_ld_32x32(tmem_dp(st) + lane_addr + half * 32, dp);
-        tmem_ld_wait();
-        if (half == 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_free(st));
+      for (int c = 0; c < 16; c += 2) {
+        float dsv[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int col = col0 + c + e;
+          float pe = ex2(fmaf(__uint_as_float(sv[c + e]), p.scale_log2, -lse_r));
+          if (diag && key0 + col > q_pos) pe = 0.f;
+          dsv[e] = pe * (__uint_as_float(dp[c + e]) - d_r) * p.scale;
         }
-        uint32_t dk[16];
+        dk[c >> 1] = pack_bf16x2(dsv[0], dsv[1]);
+      }
+      if (jj > 0) mbar_wait(ds_free, (uint32_t)(jj - 1) & 1u);
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float dsv[2];
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = half * 32 + c + e;
-            float pe = ex2(__uint_as_float(s[c + e]) * p.scale_log2 - lse_r);
-            if (diag && key0 + col > q_pos) pe = 0.f;
-            dsv[e] = pe * (__uint_as_float(dp[c + e]) - d_r) * p.scale;
-          }
-          dk[c >> 1] = pack_bf16x2(dsv[0], dsv[1]);
-        }
-        if (half == 0 && jj > 0) mbar_wait(ds_free, (uint32_t)(jj - 1) & 1u);
-#pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint32_t sw = (uint32_t)(((half * 4 + ch) ^ (r_local & 7)) << 4);
-          st_shared_16(ds_smem + r_local * 128 + sw, dk + 4 * ch);
-        }
+      for (int ch = 0; ch < 2; ++ch) {
+        const uint32_t sw = (uint32_t)(((wg * 2 + ch) ^ (r_local & 7)) << 4);
+        st_shared_16(ds_smem + r_local * 128 + sw, dk + 4 * ch);
       }
       fence_proxy_async_smem();
       __syncwarp();
@@ -525,8 +519,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
     mbar_wait(acc_full, 0);
     tc_fence_after();
     bf16* dst = p.dqkv + (size_t)(row0 + r_local) * p.dqkv_stride + q_col;
-#pragma unroll
-    for (int c = 0; c < kD / 32; ++c) {
+    for (int c = wg; c < kD / 32; c += kWG) {
       uint32_t t[32];
       tmem_ld_32x32(tmem_dq + lane_addr + c * 32, t);
       tmem_ld_wait();
