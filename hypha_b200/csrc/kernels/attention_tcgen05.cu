@@ -9,7 +9,7 @@
 //                                    O_j = P_j V_j (128x128x64, TMEM cols 64..191), V is the
 //                                    MN-major B operand so no transpose is ever made
 //   warps 4-7   softmax warpgroup: thread t owns row t; tcgen05.ld S -> scale/mask/exp2 ->
-//               running (max, sum) -> P (bf16) into swizzled smem as the A operand of the PV
+//               running (max, sum) -> P (bf16) into TMEM (cols 192..223) as the A operand of the PV
 //               MMA; O accumulates in TMEM across tiles and is rescaled in place (tcgen05.ld ->
 //               scale -> tcgen05.st) only when the row max grew by more than 2^8 (lazy rescale)
 //               -> final tcgen05.ld, normalise, store O and log-sum-exp
@@ -35,7 +35,7 @@ constexpr int kD = 128;          // head dim
 constexpr int kBM = 128;         // q rows per CTA
 constexpr int kBN = 64;          // keys per tile
 constexpr int kKVStages = 2;         // K ring depth
-constexpr int kVStages = 1;          // V is single-buffered: 2 CTAs/SM must fit in 227 KB of smem
+constexpr int kVStages = 2;          // P lives in TMEM, so its 16 KB of smem buy a second V stage
 constexpr int kQBytes = kBM * kD * 2;          // 32 KB (two 64-column swizzle atoms)
 constexpr int kKBytes = kBN * kD * 2;          // 16 KB
 constexpr int kVBytes = kBN * kD * 2;          // 16 KB
@@ -47,8 +47,7 @@ struct AttnSmem {
   static constexpr int q_off = 0;
   static constexpr int k_off = q_off + kQBytes;
   static constexpr int v_off = k_off + kKVStages * kKBytes;
-  static constexpr int p_off = v_off + kVStages * kVBytes;
-  static constexpr int bar_off = p_off + kPBytes;
+  static constexpr int bar_off = v_off + kVStages * kVBytes;
   // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full, o_full, o_free, tmem ptr
   static constexpr int total = bar_off + 16 * 8;
 };
@@ -78,7 +77,6 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
   const uint32_t q_smem = smem_base + AttnSmem::q_off;
   const uint32_t k_smem = smem_base + AttnSmem::k_off;
   const uint32_t v_smem = smem_base + AttnSmem::v_off;
-  const uint32_t p_smem = smem_base + AttnSmem::p_off;
   const uint32_t bars = smem_base + AttnSmem::bar_off;
   const uint32_t q_full = bars;
   auto k_full = [&](int s) { return bars + 8u * (1 + s); };
@@ -118,7 +116,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
-  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64;
+  const uint32_t tmem_s = tmem_base, tmem_o = tmem_base + 64, tmem_p = tmem_base + 192;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
@@ -139,10 +137,11 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
       for (int j = 0; j < n_tiles; ++j) {
         if (j + 1 < n_tiles) load_k(j + 1);                          // K runs one tile ahead of V
         const int krow = b * p.seq + j * kBN;
-        mbar_wait(v_empty(0), ((uint32_t)j & 1u) ^ 1u);               // PV_{j-1} has consumed V
-        mbar_arrive_expect_tx(v_full(0), kVBytes);
-        tma_load_2d(v_smem, &tma_kv, v_full(0), v_col, krow);
-        tma_load_2d(v_smem + kBN * 128, &tma_kv, v_full(0), v_col + 64, krow);
+        const int vs = j & 1;
+        mbar_wait(v_empty(vs), ((uint32_t)(j >> 1) & 1u) ^ 1u);       // PV_{j-2} has consumed this V stage
+        mbar_arrive_expect_tx(v_full(vs), kVBytes);
+        tma_load_2d(v_smem + vs * kVBytes, &tma_kv, v_full(vs), v_col, krow);
+        tma_load_2d(v_smem + vs * kVBytes + kBN * 128, &tma_kv, v_full(vs), v_col + 64, krow);
       }
     } else if (warp == 1 && lane == 0) {
       // ====================== MMA issuer ========================
@@ -169,17 +168,16 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
         if (j + 1 < n_tiles) issue_s(j + 1);                        // overlaps softmax_j
         const int st = j & 1;
         mbar_wait(p_full, (uint32_t)j & 1u);          // also orders any rescale of O before this MMA
-        mbar_wait(v_full(0), (uint32_t)j & 1u);
+        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
         tc_fence_after();
-        const uint32_t vb = v_smem;
+        const uint32_t vb = v_smem + st * kVBytes;
 #pragma unroll
         for (int kk = 0; kk < kBN / 16; ++kk) {
-          const uint64_t ad = umma_smem_desc(p_smem + kk * 32, 16, 1024);                 // P: K-major, one atom
           const uint64_t bd = umma_smem_desc(vb + kk * (16 * 128), kBN * 128, 1024);     // V: MN-major, 2 chunks
-          umma_bf16_ss(tmem_o, ad, bd, idesc_o, (j != 0 || kk != 0) ? 1u : 0u);          // O accumulates in TMEM
+          umma_bf16_ts(tmem_o, tmem_p + kk * 8, bd, idesc_o, (j != 0 || kk != 0) ? 1u : 0u);   // P from TMEM
         }
         umma_commit(o_full);
-        umma_commit(v_empty(0));
+        umma_commit(v_empty(st));
       }
     }
   } else {
@@ -247,13 +245,10 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
           tmem_st_wait();
         }
       }
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t dst = p_smem + r_local * 128 + ((ch ^ (r_local & 7)) << 4);
-        asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(pk[4 * ch]), "r"(pk[4 * ch + 1]),
-                     "r"(pk[4 * ch + 2]), "r"(pk[4 * ch + 3]) : "memory");
-      }
-      fence_proxy_async_smem();
+      // P (bf16 pairs) goes to TMEM columns 192..223 of this thread's lane: the PV MMA takes it as its
+      // A operand from tensor memory, so P costs neither an smem round trip nor MMA operand bandwidth
+      tmem_st_32x32(tmem_p + lane_addr, pk);
+      tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
