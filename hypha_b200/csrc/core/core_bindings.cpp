@@ -4,6 +4,7 @@
 #include <pybind11/stl.h>
 
 #include "core.hpp"
+#include "flag_barrier_model.hpp"
 
 namespace py = pybind11;
 using namespace hypha;
@@ -181,4 +182,21 @@ PYBIND11_MODULE(_core, m) {
       .def(py::init<size_t, double>(), py::arg("limit"), py::arg("window_s"))
       .def("push", &PyWindow::push).def("poll", &PyWindow::poll).def("flush", &PyWindow::flush)
       .def("next_deadline", &PyWindow::next_deadline).def("pending", &PyWindow::pending);
+
+  py::class_<FlagBarrierReport>(m, "FlagBarrierReport")
+      .def_readonly("ok", &FlagBarrierReport::ok)
+      .def_readonly("barriers_passed", &FlagBarrierReport::barriers_passed)
+      .def_readonly("violations", &FlagBarrierReport::violations)
+      .def_readonly("timeouts", &FlagBarrierReport::timeouts)
+      .def_readonly("missing_union", &FlagBarrierReport::missing_union);
+  m.def("flag_barrier_stress",
+        [](int world, uint32_t member_mask, int epochs, int stages, uint32_t seed, int dead_rank, int timeout_ms,
+           uint32_t first_epoch) {
+          py::gil_scoped_release nogil;
+          FlagBarrierModel model(world, member_mask);
+          return model.stress(epochs, stages, seed, dead_rank, timeout_ms, first_epoch);
+        },
+        py::arg("world"), py::arg("member_mask"), py::arg("epochs"), py::arg("stages"), py::arg("seed") = 1,
+        py::arg("dead_rank") = -1, py::arg("timeout_ms") = 2000, py::arg("first_epoch") = 1,
+        "Host stress test of the device flag-barrier protocol (outer_step.cu: cross_gpu_barrier).");
 }

@@ -264,3 +264,52 @@ def test_batch_window():
     assert w.push("b", 1.0) is None and w.push("c", 1.01) is None
     assert w.push("d", 1.02) == ["b", "c", "d"]
     assert w.pending() == 0 and w.flush() is None
+
+
+# ---------------------------------------------------------------------------------------------
+# host model of the device flag barrier (csrc/core/flag_barrier_model.hpp)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_flag_barrier_protocol_stress(world):
+    """Two slots + epoch-stamped tokens are enough for a K+2-stage pipeline: nobody leaves a barrier
+    before every member entered it, for any interleaving the scheduler produces."""
+    core = load_core()
+    rep = core.flag_barrier_stress(world, (1 << world) - 1, epochs=60, stages=10, seed=world)
+    assert rep.ok and rep.violations == 0 and rep.timeouts == 0
+    assert rep.barriers_passed == world * 60 * 10
+
+
+def test_flag_barrier_token_wraparound():
+    core = load_core()
+    rep = core.flag_barrier_stress(4, 0xF, epochs=64, stages=18, seed=5, first_epoch=(0xFFFFFFFF // 32) - 20)
+    assert rep.ok and rep.violations == 0
+
+
+def test_flag_barrier_reports_dead_rank():
+    """A member that never arrives costs a timeout and is named in the missing mask (the kernel then
+    returns status != 0 and the host shrinks the membership) instead of hanging the survivors."""
+    core = load_core()
+    rep = core.flag_barrier_stress(4, 0xF, epochs=3, stages=4, seed=9, dead_rank=2, timeout_ms=100)
+    assert rep.ok and rep.timeouts == 3 and rep.missing_union == 0b0100
+    # with the membership shrunk to the survivors the same ranks synchronise again
+    rep2 = core.flag_barrier_stress(4, 0b1011, epochs=20, stages=4, seed=9)
+    assert rep2.ok and rep2.barriers_passed == 3 * 20 * 4
+
+
+def test_flag_barrier_model_under_thread_sanitizer():
+    """`tools/sanitize.sh tsan`: the protocol model is data-race-free under ThreadSanitizer."""
+    import os
+    import shutil
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = os.environ.get("HYPHA_SANITIZE_CXX", "/usr/bin/g++")
+    if not os.path.exists(cxx) or shutil.which("sh") is None:
+        pytest.skip("no sanitizer-capable compiler")
+    probe = subprocess.run([cxx, "-print-file-name=libtsan.so"], capture_output=True, text=True)
+    if not os.path.isabs(probe.stdout.strip()):
+        pytest.skip("libtsan not installed")
+    r = subprocess.run(["sh", os.path.join(root, "tools", "sanitize.sh"), "tsan"], capture_output=True, text=True,
+                       timeout=300, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "FAIL" not in r.stdout and "ThreadSanitizer" not in r.stderr

@@ -2,6 +2,7 @@
 # Sanitizer / race-detection targets (the reference has none: SURVEY 5.2).
 #
 #   tools/sanitize.sh core      ASAN+UBSAN build of the C++ control-plane core, runs tests/test_core.py (CPU)
+#   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model (CPU)
 #   tools/sanitize.sh memcheck  compute-sanitizer --tool memcheck  over the kernel numerics tests (GPU box)
 #   tools/sanitize.sh racecheck compute-sanitizer --tool racecheck (shared-memory hazards; GPU box)
 #   tools/sanitize.sh synccheck compute-sanitizer --tool synccheck (barrier misuse; GPU box)
@@ -27,11 +28,20 @@ case "${1:-core}" in
     ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD="$LIBASAN $LIBCXX" HYPHA_CORE_OVERRIDE="$ROOT/$OUT" \
         $PY -m pytest tests/test_core.py -q -p no:cacheprovider
     ;;
+  tsan)
+    OUT=build/tsan
+    mkdir -p "$OUT"
+    SCXX=${HYPHA_SANITIZE_CXX:-/usr/bin/g++}
+    [ -x "$SCXX" ] || SCXX=${CXX:-g++}
+    $SCXX -O1 -g -std=c++17 -fsanitize=thread -fno-omit-frame-pointer -I hypha_b200/csrc \
+        tools/tsan_flag_barrier.cpp -o "$OUT/tsan_flag_barrier" -pthread
+    "$OUT/tsan_flag_barrier"
+    ;;
   memcheck|racecheck|synccheck)
     command -v compute-sanitizer >/dev/null 2>&1 || { echo "compute-sanitizer not found" >&2; exit 1; }
     HYPHA_NO_AUTOBUILD=1 compute-sanitizer --tool "$1" --error-exitcode 1 \
         $PY -m pytest tests/test_kernels_gpu.py -m gpu -q -x \
-        -k "rmsnorm or rope or swiglu or cross_entropy or embedding or adamw or outer_step_reference or gemm_accumulate or gemm_strided"
+        -k "rmsnorm or rope or swiglu or cross_entropy or embedding or adamw or outer_step_reference or gemm_accumulate or gemm_strided or attention_fwd_tcgen05 or attention_bwd_tcgen05"
     ;;
-  *) echo "usage: $0 {core|memcheck|racecheck|synccheck}" >&2; exit 2 ;;
+  *) echo "usage: $0 {core|tsan|memcheck|racecheck|synccheck}" >&2; exit 2 ;;
 esac
