@@ -500,4 +500,11 @@ def test_trainer_checkpoint_roundtrip(C, tmp_path):
     tr2.load_checkpoint(path)
     assert tr2.global_step == 4 and tr2.outer.round == 1
     got = tr2.step(ids).item()
-    assert got == want and torch.equal(tr2.model.flat.data, want_params)
+    # the loss is computed from the restored state: exact.  The parameters after the step go through the
+    # embedding backward's bf16 red.global atomics (duplicate token ids), whose summation order is not
+    # fixed -> compare within a couple of bf16 ulps instead of bit-for-bit.
+    assert got == want
+    a, b = tr2.model.flat.data.float(), want_params.float()
+    assert (a != b).float().mean().item() < 1e-2
+    assert torch.allclose(a, b, atol=1e-3, rtol=2e-2)
+    assert abs(tr2.step(ids).item() - tr.step(ids).item()) < 1e-2
