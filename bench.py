@@ -40,6 +40,9 @@ def parse_args():
     ap.add_argument("--state-dtype", default=os.environ.get("HYPHA_BENCH_STATE", "bf16"))
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fault-drill", action="store_true",
+                    help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
+                         "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
     ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2", "tcgen05"])
     return ap.parse_args()
@@ -275,6 +278,10 @@ def main():
         o1.record()
         barrier()
         outer_ms = max_over_ranks(o0.elapsed_time(o1)) / 2
+
+    drill = None
+    if args.fault_drill and world > 1 and trainer.outer.backend == "fused":
+        drill = fault_drill(trainer, dist, rank, world, dev_pool)
 
     if rank == 0:
         out = {
