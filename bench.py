@@ -110,6 +110,100 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+def fault_drill(trainer, dist, rank, world, batches, timeout_ms: int = 1500) -> dict:
+    """Kill/rejoin drill on the live trainer (BASELINE config 4; reference behaviour: the scheduler
+    exits on the first lease failure, SURVEY 5.3).  The last rank stops participating ("killed");
+    the survivors' fused outer step times out at its first barrier, names the missing rank, the
+    membership shrinks, the orphaned shard is adopted and the step is retried.  Training continues with
+    N-1 ranks; then the rank comes back, pulls the current weights from rank 0 over NVLink (the same
+    peer-memory path as the outer step), is re-admitted at a round boundary and the next outer step
+    runs with full membership again.  Control-plane coordination uses object all-gathers only."""
+    import torch
+
+    from hypha_b200.ops.native import load_C
+
+    outer, dead = trainer.outer, world - 1
+    load_C().set_outer_timeout_ms(timeout_ms)
+    flat = trainer.model.flat.data
+
+    def gather(obj):
+        out = [None] * world
+        dist.all_gather_object(out, obj)
+        return out
+
+    def fingerprint():
+        torch.cuda.synchronize()
+        v = flat[::4099].float()
+        return (float(v.sum().item()), float(v.abs().sum().item()))
+
+    def inner(k):
+        for i in range(k):
+            trainer.inner_step(*batches[i % len(batches)])
+
+    def timed_outer():
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        st = outer.step_resilient()
+        e1.record()
+        torch.cuda.synchronize()
+        return st, e0.elapsed_time(e1)
+
+    res = {"world": world, "killed_rank": dead, "barrier_timeout_ms": timeout_ms}
+    ok = True
+    # -- 1. the rank disappears; survivors detect, shrink, adopt, retry ------------------------------
+    detect_ms = None
+    if rank != dead:
+        inner(2)
+        t0 = time.perf_counter()
+        st, _ = timed_outer()
+        detect_ms = (time.perf_counter() - t0) * 1e3
+        ok &= st == (0, 0) and outer.members() == [r for r in range(world) if r != dead]
+    fps = gather(fingerprint() if rank != dead else None)
+    live = [f for f in fps if f is not None]
+    ok &= all(f == live[0] for f in live)
+    res["detect_and_recover_ms"] = max(x for x in gather(detect_ms) if x is not None)
+    # -- 2. training continues with N-1 ----------------------------------------------------------------
+    surv_ms = None
+    if rank != dead:
+        inner(2)
+        st, surv_ms = timed_outer()
+        ok &= st == (0, 0)
+    fps = gather(fingerprint() if rank != dead else None)
+    live = [f for f in fps if f is not None]
+    ok &= all(f == live[0] for f in live)
+    res["outer_step_ms_survivors"] = max(x for x in gather(surv_ms) if x is not None)
+    # -- 3. rejoin: parameter broadcast over peer memory -------------------------------------------------
+    dist.barrier()
+    pull_ms = None
+    if rank == dead:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        outer.reseed_from(0)
+        e1.record()
+        torch.cuda.synchronize()
+        pull_ms = e0.elapsed_time(e1)
+    dist.barrier()
+    outer.readmit(dead)
+    outer.sync_epoch()
+    fps = gather(fingerprint())
+    ok &= all(f == fps[0] for f in fps) and outer.members() == list(range(world))
+    pm = [x for x in gather(pull_ms) if x is not None][0]
+    res["rejoin_reseed_ms"] = pm                      # 16 GB pull + master/anchor/shard rebuild
+    res["rejoin_param_bytes"] = int(flat.numel() * 2)
+    res["rejoin_effective_gbs"] = flat.numel() * 2 / pm / 1e6
+    # -- 4. full membership again ----------------------------------------------------------------------------
+    inner(2)
+    st, full_ms = timed_outer()
+    ok &= st == (0, 0)
+    fps = gather(fingerprint())
+    ok &= all(f == fps[0] for f in fps)
+    res["outer_step_ms_after_rejoin"] = max(gather(full_ms))
+    res["nvls_after_rejoin"] = bool(outer._multicast_ptrs()[0])
+    res["ok"] = bool(all(gather(bool(ok))))
+    load_C().set_outer_timeout_ms(int(outer.cfg.timeout_ms))
+    return res
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
