@@ -40,6 +40,8 @@ def parse_args():
     ap.add_argument("--state-dtype", default=os.environ.get("HYPHA_BENCH_STATE", "bf16"))
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--min-free-gb", type=float, default=4.0,
+                    help="memory head-room a recompute plan must leave after two trial steps")
     ap.add_argument("--fault-drill", action="store_true",
                     help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
                          "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
@@ -269,10 +271,19 @@ def main():
     for recompute in candidates:
         ok = 1
         try:
+            torch.cuda.reset_peak_memory_stats(dev)
             cfg, trainer = make_trainer(recompute)
             for i in range(2):
                 trainer.step(pool[i % 4], lab_pool[i % 4])
             trainer.read_loss()
+            # keep head-room for what is allocated later outside the caching allocator (NCCL channels,
+            # cuDNN workspaces): a plan that only just fits is rejected like an OOM
+            free, _ = torch.cuda.mem_get_info(dev)
+            slack = free + torch.cuda.memory_reserved(dev) - torch.cuda.max_memory_allocated(dev)   # at the step's peak
+            if slack < args.min_free_gb * 2 ** 30 and recompute != candidates[-1]:
+                ok = 0
+                del trainer
+                trainer = None
         except torch.OutOfMemoryError:
             ok = 0
         if world > 1:
