@@ -305,6 +305,14 @@ def main():
     if trainer is None:
         raise SystemExit("no memory configuration fits")
 
+    def memdbg(tag):
+        if os.environ.get("HYPHA_BENCH_MEMDEBUG") == "1":
+            free, total = torch.cuda.mem_get_info(dev)
+            print(f"[mem r{rank}] {tag}: allocated {torch.cuda.memory_allocated(dev) / 2**30:.2f} GiB, peak "
+                  f"{torch.cuda.max_memory_allocated(dev) / 2**30:.2f}, reserved {torch.cuda.memory_reserved(dev) / 2**30:.2f}, "
+                  f"free {free / 2**30:.2f} of {total / 2**30:.2f}", file=sys.stderr, flush=True)
+
+    memdbg("after plan")
     tokens_per_step = B * S * world
     dev_pool = [(a.to(dev), b.to(dev)) for a, b in zip(pool, lab_pool)]
 
@@ -340,6 +348,7 @@ def main():
         trainer.step(pool[i % 4], lab_pool[i % 4])
     trainer.read_loss()
     barrier()
+    memdbg("after warm-up")
 
     # ---- device-timed region ----------------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -384,6 +393,7 @@ def main():
         barrier()
         outer_ms = max_over_ranks(o0.elapsed_time(o1)) / 2
 
+    memdbg("before drill")
     drill = None
     if args.fault_drill and world > 1 and trainer.outer.backend == "fused":
         drill = fault_drill(trainer, dist, rank, world, dev_pool)
@@ -412,6 +422,8 @@ def main():
             "model_tflops_per_gpu": value / world * cfg.flops_per_token(S) / 1e12,
             "outer_step_ms": outer_ms, "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
         }
+        if drill is not None:
+            out["fault_drill"] = drill
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
