@@ -216,6 +216,15 @@ class JobResources:
 
 
 @dataclass
+class AggregationSection:
+    mode: str = doc("`parameter-server` (reference behaviour: pseudo-gradient files through an aggregate worker) "
+                    "or `collective` (the train workers synchronise among themselves: fused NVLink outer step on "
+                    "GPUs, gloo all-reduce on CPU; no aggregate worker is allocated)", "parameter-server")
+    rendezvous: Optional[str] = doc("`tcp://host:port` the ranks of a collective job meet on "
+                                    "(default: a free port on 127.0.0.1)", None)
+
+
+@dataclass
 class DiLoCoJob:
     type: str = doc("job type (only `diloco`)", "diloco")
     model: ModelSource = doc("model source", factory=ModelSource)
@@ -225,6 +234,7 @@ class DiLoCoJob:
     inner_optimizer: AdamSection = doc("inner optimizer", factory=AdamSection)
     outer_optimizer: NesterovSection = doc("outer optimizer", factory=NesterovSection)
     resources: JobResources = doc("allocation request", factory=JobResources)
+    aggregation: AggregationSection = doc("how the outer step is carried out", factory=AggregationSection)
 
 
 @dataclass
@@ -506,6 +516,11 @@ def validate(cfg: Any) -> Any:
             raise _err(meta, "scheduler.job.preprocessor.type", f"unknown preprocessor type `{job.preprocessor.type}`")
         if job.resources.num_workers < 1:
             raise _err(meta, "scheduler.job.resources.num_workers", "need at least one worker")
+        if job.aggregation.mode not in ("parameter-server", "collective"):
+            raise _err(meta, "scheduler.job.aggregation.mode",
+                       f"unknown aggregation mode `{job.aggregation.mode}` (parameter-server | collective)")
+        if job.aggregation.rendezvous and not job.aggregation.rendezvous.startswith("tcp://"):
+            raise _err(meta, "scheduler.job.aggregation.rendezvous", "rendezvous must be a tcp://host:port address")
     if isinstance(cfg, DataConfig) and cfg.dataset_path and not os.path.isdir(cfg.dataset_path):
         raise _err(meta, "dataset_path", f"dataset_path `{cfg.dataset_path}` is not a directory")
     return cfg

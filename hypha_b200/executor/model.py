@@ -57,6 +57,18 @@ def get_model(model_path: str, model_type: str, device: str = "cpu") -> torch.nn
     meta = json.load(open(cfg_path))
     family = meta.get("model_type", "")
     weights = os.path.join(model_path, "model.safetensors")
+    # without a checkpoint every worker must still start from the SAME weights (the reference gets this
+    # from the shared HF download): random init is seeded from the config, not from the process
+    rng_state = torch.random.get_rng_state()
+    torch.manual_seed(int(meta.get("seed", 0)))
+    try:
+        return _build_model(model_path, model_type, device, meta, family, weights, cfg_path)
+    finally:
+        torch.random.set_rng_state(rng_state)
+
+
+def _build_model(model_path: str, model_type: str, device: str, meta: dict, family: str, weights: str,
+                 cfg_path: str) -> torch.nn.Module:
     if family == "gpt2":
         from ..models.gpt2 import GPT2Config, GPT2LMHeadModel
 

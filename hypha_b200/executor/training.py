@@ -105,6 +105,171 @@ class InnerLoop:
                     self.prev[k] = v.detach().clone()
 
 
+# ---------------------------------------------------------------------------------------------
+# collective mode: the train workers are the ranks of one process group and run the outer step
+# among themselves -- no aggregate worker, no files (TrainExecutorConfig.collective)
+# ---------------------------------------------------------------------------------------------
+class ReplicatedNesterov:
+    """Outer step for the CPU / generic-model plumbing path: all-reduce the pseudo-gradient over the
+    job's process group (gloo on CPU), true 1/N mean, Nesterov with the reference's numerics
+    (parameter_server.rs:386-446); every rank keeps the full outer state."""
+
+    def __init__(self, lr: float, mu: float):
+        self.lr, self.mu = lr, mu
+        self.m: Optional[Dict[str, torch.Tensor]] = None
+
+    @torch.no_grad()
+    def step(self, loop: "InnerLoop", world: int) -> None:
+        import torch.distributed as dist
+
+        first = self.m is None
+        if first:
+            self.m = {}
+        if loop.flat:
+            net = loop.model.net
+            g = loop.opt.master - loop.prev
+            dist.all_reduce(g)
+            g.div_(world)
+            m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
+            self.m["flat"] = m
+            loop.prev.add_(self.lr * (self.mu * m + g))
+            loop.opt.master.copy_(loop.prev)
+            net.flat.data.copy_(loop.prev)
+            return
+        for k, v in loop.model.state_dict().items():
+            if not v.dtype.is_floating_point:
+                continue
+            g = v.detach().float() - loop.prev[k].float()
+            dist.all_reduce(g)
+            g.div_(world)
+            m = g.clone() if first else self.m[k].mul_(self.mu).add_(g)
+            self.m[k] = m
+            v.copy_((loop.prev[k].float() + self.lr * (self.mu * m + g)).to(v.dtype))
+            loop.prev[k] = v.detach().clone()
+
+
+class _TrainerEngine:
+    """Llama on a B200: the public DiLoCoTrainer (flat buffers in peer memory, fused AdamW, fused
+    NVLink outer step)."""
+
+    def __init__(self, local: str, config: dict, coll: dict, dev_index: int):
+        from ..models.llama import LlamaConfig
+        from ..parallel.diloco import AdamWConfig, DiLoCoConfig
+        from ..parallel.peer_memory import PeerGroup
+        from ..trainer import DiLoCoTrainer
+
+        meta = json.load(open(os.path.join(local, "config.json")))
+        cfg = LlamaConfig(vocab_size=meta["vocab_size"], hidden_size=meta["hidden_size"],
+                          intermediate_size=meta["intermediate_size"], num_layers=meta["num_hidden_layers"],
+                          num_heads=meta["num_attention_heads"],
+                          num_kv_heads=meta.get("num_key_value_heads", meta["num_attention_heads"]),
+                          head_dim=meta.get("head_dim", meta["hidden_size"] // meta["num_attention_heads"]),
+                          rope_theta=float(meta.get("rope_theta", 500000.0)), rms_eps=float(meta.get("rms_norm_eps", 1e-5)),
+                          max_seq_len=int(meta.get("max_position_embeddings", 8192)), name=meta.get("name", "llama"))
+        o = config["optimizer"]
+        adamw = AdamWConfig(lr=float(o["learning-rate"]), betas=tuple(o["betas"]) if o.get("betas") else (0.9, 0.999),
+                            eps=float(o["epsilon"]) if o.get("epsilon") else 1e-8)
+        outer = coll.get("outer") or {}
+        diloco = DiLoCoConfig(inner_steps=1 << 62, outer_lr=float(outer.get("learning-rate", 0.7)),
+                              outer_momentum=float(outer.get("momentum", 0.9)))
+        group = PeerGroup.from_torch_distributed(dev_index) if coll["world"] > 1 else None
+        self.trainer = DiLoCoTrainer.create(cfg, adamw=adamw, diloco=diloco, group=group, device=dev_index,
+                                            seed=int(meta.get("seed", 0)), scheduler=config.get("scheduler"))
+        weights = os.path.join(local, "model.safetensors")
+        if os.path.exists(weights):
+            from safetensors.torch import load_file
+
+            self.trainer.model.load_hf_state_dict(load_file(weights))
+            self.trainer.opt.master.copy_(self.trainer.model.flat.data)
+        self.backend = self.trainer.outer.backend
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        ids = batch["input_ids"]
+        return self.trainer.inner_step(ids, batch.get("labels", torch.roll(ids, -1, dims=-1)))
+
+    def outer_step(self) -> None:
+        self.trainer.outer_step()
+        st = self.trainer.outer.check()
+        if st != (0, 0):
+            raise RuntimeError(f"fused outer step failed: status {st}")
+
+
+class _GenericEngine:
+    def __init__(self, local: str, config: dict, coll: dict, device: str):
+        model = get_model(local, config["model"]["task"], device)
+        self.loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device)
+        outer = coll.get("outer") or {}
+        self.outer = ReplicatedNesterov(float(outer.get("learning-rate", 0.7)), float(outer.get("momentum", 0.9)))
+        self.world = int(coll["world"])
+        self.backend = "all-reduce"
+
+    def step(self, batch):
+        return self.loop.step(batch)
+
+    def outer_step(self) -> None:
+        self.outer.step(self.loop, self.world)
+
+
+def main_collective(session: Session, config: dict, work_dir: str) -> None:
+    import torch.distributed as dist
+
+    coll = config["collective"]
+    rank, world = int(coll["rank"]), int(coll["world"])
+    use_cuda = torch.cuda.is_available() and os.environ.get("HYPHA_EXECUTOR_DEVICE", "cuda") != "cpu"
+    dev_index = int(os.environ.get("HYPHA_DEVICE", rank % max(1, torch.cuda.device_count()))) if use_cuda else -1
+    if use_cuda:
+        torch.cuda.set_device(dev_index)
+    device = f"cuda:{dev_index}" if use_cuda else "cpu"
+    if world > 1:
+        kw = {"device_id": torch.device(device)} if use_cuda else {}
+        dist.init_process_group("nccl" if use_cuda else "gloo", init_method=coll["rendezvous"], rank=rank,
+                                world_size=world, **kw)
+    prepare_files(config, session)
+    local = os.path.join(work_dir, FETCH_PATH)
+    family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
+    engine = (_TrainerEngine(local, config, coll, dev_index) if use_cuda and family == "llama"
+              else _GenericEngine(local, config, coll, device))
+    print(f"collective rank {rank}/{world} on {device}: outer step via {engine.backend}", flush=True)
+    pre_cfg = config.get("preprocessor")
+    loader = torch.utils.data.DataLoader(
+        IterableStreamDataSet(fetch_data(session, config["data"], work_dir), config["model"]["input-names"],
+                              pre_cfg["input-names"] if pre_cfg else [], get_preprocessor(pre_cfg, local)),
+        batch_size=config["batch_size"])
+    batches = forever(loader)
+    round_no = 1
+    while True:
+        loss_sum = torch.zeros((), device=device)
+        steps, counter = 0, -1
+        while counter != 0:
+            batch = next(batches)
+            loss_sum += engine.step(batch)
+            steps += 1
+            bs = int(next(iter(batch.values())).shape[0])
+            resp = session.send_status({"status": {"batch_size": bs}})
+            if resp["type"] == "ScheduleUpdate":
+                counter = resp["counter"]
+            elif resp["type"] == "Error":
+                raise RuntimeError("scheduler rejected status")
+            else:
+                counter -= 1
+        session.send_status("update")
+        engine.outer_step()                        # every rank enters: the kernel / all-reduce is the barrier
+        mean_loss = float(loss_sum.item() / max(1, steps))
+        session.send_status({"metrics": {"round": round_no, "metrics": {"loss": mean_loss}}})
+        print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}; outer step done", flush=True)
+        if rank == 0:
+            session.send_status("updated")         # what the aggregate worker reports in parameter-server mode
+        if world > 1:
+            dist.barrier()                         # nobody acknowledges before the round counter advanced
+        round_no += 1
+        if session.send_status("update-received")["type"] == "Done":
+            break
+    print(f"Finished training of {round_no - 1} DiLoCo update rounds", flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main(socket_path: str, work_dir: str, job_json: str) -> None:
     from safetensors.torch import load_file, save_file
 
@@ -114,6 +279,8 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
         executor = job["executor"]
         assert executor["class"] == "train"
         config = executor["config"]
+        if config.get("collective"):
+            return main_collective(session, config, work_dir)
         prepare_files(config, session)
         local = os.path.join(work_dir, FETCH_PATH)
         model = get_model(local, config["model"]["task"], device)

@@ -48,7 +48,8 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
         if log is not None:
             log(m)
 
-    names = [f"worker-{chr(ord('a') + i)}" for i in range(num_workers)] + ["worker-ps"]
+    collective = (job.get("aggregation") or {}).get("mode") == "collective"
+    names = [f"worker-{chr(ord('a') + i)}" for i in range(num_workers)] + ([] if collective else ["worker-ps"])
     started = [loop.create_future() for _ in range(2 + len(names))]
     gw_cfg = C.builder(C.GatewayConfig).with_overrides({"listen_addresses": [gw_addr]}).build()
     bg = [asyncio.ensure_future(roles.run_gateway(gw_cfg, peer_id="gateway", started=started[0]))]

@@ -354,6 +354,10 @@ class TrainExecutorConfig:
     batch_size: int
     preprocessor: Optional[Preprocessor] = None
     scheduler: Optional[LRScheduler] = None
+    # B200 extension (absent in the reference): when set, the train workers of the job synchronise
+    # among themselves -- fused peer-memory outer step on GPUs, gloo all-reduce on CPU -- instead of
+    # shipping files to a parameter server.  {"rank", "world", "rendezvous", "outer": Nesterov wire}
+    collective: Optional[dict] = None
 
     def to_wire(self) -> dict:
         d = {"model": self.model.to_wire(), "data": self.data.to_wire(), "updates": self.updates.to_wire(),
@@ -363,6 +367,8 @@ class TrainExecutorConfig:
             d["preprocessor"] = self.preprocessor.to_wire()
         if self.scheduler is not None:
             d["scheduler"] = self.scheduler.to_wire()
+        if self.collective is not None:
+            d["collective"] = dict(self.collective)
         return d
 
     @classmethod
@@ -370,7 +376,8 @@ class TrainExecutorConfig:
         return cls(Model.from_wire(d["model"]), Fetch.from_wire(d["data"]), Send.from_wire(d["updates"]),
                    Receive.from_wire(d["results"]), Adam.from_wire(d["optimizer"]), int(d["batch_size"]),
                    Preprocessor.from_wire(d["preprocessor"]) if d.get("preprocessor") else None,
-                   LRScheduler.from_wire(d["scheduler"]) if d.get("scheduler") else None)
+                   LRScheduler.from_wire(d["scheduler"]) if d.get("scheduler") else None,
+                   dict(d["collective"]) if d.get("collective") else None)
 
 
 @dataclass

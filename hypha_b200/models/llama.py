@@ -65,6 +65,18 @@ class LlamaConfig:
     def to_dict(self) -> dict:
         return asdict(self)
 
+    def to_hf_json(self, path: str, seed: int = 0) -> None:
+        """Write a Hugging-Face style ``config.json`` (what ``executor/model.py`` and the collective
+        executor read back); ``seed`` fixes the random init every worker of a job starts from."""
+        import json
+
+        json.dump({"model_type": "llama", "architectures": ["LlamaForCausalLM"], "name": self.name,
+                   "vocab_size": self.vocab_size, "hidden_size": self.hidden_size,
+                   "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_layers,
+                   "num_attention_heads": self.num_heads, "num_key_value_heads": self.num_kv_heads,
+                   "head_dim": self.head_dim, "rope_theta": self.rope_theta, "rms_norm_eps": self.rms_eps,
+                   "max_position_embeddings": self.max_seq_len, "seed": seed}, open(path, "w"))
+
 
 PRESETS: Dict[str, LlamaConfig] = {
     "llama3-8b": LlamaConfig(name="llama3-8b"),

@@ -203,6 +203,14 @@ class JobOutcome:
     finished: bool
 
 
+def _free_tcp_port() -> int:
+    import socket
+
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return int(sk.getsockname()[1])
+
+
 def worker_batch_size(offered_gpu: float, required_gpu: float, max_batch: Optional[int]) -> int:
     """``floor(offered.gpu / required.gpu).min(max_batch_size)`` (hypha-scheduler.rs:320-322)."""
     bs = int(math.floor(offered_gpu / required_gpu)) if required_gpu > 0 else 1
@@ -242,14 +250,22 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
         with node.telemetry.span("allocate.workers", num=res.num_workers):
             workers = await allocator.request(wspec, res.worker_price.bid, res.worker_price.max, res.num_workers)
         handles += workers
-        await asyncio.sleep(allocation_pause_s)
-        pspec = M.WorkerSpec(to_res(res.parameter_server), [M.ExecutorDescriptor("aggregate", M.AGGREGATE_EXECUTOR_NAME)])
-        with node.telemetry.span("allocate.parameter_server"):
-            ps_list = await allocator.request(pspec, res.parameter_server_price.bid, res.parameter_server_price.max, 1)
-        handles += ps_list
-        if len(workers) < res.num_workers or not ps_list:
-            raise RoleError(f"allocation incomplete: {len(workers)}/{res.num_workers} workers, {len(ps_list)} PS")
-        ps = ps_list[0]
+        collective = job.aggregation.mode == "collective"
+        if collective:
+            # B200 path: no aggregate worker.  The train workers run the outer step among themselves
+            # (fused peer-memory kernel on GPUs / gloo on CPU); rank 0 reports `updated` for the group.
+            if len(workers) < res.num_workers:
+                raise RoleError(f"allocation incomplete: {len(workers)}/{res.num_workers} workers")
+            ps = workers[0]
+        else:
+            await asyncio.sleep(allocation_pause_s)
+            pspec = M.WorkerSpec(to_res(res.parameter_server), [M.ExecutorDescriptor("aggregate", M.AGGREGATE_EXECUTOR_NAME)])
+            with node.telemetry.span("allocate.parameter_server"):
+                ps_list = await allocator.request(pspec, res.parameter_server_price.bid, res.parameter_server_price.max, 1)
+            handles += ps_list
+            if len(workers) < res.num_workers or not ps_list:
+                raise RoleError(f"allocation incomplete: {len(workers)}/{res.num_workers} workers, {len(ps_list)} PS")
+            ps = ps_list[0]
         provider, record = await get_data_provider(net, job.dataset.dataset)
         data_svc = DataSchedulerService(net, job.dataset.dataset, provider, record.num_slices)
         data_svc.start()
@@ -272,18 +288,23 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
         adam = M.Adam(job.inner_optimizer.learning_rate,
                       tuple(job.inner_optimizer.betas) if job.inner_optimizer.betas else None,
                       job.inner_optimizer.epsilon)
-        for w in workers:
+        nesterov = M.Nesterov(job.outer_optimizer.learning_rate, job.outer_optimizer.momentum)
+        rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{_free_tcp_port()}"
+        for i, w in enumerate(workers):
             bs = worker_batch_size(w.resources.gpu, res.worker.gpu, job.rounds.max_batch_size)
             batch.add_worker(w.peer_id, bs)
             tcfg = M.TrainExecutorConfig(model=model, data=M.Fetch.scheduler(net.peer_id, job.dataset.dataset),
                                          updates=M.Send.to_peers([ps.peer_id]), results=M.Receive.from_peers([ps.peer_id]),
                                          optimizer=adam, batch_size=bs, preprocessor=pre)
+            if collective:
+                tcfg.collective = {"rank": i, "world": len(workers), "rendezvous": rendezvous,
+                                   "outer": nesterov.to_wire()}
             spec = M.JobSpec(job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))
             tasks.append(await Task.try_new(net, spec, [w]))
-        acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(worker_ids), results=M.Send.to_peers(worker_ids),
-                                         optimizer=M.Nesterov(job.outer_optimizer.learning_rate,
-                                                              job.outer_optimizer.momentum))
-        tasks.append(await Task.try_new(net, M.JobSpec(job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg)), [ps]))
+        if not collective:
+            acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(worker_ids), results=M.Send.to_peers(worker_ids),
+                                             optimizer=nesterov)
+            tasks.append(await Task.try_new(net, M.JobSpec(job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg)), [ps]))
 
         collected: List[Dict[str, Any]] = []
 
@@ -312,7 +333,8 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
             log.warning("scheduler stopping before completion: %s", reason)
         await asyncio.sleep(0.05)              # let the last metrics drain
         bridge_task.cancel()
-        return JobOutcome(job_id, batch.round, worker_ids, ps.peer_id, collected, finished)
+        return JobOutcome(job_id, batch.round, worker_ids, "collective" if collective else ps.peer_id, collected,
+                          finished)
     finally:
         for t in tasks:
             t.close()

@@ -52,3 +52,41 @@ def test_gpt2_diloco_two_workers_loopback(tmp_path):
     # job work dirs are cleaned up
     for w in ("worker-a", "worker-b", "worker-ps"):
         assert [d for d in os.listdir(os.path.join(tmp, w)) if d.startswith("hypha-")] == []
+
+
+def test_gpt2_diloco_collective_mode_loopback(tmp_path):
+    """`aggregation.mode = "collective"`: no aggregate worker is allocated; the two train executors
+    form a gloo process group over the rendezvous the scheduler hands out, all-reduce the
+    pseudo-gradient, apply Nesterov locally and rank 0 reports `updated`.  On a GPU box the same job
+    runs the fused peer-memory outer step (tests/test_multigpu.py)."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 40, "update_rounds": 2, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"mode": "collective"},
+        "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cpu"
+    try:
+        outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+            tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job,
+            write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=6, samples_per_slice=16, seq_len=32,
+                                                                 vocab_size=512), timeout_s=240))
+    finally:
+        os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
+    assert outcome.finished, logs[-20:]
+    assert outcome.rounds == 2 and sorted(outcome.workers) == ["worker-a", "worker-b"]
+    assert outcome.parameter_server == "collective"
+    assert sum("outer step via all-reduce" in l for l in logs) == 2
+    losses = {}
+    for r in sink.records:
+        losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
+    assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2} for v in losses.values())
+    assert sum("Finished training of 2 DiLoCo update rounds" in l for l in logs) == 2

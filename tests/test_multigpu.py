@@ -57,3 +57,45 @@ def test_kill_and_rejoin_over_peer_memory():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=550, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"correct": true' in r.stdout
+
+
+@pytest.mark.timeout(600)
+def test_collective_job_through_the_control_plane(tmp_path):
+    """Full stack on 2 GPUs: gateway + data node + 2 workers + scheduler over the loopback fabric; the
+    scheduler allocates the workers by lease, dispatches a `collective` DiLoCo job, each worker spawns
+    the executor process for its GPU, the executors train a small Llama with the sm_100a kernels and
+    run the fused peer-memory outer step; rounds are paced by the batch scheduler over the job bridge."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import asyncio
+
+    from hypha_b200.executor.dataset import write_synthetic_token_slices
+    from hypha_b200.local_cluster import run_loopback_job
+    from hypha_b200.models.llama import get_config
+
+    cfg = get_config("llama-tiny")
+    job = {
+        "model": {"repository": "local/llama-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 24, "update_rounds": 3, "max_batch_size": 2},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"mode": "collective"},
+        "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        str(tmp_path), repo="local/llama-tiny", write_model_config=lambda p: cfg.to_hf_json(p, seed=3), job=job,
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=8, samples_per_slice=16, seq_len=128,
+                                                             vocab_size=cfg.vocab_size), timeout_s=400))
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 3 and outcome.parameter_server == "collective"
+    assert sum("outer step via fused" in l for l in logs) == 2, logs[-30:]
+    losses = {}
+    for r in sink.records:
+        losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
+    assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2, 3} for v in losses.values())
+    assert all(0 < v < 12 for w in losses.values() for v in w.values())
