@@ -216,6 +216,13 @@ class JobResources:
 
 
 @dataclass
+class ElasticSection:
+    enabled: bool = doc("keep the job running when a train worker's lease is lost (the reference scheduler "
+                        "exits on the first failure)", True)
+    min_workers: int = doc("stop the job when fewer train workers than this remain", 1)
+
+
+@dataclass
 class AggregationSection:
     mode: str = doc("`parameter-server` (reference behaviour: pseudo-gradient files through an aggregate worker) "
                     "or `collective` (the train workers synchronise among themselves: fused NVLink outer step on "
@@ -235,6 +242,7 @@ class DiLoCoJob:
     outer_optimizer: NesterovSection = doc("outer optimizer", factory=NesterovSection)
     resources: JobResources = doc("allocation request", factory=JobResources)
     aggregation: AggregationSection = doc("how the outer step is carried out", factory=AggregationSection)
+    elastic: ElasticSection = doc("behaviour on worker failure", factory=ElasticSection)
 
 
 @dataclass

@@ -522,10 +522,17 @@ class BatchScheduler {
       case ProgressKind::Update:
         if (!tracker.workers.contains(peer)) { r.kind = ResponseKind::Error; return r; }
         tracker.workers.set_state(peer, WorkerState::Updating);
+        round_advanced_ = false;
         r.kind = ResponseKind::Ok;
         return r;
       case ProgressKind::Updated:
-        tracker.next_round(now_ms);
+        // Idempotent within one synchronisation: in collective mode every rank may report `updated`
+        // (no single aggregate worker whose death would stall the round); only the first one after
+        // the workers' `update` messages advances the round.
+        if (!round_advanced_) {
+          tracker.next_round(now_ms);
+          round_advanced_ = true;
+        }
         r.kind = tracker.training_finished() ? ResponseKind::Done : ResponseKind::Ok;
         return r;
       case ProgressKind::UpdateReceived:
@@ -548,6 +555,7 @@ class BatchScheduler {
  private:
   uint64_t time_cap_;
   uint32_t update_cap_;
+  bool round_advanced_ = false;
 };
 
 // ------------------------------------------------------------------------------------

@@ -188,10 +188,16 @@ class _TrainerEngine:
         return self.trainer.inner_step(ids, batch.get("labels", torch.roll(ids, -1, dims=-1)))
 
     def outer_step(self) -> None:
-        self.trainer.outer_step()
-        st = self.trainer.outer.check()
-        if st != (0, 0):
-            raise RuntimeError(f"fused outer step failed: status {st}")
+        outer = self.trainer.outer
+        if outer.backend == "fused":
+            # a rank that never shows up costs one barrier timeout, then the survivors adopt its shard
+            # and go on (DiLoCoOuter.step_resilient); raises only if the step cannot be completed
+            before = outer.members()
+            outer.step_resilient()
+            if outer.members() != before:
+                print(f"outer step continued without ranks {sorted(set(before) - set(outer.members()))}", flush=True)
+        else:
+            self.trainer.outer_step()
 
 
 class _GenericEngine:
@@ -257,10 +263,10 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         mean_loss = float(loss_sum.item() / max(1, steps))
         session.send_status({"metrics": {"round": round_no, "metrics": {"loss": mean_loss}}})
         print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}; outer step done", flush=True)
-        if rank == 0:
-            session.send_status("updated")         # what the aggregate worker reports in parameter-server mode
-        if world > 1:
-            dist.barrier()                         # nobody acknowledges before the round counter advanced
+        # what the aggregate worker reports in parameter-server mode.  Every rank sends it (the scheduler
+        # advances the round on the first one and ignores the rest), so no rank is a single point of
+        # failure and each rank's own `updated` precedes its `update-received`.
+        session.send_status("updated")
         round_no += 1
         if session.send_status("update-received")["type"] == "Done":
             break

@@ -29,8 +29,10 @@ def worker_config(gateway: str, work_dir: str, executors: List[dict], gpu: float
 async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[[str], None],
                            write_dataset: Callable[[str], None], job: Dict[str, Any], num_workers: int = 2,
                            timeout_s: float = 600.0, log: Optional[Callable[[str], None]] = None,
-                           omp_threads: int = 2) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
-    """Returns ``(JobOutcome, metrics sink, executor logs, nodes)``."""
+                           omp_threads: int = 2, chaos: Optional[Callable[[Dict[str, Any], List[str]], Any]] = None
+                           ) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
+    """Returns ``(JobOutcome, metrics sink, executor logs, nodes)``.  ``chaos(nodes_by_peer_id, logs)`` is an
+    optional coroutine run next to the job (fault injection: e.g. stop a worker node mid-run)."""
     registry = os.path.join(tmp, "registry")
     os.makedirs(os.path.join(registry, repo), exist_ok=True)
     write_model_config(os.path.join(registry, repo, "config.json"))
@@ -67,6 +69,8 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
     over = {"listen_addresses": [], "gateway_addresses": [gw_addr], "exclude_cidr": [], "scheduler": {"job": job}}
     sched_cfg = C.builder(C.SchedulerConfig).with_overrides(over).build()
     sink = MemoryConnector()
+    if chaos is not None:
+        bg.append(asyncio.ensure_future(chaos({n.peer_id: n for n in nodes}, logs)))
     try:
         outcome = await asyncio.wait_for(
             roles.run_scheduler(sched_cfg, peer_id="scheduler", metrics_connector=sink, allocation_pause_s=0.7),

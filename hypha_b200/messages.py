@@ -520,7 +520,10 @@ class ApiRequest:
     kind: str
     body: Dict[str, Any]
 
-    KINDS = ("WorkerOffer", "RenewLease", "JobStatus", "DispatchJob", "ParameterPull", "ParameterPush", "Data")
+    # "JobMembership" is a B200 extension: the scheduler tells an aggregate job which train workers are
+    # still part of the job after a lease was lost (the reference has no such message: its PS waits forever)
+    KINDS = ("WorkerOffer", "RenewLease", "JobStatus", "DispatchJob", "ParameterPull", "ParameterPush", "Data",
+             "JobMembership")
 
     def to_wire(self) -> dict:
         return {self.kind: self.body}
@@ -553,6 +556,10 @@ class ApiRequest:
     @classmethod
     def data(cls, dataset: str):
         return cls("Data", {"dataset": dataset})
+
+    @classmethod
+    def job_membership(cls, job_id: str, workers: List[str]):
+        return cls("JobMembership", {"job_id": job_id, "workers": list(workers)})
 
     @classmethod
     def parameter_pull(cls, job_id: str, key: str, version: Optional[int] = None):
@@ -600,6 +607,10 @@ class ApiResponse:
     @classmethod
     def job_status(cls):
         return cls("JobStatus", {})
+
+    @classmethod
+    def job_membership(cls, known: bool):
+        return cls("JobMembership", {"known": bool(known)})
 
     @classmethod
     def data_success(cls, data_provider: str, index: int):

@@ -201,6 +201,7 @@ class JobOutcome:
     parameter_server: str
     metrics: List[Dict[str, Any]]
     finished: bool
+    removed_workers: List[str] = field(default_factory=list)   # train workers dropped after a lost lease
 
 
 def _free_tcp_port() -> int:
@@ -321,20 +322,46 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
         bridge.register_stream(batch.metrics)
         bridge_task = asyncio.ensure_future(bridge.run())
 
-        # wait: job done | any lease lost | stop requested (hypha-scheduler.rs:396-412)
-        waiters = {asyncio.ensure_future(batch.done.wait()): "done", asyncio.ensure_future(node.stop.wait()): "stop"}
+        # wait: job done | stop requested | lease lost.  The reference exits on the first lost lease
+        # (hypha-scheduler.rs:396-412, quirk Q9); with `elastic.enabled` a lost TRAIN worker is removed
+        # from the batch/slice schedulers, the aggregate job is told the new membership, and the job
+        # goes on while at least `elastic.min_workers` remain.
+        waiters: Dict[Any, Any] = {asyncio.ensure_future(batch.done.wait()): "done",
+                                   asyncio.ensure_future(node.stop.wait()): "stop"}
         for h in handles:
             if h.task is not None:
-                waiters[h.task] = f"lease:{h.peer_id}"
-        done, _ = await asyncio.wait(waiters.keys(), return_when=asyncio.FIRST_COMPLETED)
-        reason = waiters[next(iter(done))]
+                waiters[h.task] = h
+        live = list(worker_ids)
+        removed: List[str] = []
+        reason = "done"
+        while True:
+            done, _ = await asyncio.wait(waiters.keys(), return_when=asyncio.FIRST_COMPLETED)
+            first = next(iter(done))
+            what = waiters.pop(first)
+            if isinstance(what, str):
+                reason = what
+                break
+            peer = what.peer_id
+            reason = f"lease:{peer}"
+            if not (job.elastic.enabled and peer in live and len(live) - 1 >= max(1, job.elastic.min_workers)):
+                break
+            live.remove(peer)
+            removed.append(peer)
+            log.warning("lost the lease of train worker %s: continuing with %d worker(s)", peer, len(live))
+            batch.remove_worker(peer)
+            data_svc.remove_worker(peer)
+            if not collective:
+                try:
+                    await net.request(ps.peer_id, M.API_PROTOCOL, M.ApiRequest.job_membership(job_id, live), timeout=5.0)
+                except NetworkError as exc:
+                    log.warning("could not tell the aggregate worker about the new membership: %s", exc)
         finished = batch.done.is_set()
         if not finished:
             log.warning("scheduler stopping before completion: %s", reason)
         await asyncio.sleep(0.05)              # let the last metrics drain
         bridge_task.cancel()
         return JobOutcome(job_id, batch.round, worker_ids, "collective" if collective else ps.peer_id, collected,
-                          finished)
+                          finished, removed)
     finally:
         for t in tasks:
             t.close()

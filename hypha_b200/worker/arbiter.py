@@ -110,11 +110,23 @@ class Arbiter:
                 job.execution.cancel()
         return len(removed)
 
+    async def _on_membership(self, peer: str, msg) -> M.ApiResponse:
+        """Scheduler -> aggregate job: the set of train workers still in the job (sent after a lease was
+        lost).  Only the scheduler that owns the job may change it."""
+        body = msg["JobMembership"]
+        known = False
+        for job in self.jobs.find_jobs_by_scheduler(peer):
+            if job.spec.job_id == str(body["job_id"]):
+                job.execution.set_members([str(w) for w in body["workers"]])
+                known = True
+        return M.ApiResponse.job_membership(known)
+
     # -- main loop -----------------------------------------------------------------------------------------
     async def run(self, stop: asyncio.Event) -> None:
         self._regs = [
             self.network.on(M.API_PROTOCOL, lambda m: isinstance(m, dict) and "RenewLease" in m, self._on_renew),
             self.network.on(M.API_PROTOCOL, lambda m: isinstance(m, dict) and "DispatchJob" in m, self._on_dispatch),
+            self.network.on(M.API_PROTOCOL, lambda m: isinstance(m, dict) and "JobMembership" in m, self._on_membership),
         ]
         sub = await self.network.subscribe(M.WORKER_TOPIC)
         window = self.core.BatchWindow(WINDOW_LIMIT, WINDOW_S)

@@ -48,9 +48,15 @@ class Execution:
         self.done = asyncio.Event()
         self.status = M.JobStatus.RUNNING
         self._cancel = asyncio.Event()
+        self.members: Optional[List[str]] = None          # set by the scheduler after a lease was lost
+        self.members_changed = asyncio.Event()
 
     def cancel(self) -> None:
         self._cancel.set()
+
+    def set_members(self, workers: List[str]) -> None:
+        self.members = list(workers)
+        self.members_changed.set()
 
     async def wait(self) -> M.JobStatus:
         await self.done.wait()
@@ -177,21 +183,45 @@ class ParameterServerExecutor:
             rnd = 0
             incoming = self.connector.receive(cfg.updates, job_id=spec.job_id)
             try:
+                nxt: Optional[asyncio.Future] = None
                 while True:
                     got: Dict[str, str] = {}
                     while len(got) < len(workers):
-                        try:
-                            st = await asyncio.wait_for(incoming.__anext__(), self.receive_timeout_s)
-                        except asyncio.TimeoutError:
+                        if nxt is None:
+                            nxt = asyncio.ensure_future(incoming.__anext__())
+                        mem = asyncio.ensure_future(ex.members_changed.wait())
+                        done, _ = await asyncio.wait({nxt, mem}, timeout=self.receive_timeout_s,
+                                                     return_when=asyncio.FIRST_COMPLETED)
+                        if mem not in done:
+                            mem.cancel()
+                        if mem in done and ex.members is not None:
+                            # the scheduler lost a worker's lease: stop waiting for it (Q8/Q9)
+                            ex.members_changed.clear()
+                            gone = [w for w in workers if w not in ex.members]
+                            if gone:
+                                self.log(f"[ps {spec.job_id[:8]}] round {rnd}: scheduler removed {gone}")
+                            workers = [w for w in workers if w in ex.members]
+                            for w in gone:
+                                p_gone = got.pop(w, None)
+                                if p_gone and os.path.exists(p_gone):
+                                    os.unlink(p_gone)
+                            if not workers:
+                                raise RuntimeError("no train worker left")
+                        if nxt in done:
+                            st = nxt.result()
+                            nxt = None
+                            if st.peer not in workers:
+                                continue                               # late file from a removed worker
+                            path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
+                            await st.save(path)
+                            got[st.peer] = path
+                        elif not done:
                             missing = [w for w in workers if w not in got]
                             if not got:
-                                raise
+                                raise asyncio.TimeoutError()
                             self.log(f"[ps {spec.job_id[:8]}] round {rnd}: timeout, dropping {missing}")
                             workers = [w for w in workers if w in got]      # membership shrink (Q8)
                             break
-                        path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
-                        await st.save(path)
-                        got[st.peer] = path
                     # true mean + Nesterov, one tensor at a time, OFF the event loop: the worker must
                     # keep answering RenewLease / health RPCs while hundreds of MB are being reduced
                     out = os.path.join(work_dir, "gradient_update")
@@ -235,6 +265,8 @@ class ParameterServerExecutor:
                 self.log(f"[ps {spec.job_id[:8]}] failed: {type(exc).__name__}: {exc}")
                 ex.status = M.JobStatus.FAILED
             finally:
+                if nxt is not None and not nxt.done():
+                    nxt.cancel()
                 try:
                     await incoming.aclose()
                 except Exception:

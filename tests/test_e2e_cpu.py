@@ -90,3 +90,42 @@ def test_gpt2_diloco_collective_mode_loopback(tmp_path):
         losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
     assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2} for v in losses.values())
     assert sum("Finished training of 2 DiLoCo update rounds" in l for l in logs) == 2
+
+
+def test_scheduler_survives_a_lost_train_worker(tmp_path):
+    """Elastic job (quirks Q8/Q9): one of three train workers dies after the first round.  The scheduler
+    notices the lost lease, removes the worker from the batch and slice schedulers, tells the aggregate
+    job the new membership (so it stops waiting for that worker's pseudo-gradient) and the job
+    finishes all rounds with the two survivors.  The reference scheduler exits at this point."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 48, "update_rounds": 3, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def kill_worker_c(nodes, logs):
+        while not any(l.startswith("round 1:") or " round 1:" in l for l in logs):
+            await asyncio.sleep(0.1)
+        nodes["worker-c"].stop.set()
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=9, samples_per_slice=16, seq_len=32,
+                                                             vocab_size=512), timeout_s=300, chaos=kill_worker_c))
+    assert outcome.finished, logs[-25:]
+    assert outcome.rounds == 3 and outcome.removed_workers == ["worker-c"]
+    assert any("scheduler removed [\'worker-c\']" in l or "dropping [\'worker-c\']" in l for l in logs), logs[-25:]
+    done = [l for l in logs if "Finished training of 3 DiLoCo update rounds" in l]
+    assert len(done) == 2                                   # the two survivors ran to completion
+    last_round = {}
+    for r in sink.records:
+        last_round[r["worker_id"]] = max(last_round.get(r["worker_id"], 0), r["round"])
+    assert last_round["worker-a"] == 3 and last_round["worker-b"] == 3
