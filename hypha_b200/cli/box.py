@@ -1,0 +1,139 @@
+"""``hypha-box``: one command for one box (not in the reference, whose roles are always separate
+daemons).  Starts gateway + data node + one worker per GPU + scheduler in one process over the
+loopback fabric and runs ONE DiLoCo job to completion, in ``collective`` aggregation mode by default:
+the scheduler leases the workers, every worker spawns the executor for its GPU, the executors train
+through the sm_100a kernels and synchronise with the fused NVLink outer step.
+
+    hypha-box run --model llama3-8b --workers 8 --rounds 10 --samples-per-round 6400 --batch-size 2
+    hypha-box run --model-config ./my-llama/config.json --dataset-path ./corpus
+    hypha-box run --model gpt2-tiny --workers 2 --device cpu              # plumbing check without GPUs
+
+The job is the same `[scheduler.job]` a stand-alone ``hypha-scheduler`` takes (``--job`` merges extra
+keys as JSON); the result is printed as one JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import os
+import shutil
+import sys
+import tempfile
+from typing import List, Optional
+
+
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(prog="hypha-box", description=__doc__.split("\n\n")[0])
+    sub = p.add_subparsers(dest="command", required=True)
+    r = sub.add_parser("run", help="run one DiLoCo job on this box")
+    r.add_argument("--model", default="llama-tiny",
+                   help="preset (llama3-8b, llama3-1b, llama-small, llama-tiny, gpt2-tiny, gpt2-small)")
+    r.add_argument("--model-config", default=None, help="path to a Hugging-Face style config.json (overrides --model)")
+    r.add_argument("--workers", type=int, default=0, help="train workers (default: one per visible GPU, 2 on CPU)")
+    r.add_argument("--device", choices=["auto", "cuda", "cpu"], default="auto")
+    r.add_argument("--rounds", type=int, default=2, help="DiLoCo outer rounds")
+    r.add_argument("--samples-per-round", type=int, default=64, help="samples processed by all workers between outer steps")
+    r.add_argument("--batch-size", type=int, default=2, help="per-worker batch size cap")
+    r.add_argument("--seq-len", type=int, default=128, help="sequence length of the synthetic corpus")
+    r.add_argument("--dataset-path", default=None, help="directory of safetensors slices (default: synthetic tokens)")
+    r.add_argument("--lr", type=float, default=1e-4)
+    r.add_argument("--outer-lr", type=float, default=0.7)
+    r.add_argument("--outer-momentum", type=float, default=0.9)
+    r.add_argument("--aggregation", choices=["collective", "parameter-server"], default="collective")
+    r.add_argument("--job", default=None, help="extra [scheduler.job] keys as JSON (merged last)")
+    r.add_argument("--work-dir", default=None, help="scratch directory (default: a temporary one, removed at exit)")
+    r.add_argument("--timeout", type=float, default=3600.0)
+    r.add_argument("--verbose", action="store_true", help="echo executor output")
+    return p
+
+
+def _write_model_config(args) -> tuple:
+    """Returns (repo name, writer(path), vocab_size)."""
+    if args.model_config:
+        meta = json.load(open(args.model_config))
+        return "local/custom", (lambda p: shutil.copyfile(args.model_config, p)), int(meta.get("vocab_size", 32000))
+    if args.model.startswith("gpt2"):
+        from ..models.gpt2 import GPT2Config
+
+        cfg = GPT2Config.tiny() if args.model == "gpt2-tiny" else GPT2Config()
+        return f"local/{args.model}", cfg.to_json, int(cfg.vocab_size)
+    from ..models.llama import get_config
+
+    cfg = get_config(args.model, max_seq_len=max(args.seq_len, 8))
+    return f"local/{args.model}", (lambda p: cfg.to_hf_json(p)), int(cfg.vocab_size)
+
+
+def _deep_merge(a: dict, b: dict) -> dict:
+    for k, v in b.items():
+        a[k] = _deep_merge(a.get(k, {}), v) if isinstance(v, dict) and isinstance(a.get(k), dict) else v
+    return a
+
+
+def run(args) -> int:
+    import torch
+
+    from ..executor.dataset import write_synthetic_token_slices
+    from ..local_cluster import run_loopback_job
+
+    use_cuda = args.device == "cuda" or (args.device == "auto" and torch.cuda.is_available())
+    workers = args.workers or (torch.cuda.device_count() if use_cuda else 2)
+    if use_cuda and workers > torch.cuda.device_count():
+        print(f"hypha-box: {workers} workers requested but only {torch.cuda.device_count()} GPUs visible", file=sys.stderr)
+        return 2
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cuda" if use_cuda else "cpu"
+    repo, writer, vocab = _write_model_config(args)
+    job = {
+        "model": {"repository": repo, "filenames": ["config.json"], "type": "causal-lm", "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": os.path.basename(os.path.normpath(args.dataset_path)) if args.dataset_path else "synthetic-tokens"},
+        "rounds": {"avg_samples_between_updates": args.samples_per_round, "update_rounds": args.rounds,
+                   "max_batch_size": args.batch_size},
+        "inner_optimizer": {"learning-rate": args.lr},
+        "outer_optimizer": {"learning-rate": args.outer_lr, "momentum": args.outer_momentum},
+        "aggregation": {"mode": args.aggregation},
+        "resources": {"num_workers": workers, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+    if args.job:
+        _deep_merge(job, json.loads(args.job))
+    tmp = args.work_dir or tempfile.mkdtemp(prefix="hypha-box-")
+    os.makedirs(tmp, exist_ok=True)
+
+    def write_dataset(d: str) -> None:
+        if args.dataset_path:
+            if os.path.abspath(args.dataset_path) != os.path.abspath(d):
+                shutil.copytree(args.dataset_path, d, dirs_exist_ok=True)
+            return
+        per_round = max(args.samples_per_round, workers * args.batch_size)
+        slices = max(2 * workers, 4)
+        write_synthetic_token_slices(d, num_slices=slices, samples_per_slice=max(8, -(-per_round * 2 // slices)),
+                                     seq_len=args.seq_len, vocab_size=vocab)
+
+    log = (lambda m: print(m, file=sys.stderr, flush=True)) if args.verbose else None
+    try:
+        outcome, sink, logs, _ = asyncio.run(run_loopback_job(
+            tmp, repo=repo, write_model_config=writer, write_dataset=write_dataset, job=job, num_workers=workers,
+            timeout_s=args.timeout, log=log))
+    finally:
+        if not args.work_dir:
+            shutil.rmtree(tmp, ignore_errors=True)
+    by_worker: dict = {}
+    for rec in sink.records:
+        by_worker.setdefault(rec["worker_id"], {}).setdefault(str(rec["round"]), {})[rec["metric_name"]] = rec["value"]
+    print(json.dumps({"finished": outcome.finished, "rounds": outcome.rounds, "workers": outcome.workers,
+                      "removed_workers": outcome.removed_workers, "aggregation": args.aggregation,
+                      "device": "cuda" if use_cuda else "cpu", "metrics": by_worker}))
+    if not outcome.finished:
+        print("\n".join(logs[-30:]), file=sys.stderr)
+    return 0 if outcome.finished else 1
+
+
+def main(argv: Optional[List[str]] = None) -> int:
+    args = build_parser().parse_args(argv)
+    return run(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -20,6 +20,7 @@ import argparse
 import json
 import os
 import sys
+import time
 from typing import Any, Dict, Iterator, List, Optional
 
 import torch
@@ -243,14 +244,22 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         batch_size=config["batch_size"])
     batches = forever(loader)
     round_no = 1
+    def sync():
+        if use_cuda:
+            torch.cuda.synchronize()
+
     while True:
         loss_sum = torch.zeros((), device=device)
-        steps, counter = 0, -1
+        steps, counter, tokens = 0, -1, 0
+        sync()
+        t_round = time.perf_counter()
         while counter != 0:
             batch = next(batches)
             loss_sum += engine.step(batch)
             steps += 1
-            bs = int(next(iter(batch.values())).shape[0])
+            first = next(iter(batch.values()))
+            bs = int(first.shape[0])
+            tokens += int(first.numel()) if first.dim() == 2 and not first.dtype.is_floating_point else bs
             resp = session.send_status({"status": {"batch_size": bs}})
             if resp["type"] == "ScheduleUpdate":
                 counter = resp["counter"]
@@ -258,11 +267,21 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
                 raise RuntimeError("scheduler rejected status")
             else:
                 counter -= 1
+        sync()
+        inner_s = time.perf_counter() - t_round
         session.send_status("update")
+        t_outer = time.perf_counter()
         engine.outer_step()                        # every rank enters: the kernel / all-reduce is the barrier
+        sync()
+        outer_ms = (time.perf_counter() - t_outer) * 1e3
         mean_loss = float(loss_sum.item() / max(1, steps))
-        session.send_status({"metrics": {"round": round_no, "metrics": {"loss": mean_loss}}})
-        print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}; outer step done", flush=True)
+        # the reference reports the loss only (training.py:148-150); the extra keys are SURVEY 5.5's
+        # "tokens/s, step time, outer-step wall time" and travel through the same Metrics message
+        session.send_status({"metrics": {"round": round_no, "metrics": {
+            "loss": mean_loss, "samples_or_tokens_per_s": tokens / max(inner_s, 1e-9),
+            "inner_step_ms": inner_s * 1e3 / max(1, steps), "outer_step_ms": outer_ms}}})
+        print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}, {inner_s * 1e3 / max(1, steps):.1f} ms/step; "
+              f"outer step done in {outer_ms:.1f} ms", flush=True)
         # what the aggregate worker reports in parameter-server mode.  Every rank sends it (the scheduler
         # advances the round on the first one and ignores the rest), so no rank is a single point of
         # failure and each rank's own `updated` precedes its `update-received`.

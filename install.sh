@@ -31,7 +31,7 @@ else
 fi
 
 mkdir -p "$DEST"
-for role in gateway scheduler worker data certutil; do
+for role in gateway scheduler worker data certutil box; do
   target="$DEST/hypha-$role"
   printf '#!/bin/sh\nPYTHONPATH="%s${PYTHONPATH:+:$PYTHONPATH}" exec %s -m hypha_b200.cli.%s "$@"\n' "$ROOT" "$PY" "$role" > "$target"
   chmod +x "$target"

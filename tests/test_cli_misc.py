@@ -93,3 +93,18 @@ def test_aim_driver_jsonl_fallback(tmp_path, monkeypatch):
     assert r.status_code == 200
     assert json.loads((tmp_path / "m.jsonl").read_text())["value"] == 1.5
     assert c.post("/status", json={"worker_id": "w1"}).status_code == 422
+
+
+def test_hypha_box_runs_a_collective_job_on_cpu(capsys):
+    """`hypha-box run`: gateway + data + 2 workers + scheduler in one process, collective aggregation
+    over gloo, one JSON line with per-worker per-round metrics."""
+    import json
+
+    from hypha_b200.cli import box
+
+    rc = box.main(["run", "--model", "gpt2-tiny", "--workers", "2", "--device", "cpu", "--rounds", "2",
+                   "--samples-per-round", "32", "--batch-size", "4", "--seq-len", "32", "--timeout", "240"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rc == 0 and out["finished"] and out["rounds"] == 2 and out["aggregation"] == "collective"
+    assert sorted(out["metrics"]) == ["worker-a", "worker-b"]
+    assert set(out["metrics"]["worker-a"]["2"]) == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms"}

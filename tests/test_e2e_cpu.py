@@ -85,8 +85,13 @@ def test_gpt2_diloco_collective_mode_loopback(tmp_path):
     assert outcome.rounds == 2 and sorted(outcome.workers) == ["worker-a", "worker-b"]
     assert outcome.parameter_server == "collective"
     assert sum("outer step via all-reduce" in l for l in logs) == 2
+    names = {r["metric_name"] for r in sink.records}
+    assert names == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms"}
+    assert all(r["value"] > 0 for r in sink.records)
     losses = {}
     for r in sink.records:
+        if r["metric_name"] != "loss":
+            continue
         losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
     assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2} for v in losses.values())
     assert sum("Finished training of 2 DiLoCo update rounds" in l for l in logs) == 2

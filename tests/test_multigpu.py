@@ -96,6 +96,7 @@ def test_collective_job_through_the_control_plane(tmp_path):
     assert sum("outer step via fused" in l for l in logs) == 2, logs[-30:]
     losses = {}
     for r in sink.records:
-        losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
+        if r["metric_name"] == "loss":
+            losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
     assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2, 3} for v in losses.values())
     assert all(0 < v < 12 for w in losses.values() for v in w.values())
