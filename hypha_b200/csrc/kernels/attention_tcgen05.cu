@@ -39,7 +39,6 @@ constexpr int kVStages = 2;          // P lives in TMEM, so its 16 KB of smem bu
 constexpr int kQBytes = kBM * kD * 2;          // 32 KB (two 64-column swizzle atoms)
 constexpr int kKBytes = kBN * kD * 2;          // 16 KB
 constexpr int kVBytes = kBN * kD * 2;          // 16 KB
-constexpr int kPBytes = kBM * kBN * 2;         // 16 KB
 constexpr int kAttnTmemCols = 256;             // S: 0..63, O_j: 64..191
 constexpr int kAttnThreads = 256;
 
@@ -48,7 +47,7 @@ struct AttnSmem {
   static constexpr int k_off = q_off + kQBytes;
   static constexpr int v_off = k_off + kKVStages * kKBytes;
   static constexpr int bar_off = v_off + kVStages * kVBytes;
-  // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full, o_full, o_free, tmem ptr
+  // q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full, s_free, p_full, o_full, (spare), tmem ptr
   static constexpr int total = bar_off + 16 * 8;
 };
 constexpr int kAttnSmemBytes = AttnSmem::total + 1024;
@@ -84,7 +83,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
   auto v_full = [&](int s) { return bars + 8u * (5 + s); };
   auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
   const uint32_t s_full = bars + 8u * 9, s_free = bars + 8u * 10, p_full = bars + 8u * 11;
-  const uint32_t o_full = bars + 8u * 12, o_free = bars + 8u * 13;
+  const uint32_t o_full = bars + 8u * 12;
   const uint32_t tmem_ptr_smem = bars + 8u * 14;
   volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + AttnSmem::bar_off + 8 * 14);
 
@@ -108,7 +107,7 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
       mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
     }
     mbar_init(s_full, 1); mbar_init(s_free, 4); mbar_init(p_full, 4);
-    mbar_init(o_full, 1); mbar_init(o_free, 4);
+    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_ptr_smem, kAttnTmemCols);
