@@ -123,3 +123,28 @@ def test_tls_loader(tmp_path):
     cfg = C.builder(C.GatewayConfig).with_overrides({"key_pem": str(tmp_path / "missing.pem")}).build()
     with pytest.raises(C.ConfigError):
         C.load_tls(cfg)
+
+
+def test_scheduler_job_aggregation_and_elastic_sections(tmp_path):
+    """B200 extensions of [scheduler.job]: `aggregation.mode` is validated, `elastic` defaults on, both
+    survive an init -> TOML -> load round trip."""
+    from hypha_b200 import config as C
+
+    cfg = C.builder(C.SchedulerConfig).with_overrides(
+        {"scheduler": {"job": {"aggregation": {"mode": "collective", "rendezvous": "tcp://127.0.0.1:29400"},
+                               "elastic": {"min_workers": 2}}}}).build()
+    C.validate(cfg)
+    path = tmp_path / "s.toml"
+    path.write_text(C.to_toml(cfg))
+    back = C.builder(C.SchedulerConfig).with_toml(str(path)).build()
+    assert back.scheduler.job.aggregation.mode == "collective"
+    assert back.scheduler.job.aggregation.rendezvous == "tcp://127.0.0.1:29400"
+    assert back.scheduler.job.elastic.enabled is True and back.scheduler.job.elastic.min_workers == 2
+    bad = C.builder(C.SchedulerConfig).with_overrides({"scheduler": {"job": {"aggregation": {"mode": "ring"}}}}).build()
+    with pytest.raises(C.ConfigError) as ei:
+        C.validate(bad)
+    assert "unknown aggregation mode" in str(ei.value)
+    bad2 = C.builder(C.SchedulerConfig).with_overrides(
+        {"scheduler": {"job": {"aggregation": {"mode": "collective", "rendezvous": "udp://x"}}}}).build()
+    with pytest.raises(C.ConfigError):
+        C.validate(bad2)
