@@ -40,8 +40,9 @@ def parse_args():
     ap.add_argument("--state-dtype", default=os.environ.get("HYPHA_BENCH_STATE", "bf16"))
     ap.add_argument("--outer-backend", default="auto")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--min-free-gb", type=float, default=4.0,
-                    help="memory head-room a recompute plan must leave after two trial steps")
+    ap.add_argument("--min-free-gb", type=float, default=-1.0,
+                    help="memory head-room a recompute plan must leave at the step peak "
+                         "(default: 0.5 GB on one GPU, 3 GB with NCCL in the process)")
     ap.add_argument("--fault-drill", action="store_true",
                     help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
                          "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
@@ -268,6 +269,7 @@ def main():
     else:
         candidates = [0]
     trainer = cfg = None
+    mem_slack_gb = float("nan")
     for recompute in candidates:
         ok = 1
         try:
@@ -280,7 +282,9 @@ def main():
             # cuDNN workspaces): a plan that only just fits is rejected like an OOM
             free, _ = torch.cuda.mem_get_info(dev)
             slack = free + torch.cuda.memory_reserved(dev) - torch.cuda.max_memory_allocated(dev)   # at the step's peak
-            if slack < args.min_free_gb * 2 ** 30 and recompute != candidates[-1]:
+            need = args.min_free_gb if args.min_free_gb >= 0 else (0.5 if world == 1 else 3.0)
+            mem_slack_gb = slack / 2 ** 30
+            if slack < need * 2 ** 30 and recompute != candidates[-1]:
                 ok = 0
                 del trainer
                 trainer = None
@@ -415,7 +419,8 @@ def main():
                 "outer_nvls": bool(trainer.outer.backend == "fused" and trainer.outer._multicast_ptrs()[0]),
                 "outer_pipeline": list(trainer.outer._pipeline_shape()) if trainer.outer.backend == "fused" else None,
                 "optimizer": f"fused flat AdamW, fp32 master, {args.state_dtype} moments",
-                "recompute_layers": recompute, "gemm_backend": ops.get_gemm_backend(),
+                "recompute_layers": recompute, "mem_slack_at_peak_gb": round(mem_slack_gb, 2),
+                "gemm_backend": ops.get_gemm_backend(),
                 "attention_backend": ops.get_attention_backend(),
                 "l2": "no flush needed: >16 GB of weights/activations streamed per step >> 126 MB L2",
             },
