@@ -83,6 +83,23 @@ def _recv_fds(server: socket.socket, count: int, nfds: int):
 class NvlsBuffer(SymmetricBuffer):
     mc_ptr: int = 0                 # multicast virtual address (0 if multicast could not be set up)
     nbytes_mapped: int = 0
+    _handles: Optional[list] = None  # driver handles to release in close(): [(va, size, handle), ...]
+
+    def close(self) -> None:
+        """Unmap every view and release the allocation handles (idempotent; errors are ignored: the
+        peers may already be gone at shutdown)."""
+        if not self._handles:
+            return
+        cu = _cu()
+        for va, size, handle in self._handles:
+            try:
+                cu.cuMemUnmap(va, size)
+                cu.cuMemAddressFree(va, size)
+                cu.cuMemRelease(handle)
+            except Exception:
+                pass
+        self._handles = None
+        self.mc_ptr = 0
 
 
 def multicast_supported(device: int) -> bool:
@@ -164,10 +181,13 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     access.location.id = device
     access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
 
+    mapped: list = []
+
     def map_handle(h) -> int:
         va = _ck(cu.cuMemAddressReserve(size, gran, 0, 0), "cuMemAddressReserve")
         _ck(cu.cuMemMap(va, size, 0, h, 0), "cuMemMap")
         _ck(cu.cuMemSetAccess(va, size, [access], 1), "cuMemSetAccess")
+        mapped.append((va, size, h))
         return int(va)
 
     ptrs = [0] * world
@@ -195,6 +215,6 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     local.zero_()
     torch.cuda.synchronize()
     group._exchange(rank)
-    buf = NvlsBuffer(name, numel, dtype, local, ptrs, mc_ptr=mc_ptr, nbytes_mapped=size)
+    buf = NvlsBuffer(name, numel, dtype, local, ptrs, mc_ptr=mc_ptr, nbytes_mapped=size, _handles=mapped)
     group.buffers[name] = buf
     return buf

@@ -139,6 +139,9 @@ class PeerGroup:
             except Exception:
                 pass
         self._opened.clear()
+        for b in self.buffers.values():
+            if hasattr(b, "close"):          # NVLS (VMM + multicast) buffers release their own mappings
+                b.close()
         self.buffers.clear()
         for p in self._owned:
             try:

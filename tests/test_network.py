@@ -372,3 +372,36 @@ def test_tcp_links_use_mutual_tls(tmp_path):
             await n.close()
 
     asyncio.run(main())
+
+
+def test_nvls_descriptor_exchange_helpers(tmp_path):
+    """The VMM handle exchange of parallel/nvls.py passes POSIX file descriptors between rank processes
+    over AF_UNIX (SCM_RIGHTS); here with pipe fds instead of CUDA allocation handles."""
+    import os
+    import socket
+    import threading
+
+    from hypha_b200.parallel.nvls import _recv_fds, _send_fds
+
+    path = str(tmp_path / "r0.sock")
+    srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+    srv.bind(path)
+    srv.listen(4)
+    srv.settimeout(10)
+    box = {}
+    t = threading.Thread(target=lambda: box.update(_recv_fds(srv, 2, 2)))
+    t.start()
+    pipes = {1: os.pipe(), 2: os.pipe()}
+    for rank, (r, w) in pipes.items():
+        _send_fds(path, rank, [w] if rank == 2 else [w, r])
+    t.join()
+    srv.close()
+    assert sorted(box) == [1, 2] and len(box[1]) == 2 and len(box[2]) == 1
+    os.write(box[2][0], b"hello")                      # the duplicated descriptor reaches the same pipe
+    assert os.read(pipes[2][0], 5) == b"hello"
+    for fds in box.values():
+        for fd in fds:
+            os.close(fd)
+    for r, w in pipes.values():
+        os.close(r)
+        os.close(w)
