@@ -65,9 +65,6 @@ struct BwdParams {
   const float* lse2;      // [batch, n_heads, seq]  log-sum-exp in log2 units
   const float* delta;     // [batch, n_heads, seq]  rowsum(dO o O)
   bf16* dqkv;             // [tokens, (Hq + 2 Hkv) * 128]
-  const bf16* qkv;        // raw views for the one-time Q / dO -> TMEM load of the dQ kernel
-  const bf16* dout;
-  int qkv_stride, dout_stride;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -346,14 +343,12 @@ constexpr int kBN = 64;              // keys per iteration
 constexpr int kQBytes = kBM * kD * 2;          // 32 KB
 constexpr int kKBytes = kBN * kD * 2;          // 16 KB
 constexpr int kDSBytes = kBM * kBN * 2;        // 16 KB
-// K_j/V_j ring (a stage is held until its dQ MMAs completed).  Q_i and dO_i do not live in shared
-// memory at all: they are the A operands of every S / dP MMA of the CTA, so they are parked in TMEM
-// (2 x 64 columns) once and read from there (tcgen05.mma TS form) -- an M=128,N=64 SS MMA would
-// re-read 4 KB of A per 2 KB of B and run into the 128 B/clk shared-memory limit.
-constexpr int kKVStages = 6;
+constexpr int kKVStages = 4;                   // K_j/V_j ring (a stage is held until its dQ MMAs completed)
 
 struct DqSmem {
-  static constexpr int k_off = 0;                                 // kKVStages stages
+  static constexpr int q_off = 0;
+  static constexpr int do_off = q_off + kQBytes;
+  static constexpr int k_off = do_off + kQBytes;                  // kKVStages stages
   static constexpr int v_off = k_off + kKVStages * kKBytes;       // kKVStages stages
   static constexpr int ds_off = v_off + kKVStages * kKBytes;
   static constexpr int bar_off = ds_off + kDSBytes;
@@ -369,17 +364,18 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base + DqSmem::q_off, do_smem = smem_base + DqSmem::do_off;
   const uint32_t k_smem = smem_base + DqSmem::k_off, v_smem = smem_base + DqSmem::v_off;
   const uint32_t ds_smem = smem_base + DqSmem::ds_off;
   const uint32_t bars = smem_base + DqSmem::bar_off;
   const uint32_t qdo_full = bars;
-  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };                  // 1..6
-  auto kv_empty = [&](int s) { return bars + 8u * (7 + s); };                 // 7..12
-  auto sdp_full = [&](int s) { return bars + 8u * (13 + s); };                // 13,14
-  auto sdp_free = [&](int s) { return bars + 8u * (15 + s); };                // 15,16
-  const uint32_t ds_full = bars + 8u * 17, ds_free = bars + 8u * 18, acc_full = bars + 8u * 19;
-  const uint32_t tmem_ptr_smem = bars + 8u * 20;
-  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + DqSmem::bar_off + 8 * 20);
+  auto kv_full = [&](int s) { return bars + 8u * (1 + s); };                  // 1..4
+  auto kv_empty = [&](int s) { return bars + 8u * (5 + s); };                 // 5..8
+  auto sdp_full = [&](int s) { return bars + 8u * (9 + s); };                 // 9,10
+  auto sdp_free = [&](int s) { return bars + 8u * (11 + s); };                // 11,12
+  const uint32_t ds_full = bars + 8u * 13, ds_free = bars + 8u * 14, acc_full = bars + 8u * 15;
+  const uint32_t tmem_ptr_smem = bars + 8u * 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + DqSmem::bar_off + 8 * 16);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q_tiles = p.seq / kBM;
@@ -395,7 +391,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tma_qkv128);
     tma_prefetch_desc(&tma_qkv64);
-    mbar_init(qdo_full, 4 * kWG);            // Q_i / dO_i written to TMEM by the softmax warps
+    tma_prefetch_desc(&tma_do128);
+    mbar_init(qdo_full, 1);
     for (int s = 0; s < kKVStages; ++s) { mbar_init(kv_full(s), 1); mbar_init(kv_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(sdp_full(s), 1); mbar_init(sdp_free(s), 4 * kWG); }
     mbar_init(ds_full, 4 * kWG); mbar_init(ds_free, 1); mbar_init(acc_full, 1);
@@ -408,11 +405,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
   const uint32_t tmem_base = *tmem_ptr_gen;
   auto tmem_s = [&](int buf) { return tmem_base + 64u * buf; };
   auto tmem_dp = [&](int buf) { return tmem_base + 128u + 64u * buf; };
-  const uint32_t tmem_dq = tmem_base + 256, tmem_q = tmem_base + 384, tmem_do = tmem_base + 448;
+  const uint32_t tmem_dq = tmem_base + 256;
 
   if (warp < 4) {
     if (warp == 0 && lane == 0) {
       // ====================== TMA producer ======================
+      mbar_arrive_expect_tx(qdo_full, 2 * kQBytes);
+      tma_load_2d(q_smem, &tma_qkv128, qdo_full, q_col, row0);
+      tma_load_2d(q_smem + kBM * 128, &tma_qkv128, qdo_full, q_col + 64, row0);
+      tma_load_2d(do_smem, &tma_do128, qdo_full, q_col, row0);
+      tma_load_2d(do_smem + kBM * 128, &tma_do128, qdo_full, q_col + 64, row0);
       for (int jj = 0; jj < n_tiles; ++jj) {
         const int st = jj % kKVStages;
         const int krow = b * p.seq + jj * kBN;
@@ -434,14 +436,16 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
         tc_fence_after();
         const uint32_t kb = k_smem + st * kKBytes, vb = v_smem + st * kKBytes;
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk) {              // A = Q_i from TMEM: 8 columns per 16-wide K step
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint64_t ad = umma_smem_desc(q_smem + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t bd = umma_smem_desc(kb + (kk >> 2) * (kBN * 128) + (kk & 3) * 32, 16, 1024);
-          umma_bf16_ts(tmem_s(tb), tmem_q + kk * 8, bd, idesc_s, kk != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_s(tb), ad, bd, idesc_s, kk != 0 ? 1u : 0u);
         }
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk) {              // A = dO_i from TMEM
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint64_t ad = umma_smem_desc(do_smem + (kk >> 2) * (kBM * 128) + (kk & 3) * 32, 16, 1024);
           const uint64_t bd = umma_smem_desc(vb + (kk >> 2) * (kBN * 128) + (kk & 3) * 32, 16, 1024);
-          umma_bf16_ts(tmem_dp(tb), tmem_do + kk * 8, bd, idesc_s, kk != 0 ? 1u : 0u);
+          umma_bf16_ss(tmem_dp(tb), ad, bd, idesc_s, kk != 0 ? 1u : 0u);
         }
         umma_commit(sdp_full(tb));
       };
@@ -474,23 +478,6 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tma_qkv128,     // qkv, b
     const int col0 = wg * kColsPerWG;
     const size_t vidx = ((size_t)b * p.n_heads + h) * p.seq + q_pos;
     const float lse_r = p.lse2[vidx], d_r = p.delta[vidx];
-    {  // park Q_i and dO_i in TMEM: this thread's row, this warpgroup's 32 of the 128 head-dim elements
-      const uint4* qs = reinterpret_cast<const uint4*>(p.qkv + (size_t)(row0 + r_local) * p.qkv_stride + q_col + wg * 32);
-      const uint4* ds = reinterpret_cast<const uint4*>(p.dout + (size_t)(row0 + r_local) * p.dout_stride + q_col + wg * 32);
-      uint32_t qv[16], dv[16];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 a = qs[i], c = ds[i];
-        qv[4 * i] = a.x; qv[4 * i + 1] = a.y; qv[4 * i + 2] = a.z; qv[4 * i + 3] = a.w;
-        dv[4 * i] = c.x; dv[4 * i + 1] = c.y; dv[4 * i + 2] = c.z; dv[4 * i + 3] = c.w;
-      }
-      tmem_st_32x16(tmem_q + lane_addr + wg * 16, qv);
-      tmem_st_32x16(tmem_do + lane_addr + wg * 16, dv);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(qdo_full);
-    }
     for (int jj = 0; jj < n_tiles; ++jj) {
       const int st = jj & 1;
       mbar_wait(sdp_full(st), (uint32_t)(jj >> 1) & 1u);
@@ -621,7 +608,6 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
   p.scale = scale;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.lse2 = lse2; p.delta = delta; p.dqkv = dqkv;
-  p.qkv = qkv; p.dout = dout; p.qkv_stride = qkv_stride; p.dout_stride = dout_stride;
   attn_bwd_dkv_kernel<<<(seq / kKV) * batch * n_kv, kThreads, kDkvSmemBytes, s>>>(t_qkv128, t_qkv64, t_do64, p);
   count_launch();
   attn_bwd_dq_kernel<<<(seq / kBM) * batch * n_heads, kThreads, kDqSmemBytes, s>>>(t_qkv128, t_qkv64, t_do128, p);
