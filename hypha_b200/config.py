@@ -220,6 +220,8 @@ class ElasticSection:
     enabled: bool = doc("keep the job running when a train worker's lease is lost (the reference scheduler "
                         "exits on the first failure)", True)
     min_workers: int = doc("stop the job when fewer train workers than this remain", 1)
+    replace: bool = doc("try to lease a replacement for a lost train worker and let it join the running job "
+                        "(parameter-server mode)", True)
 
 
 @dataclass

@@ -319,6 +319,18 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
         round_no = 1
         with session.receive(config["results"], "incoming") as receiver:
             updates = iter(receiver)
+            if config.get("join"):
+                # replacement worker: theta_0 is the seeded init every worker started from; the aggregate
+                # worker sends U = sum of all outer updates so far, so theta_prev = theta_0 + U is the
+                # current global model
+                event = next(updates)
+                latest = event[-1] if isinstance(event, list) else event
+                rel = (latest.get("parameters") or {}).get("path") if isinstance(latest.get("parameters"), dict) else latest.get("path")
+                cum = load_file(os.path.join(work_dir, rel))
+                if cum:
+                    loop.apply_update(cum)
+                round_no = int(config["join"].get("after_round", 0)) + 1
+                print(f"joined a running job after round {round_no - 1} ({len(cum)} tensors of cumulative update)", flush=True)
             while True:
                 loss_sum = torch.zeros((), device=device)
                 steps, counter = 0, -1

@@ -19,18 +19,19 @@ TRAIN_EXEC = {"class": "train", "name": "diloco-transformer", "runtime": "proces
 PS_EXEC = {"class": "aggregate", "name": "parameter-server", "runtime": "parameter-server"}
 
 
-def worker_config(gateway: str, work_dir: str, executors: List[dict], gpu: float = 4.0) -> C.WorkerConfig:
+def worker_config(gateway: str, work_dir: str, executors: List[dict], gpu: float = 4.0,
+                  price: float = 1.0) -> C.WorkerConfig:
     return C.builder(C.WorkerConfig).with_overrides({
         "listen_addresses": [], "gateway_addresses": [gateway], "exclude_cidr": [], "work_dir": work_dir,
         "resources": {"gpu": gpu, "cpu": 4.0, "memory": 8.0, "storage": 10.0},
-        "offer": {"price": 1.0, "floor": 0.5, "strategy": {"type": "whole"}}, "executors": executors}).build()
+        "offer": {"price": price, "floor": 0.5, "strategy": {"type": "whole"}}, "executors": executors}).build()
 
 
 async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[[str], None],
                            write_dataset: Callable[[str], None], job: Dict[str, Any], num_workers: int = 2,
                            timeout_s: float = 600.0, log: Optional[Callable[[str], None]] = None,
-                           omp_threads: int = 2, chaos: Optional[Callable[[Dict[str, Any], List[str]], Any]] = None
-                           ) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
+                           omp_threads: int = 2, chaos: Optional[Callable[[Dict[str, Any], List[str]], Any]] = None,
+                           spare_workers: int = 0) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
     """Returns ``(JobOutcome, metrics sink, executor logs, nodes)``.  ``chaos(nodes_by_peer_id, logs)`` is an
     optional coroutine run next to the job (fault injection: e.g. stop a worker node mid-run)."""
     registry = os.path.join(tmp, "registry")
@@ -51,7 +52,9 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
             log(m)
 
     collective = (job.get("aggregation") or {}).get("mode") == "collective"
-    names = [f"worker-{chr(ord('a') + i)}" for i in range(num_workers)] + ([] if collective else ["worker-ps"])
+    # spare workers ask a higher price, so the allocator only takes them when a cheaper one is gone
+    spares = [f"worker-{chr(ord('a') + num_workers + i)}" for i in range(spare_workers)]
+    names = [f"worker-{chr(ord('a') + i)}" for i in range(num_workers)] + spares + ([] if collective else ["worker-ps"])
     started = [loop.create_future() for _ in range(2 + len(names))]
     gw_cfg = C.builder(C.GatewayConfig).with_overrides({"listen_addresses": [gw_addr]}).build()
     bg = [asyncio.ensure_future(roles.run_gateway(gw_cfg, peer_id="gateway", started=started[0]))]
@@ -63,7 +66,8 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
         wd = os.path.join(tmp, name)
         os.makedirs(wd, exist_ok=True)
         ex = [PS_EXEC] if name == "worker-ps" else [TRAIN_EXEC]
-        bg.append(asyncio.ensure_future(roles.run_worker(worker_config(gw_addr, wd, ex), peer_id=name,
+        price = 1.5 if name in spares else 1.0
+        bg.append(asyncio.ensure_future(roles.run_worker(worker_config(gw_addr, wd, ex, price=price), peer_id=name,
                                                          started=started[2 + i], log=_log)))
     nodes = [await f for f in started[1:]]
     over = {"listen_addresses": [], "gateway_addresses": [gw_addr], "exclude_cidr": [], "scheduler": {"job": job}}

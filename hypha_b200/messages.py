@@ -358,6 +358,9 @@ class TrainExecutorConfig:
     # among themselves -- fused peer-memory outer step on GPUs, gloo all-reduce on CPU -- instead of
     # shipping files to a parameter server.  {"rank", "world", "rendezvous", "outer": Nesterov wire}
     collective: Optional[dict] = None
+    # B200 extension: a replacement worker dispatched into a running parameter-server job.  It first waits
+    # for the aggregate worker's cumulative update U (theta = theta_0(seed) + U), then trains normally.
+    join: Optional[dict] = None
 
     def to_wire(self) -> dict:
         d = {"model": self.model.to_wire(), "data": self.data.to_wire(), "updates": self.updates.to_wire(),
@@ -369,6 +372,8 @@ class TrainExecutorConfig:
             d["scheduler"] = self.scheduler.to_wire()
         if self.collective is not None:
             d["collective"] = dict(self.collective)
+        if self.join is not None:
+            d["join"] = dict(self.join)
         return d
 
     @classmethod
@@ -377,7 +382,8 @@ class TrainExecutorConfig:
                    Receive.from_wire(d["results"]), Adam.from_wire(d["optimizer"]), int(d["batch_size"]),
                    Preprocessor.from_wire(d["preprocessor"]) if d.get("preprocessor") else None,
                    LRScheduler.from_wire(d["scheduler"]) if d.get("scheduler") else None,
-                   dict(d["collective"]) if d.get("collective") else None)
+                   dict(d["collective"]) if d.get("collective") else None,
+                   dict(d["join"]) if d.get("join") else None)
 
 
 @dataclass

@@ -23,6 +23,7 @@ from . import config as C
 from . import messages as M
 from .scheduler import (AimConnector, BatchSchedulerService, Connector as MetricsConnector, DataSchedulerService,
                         GreedyWorkerAllocator, JsonlConnector, MetricsBridge, NoOpConnector, Task, WorkerHandle)
+from .scheduler.allocator import TaskError
 from .telemetry import Telemetry
 from .transport import Network, NetworkError, RecordNotFound
 from .worker import Arbiter, Connector, JobManager
@@ -193,6 +194,17 @@ async def run_worker(cfg: C.WorkerConfig, *, peer_id: Optional[str] = None,
 # ---------------------------------------------------------------------------------------------
 # scheduler
 # ---------------------------------------------------------------------------------------------
+class _TaskHandle:
+    """Lets a background asyncio task sit in the scheduler's `services` list (stopped on exit)."""
+
+    def __init__(self, task: "asyncio.Future"):
+        self.task = task
+
+    def stop(self) -> None:
+        if not self.task.done():
+            self.task.cancel()
+
+
 @dataclass
 class JobOutcome:
     job_id: str
@@ -202,6 +214,7 @@ class JobOutcome:
     metrics: List[Dict[str, Any]]
     finished: bool
     removed_workers: List[str] = field(default_factory=list)   # train workers dropped after a lost lease
+    joined_workers: List[str] = field(default_factory=list)    # replacements admitted into the running job
 
 
 def _free_tcp_port() -> int:
@@ -291,12 +304,16 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
                       job.inner_optimizer.epsilon)
         nesterov = M.Nesterov(job.outer_optimizer.learning_rate, job.outer_optimizer.momentum)
         rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{_free_tcp_port()}"
-        for i, w in enumerate(workers):
+
+        def train_config(w: WorkerHandle) -> M.TrainExecutorConfig:
             bs = worker_batch_size(w.resources.gpu, res.worker.gpu, job.rounds.max_batch_size)
             batch.add_worker(w.peer_id, bs)
-            tcfg = M.TrainExecutorConfig(model=model, data=M.Fetch.scheduler(net.peer_id, job.dataset.dataset),
+            return M.TrainExecutorConfig(model=model, data=M.Fetch.scheduler(net.peer_id, job.dataset.dataset),
                                          updates=M.Send.to_peers([ps.peer_id]), results=M.Receive.from_peers([ps.peer_id]),
                                          optimizer=adam, batch_size=bs, preprocessor=pre)
+
+        for i, w in enumerate(workers):
+            tcfg = train_config(w)
             if collective:
                 tcfg.collective = {"rank": i, "world": len(workers), "rendezvous": rendezvous,
                                    "outer": nesterov.to_wire()}
@@ -333,9 +350,48 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
                 waiters[h.task] = h
         live = list(worker_ids)
         removed: List[str] = []
+        joined: List[str] = []
         reason = "done"
+        wake = asyncio.Event()                      # set when a replacement's lease task must be watched too
+
+        async def replace_worker(lost: str) -> None:
+            """Lease one more train worker and let it join the running job (parameter-server mode): it
+            is dispatched with `join`, and the aggregate worker -- told the new membership -- sends it the
+            cumulative update at the next round boundary."""
+            try:
+                if batch.round + 2 > job.rounds.update_rounds:
+                    log.info("not replacing %s: fewer than two rounds left", lost)
+                    return
+                new = await allocator.request(wspec, res.worker_price.bid, res.worker_price.max, 1)
+                new = [h for h in new if h.peer_id not in live and h.peer_id != ps.peer_id]
+                if not new:
+                    log.warning("no replacement offered for %s", lost)
+                    return
+                h = new[0]
+                handles.append(h)
+                tcfg = train_config(h)
+                tcfg.join = {"after_round": batch.round, "replaces": lost}
+                tasks.append(await Task.try_new(net, M.JobSpec(job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg)), [h]))
+                live.append(h.peer_id)
+                joined.append(h.peer_id)
+                await net.request(ps.peer_id, M.API_PROTOCOL, M.ApiRequest.job_membership(job_id, live), timeout=5.0)
+                if h.task is not None:
+                    waiters[h.task] = h
+                    wake.set()
+                log.info("replacement %s joins job %s after round %d", h.peer_id, job_id[:8], batch.round)
+            except (NetworkError, TaskError, RoleError, asyncio.TimeoutError) as exc:
+                log.warning("could not replace %s: %s", lost, exc)
+
         while True:
-            done, _ = await asyncio.wait(waiters.keys(), return_when=asyncio.FIRST_COMPLETED)
+            wake_task = asyncio.ensure_future(wake.wait())
+            done, _ = await asyncio.wait(set(waiters.keys()) | {wake_task}, return_when=asyncio.FIRST_COMPLETED)
+            if wake_task in done:
+                wake.clear()
+                if len(done) == 1:
+                    continue
+                done = done - {wake_task}
+            else:
+                wake_task.cancel()
             first = next(iter(done))
             what = waiters.pop(first)
             if isinstance(what, str):
@@ -355,13 +411,15 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
                     await net.request(ps.peer_id, M.API_PROTOCOL, M.ApiRequest.job_membership(job_id, live), timeout=5.0)
                 except NetworkError as exc:
                     log.warning("could not tell the aggregate worker about the new membership: %s", exc)
+                if job.elastic.replace:
+                    services.append(_TaskHandle(asyncio.ensure_future(replace_worker(peer))))
         finished = batch.done.is_set()
         if not finished:
             log.warning("scheduler stopping before completion: %s", reason)
         await asyncio.sleep(0.05)              # let the last metrics drain
         bridge_task.cancel()
         return JobOutcome(job_id, batch.round, worker_ids, "collective" if collective else ps.peer_id, collected,
-                          finished, removed)
+                          finished, removed, joined)
     finally:
         for t in tasks:
             t.close()

@@ -36,6 +36,8 @@ class BatchSchedulerService:
         self.sched = self.core.BatchScheduler(tracker, time_cap_ms, update_cap)
         self.metrics: asyncio.Queue = asyncio.Queue(256)
         self.done = asyncio.Event()
+        self._seen: set = set()                # workers that reported at least once
+        self.never_started: List[str] = []     # late joiners dropped because the job ended before they trained
         self._lock = asyncio.Lock()
         self._reg = None
         self._kinds = {"status": self.core.ProgressKind.Status, "metrics": self.core.ProgressKind.Metrics,
@@ -61,8 +63,20 @@ class BatchSchedulerService:
                 if self.metrics.full():
                     self.metrics.get_nowait()
                 self.metrics.put_nowait((peer, progress))
+            if progress.kind in ("status", "update", "update-received"):
+                self._seen.add(peer)
             r = self.sched.handle(peer, self._kinds[progress.kind], progress.batch_size, _now_ms(self._t0))
-            if r.all_done:
+            all_done = r.all_done
+            if (not all_done and progress.kind == "update-received"
+                    and self._resp[r.kind] == "Done"):
+                # a replacement that was dispatched too late to be admitted before the last round never
+                # reports: it must not keep the finished job open
+                wt = self.sched.tracker.worker_tracker
+                for w in [w for w in wt.worker() if w not in self._seen]:
+                    wt.remove_worker(w)
+                    self.never_started.append(w)
+                all_done = all(st == self.core.WorkerState.Done for st in wt.states())
+            if all_done:
                 self.done.set()
             return M.ProgressResponse(self._resp[r.kind], r.counter)
 

@@ -37,6 +37,7 @@ from ..telemetry.bandwidth import BandwidthCounters
 MAX_FRAME = 64 << 20
 STREAM_CHUNK = 1 << 20
 STREAM_ACCEPT_LIMIT = 8          # stream_push.rs:56, stream_pull.rs:71
+EARLY_STREAM_TTL_S = 30.0        # how long a push stream waits for its receiver to register
 
 
 class NetworkError(Exception):
@@ -218,6 +219,7 @@ class Network:
         self._records: Dict[str, Tuple[bytes, str]] = {}
         self._providers: Dict[str, Set[str]] = {}
         self._stream_rx: Dict[Tuple[str, Optional[str]], asyncio.Queue] = {}
+        self._early_streams: Dict[Tuple[str, Optional[str]], List[Tuple[float, IncomingStream]]] = {}
         self._streams: Dict[str, IncomingStream] = {}
         self._pull_handlers: Dict[str, Callable[[str, Any], Awaitable[Any]]] = {}
         self._tasks: Set[asyncio.Task] = set()
@@ -687,6 +689,12 @@ class Network:
             raise AlreadyRegistered(f"push stream receiver already registered for job {job_id}")
         q: asyncio.Queue = asyncio.Queue(STREAM_ACCEPT_LIMIT)
         self._stream_rx[key] = q
+        # streams that arrived before the receiver existed (an executor that is still starting up while
+        # the aggregate worker already pushes its first file) were parked, not dropped
+        now = time.monotonic()
+        for t0, st in self._early_streams.pop(key, []):
+            if now - t0 <= EARLY_STREAM_TTL_S and not q.full():
+                q.put_nowait(st)
         return q
 
     def close_streams_push(self, job_id: Optional[str] = None) -> None:
@@ -705,7 +713,16 @@ class Network:
             st = IncomingStream(src, proto, frame.get("header"), frame.get("job"), asyncio.Queue(64))
             self._streams[sid] = st
             if q is None:
-                self._streams.pop(sid, None)     # nobody listens: drop silently
+                # nobody listens yet: park the stream for a receiver that registers shortly (bounded: a
+                # few streams per job, a short time-to-live, chunks back-pressure the sender's link)
+                key = (proto, frame.get("job"))
+                now = time.monotonic()
+                parked = [(t0, s) for t0, s in self._early_streams.get(key, []) if now - t0 <= EARLY_STREAM_TTL_S]
+                if frame.get("job") is None or len(parked) >= STREAM_ACCEPT_LIMIT:
+                    self._streams.pop(sid, None)             # no job to wait for / too many: drop
+                    return
+                parked.append((now, st))
+                self._early_streams[key] = parked
                 return
             await q.put(st)
         elif proto == "/hypha-tensor-stream/pull":

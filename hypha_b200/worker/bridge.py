@@ -143,11 +143,14 @@ class Connector:
         return total
 
     # -- receive ------------------------------------------------------------------------------------
-    async def receive(self, ref: M.Reference, job_id: Optional[str] = None) -> AsyncIterator[IncomingStream]:
-        """Incoming push streams from the allow-listed peers (connector/mod.rs:397-432)."""
+    async def receive(self, ref: M.Reference, job_id: Optional[str] = None,
+                      allowed: Optional[set] = None) -> AsyncIterator[IncomingStream]:
+        """Incoming push streams from the allow-listed peers (connector/mod.rs:397-432).  ``allowed`` may
+        be a live set the caller extends when the job's membership grows."""
         if ref.type != "peers":
             raise InvalidResource("receive needs a peers reference")
-        allowed = set(ref.peers)
+        if allowed is None:
+            allowed = set(ref.peers)
         q = self.network.streams_push(job_id)
         try:
             while True:

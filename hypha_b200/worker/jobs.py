@@ -179,12 +179,30 @@ class ParameterServerExecutor:
             from safetensors.torch import load_file, save_file
 
             workers = list(cfg.updates.get_peers())
+            allowed = set(workers)                 # live allow-list of the push-stream receiver
+            result_peers = list(cfg.results.peers)
+            pending_join: List[str] = []
+            cum_path = os.path.join(work_dir, "cumulative_update")     # U = sum of all outer updates so far
             momentum = None
             rnd = 0
-            incoming = self.connector.receive(cfg.updates, job_id=spec.job_id)
+            incoming = self.connector.receive(cfg.updates, job_id=spec.job_id, allowed=allowed)
             try:
                 nxt: Optional[asyncio.Future] = None
                 while True:
+                    # round boundary: admit replacement workers.  They start from theta_0(seed) + U, which
+                    # is exactly the theta_prev every other worker holds now.
+                    for w in pending_join:
+                        if os.path.exists(cum_path):
+                            await self.connector.send(M.Send.to_peers([w]), cum_path, job_id=spec.job_id)
+                        else:
+                            first = os.path.join(work_dir, "empty_update")
+                            save_file({}, first)
+                            await self.connector.send(M.Send.to_peers([w]), first, job_id=spec.job_id)
+                            os.unlink(first)
+                        workers.append(w)
+                        result_peers.append(w)
+                        self.log(f"[ps {spec.job_id[:8]}] round {rnd}: {w} joined (cumulative update sent)")
+                    pending_join.clear()
                     got: Dict[str, str] = {}
                     while len(got) < len(workers):
                         if nxt is None:
@@ -200,7 +218,12 @@ class ParameterServerExecutor:
                             gone = [w for w in workers if w not in ex.members]
                             if gone:
                                 self.log(f"[ps {spec.job_id[:8]}] round {rnd}: scheduler removed {gone}")
+                            for w in ex.members:           # newcomers are admitted at the next round boundary
+                                if w not in workers and w not in pending_join:
+                                    pending_join.append(w)
+                                    allowed.add(w)
                             workers = [w for w in workers if w in ex.members]
+                            result_peers = [w for w in result_peers if w in ex.members or w in pending_join]
                             for w in gone:
                                 p_gone = got.pop(w, None)
                                 if p_gone and os.path.exists(p_gone):
@@ -240,6 +263,8 @@ class ParameterServerExecutor:
                         new_m, upd = nesterov_step(avg, prev_momentum, cfg.optimizer.learning_rate,
                                                    cfg.optimizer.momentum)
                         save_file({k: v.contiguous() for k, v in upd.items()}, out)
+                        cum = load_file(cum_path) if os.path.exists(cum_path) else {}
+                        save_file({k: (cum[k] + v if k in cum else v).contiguous() for k, v in upd.items()}, cum_path)
                         save_file({k: v.contiguous() for k, v in new_m.items()}, os.path.join(work_dir, "momentum"))
                         return new_m
 
@@ -250,7 +275,7 @@ class ParameterServerExecutor:
                     # parameter_server.rs:232-282, and has this race).
                     resp = await self.network.request(scheduler, M.PROGRESS_PROTOCOL,
                                                       M.ProgressRequest(spec.job_id, M.Progress("updated")))
-                    send_ref = M.Send.to_peers([p for p in cfg.results.peers if p in got] or cfg.results.peers)
+                    send_ref = M.Send.to_peers([p for p in result_peers if p in got] or result_peers)
                     await self.connector.send(send_ref, out, job_id=spec.job_id)
                     for p in got.values():
                         os.unlink(p)

@@ -134,3 +134,47 @@ def test_scheduler_survives_a_lost_train_worker(tmp_path):
     for r in sink.records:
         last_round[r["worker_id"]] = max(last_round.get(r["worker_id"], 0), r["round"])
     assert last_round["worker-a"] == 3 and last_round["worker-b"] == 3
+
+
+def test_lost_worker_is_replaced_and_the_newcomer_joins(tmp_path):
+    """Rejoin through the control plane (quirk Q9, parameter-server mode): three train workers plus one
+    more expensive spare.  worker-c dies after round 1; the scheduler drops it, leases the spare,
+    dispatches a `join` train job and tells the aggregate worker the new membership; at the next round
+    boundary the aggregate worker sends the newcomer the cumulative update U, so it starts from
+    theta_0(seed) + U = the current global model, and takes part in the remaining rounds."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 48, "update_rounds": 10, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def kill_worker_c(nodes, logs):
+        while not any(" round 1:" in l or l.startswith("round 1:") for l in logs):
+            await asyncio.sleep(0.1)
+        nodes["worker-c"].stop.set()
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+        spare_workers=1, chaos=kill_worker_c, timeout_s=400,
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=12, samples_per_slice=16, seq_len=32,
+                                                             vocab_size=512)))
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 10
+    assert sorted(outcome.workers) == ["worker-a", "worker-b", "worker-c"]       # the initial allocation
+    assert outcome.removed_workers == ["worker-c"] and outcome.joined_workers == ["worker-d"]
+    assert any("worker-d joined (cumulative update sent)" in l for l in logs), logs[-30:]
+    assert any("joined a running job after round" in l for l in logs)
+    rounds = {}
+    for r in sink.records:
+        rounds.setdefault(r["worker_id"], set()).add(r["round"])
+    assert rounds["worker-a"] == set(range(1, 11)) and rounds["worker-b"] == set(range(1, 11))
+    assert len(rounds.get("worker-d", set())) >= 2                                  # it trained for real
+    assert sum("Finished training of" in l for l in logs) == 3                      # a, b and the newcomer

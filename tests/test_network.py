@@ -405,3 +405,27 @@ def test_nvls_descriptor_exchange_helpers(tmp_path):
     for r, w in pipes.values():
         os.close(r)
         os.close(w)
+
+
+def test_push_stream_waits_for_a_late_receiver():
+    """A push stream that arrives before the job's receiver registered is parked and delivered once the
+    receiver exists (a starting executor must not lose the aggregate worker's first file); streams
+    without a job id are still dropped when nobody listens."""
+    from hypha_b200.transport.network import Network
+
+    async def main():
+        a, b = Network("a"), Network("b")
+        addr = await b.listen("memory://late-rx")
+        await a.dial(addr)
+        await a.stream_push("b", b"payload-1", job_id="job-7")       # nobody listens for job-7 yet
+        await a.stream_push("b", b"orphan")                          # no job id: dropped
+        await asyncio.sleep(0.05)
+        q = b.streams_push("job-7")
+        st = await asyncio.wait_for(q.get(), 2.0)
+        data = b"".join([c async for c in st.chunks()])
+        assert st.peer == "a" and data == b"payload-1"
+        assert q.empty()
+        await a.close()
+        await b.close()
+
+    asyncio.run(main())
