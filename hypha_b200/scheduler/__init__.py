@@ -4,6 +4,8 @@ from .allocator import (AllocatorError, GreedyWorkerAllocator, LeaseExpired, NoO
 from .scheduling import (AimConnector, BatchSchedulerService, Connector, DataSchedulerService, JsonlConnector,
                          MemoryConnector, MetricsBridge, NoOpConnector)
 
-__all__ = ["AllocatorError", "GreedyWorkerAllocator", "LeaseExpired", "NoOffersReceived", "Offer", "Task",
+from .job import DiLoCoJobRun, JobError, JobOutcome, worker_batch_size
+
+__all__ = ["DiLoCoJobRun", "JobError", "JobOutcome", "worker_batch_size", "AllocatorError", "GreedyWorkerAllocator", "LeaseExpired", "NoOffersReceived", "Offer", "Task",
            "TaskError", "WorkerHandle", "AimConnector", "BatchSchedulerService", "Connector",
            "DataSchedulerService", "JsonlConnector", "MemoryConnector", "MetricsBridge", "NoOpConnector"]

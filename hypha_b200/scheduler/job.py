@@ -1,0 +1,279 @@
+"""One DiLoCo job from the scheduler's point of view: allocate -> dispatch -> watch -> tear down.
+
+Reference flow: crates/scheduler/src/bin/hypha-scheduler.rs:54-432.  What is added here: the
+`collective` aggregation mode (no aggregate worker; the train workers' executors run the outer step
+among themselves) and elasticity (a lost train worker is dropped, optionally replaced by a newcomer
+that joins the running job) -- the reference exits on the first lost lease.
+"""
+from __future__ import annotations
+
+import asyncio
+import socket
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
+
+from .. import messages as M
+from ..transport import Network, NetworkError
+from .allocator import GreedyWorkerAllocator, Task, TaskError, WorkerHandle
+from .scheduling import (AimConnector, BatchSchedulerService, Connector as MetricsConnector, DataSchedulerService,
+                         MetricsBridge, NoOpConnector)
+
+ALLOCATION_PAUSE_S = 1.0        # hypha-scheduler.rs:243
+
+
+class JobError(Exception):
+    pass
+
+
+@dataclass
+class JobOutcome:
+    job_id: str
+    rounds: int
+    workers: List[str]
+    parameter_server: str
+    metrics: List[Dict[str, Any]]
+    finished: bool
+    removed_workers: List[str] = field(default_factory=list)   # train workers dropped after a lost lease
+    joined_workers: List[str] = field(default_factory=list)    # replacements admitted into the running job
+
+
+def free_tcp_port() -> int:
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return int(sk.getsockname()[1])
+
+
+def worker_batch_size(offered_gpu: float, required_gpu: float, max_batch: Optional[int]) -> int:
+    """``floor(offered.gpu / required.gpu).min(max_batch_size)`` (hypha-scheduler.rs:320-322)."""
+    bs = int(offered_gpu // required_gpu) if required_gpu > 0 else 1
+    bs = max(1, bs)
+    return min(bs, max_batch) if max_batch else bs
+
+
+class _Tee(MetricsConnector):
+    """Keeps a copy of every metric for the JobOutcome while forwarding to the configured sink."""
+
+    def __init__(self, inner: MetricsConnector, collected: List[Dict[str, Any]]):
+        self.inner, self.collected = inner, collected
+
+    async def send(self, worker_id, round, name, value):
+        self.collected.append({"worker_id": worker_id, "round": round, "metric_name": name, "value": value})
+        await self.inner.send(worker_id, round, name, value)
+
+
+class DiLoCoJobRun:
+    """Owns the handles, services and tasks of one job; ``run()`` returns its :class:`JobOutcome`."""
+
+    def __init__(self, net: Network, job, *, telemetry, stop: asyncio.Event, data_provider,
+                 metrics_connector: Optional[MetricsConnector] = None, status_bridge: Optional[str] = None,
+                 allocation_pause_s: float = ALLOCATION_PAUSE_S):
+        self.net, self.job, self.res = net, job, job.resources
+        self.telemetry, self.log, self.stop = telemetry, telemetry.logger, stop
+        self.get_data_provider = data_provider
+        self.sink = metrics_connector or (AimConnector(status_bridge) if status_bridge else NoOpConnector())
+        self.allocation_pause_s = allocation_pause_s
+        self.collective = job.aggregation.mode == "collective"
+        self.allocator = GreedyWorkerAllocator(net)
+        self.job_id = M.new_id()
+        self.handles: List[WorkerHandle] = []
+        self.services: List[Any] = []
+        self.tasks: List[Task] = []
+        self.background: List[asyncio.Future] = []
+        self.workers: List[WorkerHandle] = []
+        self.ps: Optional[WorkerHandle] = None
+        self.batch: Optional[BatchSchedulerService] = None
+        self.data_svc: Optional[DataSchedulerService] = None
+        self.live: List[str] = []
+        self.removed: List[str] = []
+        self.joined: List[str] = []
+        self.collected: List[Dict[str, Any]] = []
+        to_res = lambda r: M.Resources(gpu=r.gpu, cpu=r.cpu, storage=r.storage, memory=r.memory)
+        self.wspec = M.WorkerSpec(to_res(self.res.worker), [M.ExecutorDescriptor("train", M.TRAIN_EXECUTOR_NAME)])
+        self.pspec = M.WorkerSpec(to_res(self.res.parameter_server),
+                                  [M.ExecutorDescriptor("aggregate", M.AGGREGATE_EXECUTOR_NAME)])
+
+    # -- allocate -------------------------------------------------------------------------------
+    async def allocate(self) -> None:
+        res = self.res
+        with self.telemetry.span("allocate.workers", num=res.num_workers):
+            self.workers = await self.allocator.request(self.wspec, res.worker_price.bid, res.worker_price.max,
+                                                        res.num_workers)
+        self.handles += self.workers
+        if self.collective:
+            # B200 path: no aggregate worker.  The train workers run the outer step among themselves
+            # (fused peer-memory kernel on GPUs / gloo on CPU) and report `updated` for the group.
+            if len(self.workers) < res.num_workers:
+                raise JobError(f"allocation incomplete: {len(self.workers)}/{res.num_workers} workers")
+            self.ps = self.workers[0]
+            return
+        await asyncio.sleep(self.allocation_pause_s)
+        with self.telemetry.span("allocate.parameter_server"):
+            ps_list = await self.allocator.request(self.pspec, res.parameter_server_price.bid,
+                                                   res.parameter_server_price.max, 1)
+        self.handles += ps_list
+        if len(self.workers) < res.num_workers or not ps_list:
+            raise JobError(f"allocation incomplete: {len(self.workers)}/{res.num_workers} workers, {len(ps_list)} PS")
+        self.ps = ps_list[0]
+
+    # -- dispatch -------------------------------------------------------------------------------
+    def _job_messages(self) -> None:
+        job = self.job
+        self.model = M.Model(job.model.type, M.Fetch.huggingface(job.model.repository, job.model.revision,
+                                                                 job.model.filenames, job.model.token),
+                             list(job.model.input_names))
+        self.pre = None
+        if job.preprocessor is not None:
+            p = job.preprocessor
+            self.pre = M.Preprocessor(p.type, M.Fetch.huggingface(p.repository, p.revision, p.filenames, p.token),
+                                      list(p.input_names))
+        self.adam = M.Adam(job.inner_optimizer.learning_rate,
+                           tuple(job.inner_optimizer.betas) if job.inner_optimizer.betas else None,
+                           job.inner_optimizer.epsilon)
+        self.nesterov = M.Nesterov(job.outer_optimizer.learning_rate, job.outer_optimizer.momentum)
+
+    def train_config(self, w: WorkerHandle) -> M.TrainExecutorConfig:
+        bs = worker_batch_size(w.resources.gpu, self.res.worker.gpu, self.job.rounds.max_batch_size)
+        self.batch.add_worker(w.peer_id, bs)
+        return M.TrainExecutorConfig(model=self.model, data=M.Fetch.scheduler(self.net.peer_id, self.job.dataset.dataset),
+                                     updates=M.Send.to_peers([self.ps.peer_id]),
+                                     results=M.Receive.from_peers([self.ps.peer_id]),
+                                     optimizer=self.adam, batch_size=bs, preprocessor=self.pre)
+
+    async def _dispatch_train(self, w: WorkerHandle, tcfg: M.TrainExecutorConfig) -> None:
+        spec = M.JobSpec(self.job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))
+        self.tasks.append(await Task.try_new(self.net, spec, [w]))
+
+    async def dispatch(self) -> None:
+        job = self.job
+        provider, record = await self.get_data_provider(self.net, job.dataset.dataset)
+        self.data_svc = DataSchedulerService(self.net, job.dataset.dataset, provider, record.num_slices)
+        self.data_svc.start()
+        self.services.append(self.data_svc)
+        self.batch = BatchSchedulerService(self.net, self.job_id, self.ps.peer_id,
+                                           job.rounds.avg_samples_between_updates, job.rounds.update_rounds)
+        self.batch.start()
+        self.services.append(self.batch)
+        self._job_messages()
+        self.live = [w.peer_id for w in self.workers]
+        rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{free_tcp_port()}"
+        for i, w in enumerate(self.workers):
+            tcfg = self.train_config(w)
+            if self.collective:
+                tcfg.collective = {"rank": i, "world": len(self.workers), "rendezvous": rendezvous,
+                                   "outer": self.nesterov.to_wire()}
+            await self._dispatch_train(w, tcfg)
+        if not self.collective:
+            acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(self.live), results=M.Send.to_peers(self.live),
+                                             optimizer=self.nesterov)
+            spec = M.JobSpec(self.job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg))
+            self.tasks.append(await Task.try_new(self.net, spec, [self.ps]))
+
+    # -- elasticity -----------------------------------------------------------------------------
+    async def _tell_aggregate_worker(self) -> None:
+        await self.net.request(self.ps.peer_id, M.API_PROTOCOL, M.ApiRequest.job_membership(self.job_id, self.live),
+                               timeout=5.0)
+
+    async def _drop_worker(self, peer: str) -> None:
+        self.live.remove(peer)
+        self.removed.append(peer)
+        self.log.warning("lost the lease of train worker %s: continuing with %d worker(s)", peer, len(self.live))
+        self.batch.remove_worker(peer)
+        self.data_svc.remove_worker(peer)
+        if self.collective:
+            return      # the survivors' fused outer step finds out by its barrier timeout (step_resilient)
+        try:
+            await self._tell_aggregate_worker()
+        except NetworkError as exc:
+            self.log.warning("could not tell the aggregate worker about the new membership: %s", exc)
+        if self.job.elastic.replace:
+            self.background.append(asyncio.ensure_future(self._replace_worker(peer)))
+
+    async def _replace_worker(self, lost: str) -> None:
+        """Lease one more train worker and let it join the running job (parameter-server mode): it is
+        dispatched with `join`, and the aggregate worker -- told the new membership -- sends it the
+        cumulative update at the next round boundary."""
+        try:
+            if self.batch.round + 2 > self.job.rounds.update_rounds:
+                self.log.info("not replacing %s: fewer than two rounds left", lost)
+                return
+            new = await self.allocator.request(self.wspec, self.res.worker_price.bid, self.res.worker_price.max, 1)
+            new = [h for h in new if h.peer_id not in self.live and h.peer_id != self.ps.peer_id]
+            if not new:
+                self.log.warning("no replacement offered for %s", lost)
+                return
+            h = new[0]
+            self.handles.append(h)
+            tcfg = self.train_config(h)
+            tcfg.join = {"after_round": self.batch.round, "replaces": lost}
+            await self._dispatch_train(h, tcfg)
+            self.live.append(h.peer_id)
+            self.joined.append(h.peer_id)
+            await self._tell_aggregate_worker()
+            if h.task is not None:
+                self._waiters[h.task] = h
+                self._wake.set()
+            self.log.info("replacement %s joins job %s after round %d", h.peer_id, self.job_id[:8], self.batch.round)
+        except (NetworkError, TaskError, JobError, asyncio.TimeoutError) as exc:
+            self.log.warning("could not replace %s: %s", lost, exc)
+
+    # -- watch ----------------------------------------------------------------------------------
+    async def watch(self) -> str:
+        """Wait for: job done | stop requested | lease lost.  The reference exits on the first lost lease
+        (hypha-scheduler.rs:396-412); with `elastic.enabled` a lost TRAIN worker is removed from the
+        batch/slice schedulers, the aggregate job is told the new membership, and the job goes on while
+        at least `elastic.min_workers` remain.  Returns the reason the wait ended."""
+        el = self.job.elastic
+        self._waiters: Dict[Any, Any] = {asyncio.ensure_future(self.batch.done.wait()): "done",
+                                         asyncio.ensure_future(self.stop.wait()): "stop"}
+        for h in self.handles:
+            if h.task is not None:
+                self._waiters[h.task] = h
+        self._wake = asyncio.Event()        # set when a replacement's lease task must be watched too
+        while True:
+            wake_task = asyncio.ensure_future(self._wake.wait())
+            done, _ = await asyncio.wait(set(self._waiters.keys()) | {wake_task}, return_when=asyncio.FIRST_COMPLETED)
+            if wake_task in done:
+                self._wake.clear()
+                done = done - {wake_task}
+                if not done:
+                    continue
+            else:
+                wake_task.cancel()
+            what = self._waiters.pop(next(iter(done)))
+            if isinstance(what, str):
+                return what
+            peer = what.peer_id
+            if not (el.enabled and peer in self.live and len(self.live) - 1 >= max(1, el.min_workers)):
+                return f"lease:{peer}"
+            await self._drop_worker(peer)
+
+    # -- run ------------------------------------------------------------------------------------
+    async def run(self) -> JobOutcome:
+        try:
+            await self.allocate()
+            await self.dispatch()
+            bridge = MetricsBridge(_Tee(self.sink, self.collected))
+            bridge.register_stream(self.batch.metrics)
+            bridge_task = asyncio.ensure_future(bridge.run())
+            self.background.append(bridge_task)
+            reason = await self.watch()
+            finished = self.batch.done.is_set()
+            if not finished:
+                self.log.warning("scheduler stopping before completion: %s", reason)
+            await asyncio.sleep(0.05)              # let the last metrics drain
+            return JobOutcome(self.job_id, self.batch.round, [w.peer_id for w in self.workers],
+                              "collective" if self.collective else self.ps.peer_id, self.collected, finished,
+                              self.removed, self.joined)
+        finally:
+            await self.close()
+
+    async def close(self) -> None:
+        for b in self.background:
+            if not b.done():
+                b.cancel()
+        for t in self.tasks:
+            t.close()
+        for s in self.services:
+            s.stop()
+        for h in self.handles:
+            await h.release()
