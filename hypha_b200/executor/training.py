@@ -291,8 +291,12 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
             break
     print(f"Finished training of {round_no - 1} DiLoCo update rounds", flush=True)
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        # no closing barrier: nothing touches peer memory after the last outer step, and a barrier would
+        # hang the survivors of a job that lost a rank
+        try:
+            dist.destroy_process_group()
+        except Exception:
+            pass
 
 
 def main(socket_path: str, work_dir: str, job_json: str) -> None:
