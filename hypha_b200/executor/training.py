@@ -19,9 +19,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import sys
 import time
-from typing import Any, Dict, Iterator, List, Optional
+from typing import Any, Dict, Iterator, Optional
 
 import torch
 

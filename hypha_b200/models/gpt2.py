@@ -9,7 +9,7 @@ from __future__ import annotations
 import json
 import math
 from dataclasses import asdict, dataclass
-from typing import Dict, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn

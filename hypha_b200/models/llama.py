@@ -19,7 +19,7 @@ architecture is local and weights are random-init or loaded from safetensors.
 from __future__ import annotations
 
 import math
-from dataclasses import asdict, dataclass, field
+from dataclasses import asdict, dataclass
 from typing import Dict, Iterator, List, Optional, Tuple
 
 import torch

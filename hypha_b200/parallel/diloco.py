@@ -20,7 +20,7 @@ Three interchangeable outer back-ends:
 from __future__ import annotations
 
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import Callable, Dict, List, Optional
 
 import torch

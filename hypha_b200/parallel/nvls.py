@@ -15,13 +15,12 @@ This is the B200-native replacement of the reference's parameter-server fan-in /
 """
 from __future__ import annotations
 
-import array
 import os
 import socket
 import tempfile
 import time
 from dataclasses import dataclass
-from typing import Callable, List, Optional
+from typing import List, Optional
 
 import torch
 

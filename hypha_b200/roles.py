@@ -13,11 +13,9 @@ from __future__ import annotations
 
 import asyncio
 import json
-import math
 import os
-import time
 from dataclasses import dataclass, field
-from typing import Any, Callable, Dict, List, Optional
+from typing import Any, Callable, List, Optional
 
 from . import config as C
 from . import messages as M

@@ -13,7 +13,6 @@ removes the reference's per-step ``loss.cpu()`` + HTTP status round trip
 from __future__ import annotations
 
 import os
-import time
 from dataclasses import dataclass
 from typing import Dict, Optional
 

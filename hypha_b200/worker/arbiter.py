@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import asyncio
 import time
-from typing import Any, Callable, List, Optional
+from typing import Any, Callable, List
 
 from .. import messages as M
 from ..ops.native import load_core

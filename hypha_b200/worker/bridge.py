@@ -17,7 +17,7 @@ import json
 import os
 import random
 import shutil
-from typing import Any, AsyncIterator, Dict, List, Optional, Tuple
+from typing import Any, AsyncIterator, Dict, Optional, Tuple
 from urllib.parse import urlparse
 
 from aiohttp import web
