@@ -251,20 +251,27 @@ class ParameterServerExecutor:
                     prev_momentum = momentum
 
                     def reduce_and_step():
-                        files = [load_file(p) for p in paths]
-                        avg = {}
-                        for k in files[0].keys():
-                            acc = files[0][k].float().clone()
-                            for f in files[1:]:
-                                acc += f[k].float()
-                            avg[k] = acc / len(files)
-                        del files
-                        new_m, upd = nesterov_step(avg, prev_momentum, cfg.optimizer.learning_rate,
-                                                   cfg.optimizer.momentum)
-                        save_file({k: v.contiguous() for k, v in upd.items()}, out)
+                        # one tensor of every worker in RAM at a time (the reference streams tensor pairs
+                        # the same way, parameter_server.rs:331-384): peak = update + momentum + N tensors
+                        from safetensors import safe_open
+
+                        handles = [safe_open(p, framework="pt") for p in paths]
                         cum = load_file(cum_path) if os.path.exists(cum_path) else {}
-                        save_file({k: (cum[k] + v if k in cum else v).contiguous() for k, v in upd.items()}, cum_path)
-                        save_file({k: v.contiguous() for k, v in new_m.items()}, os.path.join(work_dir, "momentum"))
+                        new_m, upd = {}, {}
+                        inv = 1.0 / len(handles)
+                        for k in handles[0].keys():
+                            acc = handles[0].get_tensor(k).float()
+                            for h in handles[1:]:
+                                acc += h.get_tensor(k).float()
+                            acc *= inv                                                   # true 1/N mean (Q1)
+                            m1, u1 = nesterov_step({k: acc}, None if prev_momentum is None else {k: prev_momentum[k]},
+                                                   cfg.optimizer.learning_rate, cfg.optimizer.momentum)
+                            new_m[k], upd[k] = m1[k].contiguous(), u1[k].contiguous()
+                            cum[k] = (cum[k] + upd[k]) if k in cum else upd[k].clone()
+                        del handles
+                        save_file(upd, out)
+                        save_file(new_m, os.path.join(work_dir, "momentum"))
+                        save_file({k: v.contiguous() for k, v in cum.items()}, cum_path)
                         return new_m
 
                     momentum = await asyncio.get_event_loop().run_in_executor(None, reduce_and_step)
