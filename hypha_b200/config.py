@@ -139,6 +139,8 @@ class WorkerConfig(NetworkMixin):
     gateway_addresses: List[str] = doc("gateways to dial at start-up", factory=list)
     relay_circuit: bool = doc("listen on a relay circuit through each gateway", True)
     work_dir: str = doc("base directory for per-job work dirs", "/tmp")
+    device: Optional[int] = doc("CUDA device index this worker's executors train on (exported to them as "
+                                "HYPHA_DEVICE; one worker per GPU on a multi-GPU box)", None)
     resources: ResourcesSection = doc("capacity offered to schedulers", factory=ResourcesSection)
     offer: OfferSection = doc("pricing", factory=OfferSection)
     executors: List[ExecutorSection] = doc("executors this worker can run", factory=_default_executors)

@@ -301,7 +301,13 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
 def main(socket_path: str, work_dir: str, job_json: str) -> None:
     from safetensors.torch import load_file, save_file
 
-    device = "cuda" if torch.cuda.is_available() else "cpu"
+    if torch.cuda.is_available() and os.environ.get("HYPHA_EXECUTOR_DEVICE", "cuda") != "cpu":
+        # one worker per GPU: the worker exports its `device` as HYPHA_DEVICE (config.WorkerConfig.device)
+        index = int(os.environ.get("HYPHA_DEVICE", "0")) % max(1, torch.cuda.device_count())
+        torch.cuda.set_device(index)
+        device = f"cuda:{index}"
+    else:
+        device = "cpu"
     with Session(socket_path) as session:
         job = json.loads(job_json)
         executor = job["executor"]

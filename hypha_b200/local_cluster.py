@@ -20,9 +20,10 @@ PS_EXEC = {"class": "aggregate", "name": "parameter-server", "runtime": "paramet
 
 
 def worker_config(gateway: str, work_dir: str, executors: List[dict], gpu: float = 4.0,
-                  price: float = 1.0) -> C.WorkerConfig:
+                  price: float = 1.0, device: Optional[int] = None) -> C.WorkerConfig:
     return C.builder(C.WorkerConfig).with_overrides({
         "listen_addresses": [], "gateway_addresses": [gateway], "exclude_cidr": [], "work_dir": work_dir,
+        "device": device,
         "resources": {"gpu": gpu, "cpu": 4.0, "memory": 8.0, "storage": 10.0},
         "offer": {"price": price, "floor": 0.5, "strategy": {"type": "whole"}}, "executors": executors}).build()
 
@@ -67,7 +68,9 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
         os.makedirs(wd, exist_ok=True)
         ex = [PS_EXEC] if name == "worker-ps" else [TRAIN_EXEC]
         price = 1.5 if name in spares else 1.0
-        bg.append(asyncio.ensure_future(roles.run_worker(worker_config(gw_addr, wd, ex, price=price), peer_id=name,
+        # train worker i drives GPU i (ignored on CPU; collective jobs pick the device from their rank)
+        dev = i if name != "worker-ps" else None
+        bg.append(asyncio.ensure_future(roles.run_worker(worker_config(gw_addr, wd, ex, price=price, device=dev), peer_id=name,
                                                          started=started[2 + i], log=_log)))
     nodes = [await f for f in started[1:]]
     over = {"listen_addresses": [], "gateway_addresses": [gw_addr], "exclude_cidr": [], "scheduler": {"job": job}}

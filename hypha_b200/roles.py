@@ -171,7 +171,8 @@ async def run_worker(cfg: C.WorkerConfig, *, peer_id: Optional[str] = None,
     node = await start_node("worker", cfg, peer_id=peer_id)
     net = node.network
     connector = Connector(net)
-    jobs = JobManager(connector, net, cfg.work_dir, cfg.executors, log=log)
+    exec_env = {"HYPHA_DEVICE": str(cfg.device)} if cfg.device is not None else {}
+    jobs = JobManager(connector, net, cfg.work_dir, cfg.executors, log=log, executor_env=exec_env)
     cap = M.Resources(gpu=cfg.resources.gpu, cpu=cfg.resources.cpu, storage=cfg.resources.storage,
                       memory=cfg.resources.memory)
     arbiter = Arbiter(net, cap, jobs, price=cfg.offer.price, floor=cfg.offer.floor,

@@ -336,9 +336,10 @@ class JobManager:
     """Picks the executor for a dispatched job and tracks running jobs by id / lease."""
 
     def __init__(self, connector: Connector, network: Network, work_dir: str, executor_configs: List[Any],
-                 log: Callable[[str], None] = print):
+                 log: Callable[[str], None] = print, executor_env: Optional[Dict[str, str]] = None):
         self.connector, self.network, self.work_dir, self.log = connector, network, work_dir, log
         self.executor_configs = executor_configs
+        self.executor_env = dict(executor_env or {})      # extra environment of process executors (HYPHA_DEVICE)
         self.jobs: Dict[str, Job] = {}
 
     def supported(self) -> List[M.ExecutorDescriptor]:
@@ -353,7 +354,8 @@ class JobManager:
     async def execute(self, task_id: str, spec: M.JobSpec, lease_id: str, scheduler: str) -> Job:
         ec = self._find(spec.executor.descriptor)
         if ec.runtime == "process":
-            runner = ProcessExecutor(self.connector, self.network, self.work_dir, ec.cmd, list(ec.args), log=self.log)
+            runner = ProcessExecutor(self.connector, self.network, self.work_dir, ec.cmd, list(ec.args),
+                                     env=self.executor_env, log=self.log)
         elif ec.runtime == "parameter-server":
             if spec.executor.descriptor.cls != "aggregate":
                 raise JobManagerError("parameter-server runtime only runs aggregate jobs")
