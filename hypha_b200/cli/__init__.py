@@ -34,6 +34,10 @@ def build_parser(role: str) -> argparse.ArgumentParser:
         i.add_argument("--job", default=None, help="job definition as JSON, merged into [scheduler.job]")
     if role == "data":
         i.add_argument("--dataset-path", default=None)
+    if role == "worker":
+        i.add_argument("--detect", action="store_true",
+                       help="fill [resources] from this machine (visible GPUs, cores, RAM, free disk)")
+        i.add_argument("--device", type=int, default=None, help="CUDA device index of this worker's executors")
     pr = sub.add_parser("probe", help="check a node's health endpoint")
     pr.add_argument("address")
     pr.add_argument("--timeout", type=float, default=5.0)
@@ -46,6 +50,7 @@ def build_parser(role: str) -> argparse.ArgumentParser:
     r.add_argument("--peer-id", default=None)
     if role == "worker":
         r.add_argument("--work-dir", default=None)
+        r.add_argument("--device", type=int, default=None, help="CUDA device index of this worker's executors")
     if role == "scheduler":
         r.add_argument("--status-bridge", default=None)
     if role == "data":
@@ -60,6 +65,32 @@ def cli_markdown(role: str) -> str:
     for name, sp in p._subparsers._group_actions[0].choices.items():  # type: ignore[union-attr]
         out += [f"## hypha-{role} {name}", "", "```", sp.format_help().rstrip(), "```", ""]
     return "\n".join(out)
+
+
+def detect_resources(work_dir: str = "/tmp", one_gpu: bool = False) -> Dict[str, float]:
+    """What `hypha-worker init --detect` writes into [resources]: GPUs visible to CUDA (1 when the
+    worker is pinned to one device), CPU cores, RAM in GB, free disk under ``work_dir`` in GB."""
+    import os
+    import shutil
+
+    gpus = 0
+    try:
+        import torch
+
+        gpus = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        gpus = 0
+    if one_gpu and gpus > 0:
+        gpus = 1
+    try:
+        import psutil
+
+        mem_gb = psutil.virtual_memory().total / 2 ** 30
+    except Exception:
+        mem_gb = os.sysconf("SC_PAGE_SIZE") * os.sysconf("SC_PHYS_PAGES") / 2 ** 30
+    disk_gb = shutil.disk_usage(work_dir if os.path.isdir(work_dir) else "/").free / 2 ** 30
+    return {"gpu": float(gpus), "cpu": float(os.cpu_count() or 1), "memory": float(int(mem_gb)),
+            "storage": float(int(disk_gb))}
 
 
 def _overrides(ns: argparse.Namespace, keys: List[str]) -> Dict[str, Any]:
@@ -77,6 +108,11 @@ def main(role: str, argv: Optional[List[str]] = None) -> int:
             over["scheduler"] = {"job": json.loads(ns.job)}
         if role == "data" and ns.dataset_path:
             over["dataset_path"] = ns.dataset_path
+        if role == "worker":
+            if ns.detect:
+                over["resources"] = detect_resources(one_gpu=ns.device is not None)
+            if ns.device is not None:
+                over["device"] = ns.device
         cfg = C.builder(cls).with_overrides(over).build()
         with open(ns.output, "w") as f:
             f.write(C.to_toml(cfg))
@@ -87,7 +123,7 @@ def main(role: str, argv: Optional[List[str]] = None) -> int:
         print("healthy" if ok else "unhealthy")
         return 0 if ok else 1
     keys = ["gateway_addresses", "listen_addresses", "external_addresses", "exclude_cidr", "work_dir",
-            "status_bridge", "dataset_path"]
+            "status_bridge", "dataset_path", "device"]
     try:
         cfg = C.validate(C.builder(cls).with_toml(ns.config).with_env().with_overrides(_overrides(ns, keys)).build())
     except C.ConfigError as exc:

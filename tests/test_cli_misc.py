@@ -108,3 +108,14 @@ def test_hypha_box_runs_a_collective_job_on_cpu(capsys):
     assert rc == 0 and out["finished"] and out["rounds"] == 2 and out["aggregation"] == "collective"
     assert sorted(out["metrics"]) == ["worker-a", "worker-b"]
     assert set(out["metrics"]["worker-a"]["2"]) == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms"}
+
+
+def test_worker_init_detects_resources_and_pins_a_device(tmp_path):
+    from hypha_b200 import cli
+    from hypha_b200 import config as C
+
+    out = tmp_path / "w.toml"
+    assert cli.main("worker", ["init", "--detect", "--device", "2", "-o", str(out)]) == 0
+    cfg = C.builder(C.WorkerConfig).with_toml(str(out)).build()
+    assert cfg.device == 2 and cfg.resources.cpu >= 1 and cfg.resources.memory >= 1
+    assert cfg.resources.gpu in (0.0, 1.0)            # pinned to one device (0 on a CPU-only host)
