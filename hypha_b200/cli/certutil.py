@@ -5,28 +5,32 @@ import sys
 from .. import certutil as cu
 
 
-def main(argv=None) -> int:
+def build_parser() -> argparse.ArgumentParser:
     p = argparse.ArgumentParser(prog="hypha-certutil", description="development PKI for hypha nodes")
     sub = p.add_subparsers(dest="command", required=True)
-    r = sub.add_parser("root")
+    r = sub.add_parser("root", help="self-signed Ed25519 root CA")
     r.add_argument("-o", "--organization", required=True)
     r.add_argument("--country", default="US")
     r.add_argument("-n", "--name", default=None)
     r.add_argument("-d", "--dir", default=".")
-    o = sub.add_parser("org")
+    o = sub.add_parser("org", help="organisation CA signed by the root")
     o.add_argument("--root-cert", required=True)
     o.add_argument("--root-key", required=True)
     o.add_argument("-o", "--organization", required=True)
     o.add_argument("--country", default="US")
     o.add_argument("-n", "--name", default=None)
     o.add_argument("-d", "--dir", default=".")
-    n = sub.add_parser("node")
+    n = sub.add_parser("node", help="node certificate (+ chain and trust file) signed by an organisation CA")
     n.add_argument("--ca-cert", required=True)
     n.add_argument("--ca-key", required=True)
     n.add_argument("-n", "--name", required=True)
     n.add_argument("-s", "--san", action="append", default=[])
     n.add_argument("-d", "--dir", default=".")
-    a = p.parse_args(argv)
+    return p
+
+
+def main(argv=None) -> int:
+    a = build_parser().parse_args(argv)
     if a.command == "root":
         print(*cu.make_root(a.organization, a.name, a.country, a.dir))
     elif a.command == "org":
