@@ -313,3 +313,27 @@ def test_flag_barrier_model_under_thread_sanitizer():
                        timeout=300, cwd=root)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "FAIL" not in r.stdout and "ThreadSanitizer" not in r.stderr
+
+
+def test_updated_is_idempotent_within_one_synchronisation():
+    """Collective jobs: every rank reports `updated`; only the first one after the workers' `update`
+    messages advances the round (the reference has a single aggregate worker and no such rule)."""
+    core = load_core()
+    tr = core.ProgressTracker("w0", 8, 2, 0)
+    for w in ("w0", "w1"):
+        tr.worker_tracker.add_worker(w, 4)
+    sched = core.BatchScheduler(tr, 10000, 3)
+    K, R = core.ProgressKind, core.ResponseKind
+    t = 0
+    for rnd in range(2):
+        for w in ("w0", "w1"):
+            t += 10
+            assert sched.handle(w, K.Update, 0, t).kind == R.Ok
+        want = R.Done if rnd == 1 else R.Ok
+        for w in ("w0", "w1"):                      # both ranks report `updated`
+            t += 1
+            assert sched.handle(w, K.Updated, 0, t).kind == want
+        assert sched.tracker.round() == rnd + 1     # advanced exactly once
+        acks = [sched.handle(w, K.UpdateReceived, 0, t + 5) for w in ("w0", "w1")]
+        assert all(a.kind == (R.Done if rnd == 1 else R.Continue) for a in acks)
+    assert acks[-1].all_done and sched.tracker.training_finished()
