@@ -60,8 +60,12 @@ def _send_fds(path: str, rank: int, fds: List[int]) -> None:
                 raise NvlsUnavailable(f"peer socket {path} never appeared")
             time.sleep(0.02)
     with s:
-        socket.send_fds(s, [rank.to_bytes(4, "little")], fds)
-        s.recv(1)           # ack: the receiver has dup'ed the descriptors
+        s.settimeout(60)    # a receiver that failed before accepting must not hang the sender
+        try:
+            socket.send_fds(s, [rank.to_bytes(4, "little")], fds)
+            s.recv(1)       # ack: the receiver has dup'ed the descriptors
+        except (socket.timeout, OSError) as exc:
+            raise NvlsUnavailable(f"peer at {path} did not take the memory handles: {exc}") from exc
 
 
 def _recv_fds(server: socket.socket, count: int, nfds: int):
@@ -110,6 +114,58 @@ def multicast_supported(device: int) -> bool:
         return err == cu.CUresult.CUDA_SUCCESS and bool(val)
     except Exception:
         return False
+
+
+def nvls_usable(device: int, world: int) -> bool:
+    """Rank-local pre-flight for the NVLS path, with NO inter-rank communication: the attribute says
+    multicast exists, and this process can actually create an exportable allocation and a multicast
+    object for ``world`` devices and add its own device to it.  Any failure (fabric manager not running,
+    multicast not permitted in this container, out of handles, ...) returns False, so that all ranks can
+    agree on plain CUDA-IPC buffers *before* anyone enters the collective set-up in ``alloc_nvls``."""
+    if not multicast_supported(device):
+        return False
+    cu = _cu()
+    handles = []
+    fds = []
+    try:
+        dev = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
+        H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        prop = cu.CUmemAllocationProp()
+        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = device
+        prop.requestedHandleTypes = H
+        mcprop = cu.CUmulticastObjectProp()
+        mcprop.numDevices = max(1, int(world))
+        mcprop.handleTypes = H
+        mcprop.flags = 0
+        mcprop.size = 1
+        gran = max(int(_ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
+                           "cuMulticastGetGranularity")),
+                   int(_ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
+                           "cuMemGetAllocationGranularity")))
+        mcprop.size = gran
+        h = _ck(cu.cuMemCreate(gran, prop, 0), "cuMemCreate")
+        handles.append(h)
+        fds.append(int(_ck(cu.cuMemExportToShareableHandle(h, H, 0), "cuMemExportToShareableHandle")))
+        mc = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
+        handles.append(mc)
+        fds.append(int(_ck(cu.cuMemExportToShareableHandle(mc, H, 0), "export multicast handle")))
+        _ck(cu.cuMulticastAddDevice(mc, dev), "cuMulticastAddDevice")
+        return True
+    except Exception:
+        return False
+    finally:
+        for fd in fds:
+            try:
+                os.close(fd)
+            except OSError:
+                pass
+        for h in reversed(handles):
+            try:
+                cu.cuMemRelease(h)
+            except Exception:
+                pass
 
 
 def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock_dir: Optional[str] = None) -> NvlsBuffer:

@@ -66,16 +66,19 @@ class DiLoCoTrainer:
         want_fused = group is not None and group.world > 1 and diloco.backend in ("auto", "fused")
         if want_fused:
             holders = {}
-            use_nvls = os.environ.get("HYPHA_NVLS", "1") == "1" and group.world >= 4
+            nvls_mode = os.environ.get("HYPHA_NVLS", "1")      # "0" off | "1" after a local pre-flight | "force"
+            use_nvls = nvls_mode != "0" and group.world >= 4
 
             def sym_alloc(name, n, dt):
                 """NVLS (multicast-bound VMM) buffer when the fabric supports it, else CUDA-IPC.  All
                 ranks take the same branch: the decision is agreed through the control plane."""
                 nonlocal use_nvls
                 if use_nvls:
-                    from .parallel.nvls import NvlsUnavailable, alloc_nvls, multicast_supported
+                    from .parallel.nvls import NvlsUnavailable, alloc_nvls, multicast_supported, nvls_usable
 
-                    ok = all(group._exchange(bool(multicast_supported(dev))))
+                    # every rank probes locally (no communication), then ONE aligned exchange decides
+                    mine = multicast_supported(dev) if nvls_mode == "force" else nvls_usable(dev, group.world)
+                    ok = all(group._exchange(bool(mine)))
                     if ok:
                         try:
                             return alloc_nvls(group, name, n, dt)
