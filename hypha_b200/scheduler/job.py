@@ -19,6 +19,8 @@ from .scheduling import (AimConnector, BatchSchedulerService, Connector as Metri
                          MetricsBridge, NoOpConnector)
 
 ALLOCATION_PAUSE_S = 1.0        # hypha-scheduler.rs:243
+REPLACE_ATTEMPTS = 4            # advertisements for a replacement worker before giving up
+REPLACE_RETRY_S = 3.0
 
 
 class JobError(Exception):
@@ -87,6 +89,7 @@ class DiLoCoJobRun:
         self.removed: List[str] = []
         self.joined: List[str] = []
         self.collected: List[Dict[str, Any]] = []
+        self._statuses: asyncio.Queue = asyncio.Queue(64)      # (peer, JobStatus value) from every task
         to_res = lambda r: M.Resources(gpu=r.gpu, cpu=r.cpu, storage=r.storage, memory=r.memory)
         self.wspec = M.WorkerSpec(to_res(self.res.worker), [M.ExecutorDescriptor("train", M.TRAIN_EXECUTOR_NAME)])
         self.pspec = M.WorkerSpec(to_res(self.res.parameter_server),
@@ -141,7 +144,18 @@ class DiLoCoJobRun:
 
     async def _dispatch_train(self, w: WorkerHandle, tcfg: M.TrainExecutorConfig) -> None:
         spec = M.JobSpec(self.job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))
-        self.tasks.append(await Task.try_new(self.net, spec, [w]))
+        self._watch_task(await Task.try_new(self.net, spec, [w]))
+
+    def _watch_task(self, task: Task) -> None:
+        """Forward the task's JobStatus reports (task.rs:27-121) into the watch loop."""
+        self.tasks.append(task)
+
+        async def pump():
+            while True:
+                peer, status = await task.statuses.get()
+                await self._statuses.put((peer, status))
+
+        self.background.append(asyncio.ensure_future(pump()))
 
     async def dispatch(self) -> None:
         job = self.job
@@ -166,17 +180,17 @@ class DiLoCoJobRun:
             acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(self.live), results=M.Send.to_peers(self.live),
                                              optimizer=self.nesterov)
             spec = M.JobSpec(self.job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg))
-            self.tasks.append(await Task.try_new(self.net, spec, [self.ps]))
+            self._watch_task(await Task.try_new(self.net, spec, [self.ps]))
 
     # -- elasticity -----------------------------------------------------------------------------
     async def _tell_aggregate_worker(self) -> None:
         await self.net.request(self.ps.peer_id, M.API_PROTOCOL, M.ApiRequest.job_membership(self.job_id, self.live),
                                timeout=5.0)
 
-    async def _drop_worker(self, peer: str) -> None:
+    async def _drop_worker(self, peer: str, why: str = "lost the lease of") -> None:
         self.live.remove(peer)
         self.removed.append(peer)
-        self.log.warning("lost the lease of train worker %s: continuing with %d worker(s)", peer, len(self.live))
+        self.log.warning("%s train worker %s: continuing with %d worker(s)", why, peer, len(self.live))
         self.batch.remove_worker(peer)
         self.data_svc.remove_worker(peer)
         if self.collective:
@@ -196,8 +210,23 @@ class DiLoCoJobRun:
             if self.batch.round + 2 > self.job.rounds.update_rounds:
                 self.log.info("not replacing %s: fewer than two rounds left", lost)
                 return
-            new = await self.allocator.request(self.wspec, self.res.worker_price.bid, self.res.worker_price.max, 1)
-            new = [h for h in new if h.peer_id not in self.live and h.peer_id != self.ps.peer_id]
+            new: List[WorkerHandle] = []
+            for attempt in range(REPLACE_ATTEMPTS):
+                # a worker whose executor crashed still holds its old lease until it expires (10 s), so
+                # the first advertisement may go unanswered
+                try:
+                    got = await self.allocator.request(self.wspec, self.res.worker_price.bid,
+                                                       self.res.worker_price.max, 1)
+                except Exception as exc:                      # NoOffersReceived and friends
+                    self.log.info("replacement attempt %d for %s: %s", attempt + 1, lost, exc)
+                    got = []
+                new = [h for h in got if h.peer_id not in self.live and h.peer_id != self.ps.peer_id]
+                for h in got:
+                    if h not in new:
+                        await h.release()
+                if new or self.batch.done.is_set() or self.batch.round + 2 > self.job.rounds.update_rounds:
+                    break
+                await asyncio.sleep(REPLACE_RETRY_S)
             if not new:
                 self.log.warning("no replacement offered for %s", lost)
                 return
@@ -229,21 +258,47 @@ class DiLoCoJobRun:
             if h.task is not None:
                 self._waiters[h.task] = h
         self._wake = asyncio.Event()        # set when a replacement's lease task must be watched too
+
+        def can_drop(peer: str) -> bool:
+            return el.enabled and peer in self.live and len(self.live) - 1 >= max(1, el.min_workers)
+
         while True:
             wake_task = asyncio.ensure_future(self._wake.wait())
-            done, _ = await asyncio.wait(set(self._waiters.keys()) | {wake_task}, return_when=asyncio.FIRST_COMPLETED)
+            status_task = asyncio.ensure_future(self._statuses.get())
+            done, _ = await asyncio.wait(set(self._waiters.keys()) | {wake_task, status_task},
+                                         return_when=asyncio.FIRST_COMPLETED)
             if wake_task in done:
                 self._wake.clear()
-                done = done - {wake_task}
-                if not done:
-                    continue
             else:
                 wake_task.cancel()
-            what = self._waiters.pop(next(iter(done)))
+            if status_task in done:
+                peer, status = status_task.result()
+                if status == M.JobStatus.FAILED.value and not self.batch.done.is_set():
+                    # the executor died although the worker (and its lease) is alive
+                    if not self.collective and peer == self.ps.peer_id:
+                        return f"aggregate-job-{status.lower()}"
+                    if peer in self.live:
+                        if not can_drop(peer):
+                            return f"job-{status.lower()}:{peer}"
+                        handle = next((h for h in self.handles if h.peer_id == peer), None)
+                        if handle is not None:
+                            if handle.task is not None:
+                                self._waiters.pop(handle.task, None)
+                            await handle.release()          # free the worker: it may offer again
+                            self.handles.remove(handle)
+                        await self._drop_worker(peer, why=f"job {status.lower()} on")
+            else:
+                status_task.cancel()
+            done = done - {wake_task, status_task}
+            if not done:
+                continue
+            what = self._waiters.pop(next(iter(done)), None)
+            if what is None:
+                continue
             if isinstance(what, str):
                 return what
             peer = what.peer_id
-            if not (el.enabled and peer in self.live and len(self.live) - 1 >= max(1, el.min_workers)):
+            if not can_drop(peer):
                 return f"lease:{peer}"
             await self._drop_worker(peer)
 

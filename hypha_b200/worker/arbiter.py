@@ -39,6 +39,22 @@ class Arbiter:
         self.log = log
         self._regs: List[Any] = []
         self.offers_sent = 0
+        job_manager.on_job_end = self._job_ended
+
+    def _job_ended(self, job, status) -> None:
+        """A FAILED job gives its lease back at once (the scheduler will stop renewing it anyway, but the
+        10 s expiry would keep this worker from offering for a replacement job in the meantime).  Finished
+        jobs keep the reference behaviour: the lease simply expires."""
+        if status != M.JobStatus.FAILED:
+            return
+        others = [j for j in self.jobs.find_jobs_by_lease(job.lease_id)
+                  if j.id != job.id and j.execution.status == M.JobStatus.RUNNING]
+        if not others:
+            try:
+                self.leases.remove(job.lease_id)
+                self.log(f"[arbiter] job {job.id[:8]} failed -> lease {job.lease_id[:8]} released")
+            except Exception:
+                pass
 
     # -- handlers ---------------------------------------------------------------------------------
     async def _on_renew(self, peer: str, msg) -> M.ApiResponse:

@@ -340,6 +340,7 @@ class JobManager:
         self.connector, self.network, self.work_dir, self.log = connector, network, work_dir, log
         self.executor_configs = executor_configs
         self.executor_env = dict(executor_env or {})      # extra environment of process executors (HYPHA_DEVICE)
+        self.on_job_end: Optional[Callable[[Job, M.JobStatus], None]] = None    # set by the arbiter
         self.jobs: Dict[str, Job] = {}
 
     def supported(self) -> List[M.ExecutorDescriptor]:
@@ -370,6 +371,11 @@ class JobManager:
 
     async def _report(self, job: Job) -> None:
         status = await job.execution.wait()
+        if self.on_job_end is not None:
+            try:
+                self.on_job_end(job, status)
+            except Exception as exc:
+                self.log(f"[jobs] on_job_end failed: {exc}")
         try:
             await self.network.request(job.scheduler, M.API_PROTOCOL, M.ApiRequest.job_status(job.id, status),
                                        timeout=5.0)

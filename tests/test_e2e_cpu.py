@@ -178,3 +178,42 @@ def test_lost_worker_is_replaced_and_the_newcomer_joins(tmp_path):
     assert rounds["worker-a"] == set(range(1, 11)) and rounds["worker-b"] == set(range(1, 11))
     assert len(rounds.get("worker-d", set())) >= 2                                  # it trained for real
     assert sum("Finished training of" in l for l in logs) == 3                      # a, b and the newcomer
+
+
+def test_crashed_executor_is_restarted_on_the_same_worker(tmp_path):
+    """The worker role stays up but its executor process is killed: the worker reports JobStatus Failed,
+    the scheduler drops the rank, frees the lease, and -- the worker being the cheapest offer again --
+    re-leases it and dispatches a `join` job, which resumes from the cumulative update."""
+    import signal
+
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 480, "update_rounds": 14, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def kill_executor_of_c(nodes, logs):
+        while not any(" round 1:" in l or l.startswith("round 1:") for l in logs):
+            await asyncio.sleep(0.1)
+        jobs = list(nodes["worker-c"].jobs.jobs.values())
+        assert jobs, "worker-c runs no job"
+        os.killpg(jobs[0].execution.pid, signal.SIGKILL)
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+        chaos=kill_executor_of_c, timeout_s=400,
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=12, samples_per_slice=64, seq_len=32,
+                                                             vocab_size=512)))
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 14 and outcome.removed_workers == ["worker-c"]
+    assert outcome.joined_workers == ["worker-c"], (outcome.joined_workers, logs[-30:])
+    assert any("joined a running job after round" in l for l in logs)
+    assert sum("Finished training of" in l for l in logs) == 3
