@@ -167,7 +167,7 @@ class ModelSource:
 
 @dataclass
 class PreprocessorSource:
-    repository: str = doc("preprocessor repository", "hypha-space/lenet")
+    repository: str = doc("preprocessor repository (empty = the job has no preprocessor)", "hypha-space/lenet")
     revision: Optional[str] = doc("revision", None)
     filenames: List[str] = doc("files to fetch", factory=lambda: ["preprocessor_config.json"])
     token: Optional[str] = doc("access token", None)
@@ -224,6 +224,8 @@ class ElasticSection:
     min_workers: int = doc("stop the job when fewer train workers than this remain", 1)
     replace: bool = doc("try to lease a replacement for a lost train worker and let it join the running job "
                         "(parameter-server mode)", True)
+    max_replacements: int = doc("stop replacing after this many replacements (a job whose executor always "
+                                "crashes must not be restarted forever)", 4)
 
 
 @dataclass
@@ -452,6 +454,12 @@ class ConfigBuilder:
     def build(self) -> T:
         cfg = from_dict(self.cls, self.data, meta=self.meta)
         cfg._meta = self.meta  # type: ignore[attr-defined]
+        # TOML has no null: an empty `repository` (or `enabled = false` style `type = "none"`) under
+        # [scheduler.job.preprocessor] means "this job has no preprocessor"
+        job = getattr(getattr(cfg, "scheduler", None), "job", None)
+        pre = getattr(job, "preprocessor", None)
+        if pre is not None and (not pre.repository or pre.type == "none"):
+            job.preprocessor = None
         return cfg
 
 

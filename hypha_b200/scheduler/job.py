@@ -90,6 +90,7 @@ class DiLoCoJobRun:
         self.joined: List[str] = []
         self.collected: List[Dict[str, Any]] = []
         self._statuses: asyncio.Queue = asyncio.Queue(64)      # (peer, JobStatus value) from every task
+        self._replacements = 0
         to_res = lambda r: M.Resources(gpu=r.gpu, cpu=r.cpu, storage=r.storage, memory=r.memory)
         self.wspec = M.WorkerSpec(to_res(self.res.worker), [M.ExecutorDescriptor("train", M.TRAIN_EXECUTOR_NAME)])
         self.pspec = M.WorkerSpec(to_res(self.res.parameter_server),
@@ -199,8 +200,11 @@ class DiLoCoJobRun:
             await self._tell_aggregate_worker()
         except NetworkError as exc:
             self.log.warning("could not tell the aggregate worker about the new membership: %s", exc)
-        if self.job.elastic.replace:
+        if self.job.elastic.replace and self._replacements < self.job.elastic.max_replacements:
+            self._replacements += 1
             self.background.append(asyncio.ensure_future(self._replace_worker(peer)))
+        elif self.job.elastic.replace:
+            self.log.warning("not replacing %s: %d replacements already made", peer, self._replacements)
 
     async def _replace_worker(self, lost: str) -> None:
         """Lease one more train worker and let it join the running job (parameter-server mode): it is
