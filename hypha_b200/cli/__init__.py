@@ -149,7 +149,8 @@ def main(role: str, argv: Optional[List[str]] = None) -> int:
             return 130
         if role == "scheduler":
             print(json.dumps({"job_id": out.job_id, "rounds": out.rounds, "finished": out.finished,
-                              "workers": out.workers, "parameter_server": out.parameter_server}))
+                              "workers": out.workers, "parameter_server": out.parameter_server,
+                              "removed_workers": out.removed_workers, "joined_workers": out.joined_workers}))
             return 0 if out.finished else 1
         return 0
 

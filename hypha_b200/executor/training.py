@@ -128,8 +128,9 @@ class ReplicatedNesterov:
         if loop.flat:
             net = loop.model.net
             g = loop.opt.master - loop.prev
-            dist.all_reduce(g)
-            g.div_(world)
+            if world > 1:
+                dist.all_reduce(g)
+                g.div_(world)
             m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
             self.m["flat"] = m
             loop.prev.add_(self.lr * (self.mu * m + g))
@@ -140,8 +141,9 @@ class ReplicatedNesterov:
             if not v.dtype.is_floating_point:
                 continue
             g = v.detach().float() - loop.prev[k].float()
-            dist.all_reduce(g)
-            g.div_(world)
+            if world > 1:
+                dist.all_reduce(g)
+                g.div_(world)
             m = g.clone() if first else self.m[k].mul_(self.mu).add_(g)
             self.m[k] = m
             v.copy_((loop.prev[k].float() + self.lr * (self.mu * m + g)).to(v.dtype))

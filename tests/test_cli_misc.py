@@ -119,3 +119,43 @@ def test_worker_init_detects_resources_and_pins_a_device(tmp_path):
     cfg = C.builder(C.WorkerConfig).with_toml(str(out)).build()
     assert cfg.device == 2 and cfg.resources.cpu >= 1 and cfg.resources.memory >= 1
     assert cfg.resources.gpu in (0.0, 1.0)            # pinned to one device (0 on a CPU-only host)
+
+
+def test_replicated_nesterov_matches_the_reference_vector():
+    """Single-rank collective engine (no process group): the outer step is the reference's Nesterov
+    (parameter_server.rs:452-524): lr=.1 mu=.7, g0=.5 -> u0=.085; g1=[.1..5] -> u1=[.0415 .. .1095]."""
+    import torch
+
+    from hypha_b200.executor.training import ReplicatedNesterov
+
+    class _Loop:
+        flat = False
+
+        def __init__(self):
+            self.model = torch.nn.Linear(5, 1, bias=False)
+            with torch.no_grad():
+                self.model.weight.zero_()
+            self.prev = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+
+    loop, outer = _Loop(), ReplicatedNesterov(0.1, 0.7)
+    with torch.no_grad():
+        loop.model.weight.add_(0.5)                       # pseudo-gradient g0 = 0.5
+    outer.step(loop, 1)
+    assert torch.allclose(loop.model.weight, torch.full((1, 5), 0.085), atol=1e-7)
+    with torch.no_grad():
+        loop.model.weight.add_(torch.tensor([[0.1, 0.2, 0.3, 0.4, 0.5]]))
+    outer.step(loop, 1)
+    want = 0.085 + torch.tensor([[0.0415, 0.0585, 0.0755, 0.0925, 0.1095]])
+    assert torch.allclose(loop.model.weight, want, atol=1e-6)
+    assert torch.equal(loop.prev["weight"], loop.model.weight)
+
+
+def test_hypha_box_single_worker_on_cpu(capsys):
+    import json
+
+    from hypha_b200.cli import box
+
+    rc = box.main(["run", "--model", "gpt2-tiny", "--workers", "1", "--device", "cpu", "--rounds", "2",
+                   "--samples-per-round", "16", "--batch-size", "4", "--seq-len", "32", "--timeout", "240"])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rc == 0 and out["finished"] and out["rounds"] == 2 and list(out["metrics"]) == ["worker-a"]
