@@ -57,17 +57,19 @@ def write_synthetic_token_slices(path: str, num_slices: int, samples_per_slice: 
 
 
 def write_synthetic_image_slices(path: str, num_slices: int, samples_per_slice: int, image_size: int = 28,
-                                 num_classes: int = 10, seed: int = 0) -> List[str]:
+                                 num_classes: int = 10, seed: int = 0, pixel_key: str = "pixel_values") -> List[str]:
+    """MNIST-shaped stand-in: one fixed random prototype per class + noise, so a classifier can learn it.
+    ``pixel_key="images"`` writes the raw key an image preprocessor consumes."""
     from safetensors.torch import save_file
 
     os.makedirs(path, exist_ok=True)
     g = torch.Generator().manual_seed(seed)
+    base = torch.randn(num_classes, image_size, image_size, generator=g)       # the same classes in every slice
     out = []
     for i in range(num_slices):
         labels = torch.randint(0, num_classes, (samples_per_slice,), generator=g)
-        base = torch.randn(num_classes, image_size, image_size, generator=g)
         px = base[labels] + 0.1 * torch.randn(samples_per_slice, image_size, image_size, generator=g)
         f = os.path.join(path, f"slice-{i:05d}.safetensors")
-        save_file({"pixel_values": px.contiguous(), "labels": labels}, f)
+        save_file({pixel_key: px.contiguous(), "labels": labels}, f)
         out.append(f)
     return out

@@ -217,3 +217,43 @@ def test_crashed_executor_is_restarted_on_the_same_worker(tmp_path):
     assert outcome.joined_workers == ["worker-c"], (outcome.joined_workers, logs[-30:])
     assert any("joined a running job after round" in l for l in logs)
     assert sum("Finished training of" in l for l in logs) == 3
+
+
+def test_default_style_lenet_job_with_image_preprocessor(tmp_path):
+    """The reference's default job shape (scheduler_config.rs:52-105): LeNet image classification with an
+    image preprocessor, parameter-server aggregation.  Slices carry raw `images`; the preprocessor turns
+    them into `pixel_values`.  The synthetic classes are learnable, so the loss must fall."""
+    from hypha_b200.executor.dataset import write_synthetic_image_slices
+    from hypha_b200.models.lenet import LeNetConfig
+
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/lenet", "filenames": ["config.json"], "type": "image-classification",
+                  "input_names": ["pixel_values", "labels"]},
+        "preprocessor": {"repository": "local/lenet", "filenames": ["preprocessor_config.json"], "type": "image",
+                         "input_names": ["images"]},
+        "dataset": {"dataset": "mnist-like"},
+        "rounds": {"avg_samples_between_updates": 256, "update_rounds": 4, "max_batch_size": 32},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 2, "worker": {"gpu": 0.125, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    def write_model(p):
+        LeNetConfig().to_json(p)
+        json.dump({"image_processor_type": "hypha-identity"}, open(os.path.join(os.path.dirname(p), "preprocessor_config.json"), "w"))
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/lenet", write_model_config=write_model, job=job, timeout_s=300,
+        write_dataset=lambda d: write_synthetic_image_slices(d, num_slices=8, samples_per_slice=128, pixel_key="images")))
+    assert outcome.finished, logs[-20:]
+    assert outcome.rounds == 4
+    loss = {}
+    for r in sink.records:
+        if r["metric_name"] == "loss":
+            loss.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
+    assert set(loss) == {"worker-a", "worker-b"}
+    for w, v in loss.items():
+        assert v[4] < v[1] * 0.8, (w, v)          # the model learns the synthetic classes
