@@ -192,7 +192,7 @@ def test_crashed_executor_is_restarted_on_the_same_worker(tmp_path):
                   "input_names": ["input_ids", "labels"]},
         "preprocessor": None,
         "dataset": {"dataset": "toyset"},
-        "rounds": {"avg_samples_between_updates": 480, "update_rounds": 14, "max_batch_size": 4},
+        "rounds": {"avg_samples_between_updates": 480, "update_rounds": 30, "max_batch_size": 4},
         "inner_optimizer": {"learning-rate": 3e-3},
         "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
         "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
@@ -213,7 +213,7 @@ def test_crashed_executor_is_restarted_on_the_same_worker(tmp_path):
         write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=12, samples_per_slice=64, seq_len=32,
                                                              vocab_size=512)))
     assert outcome.finished, logs[-30:]
-    assert outcome.rounds == 14 and outcome.removed_workers == ["worker-c"]
+    assert outcome.rounds == 30 and outcome.removed_workers == ["worker-c"]
     assert outcome.joined_workers == ["worker-c"], (outcome.joined_workers, logs[-30:])
     assert any("joined a running job after round" in l for l in logs)
     assert sum("Finished training of" in l for l in logs) == 3
