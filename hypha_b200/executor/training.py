@@ -105,6 +105,57 @@ class InnerLoop:
                     self.prev[k] = v.detach().clone()
 
 
+class StatusPipe:
+    """Per-batch `status{batch_size}` reports without stalling the training loop (the
+    reference does a synchronous HTTP -> RPC round trip after every batch).  The report for batch k travels
+    on a helper thread while batch k+1 computes; its answer is read one batch later.  A
+    `ScheduleUpdate{counter}` answer to batch k-1 means "counter more batches after k-1": batch k was the
+    first of them, so counter-1 remain -- the worker still runs exactly the number of batches the
+    scheduler projected.  ``HYPHA_SYNC_STATUS=1`` restores the blocking behaviour.
+
+    ``counter``: < 0 unknown, > 0 batches still to run, 0 synchronise now."""
+
+    def __init__(self, session: Session):
+        from concurrent.futures import ThreadPoolExecutor
+
+        self.session = session
+        self.sync = os.environ.get("HYPHA_SYNC_STATUS", "0") == "1"
+        self._pool = None if self.sync else ThreadPoolExecutor(max_workers=1, thread_name_prefix="status")
+        self._pending = None
+
+    @staticmethod
+    def _checked(resp: dict) -> dict:
+        if resp["type"] == "Error":
+            raise RuntimeError("scheduler rejected status")
+        return resp
+
+    def _harvest(self) -> Optional[dict]:
+        if self._pending is None:
+            return None
+        resp, self._pending = self._checked(self._pending.result()), None
+        return resp
+
+    def report(self, batch_size: int, counter: int) -> int:
+        """Report one finished batch; returns the updated countdown."""
+        msg = {"status": {"batch_size": batch_size}}
+        if self.sync:
+            resp = self._checked(self.session.send_status(msg))
+            return int(resp["counter"]) if resp["type"] == "ScheduleUpdate" else counter - 1
+        prev = self._harvest()
+        if counter > 0:
+            counter -= 1                                   # this batch counts against the known countdown
+        elif prev is not None and prev["type"] == "ScheduleUpdate":
+            counter = max(0, int(prev["counter"]) - 1)     # the batch just finished was the first of them
+        if counter == 0:
+            self._checked(self.session.send_status(msg))   # last batch: report it before `update`
+        else:
+            self._pending = self._pool.submit(self.session.send_status, msg)
+        return counter
+
+    def drain(self) -> None:
+        self._harvest()
+
+
 # ---------------------------------------------------------------------------------------------
 # collective mode: the train workers are the ranks of one process group and run the outer step
 # among themselves -- no aggregate worker, no files (TrainExecutorConfig.collective)
@@ -249,6 +300,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         if use_cuda:
             torch.cuda.synchronize()
 
+    status = StatusPipe(session)
+
     while True:
         loss_sum = torch.zeros((), device=device)
         steps, counter, tokens = 0, -1, 0
@@ -261,13 +314,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
             first = next(iter(batch.values()))
             bs = int(first.shape[0])
             tokens += int(first.numel()) if first.dim() == 2 and not first.dtype.is_floating_point else bs
-            resp = session.send_status({"status": {"batch_size": bs}})
-            if resp["type"] == "ScheduleUpdate":
-                counter = resp["counter"]
-            elif resp["type"] == "Error":
-                raise RuntimeError("scheduler rejected status")
-            else:
-                counter -= 1
+            counter = status.report(bs, counter)
+        status.drain()
         sync()
         inner_s = time.perf_counter() - t_round
         session.send_status("update")
@@ -328,6 +376,7 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
             batch_size=config["batch_size"])
         batches = forever(loader)
         round_no = 1
+        status = StatusPipe(session)
         with session.receive(config["results"], "incoming") as receiver:
             updates = iter(receiver)
             if config.get("join"):
@@ -350,13 +399,8 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
                     loss_sum += loop.step(batch)
                     steps += 1
                     bs = int(next(iter(batch.values())).shape[0])
-                    resp = session.send_status({"status": {"batch_size": bs}})
-                    if resp["type"] == "ScheduleUpdate":
-                        counter = resp["counter"]
-                    elif resp["type"] == "Error":
-                        raise RuntimeError("scheduler rejected status")
-                    else:
-                        counter -= 1
+                    counter = status.report(bs, counter)
+                status.drain()
                 session.send_status("update")
                 name = f"{round_no}_local_gradients.safetensors"
                 save_file(loop.delta_state_dict(), os.path.join(work_dir, name))

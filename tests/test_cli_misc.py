@@ -159,3 +159,39 @@ def test_hypha_box_single_worker_on_cpu(capsys):
                    "--samples-per-round", "16", "--batch-size", "4", "--seq-len", "32", "--timeout", "240"])
     out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert rc == 0 and out["finished"] and out["rounds"] == 2 and list(out["metrics"]) == ["worker-a"]
+
+
+def test_status_pipe_runs_exactly_the_projected_number_of_batches(monkeypatch):
+    """Asynchronous status reports (quirk Q10): the answer to batch k-1 is read after batch k, and a
+    `ScheduleUpdate{counter}` is corrected for that batch, so async and sync modes stop at the same batch."""
+    from hypha_b200.executor.training import StatusPipe
+
+    class FakeSession:
+        def __init__(self, schedule_at, counter):
+            self.n, self.schedule_at, self.counter, self.sent = 0, schedule_at, counter, []
+
+        def send_status(self, msg):
+            self.n += 1
+            self.sent.append(msg)
+            if self.n == self.schedule_at:
+                return {"type": "ScheduleUpdate", "counter": self.counter}
+            return {"type": "Continue", "counter": 0}
+
+    def run(sync, schedule_at, c):
+        monkeypatch.setenv("HYPHA_SYNC_STATUS", "1" if sync else "0")
+        sess = FakeSession(schedule_at, c)
+        pipe, counter, batches = StatusPipe(sess), -1, 0
+        while counter != 0:
+            batches += 1
+            counter = pipe.report(4, counter)
+            assert batches < 100
+        pipe.drain()
+        return batches, sess.n
+
+    for schedule_at, c in ((1, 3), (2, 1), (3, 5), (4, 2)):
+        sync_batches, sync_reports = run(True, schedule_at, c)
+        async_batches, async_reports = run(False, schedule_at, c)
+        assert sync_batches == schedule_at + c
+        assert async_batches == sync_batches and async_reports == async_batches      # one report per batch
+    # counter 0 answered one batch late: a single batch of overshoot, never a hang
+    assert run(True, 2, 0)[0] == 2 and run(False, 2, 0)[0] == 3
