@@ -280,9 +280,13 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         torch.cuda.set_device(dev_index)
     device = f"cuda:{dev_index}" if use_cuda else "cpu"
     if world > 1:
+        from datetime import timedelta
+
         kw = {"device_id": torch.device(device)} if use_cuda else {}
+        # a rank that dies must not leave the others blocked in a collective for the default 30 minutes
+        timeout_s = float(os.environ.get("HYPHA_COLLECTIVE_TIMEOUT_S", "300"))
         dist.init_process_group("nccl" if use_cuda else "gloo", init_method=coll["rendezvous"], rank=rank,
-                                world_size=world, **kw)
+                                world_size=world, timeout=timedelta(seconds=timeout_s), **kw)
     prepare_files(config, session)
     local = os.path.join(work_dir, FETCH_PATH)
     family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
