@@ -218,6 +218,14 @@ class JobResources:
 
 
 @dataclass
+class CheckpointSection:
+    dir: Optional[str] = doc("directory (on the aggregate worker) where the job's outer state is saved: momentum "
+                             "and the cumulative update U, from which any worker rebuilds theta = theta_0(seed) + U", None)
+    every: int = doc("save after every N-th round", 1)
+    resume: bool = doc("start from the newest checkpoint in `dir` instead of round 0", False)
+
+
+@dataclass
 class ElasticSection:
     enabled: bool = doc("keep the job running when a train worker's lease is lost (the reference scheduler "
                         "exits on the first failure)", True)
@@ -249,6 +257,7 @@ class DiLoCoJob:
     resources: JobResources = doc("allocation request", factory=JobResources)
     aggregation: AggregationSection = doc("how the outer step is carried out", factory=AggregationSection)
     elastic: ElasticSection = doc("behaviour on worker failure", factory=ElasticSection)
+    checkpoint: CheckpointSection = doc("job-level checkpoint / resume (parameter-server mode)", factory=CheckpointSection)
 
 
 @dataclass

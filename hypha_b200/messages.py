@@ -391,14 +391,20 @@ class AggregateExecutorConfig:
     updates: Receive
     results: Send
     optimizer: Nesterov
+    # B200 extension (the reference has no checkpointing): {"dir", "every", "resume_round"?}
+    checkpoint: Optional[dict] = None
 
     def to_wire(self) -> dict:
-        return {"updates": self.updates.to_wire(), "results": self.results.to_wire(),
-                "optimizer": self.optimizer.to_wire()}
+        d = {"updates": self.updates.to_wire(), "results": self.results.to_wire(),
+             "optimizer": self.optimizer.to_wire()}
+        if self.checkpoint is not None:
+            d["checkpoint"] = dict(self.checkpoint)
+        return d
 
     @classmethod
     def from_wire(cls, d: dict) -> "AggregateExecutorConfig":
-        return cls(Receive.from_wire(d["updates"]), Send.from_wire(d["results"]), Nesterov.from_wire(d["optimizer"]))
+        return cls(Receive.from_wire(d["updates"]), Send.from_wire(d["results"]), Nesterov.from_wire(d["optimizer"]),
+                   dict(d["checkpoint"]) if d.get("checkpoint") else None)
 
 
 @dataclass(frozen=True)

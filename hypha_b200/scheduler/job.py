@@ -170,16 +170,34 @@ class DiLoCoJobRun:
         self.services.append(self.batch)
         self._job_messages()
         self.live = [w.peer_id for w in self.workers]
+        ck = job.checkpoint
+        resume_round = 0
+        if ck.dir and ck.resume and not self.collective:
+            from ..worker.jobs import latest_checkpoint
+
+            found = latest_checkpoint(ck.dir)
+            if found is not None:
+                resume_round = min(found["round"], job.rounds.update_rounds)
+                self.batch.start_at_round(resume_round)
+                self.log.info("resuming job from the checkpoint of round %d in %s", resume_round, ck.dir)
+            else:
+                self.log.warning("checkpoint.resume is set but %s holds no checkpoint: starting at round 0", ck.dir)
         rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{free_tcp_port()}"
         for i, w in enumerate(self.workers):
             tcfg = self.train_config(w)
             if self.collective:
                 tcfg.collective = {"rank": i, "world": len(self.workers), "rendezvous": rendezvous,
                                    "outer": self.nesterov.to_wire()}
+            elif resume_round:
+                tcfg.join = {"after_round": resume_round, "resume": True}      # theta = theta_0(seed) + U
             await self._dispatch_train(w, tcfg)
         if not self.collective:
             acfg = M.AggregateExecutorConfig(updates=M.Receive.from_peers(self.live), results=M.Send.to_peers(self.live),
                                              optimizer=self.nesterov)
+            if ck.dir:
+                acfg.checkpoint = {"dir": ck.dir, "every": ck.every}
+                if resume_round:
+                    acfg.checkpoint["resume_round"] = resume_round
             spec = M.JobSpec(self.job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg))
             self._watch_task(await Task.try_new(self.net, spec, [self.ps]))
 

@@ -47,6 +47,11 @@ class BatchSchedulerService:
                       self.core.ResponseKind.ScheduleUpdate: "ScheduleUpdate", self.core.ResponseKind.Done: "Done",
                       self.core.ResponseKind.Error: "Error"}
 
+    def start_at_round(self, completed_rounds: int) -> None:
+        """Resume: account for rounds that a previous run of the job already completed."""
+        for _ in range(max(0, completed_rounds)):
+            self.sched.tracker.next_round(_now_ms(self._t0))
+
     def add_worker(self, peer: str, batch_size: int) -> None:
         self.sched.tracker.worker_tracker.add_worker(peer, batch_size)
 

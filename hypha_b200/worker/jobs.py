@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import asyncio
 import hashlib
+import json
 import os
 import shutil
 import signal
@@ -160,6 +161,38 @@ def nesterov_step(avg: Dict[str, Any], momentum: Optional[Dict[str, Any]], lr: f
     return new_m, upd
 
 
+def latest_checkpoint(ckpt_dir: str) -> Optional[dict]:
+    """``{"round": r, "path": <dir>/round-r}`` of the newest complete job checkpoint, or None."""
+    try:
+        meta = json.load(open(os.path.join(ckpt_dir, "latest.json")))
+        path = os.path.join(ckpt_dir, f"round-{int(meta['round'])}")
+        if os.path.isfile(os.path.join(path, "cumulative_update")) and os.path.isfile(os.path.join(path, "momentum")):
+            return {"round": int(meta["round"]), "path": path}
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
+
+
+def save_job_checkpoint(ckpt_dir: str, round_no: int, cum_path: str, momentum_path: str, keep: int = 2) -> str:
+    """Copy the aggregate job's outer state (cumulative update U + momentum) to ``<dir>/round-<n>`` and flip
+    ``latest.json`` atomically; older checkpoints beyond ``keep`` are removed."""
+    dst = os.path.join(ckpt_dir, f"round-{round_no}")
+    tmp = dst + ".tmp"
+    shutil.rmtree(tmp, ignore_errors=True)
+    os.makedirs(tmp, exist_ok=True)
+    shutil.copyfile(cum_path, os.path.join(tmp, "cumulative_update"))
+    shutil.copyfile(momentum_path, os.path.join(tmp, "momentum"))
+    shutil.rmtree(dst, ignore_errors=True)
+    os.replace(tmp, dst)
+    meta_tmp = os.path.join(ckpt_dir, "latest.json.tmp")
+    json.dump({"round": round_no}, open(meta_tmp, "w"))
+    os.replace(meta_tmp, os.path.join(ckpt_dir, "latest.json"))
+    rounds = sorted(int(d.split("-")[1]) for d in os.listdir(ckpt_dir) if d.startswith("round-") and d.split("-")[1].isdigit())
+    for r in rounds[:-keep]:
+        shutil.rmtree(os.path.join(ckpt_dir, f"round-{r}"), ignore_errors=True)
+    return dst
+
+
 class ParameterServerExecutor:
     def __init__(self, connector: Connector, network: Network, work_dir_base: str,
                  receive_timeout_s: float = 600.0, log: Callable[[str], None] = print):
@@ -184,6 +217,19 @@ class ParameterServerExecutor:
             cum_path = os.path.join(work_dir, "cumulative_update")     # U = sum of all outer updates so far
             momentum = None
             rnd = 0
+            ckpt = cfg.checkpoint or {}
+            ckpt_dir, ckpt_every = ckpt.get("dir"), max(1, int(ckpt.get("every", 1)))
+            if ckpt_dir and ckpt.get("resume_round"):
+                # resume: outer state from the checkpoint; every worker is (re)admitted like a newcomer and
+                # receives U at this first round boundary
+                found = latest_checkpoint(ckpt_dir)
+                if found is None or found["round"] != int(ckpt["resume_round"]):
+                    raise RuntimeError(f"checkpoint of round {ckpt['resume_round']} not found in {ckpt_dir}")
+                shutil.copyfile(os.path.join(found["path"], "cumulative_update"), cum_path)
+                momentum = load_file(os.path.join(found["path"], "momentum"))
+                rnd = found["round"]
+                pending_join, workers, result_peers = list(workers), [], []
+                self.log(f"[ps {spec.job_id[:8]}] resumed from round {rnd} ({ckpt_dir})")
             incoming = self.connector.receive(cfg.updates, job_id=spec.job_id, allowed=allowed)
             try:
                 nxt: Optional[asyncio.Future] = None
@@ -287,6 +333,10 @@ class ParameterServerExecutor:
                         os.unlink(p)
                     os.unlink(out)
                     rnd += 1
+                    if ckpt_dir and rnd % ckpt_every == 0:
+                        os.makedirs(ckpt_dir, exist_ok=True)
+                        await asyncio.get_event_loop().run_in_executor(
+                            None, save_job_checkpoint, ckpt_dir, rnd, cum_path, os.path.join(work_dir, "momentum"))
                     if M.ProgressResponse.from_wire(resp).type == "Done":
                         ex.status = M.JobStatus.FINISHED
                         return

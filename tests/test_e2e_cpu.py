@@ -8,6 +8,7 @@ import os
 import sys
 
 import pytest
+import torch
 
 from hypha_b200 import config as C
 from hypha_b200 import roles
@@ -257,3 +258,54 @@ def test_default_style_lenet_job_with_image_preprocessor(tmp_path):
     assert set(loss) == {"worker-a", "worker-b"}
     for w, v in loss.items():
         assert v[4] < v[1] * 0.8, (w, v)          # the model learns the synthetic classes
+
+
+def test_job_checkpoint_and_resume(tmp_path):
+    """Job-level checkpoint/resume (absent in the reference).  Run A trains 3 rounds and the
+    aggregate worker saves momentum + the cumulative update U after every round.  Run B -- a new scheduler,
+    new workers, same checkpoint directory, `resume = true` -- starts at round 3: the aggregate job loads
+    the outer state, every worker is admitted like a newcomer (theta = theta_0(seed) + U) and three more
+    rounds complete the six."""
+    from safetensors.torch import load_file
+
+    ckpt = str(tmp_path / "ckpt")
+
+    def job(rounds, resume):
+        return {
+            "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                      "input_names": ["input_ids", "labels"]},
+            "preprocessor": None,
+            "dataset": {"dataset": "toyset"},
+            "rounds": {"avg_samples_between_updates": 40, "update_rounds": rounds, "max_batch_size": 4},
+            "inner_optimizer": {"learning-rate": 3e-3},
+            "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+            "checkpoint": {"dir": ckpt, "every": 1, "resume": resume},
+            "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+        }
+
+    def run(sub, j):
+        d = str(tmp_path / sub)
+        os.makedirs(d)
+        return asyncio.run(run_loopback_job(
+            d, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=j, timeout_s=240,
+            write_dataset=lambda p: write_synthetic_token_slices(p, num_slices=6, samples_per_slice=16, seq_len=32,
+                                                                 vocab_size=512)))
+
+    a, _, logs_a, _ = run("a", job(3, False))
+    assert a.finished and a.rounds == 3
+    assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 3}
+    assert sorted(os.listdir(ckpt)) == ["latest.json", "round-2", "round-3"]           # the two newest are kept
+    u3 = load_file(os.path.join(ckpt, "round-3", "cumulative_update"))
+    assert u3 and all(torch.isfinite(v).all() for v in u3.values())
+
+    b, sink_b, logs_b, _ = run("b", job(6, True))
+    assert b.finished and b.rounds == 6, logs_b[-20:]
+    assert any("resumed from round 3" in l for l in logs_b)
+    assert sum("joined a running job after round 3" in l for l in logs_b) == 2
+    assert sum("Finished training of 6 DiLoCo update rounds" in l for l in logs_b) == 2
+    assert {r["round"] for r in sink_b.records} == {4, 5, 6}                          # only the new rounds ran
+    assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 6}
+    u6 = load_file(os.path.join(ckpt, "round-6", "cumulative_update"))
+    assert any(not torch.equal(u6[k], u3[k]) for k in u3)                             # U kept accumulating
