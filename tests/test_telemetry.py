@@ -91,3 +91,51 @@ def test_from_config_reads_telemetry_keys():
     tel = T.Telemetry.from_config("gw", cfg)
     assert tel.resource.attributes["deployment"] == "box7" and tel.resource.attributes["service.name"] == "gw"
     tel.shutdown()
+
+
+def test_otlp_http_export_reaches_a_collector():
+    """With `telemetry_endpoint` set, traces, metrics (incl. the bandwidth counters) and logs are POSTed as
+    OTLP/HTTP protobuf to `<endpoint>/v1/{traces,metrics,logs}` with the configured headers
+    (telemetry/src/{tracing,metrics,logging}.rs).  The collector here is a local HTTP server."""
+    import threading
+    from http.server import BaseHTTPRequestHandler, HTTPServer
+
+    from hypha_b200.telemetry import Telemetry
+    from hypha_b200.telemetry.bandwidth import BandwidthCounters
+
+    got = []
+
+    class Collector(BaseHTTPRequestHandler):
+        def do_POST(self):
+            n = int(self.headers.get("Content-Length", 0))
+            body = self.rfile.read(n)
+            got.append((self.path, self.headers.get("Content-Type"), self.headers.get("x-api-key"), len(body)))
+            self.send_response(200)
+            self.send_header("Content-Type", "application/x-protobuf")
+            self.end_headers()
+
+        def log_message(self, *a):
+            pass
+
+    srv = HTTPServer(("127.0.0.1", 0), Collector)
+    t = threading.Thread(target=srv.serve_forever, daemon=True)
+    t.start()
+    try:
+        tel = Telemetry("hypha-test", endpoint=f"http://127.0.0.1:{srv.server_port}", protocol="http/protobuf",
+                        headers="x-api-key=secret", attributes="deployment=ci", metric_interval_s=0.2)
+        bw = BandwidthCounters()
+        bw.add("/hypha-api/0.0.1", inbound=123, outbound=456)
+        tel.register_bandwidth(bw)
+        with tel.span("allocate.workers", num=2):
+            tel.logger.warning("lease lost")
+        import time
+
+        time.sleep(0.5)                     # one periodic metric export
+        tel.shutdown()                      # flushes the batch processors
+    finally:
+        srv.shutdown()
+    paths = {p for p, *_ in got}
+    assert {"/v1/traces", "/v1/metrics"} <= paths, got
+    assert all(ct == "application/x-protobuf" and key == "secret" and size > 0 for p, ct, key, size in got
+               if p in ("/v1/traces", "/v1/metrics"))
+    assert "/v1/logs" in paths          # the log bridge exported the warning
