@@ -1,0 +1,1 @@
+"""Optional sidecar services (AIM metrics driver)."""
