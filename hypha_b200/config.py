@@ -440,11 +440,24 @@ class ConfigBuilder:
         env = os.environ if environ is None else environ
         over: dict = {}
         top = {_key(f): f for f in fields(self.cls)}
-        for name, value in env.items():
+        for name, value in sorted(env.items()):
             if name.startswith("HYPHA_"):
-                key = name[len("HYPHA_"):].lower()
-                if key in top:
-                    over[key] = _parse_env_value(value)
+                # HYPHA_<KEY> for top-level keys (the reference's figment Env::prefixed); nested keys are
+                # reachable either as JSON (HYPHA_SCHEDULER='{"job": ...}') or with `__` as the separator
+                # (HYPHA_SCHEDULER__JOB__ROUNDS__UPDATE_ROUNDS=5)
+                path = name[len("HYPHA_"):].lower().split("__")
+                if path[0] not in top:
+                    continue
+                node = over
+                for part in path[:-1]:
+                    nxt = node.get(part)
+                    if not isinstance(nxt, dict):
+                        nxt = node[part] = {}
+                    node = nxt
+                val = _parse_env_value(value)
+                if len(path) > 1 and isinstance(val, str):
+                    val = _parse_scalar(val)
+                node[path[-1]] = val
         self._layer(over, "env:HYPHA_*")
         over = {}
         for name, value in env.items():
@@ -470,6 +483,19 @@ class ConfigBuilder:
         if pre is not None and (not pre.repository or pre.type == "none"):
             job.preprocessor = None
         return cfg
+
+
+def _parse_scalar(v: str) -> Any:
+    """Nested `__` variables carry scalars: numbers and booleans are recognised, the rest stays text."""
+    low = v.strip().lower()
+    if low in ("true", "false"):
+        return low == "true"
+    for cast in (int, float):
+        try:
+            return cast(v)
+        except ValueError:
+            pass
+    return v
 
 
 def _parse_env_value(v: str) -> Any:

@@ -148,3 +148,20 @@ def test_scheduler_job_aggregation_and_elastic_sections(tmp_path):
         {"scheduler": {"job": {"aggregation": {"mode": "collective", "rendezvous": "udp://x"}}}}).build()
     with pytest.raises(C.ConfigError):
         C.validate(bad2)
+
+
+def test_nested_env_keys_with_double_underscore():
+    """`HYPHA_<KEY>` covers top-level keys like the reference; `__` reaches nested ones and JSON values
+    still work.  Unknown top-level names are ignored (other tools also use the HYPHA_ prefix)."""
+    from hypha_b200 import config as C
+
+    env = {"HYPHA_SCHEDULER__JOB__ROUNDS__UPDATE_ROUNDS": "7", "HYPHA_SCHEDULER__JOB__ELASTIC__ENABLED": "false",
+           "HYPHA_SCHEDULER__JOB__AGGREGATION__MODE": "collective", "HYPHA_STATUS_BRIDGE": "127.0.0.1:61000",
+           "HYPHA_GATEWAY_ADDRESSES": '["tcp://10.1.2.3:4001"]', "HYPHA_DEVICE": "3", "HYPHA_NO_AUTOBUILD": "1"}
+    cfg = C.builder(C.SchedulerConfig).with_env(env).build()
+    job = cfg.scheduler.job
+    assert job.rounds.update_rounds == 7 and job.elastic.enabled is False and job.aggregation.mode == "collective"
+    assert job.rounds.avg_samples_between_updates == 1200            # siblings keep their defaults
+    assert cfg.status_bridge == "127.0.0.1:61000" and cfg.gateway_addresses == ["tcp://10.1.2.3:4001"]
+    w = C.builder(C.WorkerConfig).with_env(env).build()
+    assert w.device == 3
