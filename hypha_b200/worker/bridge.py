@@ -17,7 +17,7 @@ import json
 import os
 import random
 import shutil
-from typing import Any, AsyncIterator, Dict, Optional, Tuple
+from typing import Any, AsyncIterator, Callable, Dict, Optional, Tuple
 from urllib.parse import urlparse
 
 from aiohttp import web
@@ -178,8 +178,9 @@ class Bridge:
     """aiohttp app on ``<work_dir>/bridge.sock`` (0600) serving one job."""
 
     def __init__(self, connector: Connector, network: Network, work_dir: str, socket_path: str,
-                 job_id: str, scheduler: str):
+                 job_id: str, scheduler: str, log: Optional[Callable[[str], None]] = None):
         self.connector, self.network = connector, network
+        self.log = log or (lambda m: None)
         self.work_dir = os.path.abspath(work_dir)
         self.socket_path, self.job_id, self.scheduler = socket_path, job_id, scheduler
         self._runner: Optional[web.AppRunner] = None
@@ -269,8 +270,8 @@ class Bridge:
         async def bg():
             try:
                 await self.connector.send(ref, path, job_id=self.job_id)
-            except Exception:
-                pass
+            except Exception as exc:            # the HTTP request already returned 200: report it in the log
+                self.log(f"[bridge {self.job_id[:8]}] sending {body['path']!r} failed: {type(exc).__name__}: {exc}")
 
         self._spawn(bg())                     # 200 immediately, copy runs in the background
         return web.Response(status=200)

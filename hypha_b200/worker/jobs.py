@@ -83,7 +83,7 @@ class ProcessExecutor:
             sock_dir = tempfile.mkdtemp(prefix="hb-", dir="/tmp")
             os.chmod(sock_dir, 0o700)
             sock = os.path.join(sock_dir, "bridge.sock")
-        bridge = Bridge(self.connector, self.network, work_dir, sock, spec.job_id, scheduler)
+        bridge = Bridge(self.connector, self.network, work_dir, sock, spec.job_id, scheduler, log=self.log)
         await bridge.start()
         job_json = spec.to_json()
         argv = substitute_placeholders(self.args, sock, work_dir, job_json)
