@@ -121,6 +121,7 @@ class ExecutorSection:
     runtime: str = doc("`process` (spawn cmd) or `parameter-server` (built in)", "process")
     cmd: Optional[str] = doc("command for the process runtime", None)
     args: List[str] = doc("arguments; {SOCKET_PATH} {WORK_DIR} {JOB_JSON} are substituted", factory=list)
+    env: Dict[str, str] = doc("extra environment of the spawned process (e.g. CUDA_VISIBLE_DEVICES)", factory=dict)
 
 
 def _default_executors() -> List[ExecutorSection]:

@@ -105,6 +105,15 @@ class InnerLoop:
                     self.prev[k] = v.detach().clone()
 
 
+def _step_delay() -> float:
+    """Fault-injection / test knob: HYPHA_EXECUTOR_STEP_DELAY_MS makes every inner step that much slower
+    (a "slow worker" for the performance-aware scheduling tests); 0 in production."""
+    try:
+        return max(0.0, float(os.environ.get("HYPHA_EXECUTOR_STEP_DELAY_MS", "0"))) / 1e3
+    except ValueError:
+        return 0.0
+
+
 class StatusPipe:
     """Per-batch `status{batch_size}` reports without stalling the training loop (the
     reference does a synchronous HTTP -> RPC round trip after every batch).  The report for batch k travels
@@ -305,6 +314,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
             torch.cuda.synchronize()
 
     status = StatusPipe(session)
+    delay = _step_delay()
 
     while True:
         loss_sum = torch.zeros((), device=device)
@@ -314,6 +324,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         while counter != 0:
             batch = next(batches)
             loss_sum += engine.step(batch)
+            if delay:
+                time.sleep(delay)
             steps += 1
             first = next(iter(batch.values()))
             bs = int(first.shape[0])
@@ -381,6 +393,7 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
         batches = forever(loader)
         round_no = 1
         status = StatusPipe(session)
+        delay = _step_delay()
         with session.receive(config["results"], "incoming") as receiver:
             updates = iter(receiver)
             if config.get("join"):
@@ -401,6 +414,8 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
                 while counter != 0:
                     batch = next(batches)
                     loss_sum += loop.step(batch)
+                    if delay:
+                        time.sleep(delay)
                     steps += 1
                     bs = int(next(iter(batch.values())).shape[0])
                     counter = status.report(bs, counter)

@@ -32,7 +32,8 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
                            write_dataset: Callable[[str], None], job: Dict[str, Any], num_workers: int = 2,
                            timeout_s: float = 600.0, log: Optional[Callable[[str], None]] = None,
                            omp_threads: int = 2, chaos: Optional[Callable[[Dict[str, Any], List[str]], Any]] = None,
-                           spare_workers: int = 0) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
+                           spare_workers: int = 0, executor_env: Optional[Dict[str, Dict[str, str]]] = None
+                           ) -> Tuple[Any, MemoryConnector, List[str], List[Any]]:
     """Returns ``(JobOutcome, metrics sink, executor logs, nodes)``.  ``chaos(nodes_by_peer_id, logs)`` is an
     optional coroutine run next to the job (fault injection: e.g. stop a worker node mid-run)."""
     registry = os.path.join(tmp, "registry")
@@ -66,7 +67,7 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
     for i, name in enumerate(names):
         wd = os.path.join(tmp, name)
         os.makedirs(wd, exist_ok=True)
-        ex = [PS_EXEC] if name == "worker-ps" else [TRAIN_EXEC]
+        ex = [PS_EXEC] if name == "worker-ps" else [dict(TRAIN_EXEC, env=(executor_env or {}).get(name, {}))]
         price = 1.5 if name in spares else 1.0
         # train worker i drives GPU i (ignored on CPU; collective jobs pick the device from their rank)
         dev = i if name != "worker-ps" else None

@@ -405,8 +405,10 @@ class JobManager:
     async def execute(self, task_id: str, spec: M.JobSpec, lease_id: str, scheduler: str) -> Job:
         ec = self._find(spec.executor.descriptor)
         if ec.runtime == "process":
+            env = dict(self.executor_env)
+            env.update({str(k): str(v) for k, v in (getattr(ec, "env", None) or {}).items()})
             runner = ProcessExecutor(self.connector, self.network, self.work_dir, ec.cmd, list(ec.args),
-                                     env=self.executor_env, log=self.log)
+                                     env=env, log=self.log)
         elif ec.runtime == "parameter-server":
             if spec.executor.descriptor.cls != "aggregate":
                 raise JobManagerError("parameter-server runtime only runs aggregate jobs")

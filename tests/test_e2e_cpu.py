@@ -309,3 +309,42 @@ def test_job_checkpoint_and_resume(tmp_path):
     assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 6}
     u6 = load_file(os.path.join(ckpt, "round-6", "cumulative_update"))
     assert any(not torch.equal(u6[k], u3[k]) for k in u3)                             # U kept accumulating
+
+
+def test_performance_aware_rounds_give_the_fast_worker_more_batches(tmp_path):
+    """rfc/2025-10-16_performance_aware_scheduling.md: H is not a constant.  worker-b is made 10x slower per
+    step (`[[executors]].env`); the batch scheduler's sync-point projection, fed by the measured batch
+    latencies, lets worker-a run several times more inner steps per round, and both still meet at every
+    outer step."""
+    import re
+
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 160, "update_rounds": 3, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, timeout_s=300,
+        executor_env={"worker-a": {"HYPHA_EXECUTOR_STEP_DELAY_MS": "10"}, "worker-b": {"HYPHA_EXECUTOR_STEP_DELAY_MS": "100"}},
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=8, samples_per_slice=32, seq_len=32,
+                                                             vocab_size=512)))
+    assert outcome.finished and outcome.rounds == 3, logs[-20:]
+    steps = [int(m.group(1)) for l in logs for m in [re.search(r"round [23]: (\d+) inner steps", l)] if m]
+    assert len(steps) == 4                                  # two workers x rounds 2 and 3 (round 1 warms the estimates up)
+    fast, slow = max(steps), min(steps)
+    assert fast >= 3 * slow, steps                          # the 10x faster worker runs several times more batches
+    per_round = {}
+    for l in logs:
+        m = re.search(r"round (\d+): (\d+) inner steps", l)
+        if m:
+            per_round.setdefault(int(m.group(1)), []).append(int(m.group(2)))
+    for r in (2, 3):                                        # together they cover the round's sample target
+        assert 4 * sum(per_round[r]) >= 160 * 0.8, per_round
