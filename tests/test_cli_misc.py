@@ -195,3 +195,45 @@ def test_status_pipe_runs_exactly_the_projected_number_of_batches(monkeypatch):
         assert async_batches == sync_batches and async_reports == async_batches      # one report per batch
     # counter 0 answered one batch late: a single batch of overshoot, never a hang
     assert run(True, 2, 0)[0] == 2 and run(False, 2, 0)[0] == 3
+
+
+def test_lr_schedules_match_transformers():
+    """constant / cosine-with-warmup / linear-with-warmup / wsd (utils.py:90-102) against the Hugging Face
+    schedulers the reference executor calls; `decay_step` (the reference's typo, quirk Q4) is an alias."""
+    import torch
+    import transformers
+
+    from hypha_b200.parallel.diloco import make_lr_lambda, shard_bounds
+
+    def hf(factory, n, **kw):
+        opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1.0)
+        sched = factory(opt, **kw)
+        out = []
+        for _ in range(n):
+            out.append(opt.param_groups[0]["lr"])
+            opt.step()
+            sched.step()
+        return out
+
+    n = 60
+    ours = [make_lr_lambda({"type": "cosine-with-warmup", "warmup_steps": 5, "training_steps": 50})(s) for s in range(n)]
+    ref = hf(transformers.get_cosine_schedule_with_warmup, n, num_warmup_steps=5, num_training_steps=50)
+    assert all(abs(a - b) < 1e-6 for a, b in zip(ours[:51], ref[:51]))
+    assert all(v == 0.0 for v in ours[50:])      # past the end we stay at 0 (HF's cosine starts rising again)
+    ours = [make_lr_lambda({"type": "linear-with-warmup", "warmup_steps": 5, "training_steps": 50})(s) for s in range(n)]
+    ref = hf(transformers.get_linear_schedule_with_warmup, n, num_warmup_steps=5, num_training_steps=50)
+    assert all(abs(a - b) < 1e-6 for a, b in zip(ours, ref))
+    wsd = {"type": "wsd", "warmup_steps": 5, "stable_steps": 20, "decay_steps": 10}
+    ours = [make_lr_lambda(wsd)(s) for s in range(n)]
+    ref = hf(transformers.get_wsd_schedule, n, num_warmup_steps=5, num_stable_steps=20, num_decay_steps=10)
+    assert all(abs(a - b) < 1e-6 for a, b in zip(ours, ref)), list(zip(ours, ref))[:40]
+    typo = dict(wsd)
+    typo["decay_step"] = typo.pop("decay_steps")
+    assert [make_lr_lambda(typo)(s) for s in range(n)] == ours
+    assert all(make_lr_lambda(None)(s) == 1.0 for s in range(5))
+    # ZeRO-1 shard layout of the flat vector: aligned, disjoint, covering
+    for total, world in ((8 * 1024 + 8, 8), (1 << 20, 3), (4096, 8)):
+        spans = [shard_bounds(total, world, r) for r in range(world)]
+        assert spans[0][0] == 0 and sum(l for _, l in spans) == total
+        assert all(b % 1024 == 0 for b, _ in spans if b < total)
+        assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] or spans[i + 1][1] == 0 for i in range(world - 1))
