@@ -169,43 +169,71 @@ class StatusPipe:
 # collective mode: the train workers are the ranks of one process group and run the outer step
 # among themselves -- no aggregate worker, no files (TrainExecutorConfig.collective)
 # ---------------------------------------------------------------------------------------------
+class CollectiveBroken(RuntimeError):
+    """A rank died while the pseudo-gradients were being all-reduced; nothing was applied yet."""
+
+
 class ReplicatedNesterov:
     """Outer step for the CPU / generic-model plumbing path: all-reduce the pseudo-gradient over the
     job's process group (gloo on CPU), true 1/N mean, Nesterov with the reference's numerics
-    (parameter_server.rs:386-446); every rank keeps the full outer state."""
+    (parameter_server.rs:386-446); every rank keeps the full outer state.
+
+    Two phases so that a rank dying mid-collective cannot leave the model half-updated: first every
+    tensor's mean is reduced into a temporary (on failure nothing has changed and the step can be retried
+    with the surviving ranks), then momentum / parameters are updated locally."""
 
     def __init__(self, lr: float, mu: float):
         self.lr, self.mu = lr, mu
         self.m: Optional[Dict[str, torch.Tensor]] = None
 
-    @torch.no_grad()
-    def step(self, loop: "InnerLoop", world: int) -> None:
+    def _mean(self, g: torch.Tensor, world: int) -> torch.Tensor:
+        if world > 1:
+            import torch.distributed as dist
+
+            try:
+                dist.all_reduce(g)
+            except RuntimeError as exc:
+                raise CollectiveBroken(str(exc)) from exc
+            g.div_(world)
+        return g
+
+    def _check_round(self, round_no: int, world: int, device: str = "cpu") -> None:
+        """All ranks must be reducing the same round (guards the corner where one survivor finished an
+        interrupted collective and moved on while another one retries): fail loudly, never mix rounds."""
+        if world <= 1 or round_no < 0:
+            return
         import torch.distributed as dist
 
+        tag = torch.tensor([float(round_no), float(-round_no)], device=device)     # NCCL needs device tensors
+        try:
+            dist.all_reduce(tag, op=dist.ReduceOp.MAX)
+        except RuntimeError as exc:
+            raise CollectiveBroken(str(exc)) from exc
+        if int(tag[0]) != round_no or int(-tag[1]) != round_no:
+            raise RuntimeError(f"ranks disagree on the round being reduced ({int(-tag[1])}..{int(tag[0])} vs {round_no})")
+
+    @torch.no_grad()
+    def step(self, loop: "InnerLoop", world: int, round_no: int = -1) -> None:
         first = self.m is None
-        if first:
-            self.m = {}
+        self._check_round(round_no, world, getattr(loop, "device", "cpu"))
         if loop.flat:
             net = loop.model.net
-            g = loop.opt.master - loop.prev
-            if world > 1:
-                dist.all_reduce(g)
-                g.div_(world)
+            g = self._mean(loop.opt.master - loop.prev, world)
             m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
-            self.m["flat"] = m
+            self.m = {"flat": m}
             loop.prev.add_(self.lr * (self.mu * m + g))
             loop.opt.master.copy_(loop.prev)
             net.flat.data.copy_(loop.prev)
             return
-        for k, v in loop.model.state_dict().items():
-            if not v.dtype.is_floating_point:
-                continue
-            g = v.detach().float() - loop.prev[k].float()
-            if world > 1:
-                dist.all_reduce(g)
-                g.div_(world)
+        sd = loop.model.state_dict()
+        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), world)          # phase 1: may raise
+                 for k, v in sd.items() if v.dtype.is_floating_point}
+        if first:
+            self.m = {}
+        for k, g in means.items():                                                       # phase 2: local
             m = g.clone() if first else self.m[k].mul_(self.mu).add_(g)
             self.m[k] = m
+            v = sd[k]
             v.copy_((loop.prev[k].float() + self.lr * (self.mu * m + g)).to(v.dtype))
             loop.prev[k] = v.detach().clone()
 
@@ -249,7 +277,20 @@ class _TrainerEngine:
         ids = batch["input_ids"]
         return self.trainer.inner_step(ids, batch.get("labels", torch.roll(ids, -1, dims=-1)))
 
-    def outer_step(self) -> None:
+    def regroup(self, membership: dict, coll: dict, **_) -> None:
+        """The scheduler dropped ranks: shrink the fused kernel's membership and adopt orphaned shards now
+        (`DiLoCoOuter.drop_ranks`) instead of discovering the dead rank by a barrier timeout.  Peer-memory
+        mappings and the original rank numbering stay as they are."""
+        outer = self.trainer.outer
+        if outer.backend != "fused":
+            return
+        alive = set(membership["members"])
+        dead = [i for i, p in enumerate(coll.get("peers", [])) if p not in alive and i in outer.members()]
+        if dead:
+            outer.drop_ranks(dead)
+            print(f"membership generation {membership['generation']}: continuing without ranks {dead}", flush=True)
+
+    def outer_step(self, round_no: int = -1) -> None:
         outer = self.trainer.outer
         if outer.backend == "fused":
             # a rank that never shows up costs one barrier timeout, then the survivors adopt its shard
@@ -274,8 +315,33 @@ class _GenericEngine:
     def step(self, batch):
         return self.loop.step(batch)
 
-    def outer_step(self) -> None:
-        self.outer.step(self.loop, self.world)
+    def regroup(self, membership: dict, coll: dict, use_cuda: bool = False, device: str = "cpu") -> None:
+        """The scheduler changed the membership: leave the old process group and form a new one with the
+        surviving ranks on the fresh rendezvous address."""
+        import torch.distributed as dist
+        from datetime import timedelta
+
+        members = list(membership["members"])
+        me = coll.get("peer")
+        if me not in members:
+            raise RuntimeError("this worker was removed from the job")
+        if dist.is_initialized():
+            try:
+                dist.destroy_process_group()
+            except Exception:
+                pass
+        self.world = len(members)
+        if self.world > 1:
+            kw = {"device_id": torch.device(device)} if use_cuda else {}
+            dist.init_process_group("nccl" if use_cuda else "gloo", init_method=membership["rendezvous"],
+                                    rank=members.index(me), world_size=self.world,
+                                    timeout=timedelta(seconds=float(os.environ.get("HYPHA_COLLECTIVE_TIMEOUT_S", "300"))),
+                                    **kw)
+        print(f"membership generation {membership['generation']}: regrouped as rank {members.index(me)} of {self.world}",
+              flush=True)
+
+    def outer_step(self, round_no: int = -1) -> None:
+        self.outer.step(self.loop, self.world, round_no)
 
 
 def main_collective(session: Session, config: dict, work_dir: str) -> None:
@@ -315,6 +381,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
 
     status = StatusPipe(session)
     delay = _step_delay()
+    generation = 0
 
     while True:
         loss_sum = torch.zeros((), device=device)
@@ -334,9 +401,34 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         status.drain()
         sync()
         inner_s = time.perf_counter() - t_round
-        session.send_status("update")
+        # answered once every current member reached this point; tells us who takes part (a rank the
+        # scheduler dropped in the meantime is no longer waited for)
+        ack = session.send_status("update")
+        mem = ack.get("membership") if isinstance(ack, dict) else None
+        if mem and int(mem.get("generation", 0)) != generation:
+            generation = int(mem["generation"])
+            engine.regroup(mem, coll, use_cuda=use_cuda, device=device)
         t_outer = time.perf_counter()
-        engine.outer_step()                        # every rank enters: the kernel / all-reduce is the barrier
+        for attempt in range(240):
+            try:
+                engine.outer_step(round_no)        # every rank enters: the kernel / all-reduce is the barrier
+                break
+            except CollectiveBroken as exc:
+                # a rank died inside the collective: nothing was applied.  Ask the scheduler (it learns of the
+                # death through the worker's JobStatus or the lost lease) until the membership changes, re-form
+                # the group with the survivors and run the outer step again.
+                print(f"outer step interrupted ({str(exc)[:80]}); waiting for the new membership", flush=True)
+                while True:
+                    time.sleep(0.5)
+                    ack = session.send_status("update")
+                    mem = ack.get("membership") if isinstance(ack, dict) else None
+                    if mem and int(mem.get("generation", 0)) != generation:
+                        generation = int(mem["generation"])
+                        engine.regroup(mem, coll, use_cuda=use_cuda, device=device)
+                        break
+                    attempt += 1
+                    if attempt > 240:
+                        raise
         sync()
         outer_ms = (time.perf_counter() - t_outer) * 1e3
         mean_loss = float(loss_sum.item() / max(1, steps))

@@ -720,17 +720,23 @@ class ProgressResponse:
 
     type: str
     counter: int = 0
+    # B200 extension, only on the answer to `update` of a collective job: who takes part in this outer step
+    # {"generation": g, "members": [peer ids in rank order], "rendezvous": "tcp://..."}
+    membership: Optional[dict] = None
 
     def to_wire(self) -> dict:
+        d = {"type": self.type}
         if self.type == "ScheduleUpdate":
-            return {"type": "ScheduleUpdate", "counter": self.counter}
-        return {"type": self.type}
+            d["counter"] = self.counter
+        if self.membership is not None:
+            d["membership"] = dict(self.membership)
+        return d
 
     @classmethod
     def from_wire(cls, d: dict) -> "ProgressResponse":
         if d["type"] not in ("Ok", "Continue", "ScheduleUpdate", "Done", "Error"):
             raise MessageError(f"unknown progress response {d['type']!r}")
-        return cls(d["type"], int(d.get("counter", 0)))
+        return cls(d["type"], int(d.get("counter", 0)), dict(d["membership"]) if d.get("membership") else None)
 
 
 # -- codecs -----------------------------------------------------------------------------------------------

@@ -183,11 +183,13 @@ class DiLoCoJobRun:
             else:
                 self.log.warning("checkpoint.resume is set but %s holds no checkpoint: starting at round 0", ck.dir)
         rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{free_tcp_port()}"
+        if self.collective:
+            self.batch.enable_collective(self.live, rendezvous, lambda: f"tcp://127.0.0.1:{free_tcp_port()}")
         for i, w in enumerate(self.workers):
             tcfg = self.train_config(w)
             if self.collective:
                 tcfg.collective = {"rank": i, "world": len(self.workers), "rendezvous": rendezvous,
-                                   "outer": self.nesterov.to_wire()}
+                                   "outer": self.nesterov.to_wire(), "peer": w.peer_id, "peers": list(self.live)}
             elif resume_round:
                 tcfg.join = {"after_round": resume_round, "resume": True}      # theta = theta_0(seed) + U
             await self._dispatch_train(w, tcfg)

@@ -10,7 +10,7 @@ from __future__ import annotations
 import asyncio
 import json
 import time
-from typing import Any, Dict, List
+from typing import Any, Callable, Dict, List, Optional
 
 from .. import messages as M
 from ..ops.native import load_core
@@ -36,6 +36,14 @@ class BatchSchedulerService:
         self.sched = self.core.BatchScheduler(tracker, time_cap_ms, update_cap)
         self.metrics: asyncio.Queue = asyncio.Queue(256)
         self.done = asyncio.Event()
+        # collective jobs (enable_collective): `update` is a barrier over the CURRENT members; its answer
+        # tells every rank who takes part in the outer step, so survivors never wait for a dead rank
+        self._members: Optional[List[str]] = None
+        self._generation = 0
+        self._rendezvous_factory: Optional[Callable[[], str]] = None
+        self._rendezvous: Optional[str] = None
+        self._cond = asyncio.Condition()
+        self._arrived: Dict[int, set] = {}     # round -> members whose `update` for that round arrived
         self._seen: set = set()                # workers that reported at least once
         self.never_started: List[str] = []     # late joiners dropped because the job ended before they trained
         self._lock = asyncio.Lock()
@@ -57,6 +65,24 @@ class BatchSchedulerService:
 
     def remove_worker(self, peer: str) -> None:
         self.sched.tracker.worker_tracker.remove_worker(peer)
+        if self._members is not None and peer in self._members:
+            self._members = [m for m in self._members if m != peer]
+            self._generation += 1
+            self._rendezvous = self._rendezvous_factory() if self._rendezvous_factory else None
+            asyncio.ensure_future(self._wake())       # the barrier may be complete without the lost rank
+
+    def enable_collective(self, members: List[str], rendezvous: str, rendezvous_factory: Callable[[], str]) -> None:
+        """Collective aggregation: remember the rank order and hand out a fresh rendezvous address every
+        time the membership changes (the survivors re-form their process group on it)."""
+        self._members, self._rendezvous, self._rendezvous_factory = list(members), rendezvous, rendezvous_factory
+
+    async def _wake(self) -> None:
+        async with self._cond:
+            self._cond.notify_all()
+
+    def _barrier_complete(self, rnd: int) -> bool:
+        here = self._arrived.get(rnd, set())
+        return all(m in here for m in (self._members or []))
 
     @property
     def round(self) -> int:
@@ -83,7 +109,21 @@ class BatchSchedulerService:
                 all_done = all(st == self.core.WorkerState.Done for st in wt.states())
             if all_done:
                 self.done.set()
-            return M.ProgressResponse(self._resp[r.kind], r.counter)
+            resp = M.ProgressResponse(self._resp[r.kind], r.counter)
+        if self._members is not None and progress.kind == "update" and resp.type == "Ok":
+            # outside the lock: wait until every current member reached the sync point of THIS round (or was
+            # dropped).  Arrivals are counted per round: a slow rank that is still acknowledging round r must
+            # not satisfy a fast rank's barrier of round r+1.
+            rnd = self.round
+            self._arrived.setdefault(rnd, set()).add(peer)
+            for old in [k for k in self._arrived if k < rnd - 1]:
+                del self._arrived[old]
+            async with self._cond:
+                self._cond.notify_all()
+                await self._cond.wait_for(lambda: self._barrier_complete(rnd))
+            resp.membership = {"generation": self._generation, "members": list(self._members),
+                               "rendezvous": self._rendezvous}
+        return resp
 
     def start(self) -> None:
         async def serve(peer, msg):

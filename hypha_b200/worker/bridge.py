@@ -317,8 +317,11 @@ class Bridge:
     async def _status(self, request: web.Request) -> web.Response:
         try:
             progress = M.Progress.from_wire(await request.json())
+            # `update` of a collective job is answered when every member reached its sync point: no short
+            # RPC timeout on it (a dropped rank releases the barrier through the scheduler, not a timer)
+            timeout = 6 * 3600.0 if progress.kind == "update" else 30.0
             out = await self.network.request(self.scheduler, M.PROGRESS_PROTOCOL,
-                                             M.ProgressRequest(self.job_id, progress))
+                                             M.ProgressRequest(self.job_id, progress), timeout=timeout)
             return web.json_response(M.ProgressResponse.from_wire(out).to_wire())
         except (M.MessageError, NetworkError, KeyError, ValueError) as exc:
             return self._fail(exc)

@@ -348,3 +348,43 @@ def test_performance_aware_rounds_give_the_fast_worker_more_batches(tmp_path):
             per_round.setdefault(int(m.group(1)), []).append(int(m.group(2)))
     for r in (2, 3):                                        # together they cover the round's sample target
         assert 4 * sum(per_round[r]) >= 160 * 0.8, per_round
+
+
+def test_collective_job_survives_a_lost_rank(tmp_path):
+    """Collective aggregation, three gloo ranks, worker-c dies after round 1.  `update` is a barrier at the
+    scheduler over the CURRENT members; when the lost lease removes worker-c the barrier completes, its
+    answer carries the new membership and a fresh rendezvous, the two survivors re-form their process group
+    and finish the job."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 48, "update_rounds": 4, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"mode": "collective"},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def kill_worker_c(nodes, logs):
+        while not any("round 1:" in l for l in logs):
+            await asyncio.sleep(0.1)
+        nodes["worker-c"].stop.set()
+
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cpu"
+    try:
+        outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+            tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+            chaos=kill_worker_c, timeout_s=300,
+            write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=9, samples_per_slice=16, seq_len=32,
+                                                                 vocab_size=512)))
+    finally:
+        os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 4 and outcome.removed_workers == ["worker-c"] and outcome.joined_workers == []
+    assert sum("regrouped as rank" in l and "of 2" in l for l in logs) == 2, logs[-30:]
+    assert sum("Finished training of 4 DiLoCo update rounds" in l for l in logs) == 2
