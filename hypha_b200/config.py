@@ -594,6 +594,8 @@ def _toml_value(v: Any) -> str:
         return json.dumps(v)
     if isinstance(v, list):
         return "[" + ", ".join(_toml_value(x) for x in v) + "]"
+    if isinstance(v, dict):                      # inline table, e.g. an executor's `env`
+        return "{ " + ", ".join(f"{json.dumps(str(k))} = {_toml_value(x)}" for k, x in v.items()) + " }" if v else "{}"
     raise TypeError(type(v))
 
 
