@@ -173,10 +173,57 @@ class CollectiveBroken(RuntimeError):
     """A rank died while the pseudo-gradients were being all-reduced; nothing was applied yet."""
 
 
+class _Group:
+    """The ranks an outer step is reduced over.  On GPUs this is the default torch.distributed (NCCL)
+    group.  On CPU it is a gloo group this object OWNS (its own TCPStore + ProcessGroupGloo, no global
+    state): it can be abandoned and re-created with other members while the job runs, and its collectives
+    carry a short timeout so that a rank blocked on a peer that left fails fast instead of hanging."""
+
+    def __init__(self, kind: str, rendezvous: Optional[str], rank: int, world: int):
+        self.kind, self.rank, self.world = (kind if world > 1 else "solo"), rank, world
+        self.pg = self.store = None
+        if self.kind == "gloo":
+            import torch.distributed as dist
+            from datetime import timedelta
+
+            host, port = rendezvous[len("tcp://"):].rsplit(":", 1)
+            op_timeout = float(os.environ.get("HYPHA_COLLECTIVE_TIMEOUT_S", "20"))
+            self.store = dist.TCPStore(host, int(port), world, rank == 0, timedelta(seconds=120))
+            self.pg = dist.ProcessGroupGloo(self.store, rank, world, timedelta(seconds=op_timeout))
+
+    def all_reduce(self, t: torch.Tensor, op: str = "sum") -> None:
+        if self.kind == "solo":
+            return
+        import torch.distributed as dist
+
+        rop = dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM
+        try:
+            if self.kind == "gloo":
+                opts = dist.AllreduceOptions()
+                opts.reduceOp = rop
+                self.pg.allreduce([t], opts).wait()
+            else:
+                dist.all_reduce(t, op=rop)
+        except RuntimeError as exc:
+            raise CollectiveBroken(str(exc)) from exc
+
+    def abandon(self) -> None:
+        """Drop an owned group without blocking: the C++ destructors (which close the sockets and thereby
+        fail the peers' pending operations) run on a helper thread."""
+        if self.kind != "gloo":
+            return
+        import threading
+
+        refs = [self.pg, self.store]
+        self.pg = self.store = None
+        self.kind = "abandoned"
+        threading.Thread(target=refs.clear, daemon=True).start()
+
+
 class ReplicatedNesterov:
     """Outer step for the CPU / generic-model plumbing path: all-reduce the pseudo-gradient over the
-    job's process group (gloo on CPU), true 1/N mean, Nesterov with the reference's numerics
-    (parameter_server.rs:386-446); every rank keeps the full outer state.
+    job's ranks, true 1/N mean, Nesterov with the reference's numerics (parameter_server.rs:386-446);
+    every rank keeps the full outer state.
 
     Two phases so that a rank dying mid-collective cannot leave the model half-updated: first every
     tensor's mean is reduced into a temporary (on failure nothing has changed and the step can be retried
@@ -186,39 +233,33 @@ class ReplicatedNesterov:
         self.lr, self.mu = lr, mu
         self.m: Optional[Dict[str, torch.Tensor]] = None
 
-    def _mean(self, g: torch.Tensor, world: int) -> torch.Tensor:
-        if world > 1:
-            import torch.distributed as dist
-
-            try:
-                dist.all_reduce(g)
-            except RuntimeError as exc:
-                raise CollectiveBroken(str(exc)) from exc
-            g.div_(world)
+    @staticmethod
+    def _mean(g: torch.Tensor, group: _Group) -> torch.Tensor:
+        if group.world > 1:
+            group.all_reduce(g)
+            g.div_(group.world)
         return g
 
-    def _check_round(self, round_no: int, world: int, device: str = "cpu") -> None:
+    @staticmethod
+    def _check_round(round_no: int, group: _Group, device: str = "cpu") -> None:
         """All ranks must be reducing the same round (guards the corner where one survivor finished an
         interrupted collective and moved on while another one retries): fail loudly, never mix rounds."""
-        if world <= 1 or round_no < 0:
+        if group.world <= 1 or round_no < 0:
             return
-        import torch.distributed as dist
-
         tag = torch.tensor([float(round_no), float(-round_no)], device=device)     # NCCL needs device tensors
-        try:
-            dist.all_reduce(tag, op=dist.ReduceOp.MAX)
-        except RuntimeError as exc:
-            raise CollectiveBroken(str(exc)) from exc
+        group.all_reduce(tag, "max")
         if int(tag[0]) != round_no or int(-tag[1]) != round_no:
             raise RuntimeError(f"ranks disagree on the round being reduced ({int(-tag[1])}..{int(tag[0])} vs {round_no})")
 
     @torch.no_grad()
-    def step(self, loop: "InnerLoop", world: int, round_no: int = -1) -> None:
+    def step(self, loop: "InnerLoop", group, round_no: int = -1) -> None:
+        if isinstance(group, int):                       # plain world size: single rank / tests
+            group = _Group("solo", None, 0, 1) if group <= 1 else _Group("default", None, 0, group)
         first = self.m is None
-        self._check_round(round_no, world, getattr(loop, "device", "cpu"))
+        self._check_round(round_no, group, getattr(loop, "device", "cpu"))
         if loop.flat:
             net = loop.model.net
-            g = self._mean(loop.opt.master - loop.prev, world)
+            g = self._mean(loop.opt.master - loop.prev, group)
             m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
             self.m = {"flat": m}
             loop.prev.add_(self.lr * (self.mu * m + g))
@@ -226,7 +267,7 @@ class ReplicatedNesterov:
             net.flat.data.copy_(loop.prev)
             return
         sd = loop.model.state_dict()
-        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), world)          # phase 1: may raise
+        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), group)          # phase 1: may raise
                  for k, v in sd.items() if v.dtype.is_floating_point}
         if first:
             self.m = {}
@@ -304,44 +345,38 @@ class _TrainerEngine:
 
 
 class _GenericEngine:
-    def __init__(self, local: str, config: dict, coll: dict, device: str):
+    def __init__(self, local: str, config: dict, coll: dict, device: str, group: _Group):
         model = get_model(local, config["model"]["task"], device)
         self.loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device)
         outer = coll.get("outer") or {}
         self.outer = ReplicatedNesterov(float(outer.get("learning-rate", 0.7)), float(outer.get("momentum", 0.9)))
-        self.world = int(coll["world"])
+        self.group = group
         self.backend = "all-reduce"
 
     def step(self, batch):
         return self.loop.step(batch)
 
-    def regroup(self, membership: dict, coll: dict, use_cuda: bool = False, device: str = "cpu") -> None:
-        """The scheduler changed the membership: leave the old process group and form a new one with the
-        surviving ranks on the fresh rendezvous address."""
-        import torch.distributed as dist
-        from datetime import timedelta
+    def abort_group(self) -> None:
+        """Leave the group NOW (owned gloo groups only): closing our side makes the peers' pending
+        collective fail too instead of leaving them blocked on us."""
+        self.group.abandon()
 
+    def regroup(self, membership: dict, coll: dict, use_cuda: bool = False, device: str = "cpu") -> None:
+        """The scheduler changed the membership: form a new group with the surviving ranks on the fresh
+        rendezvous address (CPU / gloo; the NCCL group of a GPU job is fixed)."""
         members = list(membership["members"])
         me = coll.get("peer")
         if me not in members:
             raise RuntimeError("this worker was removed from the job")
-        if dist.is_initialized():
-            try:
-                dist.destroy_process_group()
-            except Exception:
-                pass
-        self.world = len(members)
-        if self.world > 1:
-            kw = {"device_id": torch.device(device)} if use_cuda else {}
-            dist.init_process_group("nccl" if use_cuda else "gloo", init_method=membership["rendezvous"],
-                                    rank=members.index(me), world_size=self.world,
-                                    timeout=timedelta(seconds=float(os.environ.get("HYPHA_COLLECTIVE_TIMEOUT_S", "300"))),
-                                    **kw)
-        print(f"membership generation {membership['generation']}: regrouped as rank {members.index(me)} of {self.world}",
-              flush=True)
+        if use_cuda:
+            raise RuntimeError("membership changed: NCCL-backed generic jobs cannot regroup")
+        self.group.abandon()
+        self.group = _Group("gloo", membership["rendezvous"], members.index(me), len(members))
+        print(f"membership generation {membership['generation']}: regrouped as rank {members.index(me)} of "
+              f"{len(members)}", flush=True)
 
     def outer_step(self, round_no: int = -1) -> None:
-        self.outer.step(self.loop, self.world, round_no)
+        self.outer.step(self.loop, self.group, round_no)
 
 
 def main_collective(session: Session, config: dict, work_dir: str) -> None:
@@ -354,19 +389,21 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     if use_cuda:
         torch.cuda.set_device(dev_index)
     device = f"cuda:{dev_index}" if use_cuda else "cpu"
-    if world > 1:
+    if world > 1 and use_cuda:
         from datetime import timedelta
 
-        kw = {"device_id": torch.device(device)} if use_cuda else {}
-        # a rank that dies must not leave the others blocked in a collective for the default 30 minutes
+        # GPUs: the default NCCL group (the peer-memory handle exchange of the fused path runs over it)
         timeout_s = float(os.environ.get("HYPHA_COLLECTIVE_TIMEOUT_S", "300"))
-        dist.init_process_group("nccl" if use_cuda else "gloo", init_method=coll["rendezvous"], rank=rank,
-                                world_size=world, timeout=timedelta(seconds=timeout_s), **kw)
+        dist.init_process_group("nccl", init_method=coll["rendezvous"], rank=rank, world_size=world,
+                                timeout=timedelta(seconds=timeout_s), device_id=torch.device(device))
     prepare_files(config, session)
     local = os.path.join(work_dir, FETCH_PATH)
     family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
-    engine = (_TrainerEngine(local, config, coll, dev_index) if use_cuda and family == "llama"
-              else _GenericEngine(local, config, coll, device))
+    if use_cuda and family == "llama":
+        engine = _TrainerEngine(local, config, coll, dev_index)
+    else:
+        group = _Group("default" if use_cuda else "gloo", coll["rendezvous"], rank, world)
+        engine = _GenericEngine(local, config, coll, device, group)
     print(f"collective rank {rank}/{world} on {device}: outer step via {engine.backend}", flush=True)
     pre_cfg = config.get("preprocessor")
     loader = torch.utils.data.DataLoader(
@@ -418,6 +455,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
                 # death through the worker's JobStatus or the lost lease) until the membership changes, re-form
                 # the group with the survivors and run the outer step again.
                 print(f"outer step interrupted ({str(exc)[:80]}); waiting for the new membership", flush=True)
+                if hasattr(engine, "abort_group"):
+                    engine.abort_group()
                 while True:
                     time.sleep(0.5)
                     ack = session.send_status("update")
@@ -447,7 +486,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         if session.send_status("update-received")["type"] == "Done":
             break
     print(f"Finished training of {round_no - 1} DiLoCo update rounds", flush=True)
-    if world > 1:
+    if world > 1 and use_cuda:
         # no closing barrier: nothing touches peer memory after the last outer step, and a barrier would
         # hang the survivors of a job that lost a rank
         try:
