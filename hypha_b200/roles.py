@@ -19,7 +19,7 @@ from typing import Any, Callable, List, Optional
 
 from . import config as C
 from . import messages as M
-from .scheduler import Connector as MetricsConnector
+from .scheduler import AllocatorError, Connector as MetricsConnector
 from .scheduler.job import DiLoCoJobRun, JobError, JobOutcome as _JobOutcome, worker_batch_size as _worker_batch_size
 from .telemetry import Telemetry
 from .transport import Network, NetworkError, RecordNotFound
@@ -224,5 +224,7 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
         return await run.run()
     except JobError as exc:
         raise RoleError(str(exc)) from exc
+    except AllocatorError as exc:             # e.g. nobody answered the advertisement within the deadline
+        raise RoleError(f"allocation failed: {exc}") from exc
     finally:
         await node.shutdown()

@@ -2,6 +2,7 @@
 acceptance by renewal -> dispatch guard -> expiry.  (The reference has no tests for the arbiter /
 allocator / lease manager: SURVEY section 4 "not tested at all".)"""
 import asyncio
+import os
 import time
 
 import pytest
@@ -131,4 +132,42 @@ def test_lease_expiry_cancels_the_job_and_fails_the_handle(monkeypatch):
         await asyncio.wait_for(job.execution.wait(), 5.0)
         assert job.execution.status == M.JobStatus.FAILED and a.leases.available().gpu == 2
         await _teardown(gw, sched, workers)
+    asyncio.run(main())
+
+
+def test_scheduler_without_workers_fails_with_a_role_error():
+    """Nobody answers the advertisement: `run_scheduler` raises RoleError("allocation failed: ...") after the
+    5 s allocator deadline (the CLI turns that into exit code 1 with a one-line message, no traceback)."""
+    import tempfile
+    import time
+
+    from hypha_b200 import config as C
+    from hypha_b200 import roles
+    from hypha_b200.executor.dataset import write_synthetic_token_slices
+
+    async def main():
+        tmp = tempfile.mkdtemp()
+        ds = os.path.join(tmp, "toyset")
+        write_synthetic_token_slices(ds, 2, 4, 8, 32)
+        gw = f"memory://gw-noworkers-{os.getpid()}"
+        loop = asyncio.get_event_loop()
+        s0, s1 = loop.create_future(), loop.create_future()
+        bg = [asyncio.ensure_future(roles.run_gateway(
+            C.builder(C.GatewayConfig).with_overrides({"listen_addresses": [gw]}).build(), peer_id="gw", started=s0))]
+        await s0
+        bg.append(asyncio.ensure_future(roles.run_data(C.builder(C.DataConfig).with_overrides(
+            {"listen_addresses": [], "gateway_addresses": [gw], "exclude_cidr": [], "dataset_path": ds}).build(),
+            peer_id="data", started=s1)))
+        await s1
+        cfg = C.builder(C.SchedulerConfig).with_overrides(
+            {"listen_addresses": [], "gateway_addresses": [gw], "exclude_cidr": [],
+             "scheduler": {"job": {"dataset": {"dataset": "toyset"}, "preprocessor": None}}}).build()
+        t0 = time.time()
+        with pytest.raises(roles.RoleError) as ei:
+            await roles.run_scheduler(cfg, peer_id="sched")
+        assert "allocation failed" in str(ei.value) and 4.0 < time.time() - t0 < 15.0
+        for n in (s0.result(), s1.result()):
+            n.stop.set()
+        await asyncio.wait(bg, timeout=5)
+
     asyncio.run(main())
