@@ -19,7 +19,7 @@ from typing import Any, Callable, List, Optional
 
 from . import config as C
 from . import messages as M
-from .scheduler import AllocatorError, Connector as MetricsConnector
+from .scheduler import AllocatorError, Connector as MetricsConnector, TaskError
 from .scheduler.job import DiLoCoJobRun, JobError, JobOutcome as _JobOutcome, worker_batch_size as _worker_batch_size
 from .telemetry import Telemetry
 from .transport import Network, NetworkError, RecordNotFound
@@ -222,7 +222,7 @@ async def run_scheduler(cfg: C.SchedulerConfig, *, peer_id: Optional[str] = None
                        status_bridge=cfg.status_bridge, allocation_pause_s=allocation_pause_s)
     try:
         return await run.run()
-    except JobError as exc:
+    except (JobError, TaskError) as exc:      # incomplete allocation / a worker refused the dispatch
         raise RoleError(str(exc)) from exc
     except AllocatorError as exc:             # e.g. nobody answered the advertisement within the deadline
         raise RoleError(f"allocation failed: {exc}") from exc
