@@ -207,6 +207,21 @@ class _Group:
         except RuntimeError as exc:
             raise CollectiveBroken(str(exc)) from exc
 
+    def broadcast(self, t: torch.Tensor, root: int = 0) -> None:
+        if self.kind == "solo":
+            return
+        import torch.distributed as dist
+
+        try:
+            if self.kind == "gloo":
+                opts = dist.BroadcastOptions()
+                opts.rootRank = root
+                self.pg.broadcast([t], opts).wait()
+            else:
+                dist.broadcast(t, root)
+        except RuntimeError as exc:
+            raise CollectiveBroken(str(exc)) from exc
+
     def abandon(self) -> None:
         """Drop an owned group without blocking: the C++ destructors (which close the sockets and thereby
         fail the peers' pending operations) run on a helper thread."""
@@ -234,10 +249,10 @@ class ReplicatedNesterov:
         self.m: Optional[Dict[str, torch.Tensor]] = None
 
     @staticmethod
-    def _mean(g: torch.Tensor, group: _Group) -> torch.Tensor:
+    def _mean(g: torch.Tensor, group: _Group, exclude: int = 0) -> torch.Tensor:
         if group.world > 1:
             group.all_reduce(g)
-            g.div_(group.world)
+            g.div_(max(1, group.world - exclude))      # ranks that just joined contribute a zero delta
         return g
 
     @staticmethod
@@ -252,14 +267,14 @@ class ReplicatedNesterov:
             raise RuntimeError(f"ranks disagree on the round being reduced ({int(-tag[1])}..{int(tag[0])} vs {round_no})")
 
     @torch.no_grad()
-    def step(self, loop: "InnerLoop", group, round_no: int = -1) -> None:
+    def step(self, loop: "InnerLoop", group, round_no: int = -1, exclude: int = 0) -> None:
         if isinstance(group, int):                       # plain world size: single rank / tests
             group = _Group("solo", None, 0, 1) if group <= 1 else _Group("default", None, 0, group)
         first = self.m is None
         self._check_round(round_no, group, getattr(loop, "device", "cpu"))
         if loop.flat:
             net = loop.model.net
-            g = self._mean(loop.opt.master - loop.prev, group)
+            g = self._mean(loop.opt.master - loop.prev, group, exclude)
             m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
             self.m = {"flat": m}
             loop.prev.add_(self.lr * (self.mu * m + g))
@@ -267,7 +282,7 @@ class ReplicatedNesterov:
             net.flat.data.copy_(loop.prev)
             return
         sd = loop.model.state_dict()
-        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), group)          # phase 1: may raise
+        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), group, exclude)  # phase 1: may raise
                  for k, v in sd.items() if v.dtype.is_floating_point}
         if first:
             self.m = {}
@@ -352,9 +367,43 @@ class _GenericEngine:
         self.outer = ReplicatedNesterov(float(outer.get("learning-rate", 0.7)), float(outer.get("momentum", 0.9)))
         self.group = group
         self.backend = "all-reduce"
+        self._exclude = 0             # newcomers in the coming outer step (they contribute a zero delta)
 
     def step(self, batch):
         return self.loop.step(batch)
+
+    @torch.no_grad()
+    def welcome(self, membership: dict, me: Optional[str] = None) -> None:
+        """Right after a regroup that admitted newcomers: rank 0 (always a survivor -- newcomers are appended
+        to the member list) broadcasts the current global model theta_prev and the outer momentum; every rank
+        takes part, the newcomers adopt what they receive."""
+        if self.loop.flat:
+            raise RuntimeError("collective join is implemented for the replicated (non-flat) engine only")
+        joined = list(membership.get("joined") or [])
+        if not joined:
+            return
+        flag = torch.tensor([0.0 if self.outer.m is None else 1.0])
+        self.group.broadcast(flag)
+        has_m = bool(flag.item())
+        sd = self.loop.model.state_dict()
+        if has_m and self.outer.m is None:
+            self.outer.m = {}
+        for k in sorted(k for k, v in sd.items() if v.dtype.is_floating_point):
+            prev = self.loop.prev[k].contiguous()
+            self.group.broadcast(prev)
+            self.loop.prev[k] = prev
+            if me in joined:
+                sd[k].copy_(prev)                  # newcomers start from the global model; survivors keep
+                                                   # their locally trained weights (= their pseudo-gradient)
+            if has_m:
+                m = self.outer.m.get(k)
+                if m is None:
+                    m = torch.zeros_like(prev, dtype=torch.float32)
+                m = m.contiguous()
+                self.group.broadcast(m)
+                self.outer.m[k] = m
+        self._exclude = len(joined)
+        print(f"welcomed {joined}: model and outer momentum broadcast from rank 0", flush=True)
 
     def abort_group(self) -> None:
         """Leave the group NOW (owned gloo groups only): closing our side makes the peers' pending
@@ -376,7 +425,8 @@ class _GenericEngine:
               f"{len(members)}", flush=True)
 
     def outer_step(self, round_no: int = -1) -> None:
-        self.outer.step(self.loop, self.group, round_no)
+        self.outer.step(self.loop, self.group, round_no, self._exclude)
+        self._exclude = 0
 
 
 def main_collective(session: Session, config: dict, work_dir: str) -> None:
@@ -389,6 +439,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     if use_cuda:
         torch.cuda.set_device(dev_index)
     device = f"cuda:{dev_index}" if use_cuda else "cpu"
+    if coll.get("join") and use_cuda:
+        raise RuntimeError("joining a running collective job is implemented for the CPU (gloo) engine only")
     if world > 1 and use_cuda:
         from datetime import timedelta
 
@@ -401,6 +453,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
     if use_cuda and family == "llama":
         engine = _TrainerEngine(local, config, coll, dev_index)
+    elif coll.get("join"):
+        engine = _GenericEngine(local, config, coll, device, _Group("solo", None, 0, 1))   # regrouped at its first barrier
     else:
         group = _Group("default" if use_cuda else "gloo", coll["rendezvous"], rank, world)
         engine = _GenericEngine(local, config, coll, device, group)
@@ -419,10 +473,11 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     status = StatusPipe(session)
     delay = _step_delay()
     generation = 0
+    joining = bool(coll.get("join"))        # a replacement rank: no training before its first barrier
 
     while True:
         loss_sum = torch.zeros((), device=device)
-        steps, counter, tokens = 0, -1, 0
+        steps, counter, tokens = 0, (0 if joining else -1), 0
         sync()
         t_round = time.perf_counter()
         while counter != 0:
@@ -445,6 +500,12 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         if mem and int(mem.get("generation", 0)) != generation:
             generation = int(mem["generation"])
             engine.regroup(mem, coll, use_cuda=use_cuda, device=device)
+            if mem.get("joined") and hasattr(engine, "welcome"):
+                engine.welcome(mem, coll.get("peer"))
+        if joining:
+            round_no = int(mem["round"]) + 1 if mem else round_no
+            joining = False
+            print(f"joined a running collective job at round {round_no}", flush=True)
         t_outer = time.perf_counter()
         for attempt in range(240):
             try:
@@ -473,9 +534,10 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         mean_loss = float(loss_sum.item() / max(1, steps))
         # the reference reports the loss only (training.py:148-150); the extra keys are SURVEY 5.5's
         # "tokens/s, step time, outer-step wall time" and travel through the same Metrics message
-        session.send_status({"metrics": {"round": round_no, "metrics": {
-            "loss": mean_loss, "samples_or_tokens_per_s": tokens / max(inner_s, 1e-9),
-            "inner_step_ms": inner_s * 1e3 / max(1, steps), "outer_step_ms": outer_ms}}})
+        if steps > 0:                              # a rank that joined at this barrier has nothing to report yet
+            session.send_status({"metrics": {"round": round_no, "metrics": {
+                "loss": mean_loss, "samples_or_tokens_per_s": tokens / max(inner_s, 1e-9),
+                "inner_step_ms": inner_s * 1e3 / max(1, steps), "outer_step_ms": outer_ms}}})
         print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}, {inner_s * 1e3 / max(1, steps):.1f} ms/step; "
               f"outer step done in {outer_ms:.1f} ms", flush=True)
         # what the aggregate worker reports in parameter-server mode.  Every rank sends it (the scheduler

@@ -214,12 +214,11 @@ class DiLoCoJobRun:
         self.log.warning("%s train worker %s: continuing with %d worker(s)", why, peer, len(self.live))
         self.batch.remove_worker(peer)
         self.data_svc.remove_worker(peer)
-        if self.collective:
-            return      # the survivors' fused outer step finds out by its barrier timeout (step_resilient)
-        try:
-            await self._tell_aggregate_worker()
-        except NetworkError as exc:
-            self.log.warning("could not tell the aggregate worker about the new membership: %s", exc)
+        if not self.collective:
+            try:
+                await self._tell_aggregate_worker()
+            except NetworkError as exc:
+                self.log.warning("could not tell the aggregate worker about the new membership: %s", exc)
         if self.job.elastic.replace and self._replacements < self.job.elastic.max_replacements:
             self._replacements += 1
             self.background.append(asyncio.ensure_future(self._replace_worker(peer)))
@@ -244,7 +243,7 @@ class DiLoCoJobRun:
                 except Exception as exc:                      # NoOffersReceived and friends
                     self.log.info("replacement attempt %d for %s: %s", attempt + 1, lost, exc)
                     got = []
-                new = [h for h in got if h.peer_id not in self.live and h.peer_id != self.ps.peer_id]
+                new = [h for h in got if h.peer_id not in self.live and (self.collective or h.peer_id != self.ps.peer_id)]
                 for h in got:
                     if h not in new:
                         await h.release()
@@ -257,11 +256,22 @@ class DiLoCoJobRun:
             h = new[0]
             self.handles.append(h)
             tcfg = self.train_config(h)
-            tcfg.join = {"after_round": self.batch.round, "replaces": lost}
+            if self.collective:
+                # joins at the next `update` barrier: the survivors re-form their group with it and rank 0
+                # broadcasts the current model and outer momentum (CPU engine; see executor/training.py)
+                tcfg.collective = {"rank": -1, "world": len(self.live) + 1, "rendezvous": None,
+                                   "outer": self.nesterov.to_wire(), "peer": h.peer_id,
+                                   "peers": [w.peer_id for w in self.workers], "join": True,
+                                   "after_round": self.batch.round}
+            else:
+                tcfg.join = {"after_round": self.batch.round, "replaces": lost}
             await self._dispatch_train(h, tcfg)
             self.live.append(h.peer_id)
             self.joined.append(h.peer_id)
-            await self._tell_aggregate_worker()
+            if self.collective:
+                self.batch.add_member(h.peer_id)
+            else:
+                await self._tell_aggregate_worker()
             if h.task is not None:
                 self._waiters[h.task] = h
                 self._wake.set()

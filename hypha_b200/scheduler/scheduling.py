@@ -44,6 +44,8 @@ class BatchSchedulerService:
         self._rendezvous: Optional[str] = None
         self._cond = asyncio.Condition()
         self._arrived: Dict[int, set] = {}     # round -> members whose `update` for that round arrived
+        self._joiners: List[str] = []          # members that have not taken part in an outer step yet
+        self._released: Dict[int, set] = {}    # round -> members that got the barrier's answer
         self._seen: set = set()                # workers that reported at least once
         self.never_started: List[str] = []     # late joiners dropped because the job ended before they trained
         self._lock = asyncio.Lock()
@@ -67,6 +69,7 @@ class BatchSchedulerService:
         self.sched.tracker.worker_tracker.remove_worker(peer)
         if self._members is not None and peer in self._members:
             self._members = [m for m in self._members if m != peer]
+            self._joiners = [j for j in self._joiners if j != peer]
             self._generation += 1
             self._rendezvous = self._rendezvous_factory() if self._rendezvous_factory else None
             asyncio.ensure_future(self._wake())       # the barrier may be complete without the lost rank
@@ -75,6 +78,17 @@ class BatchSchedulerService:
         """Collective aggregation: remember the rank order and hand out a fresh rendezvous address every
         time the membership changes (the survivors re-form their process group on it)."""
         self._members, self._rendezvous, self._rendezvous_factory = list(members), rendezvous, rendezvous_factory
+
+    def add_member(self, peer: str) -> None:
+        """Collective jobs: a replacement rank joins at the next `update` barrier (it is reported in
+        `membership.joined` until it has taken part in one outer step)."""
+        if self._members is None or peer in self._members:
+            return
+        self._members.append(peer)
+        self._joiners.append(peer)
+        self._generation += 1
+        self._rendezvous = self._rendezvous_factory() if self._rendezvous_factory else None
+        asyncio.ensure_future(self._wake())
 
     async def _wake(self) -> None:
         async with self._cond:
@@ -122,7 +136,14 @@ class BatchSchedulerService:
                 self._cond.notify_all()
                 await self._cond.wait_for(lambda: self._barrier_complete(rnd))
             resp.membership = {"generation": self._generation, "members": list(self._members),
-                               "rendezvous": self._rendezvous}
+                               "rendezvous": self._rendezvous, "round": rnd,
+                               "joined": [j for j in self._joiners if j in self._members]}
+            self._released.setdefault(rnd, set()).add(peer)
+            if self._released[rnd] >= set(self._members):
+                # everybody has the answer of this round's barrier: the newcomers are regular members now
+                self._joiners = [j for j in self._joiners if j not in self._released[rnd]]
+                for old in [k for k in self._released if k < rnd]:
+                    del self._released[old]
         return resp
 
     def start(self) -> None:

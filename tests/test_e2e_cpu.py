@@ -388,3 +388,50 @@ def test_collective_job_survives_a_lost_rank(tmp_path):
     assert outcome.rounds == 4 and outcome.removed_workers == ["worker-c"] and outcome.joined_workers == []
     assert sum("regrouped as rank" in l and "of 2" in l for l in logs) == 2, logs[-30:]
     assert sum("Finished training of 4 DiLoCo update rounds" in l for l in logs) == 2
+
+
+def test_collective_job_replaces_a_lost_rank(tmp_path):
+    """Collective aggregation with a spare worker: worker-c dies after round 1, the scheduler leases the
+    spare, dispatches it with `collective.join`, and at the next `update` barrier everybody regroups: rank 0
+    broadcasts the current model and outer momentum, the newcomer takes part in that outer step with a zero
+    pseudo-gradient (excluded from the mean) and trains from then on."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 240, "update_rounds": 12, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"mode": "collective"},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def kill_worker_c(nodes, logs):
+        while not any("round 1:" in l for l in logs):
+            await asyncio.sleep(0.1)
+        nodes["worker-c"].stop.set()
+
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cpu"
+    try:
+        outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+            tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+            spare_workers=1, chaos=kill_worker_c, timeout_s=300,
+            write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=12, samples_per_slice=64, seq_len=32,
+                                                                 vocab_size=512)))
+    finally:
+        os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 12 and outcome.removed_workers == ["worker-c"] and outcome.joined_workers == ["worker-d"]
+    assert any("joined a running collective job at round" in l for l in logs), logs[-30:]
+    assert sum("welcomed ['worker-d']" in l for l in logs) == 3                # both survivors and the newcomer
+    rounds = {}
+    for r in sink.records:
+        if r["metric_name"] == "loss":
+            rounds.setdefault(r["worker_id"], set()).add(r["round"])
+    assert 12 in rounds["worker-a"] and 12 in rounds["worker-b"]
+    assert len(rounds.get("worker-d", set())) >= 2 and 12 in rounds["worker-d"]     # it trained for real
+    assert sum("Finished training of 12 DiLoCo update rounds" in l for l in logs) == 3
