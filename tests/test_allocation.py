@@ -171,3 +171,59 @@ def test_scheduler_without_workers_fails_with_a_role_error():
         await asyncio.wait(bg, timeout=5)
 
     asyncio.run(main())
+
+
+def test_collective_membership_barrier_semantics():
+    """`update` of a collective job is a barrier over the current members of the current round: it is
+    released by the last arrival or by the removal of the missing rank, its answer names the membership
+    generation, and a newcomer is reported in `joined` for exactly one barrier."""
+    from hypha_b200.scheduler.scheduling import BatchSchedulerService
+    from hypha_b200.transport import Network
+
+    async def main():
+        svc = BatchSchedulerService(Network("sched-unit"), "job", "a", update_target=12, update_rounds=3)
+        for w in ("a", "b", "c"):
+            svc.add_worker(w, 4)
+        ports = iter(range(40000, 40100))
+        svc.enable_collective(["a", "b", "c"], "tcp://127.0.0.1:1", lambda: f"tcp://127.0.0.1:{next(ports)}")
+        upd = M.Progress("update")
+
+        # round 0: a and b wait until c is removed
+        ta = asyncio.ensure_future(svc.handle("a", upd))
+        tb = asyncio.ensure_future(svc.handle("b", upd))
+        await asyncio.sleep(0.1)
+        assert not ta.done() and not tb.done()
+        svc.remove_worker("c")
+        ra, rb = await asyncio.wait_for(asyncio.gather(ta, tb), 2)
+        for r in (ra, rb):
+            assert r.type == "Ok" and r.membership["generation"] == 1 and r.membership["members"] == ["a", "b"]
+            assert r.membership["joined"] == [] and r.membership["round"] == 0
+            assert r.membership["rendezvous"] == "tcp://127.0.0.1:40000"
+        assert (await svc.handle("a", M.Progress("updated"))).type == "Ok"
+        assert (await svc.handle("b", M.Progress("updated"))).type == "Ok"          # idempotent
+        assert svc.round == 1
+        for w in ("a", "b"):
+            assert (await svc.handle(w, M.Progress("update-received"))).type == "Continue"
+
+        # round 1: a newcomer d is admitted; a fast rank's barrier must wait for everybody of THIS round
+        svc.add_worker("d", 4)
+        svc.add_member("d")
+        td = asyncio.ensure_future(svc.handle("d", upd))
+        ta = asyncio.ensure_future(svc.handle("a", upd))
+        await asyncio.sleep(0.1)
+        assert not td.done() and not ta.done()
+        rb = await asyncio.wait_for(svc.handle("b", upd), 2)
+        ra, rd = await asyncio.wait_for(asyncio.gather(ta, td), 2)
+        for r in (ra, rb, rd):
+            assert r.membership["generation"] == 2 and r.membership["members"] == ["a", "b", "d"]
+            assert r.membership["joined"] == ["d"] and r.membership["round"] == 1
+        await svc.handle("a", M.Progress("updated"))
+        for w in ("a", "b", "d"):
+            await svc.handle(w, M.Progress("update-received"))
+
+        # round 2: d is a regular member now
+        tasks = [asyncio.ensure_future(svc.handle(w, upd)) for w in ("a", "b", "d")]
+        rs = await asyncio.wait_for(asyncio.gather(*tasks), 2)
+        assert all(r.membership["joined"] == [] and r.membership["generation"] == 2 for r in rs)
+
+    asyncio.run(main())
