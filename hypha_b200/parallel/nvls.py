@@ -169,107 +169,200 @@ def nvls_usable(device: int, world: int) -> bool:
 
 
 def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock_dir: Optional[str] = None) -> NvlsBuffer:
-    """Collective: every rank of ``group`` must call it with the same arguments."""
-    cu = _cu()
-    rank, world, device = group.rank, group.world, group.device
-    torch.cuda.set_device(device)
-    torch.cuda.current_stream().synchronize()     # make sure the primary context exists
-    if not multicast_supported(device):
-        raise NvlsUnavailable("device does not report CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED")
-    _ck(cu.cuInit(0), "cuInit")
-    dev = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
-    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+    """Collective: every rank of ``group`` must call it with the same arguments.
 
-    prop = cu.CUmemAllocationProp()
-    prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
-    prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-    prop.location.id = device
-    prop.requestedHandleTypes = H
-
-    mcprop = cu.CUmulticastObjectProp()
-    mcprop.numDevices = world
-    mcprop.handleTypes = H
-    mcprop.flags = 0
-    nbytes = numel * _DT_SIZE[dtype]
-    mcprop.size = nbytes
-    gran_mc = _ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
-                  "cuMulticastGetGranularity")
-    gran_mem = _ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
-                   "cuMemGetAllocationGranularity")
-    gran = max(int(gran_mc), int(gran_mem))
-    size = (nbytes + gran - 1) // gran * gran
-    mcprop.size = size
-
-    h_local = _ck(cu.cuMemCreate(size, prop, 0), "cuMemCreate")
-    fd_local = int(_ck(cu.cuMemExportToShareableHandle(h_local, H, 0), "cuMemExportToShareableHandle"))
-
-    # ---- descriptor exchange over AF_UNIX --------------------------------------------------
-    tag = group._exchange(os.getpid() if rank == 0 else None)[0]
-    base = sock_dir or tempfile.gettempdir()
-    paths = [os.path.join(base, f"hb-nvls-{tag}-{name.replace('.', '_')}-{r}.sock") for r in range(world)]
-    if os.path.exists(paths[rank]):
-        os.unlink(paths[rank])
-    server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-    server.bind(paths[rank])
-    server.listen(world)
-    server.settimeout(60)                          # a rank that failed earlier must not hang the others
-    group._exchange(rank)                          # everyone is listening
-    mc_handle = None
-    fd_mc = -1
-    if rank == 0:
-        mc_handle = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
-        fd_mc = int(_ck(cu.cuMemExportToShareableHandle(mc_handle, H, 0), "export multicast handle"))
+    The set-up is five stages separated by control-plane exchanges.  A stage that fails on one rank does not
+    raise there and then (the other ranks would block in the next exchange, or bind memory to a team with a
+    missing member): the error travels WITH the next exchange, every rank sees it at the same point, undoes
+    what it mapped so far and raises ``NvlsUnavailable`` -- the number of exchanges each rank performs is the
+    same on every path, so the caller can go on using the group (``trainer.py`` falls back to CUDA-IPC)."""
     import threading
 
-    recv_box = {}
-    t = threading.Thread(target=lambda: recv_box.update(_recv_fds(server, world - 1, 2)))
-    t.start()
-    for p in range(world):
-        if p != rank:
-            _send_fds(paths[p], rank, [fd_local] + ([fd_mc] if rank == 0 else []))
-    t.join()
-    server.close()
-    os.unlink(paths[rank])
+    cu = _cu()
+    rank, world, device = group.rank, group.world, group.device
+    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+    st = {"err": None, "fds": [], "mapped": [], "loose": [], "server": None, "path": None}
 
-    access = cu.CUmemAccessDesc()
-    access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-    access.location.id = device
-    access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+    def stage(fn) -> None:
+        if st["err"] is None:
+            try:
+                fn()
+            except Exception as exc:     # noqa: BLE001 - reported to every rank by the next exchange
+                st["err"] = f"rank {rank}: {type(exc).__name__}: {exc}"
 
-    mapped: list = []
+    def undo() -> None:
+        for fd in st["fds"]:
+            try:
+                os.close(fd)
+            except OSError:
+                pass
+        st["fds"].clear()
+        if st["server"] is not None:
+            st["server"].close()
+            st["server"] = None
+        if st["path"] and os.path.exists(st["path"]):
+            os.unlink(st["path"])
+        for va, size, h in st["mapped"]:
+            try:
+                cu.cuMemUnmap(va, size)
+                cu.cuMemAddressFree(va, size)
+            except Exception:
+                pass
+        for h in [m[2] for m in st["mapped"]] + st["loose"]:
+            try:
+                cu.cuMemRelease(h)
+            except Exception:
+                pass
+        st["mapped"].clear()
+        st["loose"].clear()
 
+    def agree(extra=None) -> list:
+        got = group._exchange((st["err"], extra))
+        bad = [e for e, _ in got if e]
+        if bad:
+            undo()
+            raise NvlsUnavailable("; ".join(bad))
+        return [x for _, x in got]
+
+    # ---- stage 1: local allocation (+ the multicast object on rank 0), exportable as POSIX fds ----------------
+    def s_create() -> None:
+        torch.cuda.set_device(device)
+        torch.cuda.current_stream().synchronize()     # make sure the primary context exists
+        if not multicast_supported(device):
+            raise NvlsUnavailable("device does not report CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED")
+        _ck(cu.cuInit(0), "cuInit")
+        st["dev"] = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
+        prop = cu.CUmemAllocationProp()
+        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
+        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        prop.location.id = device
+        prop.requestedHandleTypes = H
+        mcprop = cu.CUmulticastObjectProp()
+        mcprop.numDevices = world
+        mcprop.handleTypes = H
+        mcprop.flags = 0
+        nbytes = numel * _DT_SIZE[dtype]
+        mcprop.size = nbytes
+        gran_mc = _ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
+                      "cuMulticastGetGranularity")
+        gran_mem = _ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
+                       "cuMemGetAllocationGranularity")
+        st["gran"] = gran = max(int(gran_mc), int(gran_mem))
+        st["size"] = size = (nbytes + gran - 1) // gran * gran
+        mcprop.size = size
+        st["h_local"] = _ck(cu.cuMemCreate(size, prop, 0), "cuMemCreate")
+        st["loose"].append(st["h_local"])
+        st["fd_local"] = int(_ck(cu.cuMemExportToShareableHandle(st["h_local"], H, 0), "cuMemExportToShareableHandle"))
+        st["fds"].append(st["fd_local"])
+        if rank == 0:
+            st["mc"] = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
+            st["loose"].append(st["mc"])
+            st["fd_mc"] = int(_ck(cu.cuMemExportToShareableHandle(st["mc"], H, 0), "export multicast handle"))
+            st["fds"].append(st["fd_mc"])
+
+    stage(s_create)
+    tag = agree(os.getpid() if rank == 0 else None)[0]
+
+    # ---- stage 2: every rank listens on an AF_UNIX socket --------------------------------------------------------
+    base = sock_dir or tempfile.gettempdir()
+    paths = [os.path.join(base, f"hb-nvls-{tag}-{name.replace('.', '_')}-{r}.sock") for r in range(world)]
+
+    def s_listen() -> None:
+        if os.path.exists(paths[rank]):
+            os.unlink(paths[rank])
+        st["path"] = paths[rank]
+        server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+        st["server"] = server
+        server.bind(paths[rank])
+        server.listen(world)
+        server.settimeout(60)                      # a peer that dies mid-way must not hang this rank forever
+
+    stage(s_listen)
+    agree()                                        # everyone is listening
+
+    # ---- stage 3: descriptors travel (SCM_RIGHTS), peers' memory is mapped, the device joins the team --------------
     def map_handle(h) -> int:
-        va = _ck(cu.cuMemAddressReserve(size, gran, 0, 0), "cuMemAddressReserve")
-        _ck(cu.cuMemMap(va, size, 0, h, 0), "cuMemMap")
-        _ck(cu.cuMemSetAccess(va, size, [access], 1), "cuMemSetAccess")
-        mapped.append((va, size, h))
+        size = st["size"]
+        va = _ck(cu.cuMemAddressReserve(size, st["gran"], 0, 0), "cuMemAddressReserve")
+        try:
+            _ck(cu.cuMemMap(va, size, 0, h, 0), "cuMemMap")
+        except Exception:
+            cu.cuMemAddressFree(va, size)
+            raise
+        st["mapped"].append((va, size, h))
+        if h in st["loose"]:
+            st["loose"].remove(h)
+        _ck(cu.cuMemSetAccess(va, size, [st["access"]], 1), "cuMemSetAccess")
         return int(va)
 
     ptrs = [0] * world
-    ptrs[rank] = map_handle(h_local)
-    for p in range(world):
-        if p == rank:
-            continue
-        hp = _ck(cu.cuMemImportFromShareableHandle(recv_box[p][0], H), "cuMemImportFromShareableHandle")
-        ptrs[p] = map_handle(hp)
-        os.close(recv_box[p][0])
-    if rank != 0:
-        mc_handle = _ck(cu.cuMemImportFromShareableHandle(recv_box[0][1], H), "import multicast handle")
-        os.close(recv_box[0][1])
-    else:
-        os.close(fd_mc)
-    os.close(fd_local)
 
-    _ck(cu.cuMulticastAddDevice(mc_handle, dev), "cuMulticastAddDevice")
-    group._exchange(rank)                          # every device is part of the team before binding
-    _ck(cu.cuMulticastBindMem(mc_handle, 0, h_local, 0, size, 0), "cuMulticastBindMem")
-    group._exchange(rank)
-    mc_ptr = map_handle(mc_handle)
+    def s_swap() -> None:
+        recv_box: dict = {}
+        recv_err: list = []
 
-    local = tensor_from_ptr(ptrs[rank], numel, dtype, device)
-    local.zero_()
-    torch.cuda.synchronize()
-    group._exchange(rank)
-    buf = NvlsBuffer(name, numel, dtype, local, ptrs, mc_ptr=mc_ptr, nbytes_mapped=size, _handles=mapped)
+        def receiver() -> None:
+            try:
+                recv_box.update(_recv_fds(st["server"], world - 1, 2))
+            except Exception as exc:     # noqa: BLE001
+                recv_err.append(exc)
+
+        t = threading.Thread(target=receiver)
+        t.start()
+        send_err = None
+        for p in range(world):
+            if p != rank:
+                try:
+                    _send_fds(paths[p], rank, [st["fd_local"]] + ([st["fd_mc"]] if rank == 0 else []))
+                except Exception as exc:     # noqa: BLE001 - keep serving the other peers
+                    send_err = send_err or exc
+        t.join()
+        st["server"].close()
+        st["server"] = None
+        os.unlink(paths[rank])
+        for fds in recv_box.values():
+            st["fds"].extend(fds)
+        if send_err or recv_err:
+            raise send_err or recv_err[0]
+
+        access = cu.CUmemAccessDesc()
+        access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        access.location.id = device
+        access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        st["access"] = access
+        ptrs[rank] = map_handle(st["h_local"])
+        for p in range(world):
+            if p == rank:
+                continue
+            hp = _ck(cu.cuMemImportFromShareableHandle(recv_box[p][0], H), "cuMemImportFromShareableHandle")
+            st["loose"].append(hp)
+            ptrs[p] = map_handle(hp)
+        if rank != 0:
+            st["mc"] = _ck(cu.cuMemImportFromShareableHandle(recv_box[0][1], H), "import multicast handle")
+            st["loose"].append(st["mc"])
+        for fd in st["fds"]:
+            os.close(fd)
+        st["fds"].clear()
+        _ck(cu.cuMulticastAddDevice(st["mc"], st["dev"]), "cuMulticastAddDevice")
+
+    stage(s_swap)
+    agree()                                        # every device is part of the team before anyone binds
+
+    # ---- stage 4: bind the local memory to the multicast object -------------------------------------------------------
+    stage(lambda: _ck(cu.cuMulticastBindMem(st["mc"], 0, st["h_local"], 0, st["size"], 0), "cuMulticastBindMem"))
+    agree()
+
+    # ---- stage 5: map the multicast view, zero the local slice ----------------------------------------------------------
+    def s_view() -> None:
+        st["mc_ptr"] = map_handle(st["mc"])
+        local = tensor_from_ptr(ptrs[rank], numel, dtype, device)
+        local.zero_()
+        torch.cuda.synchronize()
+        st["local"] = local
+
+    stage(s_view)
+    agree()
+    buf = NvlsBuffer(name, numel, dtype, st["local"], ptrs, mc_ptr=st["mc_ptr"], nbytes_mapped=st["size"],
+                     _handles=list(st["mapped"]))
     group.buffers[name] = buf
     return buf

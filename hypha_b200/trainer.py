@@ -82,8 +82,13 @@ class DiLoCoTrainer:
                     if ok:
                         try:
                             return alloc_nvls(group, name, n, dt)
-                        except NvlsUnavailable as exc:        # collective failure is fatal by design
-                            raise RuntimeError(f"NVLS set-up failed ({exc}); rerun with HYPHA_NVLS=0") from exc
+                        except NvlsUnavailable as exc:
+                            # alloc_nvls reports a failure to EVERY rank at the same exchange and undoes its
+                            # mappings, so all ranks arrive here together and the group is still aligned
+                            if nvls_mode == "force":
+                                raise RuntimeError(f"NVLS set-up failed ({exc}); rerun with HYPHA_NVLS=0") from exc
+                            if group.rank == 0:
+                                print(f"[trainer] NVLS set-up failed ({exc}); using CUDA-IPC peer buffers", flush=True)
                     use_nvls = False
                 return group.alloc(name, n, dt)
 
