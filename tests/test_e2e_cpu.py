@@ -435,3 +435,53 @@ def test_collective_job_replaces_a_lost_rank(tmp_path):
     assert 12 in rounds["worker-a"] and 12 in rounds["worker-b"]
     assert len(rounds.get("worker-d", set())) >= 2 and 12 in rounds["worker-d"]     # it trained for real
     assert sum("Finished training of 12 DiLoCo update rounds" in l for l in logs) == 3
+
+
+def test_transformers_auto_class_job(tmp_path):
+    """A model family that is NOT one of ours (llama / gpt2 / lenet): `type = "sequence-classification"` with a
+    BERT checkpoint resolves through the `transformers` auto-class table like the reference's executor
+    (model.py:47-126), here without remote code.  The artifact carries config + weights, slices carry
+    input_ids / attention_mask / labels, and the label is a function of the first token so the loss falls."""
+    transformers = pytest.importorskip("transformers")
+    from safetensors.torch import save_file
+
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/bert-tiny", "filenames": ["config.json", "model.safetensors"],
+                  "type": "sequence-classification", "input_names": ["input_ids", "attention_mask", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "parity"},
+        "rounds": {"avg_samples_between_updates": 128, "update_rounds": 3, "max_batch_size": 16},
+        "inner_optimizer": {"learning-rate": 2e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    def write_model(p):
+        torch.manual_seed(0)
+        cfg = transformers.BertConfig(vocab_size=64, hidden_size=32, num_hidden_layers=2, num_attention_heads=2,
+                                      intermediate_size=64, max_position_embeddings=32, num_labels=2,
+                                      hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0)
+        transformers.BertForSequenceClassification(cfg).save_pretrained(os.path.dirname(p))
+
+    def write_dataset(d):
+        os.makedirs(d, exist_ok=True)
+        g = torch.Generator().manual_seed(1)
+        for i in range(6):
+            ids = torch.randint(0, 64, (64, 16), generator=g)
+            save_file({"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": (ids[:, 0] % 2).contiguous()},
+                      os.path.join(d, f"slice-{i:05d}.safetensors"))
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/bert-tiny", write_model_config=write_model, job=job, write_dataset=write_dataset, timeout_s=300))
+    assert outcome.finished, logs[-20:]
+    assert outcome.rounds == 3
+    loss = {}
+    for r in sink.records:
+        if r["metric_name"] == "loss":
+            loss.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
+    assert set(loss) == {"worker-a", "worker-b"}
+    for w, v in loss.items():
+        assert v[3] < v[1], (w, v)
