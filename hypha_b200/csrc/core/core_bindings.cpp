@@ -5,6 +5,7 @@
 
 #include "core.hpp"
 #include "flag_barrier_model.hpp"
+#include "ps_reduce.hpp"
 
 namespace py = pybind11;
 using namespace hypha;
@@ -199,4 +200,28 @@ PYBIND11_MODULE(_core, m) {
         py::arg("world"), py::arg("member_mask"), py::arg("epochs"), py::arg("stages"), py::arg("seed") = 1,
         py::arg("dead_rank") = -1, py::arg("timeout_ms") = 2000, py::arg("first_epoch") = 1,
         "Host stress test of the device flag-barrier protocol (outer_step.cu: cross_gpu_barrier).");
+
+  m.def("ps_fused_round",
+        [](const std::vector<std::string>& in_paths, const std::vector<std::vector<uint64_t>>& in_offsets,
+           const std::vector<uint64_t>& numels, const std::string& prev_m_path,
+           const std::vector<uint64_t>& prev_m_offsets, const std::string& prev_cum_path,
+           const std::vector<uint64_t>& prev_cum_offsets, const std::string& out_u_path,
+           const std::string& out_m_path, const std::string& out_cum_path,
+           const std::vector<uint64_t>& out_offsets, double lr, double mu, int threads) {
+          PsRoundStats s;
+          {
+            py::gil_scoped_release nogil;
+            s = ps_fused_round(in_paths, in_offsets, numels, prev_m_path, prev_m_offsets, prev_cum_path,
+                               prev_cum_offsets, out_u_path, out_m_path, out_cum_path, out_offsets, lr, mu, threads);
+          }
+          py::dict d;
+          d["elements"] = s.elements; d["bytes_read"] = s.bytes_read; d["bytes_written"] = s.bytes_written;
+          d["threads"] = s.threads; d["seconds"] = s.seconds;
+          return d;
+        },
+        py::arg("in_paths"), py::arg("in_offsets"), py::arg("numels"), py::arg("prev_m_path"),
+        py::arg("prev_m_offsets"), py::arg("prev_cum_path"), py::arg("prev_cum_offsets"), py::arg("out_u_path"),
+        py::arg("out_m_path"), py::arg("out_cum_path"), py::arg("out_offsets"), py::arg("lr"), py::arg("mu"),
+        py::arg("threads") = 0,
+        "One parameter-server round (mean, momentum, Nesterov, cumulative update) over mmapped safetensors files.");
 }

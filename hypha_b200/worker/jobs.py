@@ -28,6 +28,7 @@ from typing import Any, Callable, Dict, List, Optional
 from .. import messages as M
 from ..transport import Network, NetworkError
 from .bridge import Bridge, Connector
+from .ps_round import outer_round
 
 KILL_GRACE_S = 5.0
 
@@ -208,14 +209,13 @@ class ParameterServerExecutor:
         ex.work_dir = work_dir  # type: ignore[attr-defined]
 
         async def run():
-            from safetensors.torch import load_file, save_file
+            from safetensors.torch import save_file
 
             workers = list(cfg.updates.get_peers())
             allowed = set(workers)                 # live allow-list of the push-stream receiver
             result_peers = list(cfg.results.peers)
             pending_join: List[str] = []
             cum_path = os.path.join(work_dir, "cumulative_update")     # U = sum of all outer updates so far
-            momentum = None
             rnd = 0
             ckpt = cfg.checkpoint or {}
             ckpt_dir, ckpt_every = ckpt.get("dir"), max(1, int(ckpt.get("every", 1)))
@@ -226,7 +226,7 @@ class ParameterServerExecutor:
                 if found is None or found["round"] != int(ckpt["resume_round"]):
                     raise RuntimeError(f"checkpoint of round {ckpt['resume_round']} not found in {ckpt_dir}")
                 shutil.copyfile(os.path.join(found["path"], "cumulative_update"), cum_path)
-                momentum = load_file(os.path.join(found["path"], "momentum"))
+                shutil.copyfile(os.path.join(found["path"], "momentum"), os.path.join(work_dir, "momentum"))
                 rnd = found["round"]
                 pending_join, workers, result_peers = list(workers), [], []
                 self.log(f"[ps {spec.job_id[:8]}] resumed from round {rnd} ({ckpt_dir})")
@@ -290,37 +290,15 @@ class ParameterServerExecutor:
                             self.log(f"[ps {spec.job_id[:8]}] round {rnd}: timeout, dropping {missing}")
                             workers = [w for w in workers if w in got]      # membership shrink (Q8)
                             break
-                    # true mean + Nesterov, one tensor at a time, OFF the event loop: the worker must
-                    # keep answering RenewLease / health RPCs while hundreds of MB are being reduced
-                    out = os.path.join(work_dir, "gradient_update")
+                    # true mean + momentum + Nesterov + cumulative update in ONE pass over the mmapped files
+                    # (C++ core, all cores; torch fallback for non-F32 tensors), OFF the event loop: the worker
+                    # must keep answering RenewLease / health RPCs while GBs are being reduced
                     paths = list(got.values())
-                    prev_momentum = momentum
-
-                    def reduce_and_step():
-                        # one tensor of every worker in RAM at a time (the reference streams tensor pairs
-                        # the same way, parameter_server.rs:331-384): peak = update + momentum + N tensors
-                        from safetensors import safe_open
-
-                        handles = [safe_open(p, framework="pt") for p in paths]
-                        cum = load_file(cum_path) if os.path.exists(cum_path) else {}
-                        new_m, upd = {}, {}
-                        inv = 1.0 / len(handles)
-                        for k in handles[0].keys():
-                            acc = handles[0].get_tensor(k).float()
-                            for h in handles[1:]:
-                                acc += h.get_tensor(k).float()
-                            acc *= inv                                                   # true 1/N mean (Q1)
-                            m1, u1 = nesterov_step({k: acc}, None if prev_momentum is None else {k: prev_momentum[k]},
-                                                   cfg.optimizer.learning_rate, cfg.optimizer.momentum)
-                            new_m[k], upd[k] = m1[k].contiguous(), u1[k].contiguous()
-                            cum[k] = (cum[k] + upd[k]) if k in cum else upd[k].clone()
-                        del handles
-                        save_file(upd, out)
-                        save_file(new_m, os.path.join(work_dir, "momentum"))
-                        save_file({k: v.contiguous() for k, v in cum.items()}, cum_path)
-                        return new_m
-
-                    momentum = await asyncio.get_event_loop().run_in_executor(None, reduce_and_step)
+                    stats = await asyncio.get_event_loop().run_in_executor(
+                        None, lambda: outer_round(paths, work_dir, cfg.optimizer.learning_rate, cfg.optimizer.momentum))
+                    out = stats["path"]
+                    self.log(f"[ps {spec.job_id[:8]}] round {rnd}: reduced {len(paths)} x {stats['elements']} elements in "
+                             f"{stats['seconds'] * 1e3:.1f} ms ({'native, ' + str(stats['threads']) + ' threads' if stats['native'] else 'torch fallback'})")
                     # Tell the scheduler the round is complete BEFORE distributing the result: a worker
                     # that gets its file early would otherwise ack ("update-received") against the old
                     # round number and be told to continue (the reference sends results first,

@@ -2,7 +2,8 @@
 # Sanitizer / race-detection targets (the reference has none: SURVEY 5.2).
 #
 #   tools/sanitize.sh core      ASAN+UBSAN build of the C++ control-plane core, runs tests/test_core.py (CPU)
-#   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model (CPU)
+#   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model and of the
+#                               parameter-server reducer (+ ASAN/UBSAN over the latter) (CPU)
 #   tools/sanitize.sh memcheck  compute-sanitizer --tool memcheck  over the kernel numerics tests (GPU box)
 #   tools/sanitize.sh racecheck compute-sanitizer --tool racecheck (shared-memory hazards; GPU box)
 #   tools/sanitize.sh synccheck compute-sanitizer --tool synccheck (barrier misuse; GPU box)
@@ -36,6 +37,13 @@ case "${1:-core}" in
     $SCXX -O1 -g -std=c++17 -fsanitize=thread -fno-omit-frame-pointer -I hypha_b200/csrc \
         tools/tsan_flag_barrier.cpp -o "$OUT/tsan_flag_barrier" -pthread
     "$OUT/tsan_flag_barrier"
+    $SCXX -O1 -g -std=c++17 -fsanitize=thread -fno-omit-frame-pointer -I hypha_b200/csrc \
+        tools/tsan_ps_reduce.cpp -o "$OUT/tsan_ps_reduce" -pthread
+    "$OUT/tsan_ps_reduce"
+    # the same driver under ASAN+UBSAN: mmap bounds and unaligned tensor data
+    $SCXX -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -I hypha_b200/csrc \
+        tools/tsan_ps_reduce.cpp -o "$OUT/asan_ps_reduce" -pthread
+    ASAN_OPTIONS=detect_leaks=1 "$OUT/asan_ps_reduce"
     ;;
   memcheck|racecheck|synccheck)
     command -v compute-sanitizer >/dev/null 2>&1 || { echo "compute-sanitizer not found" >&2; exit 1; }
