@@ -36,6 +36,8 @@ from ..telemetry.bandwidth import BandwidthCounters
 
 MAX_FRAME = 64 << 20
 STREAM_CHUNK = 1 << 20
+SPLIT_BIT = 1 << 31              # length-prefix flag of a bulk stream_data frame (raw payload after a CBOR header)
+SPLIT_FRAME_MIN = 4096
 STREAM_ACCEPT_LIMIT = 8          # stream_push.rs:56, stream_pull.rs:71
 EARLY_STREAM_TTL_S = 30.0        # how long a push stream waits for its receiver to register
 
@@ -99,7 +101,7 @@ class MemoryLink(Link):
         if self.closed or self.other is None or self.other.closed:
             raise NetworkError("link closed")
         data = cbor2.dumps(frame)            # same bytes a socket would carry (counted + isolation)
-        await self.other._deliver(cbor2.loads(data), self.other)
+        await self.other._deliver(cbor2.loads(data), self.other, None, len(data))
         return len(data)
 
     async def close(self) -> None:
@@ -117,19 +119,40 @@ class SocketLink(Link):
     async def send(self, frame: dict) -> int:
         if self.closed:
             raise NetworkError("link closed")
-        data = cbor2.dumps(frame)
+        payload = frame.get("data") if frame.get("t") == "stream_data" else None
+        if payload is not None and len(payload) >= SPLIT_FRAME_MIN:
+            # bulk chunk: [len | SPLIT_BIT][meta len][CBOR of the frame without "data"][raw bytes] -- the chunk
+            # is handed to the socket as is instead of being copied into a CBOR byte string and a joined frame
+            meta = cbor2.dumps({k: v for k, v in frame.items() if k != "data"})
+            total = 4 + len(meta) + len(payload)
+            parts = [struct.pack("<II", total | SPLIT_BIT, len(meta)), meta, payload]
+        else:
+            data = cbor2.dumps(frame)
+            total = len(data)
+            parts = [struct.pack("<I", total), data]
         async with self._wlock:
-            self.writer.write(struct.pack("<I", len(data)) + data)
+            self.writer.writelines(parts)
             await self.writer.drain()
-        return len(data)
+        return total
 
-    async def recv(self) -> Optional[dict]:
+    async def recv(self) -> Optional[Tuple[dict, int]]:
+        """``(frame, wire bytes)`` or None when the connection ended."""
         try:
             hdr = await self.reader.readexactly(4)
             (n,) = struct.unpack("<I", hdr)
+            split = bool(n & SPLIT_BIT)
+            n &= ~SPLIT_BIT
             if n > MAX_FRAME:
                 raise NetworkError("frame too large")
-            return cbor2.loads(await self.reader.readexactly(n))
+            buf = await self.reader.readexactly(n)
+            if not split:
+                return cbor2.loads(buf), n
+            (m,) = struct.unpack_from("<I", buf, 0)
+            if 4 + m > n:
+                raise NetworkError("malformed bulk frame")
+            frame = cbor2.loads(buf[4:4 + m])
+            frame["data"] = memoryview(buf)[4 + m:]          # no copy: the consumer writes it to its file
+            return frame, n
         except (asyncio.IncompleteReadError, ConnectionError, OSError):
             return None
 
@@ -290,10 +313,10 @@ class Network:
 
     async def _socket_loop(self, link: SocketLink) -> None:
         while not link.closed:
-            frame = await link.recv()
-            if frame is None:
+            got = await link.recv()
+            if got is None:
                 break
-            await self._on_frame(frame, link)
+            await self._on_frame(got[0], link, None, got[1])
         await self._drop_link(link)
 
     async def _drop_link(self, link: Link) -> None:
@@ -406,13 +429,15 @@ class Network:
         await self._send(link, frame, protocol)
 
     # -- frame dispatch -------------------------------------------------------------------------------
-    async def _on_frame(self, frame: dict, link: Link, src_override: Optional[str] = None) -> None:
+    async def _on_frame(self, frame: dict, link: Link, src_override: Optional[str] = None,
+                        size: Optional[int] = None) -> None:
         t = frame.get("t")
         src = src_override or link.peer_id
-        try:
-            size = len(cbor2.dumps(frame))
-        except Exception:
-            size = 0
+        if size is None:                       # inner frame of a relayed one: only the outer size is known
+            try:
+                size = len(cbor2.dumps(frame))
+            except Exception:
+                size = 0
         self.counters.add(frame.get("proto") or f"/hypha-frame/{t}", inbound=size)
         if t == "hello":
             peer = frame["peer"]
@@ -438,7 +463,7 @@ class Network:
         elif t == "relay":
             dst = frame["dst"]
             if dst == self.peer_id:
-                await self._on_frame(frame["inner"], link, src_override=frame["src"])
+                await self._on_frame(frame["inner"], link, frame["src"], size)
             elif self.relay_server and dst in self.links:
                 await self._send(self.links[dst], frame, "/hypha-relay")
             # else: drop (no route)

@@ -429,3 +429,32 @@ def test_push_stream_waits_for_a_late_receiver():
         await b.close()
 
     asyncio.run(main())
+
+
+def test_bulk_frames_keep_payload_and_count_wire_bytes():
+    """Stream chunks >= 4 KiB travel as split frames (CBOR header + raw payload, no re-encoding on either
+    side); smaller ones as plain CBOR.  Both arrive intact, also interleaved with requests on the same link,
+    and the bandwidth counters see the bytes that were on the wire."""
+    from hypha_b200.transport.network import SPLIT_FRAME_MIN
+
+    async def main():
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = await pair("unix", tmp)
+            a.on("/echo/1", None, lambda peer, m: _echo(m))
+            rx = a.streams_push(job_id="j")
+            sizes = [0, 1, SPLIT_FRAME_MIN - 1, SPLIT_FRAME_MIN, (1 << 20) - 1, (1 << 20) + 1, 5 * (1 << 20) + 3]
+            for n in sizes:
+                payload = os.urandom(n)
+                push = asyncio.ensure_future(b.stream_push("A", payload, job_id="j"))
+                echo = asyncio.ensure_future(b.request("A", "/echo/1", {"n": n}))
+                st = await rx.get()
+                got = await st.read_all()
+                assert await push == n and got == payload, n
+                assert (await echo) == {"n": n}
+            snap = a.counters.snapshot()["hypha.bandwidth.inbound.bytes"]["/hypha-tensor-stream/push"]
+            assert sum(sizes) < snap < sum(sizes) + 4096 * len(sizes)
+            await a.close(); await b.close()
+
+    async def _echo(m):
+        return m
+    run(main())
