@@ -237,3 +237,15 @@ def test_lr_schedules_match_transformers():
         assert spans[0][0] == 0 and sum(l for _, l in spans) == total
         assert all(b % 1024 == 0 for b, _ in spans if b < total)
         assert all(spans[i][0] + spans[i][1] == spans[i + 1][0] or spans[i + 1][1] == 0 for i in range(world - 1))
+
+
+def test_cli_reference_is_up_to_date():
+    """docs/cli.md is generated from the parsers (`tools/gen_cli_docs.py`); a flag added without regenerating
+    the reference fails here."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_cli_docs.py"), "--check"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
