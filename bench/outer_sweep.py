@@ -21,7 +21,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from hypha_b200.parallel.diloco import AdamWConfig, DiLoCoConfig, DiLoCoOuter, FlatAdamW  # noqa: E402
+from hypha_b200.parallel.diloco import DiLoCoConfig, DiLoCoOuter  # noqa: E402
 from hypha_b200.parallel.peer_memory import PeerGroup  # noqa: E402
 
 PEER_COPY_GBS, NVLINK_NOMINAL_GBS = 770.0, 900.0
