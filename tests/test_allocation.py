@@ -227,3 +227,21 @@ def test_collective_membership_barrier_semantics():
         assert all(r.membership["joined"] == [] and r.membership["generation"] == 2 for r in rs)
 
     asyncio.run(main())
+
+
+def test_allocation_scales_to_hundreds_of_workers():
+    """256 arbiters behind one gateway answer one ad; the allocator collects one offer per peer, accepts all of
+    them by renewal and returns early -- in well under the 5 s deadline (the 200 ms ad window dominates)."""
+    async def main():
+        n = 256
+        gw, sched, workers = await _cluster([(f"w{i:03d}", 8, 10.0 + i % 7, 1.0, "flexible") for i in range(n)])
+        alloc = GreedyWorkerAllocator(sched)
+        t0 = time.perf_counter()
+        handles = await alloc.request(SPEC, bid=50.0, max_price=100.0, num=n, deadline_s=5.0)
+        dt = time.perf_counter() - t0
+        assert len({h.peer_id for h in handles}) == n and dt < 3.0, dt
+        assert all(h.renewals >= 1 for h in handles)
+        for h in handles:
+            await h.release()
+        await _teardown(gw, sched, workers)
+    asyncio.run(main())
