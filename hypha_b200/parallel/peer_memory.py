@@ -56,6 +56,31 @@ class SymmetricBuffer:
         return self.numel * _DT_SIZE[self.dtype]
 
 
+def store_exchange(store, rank: int, world: int, prefix: str = "hb-xchg", timeout_s: float = 120.0) -> Callable[[object], List[object]]:
+    """Control-plane all-gather over a key-value store (``torch.distributed.TCPStore`` or anything with
+    ``set`` / ``get`` / ``wait``): needs no process group, so a membership generation that contains a
+    replacement PROCESS can use it (a torch process group cannot admit one).  Every call of the returned
+    function is one round; all ``world`` ranks must make the same sequence of calls."""
+    import pickle
+    from datetime import timedelta
+
+    seq = [0]
+
+    def exchange(obj):
+        n = seq[0]
+        seq[0] += 1
+        store.set(f"{prefix}/{n}/{rank}", pickle.dumps(obj))
+        keys = [f"{prefix}/{n}/{r}" for r in range(world)]
+        store.wait(keys, timedelta(seconds=timeout_s))
+        return [pickle.loads(store.get(k)) for k in keys]
+
+    return exchange
+
+
+class RebindError(RuntimeError):
+    pass
+
+
 class PeerGroup:
     """Ranks of one box that share symmetric buffers.
 
@@ -69,6 +94,7 @@ class PeerGroup:
                  local_devices: Optional[Sequence[int]] = None):
         self.rank, self.world, self.device = rank, world, device
         self._exchange = exchange
+        self.deferred = False        # a joining process allocates locally first and maps peers in rebind()
         self._local_devices = list(local_devices) if local_devices is not None else None
         self.buffers: Dict[str, SymmetricBuffer] = {}
         self.counters = BandwidthCounters()
@@ -106,6 +132,8 @@ class PeerGroup:
         buf = SymmetricBuffer(name, numel, dtype, local)
         if self.world == 1:
             buf.peer_ptrs = [ptr]
+        elif self.deferred:
+            buf.peer_ptrs = [ptr if r == self.rank else 0 for r in range(self.world)]
         else:
             handles = self._exchange((self.rank, C.ipc_export(ptr)))
             ptrs = [0] * self.world
@@ -120,6 +148,66 @@ class PeerGroup:
             buf.peer_ptrs = ptrs
         self.buffers[name] = buf
         return buf
+
+    @classmethod
+    def joining(cls, rank: int, world: int, device: int) -> "PeerGroup":
+        """The group handle of a replacement process: ``alloc`` creates the local buffers only (the survivors
+        are not allocating anything, so there is nobody to exchange with); ``rebind`` then maps the peers."""
+        g = cls(rank, world, device, None)
+        g.deferred = True
+        return g
+
+    def rebind(self, exchange: Callable[[object], List[object]], replaced: Sequence[int]) -> None:
+        """Collective over the processes of a NEW membership generation (same rank numbering, ``replaced`` =
+        ranks whose process is new): every rank publishes IPC handles of all its buffers; survivors drop
+        their mappings of the dead processes' buffers and open the newcomers', newcomers open everybody's.
+        Mappings between two survivors are left alone.  Kernels pick the new addresses up at their next
+        launch (pointer tables are read from ``SymmetricBuffer.peer_ptrs``).  NVLS buffers cannot be
+        re-bound (the multicast team is fixed): run elastic GPU jobs with ``HYPHA_NVLS=0``."""
+        C = load_C()
+        replaced = sorted(set(int(r) for r in replaced))
+        self._exchange = exchange
+        names = sorted(self.buffers)
+        for n in names:
+            if getattr(self.buffers[n], "mc_ptr", 0):
+                raise RebindError(f"buffer {n!r} is bound to an NVSwitch multicast object and cannot be re-bound")
+        mine = {n: (self.buffers[n].numel, str(self.buffers[n].dtype), C.ipc_export(self.buffers[n].local.data_ptr()))
+                for n in names}
+        table = dict(exchange((self.rank, mine)))
+        if sorted(table) != list(range(self.world)):
+            raise RebindError(f"membership exchange returned ranks {sorted(table)}, expected 0..{self.world - 1}")
+        problems = []
+        for r, bufs in table.items():
+            if sorted(bufs) != names:
+                problems.append(f"rank {r} holds buffers {sorted(bufs)}, this rank {names}")
+                continue
+            for n in names:
+                if tuple(bufs[n][:2]) != (self.buffers[n].numel, str(self.buffers[n].dtype)):
+                    problems.append(f"rank {r} buffer {n!r} is {bufs[n][:2]}, here {(self.buffers[n].numel, str(self.buffers[n].dtype))}")
+        # agree on the verdict before anybody changes a mapping
+        verdicts = exchange(problems[:3])
+        bad = [p for v in verdicts for p in v]
+        if bad:
+            raise RebindError("; ".join(bad[:3]))
+        i_am_new = self.rank in replaced
+        for r in range(self.world):
+            if r == self.rank or not (i_am_new or r in replaced):
+                continue
+            for n in names:
+                buf = self.buffers[n]
+                old = buf.peer_ptrs[r] if r < len(buf.peer_ptrs) else 0
+                if old and old in self._opened:
+                    try:
+                        C.ipc_close(old)            # the exporting process is gone; the mapping is stale
+                    except Exception:
+                        pass
+                    self._opened.remove(old)
+                with torch.cuda.device(self.device):
+                    p = C.ipc_open(table[r][n][2])
+                self._opened.append(p)
+                buf.peer_ptrs[r] = p
+        self.deferred = False
+        exchange(self.rank)                           # nobody launches before every mapping exists
 
     def pull(self, src_rank: int, name: str, num_ctas: int = 0) -> None:
         """Copy rank ``src_rank``'s copy of ``name`` into the local copy over NVLink
