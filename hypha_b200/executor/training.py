@@ -20,7 +20,7 @@ import argparse
 import json
 import os
 import time
-from typing import Any, Dict, Iterator, Optional
+from typing import Any, Dict, Iterator, List, Optional
 
 import torch
 
@@ -294,11 +294,17 @@ class ReplicatedNesterov:
             loop.prev[k] = v.detach().clone()
 
 
+def gpu_join_enabled() -> bool:
+    """Replacement processes may join the fused GPU engine (`_TrainerEngine._admit`).  Off by default until
+    the path has run on a multi-GPU box; the host-side protocol is covered by tests/test_peer_rebind.py."""
+    return os.environ.get("HYPHA_GPU_JOIN", "0") == "1"
+
+
 class _TrainerEngine:
     """Llama on a B200: the public DiLoCoTrainer (flat buffers in peer memory, fused AdamW, fused
     NVLink outer step)."""
 
-    def __init__(self, local: str, config: dict, coll: dict, dev_index: int):
+    def __init__(self, local: str, config: dict, coll: dict, dev_index: int, joining: bool = False):
         from ..models.llama import LlamaConfig
         from ..parallel.diloco import AdamWConfig, DiLoCoConfig
         from ..parallel.peer_memory import PeerGroup
@@ -318,7 +324,15 @@ class _TrainerEngine:
         outer = coll.get("outer") or {}
         diloco = DiLoCoConfig(inner_steps=1 << 62, outer_lr=float(outer.get("learning-rate", 0.7)),
                               outer_momentum=float(outer.get("momentum", 0.9)))
-        group = PeerGroup.from_torch_distributed(dev_index) if coll["world"] > 1 else None
+        self.joining = joining          # a replacement PROCESS: maps its peers in _admit(), trains afterwards
+        self._pending: List[int] = []   # slots of newcomers to admit after the coming outer step
+        self._mem: Optional[dict] = None
+        self._me = coll.get("peer")
+        if joining:
+            # the dead rank's number and the ORIGINAL world size: shard ownership is by rank
+            group = PeerGroup.joining(int(coll["slot"]), int(coll["slots_world"]), dev_index)
+        else:
+            group = PeerGroup.from_torch_distributed(dev_index) if coll["world"] > 1 else None
         self.trainer = DiLoCoTrainer.create(cfg, adamw=adamw, diloco=diloco, group=group, device=dev_index,
                                             seed=int(meta.get("seed", 0)), scheduler=config.get("scheduler"))
         weights = os.path.join(local, "model.safetensors")
@@ -341,13 +355,66 @@ class _TrainerEngine:
         if outer.backend != "fused":
             return
         alive = set(membership["members"])
-        dead = [i for i, p in enumerate(coll.get("peers", [])) if p not in alive and i in outer.members()]
+        slots = membership.get("slots") or {}
+        self._mem = membership
+        if self.joining:
+            return                       # nothing mapped yet: everything happens in _admit()
+        # ranks by slot (stable numbering); the dispatch-time peer list gives the slots of the first generation
+        by_slot = {i: p for i, p in enumerate(coll.get("peers", []))}
+        by_slot.update({int(v): k for k, v in slots.items()})
+        joined = [int(slots[p]) for p in (membership.get("joined") or []) if p in slots]
+        dead = [i for i in outer.members() if by_slot.get(i) not in alive or i in joined]
         if dead:
             outer.drop_ranks(dead)
             print(f"membership generation {membership['generation']}: continuing without ranks {dead}", flush=True)
+        if joined and gpu_join_enabled():
+            self._pending = joined
+
+    def _admit(self) -> None:
+        """Round boundary with newcomers (HYPHA_GPU_JOIN=1): the survivors have just finished their outer step.
+        All members of the new generation meet on a TCPStore at the generation's rendezvous (no process group:
+        a torch group cannot admit a process), re-bind the peer-memory mappings (`PeerGroup.rebind`), hand the
+        newcomers' shards back and align the flag epoch; a newcomer then pulls the current weights from the
+        lowest surviving rank over NVLink and rebuilds master / anchor / its outer shard (`reseed_from`)."""
+        from datetime import timedelta
+        from urllib.parse import urlparse
+
+        import torch.distributed as dist
+
+        from ..parallel.peer_memory import store_exchange
+
+        mem, outer = self._mem, self.trainer.outer
+        slots = {k: int(v) for k, v in (mem.get("slots") or {}).items() if k in mem["members"]}
+        order = sorted(slots.values())
+        me = outer.rank
+        new = sorted(int(slots[p]) for p in (mem.get("joined") or []) if p in slots)
+        survivors = [r for r in order if r not in new]
+        u = urlparse(mem["rendezvous"])
+        store = dist.TCPStore(u.hostname, u.port, len(order), me == survivors[0], timedelta(seconds=120),
+                              wait_for_workers=False)
+        exchange = store_exchange(store, order.index(me), len(order), prefix=f"gen{mem['generation']}")
+        outer.group.rebind(exchange, new, members=order)
+        if self.joining:
+            outer.set_members(order)
+        else:
+            for r in new:
+                outer.readmit(r)
+        rounds = exchange(int(outer.round))
+        outer.round = max(int(r) for r in rounds)
+        outer.sync_epoch()
+        if self.joining:
+            outer.reseed_from(survivors[0])
+            torch.cuda.synchronize()
+        exchange("ready")                 # nobody launches the next outer step before the newcomers are seeded
+        self._store = store               # keep the exchange alive for later sync_epoch calls
+        print(f"membership generation {mem['generation']}: ranks {new} admitted into the fused engine", flush=True)
+        self._pending, self.joining = [], False
 
     def outer_step(self, round_no: int = -1) -> None:
         outer = self.trainer.outer
+        if self.joining:
+            self._admit()                 # the survivors run this round's outer step without the newcomer
+            return
         if outer.backend == "fused":
             # a rank that never shows up costs one barrier timeout, then the survivors adopt its shard
             # and go on (DiLoCoOuter.step_resilient); raises only if the step cannot be completed
@@ -355,6 +422,8 @@ class _TrainerEngine:
             outer.step_resilient()
             if outer.members() != before:
                 print(f"outer step continued without ranks {sorted(set(before) - set(outer.members()))}", flush=True)
+            if self._pending:
+                self._admit()
         else:
             self.trainer.outer_step()
 
@@ -439,9 +508,11 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     if use_cuda:
         torch.cuda.set_device(dev_index)
     device = f"cuda:{dev_index}" if use_cuda else "cpu"
-    if coll.get("join") and use_cuda:
-        raise RuntimeError("joining a running collective job is implemented for the CPU (gloo) engine only")
-    if world > 1 and use_cuda:
+    gpu_join = bool(coll.get("join")) and use_cuda
+    if gpu_join and not gpu_join_enabled():
+        raise RuntimeError("joining a running collective job on GPUs is experimental: set HYPHA_GPU_JOIN=1 on every "
+                           "worker of the job (and HYPHA_NVLS=0); the CPU (gloo) engine joins without it")
+    if world > 1 and use_cuda and not gpu_join:
         from datetime import timedelta
 
         # GPUs: the default NCCL group (the peer-memory handle exchange of the fused path runs over it)
@@ -452,7 +523,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     local = os.path.join(work_dir, FETCH_PATH)
     family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
     if use_cuda and family == "llama":
-        engine = _TrainerEngine(local, config, coll, dev_index)
+        engine = _TrainerEngine(local, config, coll, dev_index, joining=gpu_join)
     elif coll.get("join"):
         engine = _GenericEngine(local, config, coll, device, _Group("solo", None, 0, 1))   # regrouped at its first barrier
     else:

@@ -157,12 +157,14 @@ class PeerGroup:
         g.deferred = True
         return g
 
-    def rebind(self, exchange: Callable[[object], List[object]], replaced: Sequence[int]) -> None:
+    def rebind(self, exchange: Callable[[object], List[object]], replaced: Sequence[int],
+               members: Optional[Sequence[int]] = None) -> None:
         """Collective over the processes of a NEW membership generation (same rank numbering, ``replaced`` =
         ranks whose process is new): every rank publishes IPC handles of all its buffers; survivors drop
         their mappings of the dead processes' buffers and open the newcomers', newcomers open everybody's.
         Mappings between two survivors are left alone.  Kernels pick the new addresses up at their next
-        launch (pointer tables are read from ``SymmetricBuffer.peer_ptrs``).  NVLS buffers cannot be
+        launch (pointer tables are read from ``SymmetricBuffer.peer_ptrs``).  ``members`` = the ranks that
+        take part (default: all ``world``; ranks whose slot is vacant are skipped).  NVLS buffers cannot be
         re-bound (the multicast team is fixed): run elastic GPU jobs with ``HYPHA_NVLS=0``."""
         C = load_C()
         replaced = sorted(set(int(r) for r in replaced))
@@ -174,8 +176,9 @@ class PeerGroup:
         mine = {n: (self.buffers[n].numel, str(self.buffers[n].dtype), C.ipc_export(self.buffers[n].local.data_ptr()))
                 for n in names}
         table = dict(exchange((self.rank, mine)))
-        if sorted(table) != list(range(self.world)):
-            raise RebindError(f"membership exchange returned ranks {sorted(table)}, expected 0..{self.world - 1}")
+        expect = sorted(int(m) for m in members) if members is not None else list(range(self.world))
+        if sorted(table) != expect:
+            raise RebindError(f"membership exchange returned ranks {sorted(table)}, expected {expect}")
         problems = []
         for r, bufs in table.items():
             if sorted(bufs) != names:
@@ -190,7 +193,7 @@ class PeerGroup:
         if bad:
             raise RebindError("; ".join(bad[:3]))
         i_am_new = self.rank in replaced
-        for r in range(self.world):
+        for r in expect:
             if r == self.rank or not (i_am_new or r in replaced):
                 continue
             for n in names:

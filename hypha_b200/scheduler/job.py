@@ -259,13 +259,19 @@ class DiLoCoJobRun:
             if self.collective:
                 # joins at the next `update` barrier: the survivors re-form their group with it and rank 0
                 # broadcasts the current model and outer momentum (CPU engine; see executor/training.py)
+                # `slot`: the rank number it takes over (engines that shard state by rank: the fused GPU step)
                 tcfg.collective = {"rank": -1, "world": len(self.live) + 1, "rendezvous": None,
                                    "outer": self.nesterov.to_wire(), "peer": h.peer_id,
                                    "peers": [w.peer_id for w in self.workers], "join": True,
-                                   "after_round": self.batch.round}
+                                   "after_round": self.batch.round, "slot": self.batch.reserve_slot(h.peer_id),
+                                   "slots_world": len(self.workers)}
             else:
                 tcfg.join = {"after_round": self.batch.round, "replaces": lost}
-            await self._dispatch_train(h, tcfg)
+            try:
+                await self._dispatch_train(h, tcfg)
+            except BaseException:
+                self.batch.release_slot(h.peer_id)
+                raise
             self.live.append(h.peer_id)
             self.joined.append(h.peer_id)
             if self.collective:

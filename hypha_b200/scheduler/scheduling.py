@@ -39,6 +39,7 @@ class BatchSchedulerService:
         # collective jobs (enable_collective): `update` is a barrier over the CURRENT members; its answer
         # tells every rank who takes part in the outer step, so survivors never wait for a dead rank
         self._members: Optional[List[str]] = None
+        self._slots: Dict[str, int] = {}       # member -> stable rank slot (a replacement takes a freed slot)
         self._generation = 0
         self._rendezvous_factory: Optional[Callable[[], str]] = None
         self._rendezvous: Optional[str] = None
@@ -69,6 +70,7 @@ class BatchSchedulerService:
         self.sched.tracker.worker_tracker.remove_worker(peer)
         if self._members is not None and peer in self._members:
             self._members = [m for m in self._members if m != peer]
+            self._slots.pop(peer, None)
             self._joiners = [j for j in self._joiners if j != peer]
             self._generation += 1
             self._rendezvous = self._rendezvous_factory() if self._rendezvous_factory else None
@@ -78,6 +80,19 @@ class BatchSchedulerService:
         """Collective aggregation: remember the rank order and hand out a fresh rendezvous address every
         time the membership changes (the survivors re-form their process group on it)."""
         self._members, self._rendezvous, self._rendezvous_factory = list(members), rendezvous, rendezvous_factory
+        self._slots = {m: i for i, m in enumerate(self._members)}
+
+    def reserve_slot(self, peer: str) -> int:
+        """The rank number a replacement will run under (lowest free one; needed BEFORE it is dispatched:
+        engines that shard state by rank build their shard from it).  Kept by `add_member`."""
+        if peer not in self._slots:
+            taken = set(self._slots.values())
+            self._slots[peer] = next(i for i in range(len(taken) + 1) if i not in taken)
+        return self._slots[peer]
+
+    def release_slot(self, peer: str) -> None:
+        if self._members is None or peer not in self._members:
+            self._slots.pop(peer, None)
 
     def add_member(self, peer: str) -> None:
         """Collective jobs: a replacement rank joins at the next `update` barrier (it is reported in
@@ -85,6 +100,9 @@ class BatchSchedulerService:
         if self._members is None or peer in self._members:
             return
         self._members.append(peer)
+        # engines whose state is sharded BY RANK (the fused GPU outer step) need the newcomer to take over a
+        # dead rank's number: lowest free slot first, a new one only when the group grows
+        self.reserve_slot(peer)
         self._joiners.append(peer)
         self._generation += 1
         self._rendezvous = self._rendezvous_factory() if self._rendezvous_factory else None
@@ -137,7 +155,8 @@ class BatchSchedulerService:
                 await self._cond.wait_for(lambda: self._barrier_complete(rnd))
             resp.membership = {"generation": self._generation, "members": list(self._members),
                                "rendezvous": self._rendezvous, "round": rnd,
-                               "joined": [j for j in self._joiners if j in self._members]}
+                               "joined": [j for j in self._joiners if j in self._members],
+                               "slots": {m: self._slots[m] for m in self._members if m in self._slots}}
             self._released.setdefault(rnd, set()).add(peer)
             if self._released[rnd] >= set(self._members):
                 # everybody has the answer of this round's barrier: the newcomers are regular members now

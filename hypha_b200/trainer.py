@@ -67,7 +67,8 @@ class DiLoCoTrainer:
         if want_fused:
             holders = {}
             nvls_mode = os.environ.get("HYPHA_NVLS", "1")      # "0" off | "1" after a local pre-flight | "force"
-            use_nvls = nvls_mode != "0" and group.world >= 4
+            # a joining process allocates alone (PeerGroup.joining): no collective NVLS set-up
+            use_nvls = nvls_mode != "0" and group.world >= 4 and not getattr(group, "deferred", False)
 
             def sym_alloc(name, n, dt):
                 """NVLS (multicast-bound VMM) buffer when the fabric supports it, else CUDA-IPC.  All

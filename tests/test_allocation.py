@@ -199,6 +199,7 @@ def test_collective_membership_barrier_semantics():
             assert r.type == "Ok" and r.membership["generation"] == 1 and r.membership["members"] == ["a", "b"]
             assert r.membership["joined"] == [] and r.membership["round"] == 0
             assert r.membership["rendezvous"] == "tcp://127.0.0.1:40000"
+            assert r.membership["slots"] == {"a": 0, "b": 1}                   # c's slot 2 is free now
         assert (await svc.handle("a", M.Progress("updated"))).type == "Ok"
         assert (await svc.handle("b", M.Progress("updated"))).type == "Ok"          # idempotent
         assert svc.round == 1
@@ -217,6 +218,8 @@ def test_collective_membership_barrier_semantics():
         for r in (ra, rb, rd):
             assert r.membership["generation"] == 2 and r.membership["members"] == ["a", "b", "d"]
             assert r.membership["joined"] == ["d"] and r.membership["round"] == 1
+            # stable rank numbering for engines that shard state by rank: d took over the dead rank's slot
+            assert r.membership["slots"] == {"a": 0, "b": 1, "d": 2}
         await svc.handle("a", M.Progress("updated"))
         for w in ("a", "b", "d"):
             await svc.handle(w, M.Progress("update-received"))

@@ -193,3 +193,100 @@ def test_store_exchange_over_a_tcp_store():
     for a, b in res:
         assert [x["rank"] for x in a] == [0, 1, 2] and [len(x["blob"]) for x in a] == [1, 2, 3]
         assert b == [0, 10, 20]
+
+
+def test_rebind_with_a_vacant_slot(fake):
+    """4 slots, rank 1 and rank 3 died, only rank 3 is replaced: rank 1's slot stays vacant."""
+    C, world = fake, 4
+    groups = _group_of(world, C, SHAPES)
+    for d in (1, 3):
+        for name in SHAPES:
+            C.allocs[groups[d].buffers[name].local.data_ptr()] = False
+    new = pm.PeerGroup.joining(3, world, 3)
+    for name, (n, dt) in SHAPES.items():
+        new.alloc(name, n, dt)
+    members = [groups[0], groups[2], new]
+    slots = [0, 2, 3]
+    make = _barrier_exchange(3)
+    res = _in_threads([lambda g=g, i=i: g.rebind(make(i), [3], members=slots) for i, g in enumerate(members)])
+    assert res == [None] * 3, res
+    for g in members:
+        for name in SHAPES:
+            for x in members:
+                assert _resolve(C, g, name, x.rank) == x.buffers[name].local.data_ptr()
+    assert new.buffers["model.params"].peer_ptrs[1] == 0          # nothing mapped for the vacant slot
+
+
+def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
+    """`_TrainerEngine.regroup` + `_admit` (HYPHA_GPU_JOIN=1) with the real DiLoCoOuter membership methods, a
+    real TCPStore rendezvous and the fake IPC layer: 4 slots, rank 2's process is replaced.  Survivors hand the
+    shard back and keep their mutual mappings; the newcomer maps everyone, takes the survivors' round and flag
+    epoch and reseeds from the lowest surviving rank."""
+    import socket
+
+    from hypha_b200.executor import training as T
+    from hypha_b200.parallel.diloco import DiLoCoOuter
+
+    monkeypatch.setenv("HYPHA_GPU_JOIN", "1")
+    monkeypatch.setattr(T.torch.cuda, "synchronize", lambda *a, **k: None)
+    C, world, dead = fake, 4, 2
+    groups = _group_of(world, C, SHAPES)
+    peers = ["w0", "w1", "w2", "w3"]
+    reseeded = []
+
+    def make_outer(group, rank, round_no, attempt, members):
+        o = object.__new__(DiLoCoOuter)
+        o.world, o.rank, o.group, o.round, o.attempt, o.backend = world, rank, group, round_no, attempt, "fused"
+        o.n, o.segments = 4096 * world, {rank: ("own",)}
+        o.set_members(members)
+        o.reseed_from = lambda src, r=rank: reseeded.append((r, src))
+        return o
+
+    def make_engine(outer, joining, me):
+        e = object.__new__(T._TrainerEngine)
+        e.trainer = types.SimpleNamespace(outer=outer)
+        e.joining, e._pending, e._mem, e._me = joining, [], None, me
+        return e
+
+    # survivors have already dropped rank 2 (its lease was lost a round ago); rank 3 adopted its shard
+    engines = {}
+    for r in (0, 1, 3):
+        o = make_outer(groups[r], r, round_no=5, attempt=17 + r, members=[0, 1, 3])
+        if r == 3:
+            o.segments[dead] = ("adopted",)
+        engines[r] = make_engine(o, False, peers[r])
+    for name in SHAPES:
+        C.allocs[groups[dead].buffers[name].local.data_ptr()] = False
+    new_group = pm.PeerGroup.joining(dead, world, dead)
+    for name, (n, dt) in SHAPES.items():
+        new_group.alloc(name, n, dt)
+    engines[dead] = make_engine(make_outer(new_group, dead, round_no=0, attempt=0, members=[0, 1, 2, 3]), True, "w9")
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mem = {"generation": 3, "members": ["w0", "w1", "w3", "w9"], "joined": ["w9"], "round": 5,
+           "rendezvous": f"tcp://127.0.0.1:{port}", "slots": {"w0": 0, "w1": 1, "w3": 3, "w9": 2}}
+    coll = {"peers": peers, "peer": None}
+    stepped = []
+
+    def run(r):
+        e = engines[r]
+        e.regroup(mem, coll)
+        if not e.joining:
+            assert e._pending == [dead]
+            e.trainer.outer.step_resilient = lambda r=r: stepped.append(r)      # the survivors' own outer step
+        e.outer_step(6)
+        return True
+    res = _in_threads([lambda r=r: run(r) for r in (0, 1, 2, 3)])
+    assert res == [True] * 4, res
+    assert sorted(stepped) == [0, 1, 3] and reseeded == [(dead, 0)]
+    members = {0: groups[0], 1: groups[1], 2: new_group, 3: groups[3]}
+    for r, e in engines.items():
+        o = e.trainer.outer
+        assert o.members() == [0, 1, 2, 3] and o.round == 5 and o.attempt == 20 and not e.joining and not e._pending
+        for name in SHAPES:
+            assert [_resolve(C, members[r], name, x) for x in range(world)] == \
+                   [members[x].buffers[name].local.data_ptr() for x in range(world)]
+    assert dead not in engines[3].trainer.outer.segments                       # the adopter gave the shard back
