@@ -388,24 +388,12 @@ class _TrainerEngine:
         order = sorted(slots.values())
         me = outer.rank
         new = sorted(int(slots[p]) for p in (mem.get("joined") or []) if p in slots)
-        survivors = [r for r in order if r not in new]
+        survivors = [r for r in order if r not in new]      # the lowest one hosts the store
         u = urlparse(mem["rendezvous"])
         store = dist.TCPStore(u.hostname, u.port, len(order), me == survivors[0], timedelta(seconds=120),
                               wait_for_workers=False)
         exchange = store_exchange(store, order.index(me), len(order), prefix=f"gen{mem['generation']}")
-        outer.group.rebind(exchange, new, members=order)
-        if self.joining:
-            outer.set_members(order)
-        else:
-            for r in new:
-                outer.readmit(r)
-        rounds = exchange(int(outer.round))
-        outer.round = max(int(r) for r in rounds)
-        outer.sync_epoch()
-        if self.joining:
-            outer.reseed_from(survivors[0])
-            torch.cuda.synchronize()
-        exchange("ready")                 # nobody launches the next outer step before the newcomers are seeded
+        outer.admit(exchange, order, new, self.joining)
         self._store = store               # keep the exchange alive for later sync_epoch calls
         print(f"membership generation {mem['generation']}: ranks {new} admitted into the fused engine", flush=True)
         self._pending, self.joining = [], False

@@ -332,6 +332,29 @@ class DiLoCoOuter:
         vals = self.group._exchange(int(self.attempt))
         self.attempt = max(int(v) for v in vals)
 
+    def admit(self, exchange, order: List[int], new: List[int], joining: bool) -> None:
+        """Round boundary at which replacement PROCESSES join (collective over all ranks in ``order``, the
+        survivors right after their outer step).  ``exchange`` is a control-plane all-gather that includes
+        the newcomers (``peer_memory.store_exchange``; a torch process group cannot admit a process).
+        Peer-memory mappings are re-bound, survivors hand the newcomers' shards back, round and flag epoch are
+        agreed; a newcomer (``joining``) then pulls the current weights from the lowest surviving rank over
+        NVLink and rebuilds master / anchor / its outer shard.  The last exchange keeps everybody from
+        launching the next outer step before the newcomers are seeded."""
+        new = sorted(int(r) for r in new)
+        survivors = [r for r in order if r not in new]
+        self.group.rebind(exchange, new, members=order)
+        if joining:
+            self.set_members(order)
+        else:
+            for r in new:
+                self.readmit(r)
+        self.round = max(int(r) for r in exchange(int(self.round)))
+        self.sync_epoch()
+        if joining:
+            self.reseed_from(survivors[0])
+            torch.cuda.synchronize()
+        exchange("ready")
+
     def reseed_from(self, src_rank: int) -> None:
         """(Re)join: pull the current global weights from a live rank over peer memory and rebuild
         every piece of local state that derives from them."""

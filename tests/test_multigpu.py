@@ -100,3 +100,18 @@ def test_collective_job_through_the_control_plane(tmp_path):
             losses.setdefault(r["worker_id"], {})[r["round"]] = r["value"]
     assert set(losses) == {"worker-a", "worker-b"} and all(set(v) == {1, 2, 3} for v in losses.values())
     assert all(0 < v < 12 for w in losses.values() for v in w.values())
+
+
+@pytest.mark.timeout(600)
+def test_replacement_process_joins_the_fused_engine():
+    """Experimental (`HYPHA_RUN_EXPERIMENTAL=1`): a process that was never part of the group takes over a dead
+    rank -- `PeerGroup.rebind` with real IPC handles + `DiLoCoOuter.admit`.  The host-side choreography is
+    covered on CPU by tests/test_peer_rebind.py."""
+    if os.environ.get("HYPHA_RUN_EXPERIMENTAL") != "1":
+        pytest.skip("experimental: set HYPHA_RUN_EXPERIMENTAL=1")
+    if _ngpu() < 3:
+        pytest.skip("needs 3 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "mgpu_join_check.py"), "--world", "3"],
+                       capture_output=True, text=True, timeout=550, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert '"correct": true' in r.stdout
