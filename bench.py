@@ -47,7 +47,8 @@ def parse_args():
                     help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
                          "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
-    ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "cudnn"), choices=["cudnn", "flash2", "tcgen05"])
+    ap.add_argument("--attn", default=os.environ.get("HYPHA_ATTN", "tcgen05"), choices=["cudnn", "flash2", "tcgen05"],
+                    help="tcgen05 = the hand-written flash attention (default); cudnn / flash2 = library kernels for A/B runs")
     return ap.parse_args()
 
 

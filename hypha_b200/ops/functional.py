@@ -658,12 +658,14 @@ def attention_fwd_tcgen05(qkv: torch.Tensor, batch: int, seq: int, n_heads: int,
     return out, lse
 
 
-_ATTN_BACKEND = os.environ.get("HYPHA_ATTN", "cudnn")
+_ATTN_BACKEND = os.environ.get("HYPHA_ATTN", "tcgen05")
 
 
 def set_attention_backend(name: str) -> None:
-    """``cudnn`` (cuDNN fused attention through torch SDPA; library), ``flash2`` (flash-attn 2
-    mma.sync kernels; library) -- the hand-written tcgen05 attention replaces both."""
+    """``tcgen05`` (default): the hand-written flash attention, forward and backward, for head_dim 128 and
+    sequence lengths that are multiples of 128 -- other shapes run cuDNN.  ``cudnn`` (cuDNN fused attention
+    through torch SDPA; library; +6 % on the Llama-3-8B step) and ``flash2`` (flash-attn 2 mma.sync kernels;
+    library) are kept for A/B runs."""
     global _ATTN_BACKEND
     if name not in ("cudnn", "flash2", "tcgen05"):
         raise ValueError(name)
@@ -729,11 +731,11 @@ def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: i
     """Causal self-attention on a fused (already RoPE'd) qkv activation -> ``[tokens, Hq*D]``."""
     if not qkv.is_cuda:
         return _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim)
-    if _ATTN_BACKEND == "cudnn":
-        return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "tcgen05" and head_dim == 128 and seq % 128 == 0:
         return _TcgenAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
-    return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+    if _ATTN_BACKEND == "flash2":
+        return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+    return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)      # cudnn, or a shape tcgen05 does not cover
 
 
 # -----------------------------------------------------------------------------

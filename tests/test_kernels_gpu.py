@@ -256,13 +256,17 @@ def test_attention_matches_sdpa(C, backend):
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _attention_ref
 
+    prev = ops.get_attention_backend()
     ops.set_attention_backend(backend)
     torch.manual_seed(0)
     B, S, Hq, Hk, D = 2, 256, 8, 2, 128
     qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-    out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
-    d = torch.randn_like(out)
-    out.backward(d)
+    try:
+        out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
+        d = torch.randn_like(out)
+        out.backward(d)
+    finally:
+        ops.set_attention_backend(prev)
     qf = qkv.detach().float().requires_grad_(True)
     of = _attention_ref(qf, B, S, Hq, Hk, D)
     of.backward(d.float())
@@ -465,14 +469,17 @@ def test_attention_tcgen05_backend_grad(C):
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _attention_ref
 
+    prev = ops.get_attention_backend()
     ops.set_attention_backend("tcgen05")
     torch.manual_seed(0)
     B, S, Hq, Hk, D = 2, 256, 8, 2, 128
     qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
-    out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
-    d = torch.randn_like(out)
-    out.backward(d)
-    ops.set_attention_backend("cudnn")
+    try:
+        out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
+        d = torch.randn_like(out)
+        out.backward(d)
+    finally:
+        ops.set_attention_backend(prev)
     qf = qkv.detach().float().requires_grad_(True)
     of = _attention_ref(qf, B, S, Hq, Hk, D)
     of.backward(d.float())
