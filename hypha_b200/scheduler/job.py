@@ -8,6 +8,8 @@ that joins the running job) -- the reference exits on the first lost lease (SURV
 from __future__ import annotations
 
 import asyncio
+import json
+import os
 import socket
 from dataclasses import dataclass, field
 from typing import Any, Dict, List, Optional
@@ -202,6 +204,51 @@ class DiLoCoJobRun:
                     acfg.checkpoint["resume_round"] = resume_round
             spec = M.JobSpec(self.job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg))
             self._watch_task(await Task.try_new(self.net, spec, [self.ps]))
+            if ck.dir:
+                if resume_round:
+                    self._restore_scheduler_state(ck.dir, resume_round)
+                self.background.append(asyncio.ensure_future(self._checkpoint_scheduler_state(ck.dir, ck.every)))
+
+    # -- scheduler side of the job checkpoint -----------------------------------------------------
+    def _restore_scheduler_state(self, ckpt_dir: str, round_no: int) -> None:
+        """The aggregate worker's checkpoint holds the outer state; the scheduler adds its own: which slices
+        of the current data epoch were already handed out (round + slice-tracker state)."""
+        path = os.path.join(ckpt_dir, "scheduler_state.json")
+        try:
+            st = json.load(open(path))
+            if int(st["round"]) != int(round_no):
+                self.log.info("scheduler state in %s is of round %s, resuming round %d: new data epoch", path, st["round"], round_no)
+                return
+            self.data_svc.tracker.restore([(str(o), bool(p)) for o, p in st["slices"]], int(st["epochs"]))
+            self.log.info("data scheduler resumed: %d of %d slices of epoch %d already used",
+                          sum(1 for _, p in st["slices"] if p), len(st["slices"]), int(st["epochs"]))
+        except FileNotFoundError:
+            pass
+        except (OSError, ValueError, KeyError, TypeError) as exc:
+            self.log.warning("ignoring unreadable scheduler state %s: %s", path, exc)
+
+    def _write_scheduler_state(self, ckpt_dir: str, rnd: int) -> None:
+        try:
+            os.makedirs(ckpt_dir, exist_ok=True)
+            tmp = os.path.join(ckpt_dir, "scheduler_state.json.tmp")
+            with open(tmp, "w") as f:
+                json.dump({"round": rnd, "epochs": int(self.data_svc.tracker.rounds()),
+                           "slices": [[o, bool(p)] for o, p in self.data_svc.tracker.snapshot()]}, f)
+            os.replace(tmp, os.path.join(ckpt_dir, "scheduler_state.json"))
+        except OSError as exc:
+            self.log.warning("could not write the scheduler state: %s", exc)
+
+    async def _checkpoint_scheduler_state(self, ckpt_dir: str, every: int) -> None:
+        last = self.batch.round
+        while True:
+            finished = self.batch.done.is_set()
+            rnd = self.batch.round
+            if rnd != last and (finished or rnd % max(1, int(every)) == 0):
+                last = rnd
+                self._write_scheduler_state(ckpt_dir, rnd)
+            if finished:
+                return
+            await asyncio.sleep(0.25)
 
     # -- elasticity -----------------------------------------------------------------------------
     async def _tell_aggregate_worker(self) -> None:
@@ -363,6 +410,9 @@ class DiLoCoJobRun:
             await self.close()
 
     async def close(self) -> None:
+        ck = self.job.checkpoint
+        if ck.dir and not self.collective and getattr(self, "data_svc", None) is not None and self.batch.round > 0:
+            self._write_scheduler_state(ck.dir, self.batch.round)      # the state the last checkpoint belongs to
         for b in self.background:
             if not b.done():
                 b.cancel()

@@ -296,7 +296,10 @@ def test_job_checkpoint_and_resume(tmp_path):
     a, _, logs_a, _ = run("a", job(3, False))
     assert a.finished and a.rounds == 3
     assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 3}
-    assert sorted(os.listdir(ckpt)) == ["latest.json", "round-2", "round-3"]           # the two newest are kept
+    assert sorted(os.listdir(ckpt)) == ["latest.json", "round-2", "round-3", "scheduler_state.json"]   # two newest kept
+    st = json.load(open(os.path.join(ckpt, "scheduler_state.json")))                   # the scheduler's share
+    assert st["round"] == 3 and len(st["slices"]) == 6 and any(p for _, p in st["slices"])
+    assert {o for o, _ in st["slices"]} <= {"", "worker-a", "worker-b"}
     u3 = load_file(os.path.join(ckpt, "round-3", "cumulative_update"))
     assert u3 and all(torch.isfinite(v).all() for v in u3.values())
 
@@ -307,6 +310,9 @@ def test_job_checkpoint_and_resume(tmp_path):
     assert sum("Finished training of 6 DiLoCo update rounds" in l for l in logs_b) == 2
     assert {r["round"] for r in sink_b.records} == {4, 5, 6}                          # only the new rounds ran
     assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 6}
+    st6 = json.load(open(os.path.join(ckpt, "scheduler_state.json")))
+    # the data scheduler went on from the restored state: same epoch bookkeeping, more slices used (or a new epoch)
+    assert st6["round"] == 6 and (st6["epochs"], sum(p for _, p in st6["slices"])) != (st["epochs"], sum(p for _, p in st["slices"]))
     u6 = load_file(os.path.join(ckpt, "round-6", "cumulative_update"))
     assert any(not torch.equal(u6[k], u3[k]) for k in u3)                             # U kept accumulating
 
