@@ -22,6 +22,7 @@ Handler matching is *first registered match wins*, as in the reference
 from __future__ import annotations
 
 import asyncio
+import collections
 import itertools
 import os
 import struct
@@ -110,10 +111,125 @@ class MemoryLink(Link):
             self.other.closed = True
 
 
+class _FrameProtocol(asyncio.BufferedProtocol):
+    """Length-prefixed frames received straight into their final buffer: the event loop `recv_into`s the
+    4-byte prefix, then the frame body (a bytearray of exactly the frame's size), so a 1 MiB stream chunk is
+    copied once (kernel -> user) instead of three times (StreamReader buffer, `readexactly` slice, CBOR
+    byte string).  Works under TLS as well (asyncio's SSL layer feeds buffered protocols).  Reading pauses
+    while more than HIGH frames wait for the consumer."""
+
+    HIGH, LOW = 32, 8
+
+    def __init__(self, on_connect: Optional[Callable[["_FrameProtocol"], None]] = None):
+        self.transport: Optional[asyncio.Transport] = None
+        self._on_connect = on_connect
+        self._hdr = bytearray(4)
+        self._hv = memoryview(self._hdr)
+        self._body: Optional[bytearray] = None
+        self._bv: Optional[memoryview] = None
+        self._pos = self._need = 0
+        self._split = False
+        self._frames: collections.deque = collections.deque()
+        self._waiter: Optional[asyncio.Future] = None
+        self._eof = False
+        self._reading_paused = False
+        self._writing_paused = False
+        self._drain_waiters: collections.deque = collections.deque()
+        self.error: Optional[Exception] = None
+
+    # -- transport callbacks ----------------------------------------------------------------------
+    def connection_made(self, transport) -> None:
+        self.transport = transport
+        if self._on_connect is not None:
+            self._on_connect(self)
+
+    def get_buffer(self, sizehint: int):
+        return self._hv[self._pos:] if self._body is None else self._bv[self._pos:]
+
+    def buffer_updated(self, nbytes: int) -> None:
+        self._pos += nbytes
+        if self._body is None:
+            if self._pos < 4:
+                return
+            (n,) = struct.unpack("<I", self._hdr)
+            self._split = bool(n & SPLIT_BIT)
+            n &= ~SPLIT_BIT
+            self._pos = 0
+            if n > MAX_FRAME:
+                self.error = NetworkError("frame too large")
+                self.transport.close()
+                return
+            if n == 0:
+                self._deliver(bytearray(), self._split)
+                return
+            self._body = bytearray(n)
+            self._bv = memoryview(self._body)
+            self._need = n
+        elif self._pos == self._need:
+            body, self._body, self._bv, self._pos = self._body, None, None, 0
+            self._deliver(body, self._split)
+
+    def _deliver(self, body: bytearray, split: bool) -> None:
+        self._frames.append((body, split))
+        self._wake()
+        if len(self._frames) >= self.HIGH and not self._reading_paused and self.transport is not None:
+            self._reading_paused = True
+            self.transport.pause_reading()
+
+    def _wake(self) -> None:
+        w, self._waiter = self._waiter, None
+        if w is not None and not w.done():
+            w.set_result(None)
+
+    def eof_received(self):
+        self._eof = True
+        self._wake()
+        return False
+
+    def connection_lost(self, exc) -> None:
+        self._eof = True
+        self._wake()
+        for w in self._drain_waiters:
+            if not w.done():
+                w.set_exception(ConnectionResetError("connection lost"))
+        self._drain_waiters.clear()
+
+    def pause_writing(self) -> None:
+        self._writing_paused = True
+
+    def resume_writing(self) -> None:
+        self._writing_paused = False
+        for w in self._drain_waiters:
+            if not w.done():
+                w.set_result(None)
+        self._drain_waiters.clear()
+
+    # -- consumer side ----------------------------------------------------------------------------------
+    async def read_frame(self) -> Optional[Tuple[bytearray, bool]]:
+        while not self._frames:
+            if self._eof:
+                return None
+            self._waiter = asyncio.get_running_loop().create_future()
+            await self._waiter
+        item = self._frames.popleft()
+        if self._reading_paused and len(self._frames) <= self.LOW and self.transport is not None:
+            self._reading_paused = False
+            self.transport.resume_reading()
+        return item
+
+    async def drain(self) -> None:
+        if self.transport is None or self.transport.is_closing():
+            raise ConnectionResetError("connection closed")
+        if self._writing_paused:
+            w = asyncio.get_running_loop().create_future()
+            self._drain_waiters.append(w)
+            await w
+
+
 class SocketLink(Link):
-    def __init__(self, reader: asyncio.StreamReader, writer: asyncio.StreamWriter):
+    def __init__(self, proto: _FrameProtocol):
         super().__init__()
-        self.reader, self.writer = reader, writer
+        self.proto = proto
         self._wlock = asyncio.Lock()
 
     async def send(self, frame: dict) -> int:
@@ -130,36 +246,43 @@ class SocketLink(Link):
             data = cbor2.dumps(frame)
             total = len(data)
             parts = [struct.pack("<I", total), data]
-        async with self._wlock:
-            self.writer.writelines(parts)
-            await self.writer.drain()
+        try:
+            async with self._wlock:
+                self.proto.transport.writelines(parts)
+                await self.proto.drain()
+        except (ConnectionError, OSError, AttributeError) as exc:
+            raise NetworkError(f"link closed: {exc}") from exc
         return total
 
     async def recv(self) -> Optional[Tuple[dict, int]]:
         """``(frame, wire bytes)`` or None when the connection ended."""
-        try:
-            hdr = await self.reader.readexactly(4)
-            (n,) = struct.unpack("<I", hdr)
-            split = bool(n & SPLIT_BIT)
-            n &= ~SPLIT_BIT
-            if n > MAX_FRAME:
-                raise NetworkError("frame too large")
-            buf = await self.reader.readexactly(n)
-            if not split:
-                return cbor2.loads(buf), n
-            (m,) = struct.unpack_from("<I", buf, 0)
+        got = await self.proto.read_frame()
+        if got is None:
+            return None
+        body, split = got
+        n = len(body)
+        m = 0
+        if split:
+            if n < 4:
+                raise NetworkError("malformed bulk frame")
+            (m,) = struct.unpack_from("<I", body, 0)
             if 4 + m > n:
                 raise NetworkError("malformed bulk frame")
-            frame = cbor2.loads(buf[4:4 + m])
-            frame["data"] = memoryview(buf)[4 + m:]          # no copy: the consumer writes it to its file
-            return frame, n
-        except (asyncio.IncompleteReadError, ConnectionError, OSError):
-            return None
+        try:
+            frame = cbor2.loads(bytes(body[4:4 + m]) if split else bytes(body))
+        except cbor2.CBORError as exc:
+            raise NetworkError(f"undecodable frame: {exc}") from exc
+        if not isinstance(frame, dict):
+            raise NetworkError("frame is not a map")
+        if split:
+            frame["data"] = memoryview(body)[4 + m:]          # no copy: the consumer writes it to its file
+        return frame, n
 
     async def close(self) -> None:
         self.closed = True
         try:
-            self.writer.close()
+            if self.proto.transport is not None:
+                self.proto.transport.close()
         except Exception:
             pass
 
@@ -289,12 +412,13 @@ class Network:
             path = addr[len("unix://"):]
             if os.path.exists(path):
                 os.unlink(path)
-            srv = await asyncio.start_unix_server(self._on_socket, path=path)
+            srv = await asyncio.get_running_loop().create_unix_server(lambda: _FrameProtocol(self._on_socket), path=path)
             os.chmod(path, 0o600)
             self._servers.append(srv)
         elif addr.startswith("tcp://"):
             host, port = addr[len("tcp://"):].rsplit(":", 1)
-            srv = await asyncio.start_server(self._on_socket, host=host, port=int(port), ssl=self._ssl_context(True))
+            srv = await asyncio.get_running_loop().create_server(lambda: _FrameProtocol(self._on_socket), host=host,
+                                                                 port=int(port), ssl=self._ssl_context(True))
             port = srv.sockets[0].getsockname()[1]
             addr = f"tcp://{host}:{port}"
             self._servers.append(srv)
@@ -307,13 +431,15 @@ class Network:
         if addr not in self.external_addrs:
             self.external_addrs.append(addr)
 
-    async def _on_socket(self, reader, writer) -> None:
-        link = SocketLink(reader, writer)
-        self._spawn(self._socket_loop(link))
+    def _on_socket(self, proto: _FrameProtocol) -> None:
+        self._spawn(self._socket_loop(SocketLink(proto)))
 
     async def _socket_loop(self, link: SocketLink) -> None:
         while not link.closed:
-            got = await link.recv()
+            try:
+                got = await link.recv()
+            except (NetworkError, ValueError):             # malformed frame / undecodable CBOR: drop the peer
+                break
             if got is None:
                 break
             await self._on_frame(got[0], link, None, got[1])
@@ -346,14 +472,16 @@ class Network:
                 a.other, b.other = b, a
                 link: Link = a
             elif addr.startswith("unix://"):
-                r, w = await asyncio.wait_for(asyncio.open_unix_connection(addr[len("unix://"):]), timeout)
-                link = SocketLink(r, w)
+                _, proto = await asyncio.wait_for(
+                    asyncio.get_running_loop().create_unix_connection(_FrameProtocol, addr[len("unix://"):]), timeout)
+                link = SocketLink(proto)
                 self._spawn(self._socket_loop(link))
             elif addr.startswith("tcp://"):
                 host, port = addr[len("tcp://"):].rsplit(":", 1)
-                r, w = await asyncio.wait_for(asyncio.open_connection(host, int(port), ssl=self._ssl_context(False)),
-                                              timeout)
-                link = SocketLink(r, w)
+                _, proto = await asyncio.wait_for(
+                    asyncio.get_running_loop().create_connection(_FrameProtocol, host, int(port),
+                                                                 ssl=self._ssl_context(False)), timeout)
+                link = SocketLink(proto)
                 self._spawn(self._socket_loop(link))
             else:
                 raise DialError(f"unsupported address {addr!r}")

@@ -458,3 +458,30 @@ def test_bulk_frames_keep_payload_and_count_wire_bytes():
     async def _echo(m):
         return m
     run(main())
+
+
+def test_garbage_on_a_socket_drops_only_that_link():
+    """A peer that sends an oversized length prefix or bytes that are not CBOR is disconnected; the node keeps
+    serving its other links."""
+    import struct
+
+    async def main():
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = await pair("unix", tmp)
+            a.on("/echo/1", None, lambda peer, m: _ret(m))
+            for junk in (struct.pack("<I", (1 << 30)) + b"x" * 16, struct.pack("<I", 5) + b"\xff\xff\xff\xff\xff",
+                         struct.pack("<II", (1 << 31) | 6, 99) + b"zz"):
+                r, w = await asyncio.open_unix_connection(f"{tmp}/a.sock")
+                w.write(junk)
+                await w.drain()
+                try:
+                    assert await asyncio.wait_for(r.read(1), 5) == b""    # closed by the node ...
+                except ConnectionResetError:
+                    pass                                                  # ... or reset (unread bytes pending)
+                w.close()
+            assert await b.request("A", "/echo/1", {"still": "here"}) == {"still": "here"}
+            await a.close(); await b.close()
+
+    async def _ret(m):
+        return m
+    run(main())
