@@ -28,6 +28,7 @@ def _key_pem(key: Ed25519PrivateKey) -> bytes:
 
 
 def _write(path: str, data: bytes, mode: int) -> None:
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)       # `-d pki` may not exist yet
     fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, mode)
     with os.fdopen(fd, "wb") as f:
         f.write(data)

@@ -31,12 +31,16 @@ def build_parser() -> argparse.ArgumentParser:
 
 def main(argv=None) -> int:
     a = build_parser().parse_args(argv)
-    if a.command == "root":
-        print(*cu.make_root(a.organization, a.name, a.country, a.dir))
-    elif a.command == "org":
-        print(*cu.make_org(a.root_cert, a.root_key, a.organization, a.name, a.country, a.dir))
-    else:
-        print(*cu.make_node(a.ca_cert, a.ca_key, a.name, tuple(a.san), a.dir))
+    try:
+        if a.command == "root":
+            print(*cu.make_root(a.organization, a.name, a.country, a.dir))
+        elif a.command == "org":
+            print(*cu.make_org(a.root_cert, a.root_key, a.organization, a.name, a.country, a.dir))
+        else:
+            print(*cu.make_node(a.ca_cert, a.ca_key, a.name, tuple(a.san), a.dir))
+    except (OSError, ValueError) as exc:          # unreadable / malformed CA files, unwritable directory
+        print(f"hypha-certutil: error: {exc}", file=sys.stderr)
+        return 1
     return 0
 
 

@@ -249,3 +249,14 @@ def test_cli_reference_is_up_to_date():
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "gen_cli_docs.py"), "--check"],
                        capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stderr
+
+
+def test_certutil_creates_the_output_directory_and_reports_missing_files(tmp_path, capsys):
+    from hypha_b200.cli import certutil as cli_cu
+
+    d = str(tmp_path / "pki" / "nested")                      # does not exist yet
+    assert cli_cu.main(["root", "-o", "Acme", "-d", d]) == 0
+    assert sorted(os.listdir(d)) == ["Acme-root-cert.pem", "Acme-root-key.pem"]
+    assert cli_cu.main(["node", "--ca-cert", os.path.join(d, "missing.pem"), "--ca-key", os.path.join(d, "Acme-root-key.pem"),
+                        "-n", "w0", "-d", d]) == 1
+    assert "hypha-certutil: error:" in capsys.readouterr().err
