@@ -240,7 +240,8 @@ def main():
     from hypha_b200.parallel.peer_memory import PeerGroup
     from hypha_b200.trainer import DiLoCoTrainer
 
-    if args.impl == "baseline" and "--attn" not in sys.argv and "HYPHA_ATTN" not in os.environ:
+    if (args.impl == "baseline" and "HYPHA_ATTN" not in os.environ
+            and not any(a == "--attn" or a.startswith("--attn=") for a in sys.argv)):
         args.attn = "cudnn"              # the stock-components arm: library GEMMs, library attention, NCCL
     ops.set_attention_backend(args.attn)
     ops.set_fp8(args.fp8)
