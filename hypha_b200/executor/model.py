@@ -123,8 +123,8 @@ def get_preprocessor(cfg: Optional[dict], model_path: str) -> Optional[Any]:
             return getattr(transformers, cls).from_pretrained(model_path)
     except KeyError:
         raise RuntimeError(f"Pre-Processor of type {kind} not found")
-    except Exception:
-        pass
+    except Exception as exc:      # a broken processor config: say so, then use the built-in fallback if there is one
+        print(f"preprocessor of type {kind} could not be loaded from {model_path}: {type(exc).__name__}: {exc}", flush=True)
     if kind == "image":
         return lambda images: {"pixel_values": images}
     return None

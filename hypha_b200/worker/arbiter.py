@@ -53,8 +53,8 @@ class Arbiter:
             try:
                 self.leases.remove(job.lease_id)
                 self.log(f"[arbiter] job {job.id[:8]} failed -> lease {job.lease_id[:8]} released")
-            except Exception:
-                pass
+            except KeyError:
+                pass                     # already expired and pruned
 
     # -- handlers ---------------------------------------------------------------------------------
     async def _on_renew(self, peer: str, msg) -> M.ApiResponse:
