@@ -71,6 +71,10 @@ class RecordNotFound(NetworkError):
     pass
 
 
+class StreamAborted(NetworkError):
+    """A tensor stream ended without its sender's close (link lost, or the serving side failed)."""
+
+
 def new_peer_id(prefix: str = "peer") -> str:
     return f"{prefix}-{uuid.uuid4().hex[:16]}"
 
@@ -312,11 +316,25 @@ class IncomingStream:
     header: Any
     job_id: Optional[str]
     queue: "asyncio.Queue[Optional[bytes]]"
+    error: Optional[str] = None          # set when the stream ended without its sender's regular close
+
+    def abort(self, why: str) -> None:
+        """The sender is gone (link dropped) or reported a failure: the consumer must not mistake what arrived
+        so far for the whole file."""
+        self.error = why
+        while True:
+            try:
+                self.queue.put_nowait(None)
+                return
+            except asyncio.QueueFull:           # make room: the chunks are worthless now
+                self.queue.get_nowait()
 
     async def chunks(self) -> AsyncIterator[bytes]:
         while True:
             c = await self.queue.get()
             if c is None:
+                if self.error is not None:
+                    raise StreamAborted(self.error)
                 return
             yield c
 
@@ -450,6 +468,10 @@ class Network:
         if link.peer_id and self.links.get(link.peer_id) is link:
             del self.links[link.peer_id]
             self._peer_topics.pop(link.peer_id, None)
+            for sid, st in list(self._streams.items()):
+                if st.peer == link.peer_id:          # half-received files must not look complete
+                    self._streams.pop(sid, None)
+                    st.abort(f"connection to {link.peer_id} lost mid-stream")
             for rid, fut in list(self._pending.items()):
                 if getattr(fut, "_peer", None) == link.peer_id and not fut.done():
                     fut.set_exception(RequestFailed(f"connection to {link.peer_id} closed"))
@@ -624,7 +646,10 @@ class Network:
         elif t == "stream_close":
             st = self._streams.pop(frame["sid"], None)
             if st is not None:
-                await st.queue.put(None)
+                if frame.get("error"):
+                    st.abort(f"{st.peer} could not serve the stream: {frame['error']}")
+                else:
+                    await st.queue.put(None)
         elif t == "ping":
             await self._send_to(src, {"t": "pong", "id": frame["id"]}, "/ipfs/ping/1.0.0")
         elif t == "pong":

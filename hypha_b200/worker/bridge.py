@@ -293,7 +293,14 @@ class Bridge:
             idx = 0
             async for st in self.connector.receive(ref, job_id=self.job_id):
                 name = hashlib.sha256(f"{st.peer}:{idx}".encode()).hexdigest()[:32]
-                info = await self._store(name, st, dir_rel)
+                try:
+                    info = await self._store(name, st, dir_rel)
+                except NetworkError as exc:       # the sender vanished mid-file: never announce half a tensor file
+                    self.log(f"[bridge] incoming file from {st.peer} dropped: {exc}")
+                    partial = safe_join(self.work_dir, f"{dir_rel}/{name}")
+                    if os.path.exists(partial):
+                        os.unlink(partial)
+                    continue
                 info["from_peer"] = st.peer
                 await events.put(info)
                 idx += 1

@@ -281,7 +281,15 @@ class ParameterServerExecutor:
                             if st.peer not in workers:
                                 continue                               # late file from a removed worker
                             path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
-                            await st.save(path)
+                            try:
+                                await st.save(path)
+                            except NetworkError as exc:
+                                # the worker died while pushing: half a file is no pseudo-gradient.  Keep waiting;
+                                # the scheduler will shrink the membership (or the receive timeout drops the worker)
+                                self.log(f"[ps {spec.job_id[:8]}] round {rnd}: pseudo-gradient of {st.peer} incomplete ({exc})")
+                                if os.path.exists(path):
+                                    os.unlink(path)
+                                continue
                             got[st.peer] = path
                         elif not done:
                             missing = [w for w in workers if w not in got]

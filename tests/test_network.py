@@ -485,3 +485,38 @@ def test_garbage_on_a_socket_drops_only_that_link():
     async def _ret(m):
         return m
     run(main())
+
+
+def test_stream_that_loses_its_sender_is_not_mistaken_for_a_complete_file():
+    """The sender's link drops mid-push: the receiver's `save` raises StreamAborted instead of returning a
+    truncated file; a pull whose handler fails raises on the requesting side as well."""
+    from hypha_b200.transport import StreamAborted
+
+    async def main():
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = await pair("unix", tmp)
+            rx = a.streams_push(job_id="j")
+
+            # a sender that opens a stream, sends one chunk and then loses its connection
+            await b._send_to("A", {"t": "stream_open", "sid": "s1", "proto": "/hypha-tensor-stream/push", "job": "j",
+                                   "header": None}, "/hypha-tensor-stream/push")
+            await b._send_to("A", {"t": "stream_data", "sid": "s1", "data": b"x" * 100_000,
+                                   "proto": "/hypha-tensor-stream/push"}, "/hypha-tensor-stream/push")
+            st = await rx.get()
+            saver = asyncio.ensure_future(st.save(os.path.join(tmp, "partial.bin")))
+            await asyncio.sleep(0.1)
+            await b.disconnect("A")
+            with pytest.raises(StreamAborted, match="lost mid-stream"):
+                await asyncio.wait_for(saver, 5)
+
+            # pull: the serving side fails -> the requester sees the reason
+            async def broken(peer, header):
+                raise FileNotFoundError("slice 7 does not exist")
+            a.serve_pull(broken)
+            c = Network("C")
+            await c.dial(a.listen_addrs[0])
+            pulled = await c.stream_pull("A", {"dataset": "d", "index": 7})
+            with pytest.raises(StreamAborted, match="slice 7 does not exist"):
+                await asyncio.wait_for(pulled.read_all(), 5)
+            await a.close(); await b.close(); await c.close()
+    run(main())
