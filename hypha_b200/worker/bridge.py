@@ -61,6 +61,7 @@ class Connector:
         self.network = network
         # offline model registry: <hf_local>/<repository>/<filename>; HYPHA_HF_LOCAL overrides
         self.hf_local = hf_local or os.environ.get("HYPHA_HF_LOCAL")
+        self.last_send_failures: list = []      # [(peer, reason)] of the last tolerate_partial send
 
     # -- fetch: yields (file_name, async chunk iterator | local path) ---------------------------
     async def fetch(self, ref: M.Reference, scheduler_hint: Optional[str] = None):
@@ -128,7 +129,10 @@ class Connector:
         return str(index), st
 
     # -- send -----------------------------------------------------------------------------------
-    async def send(self, ref: M.Reference, path: str, job_id: Optional[str] = None) -> int:
+    async def send(self, ref: M.Reference, path: str, job_id: Optional[str] = None, tolerate_partial: bool = False) -> int:
+        """Push ``path`` to the reference's peers; returns the bytes sent.  With ``tolerate_partial`` a peer that
+        cannot be reached does not fail the others (``last_send_failures`` lists them); it still raises when
+        nobody could be reached."""
         if ref.type != "peers":
             raise InvalidResource("send needs a peers reference")
         peers = list(ref.peers)
@@ -137,10 +141,18 @@ class Connector:
             peers = peers[:1]
         elif strat == M.SelectionStrategy.RANDOM:
             peers = [random.choice(peers)] if peers else []
-        total = 0
-        for p in peers:
-            total += await self.network.stream_push(p, path, job_id=job_id)
-        return total
+        # one stream per peer, all at once: the links are independent sockets, so the fan-out of an update to N
+        # workers takes about as long as the slowest transfer instead of the sum
+        results = await asyncio.gather(*(self.network.stream_push(p, path, job_id=job_id) for p in peers),
+                                       return_exceptions=True)
+        failed = [(p, r) for p, r in zip(peers, results) if isinstance(r, BaseException)]
+        for p, r in failed:
+            if not isinstance(r, NetworkError):
+                raise r
+        if failed and (not tolerate_partial or len(failed) == len(peers)):
+            raise failed[0][1]
+        self.last_send_failures = [(p, str(r)) for p, r in failed]
+        return sum(r for r in results if isinstance(r, int))
 
     # -- receive ------------------------------------------------------------------------------------
     async def receive(self, ref: M.Reference, job_id: Optional[str] = None,
@@ -156,7 +168,10 @@ class Connector:
             while True:
                 st: IncomingStream = await q.get()
                 if st.peer not in allowed:
-                    async for _ in st.chunks():      # drain + drop
+                    try:
+                        async for _ in st.chunks():      # drain + drop
+                            pass
+                    except NetworkError:
                         pass
                     continue
                 yield st

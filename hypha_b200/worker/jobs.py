@@ -314,7 +314,10 @@ class ParameterServerExecutor:
                     resp = await self.network.request(scheduler, M.PROGRESS_PROTOCOL,
                                                       M.ProgressRequest(spec.job_id, M.Progress("updated")))
                     send_ref = M.Send.to_peers([p for p in result_peers if p in got] or result_peers)
-                    await self.connector.send(send_ref, out, job_id=spec.job_id)
+                    # a worker that died since it pushed its pseudo-gradient must not cost the others the round
+                    await self.connector.send(send_ref, out, job_id=spec.job_id, tolerate_partial=True)
+                    for p, why in self.connector.last_send_failures:
+                        self.log(f"[ps {spec.job_id[:8]}] round {rnd}: update not delivered to {p}: {why}")
                     for p in got.values():
                         os.unlink(p)
                     os.unlink(out)

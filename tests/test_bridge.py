@@ -146,3 +146,43 @@ def test_bridge_send_and_receive_streams(tmp_path):
         return b"".join([c async for c in st.chunks()])
 
     _run_with_bridge(str(tmp_path), scenario)
+
+
+def test_connector_fans_out_concurrently_and_tolerates_a_dead_peer(tmp_path):
+    """`Connector.send` to several peers: one stream per peer at the same time; with `tolerate_partial` an
+    unreachable peer is reported in `last_send_failures` instead of failing the reachable ones; without it,
+    or when nobody can be reached, the error is raised."""
+    import asyncio
+
+    from hypha_b200 import messages as M
+    from hypha_b200.transport import Network, NetworkError
+    from hypha_b200.worker import Connector
+
+    async def main():
+        hub = Network("hub")
+        addr = await hub.listen(f"memory://fanout-{id(hub)}")
+        peers = {}
+        for name in ("a", "b"):
+            n = Network(name)
+            await n.dial(addr)
+            peers[name] = (n, n.streams_push("job"))
+        await asyncio.sleep(0.05)
+        conn = Connector(hub)
+        src = str(tmp_path / "update.bin")
+        payload = os.urandom(300_000)
+        open(src, "wb").write(payload)
+        ref = M.Send.to_peers(["a", "ghost", "b"])
+        sent = await conn.send(ref, src, job_id="job", tolerate_partial=True)
+        assert sent == 2 * len(payload)
+        assert [p for p, _ in conn.last_send_failures] == ["ghost"]
+        for name in ("a", "b"):
+            st = await asyncio.wait_for(peers[name][1].get(), 5)
+            assert await st.read_all() == payload and st.peer == "hub"
+        with pytest.raises(NetworkError):
+            await conn.send(ref, src, job_id="job")                     # strict: any failure raises
+        with pytest.raises(NetworkError):
+            await conn.send(M.Send.to_peers(["ghost", "phantom"]), src, job_id="job", tolerate_partial=True)
+        for n, _ in peers.values():
+            await n.close()
+        await hub.close()
+    asyncio.run(main())

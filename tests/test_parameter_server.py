@@ -138,6 +138,10 @@ def test_membership_changes_and_cumulative_update_for_a_newcomer(tmp_path):
         await _result(queues["w2"], tmp, "w2-1")
         peer, cum = await _result(queues["w4"], tmp, "w4-cum")
         assert peer == "ps" and torch.allclose(cum["w"], u0 + u1, atol=1e-7)
+        for _ in range(100):                  # the PS logs after its send returned; the receiver may be quicker
+            if any("w4 joined (cumulative update sent)" in l for l in logs):
+                break
+            await asyncio.sleep(0.02)
         assert any("w4 joined (cumulative update sent)" in l for l in logs)
         # round 2: all three current members contribute and all three get the result
         for w in ("w1", "w2", "w4"):
