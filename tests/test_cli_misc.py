@@ -260,3 +260,26 @@ def test_certutil_creates_the_output_directory_and_reports_missing_files(tmp_pat
     assert cli_cu.main(["node", "--ca-cert", os.path.join(d, "missing.pem"), "--ca-key", os.path.join(d, "Acme-root-key.pem"),
                         "-n", "w0", "-d", d]) == 1
     assert "hypha-certutil: error:" in capsys.readouterr().err
+
+
+def test_bench_contract_on_a_box_without_gpus():
+    """`bench.py --impl reference` must print ONE JSON line saying why the reference arm is unavailable and exit
+    0 (the driver runs it first on every box); the default arm needs a GPU and must say so instead of falling
+    back to anything slower."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1", "--steps", "2",
+                        "--warmup", "1"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    out = json.loads(lines[0])
+    assert out["impl"] == "reference" and isinstance(out["unavailable"], str) and "\n" not in out["unavailable"]
+    import torch
+
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
+                           capture_output=True, text=True, timeout=300, cwd=root)
+        assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
