@@ -1,7 +1,8 @@
 #!/bin/sh
 # Sanitizer / race-detection targets (the reference has none: SURVEY 5.2).
 #
-#   tools/sanitize.sh core      ASAN+UBSAN build of the C++ control-plane core, runs tests/test_core.py (CPU)
+#   tools/sanitize.sh core      ASAN+UBSAN build of the C++ control-plane core, runs tests/test_core.py and
+#                               tests/test_ps_round.py against it (CPU)
 #   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model and of the
 #                               parameter-server reducer (+ ASAN/UBSAN over the latter) (CPU)
 #   tools/sanitize.sh memcheck  compute-sanitizer --tool memcheck  over the kernel numerics tests (GPU box)
@@ -27,9 +28,10 @@ case "${1:-core}" in
     # run the reference test vectors against the instrumented module
     LIBCXX=$($SCXX -print-file-name=libstdc++.so.6)   # so ASAN can intercept __cxa_throw
     ASAN_OPTIONS=detect_leaks=0 LD_PRELOAD="$LIBASAN $LIBCXX" HYPHA_CORE_OVERRIDE="$ROOT/$OUT" \
-        $PY -m pytest tests/test_core.py -q -p no:cacheprovider
+        $PY -m pytest tests/test_core.py tests/test_ps_round.py -q -p no:cacheprovider
     ;;
   tsan)
+    unset LD_PRELOAD ASAN_OPTIONS || true      # when called from the ASAN run of the test-suite (`core` target)
     OUT=build/tsan
     mkdir -p "$OUT"
     SCXX=${HYPHA_SANITIZE_CXX:-/usr/bin/g++}
