@@ -122,3 +122,36 @@ def test_native_round_is_faster_than_the_torch_path(tmp_path):
     tb = ps_round.outer_round(_files(b, 2, shapes, seed=1), b, 0.7, 0.9, force_fallback=True)["seconds"]
     print(f"native {ta * 1e3:.1f} ms vs torch {tb * 1e3:.1f} ms")
     assert ta < tb * 1.5
+
+
+def test_native_equals_fallback_property(tmp_path):
+    """Property: for any number of workers, tensor shapes (incl. empty and scalar ones), learning rate and
+    momentum, the one-pass reducer and the torch path agree on update, momentum and cumulative update over
+    two consecutive rounds."""
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+
+    counter = iter(range(10 ** 6))
+    shape = st.lists(st.integers(0, 9), min_size=0, max_size=3).map(tuple)
+
+    @settings(max_examples=20, deadline=None)
+    @given(workers=st.integers(1, 4), shapes=st.lists(shape, min_size=1, max_size=4),
+           lr=st.floats(0.01, 2.0), mu=st.floats(0.0, 0.99))
+    def check(workers, shapes, lr, mu):
+        i = next(counter)
+        a, b = os.path.join(str(tmp_path), f"n{i}"), os.path.join(str(tmp_path), f"t{i}")
+        os.makedirs(a)
+        os.makedirs(b)
+        named = {f"t{j}": s for j, s in enumerate(shapes)}
+        for rnd in range(2):
+            ra = ps_round.outer_round(_files(a, workers, named, seed=rnd), a, lr, mu, threads=2)
+            rb = ps_round.outer_round(_files(b, workers, named, seed=rnd), b, lr, mu, force_fallback=True)
+            assert ra["native"] and not rb["native"]
+            for name in ("gradient_update", "momentum", "cumulative_update"):
+                x, y = load_file(os.path.join(a, name)), load_file(os.path.join(b, name))
+                assert set(x) == set(y)
+                for k in x:
+                    assert x[k].shape == y[k].shape
+                    torch.testing.assert_close(x[k], y[k], rtol=2e-6, atol=1e-6)
+
+    check()
