@@ -28,6 +28,9 @@ from .worker import Arbiter, Connector, JobManager
 ALLOCATION_PAUSE_S = 1.0          # hypha-scheduler.rs:241 (let losers' tentative leases expire)
 
 
+GATEWAY_REDIAL_S = float(os.environ.get("HYPHA_GATEWAY_REDIAL_S", "3"))
+
+
 class RoleError(Exception):
     pass
 
@@ -41,13 +44,48 @@ class Node:
     telemetry: Telemetry
     ready: asyncio.Event = field(default_factory=asyncio.Event)
     stop: asyncio.Event = field(default_factory=asyncio.Event)
+    gateways: dict = field(default_factory=dict)             # configured address -> peer id (None: not reached yet)
+    on_gateway_reconnect: list = field(default_factory=list)  # async callbacks(addr, peer) after a successful re-dial
+    background: list = field(default_factory=list)
 
     @property
     def peer_id(self) -> str:
         return self.network.peer_id
 
+    async def maintain_gateways(self, interval_s: Optional[float] = None) -> None:
+        """Keep the links to the configured gateways up: a gateway that restarts (or a link that drops) is
+        re-dialed every ``interval_s``; after a successful re-dial the role's callbacks run (the data node
+        re-announces its dataset: the DHT records lived in the old gateway process).  Topic subscriptions and
+        addresses travel with the hello frame, so gossip works again right away."""
+        interval_s = GATEWAY_REDIAL_S if interval_s is None else interval_s
+        while not self.stop.is_set():
+            try:
+                await asyncio.wait_for(self.stop.wait(), interval_s)
+                return
+            except asyncio.TimeoutError:
+                pass
+            for addr, peer in list(self.gateways.items()):
+                link = self.network.links.get(peer) if peer is not None else None
+                if link is not None and not link.closed:
+                    continue
+                if link is not None:                      # in-memory links do not notice the other side's exit
+                    await self.network.disconnect(peer)
+                try:
+                    new_peer = await self.network.dial(addr, timeout=min(5.0, max(1.0, interval_s)))
+                except NetworkError:
+                    continue
+                self.gateways[addr] = new_peer
+                self.telemetry.logger.info("%s re-connected to gateway %s (%s)", self.name, addr, new_peer)
+                for cb in list(self.on_gateway_reconnect):
+                    try:
+                        await cb(addr, new_peer)
+                    except Exception as exc:      # noqa: BLE001 - a failing callback must not stop the loop
+                        self.telemetry.logger.warning("gateway reconnect callback failed: %s", exc)
+
     async def shutdown(self) -> None:
         self.stop.set()
+        for t in self.background:
+            t.cancel()
         await self.network.close()
         self.telemetry.shutdown()
 
@@ -81,14 +119,17 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
     dialed = 0
     for addr in gateways:
         try:
-            await net.dial(addr)
+            node.gateways[addr] = await net.dial(addr)
             dialed += 1
         except NetworkError as exc:
+            node.gateways[addr] = None
             tel.logger.warning("dial gateway %s failed: %s", addr, exc)
     if gateways and dialed == 0:
         raise RoleError(f"{role}: none of the gateways {gateways} could be dialed")
     if need_bootstrap and gateways:
         await net.wait_for_bootstrap(10.0)
+    if gateways:
+        node.background.append(asyncio.ensure_future(node.maintain_gateways()))
     return node
 
 
@@ -150,8 +191,13 @@ async def run_data(cfg: C.DataConfig, *, peer_id: Optional[str] = None,
         return files[sl.index]
 
     node.network.serve_pull(serve)
-    await node.network.put_record(name, json.dumps(M.DataRecord(len(files)).to_wire()).encode())
-    await node.network.provide(name)
+
+    async def announce(*_):
+        await node.network.put_record(name, json.dumps(M.DataRecord(len(files)).to_wire()).encode())
+        await node.network.provide(name)
+
+    await announce()
+    node.on_gateway_reconnect.append(announce)       # a restarted gateway has an empty DHT
     node.ready.set()
     node.telemetry.logger.info("data node %s announces %s (%d slices)", node.peer_id, name, len(files))
     if started is not None and not started.done():

@@ -2,6 +2,7 @@
 acceptance by renewal -> dispatch guard -> expiry.  (The reference has no tests for the arbiter /
 allocator / lease manager: SURVEY section 4 "not tested at all".)"""
 import asyncio
+import json
 import os
 import time
 
@@ -247,4 +248,65 @@ def test_allocation_scales_to_hundreds_of_workers():
         for h in handles:
             await h.release()
         await _teardown(gw, sched, workers)
+    asyncio.run(main())
+
+
+def test_roles_survive_a_gateway_restart(monkeypatch):
+    """The gateway process is replaced (same address, empty DHT): the data node re-dials it, announces its
+    dataset again and a scheduler that arrives later finds the dataset and the worker's offers through the new
+    gateway."""
+    import tempfile
+
+    from hypha_b200 import config as C
+    from hypha_b200 import roles
+    from hypha_b200.executor.dataset import write_synthetic_token_slices
+    from hypha_b200.transport import Network, RecordNotFound
+
+    monkeypatch.setattr(roles, "GATEWAY_REDIAL_S", 0.2)
+
+    async def main():
+        tmp = tempfile.mkdtemp()
+        ds = os.path.join(tmp, "toyset")
+        write_synthetic_token_slices(ds, 2, 4, 8, 32)
+        gw = f"memory://gw-restart-{os.getpid()}"
+        loop = asyncio.get_event_loop()
+
+        async def start_gateway(pid):
+            fut = loop.create_future()
+            t = asyncio.ensure_future(roles.run_gateway(
+                C.builder(C.GatewayConfig).with_overrides({"listen_addresses": [gw]}).build(), peer_id=pid, started=fut))
+            return t, await fut
+
+        t1, g1 = await start_gateway("gw-1")
+        s1 = loop.create_future()
+        data_task = asyncio.ensure_future(roles.run_data(C.builder(C.DataConfig).with_overrides(
+            {"listen_addresses": [], "gateway_addresses": [gw], "exclude_cidr": [], "dataset_path": ds}).build(),
+            peer_id="data", started=s1))
+        data = await s1
+        assert data.gateways == {gw: "gw-1"}
+        g1.stop.set()                                   # the gateway goes away ...
+        await asyncio.wait([t1], timeout=5)
+        await asyncio.sleep(0.5)
+        assert "gw-1" not in data.network.links          # noticed and dropped by the maintenance loop
+        t2, g2 = await start_gateway("gw-2")            # ... and comes back as a new process
+        for _ in range(100):
+            if data.gateways.get(gw) == "gw-2" and "gw-2" in data.network.links:
+                break
+            await asyncio.sleep(0.05)
+        assert data.gateways == {gw: "gw-2"}
+        probe = Network("late-scheduler")
+        await probe.dial(gw)
+        rec = None
+        for _ in range(100):
+            try:
+                rec = await probe.get_record("toyset")
+                break
+            except RecordNotFound:
+                await asyncio.sleep(0.05)
+        assert rec is not None and json.loads(rec[0])["num_slices"] == 2 and rec[1] == "data"   # re-announced into the new DHT
+        await probe.close()
+        for n in (data, g2):
+            n.stop.set()
+        await asyncio.wait([data_task, t2], timeout=5)
+
     asyncio.run(main())
