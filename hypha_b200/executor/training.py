@@ -430,6 +430,45 @@ class _GenericEngine:
         return self.loop.step(batch)
 
     @torch.no_grad()
+    def save_checkpoint(self, ckpt_dir: str, round_no: int, work_dir: str) -> Optional[str]:
+        """Collective-mode job checkpoint: every rank holds the same global model theta_prev and outer momentum
+        after an outer step, so rank 0 of the current group writes them (`<dir>/round-<n>/collective_state`).
+        The inner AdamW state is not part of it (as in parameter-server mode a resumed job starts its inner
+        optimizers afresh)."""
+        if self.loop.flat or self.group.rank != 0:
+            return None
+        from safetensors.torch import save_file
+
+        from ..worker.jobs import publish_checkpoint
+
+        sd = self.loop.model.state_dict()
+        out = {f"prev/{k}": v.detach().cpu().contiguous() for k, v in self.loop.prev.items()}
+        out.update({f"buf/{k}": v.detach().cpu().contiguous() for k, v in sd.items() if k not in self.loop.prev})
+        out.update({f"m/{k}": v.detach().cpu().contiguous() for k, v in (self.outer.m or {}).items()})
+        tmp = os.path.join(work_dir, "collective_state.tmp")
+        save_file(out, tmp)
+        dst = publish_checkpoint(ckpt_dir, round_no, {"collective_state": tmp})
+        os.unlink(tmp)
+        return dst
+
+    @torch.no_grad()
+    def load_checkpoint(self, path: str) -> None:
+        from safetensors.torch import load_file
+
+        st = load_file(os.path.join(path, "collective_state"))
+        sd = self.loop.model.state_dict()
+        m = {}
+        for key, v in st.items():
+            kind, k = key.split("/", 1)
+            if kind == "m":
+                m[k] = v.to(self.loop.device).float()
+            elif k in sd:
+                sd[k].copy_(v.to(sd[k].dtype))
+                if kind == "prev":
+                    self.loop.prev[k] = sd[k].detach().clone()
+        self.outer.m = m or None
+
+    @torch.no_grad()
     def welcome(self, membership: dict, me: Optional[str] = None) -> None:
         """Right after a regroup that admitted newcomers: rank 0 (always a survivor -- newcomers are appended
         to the member list) broadcasts the current global model theta_prev and the outer momentum; every rank
@@ -533,6 +572,14 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     delay = _step_delay()
     generation = 0
     joining = bool(coll.get("join"))        # a replacement rank: no training before its first barrier
+    ckpt = coll.get("checkpoint") or {}
+    if ckpt.get("resume_round"):
+        if not hasattr(engine, "load_checkpoint"):
+            raise RuntimeError("resuming a collective job from a job checkpoint is implemented for the CPU (gloo) "
+                               "engine; the GPU trainer has DiLoCoTrainer.save_checkpoint / load_checkpoint")
+        engine.load_checkpoint(os.path.join(ckpt["dir"], f"round-{int(ckpt['resume_round'])}"))
+        round_no = int(ckpt["resume_round"]) + 1
+        print(f"resumed from the collective checkpoint of round {round_no - 1}", flush=True)
 
     while True:
         loss_sum = torch.zeros((), device=device)
@@ -603,6 +650,10 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         # advances the round on the first one and ignores the rest), so no rank is a single point of
         # failure and each rank's own `updated` precedes its `update-received`.
         session.send_status("updated")
+        if ckpt.get("dir") and round_no % max(1, int(ckpt.get("every", 1))) == 0 and hasattr(engine, "save_checkpoint"):
+            where = engine.save_checkpoint(ckpt["dir"], round_no, work_dir)
+            if where:
+                print(f"collective checkpoint of round {round_no} written to {where}", flush=True)
         round_no += 1
         if session.send_status("update-received")["type"] == "Done":
             break

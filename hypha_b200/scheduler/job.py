@@ -174,10 +174,14 @@ class DiLoCoJobRun:
         self.live = [w.peer_id for w in self.workers]
         ck = job.checkpoint
         resume_round = 0
-        if ck.dir and ck.resume and not self.collective:
+        if ck.dir and ck.resume:
             from ..worker.jobs import latest_checkpoint
 
             found = latest_checkpoint(ck.dir)
+            want = "collective" if self.collective else "parameter-server"
+            if found is not None and found.get("kind") != want:
+                raise JobError(f"the checkpoint in {ck.dir} was written in {found.get('kind')} mode, "
+                               f"this job aggregates in {want} mode")
             if found is not None:
                 resume_round = min(found["round"], job.rounds.update_rounds)
                 self.batch.start_at_round(resume_round)
@@ -192,6 +196,8 @@ class DiLoCoJobRun:
             if self.collective:
                 tcfg.collective = {"rank": i, "world": len(self.workers), "rendezvous": rendezvous,
                                    "outer": self.nesterov.to_wire(), "peer": w.peer_id, "peers": list(self.live)}
+                if ck.dir:      # rank 0 of the current group writes theta_prev + outer momentum every `every` rounds
+                    tcfg.collective["checkpoint"] = {"dir": ck.dir, "every": ck.every, "resume_round": resume_round}
             elif resume_round:
                 tcfg.join = {"after_round": resume_round, "resume": True}      # theta = theta_0(seed) + U
             await self._dispatch_train(w, tcfg)
@@ -204,10 +210,10 @@ class DiLoCoJobRun:
                     acfg.checkpoint["resume_round"] = resume_round
             spec = M.JobSpec(self.job_id, M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, acfg))
             self._watch_task(await Task.try_new(self.net, spec, [self.ps]))
-            if ck.dir:
-                if resume_round:
-                    self._restore_scheduler_state(ck.dir, resume_round)
-                self.background.append(asyncio.ensure_future(self._checkpoint_scheduler_state(ck.dir, ck.every)))
+        if ck.dir:
+            if resume_round:
+                self._restore_scheduler_state(ck.dir, resume_round)
+            self.background.append(asyncio.ensure_future(self._checkpoint_scheduler_state(ck.dir, ck.every)))
 
     # -- scheduler side of the job checkpoint -----------------------------------------------------
     def _restore_scheduler_state(self, ckpt_dir: str, round_no: int) -> None:
@@ -411,7 +417,7 @@ class DiLoCoJobRun:
 
     async def close(self) -> None:
         ck = self.job.checkpoint
-        if ck.dir and not self.collective and getattr(self, "data_svc", None) is not None and self.batch.round > 0:
+        if ck.dir and getattr(self, "data_svc", None) is not None and self.batch.round > 0:
             self._write_scheduler_state(ck.dir, self.batch.round)      # the state the last checkpoint belongs to
         for b in self.background:
             if not b.done():

@@ -168,7 +168,9 @@ def latest_checkpoint(ckpt_dir: str) -> Optional[dict]:
         meta = json.load(open(os.path.join(ckpt_dir, "latest.json")))
         path = os.path.join(ckpt_dir, f"round-{int(meta['round'])}")
         if os.path.isfile(os.path.join(path, "cumulative_update")) and os.path.isfile(os.path.join(path, "momentum")):
-            return {"round": int(meta["round"]), "path": path}
+            return {"round": int(meta["round"]), "path": path, "kind": "parameter-server"}
+        if os.path.isfile(os.path.join(path, "collective_state")):
+            return {"round": int(meta["round"]), "path": path, "kind": "collective"}
     except (OSError, ValueError, KeyError):
         pass
     return None
@@ -177,12 +179,18 @@ def latest_checkpoint(ckpt_dir: str) -> Optional[dict]:
 def save_job_checkpoint(ckpt_dir: str, round_no: int, cum_path: str, momentum_path: str, keep: int = 2) -> str:
     """Copy the aggregate job's outer state (cumulative update U + momentum) to ``<dir>/round-<n>`` and flip
     ``latest.json`` atomically; older checkpoints beyond ``keep`` are removed."""
+    return publish_checkpoint(ckpt_dir, round_no, {"cumulative_update": cum_path, "momentum": momentum_path}, keep)
+
+
+def publish_checkpoint(ckpt_dir: str, round_no: int, files: Dict[str, str], keep: int = 2) -> str:
+    """``files`` = {name in the checkpoint: path of the file to copy}.  The round directory appears complete or
+    not at all, ``latest.json`` flips last."""
     dst = os.path.join(ckpt_dir, f"round-{round_no}")
     tmp = dst + ".tmp"
     shutil.rmtree(tmp, ignore_errors=True)
     os.makedirs(tmp, exist_ok=True)
-    shutil.copyfile(cum_path, os.path.join(tmp, "cumulative_update"))
-    shutil.copyfile(momentum_path, os.path.join(tmp, "momentum"))
+    for name, src in files.items():
+        shutil.copyfile(src, os.path.join(tmp, name))
     shutil.rmtree(dst, ignore_errors=True)
     os.replace(tmp, dst)
     meta_tmp = os.path.join(ckpt_dir, "latest.json.tmp")

@@ -491,3 +491,59 @@ def test_transformers_auto_class_job(tmp_path):
     assert set(loss) == {"worker-a", "worker-b"}
     for w, v in loss.items():
         assert v[3] < v[1], (w, v)
+
+
+def test_collective_job_checkpoint_and_resume(tmp_path):
+    """Checkpoint / resume in collective mode (CPU engine): after every outer step rank 0 writes the global
+    model and the outer momentum; a second run with `resume = true` loads them on every rank, starts at the
+    saved round and finishes the remaining rounds.  A checkpoint of the other aggregation mode is refused."""
+    from safetensors.torch import load_file
+
+    ckpt = str(tmp_path / "ckpt")
+
+    def job(rounds, resume, mode="collective"):
+        return {
+            "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                      "input_names": ["input_ids", "labels"]},
+            "preprocessor": None,
+            "dataset": {"dataset": "toyset"},
+            "rounds": {"avg_samples_between_updates": 40, "update_rounds": rounds, "max_batch_size": 4},
+            "inner_optimizer": {"learning-rate": 3e-3},
+            "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+            "aggregation": {"mode": mode},
+            "checkpoint": {"dir": ckpt, "every": 1, "resume": resume},
+            "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+        }
+
+    def run(sub, j):
+        d = str(tmp_path / sub)
+        os.makedirs(d)
+        return asyncio.run(run_loopback_job(
+            d, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=j, timeout_s=240,
+            write_dataset=lambda p: write_synthetic_token_slices(p, num_slices=6, samples_per_slice=16, seq_len=32,
+                                                                 vocab_size=512)))
+
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cpu"
+    try:
+        a, _, logs_a, _ = run("a", job(2, False))
+        assert a.finished and a.rounds == 2, logs_a[-20:]
+        assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 2}
+        s2 = load_file(os.path.join(ckpt, "round-2", "collective_state"))
+        assert any(k.startswith("prev/") for k in s2) and any(k.startswith("m/") for k in s2)
+        assert sum("collective checkpoint of round" in l for l in logs_a) == 2            # one writer per round
+
+        b, sink_b, logs_b, _ = run("b", job(4, True))
+        assert b.finished and b.rounds == 4, logs_b[-20:]
+        assert sum("resumed from the collective checkpoint of round 2" in l for l in logs_b) == 2   # every rank loads
+        assert {r["round"] for r in sink_b.records} == {3, 4}
+        assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 4}
+        s4 = load_file(os.path.join(ckpt, "round-4", "collective_state"))
+        moved = [k for k in s2 if k.startswith("prev/") and s2[k].dtype.is_floating_point and not torch.equal(s2[k], s4[k])]
+        assert moved                                                                           # training went on
+
+        with pytest.raises(Exception, match="collective mode"):
+            run("c", job(6, True, mode="parameter-server"))
+    finally:
+        os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
