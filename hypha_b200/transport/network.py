@@ -40,6 +40,7 @@ STREAM_CHUNK = 1 << 20
 SPLIT_BIT = 1 << 31              # length-prefix flag of a bulk stream_data frame (raw payload after a CBOR header)
 SPLIT_FRAME_MIN = 4096
 STREAM_ACCEPT_LIMIT = 8          # stream_push.rs:56, stream_pull.rs:71
+MAX_STREAM_HEADER = 1 << 20      # stream_pull.rs:28
 EARLY_STREAM_TTL_S = 30.0        # how long a push stream waits for its receiver to register
 
 
@@ -957,6 +958,8 @@ class Network:
         proto = "/hypha-tensor-stream/pull"
         sid = uuid.uuid4().hex
         hdr = header.to_wire() if hasattr(header, "to_wire") else header
+        if len(cbor2.dumps(hdr)) > MAX_STREAM_HEADER:          # stream_pull.rs:28: resource headers stay below 1 MiB
+            raise NetworkError("pull-stream header larger than 1 MiB")
         st = IncomingStream(peer, proto, hdr, None, asyncio.Queue(64))
         self._streams[sid] = st
         await self._send_to(peer, {"t": "stream_open", "sid": sid, "proto": proto, "header": hdr}, proto)
