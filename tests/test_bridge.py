@@ -34,7 +34,10 @@ def _run_with_bridge(tmp, scenario):
 
         sched.on(M.PROGRESS_PROTOCOL, None, progress)
         work = os.path.join(tmp, "work")
-        sock = os.path.join(tmp, "b.sock")
+        import tempfile
+
+        sock_dir = tempfile.mkdtemp(prefix="hbb", dir="/tmp")      # AF_UNIX paths are limited to 107 bytes
+        sock = os.path.join(sock_dir, "b.sock")
         registry = os.path.join(tmp, "registry")
         os.makedirs(os.path.join(registry, "org", "model"))
         open(os.path.join(registry, "org", "model", "config.json"), "w").write('{"model_type": "gpt2"}')

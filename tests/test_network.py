@@ -383,7 +383,9 @@ def test_nvls_descriptor_exchange_helpers(tmp_path):
 
     from hypha_b200.parallel.nvls import _recv_fds, _send_fds
 
-    path = str(tmp_path / "r0.sock")
+    import tempfile
+
+    path = os.path.join(tempfile.mkdtemp(prefix="hbn", dir="/tmp"), "r0.sock")   # AF_UNIX paths: 107 bytes at most
     srv = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
     srv.bind(path)
     srv.listen(4)

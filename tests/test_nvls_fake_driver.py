@@ -128,6 +128,17 @@ class FakeGroup:
         return out
 
 
+@pytest.fixture
+def sock_dir():
+    """AF_UNIX paths are limited to 107 bytes: keep the sockets out of pytest's (possibly long) basetemp."""
+    import shutil
+    import tempfile
+
+    d = tempfile.mkdtemp(prefix="hbn", dir="/tmp")
+    yield d
+    shutil.rmtree(d, ignore_errors=True)
+
+
 def _run(world, fake, tmp, monkeypatch):
     monkeypatch.setattr(nvls, "_cu", lambda: fake)
     monkeypatch.setattr(nvls, "tensor_from_ptr", lambda ptr, numel, dtype, device: torch.zeros(numel, dtype=dtype))
@@ -154,9 +165,9 @@ def _run(world, fake, tmp, monkeypatch):
 
 
 @pytest.mark.parametrize("world", [2, 4])
-def test_alloc_nvls_choreography(world, tmp_path, monkeypatch):
+def test_alloc_nvls_choreography(world, sock_dir, monkeypatch):
     fake = FakeCu()
-    groups, results = _run(world, fake, str(tmp_path), monkeypatch)
+    groups, results = _run(world, fake, sock_dir, monkeypatch)
     assert all(isinstance(b, nvls.NvlsBuffer) for b in results), results
     for r, b in enumerate(results):
         assert b.mc_ptr and len(b.peer_ptrs) == world and len(set(b.peer_ptrs)) == world and b.local.numel() == 1 << 20
@@ -168,7 +179,7 @@ def test_alloc_nvls_choreography(world, tmp_path, monkeypatch):
     per_rank_imports = [sum(1 for d, n in fake.log if d == r and n == "cuMemImportFromShareableHandle") for r in range(world)]
     assert per_rank_imports == [world - 1] + [world] * (world - 1)      # peers' memory (+ the multicast object)
     assert len({g.exchanges for g in groups}) == 1                       # every rank made the same number of exchanges
-    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith(".sock")]
+    assert not [f for f in os.listdir(sock_dir) if f.endswith(".sock")]
     for b in results:
         b.close()
         assert b.mc_ptr == 0
@@ -181,15 +192,15 @@ def test_alloc_nvls_choreography(world, tmp_path, monkeypatch):
     ("cuMulticastAddDevice", 2, 3),
     ("cuMulticastBindMem", 1, 4),             # binding fails on one rank                    -> nobody maps the view
 ])
-def test_alloc_nvls_failure_is_agreed_by_all_ranks(call, dev, exchanges, tmp_path, monkeypatch):
+def test_alloc_nvls_failure_is_agreed_by_all_ranks(call, dev, exchanges, sock_dir, monkeypatch):
     world = 3
     fake = FakeCu(fail={(call, dev): True})
-    groups, results = _run(world, fake, str(tmp_path), monkeypatch)
+    groups, results = _run(world, fake, sock_dir, monkeypatch)
     assert all(isinstance(e, nvls.NvlsUnavailable) for e in results), results
     assert all(f"rank {dev}" in str(e) and call.replace("cuMemImportFromShareableHandle", "mport") in str(e) for e in results), results
     assert [g.exchanges for g in groups] == [exchanges] * world         # still aligned: the group stays usable
     assert not any(g.buffers for g in groups)
-    assert not [f for f in os.listdir(str(tmp_path)) if f.endswith(".sock")]
+    assert not [f for f in os.listdir(sock_dir) if f.endswith(".sock")]
     # what was mapped before the failure has been unmapped again
     maps = sum(1 for d, n in fake.log if n == "cuMemMap")
     unmaps = sum(1 for d, n in fake.log if n == "cuMemUnmap")
