@@ -309,13 +309,26 @@ class DiLoCoOuter:
                 return c
         raise RuntimeError("no live rank left")
 
+    def owners(self) -> Dict[int, int]:
+        """shard -> rank that currently runs its outer update.  Replicated bookkeeping: every rank applies the
+        same membership events in the same order, so the maps agree without communication."""
+        own = getattr(self, "_owner", None)
+        if own is None:
+            own = self._owner = {r: r for r in range(self.world)}
+        return own
+
     def drop_ranks(self, dead: List[int]) -> None:
         """Shrink the membership; orphaned shards are adopted with theta_outer re-derived from the
-        common bf16 anchor (every rank holds it) and zero momentum."""
+        common bf16 anchor (every rank holds it) and zero momentum.  "Orphaned" includes shards a now-dead
+        rank had adopted earlier (cascaded failures): every shard whose owner is not live gets a new one."""
         live = [r for r in self.members() if r not in dead]
         self.set_members(live)
-        for k in dead:
-            if self.adopter_of(k, live) == self.rank and k not in self.segments:
+        own = self.owners()
+        for k in range(self.world):
+            if own[k] in live:
+                continue
+            own[k] = self.adopter_of(k, live)
+            if own[k] == self.rank and k not in self.segments:
                 b, l = shard_bounds(self.n, self.world, k)
                 theta = self.anchor_buf.local[b:b + l].float()
                 self.segments[k] = (b, l, theta, torch.zeros_like(theta))
@@ -324,6 +337,7 @@ class DiLoCoOuter:
         """A (re)joined rank takes its shard back at a round boundary."""
         if rank != self.rank:
             self.segments.pop(rank, None)
+        self.owners()[rank] = rank
         self.set_members(sorted(set(self.members()) | {rank}))
 
     def sync_epoch(self) -> None:
@@ -349,6 +363,10 @@ class DiLoCoOuter:
             for r in new:
                 self.readmit(r)
         self.round = max(int(r) for r in exchange(int(self.round)))
+        maps = exchange(None if joining else dict(self.owners()))       # who runs which dead rank's shard
+        if joining:
+            self._owner = dict(next(m for m in maps if m is not None))
+            self._owner[self.rank] = self.rank
         self.sync_epoch()
         if joining:
             self.reseed_from(survivors[0])

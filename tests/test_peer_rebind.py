@@ -290,3 +290,70 @@ def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
             assert [_resolve(C, members[r], name, x) for x in range(world)] == \
                    [members[x].buffers[name].local.data_ptr() for x in range(world)]
     assert dead not in engines[3].trainer.outer.segments                       # the adopter gave the shard back
+
+
+def test_outer_membership_bookkeeping_on_cpu():
+    """`DiLoCoOuter` drop / adopt / readmit without a GPU: every shard has exactly one owner at all times, the
+    adopter is the next live rank in cyclic order, adopted shards are re-derived from the common anchor, and a
+    re-admitted rank gets its shard back."""
+    from hypha_b200.parallel.diloco import DiLoCoOuter, shard_bounds
+
+    world, n = 5, 5 * 4096
+    anchor = torch.arange(n, dtype=torch.float32).to(torch.bfloat16)
+
+    def outer_of(rank):
+        o = object.__new__(DiLoCoOuter)
+        o.world, o.rank, o.n, o.backend = world, rank, n, "fused"
+        o.anchor_buf = types.SimpleNamespace(local=anchor)
+        b, l = shard_bounds(n, world, rank)
+        o.segments = {rank: (b, l, anchor[b:b + l].float(), torch.zeros(l))}
+        o.set_members(list(range(world)))
+        return o
+
+    outers = {r: outer_of(r) for r in range(world)}
+
+    def owners():
+        own = {}
+        for r, o in outers.items():
+            if r in o.members():                      # a dropped rank's own view does not count
+                for k in o.segments:
+                    own.setdefault(k, []).append(r)
+        return own
+
+    assert owners() == {r: [r] for r in range(world)}
+    live = [0, 1, 2, 3, 4]
+
+    def exactly_one_live_owner():
+        own = owners()
+        assert sorted(own) == list(range(world)), f"shards without an owner: {sorted(set(range(world)) - set(own))}"
+        assert all(len(v) == 1 and v[0] in live for v in own.values()), own
+        maps = [outers[r].owners() for r in live]
+        assert all(m == maps[0] for m in maps)                         # replicated bookkeeping agrees
+        assert {k: v[0] for k, v in own.items()} == maps[0]            # ... and matches who holds the segments
+
+    # cascaded failures: 3 dies (4 adopts its shard), then 4 dies (0 must take over BOTH 4's shard and the
+    # adopted shard 3), then 0 dies (1 inherits 0, 3 and 4)
+    for dead in ([3], [4], [0]):
+        live = [r for r in live if r not in dead]
+        for r in live:
+            outers[r].drop_ranks(dead)
+        for r in dead:
+            outers[r].set_members([])                 # that process is gone
+        exactly_one_live_owner()
+    assert sorted(outers[1].segments) == [0, 1, 3, 4]
+    # rank 4 comes back (fresh state: only its own shard), takes shard 4 back; 3 stays where it is
+    outers[4] = outer_of(4)
+    outers[4]._owner = dict(outers[1].owners())       # what `admit` hands a newcomer
+    live = [1, 2, 4]
+    for r in live:
+        outers[r].set_members([1, 2] if r != 4 else live)
+        outers[r].readmit(4)
+    exactly_one_live_owner()
+    assert sorted(outers[1].segments) == [0, 1, 3] and sorted(outers[4].segments) == [4]
+    # a later failure must not hand shard 3 to a second owner (its cyclic successor 4 is alive again)
+    live = [1, 4]
+    for r in live:
+        outers[r].drop_ranks([2])
+    outers[2].set_members([])
+    exactly_one_live_owner()
+    assert outers[1].owners()[3] == 1 and outers[4].owners()[2] == 4
