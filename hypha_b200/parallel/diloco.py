@@ -445,10 +445,21 @@ class DiLoCoOuter:
         return 2 * 2 * self.shard_len * (self.world - 1)
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
-        return {"theta_outer": self.theta_outer, "momentum": self.momentum,
-                "round": torch.tensor(self.round), "shard_begin": torch.tensor(self.shard_begin)}
+        sd = {"theta_outer": self.theta_outer, "momentum": self.momentum,
+              "round": torch.tensor(self.round), "shard_begin": torch.tensor(self.shard_begin)}
+        if self.backend == "fused":
+            # the pseudo-gradient is theta - anchor, anchor = the weights right after the last outer step (bf16,
+            # full length, one copy per rank): part of the state unless the checkpoint is taken exactly at a
+            # round boundary.  Shards adopted from dropped ranks are NOT saved: checkpoint with full membership.
+            sd["anchor"] = self.anchor_buf.local
+        return sd
 
     def load_state_dict(self, sd) -> None:
         self.theta_outer.copy_(sd["theta_outer"])
         self.momentum.copy_(sd["momentum"])
         self.round = int(sd["round"])
+        if self.backend == "fused":
+            if "anchor" in sd:
+                self.anchor_buf.local.copy_(sd["anchor"])
+            else:       # checkpoint written before the anchor was saved: only right at a round boundary
+                self.anchor_buf.local.copy_(self.opt.params)

@@ -357,3 +357,66 @@ def test_outer_membership_bookkeeping_on_cpu():
     outers[2].set_members([])
     exactly_one_live_owner()
     assert outers[1].owners()[3] == 1 and outers[4].owners()[2] == 4
+
+
+def test_outer_step_launch_shape_rules(monkeypatch):
+    """Host-side launch decisions of the fused outer step (tuned on 8xB200, profiles/outer_sweep_n8_v2.json): one
+    chunk per 128 MB of bf16 delta (at most 16) from 4 ranks up, no pipelining at N<=2; 32 link CTAs with NVLS, 48
+    with P2P, 66 at N<=2; multicast only when both buffers are NVLS-bound AND every rank takes part."""
+    from hypha_b200.parallel.diloco import DiLoCoConfig, DiLoCoOuter
+
+    monkeypatch.delenv("HYPHA_OUTER_CHUNKS", raising=False)
+    monkeypatch.delenv("HYPHA_OUTER_LINK_CTAS", raising=False)
+
+    def outer(world, n, mc=False, members=None):
+        o = object.__new__(DiLoCoOuter)
+        o.world, o.rank, o.n, o.cfg, o.use_nvls = world, 0, n, DiLoCoConfig(), world >= 4
+        o.delta_buf = types.SimpleNamespace(mc_ptr=0xd000 if mc else 0)
+        o.param_buf = types.SimpleNamespace(mc_ptr=0xe000 if mc else 0)
+        o.set_members(members if members is not None else list(range(world)))
+        return o
+
+    llama8b = 8_030_261_248
+    assert outer(2, llama8b)._pipeline_shape() == (1, 66)
+    assert outer(8, llama8b, mc=True)._pipeline_shape() == (16, 32)
+    assert outer(8, llama8b, mc=False)._pipeline_shape() == (16, 48)
+    assert outer(4, 64 << 20)._pipeline_shape() == (1, 48)                      # 128 MB of delta: one chunk
+    assert outer(4, 320 << 20)._pipeline_shape()[0] == 5
+    assert outer(8, llama8b, mc=True)._multicast_ptrs() == (0xd000, 0xe000)
+    assert outer(8, llama8b, mc=True, members=[0, 1, 2, 3, 4, 5, 6])._multicast_ptrs() == (0, 0)   # a rank is missing
+    assert outer(8, llama8b, mc=True, members=[0, 1, 2, 3, 4, 5, 6])._pipeline_shape() == (16, 48)
+    assert outer(2, llama8b, mc=True)._multicast_ptrs() == (0, 0)               # NVLS is not used below 4 ranks
+    monkeypatch.setenv("HYPHA_OUTER_CHUNKS", "3")
+    monkeypatch.setenv("HYPHA_OUTER_LINK_CTAS", "20")
+    assert outer(8, llama8b)._pipeline_shape() == (3, 20)
+
+
+def test_fused_outer_state_includes_the_anchor():
+    """Resuming the fused engine mid-round in a NEW process: the anchor (weights after the last outer step) is
+    part of the outer state -- without it the next pseudo-gradient would be taken against the fresh process's
+    initial weights."""
+    from hypha_b200.parallel.diloco import DiLoCoOuter
+
+    n = 4096
+
+    def outer(params, anchor, backend="fused"):
+        o = object.__new__(DiLoCoOuter)
+        o.backend, o.round, o.shard_begin = backend, 7, 0
+        o.theta_outer, o.momentum = torch.randn(n), torch.randn(n)
+        o.opt = types.SimpleNamespace(params=params)
+        o.anchor_buf = types.SimpleNamespace(local=anchor)
+        return o
+
+    trained = torch.randn(n).to(torch.bfloat16)
+    a = outer(trained + 1, trained.clone())                               # mid-round: params moved away from the anchor
+    sd = {k: v.clone() for k, v in a.state_dict().items()}
+    assert torch.equal(sd["anchor"], trained)
+    b = outer(torch.zeros(n, dtype=torch.bfloat16), torch.zeros(n, dtype=torch.bfloat16))   # a fresh process
+    b.load_state_dict(sd)
+    assert torch.equal(b.anchor_buf.local, trained) and b.round == 7 and torch.equal(b.theta_outer, a.theta_outer)
+    # old checkpoints (no anchor): treated as taken at a round boundary
+    del sd["anchor"]
+    c = outer(trained.clone(), torch.zeros(n, dtype=torch.bfloat16))
+    c.load_state_dict(sd)
+    assert torch.equal(c.anchor_buf.local, trained)
+    assert "anchor" not in outer(trained, trained, backend="local").state_dict()
