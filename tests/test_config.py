@@ -1,5 +1,4 @@
 """Layered config tests (model: crates/config/src/lib.rs:642-910, worker/src/config.rs:618-651)."""
-import os
 import tomllib
 
 import pytest

@@ -5,13 +5,10 @@ full GPT-2 small variant."""
 import asyncio
 import json
 import os
-import sys
 
 import pytest
 import torch
 
-from hypha_b200 import config as C
-from hypha_b200 import roles
 from hypha_b200.executor.dataset import write_synthetic_token_slices
 from hypha_b200.models.gpt2 import GPT2Config
 from hypha_b200.local_cluster import run_loopback_job

@@ -107,7 +107,6 @@ def test_rmsnorm_fwd_bwd(C, rows, cols):
 
 def test_add_norm_linear_and_swiglu_linear(C):
     from hypha_b200 import ops
-    from hypha_b200.ops.functional import _rmsnorm_ref
 
     torch.manual_seed(0)
     T, H, N, I = 200, 256, 384, 512

@@ -5,7 +5,6 @@ membership changes with the cumulative update for a newcomer."""
 import asyncio
 import os
 
-import pytest
 import torch
 from safetensors.torch import load_file, save_file
 
