@@ -544,3 +544,78 @@ def test_collective_job_checkpoint_and_resume(tmp_path):
             run("c", job(6, True, mode="parameter-server"))
     finally:
         os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
+
+
+def test_job_survives_two_lost_workers_one_after_the_other(tmp_path):
+    """Cascaded failures in parameter-server mode: worker-c dies after round 1, worker-b after round 2; with
+    `elastic.min_workers = 1` the last worker and the aggregate worker finish all rounds."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 48, "update_rounds": 4, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "elastic": {"enabled": True, "min_workers": 1},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def chaos(nodes, logs):
+        for victim, after in (("worker-c", 1), ("worker-b", 2)):
+            while not any(f"round {after}:" in l for l in logs):
+                await asyncio.sleep(0.1)
+            nodes[victim].stop.set()
+
+    outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+        tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+        write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=9, samples_per_slice=16, seq_len=32,
+                                                             vocab_size=512), timeout_s=300, chaos=chaos))
+    assert outcome.finished, logs[-25:]
+    assert outcome.rounds == 4 and sorted(outcome.removed_workers) == ["worker-b", "worker-c"]
+    assert sum("Finished training of 4 DiLoCo update rounds" in l for l in logs) == 1      # worker-a alone
+    rounds_a = sorted(r["round"] for r in sink.records if r["worker_id"] == "worker-a" and r["metric_name"] == "loss")
+    assert rounds_a == [1, 2, 3, 4]
+
+
+def test_collective_job_survives_two_lost_ranks_down_to_one(tmp_path):
+    """Collective aggregation under cascaded failures: three gloo ranks, worker-c dies after round 1, worker-b after
+    round 2; the last rank goes on alone (its group has one member, the outer step needs no collective)."""
+    tmp = str(tmp_path)
+    job = {
+        "model": {"repository": "local/gpt2-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                  "input_names": ["input_ids", "labels"]},
+        "preprocessor": None,
+        "dataset": {"dataset": "toyset"},
+        "rounds": {"avg_samples_between_updates": 48, "update_rounds": 4, "max_batch_size": 4},
+        "inner_optimizer": {"learning-rate": 3e-3},
+        "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"mode": "collective"},
+        "elastic": {"enabled": True, "min_workers": 1},
+        "resources": {"num_workers": 3, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                      "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+    }
+
+    async def chaos(nodes, logs):
+        for victim, after in (("worker-c", 1), ("worker-b", 2)):
+            while not any(f"round {after}:" in l for l in logs):
+                await asyncio.sleep(0.1)
+            nodes[victim].stop.set()
+
+    os.environ["HYPHA_EXECUTOR_DEVICE"] = "cpu"
+    try:
+        outcome, sink, logs, nodes = asyncio.run(run_loopback_job(
+            tmp, repo="local/gpt2-tiny", write_model_config=lambda p: GPT2Config.tiny().to_json(p), job=job, num_workers=3,
+            chaos=chaos, timeout_s=300,
+            write_dataset=lambda d: write_synthetic_token_slices(d, num_slices=9, samples_per_slice=16, seq_len=32,
+                                                                 vocab_size=512)))
+    finally:
+        os.environ.pop("HYPHA_EXECUTOR_DEVICE", None)
+    assert outcome.finished, logs[-30:]
+    assert outcome.rounds == 4 and sorted(outcome.removed_workers) == ["worker-b", "worker-c"]
+    assert sum("Finished training of 4 DiLoCo update rounds" in l for l in logs) == 1
+    assert any("regrouped as rank 0 of 1" in l for l in logs), [l for l in logs if "regroup" in l]
