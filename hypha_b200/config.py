@@ -244,6 +244,9 @@ class AggregationSection:
                     "GPUs, gloo all-reduce on CPU; no aggregate worker is allocated)", "parameter-server")
     rendezvous: Optional[str] = doc("`tcp://host:port` the ranks of a collective job meet on "
                                     "(default: a free port on 127.0.0.1)", None)
+    weighting: str = doc("`uniform` (every worker's pseudo-gradient counts 1/N, like the reference's intent) or "
+                         "`samples` (weighted by the samples each worker processed in the round; matters when "
+                         "performance-aware pacing gives workers different shares)", "uniform")
 
 
 @dataclass
@@ -575,6 +578,9 @@ def validate(cfg: Any) -> Any:
         if job.aggregation.mode not in ("parameter-server", "collective"):
             raise _err(meta, "scheduler.job.aggregation.mode",
                        f"unknown aggregation mode `{job.aggregation.mode}` (parameter-server | collective)")
+        if job.aggregation.weighting not in ("uniform", "samples"):
+            raise _err(meta, "scheduler.job.aggregation.weighting",
+                       f"unknown weighting `{job.aggregation.weighting}` (uniform | samples)")
         if job.aggregation.rendezvous and not job.aggregation.rendezvous.startswith("tcp://"):
             raise _err(meta, "scheduler.job.aggregation.rendezvous", "rendezvous must be a tcp://host:port address")
     if isinstance(cfg, DataConfig) and cfg.dataset_path and not os.path.isdir(cfg.dataset_path):

@@ -207,12 +207,14 @@ PYBIND11_MODULE(_core, m) {
            const std::vector<uint64_t>& prev_m_offsets, const std::string& prev_cum_path,
            const std::vector<uint64_t>& prev_cum_offsets, const std::string& out_u_path,
            const std::string& out_m_path, const std::string& out_cum_path,
-           const std::vector<uint64_t>& out_offsets, double lr, double mu, int threads) {
+           const std::vector<uint64_t>& out_offsets, double lr, double mu, int threads,
+           const std::vector<double>& weights) {
           PsRoundStats s;
           {
             py::gil_scoped_release nogil;
             s = ps_fused_round(in_paths, in_offsets, numels, prev_m_path, prev_m_offsets, prev_cum_path,
-                               prev_cum_offsets, out_u_path, out_m_path, out_cum_path, out_offsets, lr, mu, threads);
+                               prev_cum_offsets, out_u_path, out_m_path, out_cum_path, out_offsets, lr, mu, threads,
+                               weights);
           }
           py::dict d;
           d["elements"] = s.elements; d["bytes_read"] = s.bytes_read; d["bytes_written"] = s.bytes_written;
@@ -222,6 +224,6 @@ PYBIND11_MODULE(_core, m) {
         py::arg("in_paths"), py::arg("in_offsets"), py::arg("numels"), py::arg("prev_m_path"),
         py::arg("prev_m_offsets"), py::arg("prev_cum_path"), py::arg("prev_cum_offsets"), py::arg("out_u_path"),
         py::arg("out_m_path"), py::arg("out_cum_path"), py::arg("out_offsets"), py::arg("lr"), py::arg("mu"),
-        py::arg("threads") = 0,
+        py::arg("threads") = 0, py::arg("weights") = std::vector<double>{},
         "One parameter-server round (mean, momentum, Nesterov, cumulative update) over mmapped safetensors files.");
 }

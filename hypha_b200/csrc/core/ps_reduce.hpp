@@ -93,8 +93,12 @@ inline PsRoundStats ps_fused_round(const std::vector<std::string>& in_paths,
                                    const std::string& prev_cum_path, const std::vector<uint64_t>& prev_cum_offsets,
                                    const std::string& out_u_path, const std::string& out_m_path,
                                    const std::string& out_cum_path, const std::vector<uint64_t>& out_offsets,
-                                   double lr, double mu, int threads) {
+                                   double lr, double mu, int threads,
+                                   const std::vector<double>& weights = {}) {
+  // weights: empty = true mean (every input counts 1/N); else one weight per input, normalised by the caller
+  // (sample-weighted mean: w_k = samples_k / sum of samples)
   const size_t N = in_paths.size(), T = numels.size();
+  if (!weights.empty() && weights.size() != N) throw std::invalid_argument("weights: one per worker file");
   if (N == 0) throw std::invalid_argument("no worker files");
   if (in_offsets.size() != N) throw std::invalid_argument("in_offsets: one list per worker file");
   for (auto& o : in_offsets) if (o.size() != T) throw std::invalid_argument("in_offsets: one offset per tensor");
@@ -137,6 +141,9 @@ inline PsRoundStats ps_fused_round(const std::vector<std::string>& in_paths,
   }
 
   const float inv = 1.0f / static_cast<float>(N), fmu = static_cast<float>(mu), flr = static_cast<float>(lr);
+  const bool weighted = !weights.empty();
+  std::vector<float> w(N, 1.0f);
+  for (size_t k = 0; weighted && k < N; ++k) w[k] = static_cast<float>(weights[k]);
   std::atomic<size_t> next{0};
   auto work = [&]() {
     float acc[1024];
@@ -147,13 +154,24 @@ inline PsRoundStats ps_fused_round(const std::vector<std::string>& in_paths,
       for (uint64_t a = 0; a < p.n; a += 1024) {
         const uint64_t b = std::min<uint64_t>(1024, p.n - a);
         const unaligned_f32* s0 = reinterpret_cast<const unaligned_f32*>(p.in[0]) + a;
-        for (uint64_t j = 0; j < b; ++j) acc[j] = s0[j];
-        for (size_t k = 1; k < N; ++k) {
-          const unaligned_f32* s = reinterpret_cast<const unaligned_f32*>(p.in[k]) + a;
-          for (uint64_t j = 0; j < b; ++j) acc[j] += s[j];
+        if (weighted) {
+          const float w0 = w[0];
+          for (uint64_t j = 0; j < b; ++j) acc[j] = w0 * s0[j];
+          for (size_t k = 1; k < N; ++k) {
+            const unaligned_f32* s = reinterpret_cast<const unaligned_f32*>(p.in[k]) + a;
+            const float wk = w[k];
+            for (uint64_t j = 0; j < b; ++j) acc[j] += wk * s[j];
+          }
+        } else {
+          for (uint64_t j = 0; j < b; ++j) acc[j] = s0[j];
+          for (size_t k = 1; k < N; ++k) {
+            const unaligned_f32* s = reinterpret_cast<const unaligned_f32*>(p.in[k]) + a;
+            for (uint64_t j = 0; j < b; ++j) acc[j] += s[j];
+          }
         }
+        const float scale = weighted ? 1.0f : inv;
         for (uint64_t j = 0; j < b; ++j) {
-          const float g = acc[j] * inv;
+          const float g = acc[j] * scale;
           const float m = p.m ? fmu * p.m[a + j] + g : g;
           const float u = flr * (fmu * m + g);
           p.om[a + j] = m;

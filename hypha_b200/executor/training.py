@@ -249,11 +249,27 @@ class ReplicatedNesterov:
         self.m: Optional[Dict[str, torch.Tensor]] = None
 
     @staticmethod
-    def _mean(g: torch.Tensor, group: _Group, exclude: int = 0) -> torch.Tensor:
+    def _mean(g: torch.Tensor, group: _Group, exclude: int = 0, weight: Optional[float] = None) -> torch.Tensor:
+        """``weight`` = this rank's share of the round's samples (already normalised over the group): the mean
+        over samples is then just the sum of the weighted pseudo-gradients."""
+        if weight is not None:
+            g.mul_(weight)
+            if group.world > 1:
+                group.all_reduce(g)
+            return g
         if group.world > 1:
             group.all_reduce(g)
             g.div_(max(1, group.world - exclude))      # ranks that just joined contribute a zero delta
         return g
+
+    @staticmethod
+    def sample_share(samples: int, group: _Group, device: str = "cpu") -> Optional[float]:
+        """samples / (sum over the group); None when nobody processed anything (all ranks just joined)."""
+        t = torch.tensor([float(samples)], device=device)
+        if group.world > 1:
+            group.all_reduce(t)
+        total = float(t.item())
+        return (float(samples) / total) if total > 0 else None
 
     @staticmethod
     def _check_round(round_no: int, group: _Group, device: str = "cpu") -> None:
@@ -267,14 +283,20 @@ class ReplicatedNesterov:
             raise RuntimeError(f"ranks disagree on the round being reduced ({int(-tag[1])}..{int(tag[0])} vs {round_no})")
 
     @torch.no_grad()
-    def step(self, loop: "InnerLoop", group, round_no: int = -1, exclude: int = 0) -> None:
+    def step(self, loop: "InnerLoop", group, round_no: int = -1, exclude: int = 0,
+             samples: Optional[int] = None) -> None:
+        """``samples``: this rank's sample count of the round -> mean over samples (`aggregation.weighting =
+        "samples"`); None -> mean over ranks."""
         if isinstance(group, int):                       # plain world size: single rank / tests
             group = _Group("solo", None, 0, 1) if group <= 1 else _Group("default", None, 0, group)
         first = self.m is None
         self._check_round(round_no, group, getattr(loop, "device", "cpu"))
+        weight = None if samples is None else self.sample_share(samples, group, getattr(loop, "device", "cpu"))
+        if weight is not None:
+            exclude = 0                                  # newcomers have zero samples: their weight is zero already
         if loop.flat:
             net = loop.model.net
-            g = self._mean(loop.opt.master - loop.prev, group, exclude)
+            g = self._mean(loop.opt.master - loop.prev, group, exclude, weight)
             m = g.clone() if first else self.m["flat"].mul_(self.mu).add_(g)
             self.m = {"flat": m}
             loop.prev.add_(self.lr * (self.mu * m + g))
@@ -282,7 +304,7 @@ class ReplicatedNesterov:
             net.flat.data.copy_(loop.prev)
             return
         sd = loop.model.state_dict()
-        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), group, exclude)  # phase 1: may raise
+        means = {k: self._mean(v.detach().float() - loop.prev[k].float(), group, exclude, weight)  # phase 1: may raise
                  for k, v in sd.items() if v.dtype.is_floating_point}
         if first:
             self.m = {}
@@ -398,7 +420,8 @@ class _TrainerEngine:
         print(f"membership generation {mem['generation']}: ranks {new} admitted into the fused engine", flush=True)
         self._pending, self.joining = [], False
 
-    def outer_step(self, round_no: int = -1) -> None:
+    def outer_step(self, round_no: int = -1, samples: Optional[int] = None) -> None:
+        # `samples` is ignored: the fused kernel takes the mean over ranks (equal shares on a homogeneous box)
         outer = self.trainer.outer
         if self.joining:
             self._admit()                 # the survivors run this round's outer step without the newcomer
@@ -520,8 +543,8 @@ class _GenericEngine:
         print(f"membership generation {membership['generation']}: regrouped as rank {members.index(me)} of "
               f"{len(members)}", flush=True)
 
-    def outer_step(self, round_no: int = -1) -> None:
-        self.outer.step(self.loop, self.group, round_no, self._exclude)
+    def outer_step(self, round_no: int = -1, samples: Optional[int] = None) -> None:
+        self.outer.step(self.loop, self.group, round_no, self._exclude, samples)
         self._exclude = 0
 
 
@@ -583,7 +606,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
 
     while True:
         loss_sum = torch.zeros((), device=device)
-        steps, counter, tokens = 0, (0 if joining else -1), 0
+        steps, counter, tokens, samples = 0, (0 if joining else -1), 0, 0
         sync()
         t_round = time.perf_counter()
         while counter != 0:
@@ -594,6 +617,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
             steps += 1
             first = next(iter(batch.values()))
             bs = int(first.shape[0])
+            samples += bs
             tokens += int(first.numel()) if first.dim() == 2 and not first.dtype.is_floating_point else bs
             counter = status.report(bs, counter)
         status.drain()
@@ -615,7 +639,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         t_outer = time.perf_counter()
         for attempt in range(240):
             try:
-                engine.outer_step(round_no)        # every rank enters: the kernel / all-reduce is the barrier
+                # every rank enters: the kernel / all-reduce is the barrier
+                engine.outer_step(round_no, samples if config.get("weighting") == "samples" else None)
                 break
             except CollectiveBroken as exc:
                 # a rank died inside the collective: nothing was applied.  Ask the scheduler (it learns of the
@@ -713,7 +738,7 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
                 print(f"joined a running job after round {round_no - 1} ({len(cum)} tensors of cumulative update)", flush=True)
             while True:
                 loss_sum = torch.zeros((), device=device)
-                steps, counter = 0, -1
+                steps, counter, samples = 0, -1, 0
                 while counter != 0:
                     batch = next(batches)
                     loss_sum += loop.step(batch)
@@ -721,11 +746,16 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
                         time.sleep(delay)
                     steps += 1
                     bs = int(next(iter(batch.values())).shape[0])
+                    samples += bs
                     counter = status.report(bs, counter)
                 status.drain()
                 session.send_status("update")
                 name = f"{round_no}_local_gradients.safetensors"
-                save_file(loop.delta_state_dict(), os.path.join(work_dir, name))
+                delta = loop.delta_state_dict()
+                if config.get("weighting") == "samples":
+                    # the aggregate worker takes the mean over samples when every worker reports its count
+                    delta["__samples__"] = torch.tensor([float(samples)], dtype=torch.float32)
+                save_file(delta, os.path.join(work_dir, name))
                 session.send_resource(config["updates"], name)
                 session.send_status({"metrics": {"round": round_no, "metrics": {"loss": float(loss_sum.item() / max(1, steps))}}})
                 print(f"round {round_no}: {steps} inner steps, mean loss {float(loss_sum.item() / max(1, steps)):.4f}; "

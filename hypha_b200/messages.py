@@ -361,6 +361,9 @@ class TrainExecutorConfig:
     # B200 extension: a replacement worker dispatched into a running parameter-server job.  It first waits
     # for the aggregate worker's cumulative update U (theta = theta_0(seed) + U), then trains normally.
     join: Optional[dict] = None
+    # B200 extension: "samples" -> the executor reports the samples it processed with its pseudo-gradient and the
+    # mean is taken over samples instead of over workers (absent / "uniform": the reference's 1/N intent)
+    weighting: Optional[str] = None
 
     def to_wire(self) -> dict:
         d = {"model": self.model.to_wire(), "data": self.data.to_wire(), "updates": self.updates.to_wire(),
@@ -374,6 +377,8 @@ class TrainExecutorConfig:
             d["collective"] = dict(self.collective)
         if self.join is not None:
             d["join"] = dict(self.join)
+        if self.weighting and self.weighting != "uniform":
+            d["weighting"] = self.weighting
         return d
 
     @classmethod
@@ -383,7 +388,8 @@ class TrainExecutorConfig:
                    Preprocessor.from_wire(d["preprocessor"]) if d.get("preprocessor") else None,
                    LRScheduler.from_wire(d["scheduler"]) if d.get("scheduler") else None,
                    dict(d["collective"]) if d.get("collective") else None,
-                   dict(d["join"]) if d.get("join") else None)
+                   dict(d["join"]) if d.get("join") else None,
+                   str(d["weighting"]) if d.get("weighting") else None)
 
 
 @dataclass

@@ -143,7 +143,8 @@ class DiLoCoJobRun:
         return M.TrainExecutorConfig(model=self.model, data=M.Fetch.scheduler(self.net.peer_id, self.job.dataset.dataset),
                                      updates=M.Send.to_peers([self.ps.peer_id]),
                                      results=M.Receive.from_peers([self.ps.peer_id]),
-                                     optimizer=self.adam, batch_size=bs, preprocessor=self.pre)
+                                     optimizer=self.adam, batch_size=bs, preprocessor=self.pre,
+                                     weighting=self.job.aggregation.weighting)
 
     async def _dispatch_train(self, w: WorkerHandle, tcfg: M.TrainExecutorConfig) -> None:
         spec = M.JobSpec(self.job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))

@@ -314,7 +314,8 @@ class ParameterServerExecutor:
                         None, lambda: outer_round(paths, work_dir, cfg.optimizer.learning_rate, cfg.optimizer.momentum))
                     out = stats["path"]
                     self.log(f"[ps {spec.job_id[:8]}] round {rnd}: reduced {len(paths)} x {stats['elements']} elements in "
-                             f"{stats['seconds'] * 1e3:.1f} ms ({'native, ' + str(stats['threads']) + ' threads' if stats['native'] else 'torch fallback'})")
+                             f"{stats['seconds'] * 1e3:.1f} ms ({'native, ' + str(stats['threads']) + ' threads' if stats['native'] else 'torch fallback'})"
+                             + (f", sample weights {[round(w, 3) for w in stats['weights']]}" if stats.get("weights") else ""))
                     # Tell the scheduler the round is complete BEFORE distributing the result: a worker
                     # that gets its file early would otherwise ack ("update-received") against the old
                     # round number and be told to continue (the reference sends results first,

@@ -79,9 +79,38 @@ def _abs_offsets(header: Dict[str, dict], start: int, names: List[str]) -> List[
     return [start + header[n]["data_offsets"][0] for n in names]
 
 
+SAMPLES_KEY = "__samples__"       # optional F32 [1] tensor in a worker file: samples it processed this round
+
+
+def read_samples(path: str, header: Dict[str, dict], start: int) -> Optional[float]:
+    e = header.get(SAMPLES_KEY)
+    if e is None or e["dtype"] != "F32" or (e["data_offsets"][1] - e["data_offsets"][0]) != 4:
+        return None
+    with open(path, "rb") as f:
+        f.seek(start + e["data_offsets"][0])
+        (v,) = struct.unpack("<f", f.read(4))
+    return float(v)
+
+
+def sample_weights(paths: List[str], heads=None) -> Optional[List[float]]:
+    """``w_k = samples_k / sum`` when EVERY worker file carries a positive sample count, else None (= true
+    mean).  With performance-aware pacing workers process different numbers of samples per round; weighting
+    the pseudo-gradients by them is the mean over samples instead of over workers."""
+    heads = heads or [read_header(p) for p in paths]
+    counts = [read_samples(p, h, s) for p, (h, s) in zip(paths, heads)]
+    if any(c is None or not (c > 0) for c in counts):
+        return None
+    total = sum(counts)
+    return [c / total for c in counts]
+
+
 def _native_plan(paths: List[str], momentum_path: Optional[str], cum_path: Optional[str]):
     """Headers of all files if the fast path applies, else None."""
     heads = [read_header(p) for p in paths]
+    for h, _ in heads:
+        if SAMPLES_KEY in h and h[SAMPLES_KEY]["dtype"] != "F32":
+            return None
+    heads = [({k: v for k, v in h.items() if k != SAMPLES_KEY}, s) for h, s in heads]
     first = heads[0][0]
     names = list(first)
     for h, _ in heads:
@@ -112,6 +141,7 @@ def outer_round(paths: List[str], work_dir: str, lr: float, mu: float, *, thread
     out = os.path.join(work_dir, "gradient_update")
     have_m = m_path if os.path.exists(m_path) else None
     have_c = c_path if os.path.exists(c_path) else None
+    weights = sample_weights(paths)
     plan = None if force_fallback else _native_plan(paths, have_m, have_c)
     if plan is not None:
         heads, names, (mh, ch) = plan
@@ -124,15 +154,16 @@ def outer_round(paths: List[str], work_dir: str, lr: float, mu: float, *, thread
             paths, [_abs_offsets(h, s, names) for h, s in heads], numels,
             have_m or "", _abs_offsets(mh[0], mh[1], names) if mh else [],
             have_c or "", _abs_offsets(ch[0], ch[1], names) if ch else [],
-            out, m_path + ".new", c_path + ".new", [out_off[n] for n in names], float(lr), float(mu), int(threads))
+            out, m_path + ".new", c_path + ".new", [out_off[n] for n in names], float(lr), float(mu), int(threads),
+            weights or [])
         os.replace(m_path + ".new", m_path)
         os.replace(c_path + ".new", c_path)
         return {"path": out, "native": True, "elements": int(stats["elements"]), "seconds": float(stats["seconds"]),
-                "threads": int(stats["threads"])}
-    return _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu)
+                "threads": int(stats["threads"]), "weights": weights}
+    return _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu, weights)
 
 
-def _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu) -> dict:
+def _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu, weights=None) -> dict:
     import time
 
     from safetensors import safe_open
@@ -146,10 +177,17 @@ def _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu) -> dict:
     inv = 1.0 / len(handles)
     elements = 0
     for k in handles[0].keys():
-        acc = handles[0].get_tensor(k).float()
-        for h in handles[1:]:
-            acc += h.get_tensor(k).float()
-        acc *= inv                                                       # true 1/N mean
+        if k == SAMPLES_KEY:
+            continue
+        if weights:
+            acc = handles[0].get_tensor(k).float() * weights[0]
+            for h, w in zip(handles[1:], weights[1:]):
+                acc += h.get_tensor(k).float() * w                       # mean over samples
+        else:
+            acc = handles[0].get_tensor(k).float()
+            for h in handles[1:]:
+                acc += h.get_tensor(k).float()
+            acc *= inv                                                   # true 1/N mean
         m = acc.clone() if prev_m is None or k not in prev_m.keys() else prev_m.get_tensor(k) * mu + acc
         u = (m * mu + acc) * lr
         new_m[k], upd[k] = m.contiguous(), u.contiguous()
@@ -161,4 +199,5 @@ def _fallback_round(paths, out, m_path, c_path, have_m, have_c, lr, mu) -> dict:
     save_file({k: v.contiguous() for k, v in cum.items()}, c_path + ".new")
     os.replace(m_path + ".new", m_path)
     os.replace(c_path + ".new", c_path)
-    return {"path": out, "native": False, "elements": elements, "seconds": time.perf_counter() - t0, "threads": 1}
+    return {"path": out, "native": False, "elements": elements, "seconds": time.perf_counter() - t0, "threads": 1,
+            "weights": weights}

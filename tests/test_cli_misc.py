@@ -283,3 +283,56 @@ def test_bench_contract_on_a_box_without_gpus():
         r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "1"],
                            capture_output=True, text=True, timeout=300, cwd=root)
         assert r.returncode != 0 and "CUDA" in (r.stderr + r.stdout)
+
+
+def test_replicated_nesterov_sample_weighted_mean_over_two_gloo_ranks():
+    """`aggregation.weighting = "samples"` in the collective engine: two ranks (threads, owned gloo groups) with
+    pseudo-gradients 1.0 and 4.0 after 10 and 30 samples -> mean over samples 3.25 (mean over ranks: 2.5); a rank
+    that processed nothing (a newcomer) gets weight zero."""
+    import socket
+    import threading
+
+    import torch
+
+    from hypha_b200.executor.training import ReplicatedNesterov, _Group
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+
+    class _Loop:
+        flat, device = False, "cpu"
+
+        def __init__(self, delta):
+            self.model = torch.nn.Linear(4, 1, bias=False)
+            with torch.no_grad():
+                self.model.weight.zero_()
+            self.prev = {k: v.detach().clone() for k, v in self.model.state_dict().items()}
+            with torch.no_grad():
+                self.model.weight.add_(delta)
+
+    out = {}
+
+    def rank(r, delta, samples_by_round):
+        group = _Group("gloo", f"tcp://127.0.0.1:{port}", r, 2)
+        loop, outer = _Loop(delta), ReplicatedNesterov(1.0, 0.0)           # lr 1, mu 0: theta moves by the mean
+        res = []
+        for rnd, n in enumerate(samples_by_round):
+            outer.step(loop, group, rnd, 0, n)
+            res.append(float(loop.model.weight.detach()[0, 0]))
+            with torch.no_grad():
+                loop.model.weight.add_(delta)                             # the next round's local progress
+        out[r] = res
+
+    ts = [threading.Thread(target=rank, args=(0, 1.0, [10, 0, None])), threading.Thread(target=rank, args=(1, 4.0, [30, 8, None]))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join(120)
+    assert not any(t.is_alive() for t in ts)
+    for r in (0, 1):
+        assert out[r][0] == pytest.approx(0.25 * 1.0 + 0.75 * 4.0)          # round 0: mean over samples
+        assert out[r][1] == pytest.approx(out[r][0] + 4.0)                  # round 1: rank 0 had no samples -> weight 0
+        assert out[r][2] == pytest.approx(out[r][1] + 2.5)                  # round 2: no counts -> mean over ranks
+    assert out[0] == out[1]

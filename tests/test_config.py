@@ -164,3 +164,24 @@ def test_nested_env_keys_with_double_underscore():
     assert cfg.status_bridge == "127.0.0.1:61000" and cfg.gateway_addresses == ["tcp://10.1.2.3:4001"]
     w = C.builder(C.WorkerConfig).with_env(env).build()
     assert w.device == 3
+
+
+def test_aggregation_weighting_is_validated_and_travels_to_the_executor(tmp_path):
+    from hypha_b200 import messages as M
+
+    p = tmp_path / "s.toml"
+    p.write_text('[scheduler.job.aggregation]\nweighting = "samples"\n')
+    cfg = C.builder(C.SchedulerConfig).with_toml(str(p)).build()
+    assert cfg.scheduler.job.aggregation.weighting == "samples"
+    C.validate(cfg)
+    p.write_text('[scheduler.job.aggregation]\nweighting = "by-luck"\n')
+    with pytest.raises(C.ConfigError, match="weighting"):
+        C.validate(C.builder(C.SchedulerConfig).with_toml(str(p)).build())
+    wire = {"model": M.Model("causal-lm", M.Fetch.uri("file:///m"), ["input_ids"]).to_wire(),
+            "data": M.Fetch.scheduler("s", "d").to_wire(), "updates": M.Send.to_peers(["ps"]).to_wire(),
+            "results": M.Receive.from_peers(["ps"]).to_wire(), "optimizer": M.Adam(1e-3).to_wire(), "batch_size": 4,
+            "weighting": "samples"}
+    t = M.TrainExecutorConfig.from_wire(wire)
+    assert t.weighting == "samples" and t.to_wire()["weighting"] == "samples"
+    del wire["weighting"]
+    assert "weighting" not in M.TrainExecutorConfig.from_wire(wire).to_wire()      # reference job JSON unchanged

@@ -330,6 +330,7 @@ def test_performance_aware_rounds_give_the_fast_worker_more_batches(tmp_path):
         "rounds": {"avg_samples_between_updates": 160, "update_rounds": 3, "max_batch_size": 4},
         "inner_optimizer": {"learning-rate": 3e-3},
         "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+        "aggregation": {"weighting": "samples"},        # unequal shares -> mean over samples, not over workers
         "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
@@ -351,6 +352,10 @@ def test_performance_aware_rounds_give_the_fast_worker_more_batches(tmp_path):
             per_round.setdefault(int(m.group(1)), []).append(int(m.group(2)))
     for r in (2, 3):                                        # together they cover the round's sample target
         assert 4 * sum(per_round[r]) >= 160 * 0.8, per_round
+    # the aggregate worker weighted the pseudo-gradients by the samples behind them
+    weights = [[float(x) for x in m.group(1).split(",")] for l in logs for m in [re.search(r"sample weights \[([^\]]+)\]", l)] if m]
+    assert len(weights) == 3 and all(abs(sum(w) - 1.0) < 0.01 for w in weights), weights
+    assert all(max(w) >= 0.7 for w in weights[1:]), weights      # rounds 2, 3: the fast worker dominates
 
 
 def test_collective_job_survives_a_lost_rank(tmp_path):

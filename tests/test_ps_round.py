@@ -155,3 +155,42 @@ def test_native_equals_fallback_property(tmp_path):
                     torch.testing.assert_close(x[k], y[k], rtol=2e-6, atol=1e-6)
 
     check()
+
+
+def test_sample_weighted_mean(tmp_path):
+    """`aggregation.weighting = "samples"`: worker files carry `__samples__`; the round takes the mean over
+    samples (native and fallback agree, the helper tensor does not appear in the outputs); a file without the
+    count switches the whole round back to the mean over workers."""
+    a, b = os.path.join(str(tmp_path), "n"), os.path.join(str(tmp_path), "t")
+    os.makedirs(a)
+    os.makedirs(b)
+    g = [torch.full((3, 5), 1.0), torch.full((3, 5), 4.0), torch.full((3, 5), 10.0)]
+    counts = [10.0, 30.0, 60.0]
+
+    def files(d, with_counts=(True, True, True)):
+        out = []
+        for i, (t, c, w) in enumerate(zip(g, counts, with_counts)):
+            tensors = {"w": t.clone(), "b": t[0].clone()}
+            if w:
+                tensors["__samples__"] = torch.tensor([c])
+            p = os.path.join(d, f"w{i}")
+            save_file(tensors, p)
+            out.append(p)
+        return out
+
+    ra = ps_round.outer_round(files(a), a, 1.0, 0.0)                      # lr 1, mu 0: update == weighted mean
+    rb = ps_round.outer_round(files(b), b, 1.0, 0.0, force_fallback=True)
+    assert ra["native"] and not rb["native"]
+    assert ra["weights"] == rb["weights"] == pytest.approx([0.1, 0.3, 0.6])
+    expect = 0.1 * 1.0 + 0.3 * 4.0 + 0.6 * 10.0
+    for d in (a, b):
+        upd = load_file(os.path.join(d, "gradient_update"))
+        assert set(upd) == {"w", "b"}                                     # the helper tensor is not part of the model
+        torch.testing.assert_close(upd["w"], torch.full((3, 5), expect))
+        assert set(load_file(os.path.join(d, "momentum"))) == {"w", "b"}
+    # one worker does not report its count -> plain mean over workers
+    c = os.path.join(str(tmp_path), "u")
+    os.makedirs(c)
+    rc = ps_round.outer_round(files(c, (True, False, True)), c, 1.0, 0.0)
+    assert rc["native"] and rc["weights"] is None
+    torch.testing.assert_close(load_file(rc["path"])["w"], torch.full((3, 5), 5.0))
