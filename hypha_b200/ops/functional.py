@@ -731,7 +731,8 @@ def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: i
     """Causal self-attention on a fused (already RoPE'd) qkv activation -> ``[tokens, Hq*D]``."""
     if not qkv.is_cuda:
         return _attention_ref(qkv, batch, seq, n_heads, n_kv, head_dim)
-    if _ATTN_BACKEND == "tcgen05" and head_dim == 128 and seq % 128 == 0:
+    if (_ATTN_BACKEND == "tcgen05" and head_dim == 128 and seq % 128 == 0 and qkv.dtype == torch.bfloat16
+            and n_heads % n_kv == 0 and qkv.stride(-1) == 1 and qkv.stride(0) % 8 == 0):
         return _TcgenAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "flash2":
         return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
