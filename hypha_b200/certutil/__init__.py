@@ -96,6 +96,25 @@ def make_node(ca_cert: str, ca_key: str, name: str, sans: Tuple[str, ...] = (), 
     return cp, kp, tp
 
 
+def make_crl(ca_cert: str, ca_key: str, revoked: Tuple[str, ...] = (), out_dir: str = ".", name: Optional[str] = None,
+             days: int = 30) -> str:
+    """Certificate revocation list signed by the organisation CA for the node certificates in ``revoked`` (paths
+    of ``<name>-cert.pem`` files) -- what the roles' ``crls_pem`` key points at (the reference loads CRLs,
+    crates/network/src/cert.rs, but ships no tool to make one)."""
+    cc, ck = _load(ca_cert, ca_key)
+    now = dt.datetime.now(dt.timezone.utc)
+    b = (x509.CertificateRevocationListBuilder().issuer_name(cc.subject)
+         .last_update(now - dt.timedelta(minutes=5)).next_update(now + dt.timedelta(days=days)))
+    for path in revoked:
+        leaf = x509.load_pem_x509_certificates(open(path, "rb").read())[0]
+        b = b.add_revoked_certificate(x509.RevokedCertificateBuilder().serial_number(leaf.serial_number)
+                                      .revocation_date(now - dt.timedelta(minutes=5)).build())
+    crl = b.sign(ck, None)
+    out = os.path.join(out_dir, f"{name or 'revoked'}-crl.pem")
+    _write(out, crl.public_bytes(serialization.Encoding.PEM), 0o644)
+    return out
+
+
 def verify_chain(node_cert_path: str) -> bool:
     """Signature check of every link of the chain stored in ``<name>-cert.pem``."""
     certs = x509.load_pem_x509_certificates(open(node_cert_path, "rb").read())

@@ -1,4 +1,4 @@
-"""``hypha-certutil {root,org,node}`` (crates/certutil/src/cli.rs:59-279)."""
+"""``hypha-certutil {root,org,node}`` (crates/certutil/src/cli.rs:59-279) plus ``crl`` (revocation lists)."""
 import argparse
 import sys
 
@@ -26,6 +26,12 @@ def build_parser() -> argparse.ArgumentParser:
     n.add_argument("-n", "--name", required=True)
     n.add_argument("-s", "--san", action="append", default=[])
     n.add_argument("-d", "--dir", default=".")
+    c = sub.add_parser("crl", help="revocation list signed by an organisation CA (for the roles' crls_pem)")
+    c.add_argument("--ca-cert", required=True)
+    c.add_argument("--ca-key", required=True)
+    c.add_argument("-r", "--revoke", action="append", default=[], help="node certificate to revoke (repeatable)")
+    c.add_argument("-n", "--name", default=None)
+    c.add_argument("-d", "--dir", default=".")
     return p
 
 
@@ -36,6 +42,8 @@ def main(argv=None) -> int:
             print(*cu.make_root(a.organization, a.name, a.country, a.dir))
         elif a.command == "org":
             print(*cu.make_org(a.root_cert, a.root_key, a.organization, a.name, a.country, a.dir))
+        elif a.command == "crl":
+            print(cu.make_crl(a.ca_cert, a.ca_key, tuple(a.revoke), a.dir, a.name))
         else:
             print(*cu.make_node(a.ca_cert, a.ca_key, a.name, tuple(a.san), a.dir))
     except (OSError, ValueError) as exc:          # unreadable / malformed CA files, unwritable directory

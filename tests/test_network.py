@@ -522,3 +522,33 @@ def test_stream_that_loses_its_sender_is_not_mistaken_for_a_complete_file():
                 await asyncio.wait_for(pulled.read_all(), 5)
             await a.close(); await b.close(); await c.close()
     run(main())
+
+
+def test_revoked_node_certificate_is_refused(tmp_path):
+    """`crls_pem`: a node whose certificate is on the organisation CA's revocation list cannot connect, its
+    sibling from the same CA still can."""
+    from hypha_b200 import certutil
+    from hypha_b200.transport.network import DialError, Network
+
+    d = str(tmp_path)
+    rc, rk = certutil.make_root("Acme", out_dir=d)
+    oc, ok = certutil.make_org(rc, rk, "Acme", name="acme-org", out_dir=d)
+    tls = {}
+    for n in ("alpha", "beta", "gamma"):
+        c, k, t = certutil.make_node(oc, ok, n, sans=("127.0.0.1",), out_dir=d)
+        tls[n] = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+    crl = certutil.make_crl(oc, ok, (tls["beta"]["cert_pem"],), out_dir=d)
+    tls["alpha"]["crls_pem"] = crl
+
+    async def main():
+        a = Network("alpha", tls=tls["alpha"])
+        b = Network("beta", tls=tls["beta"])
+        g = Network("gamma", tls=tls["gamma"])
+        addr = await a.listen("tcp://127.0.0.1:0")
+        assert await g.dial(addr) == "alpha"                      # same CA, not revoked
+        with pytest.raises(DialError):
+            await b.dial(addr, timeout=2.0)
+        assert "beta" not in a.links and "gamma" in a.links
+        for n in (a, b, g):
+            await n.close()
+    asyncio.run(main())
