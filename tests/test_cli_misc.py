@@ -336,3 +336,47 @@ def test_replicated_nesterov_sample_weighted_mean_over_two_gloo_ranks():
         assert out[r][1] == pytest.approx(out[r][0] + 4.0)                  # round 1: rank 0 had no samples -> weight 0
         assert out[r][2] == pytest.approx(out[r][1] + 2.5)                  # round 2: no counts -> mean over ranks
     assert out[0] == out[1]
+
+
+def test_process_executor_escalates_from_sigterm_to_sigkill(tmp_path, monkeypatch):
+    """Cancellation of a process executor (process.rs:148-187): SIGTERM to the process group, a grace period,
+    then SIGKILL; a job that honours SIGTERM ends within the grace period; the work dir is removed either way."""
+    import signal
+    import sys
+    import time
+
+    from hypha_b200 import messages as M
+    from hypha_b200.transport import Network
+    from hypha_b200.worker import Connector
+    from hypha_b200.worker import jobs as J
+
+    monkeypatch.setattr(J, "KILL_GRACE_S", 0.6)
+    stubborn = ("import signal, time, sys\n"
+                "signal.signal(signal.SIGTERM, lambda *a: print('ignoring SIGTERM', flush=True))\n"
+                "print('ready', flush=True)\n"
+                "time.sleep(60)\n")
+    polite = "import time\nprint('ready', flush=True)\ntime.sleep(60)\n"
+    spec = M.JobSpec("job-x", M.Executor.aggregate(M.AGGREGATE_EXECUTOR_NAME, M.AggregateExecutorConfig(
+        updates=M.Receive.from_peers(["w"]), results=M.Send.to_peers(["w"]), optimizer=M.Nesterov(0.7, 0.9))))
+
+    async def run(code):
+        net = Network("w")
+        logs = []
+        ex = await J.ProcessExecutor(Connector(net), net, str(tmp_path), sys.executable, ["-c", code],
+                                     log=logs.append).execute(spec, "t", "sched")
+        for _ in range(200):
+            if any("ready" in l for l in logs):
+                break
+            await asyncio.sleep(0.02)
+        t0 = time.perf_counter()
+        ex.cancel()
+        status = await asyncio.wait_for(ex.wait(), 10)
+        dt = time.perf_counter() - t0
+        await net.close()
+        return status, dt, logs, ex.work_dir
+
+    status, dt, logs, wd = asyncio.run(run(stubborn))
+    assert status == M.JobStatus.FAILED and 0.55 <= dt < 5 and any("ignoring SIGTERM" in l for l in logs)
+    assert not os.path.exists(wd)
+    status, dt, logs, wd = asyncio.run(run(polite))
+    assert dt < 0.5 and not os.path.exists(wd)                 # SIGTERM was enough: no grace period spent
