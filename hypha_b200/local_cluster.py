@@ -41,6 +41,11 @@ async def run_loopback_job(tmp: str, *, repo: str, write_model_config: Callable[
     write_model_config(os.path.join(registry, repo, "config.json"))
     os.environ["HYPHA_HF_LOCAL"] = registry
     os.environ["OMP_NUM_THREADS"] = str(omp_threads)
+    # several executors share this machine's cores: OpenMP workers that spin while they wait burn the cores the
+    # other executors need (measured: 15x the CPU time for the same job on a 3-core box)
+    os.environ.setdefault("OMP_WAIT_POLICY", "PASSIVE")
+    os.environ.setdefault("GOMP_SPINCOUNT", "0")
+    os.environ.setdefault("KMP_BLOCKTIME", "0")
     ds_dir = os.path.join(tmp, job["dataset"]["dataset"])
     write_dataset(ds_dir)
     gw_addr = f"memory://gw-{os.getpid()}-{abs(hash(tmp)) % 10 ** 8}"

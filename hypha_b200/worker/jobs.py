@@ -90,6 +90,11 @@ class ProcessExecutor:
         argv = substitute_placeholders(self.args, sock, work_dir, job_json)
         cmd = sys.executable if self.cmd in ("python", "python3") else self.cmd
         env = dict(os.environ)
+        # executors of several workers usually share a machine: OpenMP threads that spin while waiting starve
+        # the neighbours (15x the CPU time for the same CPU job when oversubscribed); override per executor
+        # with `[[executors]].env`
+        for k, v in (("OMP_WAIT_POLICY", "PASSIVE"), ("GOMP_SPINCOUNT", "0"), ("KMP_BLOCKTIME", "0")):
+            env.setdefault(k, v)
         env.update(self.env)
         env.update({"SOCKET_PATH": sock, "WORK_DIR": work_dir, "JOB_JSON": job_json})
         try:
