@@ -5,8 +5,10 @@ Contract (driver): ``python bench.py --gpus N --steps K --warmup W`` (under torc
 one rank per GPU) prints ONE JSON line from rank 0.  ``value`` = whole-job tokens/s, timed on the
 device with CUDA events (max over ranks); ``e2e`` = the same metric through the public
 ``DiLoCoTrainer.step`` API with per-step pinned-host->device input copies and a device->host loss
-read.  ``--impl reference`` reports why the unmodified reference cannot run offline;
-``--impl baseline`` runs the stock-components re-creation (cuBLAS GEMMs, NCCL outer all-reduce).
+read.  ``--impl reference`` (alias ``--impl stock``) runs the reference arm: the reference's own optimizer /
+schedule / dataset code from ``baseline/_ref`` around stock transformers + torch + NCCL components
+(``bench/reference_arm.py`` explains why the unmodified entry point cannot run offline);
+``--impl baseline`` is the library A/B of the product (cuBLAS GEMMs, cuDNN attention, NCCL outer step).
 """
 from __future__ import annotations
 
@@ -30,7 +32,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "baseline"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "stock", "baseline"])
     ap.add_argument("--model", default=os.environ.get("HYPHA_BENCH_MODEL", "llama3-8b"))
     ap.add_argument("--seq-len", type=int, default=int(os.environ.get("HYPHA_BENCH_SEQ", "4096")))
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("HYPHA_BENCH_MB", "2")))
@@ -210,10 +212,6 @@ def fault_drill(trainer, dist, rank, world, batches, timeout_ms: int = 1500) -> 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        print(json.dumps({"impl": "reference", "unavailable": REFERENCE_UNAVAILABLE}))
-        return 0
-
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.gpus > 1 and world_env == 1 and "RANK" not in os.environ:
         # convenience: relaunch ourselves under torchrun
@@ -221,6 +219,17 @@ def main():
                f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
                os.environ.get("MASTER_PORT", "29511"), os.path.abspath(__file__)] + sys.argv[1:]
         return subprocess.call(cmd)
+
+    if args.impl in ("reference", "stock"):
+        # The unmodified reference cannot run offline (bench/reference_arm.py says why); this arm runs the
+        # reference's own optimizer/schedule/dataset code from baseline/_ref around stock torch/transformers
+        # components -- nothing of hypha_b200 is imported on this path.
+        import importlib.util
+
+        spec = importlib.util.spec_from_file_location("hypha_reference_arm", os.path.join(REPO, "bench", "reference_arm.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod.run(args, ClockSampler)
 
     import torch
     import torch.distributed as dist
