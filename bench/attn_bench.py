@@ -47,11 +47,18 @@ def main():
             row["rel_err_vs_cudnn"] = ((a.float() - b.float()).norm() / b.float().norm()).item()
             # ---- backward (2.5x the forward FLOPs): hand-written tcgen05 vs library fwd+bwd minus fwd
             dout = torch.randn_like(a)
+            for variant in ("fused", "split"):
+                try:
+                    ms = timeit(lambda: ops.attention_bwd_tcgen05(qkv, a, dout, lse, B, S, Hq, Hk, D, variant=variant))
+                    row["bwd_tcgen05_" + variant] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
+                except Exception as exc:
+                    row["bwd_tcgen05_" + variant] = {"error": repr(exc)[:200]}
             try:
-                ms = timeit(lambda: ops.attention_bwd_tcgen05(qkv, a, dout, lse, B, S, Hq, Hk, D))
-                row["bwd_tcgen05"] = {"ms": ms, "tflops": 2.5 * flops / ms / 1e9}
+                d1 = ops.attention_bwd_tcgen05(qkv, a, dout, lse, B, S, Hq, Hk, D, variant="fused").float()
+                d2 = ops.attention_bwd_tcgen05(qkv, a, dout, lse, B, S, Hq, Hk, D, variant="split").float()
+                row["bwd_fused_vs_split_rel"] = ((d1 - d2).norm() / d2.norm()).item()
             except Exception as exc:
-                row["bwd_tcgen05"] = {"error": repr(exc)[:200]}
+                row["bwd_fused_vs_split_rel"] = repr(exc)[:200]
         for name in ("cudnn", "flash2", "tcgen05"):
             # library backward = (forward + backward through the autograd Function) - forward
             try:

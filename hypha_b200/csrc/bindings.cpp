@@ -187,6 +187,18 @@ PYBIND11_MODULE(_C, m) {
                                        out_stride, dout_stride, dqkv_stride, scale, S(s));
     if (rc != 0) throw std::runtime_error(std::string("attention_bwd_tcgen05: ") + hb::attention_bwd_last_error());
   });
+  m.def("attention_bwd_fused_ws_floats", [](int batch, int seq, int n_heads) {
+    return (unsigned long long)hb::attention_bwd_fused_ws_floats(batch, seq, n_heads);
+  });
+  m.def("attention_bwd_fused", [](u64 qkv, u64 out, u64 dout, u64 lse, u64 dqkv, u64 ws, int batch, int seq, int n_heads,
+                                  int n_kv, int head_dim, int qkv_stride, int out_stride, int dout_stride,
+                                  int dqkv_stride, float scale, u64 s) {
+    int rc = hb::attention_bwd_fused_tcgen05(P<const bf16>(qkv), P<const bf16>(out), P<const bf16>(dout),
+                                             P<const float>(lse), P<bf16>(dqkv), P<float>(ws), batch, seq, n_heads, n_kv,
+                                             head_dim, qkv_stride, out_stride, dout_stride, dqkv_stride, scale, S(s));
+    if (rc != 0)
+      throw std::runtime_error(std::string("attention_bwd_fused_tcgen05: ") + hb::attention_bwd_fused_last_error());
+  });
   m.def("gemm_fp8", [](u64 A, u64 B, u64 D, int M, int N, int K, int lda, int ldb, int ldd, int a_kmajor,
                        int b_kmajor, int a_fmt, int b_fmt, u64 dq_a, u64 dq_b, int accumulate, u64 s) {
     int rc = hb::gemm_fp8_tcgen05(P<const uint8_t>(A), P<const uint8_t>(B), P<bf16>(D), M, N, K, lda, ldb, ldd,

@@ -118,6 +118,13 @@ int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, co
                           int batch, int seq, int n_heads, int n_kv, int head_dim, int qkv_stride, int out_stride,
                           int dout_stride, int dqkv_stride, float scale, cudaStream_t s);
 const char* attention_bwd_last_error();
+// ---- fused single-kernel backward, 5 GEMMs per tile pair, dQ through TMA reduce-add (attention_bwd_fused.cu) ----
+// ws: attention_bwd_fused_ws_floats() floats (D, lse2, fp32 dQ accumulator).  dqkv is fully overwritten.
+size_t attention_bwd_fused_ws_floats(int batch, int seq, int n_heads);
+int attention_bwd_fused_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, float* ws,
+                                int batch, int seq, int n_heads, int n_kv, int head_dim, int qkv_stride, int out_stride,
+                                int dout_stride, int dqkv_stride, float scale, cudaStream_t s);
+const char* attention_bwd_fused_last_error();
 
 unsigned long long launch_count();
 void reset_launch_count();

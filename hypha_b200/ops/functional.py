@@ -621,10 +621,11 @@ class _TcgenAttnQKV(torch.autograd.Function):
         qkv, out, lse = ctx.saved_tensors
         batch, seq, n_heads, n_kv, head_dim, scale = ctx.dims
         dqkv = torch.empty_like(qkv)
-        if os.environ.get("HYPHA_ATTN_BWD", "tcgen05") == "tcgen05":
+        if os.environ.get("HYPHA_ATTN_BWD", "fused") in ("fused", "split", "tcgen05"):
             dout = dout if dout.stride(-1) == 1 and dout.stride(0) % 8 == 0 else dout.contiguous()
-            return attention_bwd_tcgen05(qkv, out, dout, lse, batch, seq, n_heads, n_kv, head_dim, dqkv), \
-                None, None, None, None, None
+            variant = os.environ.get("HYPHA_ATTN_BWD", "fused")
+            return attention_bwd_tcgen05(qkv, out, dout, lse, batch, seq, n_heads, n_kv, head_dim, dqkv,
+                                         "split" if variant == "tcgen05" else variant), None, None, None, None, None
         from flash_attn.flash_attn_interface import _flash_attn_backward
 
         sl = lambda t, a, b, hh: t[:, a * head_dim: b * head_dim].view(batch, seq, hh, head_dim)
@@ -637,15 +638,40 @@ class _TcgenAttnQKV(torch.autograd.Function):
         return dqkv, None, None, None, None, None
 
 
+_ATTN_BWD_WS: dict = {}
+
+
 def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int,
-                          dqkv: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """Raw backward: returns ``dqkv [tokens, (Hq+2Hkv)*D]`` given the forward's (qkv, out, lse) and dout."""
+                          dqkv: Optional[torch.Tensor] = None, variant: Optional[str] = None) -> torch.Tensor:
+    """Raw backward: returns ``dqkv [tokens, (Hq+2Hkv)*D]`` given the forward's (qkv, out, lse) and dout.
+
+    ``variant`` (default ``HYPHA_ATTN_BWD`` or ``fused``): ``fused`` = one kernel, 5 GEMMs per tile pair, dQ
+    partials summed in fp32 by TMA reduce-add (csrc/kernels/attention_bwd_fused.cu); ``split`` = the
+    atomics-free dK/dV + dQ kernel pair that recomputes S and dP (7 GEMMs, bit-reproducible;
+    csrc/kernels/attention_bwd_tcgen05.cu)."""
+    variant = variant or os.environ.get("HYPHA_ATTN_BWD", "fused")
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
-    ws = torch.empty(2 * batch * n_heads * seq, dtype=torch.float32, device=qkv.device)
-    load_C().attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
-                           ws.data_ptr(), batch, seq, n_heads, n_kv, head_dim, qkv.stride(0), out.stride(0),
-                           dout.stride(0), dqkv.stride(0), 1.0 / math.sqrt(head_dim), cuda_stream())
+    C = load_C()
+    args = (batch, seq, n_heads, n_kv, head_dim, qkv.stride(0), out.stride(0), dout.stride(0), dqkv.stride(0),
+            1.0 / math.sqrt(head_dim), cuda_stream())
+    if variant == "fused":
+        # the workspace (D, lse2 and the fp32 dQ accumulator: 4 bytes per q element) is cached per shape and
+        # stream-ordered, so a 32-layer backward reuses one allocation instead of 32 x 134 MB
+        n = int(C.attention_bwd_fused_ws_floats(batch, seq, n_heads))
+        key = (qkv.device.index, n)
+        ws = _ATTN_BWD_WS.get(key)
+        if ws is None:
+            _ATTN_BWD_WS.clear()
+            ws = _ATTN_BWD_WS[key] = torch.empty(n, dtype=torch.float32, device=qkv.device)
+        C.attention_bwd_fused(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                              ws.data_ptr(), *args)
+    elif variant == "split":
+        ws = torch.empty(2 * batch * n_heads * seq, dtype=torch.float32, device=qkv.device)
+        C.attention_bwd(qkv.data_ptr(), out.data_ptr(), dout.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                        ws.data_ptr(), *args)
+    else:
+        raise ValueError(f"unknown attention backward variant {variant!r}")
     return dqkv
 
 

@@ -443,8 +443,9 @@ def test_attention_fwd_tcgen05(C, B, S, Hq, Hk):
     assert torch.allclose(lse, torch.logsumexp(sc, -1), atol=2e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("variant", ["fused", "split"])
 @pytest.mark.parametrize("B,S,Hq,Hk", [(1, 128, 2, 1), (2, 512, 8, 2), (1, 1024, 4, 4), (1, 384, 4, 1)])
-def test_attention_bwd_tcgen05(C, B, S, Hq, Hk):
+def test_attention_bwd_tcgen05(C, B, S, Hq, Hk, variant):
     """Hand-written tcgen05 flash-attention backward (dQ, dK, dV written into the fused d(qkv)) vs
     autograd through the fp32 reference."""
     from hypha_b200 import ops
@@ -455,7 +456,7 @@ def test_attention_bwd_tcgen05(C, B, S, Hq, Hk):
     qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16)
     out, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
     dout = torch.randn_like(out)
-    dqkv = ops.attention_bwd_tcgen05(qkv, out, dout, lse, B, S, Hq, Hk, D)
+    dqkv = ops.attention_bwd_tcgen05(qkv, out, dout, lse, B, S, Hq, Hk, D, variant=variant)
     qf = qkv.float().requires_grad_(True)
     _attention_ref(qf, B, S, Hq, Hk, D).backward(dout.float())
     ref = qf.grad
