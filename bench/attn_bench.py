@@ -35,6 +35,7 @@ def main():
         row = {"B": B, "S": S}
         with torch.no_grad():
             for name, fn in (("tcgen05", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)),
+                             ("tcgen05_v1", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D, version=1)),
                              ("cudnn", lambda: _attention_sdpa(qkv, B, S, Hq, Hk, D)),
                              ("flash2", lambda: _FlashAttnQKV.apply(qkv, B, S, Hq, Hk, D))):
                 try:
@@ -42,6 +43,14 @@ def main():
                     row[name] = {"ms": ms, "tflops": flops / ms / 1e9}
                 except Exception as exc:
                     row[name] = {"error": repr(exc)[:200]}
+            for poly in (0, 1, 2):
+                ops.set_attention_fwd_poly(poly)
+                ms = timeit(lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D))
+                a, _ = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
+                bb = _attention_sdpa(qkv, B, S, Hq, Hk, D)
+                row[f"tcgen05_poly{poly}"] = {"ms": ms, "tflops": flops / ms / 1e9,
+                                              "rel_err_vs_cudnn": ((a.float() - bb.float()).norm() / bb.float().norm()).item()}
+            ops.set_attention_fwd_poly(1)
             a, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
             b = _attention_sdpa(qkv, B, S, Hq, Hk, D)
             row["rel_err_vs_cudnn"] = ((a.float() - b.float()).norm() / b.float().norm()).item()

@@ -20,7 +20,8 @@ from hypha_b200.trainer import DiLoCoTrainer  # noqa: E402
 
 def family(name: str) -> str:
     n = name.lower()
-    for key, fam in (("gemm_bf16_tcgen05", "gemm.tcgen05"), ("nvjet", "gemm.cublas"), ("cutlass", "gemm.cublas"),
+    for key, fam in (("attn_fwd", "attention.fwd"), ("attn_bwd", "attention.bwd"), ("gemm_tcgen05_2cta", "gemm.tcgen05"),
+                     ("gemm_bf16_tcgen05", "gemm.tcgen05"), ("nvjet", "gemm.cublas"), ("cutlass", "gemm.cublas"),
                      ("gemm", "gemm.cublas"), ("flash_fwd", "attention.fwd"), ("flash_bwd", "attention.bwd"),
                      ("flash", "attention.other"), ("rmsnorm_fwd", "rmsnorm.fwd"), ("rmsnorm_bwd", "rmsnorm.bwd"),
                      ("colsum", "rmsnorm.bwd"), ("rope", "rope"), ("swiglu_fwd", "swiglu.fwd"),
@@ -37,7 +38,7 @@ def main():
     ap.add_argument("--model", default="llama3-8b")
     ap.add_argument("--seq-len", type=int, default=4096)
     ap.add_argument("--micro-batch", type=int, default=2)
-    ap.add_argument("--recompute-layers", type=int, default=8)
+    ap.add_argument("--recompute-layers", type=int, default=0)
     ap.add_argument("--tag", default=None)
     a = ap.parse_args()
     ops.set_gemm_backend(a.backend)
@@ -53,6 +54,7 @@ def main():
         tr.step(ids)
         torch.cuda.synchronize()
     fam = defaultdict(lambda: [0.0, 0])
+    kernels = []
     total = 0.0
     for ev in prof.key_averages():
         t = getattr(ev, "device_time_total", None)
@@ -61,12 +63,14 @@ def main():
         if t <= 0:
             continue
         f = family(ev.key)
+        kernels.append({"kernel": ev.key[:100], "ms": t / 1e3, "launches": ev.count})
         fam[f][0] += t / 1e3
         fam[f][1] += ev.count
         total += t / 1e3
     rows = sorted(((k, v[0], v[1]) for k, v in fam.items()), key=lambda r: -r[1])
     out = {"backend": a.backend, "config": vars(a), "total_kernel_ms": total,
-           "families": [{"family": k, "ms": ms, "share": ms / total, "launches": n} for k, ms, n in rows]}
+           "families": [{"family": k, "ms": ms, "share": ms / total, "launches": n} for k, ms, n in rows],
+           "kernels": sorted(kernels, key=lambda r: -r["ms"])[:40]}
     tag = a.tag or a.backend
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(out, open(f"gpurun_out/profile_{tag}.json", "w"), indent=1)

@@ -187,6 +187,9 @@ PYBIND11_MODULE(_C, m) {
                                        out_stride, dout_stride, dqkv_stride, scale, S(s));
     if (rc != 0) throw std::runtime_error(std::string("attention_bwd_tcgen05: ") + hb::attention_bwd_last_error());
   });
+  m.def("attention_fwd_set_version", &hb::attention_fwd_set_version);
+  m.def("attention_fwd_get_version", &hb::attention_fwd_get_version);
+  m.def("attention_fwd_set_poly", &hb::attention_fwd_set_poly);
   m.def("attention_bwd_fused_ws_floats", [](int batch, int seq, int n_heads) {
     return (unsigned long long)hb::attention_bwd_fused_ws_floats(batch, seq, n_heads);
   });

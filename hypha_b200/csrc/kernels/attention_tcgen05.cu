@@ -282,11 +282,360 @@ attn_fwd_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {
   }
 }
 
+
+// =====================================================================================================
+// Forward v2: TWO 128-row Q tiles per CTA ping-pong on one MMA issuer (one CTA per SM), 128-key tiles.
+//
+//   TMEM (512 columns): S0 0..127 | S1 128..255 | O0 256..383 | O1 384..511; P_w (bf16 pairs) overwrites the
+//   first 64 columns of S_w and is the TMEM A operand of O_w += P_w V (TS form).
+//   warps 0-3 / 4-7  softmax warpgroup of Q tile 0 / 1: thread = q row, all 128 key columns of the tile in
+//                    registers; row max with 3-input max, scale-and-subtract with packed fp32x2 FMAs, ex2,
+//                    lazy rescale of O_w in TMEM (only when the max grew by > 2^8), final normalise + store.
+//   warp 8           tcgen05.mma issuer.  Per key tile j the tensor pipe runs
+//                        O0 += P0_j V_j | S0_{j+1} = Q0 K_{j+1}^T | O1 += P1_j V_j | S1_{j+1} = Q1 K_{j+1}^T
+//                    so one tile's exponentials hide under the other tile's MMAs, and K_j / V_j are fetched
+//                    once for 256 q rows.  S_{j+1} of a tile is issued right behind its O += P_j V, so a
+//                    completed S_{j+1} also means the O accumulator is quiescent: no extra barrier for the rescale.
+//   warp 9           TMA producer: Q (256 rows) once, K and V in separate 2-stage rings.
+// =====================================================================================================
+constexpr int kBN2 = 128;
+constexpr int kQ2Bytes = 2 * kBM * kD * 2;         // 64 KB: two atoms of [256 rows x 128 B]
+constexpr int kKV2Bytes = kBN2 * kD * 2;           // 32 KB
+constexpr int kAtom2 = kBN2 * 128;                 // 16 KB: one 64-column atom of a 128-row tile
+constexpr int kFwd2Threads = 384;
+
+struct Attn2Smem {
+  static constexpr int q_off = 0;
+  static constexpr int k_off = q_off + kQ2Bytes;
+  static constexpr int v_off = k_off + 2 * kKV2Bytes;
+  static constexpr int bar_off = v_off + 2 * kKV2Bytes;
+  static constexpr int total = bar_off + 24 * 8;
+};
+constexpr int kAttn2SmemBytes = Attn2Smem::total + 1024;
+
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+// (a.x*b + c, a.y*b + c) with one packed FFMA2
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long ua, ub, uc, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(ud) : "l"(ua), "l"(ub), "l"(uc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long ua, ub, ud;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(ud) : "l"(ua), "l"(ub));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(ud));
+  return d;
+}
+// 2^x for a pair on the FMA pipe (no MUFU): round-to-nearest split x = n + r, |r| <= 0.5, degree-3 minimax
+// polynomial for 2^r (max relative error 7.5e-5, far below the bf16 rounding of P), exponent patched in with
+// an integer add.  The softmax is MUFU-bound (16 ex2/clk/SM against 8192 MMA FLOP/clk/SM), so a fraction of
+// every tile's exponentials is moved here.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  x.x = fmaxf(x.x, -126.f);
+  x.y = fmaxf(x.y, -126.f);
+  const float2 j = add2(x, make_float2(12582912.f, 12582912.f));            // 1.5 * 2^23: integer part in the low bits
+  const float2 t = add2(j, make_float2(-12582912.f, -12582912.f));
+  const float2 r = fma2(t, make_float2(-1.f, -1.f), x);
+  float2 q = fma2(r, make_float2(0.05517074465751648f, 0.05517074465751648f),
+                  make_float2(0.24260912835597992f, 0.24260912835597992f));
+  q = fma2(q, r, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  q = fma2(q, r, make_float2(0.9999281764030457f, 0.9999281764030457f));
+  q.x = __uint_as_float(__float_as_uint(q.x) + (__float_as_uint(j.x) << 23));
+  q.y = __uint_as_float(__float_as_uint(q.y) + (__float_as_uint(j.y) << 23));
+  return q;
+}
+
+template <int kPolyOf4>      // of every 4 element pairs, this many take the polynomial instead of MUFU.EX2
+__global__ void __launch_bounds__(kFwd2Threads, 1)
+attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {64, 256}
+                         const __grid_constant__ CUtensorMap tma_kv,     // box {64, 128}
+                         const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base + Attn2Smem::q_off;
+  const uint32_t k_smem = smem_base + Attn2Smem::k_off;
+  const uint32_t v_smem = smem_base + Attn2Smem::v_off;
+  const uint32_t bars = smem_base + Attn2Smem::bar_off;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bars + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
+  auto s_full = [&](int w) { return bars + 8u * (9 + w); };
+  auto p_full = [&](int w) { return bars + 8u * (11 + w); };
+  auto o_full = [&](int w) { return bars + 8u * (13 + w); };
+  const uint32_t tmem_ptr_smem = bars + 8u * 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Attn2Smem::bar_off + 8 * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_tile = p.batch * p.n_heads;
+  const int pairs = p.seq / (2 * kBM);
+  const int t = pairs - 1 - (int)(blockIdx.x / per_tile);          // heavy (late) tile pairs first
+  const int bh = (int)(blockIdx.x % per_tile);
+  const int b = bh / p.n_heads, h = bh % p.n_heads;
+  const int hk = h / (p.n_heads / p.n_kv);
+  const int n0 = 2 * t + 1, n1 = 2 * t + 2;                         // key tiles seen by Q tile 0 / 1
+  const int row0 = b * p.seq + t * 2 * kBM;
+  const int q_col = h * kD, k_col = (p.n_heads + hk) * kD, v_col = (p.n_heads + p.n_kv + hk) * kD;
+
+  if (warp == 9 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 4); mbar_init(o_full(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 8) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp >= 8) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+    if (warp == 9 && lane == 0) {
+      // ====================== TMA producer ======================
+      mbar_arrive_expect_tx(q_full, kQ2Bytes);
+      tma_load_2d(q_smem, &tma_q, q_full, q_col, row0);
+      tma_load_2d(q_smem + 2 * kAtom2, &tma_q, q_full, q_col + 64, row0);
+      for (int j = 0; j < n1; ++j) {
+        const int st = j & 1;
+        const uint32_t par = (((uint32_t)(j >> 1)) & 1u) ^ 1u;
+        const int krow = b * p.seq + j * kBN2;
+        mbar_wait(k_empty(st), par);
+        mbar_arrive_expect_tx(k_full(st), kKV2Bytes);
+        tma_load_2d(k_smem + st * kKV2Bytes, &tma_kv, k_full(st), k_col, krow);
+        tma_load_2d(k_smem + st * kKV2Bytes + kAtom2, &tma_kv, k_full(st), k_col + 64, krow);
+        mbar_wait(v_empty(st), par);
+        mbar_arrive_expect_tx(v_full(st), kKV2Bytes);
+        tma_load_2d(v_smem + st * kKV2Bytes, &tma_kv, v_full(st), v_col, krow);
+        tma_load_2d(v_smem + st * kKV2Bytes + kAtom2, &tma_kv, v_full(st), v_col + 64, krow);
+      }
+    } else if (warp == 8 && lane == 0) {
+      // ====================== MMA issuer ========================
+      const uint32_t idesc_s = umma_idesc_bf16(kBM, kBN2, 0, 0);   // S = Q K^T
+      const uint32_t idesc_o = umma_idesc_bf16(kBM, kD, 0, 1);     // O += P V : V MN-major
+      auto issue_s = [&](int w, int j) {                           // S_w = Q_w K_j^T into TMEM columns 128w..
+        const uint32_t kb = k_smem + (j & 1) * kKV2Bytes;
+        const uint32_t qb = q_smem + w * kAtom2;                   // rows 128w.. of each 256-row atom
+#pragma unroll
+        for (int kk = 0; kk < kD / 16; ++kk) {
+          const uint64_t ad = umma_smem_desc(qb + (kk >> 2) * (2 * kAtom2) + (kk & 3) * 32, 16, 1024);
+          const uint64_t bd = umma_smem_desc(kb + (kk >> 2) * kAtom2 + (kk & 3) * 32, 16, 1024);
+          umma_bf16_ss(tmem_base + 128u * w, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full(w));
+      };
+      auto issue_pv = [&](int w, int j) {
+        const uint32_t vb = v_smem + (j & 1) * kKV2Bytes;
+#pragma unroll
+        for (int kk = 0; kk < kBN2 / 16; ++kk) {
+          const uint64_t bd = umma_smem_desc(vb + kk * (16 * 128), kAtom2, 1024);
+          umma_bf16_ts(tmem_base + 256u + 128u * w, tmem_base + 128u * w + kk * 8, bd, idesc_o,
+                       (j != 0 || kk != 0) ? 1u : 0u);
+        }
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(k_empty(0));
+      for (int j = 0; j < n1; ++j) {
+        const int st = j & 1, nst = (j + 1) & 1;
+        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
+        if (j < n0) {
+          mbar_wait(p_full(0), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_pv(0, j);
+          if (j == n0 - 1) umma_commit(o_full(0));
+        }
+        if (j + 1 < n0) {
+          mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
+          tc_fence_after();
+          issue_s(0, j + 1);
+        }
+        mbar_wait(p_full(1), (uint32_t)j & 1u);
+        tc_fence_after();
+        issue_pv(1, j);
+        umma_commit(v_empty(st));
+        if (j == n1 - 1) umma_commit(o_full(1));
+        if (j + 1 < n1) {
+          mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
+          tc_fence_after();
+          issue_s(1, j + 1);
+          umma_commit(k_empty(nst));
+        }
+      }
+    }
+  } else {
+    // ====================== softmax warpgroups (w = 0, 1) ==========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int w = warp >> 2;
+    const int q4 = warp & 3;
+    const int r_local = q4 * 32 + lane;
+    const int q_pos = t * 2 * kBM + w * kBM + r_local;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tmem_s = tmem_base + 128u * w, tmem_o = tmem_base + 256u + 128u * w;
+    const int n_w = w == 0 ? n0 : n1;
+    const float sl2 = p.scale_log2;
+    float m_used = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_w; ++j) {
+      mbar_wait(s_full(w), (uint32_t)j & 1u);
+      tc_fence_after();
+      uint32_t sv[4][32];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv[c]);
+      tmem_ld_wait();
+      if (j == n_w - 1) {                                           // diagonal tile: key c is visible iff c <= row
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (c * 32 + e > r_local) sv[c][e] = 0xff800000u;       // -inf
+      }
+      if (j == 0) {                                                 // first tile: the reference max is this tile's max
+        float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+        for (int e = 0; e < 32; e += 2) {
+          a0 = max3(a0, __uint_as_float(sv[0][e]), __uint_as_float(sv[0][e + 1]));
+          a1 = max3(a1, __uint_as_float(sv[1][e]), __uint_as_float(sv[1][e + 1]));
+          a2 = max3(a2, __uint_as_float(sv[2][e]), __uint_as_float(sv[2][e + 1]));
+          a3 = max3(a3, __uint_as_float(sv[3][e]), __uint_as_float(sv[3][e + 1]));
+        }
+        m_used = max3(a0, a1, fmaxf(a2, a3)) * sl2;
+      }
+      // Optimistic pass: exponentials against the CURRENT reference max while the tile max is tracked on the
+      // side (four independent max chains, off the MUFU-bound critical path).  The reference only moves when
+      // the max grew by more than 2^8 -- rare after the first tiles -- and then the tile is redone below.
+      float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      float sum0 = 0.f, sum1 = 0.f;
+      {
+        const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float s0 = __uint_as_float(sv[c][e]), s1 = __uint_as_float(sv[c][e + 1]);
+            mxa[c] = max3(mxa[c], s0, s1);
+            const float2 x = fma2(make_float2(s0, s1), sc2, nm2);
+            float p0, p1;
+            if (((e >> 1) & 3) < kPolyOf4) {
+              const float2 pp = exp2_poly2(x);
+              p0 = pp.x;
+              p1 = pp.y;
+            } else {
+              p0 = fast_exp2(x.x);
+              p1 = fast_exp2(x.y);
+            }
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          tmem_st_32x16(tmem_s + lane_addr + c * 16, pk);
+        }
+      }
+      const float mx2 = max3(mxa[0], mxa[1], fmaxf(mxa[2], mxa[3])) * sl2;
+      const bool need = mx2 > m_used + 8.f;
+      if (__any_sync(0xffffffffu, need)) {
+        // slow path: move the reference, redo the exponentials of this tile from the S values still in
+        // registers, rescale the running sum and (after the first tile) the O accumulator.  PV_{j-1} of this
+        // tile retired before S_j was produced (in-order tensor pipe), so O is quiescent here.
+        const float m_next = need ? mx2 : m_used;
+        const float alpha = need ? fast_exp2(m_used - m_next) : 1.f;
+        m_used = m_next;
+        l_run *= alpha;
+        sum0 = 0.f;
+        sum1 = 0.f;
+        const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const float2 x = fma2(make_float2(__uint_as_float(sv[c][e]), __uint_as_float(sv[c][e + 1])), sc2, nm2);
+            const float p0 = fast_exp2(x.x), p1 = fast_exp2(x.y);
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+          tmem_st_32x16(tmem_s + lane_addr + c * 16, pk);
+        }
+        if (j > 0) {
+#pragma unroll 1
+          for (int c = 0; c < kD / 16; ++c) {
+            uint32_t tt[16];
+            tmem_ld_32x16(tmem_o + lane_addr + c * 16, tt);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tt[i] = __float_as_uint(__uint_as_float(tt[i]) * alpha);
+            tmem_st_32x16(tmem_o + lane_addr + c * 16, tt);
+          }
+        }
+      }
+      l_run += sum0 + sum1;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(w));
+    }
+    mbar_wait(o_full(w), 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* orow = p.out + (size_t)(row0 + w * kBM + r_local) * p.out_stride + h * kD;
+#pragma unroll
+    for (int c = 0; c < kD / 32; ++c) {
+      uint32_t tt[32];
+      tmem_ld_32x32(tmem_o + lane_addr + c * 32, tt);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(tt[e + i]) * inv;
+        st_bf16x8(orow + c * 32 + e, pack8(f));
+      }
+    }
+    p.lse[((size_t)b * p.n_heads + h) * p.seq + q_pos] =
+        (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_enc = nullptr;
 std::once_flag g_attn_once;
+int g_fwd_poly = 1;          // exponentials evaluated on the FMA pipe: this many of every 4 pairs (0, 1 or 2)
+int g_fwd_version = 2;       // 2 = two Q tiles per CTA, 128-key tiles (default); 1 = one Q tile, 64-key tiles
 std::string g_attn_err;
 
 void attn_init() {
@@ -296,6 +645,9 @@ void attn_init() {
       q == cudaDriverEntryPointSuccess)
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+  cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
+  cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
+  cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
 }
 
 bool attn_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld, uint32_t box_rows) {
@@ -310,6 +662,9 @@ bool attn_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, ui
 }  // namespace
 
 const char* attention_last_error() { return g_attn_err.c_str(); }
+void attention_fwd_set_version(int v) { g_fwd_version = (v == 1) ? 1 : 2; }
+int attention_fwd_get_version() { return g_fwd_version; }
+void attention_fwd_set_poly(int n) { g_fwd_poly = n < 0 ? 0 : (n > 2 ? 2 : n); }
 
 // qkv: [batch*seq, (n_heads + 2*n_kv) * 128] bf16 (row stride qkv_stride), already RoPE'd.
 // out: [batch*seq, n_heads*128] bf16 (row stride out_stride); lse: [batch, n_heads, seq] fp32.
@@ -332,8 +687,20 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int batch, int
   p.out_stride = out_stride;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.lse = lse;
-  const int grid = p.q_tiles * batch * n_heads;
-  attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, s>>>(tq, tkv, p);
+  if (g_fwd_version == 2 && seq % (2 * kBM) == 0) {
+    CUtensorMap tq2, tkv2;
+    if (!attn_tmap(&tq2, qkv, cols, rows, qkv_stride, 2 * kBM) || !attn_tmap(&tkv2, qkv, cols, rows, qkv_stride, kBN2)) {
+      g_attn_err = "cuTensorMapEncodeTiled failed";
+      return 3;
+    }
+    const int grid2 = (seq / (2 * kBM)) * batch * n_heads;
+    if (g_fwd_poly == 0) attn_fwd2_tcgen05_kernel<0><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
+    else if (g_fwd_poly == 1) attn_fwd2_tcgen05_kernel<1><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
+    else attn_fwd2_tcgen05_kernel<2><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
+  } else {
+    const int grid = p.q_tiles * batch * n_heads;
+    attn_fwd_tcgen05_kernel<<<grid, kAttnThreads, kAttnSmemBytes, s>>>(tq, tkv, p);
+  }
   count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_attn_err = cudaGetErrorString(e); return 4; }

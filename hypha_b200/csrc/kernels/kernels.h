@@ -112,6 +112,9 @@ int gemm_get_cta_mode();
 int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int batch, int seq, int n_heads, int n_kv,
                           int head_dim, int qkv_stride, int out_stride, float scale, cudaStream_t s);
 const char* attention_last_error();
+void attention_fwd_set_version(int v);   // 2 = two-Q-tile ping-pong kernel (default), 1 = one Q tile per CTA
+int attention_fwd_get_version();
+void attention_fwd_set_poly(int n);      // 0..2 of every 4 exponential pairs on the FMA pipe instead of MUFU
 // ---- tcgen05 flash-attention backward (attention_bwd_tcgen05.cu) ---------------------------------
 // ws: fp32 workspace of 2 * batch * n_heads * seq floats.  dqkv is fully overwritten.
 int attention_bwd_tcgen05(const bf16* qkv, const bf16* out, const bf16* dout, const float* lse, bf16* dqkv, float* ws,

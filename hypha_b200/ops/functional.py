@@ -675,8 +675,28 @@ def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: in
     return dqkv
 
 
-def attention_fwd_tcgen05(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int):
+def set_attention_fwd_version(version: int) -> None:
+    """2 (default) = two 128-row Q tiles per CTA ping-ponging on one MMA issuer, 128-key tiles (needs
+    seq % 256 == 0, else version 1 runs); 1 = one Q tile per CTA, 64-key tiles, two CTAs per SM."""
+    load_C().attention_fwd_set_version(int(version))
+
+
+def set_attention_fwd_poly(n: int) -> None:
+    """How many of every 4 exponential pairs the forward evaluates with the FMA-pipe polynomial instead of
+    MUFU.EX2 (0, 1 or 2; the softmax is MUFU-bound on B200)."""
+    load_C().attention_fwd_set_poly(int(n))
+
+
+def attention_fwd_tcgen05(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int,
+                          version: Optional[int] = None):
     """Raw forward: returns ``(out [tokens, Hq*D], lse [B, Hq, S])``."""
+    if version is not None:
+        prev = load_C().attention_fwd_get_version()
+        set_attention_fwd_version(version)
+        try:
+            return attention_fwd_tcgen05(qkv, batch, seq, n_heads, n_kv, head_dim)
+        finally:
+            set_attention_fwd_version(prev)
     out = torch.empty((batch * seq, n_heads * head_dim), dtype=qkv.dtype, device=qkv.device)
     lse = torch.empty((batch, n_heads, seq), dtype=torch.float32, device=qkv.device)
     load_C().attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), batch, seq, n_heads, n_kv, head_dim,

@@ -424,8 +424,9 @@ def test_llama_fp8_step_close_to_bf16(C):
     assert _rel(grads[1], grads[0]) < 0.2
 
 
-@pytest.mark.parametrize("B,S,Hq,Hk", [(1, 128, 2, 1), (2, 512, 8, 2), (1, 1024, 4, 4)])
-def test_attention_fwd_tcgen05(C, B, S, Hq, Hk):
+@pytest.mark.parametrize("version", [2, 1])
+@pytest.mark.parametrize("B,S,Hq,Hk", [(1, 128, 2, 1), (1, 256, 2, 1), (2, 512, 8, 2), (1, 1024, 4, 4), (1, 2048, 8, 2)])
+def test_attention_fwd_tcgen05(C, B, S, Hq, Hk, version):
     """Hand-written tcgen05 flash-attention forward vs fp32 SDPA reference (output and lse)."""
     from hypha_b200 import ops
     from hypha_b200.ops.functional import _attention_ref
@@ -433,7 +434,7 @@ def test_attention_fwd_tcgen05(C, B, S, Hq, Hk):
     torch.manual_seed(0)
     D = 128
     qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16)
-    out, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)
+    out, lse = ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D, version=version)
     ref = _attention_ref(qkv.float(), B, S, Hq, Hk, D)
     assert _rel(out, ref) < 2e-2, _rel(out, ref)
     q = qkv[:, : Hq * D].view(B, S, Hq, D).transpose(1, 2).float()
