@@ -35,6 +35,8 @@ def main():
         row = {"B": B, "S": S}
         with torch.no_grad():
             for name, fn in (("tcgen05", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D)),
+                             ("tcgen05_v3", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D, version=3)),
+                             ("tcgen05_v2", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D, version=2)),
                              ("tcgen05_v1", lambda: ops.attention_fwd_tcgen05(qkv, B, S, Hq, Hk, D, version=1)),
                              ("cudnn", lambda: _attention_sdpa(qkv, B, S, Hq, Hk, D)),
                              ("flash2", lambda: _FlashAttnQKV.apply(qkv, B, S, Hq, Hk, D))):

@@ -87,30 +87,39 @@ struct FusedParams {
   bf16* dqkv;
 };
 
-// D = rowsum(dO o O), lse2 = lse * log2(e), and the fp32 dQ accumulator row segment is zeroed (one warp per
-// (token, head): lane l owns 4 of the 128 columns).
+// D = rowsum(dO o O), lse2 = lse * log2(e), and the fp32 dQ accumulator is zeroed.  Eight lanes per (token, head)
+// row: 32 bytes of O and dO per lane (two 16-byte loads each, 4 rows in flight per warp) and 64 bytes of zeros.
 __global__ void __launch_bounds__(256) attn_bwd_fused_prep_kernel(const bf16* __restrict__ out, const bf16* __restrict__ dout,
                                                                   const float* __restrict__ lse, float* __restrict__ delta,
                                                                   float* __restrict__ lse2, float* __restrict__ dq_acc,
                                                                   int tokens, int seq, int n_heads, int out_stride,
                                                                   int dout_stride) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (w >= (int64_t)tokens * n_heads) return;
-  const int t = (int)(w / n_heads), h = (int)(w % n_heads);
-  const uint2 ov = *reinterpret_cast<const uint2*>(out + (size_t)t * out_stride + h * kD + lane * 4);
-  const uint2 gv = *reinterpret_cast<const uint2*>(dout + (size_t)t * dout_stride + h * kD + lane * 4);
-  const __nv_bfloat162* o2 = reinterpret_cast<const __nv_bfloat162*>(&ov);
-  const __nv_bfloat162* g2 = reinterpret_cast<const __nv_bfloat162*>(&gv);
+  const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t row = gid >> 3;                                    // (token, head)
+  const int sub = (int)(gid & 7);                                  // 16 of the 128 columns
+  const bool live = row < (int64_t)tokens * n_heads;
   float acc = 0.f;
+  int t = 0, h = 0;
+  if (live) {
+    t = (int)(row / n_heads);
+    h = (int)(row % n_heads);
+    const bf16* o = out + (size_t)t * out_stride + h * kD + sub * 16;
+    const bf16* g = dout + (size_t)t * dout_stride + h * kD + sub * 16;
+    const bf16x8 o0 = ld_stream_bf16x8(o), o1 = ld_stream_bf16x8(o + 8);
+    const bf16x8 g0 = ld_stream_bf16x8(g), g1 = ld_stream_bf16x8(g + 8);
+    float fo[16], fg[16];
+    unpack8(o0, fo); unpack8(o1, fo + 8);
+    unpack8(g0, fg); unpack8(g1, fg + 8);
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const float2 a = __bfloat1622float2(o2[i]), b = __bfloat1622float2(g2[i]);
-    acc += a.x * b.x + a.y * b.y;
+    for (int i = 0; i < 16; ++i) acc = fmaf(fo[i], fg[i], acc);
+    float4* z = reinterpret_cast<float4*>(dq_acc + (size_t)row * kD + sub * 16);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    z[0] = zero; z[1] = zero; z[2] = zero; z[3] = zero;
   }
-  *reinterpret_cast<float4*>(dq_acc + ((size_t)t * n_heads + h) * kD + lane * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-  acc = warp_sum(acc);
-  if (lane == 0) {
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (live && sub == 0) {
     const int b = t / seq, pos = t % seq;
     const size_t idx = ((size_t)b * n_heads + h) * seq + pos;
     delta[idx] = acc;
@@ -187,7 +196,7 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_qkv,     // qkv bf
   const uint32_t tmem_dk = tmem_base, tmem_dv = tmem_base + 128, tmem_dp = tmem_base + 256, tmem_s = tmem_base + 384;
 
   if (warp >= 12) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     if (warp == 13 && lane == 0) {
       // ====================== TMA producer ======================
       mbar_arrive_expect_tx(kv_full, 2 * kTileBytes);
@@ -211,39 +220,47 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_qkv,     // qkv bf
         tma_load_2d(do_smem, &tma_do, do_full, h * kD, qrow);
         tma_load_2d(do_smem + kAtomBytes, &tma_do, do_full, h * kD + 64, qrow);
       }
-    } else if (warp == 12 && lane == 0) {
-      // ====================== MMA issuer ========================
+    } else if (warp == 12) {
+      // ====================== MMA issuer: the whole warp walks the loop, one elected lane issues ========================
       const uint32_t idesc_kk = umma_idesc_bf16(kT, kT, 0, 0);     // S^T = K Q^T, dP^T = V dO^T : K-major x K-major
       const uint32_t idesc_kn = umma_idesc_bf16(kT, kD, 0, 1);     // dV += P^T dO, dK += dS^T Q : B MN-major
       const uint32_t idesc_nn = umma_idesc_bf16(kT, kD, 1, 1);     // dQ = dS K : A (dS^T read transposed) and B MN-major
-      auto kmajor = [](uint32_t base, int kk) {                    // 16-element k-step inside a two-atom K-major tile
-        return umma_smem_desc(base + (uint32_t)(kk >> 2) * kAtomBytes + (uint32_t)(kk & 3) * 32, 16, 1024);
-      };
-      auto mnmajor = [](uint32_t base, int kk) {                   // 16 k-rows of 128 B; 64-element MN chunks one atom apart
-        return umma_smem_desc(base + (uint32_t)kk * (16 * 128), kAtomBytes, 1024);
-      };
+      // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) moves
+      const uint64_t dK_k = umma_smem_desc(k_smem, 16, 1024), dK_n = umma_smem_desc(k_smem, kAtomBytes, 1024);
+      const uint64_t dV_k = umma_smem_desc(v_smem, 16, 1024);
+      const uint64_t dDO_k = umma_smem_desc(do_smem, 16, 1024), dDO_n = umma_smem_desc(do_smem, kAtomBytes, 1024);
+      const uint64_t dDS_k = umma_smem_desc(ds_smem, 16, 1024), dDS_n = umma_smem_desc(ds_smem, kAtomBytes, 1024);
+      const uint64_t dQ_k0 = umma_smem_desc(q_smem, 16, 1024), dQ_n0 = umma_smem_desc(q_smem, kAtomBytes, 1024);
+      auto koff = [](int kk) { return (uint64_t)(((kk >> 2) * kAtomBytes + (kk & 3) * 32) >> 4); };   // K-major 16-element k-step
+      auto noff = [](int kk) { return (uint64_t)((kk * 16 * 128) >> 4); };                               // MN-major: 16 k-rows
       auto issue_dq_dk = [&](int it) {                             // consumes dS_it, Q_it, K_j
-        const uint32_t qb = q_smem + (it & 1) * kTileBytes;
+        const uint64_t qn = dQ_n0 + (uint64_t)((it & 1) * (kTileBytes >> 4));
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk)
-          umma_bf16_ss(tmem_dp, mnmajor(ds_smem, kk), mnmajor(k_smem, kk), idesc_nn, kk != 0 ? 1u : 0u);
-        umma_commit(dq_full);
+          for (int kk = 0; kk < kT / 16; ++kk)
+            umma_bf16_ss(tmem_dp, dDS_n + noff(kk), dK_n + noff(kk), idesc_nn, kk != 0 ? 1u : 0u);
+          umma_commit(dq_full);
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk)
-          umma_bf16_ss(tmem_dk, kmajor(ds_smem, kk), mnmajor(qb, kk), idesc_kn, (it != 0 || kk != 0) ? 1u : 0u);
-        umma_commit(q_empty(it & 1));
-        umma_commit(ds_empty);
+          for (int kk = 0; kk < kT / 16; ++kk)
+            umma_bf16_ss(tmem_dk, dDS_k + koff(kk), qn + noff(kk), idesc_kn, (it != 0 || kk != 0) ? 1u : 0u);
+          umma_commit(q_empty(it & 1));
+          umma_commit(ds_empty);
+        }
+        __syncwarp();
       };
       mbar_wait(kv_full, 0);
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1;
-        const uint32_t qb = q_smem + st * kTileBytes;
+        const uint64_t qk = dQ_k0 + (uint64_t)(st * (kTileBytes >> 4));
         mbar_wait(q_full(st), (uint32_t)(it >> 1) & 1u);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk)
-          umma_bf16_ss(tmem_s, kmajor(k_smem, kk), kmajor(qb, kk), idesc_kk, kk != 0 ? 1u : 0u);
-        umma_commit(s_full);
+          for (int kk = 0; kk < kD / 16; ++kk)
+            umma_bf16_ss(tmem_s, dK_k + koff(kk), qk + koff(kk), idesc_kk, kk != 0 ? 1u : 0u);
+          umma_commit(s_full);
+        }
+        __syncwarp();
         if (it > 0) {
           mbar_wait(ds_full, (uint32_t)(it - 1) & 1u);
           tc_fence_after();
@@ -252,24 +269,31 @@ attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tma_qkv,     // qkv bf
         }
         mbar_wait(do_full, (uint32_t)it & 1u);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk)
-          umma_bf16_ss(tmem_dp, kmajor(v_smem, kk), kmajor(do_smem, kk), idesc_kk, kk != 0 ? 1u : 0u);
-        umma_commit(dp_full);
+          for (int kk = 0; kk < kD / 16; ++kk)
+            umma_bf16_ss(tmem_dp, dV_k + koff(kk), dDO_k + koff(kk), idesc_kk, kk != 0 ? 1u : 0u);
+          umma_commit(dp_full);
+        }
+        __syncwarp();
         mbar_wait(p_full, (uint32_t)it & 1u);
         tc_fence_after();
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kT / 16; ++kk) {
-          // P^T (bf16 pairs) sits in the S columns each warpgroup just consumed: q 0..63 -> cols 0..31, q 64..127 -> cols 64..95
-          const uint32_t a_tmem = tmem_s + (uint32_t)(kk >> 2) * 64 + (uint32_t)(kk & 3) * 8;
-          umma_bf16_ts(tmem_dv, a_tmem, mnmajor(do_smem, kk), idesc_kn, (it != 0 || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < kT / 16; ++kk) {
+            // P^T (bf16 pairs) sits in the S columns each warpgroup just consumed: q 0..63 -> cols 0..31, q 64..127 -> cols 64..95
+            const uint32_t a_tmem = tmem_s + (uint32_t)(kk >> 2) * 64 + (uint32_t)(kk & 3) * 8;
+            umma_bf16_ts(tmem_dv, a_tmem, dDO_n + noff(kk), idesc_kn, (it != 0 || kk != 0) ? 1u : 0u);
+          }
+          umma_commit(do_empty);
         }
-        umma_commit(do_empty);
+        __syncwarp();
       }
       mbar_wait(ds_full, (uint32_t)(n_it - 1) & 1u);
       tc_fence_after();
       issue_dq_dk(n_it - 1);
-      umma_commit(acc_full);
+      if (elect_one_sync()) umma_commit(acc_full);
+      __syncwarp();
     }
   } else if (warp >= 4) {
     // ====================== softmax warpgroups ==========
@@ -467,8 +491,8 @@ int attention_bwd_fused_tcgen05(const bf16* qkv, const bf16* out, const bf16* do
     return 3;
   }
   {
-    const int64_t warps = (int64_t)rows * n_heads;
-    const int blocks = (int)((warps * 32 + 255) / 256);
+    const int64_t threads = (int64_t)rows * n_heads * 8;
+    const int blocks = (int)((threads + 255) / 256);
     attn_bwd_fused_prep_kernel<<<blocks, 256, 0, s>>>(out, dout, lse, delta, lse2, dq_acc, (int)rows, seq, n_heads,
                                                       out_stride, dout_stride);
     count_launch();

@@ -313,6 +313,9 @@ struct Attn2Smem {
 };
 constexpr int kAttn2SmemBytes = Attn2Smem::total + 1024;
 
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
@@ -429,36 +432,46 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box 
         tma_load_2d(v_smem + st * kKV2Bytes, &tma_kv, v_full(st), v_col, krow);
         tma_load_2d(v_smem + st * kKV2Bytes + kAtom2, &tma_kv, v_full(st), v_col + 64, krow);
       }
-    } else if (warp == 8 && lane == 0) {
-      // ====================== MMA issuer ========================
+    } else if (warp == 8) {
+      // ====================== MMA issuer: the whole warp walks the loop, one elected lane issues ========================
       const uint32_t idesc_s = umma_idesc_bf16(kBM, kBN2, 0, 0);   // S = Q K^T
       const uint32_t idesc_o = umma_idesc_bf16(kBM, kD, 0, 1);     // O += P V : V MN-major
+      const uint64_t dq0 = umma_smem_desc(q_smem, 16, 1024), dq1 = umma_smem_desc(q_smem + kAtom2, 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(k_smem, 16, 1024), dv0 = umma_smem_desc(v_smem, kAtom2, 1024);
       auto issue_s = [&](int w, int j) {                           // S_w = Q_w K_j^T into TMEM columns 128w..
-        const uint32_t kb = k_smem + (j & 1) * kKV2Bytes;
-        const uint32_t qb = q_smem + w * kAtom2;                   // rows 128w.. of each 256-row atom
+        const uint64_t kd = dk0 + (uint64_t)((j & 1) * (kKV2Bytes >> 4));
+        const uint64_t qd = w ? dq1 : dq0;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kD / 16; ++kk) {
-          const uint64_t ad = umma_smem_desc(qb + (kk >> 2) * (2 * kAtom2) + (kk & 3) * 32, 16, 1024);
-          const uint64_t bd = umma_smem_desc(kb + (kk >> 2) * kAtom2 + (kk & 3) * 32, 16, 1024);
-          umma_bf16_ss(tmem_base + 128u * w, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint64_t ad = qd + (uint64_t)((((kk >> 2) * (2 * kAtom2)) + (kk & 3) * 32) >> 4);
+            const uint64_t bd = kd + (uint64_t)((((kk >> 2) * kAtom2) + (kk & 3) * 32) >> 4);
+            umma_bf16_ss(tmem_base + 128u * w, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(w));
         }
-        umma_commit(s_full(w));
+        __syncwarp();
       };
       auto issue_pv = [&](int w, int j) {
-        const uint32_t vb = v_smem + (j & 1) * kKV2Bytes;
+        const uint64_t vd = dv0 + (uint64_t)((j & 1) * (kKV2Bytes >> 4));
+        if (elect_one_sync()) {
 #pragma unroll
-        for (int kk = 0; kk < kBN2 / 16; ++kk) {
-          const uint64_t bd = umma_smem_desc(vb + kk * (16 * 128), kAtom2, 1024);
-          umma_bf16_ts(tmem_base + 256u + 128u * w, tmem_base + 128u * w + kk * 8, bd, idesc_o,
-                       (j != 0 || kk != 0) ? 1u : 0u);
+          for (int kk = 0; kk < kBN2 / 16; ++kk)
+            umma_bf16_ts(tmem_base + 256u + 128u * w, tmem_base + 128u * w + kk * 8, vd + (uint64_t)((kk * 16 * 128) >> 4),
+                         idesc_o, (j != 0 || kk != 0) ? 1u : 0u);
         }
+        __syncwarp();
+      };
+      auto commit = [&](uint32_t bar) {
+        if (elect_one_sync()) umma_commit(bar);
+        __syncwarp();
       };
       mbar_wait(q_full, 0);
       mbar_wait(k_full(0), 0);
       tc_fence_after();
       issue_s(0, 0);
       issue_s(1, 0);
-      umma_commit(k_empty(0));
+      commit(k_empty(0));
       for (int j = 0; j < n1; ++j) {
         const int st = j & 1, nst = (j + 1) & 1;
         mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
@@ -466,7 +479,7 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box 
           mbar_wait(p_full(0), (uint32_t)j & 1u);
           tc_fence_after();
           issue_pv(0, j);
-          if (j == n0 - 1) umma_commit(o_full(0));
+          if (j == n0 - 1) commit(o_full(0));
         }
         if (j + 1 < n0) {
           mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
@@ -476,13 +489,13 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box 
         mbar_wait(p_full(1), (uint32_t)j & 1u);
         tc_fence_after();
         issue_pv(1, j);
-        umma_commit(v_empty(st));
-        if (j == n1 - 1) umma_commit(o_full(1));
+        commit(v_empty(st));
+        if (j == n1 - 1) commit(o_full(1));
         if (j + 1 < n1) {
           mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
           tc_fence_after();
           issue_s(1, j + 1);
-          umma_commit(k_empty(nst));
+          commit(k_empty(nst));
         }
       }
     }
@@ -629,13 +642,707 @@ attn_fwd2_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box 
   }
 }
 
+
+// =====================================================================================================
+// Forward v3 = v2 made PERSISTENT: one CTA per SM walks a heavy-first, snake-ordered list of (tile pair,
+// batch, head) work items, so TMEM allocation, barrier set-up, the Q load and the O write-back of an item
+// overlap the MMAs / exponentials of its neighbours instead of costing ~16 us per item (v2 measured
+// time = 29.6 kclk + 3.3 kclk * key tiles per CTA).  A third warpgroup takes the epilogue off the softmax
+// warpgroups: it drains O_w from TMEM, normalises with the row statistics the softmax warpgroup left in
+// shared memory, and writes O and LSE while the softmax warpgroups are already on the next item.
+//
+//   warps 0-3 / 4-7  softmax of Q tile 0 / 1 (as v2)          warps 8-11  epilogue / write-back
+//   warp 12          tcgen05.mma issuer                          warp 13     TMA producer
+// =====================================================================================================
+constexpr int kFwd3Threads = 512;
+struct Attn3Smem {
+  static constexpr int q_off = 0;
+  static constexpr int k_off = q_off + kQ2Bytes;
+  static constexpr int v_off = k_off + 2 * kKV2Bytes;
+  static constexpr int stat_off = v_off + 2 * kKV2Bytes;       // [2 tiles][128 rows] x (1/l, lse)
+  static constexpr int bar_off = stat_off + 2 * 128 * 8;
+  static constexpr int total = bar_off + 32 * 8;
+};
+constexpr int kAttn3SmemBytes = Attn3Smem::total + 1024;
+
+template <int kPolyOf4>
+__global__ void __launch_bounds__(kFwd3Threads, 1)
+attn_fwd3_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {64, 256}
+                         const __grid_constant__ CUtensorMap tma_kv,     // box {64, 128}
+                         const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base + Attn3Smem::q_off;
+  const uint32_t k_smem = smem_base + Attn3Smem::k_off;
+  const uint32_t v_smem = smem_base + Attn3Smem::v_off;
+  float2* stats = reinterpret_cast<float2*>(smem_gen + Attn3Smem::stat_off);
+  const uint32_t bars = smem_base + Attn3Smem::bar_off;
+  const uint32_t q_full = bars, q_empty = bars + 8u;
+  auto k_full = [&](int s) { return bars + 8u * (2 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (4 + s); };
+  auto v_full = [&](int s) { return bars + 8u * (6 + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (8 + s); };
+  auto s_full = [&](int w) { return bars + 8u * (10 + w); };
+  auto p_full = [&](int w) { return bars + 8u * (12 + w); };
+  auto o_full = [&](int w) { return bars + 8u * (14 + w); };
+  auto o_free = [&](int w) { return bars + 8u * (16 + w); };
+  auto st_full = [&](int w) { return bars + 8u * (18 + w); };
+  const uint32_t tmem_ptr_smem = bars + 8u * 24;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Attn3Smem::bar_off + 8 * 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_tile = p.batch * p.n_heads;
+  const int pairs = p.seq / (2 * kBM);
+  const int n_items = pairs * per_tile;
+  const int G = (int)gridDim.x;
+  // item of round k for this CTA: snake order over the heavy-first list keeps the per-CTA totals within ~2 %
+  auto item_of = [&](int k) { return k * G + ((k & 1) ? (G - 1 - (int)blockIdx.x) : (int)blockIdx.x); };
+
+  if (warp == 13 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 4); mbar_init(o_full(s), 1);
+      mbar_init(o_free(s), 4); mbar_init(st_full(s), 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 12) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp >= 12) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+    if (warp == 13 && lane == 0) {
+      // ====================== TMA producer ======================
+      uint32_t kc = 0;                                             // running K/V tile count (ring position)
+      for (int k = 0;; ++k) {
+        const int item = item_of(k);
+        if (item >= n_items) break;
+        const int t = pairs - 1 - item / per_tile, bh = item % per_tile;
+        const int b = bh / p.n_heads, h = bh % p.n_heads, hk = h / (p.n_heads / p.n_kv);
+        const int row0 = b * p.seq + t * 2 * kBM;
+        const int q_col = h * kD, k_col = (p.n_heads + hk) * kD, v_col = (p.n_heads + p.n_kv + hk) * kD;
+        const int n1 = 2 * t + 2;
+        mbar_wait(q_empty, ((uint32_t)k & 1u) ^ 1u);               // the S MMAs of the previous item have read Q
+        mbar_arrive_expect_tx(q_full, kQ2Bytes);
+        tma_load_2d(q_smem, &tma_q, q_full, q_col, row0);
+        tma_load_2d(q_smem + 2 * kAtom2, &tma_q, q_full, q_col + 64, row0);
+        for (int j = 0; j < n1; ++j, ++kc) {
+          const int st = kc & 1;
+          const uint32_t par = ((kc >> 1) & 1u) ^ 1u;
+          const int krow = b * p.seq + j * kBN2;
+          mbar_wait(k_empty(st), par);
+          mbar_arrive_expect_tx(k_full(st), kKV2Bytes);
+          tma_load_2d(k_smem + st * kKV2Bytes, &tma_kv, k_full(st), k_col, krow);
+          tma_load_2d(k_smem + st * kKV2Bytes + kAtom2, &tma_kv, k_full(st), k_col + 64, krow);
+          mbar_wait(v_empty(st), par);
+          mbar_arrive_expect_tx(v_full(st), kKV2Bytes);
+          tma_load_2d(v_smem + st * kKV2Bytes, &tma_kv, v_full(st), v_col, krow);
+          tma_load_2d(v_smem + st * kKV2Bytes + kAtom2, &tma_kv, v_full(st), v_col + 64, krow);
+        }
+      }
+    } else if (warp == 12) {
+      // ====================== MMA issuer: the whole warp walks the loop, one elected lane issues ========================
+      const uint32_t idesc_s = umma_idesc_bf16(kBM, kBN2, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(kBM, kD, 0, 1);
+      // descriptors are built once; per MMA only the 14-bit start-address field (16-byte units) moves
+      const uint64_t dq0 = umma_smem_desc(q_smem, 16, 1024), dq1 = umma_smem_desc(q_smem + kAtom2, 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(k_smem, 16, 1024), dv0 = umma_smem_desc(v_smem, kAtom2, 1024);
+      auto issue_s = [&](int w, uint32_t kcnt) {
+        const uint64_t kd = dk0 + (uint64_t)((kcnt & 1) * (kKV2Bytes >> 4));
+        const uint64_t qd = w ? dq1 : dq0;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint64_t ad = qd + (uint64_t)((((kk >> 2) * (2 * kAtom2)) + (kk & 3) * 32) >> 4);
+            const uint64_t bd = kd + (uint64_t)((((kk >> 2) * kAtom2) + (kk & 3) * 32) >> 4);
+            umma_bf16_ss(tmem_base + 128u * w, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(w));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint32_t bar) {
+        if (elect_one_sync()) umma_commit(bar);
+        __syncwarp();
+      };
+      auto issue_pv = [&](int w, uint32_t kcnt, bool first) {
+        const uint64_t vd = dv0 + (uint64_t)((kcnt & 1) * (kKV2Bytes >> 4));
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < kBN2 / 16; ++kk) {
+            umma_bf16_ts(tmem_base + 256u + 128u * w, tmem_base + 128u * w + kk * 8, vd + (uint64_t)((kk * 16 * 128) >> 4),
+                         idesc_o, (!first || kk != 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      uint32_t kc = 0;                                             // K/V tiles consumed so far (ring position of tile 0 of the item)
+      uint32_t pc0 = 0, pc1 = 0;                                   // P tiles consumed per warpgroup (p_full phase)
+      for (int k = 0;; ++k) {
+        const int item = item_of(k);
+        if (item >= n_items) break;
+        const int t = pairs - 1 - item / per_tile;
+        const int n0 = 2 * t + 1, n1 = 2 * t + 2;
+        mbar_wait(q_full, (uint32_t)k & 1u);
+        mbar_wait(k_full(kc & 1), (kc >> 1) & 1u);
+        tc_fence_after();
+        issue_s(0, kc);
+        issue_s(1, kc);
+        commit(k_empty(kc & 1));
+        for (int j = 0; j < n1; ++j) {
+          const uint32_t cur = kc + j, nxt = cur + 1;
+          mbar_wait(v_full(cur & 1), (cur >> 1) & 1u);
+          if (j < n0) {
+            if (j == 0 && k > 0) mbar_wait(o_free(0), (uint32_t)(k - 1) & 1u);   // O0 of the previous item written back
+            mbar_wait(p_full(0), pc0 & 1u);
+            ++pc0;
+            tc_fence_after();
+            issue_pv(0, cur, j == 0);
+            if (j == n0 - 1) commit(o_full(0));
+          }
+          if (j + 1 < n0) {
+            mbar_wait(k_full(nxt & 1), (nxt >> 1) & 1u);
+            tc_fence_after();
+            issue_s(0, nxt);
+          }
+          if (j == 0 && k > 0) mbar_wait(o_free(1), (uint32_t)(k - 1) & 1u);
+          mbar_wait(p_full(1), pc1 & 1u);
+          ++pc1;
+          tc_fence_after();
+          issue_pv(1, cur, j == 0);
+          commit(v_empty(cur & 1));
+          if (j == n1 - 1) commit(o_full(1));
+          if (j + 1 < n1) {
+            mbar_wait(k_full(nxt & 1), (nxt >> 1) & 1u);
+            tc_fence_after();
+            issue_s(1, nxt);
+            commit(k_empty(nxt & 1));
+            if (j + 1 == n1 - 1) commit(q_empty);             // last S MMAs of this item: Q may be replaced
+          }
+        }
+        kc += (uint32_t)n1;
+      }
+    }
+  } else if (warp >= 8) {
+    // ====================== epilogue warpgroup: O_w / l -> bf16 -> global, LSE ==========
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    const int q4 = warp & 3;
+    const int r_local = q4 * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    for (int k = 0;; ++k) {
+      const int item = item_of(k);
+      if (item >= n_items) break;
+      const int t = pairs - 1 - item / per_tile, bh = item % per_tile;
+      const int b = bh / p.n_heads, h = bh % p.n_heads;
+      const int row0 = b * p.seq + t * 2 * kBM;
+#pragma unroll 1
+      for (int w = 0; w < 2; ++w) {
+        mbar_wait(st_full(w), (uint32_t)k & 1u);
+        mbar_wait(o_full(w), (uint32_t)k & 1u);
+        tc_fence_after();
+        const float2 st = stats[w * 128 + r_local];
+        bf16* orow = p.out + (size_t)(row0 + w * kBM + r_local) * p.out_stride + h * kD;
+#pragma unroll 1
+        for (int c = 0; c < kD / 32; ++c) {
+          uint32_t tt[32];
+          tmem_ld_32x32(tmem_base + 256u + 128u * w + lane_addr + c * 32, tt);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(tt[e + i]) * st.x;
+            st_bf16x8(orow + c * 32 + e, pack8(f));
+          }
+        }
+        p.lse[((size_t)b * p.n_heads + h) * p.seq + t * 2 * kBM + w * kBM + r_local] = st.y;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(o_free(w));
+      }
+    }
+  } else {
+    // ====================== softmax warpgroups (w = 0, 1) ==========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 184;");
+    const int w = warp >> 2;
+    const int q4 = warp & 3;
+    const int r_local = q4 * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tmem_s = tmem_base + 128u * w, tmem_o = tmem_base + 256u + 128u * w;
+    const float sl2 = p.scale_log2;
+    uint32_t sc = 0;                                               // S tiles consumed so far (s_full phase)
+    for (int k = 0;; ++k) {
+      const int item = item_of(k);
+      if (item >= n_items) break;
+      const int t = pairs - 1 - item / per_tile;
+      const int n_w = w == 0 ? 2 * t + 1 : 2 * t + 2;
+      float m_used = -INFINITY, l_run = 0.f;
+      for (int j = 0; j < n_w; ++j, ++sc) {
+        mbar_wait(s_full(w), sc & 1u);
+        tc_fence_after();
+        uint32_t sv[4][32];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv[c]);
+        tmem_ld_wait();
+        if (j == n_w - 1) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 32; ++e)
+              if (c * 32 + e > r_local) sv[c][e] = 0xff800000u;
+        }
+        if (j == 0) {
+          float a0 = -INFINITY, a1 = -INFINITY, a2 = -INFINITY, a3 = -INFINITY;
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            a0 = max3(a0, __uint_as_float(sv[0][e]), __uint_as_float(sv[0][e + 1]));
+            a1 = max3(a1, __uint_as_float(sv[1][e]), __uint_as_float(sv[1][e + 1]));
+            a2 = max3(a2, __uint_as_float(sv[2][e]), __uint_as_float(sv[2][e + 1]));
+            a3 = max3(a3, __uint_as_float(sv[3][e]), __uint_as_float(sv[3][e + 1]));
+          }
+          m_used = max3(a0, a1, fmaxf(a2, a3)) * sl2;
+        }
+        float mxa[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+        float sum0 = 0.f, sum1 = 0.f;
+        {
+          const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float s0 = __uint_as_float(sv[c][e]), s1 = __uint_as_float(sv[c][e + 1]);
+              mxa[c] = max3(mxa[c], s0, s1);
+              const float2 x = fma2(make_float2(s0, s1), sc2, nm2);
+              float p0, p1;
+              if (((e >> 1) & 3) < kPolyOf4) {
+                const float2 pp = exp2_poly2(x);
+                p0 = pp.x;
+                p1 = pp.y;
+              } else {
+                p0 = fast_exp2(x.x);
+                p1 = fast_exp2(x.y);
+              }
+              sum0 += p0;
+              sum1 += p1;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            tmem_st_32x16(tmem_s + lane_addr + c * 16, pk);
+          }
+        }
+        const float mx2 = max3(mxa[0], mxa[1], fmaxf(mxa[2], mxa[3])) * sl2;
+        const bool need = mx2 > m_used + 8.f;
+        if (__any_sync(0xffffffffu, need)) {
+          const float m_next = need ? mx2 : m_used;
+          const float alpha = need ? fast_exp2(m_used - m_next) : 1.f;
+          m_used = m_next;
+          l_run *= alpha;
+          sum0 = 0.f;
+          sum1 = 0.f;
+          const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t pk[16];
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const float2 x = fma2(make_float2(__uint_as_float(sv[c][e]), __uint_as_float(sv[c][e + 1])), sc2, nm2);
+              const float p0 = fast_exp2(x.x), p1 = fast_exp2(x.y);
+              sum0 += p0;
+              sum1 += p1;
+              __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+              pk[e >> 1] = *reinterpret_cast<uint32_t*>(&hh);
+            }
+            tmem_st_32x16(tmem_s + lane_addr + c * 16, pk);
+          }
+          if (j > 0) {
+            // PV_{j-1} of this tile retired before S_j was produced (in-order tensor pipe): O is quiescent; the
+            // epilogue warpgroup only touches O after o_full, i.e. after this item's last PV
+#pragma unroll 1
+            for (int c = 0; c < kD / 16; ++c) {
+              uint32_t tt[16];
+              tmem_ld_32x16(tmem_o + lane_addr + c * 16, tt);
+              tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 16; ++i) tt[i] = __float_as_uint(__uint_as_float(tt[i]) * alpha);
+              tmem_st_32x16(tmem_o + lane_addr + c * 16, tt);
+            }
+          }
+        }
+        l_run += sum0 + sum1;
+        if (j == n_w - 1) {
+          // row statistics for the epilogue warpgroup; the slot is free once the previous item's O_w was written back
+          if (k > 0) mbar_wait(o_free(w), (uint32_t)(k - 1) & 1u);
+          stats[w * 128 + r_local] = make_float2(l_run > 0.f ? 1.f / l_run : 0.f,
+                                                 l_run > 0.f ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (j == n_w - 1) mbar_arrive(st_full(w));
+          mbar_arrive(p_full(w));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+
+// =====================================================================================================
+// Forward v4 = v2 with TWO softmax warpgroups per Q tile (each owns 64 of the 128 key columns of a tile).
+// ncu on v2/v3: tensor pipe 41 %, MUFU 30 %, softmax warps at ~0.3 IPC -- one warp per scheduler cannot hide
+// the 4-cycle ALU / MUFU latencies of its own dependency chains, so the exponentials of a tile took
+// ~2200 cycles against 1024 cycles of MMAs.  With 16 softmax warps every scheduler interleaves four.
+// The two halves of a row agree on the reference max through shared memory (one named barrier per tile);
+// P stays in registers until they have agreed, so the rare "reference moved" path re-reads S from TMEM.
+//   warps 0-15  softmax: warpgroup g -> Q tile g>>1, column half g&1        warp 16  MMA issuer    warp 17  TMA
+// =====================================================================================================
+constexpr int kFwd4Threads = 640;
+struct Attn4Smem {
+  static constexpr int q_off = 0;
+  static constexpr int k_off = q_off + kQ2Bytes;
+  static constexpr int v_off = k_off + 2 * kKV2Bytes;
+  static constexpr int xch_off = v_off + 2 * kKV2Bytes;        // [2 tiles][2 halves][128 rows] floats
+  static constexpr int bar_off = xch_off + 2 * 2 * 128 * 4;
+  static constexpr int total = bar_off + 24 * 8;
+};
+constexpr int kAttn4SmemBytes = Attn4Smem::total + 1024;
+
+template <int kPolyOf4>
+__global__ void __launch_bounds__(kFwd4Threads, 1)
+attn_fwd4_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_q,      // box {64, 256}
+                         const __grid_constant__ CUtensorMap tma_kv,     // box {64, 128}
+                         const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t q_smem = smem_base + Attn4Smem::q_off;
+  const uint32_t k_smem = smem_base + Attn4Smem::k_off;
+  const uint32_t v_smem = smem_base + Attn4Smem::v_off;
+  volatile float* xch = reinterpret_cast<volatile float*>(smem_gen + Attn4Smem::xch_off);
+  const uint32_t bars = smem_base + Attn4Smem::bar_off;
+  const uint32_t q_full = bars;
+  auto k_full = [&](int s) { return bars + 8u * (1 + s); };
+  auto k_empty = [&](int s) { return bars + 8u * (3 + s); };
+  auto v_full = [&](int s) { return bars + 8u * (5 + s); };
+  auto v_empty = [&](int s) { return bars + 8u * (7 + s); };
+  auto s_full = [&](int w) { return bars + 8u * (9 + w); };
+  auto p_full = [&](int w) { return bars + 8u * (11 + w); };
+  auto o_full = [&](int w) { return bars + 8u * (13 + w); };
+  const uint32_t tmem_ptr_smem = bars + 8u * 16;
+  volatile uint32_t* tmem_ptr_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + Attn4Smem::bar_off + 8 * 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_tile = p.batch * p.n_heads;
+  const int pairs = p.seq / (2 * kBM);
+  const int t = pairs - 1 - (int)(blockIdx.x / per_tile);
+  const int bh = (int)(blockIdx.x % per_tile);
+  const int b = bh / p.n_heads, h = bh % p.n_heads;
+  const int hk = h / (p.n_heads / p.n_kv);
+  const int n0 = 2 * t + 1, n1 = 2 * t + 2;
+  const int row0 = b * p.seq + t * 2 * kBM;
+  const int q_col = h * kD, k_col = (p.n_heads + hk) * kD, v_col = (p.n_heads + p.n_kv + hk) * kD;
+
+  if (warp == 17 && lane == 0) {
+    tma_prefetch_desc(&tma_q);
+    tma_prefetch_desc(&tma_kv);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(k_full(s), 1); mbar_init(k_empty(s), 1);
+      mbar_init(v_full(s), 1); mbar_init(v_empty(s), 1);
+      mbar_init(s_full(s), 1); mbar_init(p_full(s), 8); mbar_init(o_full(s), 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_ptr_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  if (warp >= 16) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp == 17 && lane == 0) {
+      // ====================== TMA producer ======================
+      mbar_arrive_expect_tx(q_full, kQ2Bytes);
+      tma_load_2d(q_smem, &tma_q, q_full, q_col, row0);
+      tma_load_2d(q_smem + 2 * kAtom2, &tma_q, q_full, q_col + 64, row0);
+      for (int j = 0; j < n1; ++j) {
+        const int st = j & 1;
+        const uint32_t par = (((uint32_t)(j >> 1)) & 1u) ^ 1u;
+        const int krow = b * p.seq + j * kBN2;
+        mbar_wait(k_empty(st), par);
+        mbar_arrive_expect_tx(k_full(st), kKV2Bytes);
+        tma_load_2d(k_smem + st * kKV2Bytes, &tma_kv, k_full(st), k_col, krow);
+        tma_load_2d(k_smem + st * kKV2Bytes + kAtom2, &tma_kv, k_full(st), k_col + 64, krow);
+        mbar_wait(v_empty(st), par);
+        mbar_arrive_expect_tx(v_full(st), kKV2Bytes);
+        tma_load_2d(v_smem + st * kKV2Bytes, &tma_kv, v_full(st), v_col, krow);
+        tma_load_2d(v_smem + st * kKV2Bytes + kAtom2, &tma_kv, v_full(st), v_col + 64, krow);
+      }
+    } else if (warp == 16) {
+      // ====================== MMA issuer: the whole warp walks the loop, one elected lane issues ========================
+      const uint32_t idesc_s = umma_idesc_bf16(kBM, kBN2, 0, 0);
+      const uint32_t idesc_o = umma_idesc_bf16(kBM, kD, 0, 1);
+      const uint64_t dq0 = umma_smem_desc(q_smem, 16, 1024), dq1 = umma_smem_desc(q_smem + kAtom2, 16, 1024);
+      const uint64_t dk0 = umma_smem_desc(k_smem, 16, 1024), dv0 = umma_smem_desc(v_smem, kAtom2, 1024);
+      auto issue_s = [&](int w, int j) {
+        const uint64_t kd = dk0 + (uint64_t)((j & 1) * (kKV2Bytes >> 4));
+        const uint64_t qd = w ? dq1 : dq0;
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < kD / 16; ++kk) {
+            const uint64_t ad = qd + (uint64_t)((((kk >> 2) * (2 * kAtom2)) + (kk & 3) * 32) >> 4);
+            const uint64_t bd = kd + (uint64_t)((((kk >> 2) * kAtom2) + (kk & 3) * 32) >> 4);
+            umma_bf16_ss(tmem_base + 128u * w, ad, bd, idesc_s, kk != 0 ? 1u : 0u);
+          }
+          umma_commit(s_full(w));
+        }
+        __syncwarp();
+      };
+      auto commit = [&](uint32_t bar) {
+        if (elect_one_sync()) umma_commit(bar);
+        __syncwarp();
+      };
+      auto issue_pv = [&](int w, int j) {
+        const uint64_t vd = dv0 + (uint64_t)((j & 1) * (kKV2Bytes >> 4));
+        if (elect_one_sync()) {
+#pragma unroll
+          for (int kk = 0; kk < kBN2 / 16; ++kk) {
+            // P (bf16 pairs): keys 0..63 in S columns 0..31, keys 64..127 in S columns 64..95
+            const uint32_t a_tmem = tmem_base + 128u * w + (uint32_t)(kk >> 2) * 64u + (uint32_t)(kk & 3) * 8u;
+            umma_bf16_ts(tmem_base + 256u + 128u * w, a_tmem, vd + (uint64_t)((kk * 16 * 128) >> 4), idesc_o,
+                         (j != 0 || kk != 0) ? 1u : 0u);
+          }
+        }
+        __syncwarp();
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(k_full(0), 0);
+      tc_fence_after();
+      issue_s(0, 0);
+      issue_s(1, 0);
+      commit(k_empty(0));
+      for (int j = 0; j < n1; ++j) {
+        const int st = j & 1, nst = (j + 1) & 1;
+        mbar_wait(v_full(st), (uint32_t)(j >> 1) & 1u);
+        if (j < n0) {
+          mbar_wait(p_full(0), (uint32_t)j & 1u);
+          tc_fence_after();
+          issue_pv(0, j);
+          if (j == n0 - 1) commit(o_full(0));
+        }
+        if (j + 1 < n0) {
+          mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
+          tc_fence_after();
+          issue_s(0, j + 1);
+        }
+        mbar_wait(p_full(1), (uint32_t)j & 1u);
+        tc_fence_after();
+        issue_pv(1, j);
+        commit(v_empty(st));
+        if (j == n1 - 1) commit(o_full(1));
+        if (j + 1 < n1) {
+          mbar_wait(k_full(nst), (uint32_t)((j + 1) >> 1) & 1u);
+          tc_fence_after();
+          issue_s(1, j + 1);
+          commit(k_empty(nst));
+        }
+      }
+    }
+  } else {
+    // ====================== softmax warpgroups: g -> (tile w, column half hf) ==========
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+    const int g = warp >> 2;
+    const int w = g >> 1, hf = g & 1;
+    const int q4 = warp & 3;
+    const int r_local = q4 * 32 + lane;
+    const int q_pos = t * 2 * kBM + w * kBM + r_local;
+    const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tmem_s = tmem_base + 128u * w + 64u * hf;        // this half's 64 S columns (and its P, 32 columns)
+    const uint32_t tmem_o = tmem_base + 256u + 128u * w + 64u * hf; // this half's 64 O columns
+    volatile float* x_mine = xch + (w * 2 + hf) * 128 + r_local;
+    volatile float* x_other = xch + (w * 2 + (hf ^ 1)) * 128 + r_local;
+    const int bar_id = 1 + w;                                        // named barrier of the two halves of tile w
+    const int n_w = w == 0 ? n0 : n1;
+    const float sl2 = p.scale_log2;
+    float m_used = -INFINITY, l_part = 0.f;
+    for (int j = 0; j < n_w; ++j) {
+      mbar_wait(s_full(w), (uint32_t)j & 1u);
+      tc_fence_after();
+      const bool diag = j == n_w - 1;
+      uint32_t pk[32];
+      float mloc = -INFINITY, sum0 = 0.f, sum1 = 0.f;
+      if (j == 0) {
+        // first tile: the reference is the true row max of this tile -> agree on it before any exponential
+        float a0 = -INFINITY, a1 = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float s0 = __uint_as_float(sv[e]), s1 = __uint_as_float(sv[e + 1]);
+            if (diag && hf * 64 + c * 32 + e > r_local) s0 = -INFINITY;
+            if (diag && hf * 64 + c * 32 + e + 1 > r_local) s1 = -INFINITY;
+            if (c == 0) a0 = max3(a0, s0, s1); else a1 = max3(a1, s0, s1);
+          }
+        }
+        *x_mine = fmaxf(a0, a1);
+        named_bar_sync(bar_id, 256);
+        m_used = fmaxf(fmaxf(a0, a1), *x_other) * sl2;
+        named_bar_sync(bar_id, 256);                                 // the slot is rewritten below
+      }
+      {
+        const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float s0 = __uint_as_float(sv[e]), s1 = __uint_as_float(sv[e + 1]);
+            if (diag && hf * 64 + c * 32 + e > r_local) s0 = -INFINITY;
+            if (diag && hf * 64 + c * 32 + e + 1 > r_local) s1 = -INFINITY;
+            mloc = max3(mloc, s0, s1);
+            const float2 x = fma2(make_float2(s0, s1), sc2, nm2);
+            float p0, p1;
+            if (((e >> 1) & 3) < kPolyOf4) {
+              const float2 pp = exp2_poly2(x);
+              p0 = pp.x;
+              p1 = pp.y;
+            } else {
+              p0 = fast_exp2(x.x);
+              p1 = fast_exp2(x.y);
+            }
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            pk[c * 16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        }
+      }
+      // agree with the other half of the row on whether the reference max has to move (> 2^8 growth)
+      *x_mine = mloc;
+      named_bar_sync(bar_id, 256);
+      const float mx2 = fmaxf(mloc, *x_other) * sl2;
+      const bool need = mx2 > m_used + 8.f;
+      const bool slow = __any_sync(0xffffffffu, need);               // same rows in both halves -> same decision
+      if (slow) {
+        const float m_next = need ? mx2 : m_used;
+        const float alpha = need ? fast_exp2(m_used - m_next) : 1.f;
+        m_used = m_next;
+        l_part *= alpha;
+        sum0 = 0.f;
+        sum1 = 0.f;
+        const float2 sc2 = make_float2(sl2, sl2), nm2 = make_float2(-m_used, -m_used);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_s + lane_addr + c * 32, sv);            // S is still intact: P has not been stored yet
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float s0 = __uint_as_float(sv[e]), s1 = __uint_as_float(sv[e + 1]);
+            if (diag && hf * 64 + c * 32 + e > r_local) s0 = -INFINITY;
+            if (diag && hf * 64 + c * 32 + e + 1 > r_local) s1 = -INFINITY;
+            const float2 x = fma2(make_float2(s0, s1), sc2, nm2);
+            const float p0 = fast_exp2(x.x), p1 = fast_exp2(x.y);
+            sum0 += p0;
+            sum1 += p1;
+            __nv_bfloat162 hh = __floats2bfloat162_rn(p0, p1);
+            pk[c * 16 + (e >> 1)] = *reinterpret_cast<uint32_t*>(&hh);
+          }
+        }
+        if (j > 0) {
+          // PV_{j-1} of this tile retired before S_j was produced (in-order tensor pipe): O is quiescent.
+          // Each half rescales its own 64 of the 128 O columns.
+#pragma unroll 1
+          for (int c = 0; c < 4; ++c) {
+            uint32_t tt[16];
+            tmem_ld_32x16(tmem_o + lane_addr + c * 16, tt);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) tt[i] = __float_as_uint(__uint_as_float(tt[i]) * alpha);
+            tmem_st_32x16(tmem_o + lane_addr + c * 16, tt);
+          }
+        }
+      }
+      l_part += sum0 + sum1;
+      named_bar_sync(bar_id, 256);          // both halves have read the exchange slots (and all S reads of the tile are done)
+      {
+        uint32_t lo[16], hi[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { lo[i] = pk[i]; hi[i] = pk[16 + i]; }
+        tmem_st_32x16(tmem_s + lane_addr, lo);
+        tmem_st_32x16(tmem_s + lane_addr + 16, hi);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_full(w));
+    }
+    // ---- epilogue: total row sum = both halves; each half normalises and stores its 64 O columns ----
+    *x_mine = l_part;
+    named_bar_sync(bar_id, 256);
+    const float l_run = l_part + *x_other;
+    mbar_wait(o_full(w), 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    bf16* orow = p.out + (size_t)(row0 + w * kBM + r_local) * p.out_stride + h * kD + hf * 64;
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      uint32_t tt[32];
+      tmem_ld_32x32(tmem_o + lane_addr + c * 32, tt);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 32; e += 8) {
+        float f[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(tt[e + i]) * inv;
+        st_bf16x8(orow + c * 32 + e, pack8(f));
+      }
+    }
+    if (hf == 0)
+      p.lse[((size_t)b * p.n_heads + h) * p.seq + q_pos] =
+          (l_run > 0.f) ? (m_used + log2f(l_run)) * 0.6931471805599453f : -INFINITY;
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_enc = nullptr;
 std::once_flag g_attn_once;
 int g_fwd_poly = 1;          // exponentials evaluated on the FMA pipe: this many of every 4 pairs (0, 1 or 2)
-int g_fwd_version = 2;       // 2 = two Q tiles per CTA, 128-key tiles (default); 1 = one Q tile, 64-key tiles
+int g_fwd_version = 2;       // 2 = two Q tiles per CTA, one softmax warpgroup per tile (default: fastest measured);
+                             // 3 = 2 made persistent with an epilogue warpgroup; 4 = 2 with two softmax warpgroups per tile;
+                             // 1 = one Q tile per CTA, 64-key tiles, two CTAs per SM
 std::string g_attn_err;
 
 void attn_init() {
@@ -645,6 +1352,12 @@ void attn_init() {
       q == cudaDriverEntryPointSuccess)
     g_enc = reinterpret_cast<EncodeTiledFn>(fn);
   cudaFuncSetAttribute(attn_fwd_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmemBytes);
+  cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
+  cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
+  cudaFuncSetAttribute(attn_fwd4_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn4SmemBytes);
+  cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+  cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
+  cudaFuncSetAttribute(attn_fwd3_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn3SmemBytes);
   cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
   cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
   cudaFuncSetAttribute(attn_fwd2_tcgen05_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttn2SmemBytes);
@@ -662,7 +1375,7 @@ bool attn_tmap(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, ui
 }  // namespace
 
 const char* attention_last_error() { return g_attn_err.c_str(); }
-void attention_fwd_set_version(int v) { g_fwd_version = (v == 1) ? 1 : 2; }
+void attention_fwd_set_version(int v) { g_fwd_version = (v >= 1 && v <= 4) ? v : 2; }
 int attention_fwd_get_version() { return g_fwd_version; }
 void attention_fwd_set_poly(int n) { g_fwd_poly = n < 0 ? 0 : (n > 2 ? 2 : n); }
 
@@ -687,14 +1400,23 @@ int attention_fwd_tcgen05(const bf16* qkv, bf16* out, float* lse, int batch, int
   p.out_stride = out_stride;
   p.scale_log2 = scale * 1.4426950408889634f;
   p.out = out; p.lse = lse;
-  if (g_fwd_version == 2 && seq % (2 * kBM) == 0) {
+  if (g_fwd_version >= 2 && seq % (2 * kBM) == 0) {
     CUtensorMap tq2, tkv2;
     if (!attn_tmap(&tq2, qkv, cols, rows, qkv_stride, 2 * kBM) || !attn_tmap(&tkv2, qkv, cols, rows, qkv_stride, kBN2)) {
       g_attn_err = "cuTensorMapEncodeTiled failed";
       return 3;
     }
     const int grid2 = (seq / (2 * kBM)) * batch * n_heads;
-    if (g_fwd_poly == 0) attn_fwd2_tcgen05_kernel<0><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
+    if (g_fwd_version == 4) {
+      if (g_fwd_poly == 0) attn_fwd4_tcgen05_kernel<0><<<grid2, kFwd4Threads, kAttn4SmemBytes, s>>>(tq2, tkv2, p);
+      else if (g_fwd_poly == 1) attn_fwd4_tcgen05_kernel<1><<<grid2, kFwd4Threads, kAttn4SmemBytes, s>>>(tq2, tkv2, p);
+      else attn_fwd4_tcgen05_kernel<2><<<grid2, kFwd4Threads, kAttn4SmemBytes, s>>>(tq2, tkv2, p);
+    } else if (g_fwd_version == 3) {
+      const int grid3 = grid2 < kNumSMs ? grid2 : kNumSMs;
+      if (g_fwd_poly == 0) attn_fwd3_tcgen05_kernel<0><<<grid3, kFwd3Threads, kAttn3SmemBytes, s>>>(tq2, tkv2, p);
+      else if (g_fwd_poly == 1) attn_fwd3_tcgen05_kernel<1><<<grid3, kFwd3Threads, kAttn3SmemBytes, s>>>(tq2, tkv2, p);
+      else attn_fwd3_tcgen05_kernel<2><<<grid3, kFwd3Threads, kAttn3SmemBytes, s>>>(tq2, tkv2, p);
+    } else if (g_fwd_poly == 0) attn_fwd2_tcgen05_kernel<0><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
     else if (g_fwd_poly == 1) attn_fwd2_tcgen05_kernel<1><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
     else attn_fwd2_tcgen05_kernel<2><<<grid2, kFwd2Threads, kAttn2SmemBytes, s>>>(tq2, tkv2, p);
   } else {

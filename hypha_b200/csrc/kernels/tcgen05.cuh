@@ -41,6 +41,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp.  tcgen05.mma / tcgen05.commit / TMA are uniform-datapath instructions: issued
+// under `if (elect_one_sync())` inside warp-uniform control flow they compile to one predicated instruction;
+// issued from a `lane == 0` branch the compiler wraps every one of them in an ELECT / BRA.U.ANY waterfall loop
+// (ncu on the attention kernels: the issuing thread spent 63 % of its time in those loops).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- proxies / fences ----------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -677,7 +677,8 @@ def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: in
 
 def set_attention_fwd_version(version: int) -> None:
     """2 (default) = two 128-row Q tiles per CTA ping-ponging on one MMA issuer, 128-key tiles (needs
-    seq % 256 == 0, else version 1 runs); 1 = one Q tile per CTA, 64-key tiles, two CTAs per SM."""
+    seq % 256 == 0, else version 1 runs); 3 = the same kernel made persistent with a separate epilogue
+    warpgroup; 4 = two softmax warpgroups per Q tile; 1 = one Q tile per CTA, 64-key tiles, two CTAs per SM."""
     load_C().attention_fwd_set_version(int(version))
 
 
