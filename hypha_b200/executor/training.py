@@ -668,7 +668,8 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
         if steps > 0:                              # a rank that joined at this barrier has nothing to report yet
             session.send_status({"metrics": {"round": round_no, "metrics": {
                 "loss": mean_loss, "samples_or_tokens_per_s": tokens / max(inner_s, 1e-9),
-                "inner_step_ms": inner_s * 1e3 / max(1, steps), "outer_step_ms": outer_ms}}})
+                "inner_step_ms": inner_s * 1e3 / max(1, steps), "outer_step_ms": outer_ms,
+                "inner_steps": float(steps), "tokens": float(tokens)}}})
         print(f"round {round_no}: {steps} inner steps, mean loss {mean_loss:.4f}, {inner_s * 1e3 / max(1, steps):.1f} ms/step; "
               f"outer step done in {outer_ms:.1f} ms", flush=True)
         # what the aggregate worker reports in parameter-server mode.  Every rank sends it (the scheduler

@@ -333,8 +333,41 @@ class DiLoCoOuter:
                 theta = self.anchor_buf.local[b:b + l].float()
                 self.segments[k] = (b, l, theta, torch.zeros_like(theta))
 
-    def readmit(self, rank: int) -> None:
-        """A (re)joined rank takes its shard back at a round boundary."""
+    def handback(self, exchange, ranks: List[int]) -> None:
+        """Owners take their outer state back (collective over every rank of the new membership, returning /
+        joining ranks included; ``exchange`` = a control-plane all-gather that reaches all of them).  For each
+        rank in ``ranks`` whose shard somebody else has been running, the holder stages its fp32 theta_outer
+        segment, then its momentum segment, in its copy of the symmetric delta buffer (free at a round boundary:
+        it aliases the gradient buffer) and the owner pulls them over NVLink with the same peer-memory copy
+        kernel that re-seeds the parameters.  Nothing is re-derived from bf16 and no momentum is reset: the
+        shard continues exactly where the holder left it."""
+        own = self.owners()
+        as_f32 = self.delta_buf.local.view(torch.float32)
+        for r in sorted(int(x) for x in ranks):
+            holder = own.get(r, r)
+            if holder == r:
+                continue
+            b, l = shard_bounds(self.n, self.world, r)
+            assert l <= as_f32.numel(), "shard does not fit the staging buffer"
+            for which in (2, 3):                              # segment tuple index: theta_outer, momentum
+                if self.rank == holder:
+                    as_f32[:l].copy_(self.segments[r][which])
+                    torch.cuda.synchronize()
+                exchange(("staged", r, which))
+                if self.rank == r:
+                    dst = self.theta_outer if which == 2 else self.momentum
+                    load_C().peer_pull_copy(self.delta_buf.peer_ptrs[holder], dst.data_ptr(), 4 * l, 0, cuda_stream())
+                    torch.cuda.synchronize()
+                    self.group.counters.add("/hypha-peer-memory/handback", inbound=4 * l)
+                exchange(("pulled", r, which))
+
+    def readmit(self, rank: int, handback: bool = True) -> None:
+        """A (re)joined rank takes its shard back at a round boundary (collective: every rank of the new
+        membership calls it).  With ``handback`` the holder's fp32 theta_outer / momentum of that shard travel
+        back to the owner first (`handback`); the segment is dropped by the holder afterwards."""
+        if handback and self.backend == "fused" and self.group is not None and self.group._exchange is not None \
+                and self.owners().get(rank, rank) != rank:
+            self.handback(self.group._exchange, [rank])
         if rank != self.rank:
             self.segments.pop(rank, None)
         self.owners()[rank] = rank
@@ -357,25 +390,28 @@ class DiLoCoOuter:
         new = sorted(int(r) for r in new)
         survivors = [r for r in order if r not in new]
         self.group.rebind(exchange, new, members=order)
-        if joining:
-            self.set_members(order)
-        else:
-            for r in new:
-                self.readmit(r)
         self.round = max(int(r) for r in exchange(int(self.round)))
         maps = exchange(None if joining else dict(self.owners()))       # who runs which dead rank's shard
         if joining:
-            self._owner = dict(next(m for m in maps if m is not None))
-            self._owner[self.rank] = self.rank
-        self.sync_epoch()
-        if joining:
-            self.reseed_from(survivors[0])
+            self._owner = {int(k): int(v) for k, v in next(m for m in maps if m is not None).items()}
+            self.reseed_from(survivors[0])      # parameters over NVLink; theta_outer / momentum placeholders
             torch.cuda.synchronize()
+        self.handback(exchange, new)            # the holders' fp32 theta_outer + momentum go to the newcomers
+        if joining:
+            self._owner[self.rank] = self.rank
+            self.set_members(order)
+        else:
+            for r in new:
+                self.readmit(r, handback=False)
+        self.sync_epoch()
         exchange("ready")
 
     def reseed_from(self, src_rank: int) -> None:
-        """(Re)join: pull the current global weights from a live rank over peer memory and rebuild
-        every piece of local state that derives from them."""
+        """(Re)join: pull the current global weights from a live rank over peer memory and rebuild the local
+        state that derives from them.  theta_outer / momentum of the own shard are only
+        placeholders here (theta from the pulled weights, momentum zero): `readmit` / `admit` replace them with
+        the holder's exact fp32 state (`handback`) whenever somebody kept the shard going.  The inner AdamW
+        moments are left alone: a returning rank keeps its own, a new process starts from zero anyway."""
         self.group.pull(src_rank, self.param_buf.name)
         C = load_C()
         C.bf16_to_master(self.opt.params.data_ptr(), self.opt.master.data_ptr(), self.n, cuda_stream())
@@ -383,8 +419,6 @@ class DiLoCoOuter:
         sl = slice(self.shard_begin, self.shard_begin + self.shard_len)
         self.theta_outer.copy_(self.opt.master[sl])
         self.momentum.zero_()
-        self.opt.m.zero_()
-        self.opt.v.zero_()
 
     def step_resilient(self, max_retries: int = 2) -> tuple:
         """``step()`` that survives ranks that never show up: on a barrier-1 timeout the missing

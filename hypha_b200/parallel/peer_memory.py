@@ -61,18 +61,43 @@ def store_exchange(store, rank: int, world: int, prefix: str = "hb-xchg", timeou
     ``set`` / ``get`` / ``wait``): needs no process group, so a membership generation that contains a
     replacement PROCESS can use it (a torch process group cannot admit one).  Every call of the returned
     function is one round; all ``world`` ranks must make the same sequence of calls."""
-    import pickle
+    import base64
+    import json
     from datetime import timedelta
 
     seq = [0]
 
+    def enc(o):
+        # JSON with two tagged extensions (bytes for IPC handles, int-keyed dicts for owner maps): values read
+        # from the store are never unpickled (the TCPStore is unauthenticated)
+        if isinstance(o, (bytes, bytearray)):
+            return {"__b64__": base64.b64encode(bytes(o)).decode()}
+        if isinstance(o, dict):
+            if all(isinstance(k, str) for k in o):
+                return {k: enc(v) for k, v in o.items()}
+            return {"__items__": [[enc(k), enc(v)] for k, v in o.items()]}
+        if isinstance(o, (list, tuple)):
+            return [enc(v) for v in o]
+        return o
+
+    def dec(o):
+        if isinstance(o, dict):
+            if "__b64__" in o and len(o) == 1:
+                return base64.b64decode(o["__b64__"])
+            if "__items__" in o and len(o) == 1:
+                return {(tuple(k) if isinstance(k, list) else k): v for k, v in ((dec(a), dec(b)) for a, b in o["__items__"])}
+            return {k: dec(v) for k, v in o.items()}
+        if isinstance(o, list):
+            return [dec(v) for v in o]
+        return o
+
     def exchange(obj):
         n = seq[0]
         seq[0] += 1
-        store.set(f"{prefix}/{n}/{rank}", pickle.dumps(obj))
+        store.set(f"{prefix}/{n}/{rank}", json.dumps(enc(obj)))
         keys = [f"{prefix}/{n}/{r}" for r in range(world)]
         store.wait(keys, timedelta(seconds=timeout_s))
-        return [pickle.loads(store.get(k)) for k in keys]
+        return [dec(json.loads(store.get(k))) for k in keys]
 
     return exchange
 

@@ -92,8 +92,23 @@ def main():
         outer.reseed_from(0)
         torch.cuda.synchronize()
     dist.barrier()
+    # the holder of the dead rank's shard kept its fp32 theta_outer / momentum going for two rounds: `readmit`
+    # must hand exactly that state back (no re-derivation from bf16, no momentum reset)
+    held = None
+    if rank != dead and dead in outer.segments:
+        _, _, th, mo = outer.segments[dead]
+        torch.cuda.synchronize()
+        held = (float(th.double().sum().item()), float(mo.double().sum().item()), float(mo.abs().max().item()))
     outer.readmit(dead)
     outer.sync_epoch()
+    torch.cuda.synchronize()
+    mine = (float(outer.theta_outer.double().sum().item()), float(outer.momentum.double().sum().item()),
+            float(outer.momentum.abs().max().item())) if rank == dead else None
+    helds, mines = gather(held, world), gather(mine, world)
+    want = [h for h in helds if h is not None]
+    assert len(want) == 1 and want[0] == mines[dead], ("hand-back mismatch", want, mines[dead])
+    assert want[0][2] > 0.0, "the adopted shard's momentum should be non-zero after two survivor rounds"
+    log.append("hand-back of theta_outer + momentum to the returning owner ok")
     fps = gather(fingerprint(), world)
     assert all(f == fps[0] for f in fps), ("after rejoin", fps)
     assert outer.members() == list(range(world)) and (rank == dead or dead not in outer.segments)
@@ -108,6 +123,8 @@ def main():
     pulled = grp.counters.snapshot()["hypha.bandwidth.inbound.bytes"].get("/hypha-peer-memory/pull", 0)
     if rank == dead:
         assert pulled == 2 * n
+        hb = grp.counters.snapshot()["hypha.bandwidth.inbound.bytes"].get("/hypha-peer-memory/handback", 0)
+        assert hb == 2 * 4 * outer.shard_len, hb
     if rank == 0:
         print(json.dumps({"world": world, "steps": log, "correct": True}), flush=True)
     dist.barrier()

@@ -232,7 +232,7 @@ def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
     C, world, dead = fake, 4, 2
     groups = _group_of(world, C, SHAPES)
     peers = ["w0", "w1", "w2", "w3"]
-    reseeded = []
+    reseeded, handed = [], []
 
     def make_outer(group, rank, round_no, attempt, members):
         o = object.__new__(DiLoCoOuter)
@@ -240,6 +240,9 @@ def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
         o.n, o.segments = 4096 * world, {rank: ("own",)}
         o.set_members(members)
         o.reseed_from = lambda src, r=rank: reseeded.append((r, src))
+        # the state hand-back itself moves device memory (tests/mgpu_fault_check.py runs it on GPUs); here only
+        # that every rank of the new generation enters it for the newcomer, after the owner map is known
+        o.handback = lambda ex, ranks, r=rank: handed.append((r, list(ranks), dict(o.owners()).get(dead)))
         return o
 
     def make_engine(outer, joining, me):
@@ -252,6 +255,7 @@ def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
     engines = {}
     for r in (0, 1, 3):
         o = make_outer(groups[r], r, round_no=5, attempt=17 + r, members=[0, 1, 3])
+        o._owner = {0: 0, 1: 1, 2: 3, 3: 3}          # what `drop_ranks([2])` left behind on every survivor
         if r == 3:
             o.segments[dead] = ("adopted",)
         engines[r] = make_engine(o, False, peers[r])
@@ -282,6 +286,7 @@ def test_trainer_engine_admits_a_replacement_process(fake, monkeypatch):
     res = _in_threads([lambda r=r: run(r) for r in (0, 1, 2, 3)])
     assert res == [True] * 4, res
     assert sorted(stepped) == [0, 1, 3] and reseeded == [(dead, 0)]
+    assert sorted(handed) == [(r, [dead], 3) for r in range(4)], handed     # everyone, holder = rank 3
     members = {0: groups[0], 1: groups[1], 2: new_group, 3: groups[3]}
     for r, e in engines.items():
         o = e.trainer.outer
