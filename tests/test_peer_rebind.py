@@ -352,7 +352,7 @@ def test_outer_membership_bookkeeping_on_cpu():
     live = [1, 2, 4]
     for r in live:
         outers[r].set_members([1, 2] if r != 4 else live)
-        outers[r].readmit(4)
+        outers[r].readmit(4, handback=False)        # bookkeeping only: no device, no control plane here
     exactly_one_live_owner()
     assert sorted(outers[1].segments) == [0, 1, 3] and sorted(outers[4].segments) == [4]
     # a later failure must not hand shard 3 to a second owner (its cyclic successor 4 is alive again)
