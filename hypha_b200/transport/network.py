@@ -37,6 +37,9 @@ from ..telemetry.bandwidth import BandwidthCounters
 
 MAX_FRAME = 64 << 20
 STREAM_CHUNK = 1 << 20
+STREAM_WINDOW = 64               # chunks a stream's sender may have in flight (credit-based flow control)
+STREAM_CREDIT_BATCH = 16         # the receiver returns credits in batches of this many consumed chunks
+STREAM_CREDIT_TIMEOUT_S = 120.0  # a sender whose receiver stopped reading gives up after this long
 SPLIT_BIT = 1 << 31              # length-prefix flag of a bulk stream_data frame (raw payload after a CBOR header)
 SPLIT_FRAME_MIN = 4096
 STREAM_ACCEPT_LIMIT = 8          # stream_push.rs:56, stream_pull.rs:71
@@ -237,6 +240,19 @@ class SocketLink(Link):
         self.proto = proto
         self._wlock = asyncio.Lock()
 
+    def cert_peer_id(self) -> Optional[str]:
+        """The peer id the TLS peer certificate entitles the other side to (None on links without TLS)."""
+        tr = self.proto.transport
+        obj = tr.get_extra_info("ssl_object") if tr is not None else None
+        if obj is None:
+            return None
+        der = obj.getpeercert(binary_form=True)
+        if not der:
+            return None
+        from .utils import peer_id_from_cert_der
+
+        return peer_id_from_cert_der(der)
+
     async def send(self, frame: dict) -> int:
         if self.closed:
             raise NetworkError("link closed")
@@ -318,6 +334,8 @@ class IncomingStream:
     job_id: Optional[str]
     queue: "asyncio.Queue[Optional[bytes]]"
     error: Optional[str] = None          # set when the stream ended without its sender's regular close
+    on_consumed: Optional[Callable[[int], None]] = None   # returns credits to the sender (set by the Network)
+    _consumed: int = 0
 
     def abort(self, why: str) -> None:
         """The sender is gone (link dropped) or reported a failure: the consumer must not mistake what arrived
@@ -337,7 +355,19 @@ class IncomingStream:
                 if self.error is not None:
                     raise StreamAborted(self.error)
                 return
+            self._consumed += 1
+            if self.on_consumed is not None and self._consumed % STREAM_CREDIT_BATCH == 0:
+                self.on_consumed(STREAM_CREDIT_BATCH)          # the sender may put that many more chunks in flight
             yield c
+
+    def discard(self) -> None:
+        """The consumer does not want this stream (sender not on the allow-list, job gone): stop accounting
+        for it.  Its sender runs out of credit after STREAM_WINDOW chunks and gives up; nothing it sends
+        blocks the link it shares with other traffic."""
+        self.error = self.error or "discarded by the receiver"
+        self.on_consumed = None
+        while not self.queue.empty():
+            self.queue.get_nowait()
 
     async def read_all(self) -> bytes:
         return b"".join([c async for c in self.chunks()])
@@ -369,6 +399,7 @@ class Network:
         self.relay_server = relay_server
         self.dht_server = dht_server
         self.links: Dict[str, Link] = {}
+        self.identity_rejections = 0      # hellos / relayed frames / records refused because the claimed id was not the sender's
         self.peer_addrs: Dict[str, List[str]] = {}
         self.listen_addrs: List[str] = []
         self.external_addrs: List[str] = []
@@ -376,6 +407,7 @@ class Network:
         self._handlers: Dict[str, List[HandlerRegistration]] = {}
         self._hid = itertools.count(1)
         self._pending: Dict[str, asyncio.Future] = {}
+        self._stream_credits: Dict[str, asyncio.Semaphore] = {}     # sid -> chunks this node may still send
         self._subs: Dict[str, List[asyncio.Queue]] = {}
         self._peer_topics: Dict[str, Set[str]] = {}
         self._seen_msgs: Dict[str, float] = {}
@@ -592,6 +624,20 @@ class Network:
         self.counters.add(frame.get("proto") or f"/hypha-frame/{t}", inbound=size)
         if t == "hello":
             peer = frame["peer"]
+            # identity is bound to the mTLS certificate: a CA-issued certificate only entitles its holder to the
+            # peer id of ITS key; a hello that claims anything else ends the link (lease owner checks, push-stream
+            # allow-lists and job membership all rest on link.peer_id)
+            entitled = link.cert_peer_id() if hasattr(link, "cert_peer_id") else None
+            if entitled is not None and peer != entitled:
+                self.identity_rejections += 1
+                fut = getattr(link, "_hello_fut", None)
+                if fut is not None and not fut.done():
+                    fut.set_exception(DialError(f"peer claims id {peer!r} but its certificate is {entitled!r}"))
+                await self._drop_link(link)
+                return
+            if link.peer_id is not None and peer != link.peer_id:
+                await self._drop_link(link)           # an established link never changes its identity
+                return
             first = link.peer_id is None
             link.peer_id = peer
             link.is_relay = bool(frame.get("relay"))  # type: ignore[attr-defined]
@@ -614,10 +660,15 @@ class Network:
         elif t == "relay":
             dst = frame["dst"]
             if dst == self.peer_id:
-                await self._on_frame(frame["inner"], link, frame["src"], size)
-            elif self.relay_server and dst in self.links:
-                await self._send(self.links[dst], frame, "/hypha-relay")
-            # else: drop (no route)
+                # only a relay server may speak for somebody else, and what it vouches for is the id it
+                # authenticated on ITS link (it overwrites `src` below); anything else is dropped
+                if getattr(link, "is_relay", False) and link.peer_id is not None:
+                    await self._on_frame(frame["inner"], link, frame["src"], size)
+                else:
+                    self.identity_rejections += 1
+            elif self.relay_server and dst in self.links and link.peer_id is not None:
+                await self._send(self.links[dst], dict(frame, src=link.peer_id), "/hypha-relay")
+            # else: drop (no route / unidentified sender)
         elif t == "req":
             self._spawn(self._serve_request(src, frame))
         elif t == "resp":
@@ -635,22 +686,43 @@ class Network:
         elif t == "pub":
             await self._on_publish(frame, src)
         elif t == "dht_put":
-            self._records[frame["key"]] = (frame["value"], frame["publisher"])
+            if frame["publisher"] == src:            # a record is published under the sender's own id only
+                self._records[frame["key"]] = (frame["value"], frame["publisher"])
+            else:
+                self.identity_rejections += 1
         elif t == "dht_provide":
-            self._providers.setdefault(frame["key"], set()).add(frame["provider"])
+            if frame["provider"] == src:
+                self._providers.setdefault(frame["key"], set()).add(frame["provider"])
+            else:
+                self.identity_rejections += 1
         elif t == "stream_open":
             await self._on_stream_open(src, frame)
         elif t == "stream_data":
             st = self._streams.get(frame["sid"])
-            if st is not None:
-                await st.queue.put(frame["data"])
+            if st is not None and st.error is None:
+                # the sender holds a credit for every chunk in flight, so the queue has room: the link's
+                # read loop never waits on one stream's consumer (RPC responses, pings and the other streams of
+                # this link keep flowing).  A sender that ignores its credits is cut off.
+                try:
+                    st.queue.put_nowait(frame["data"])
+                except asyncio.QueueFull:
+                    self._streams.pop(frame["sid"], None)
+                    st.abort(f"{st.peer} sent more than its flow-control window")
+        elif t == "stream_credit":
+            sem = self._stream_credits.get(frame["sid"])
+            if sem is not None:
+                for _ in range(min(int(frame.get("n", 0)), STREAM_WINDOW)):
+                    sem.release()
         elif t == "stream_close":
             st = self._streams.pop(frame["sid"], None)
             if st is not None:
                 if frame.get("error"):
                     st.abort(f"{st.peer} could not serve the stream: {frame['error']}")
                 else:
-                    await st.queue.put(None)
+                    try:
+                        st.queue.put_nowait(None)
+                    except asyncio.QueueFull:
+                        st.abort(f"{st.peer} closed a stream it had overfilled")
         elif t == "ping":
             await self._send_to(src, {"t": "pong", "id": frame["id"]}, "/ipfs/ping/1.0.0")
         elif t == "pong":
@@ -883,11 +955,33 @@ class Network:
             raise AlreadyRegistered("pull stream sender already registered")
         self._pull_handlers["/hypha-tensor-stream/pull"] = handler
 
+    def _wire_credits(self, st: IncomingStream, sid: str, proto: str) -> None:
+        """Receiver side of the flow control: consumed chunks are acknowledged to the sender in batches."""
+        def grant(n: int, peer=st.peer) -> None:
+            async def send():
+                try:
+                    await self._send_to(peer, {"t": "stream_credit", "sid": sid, "n": n, "proto": proto}, proto)
+                except NetworkError:
+                    pass
+            self._spawn(send())
+        st.on_consumed = grant
+
+    async def _send_chunk(self, peer: str, sid: str, proto: str, data: bytes) -> None:
+        """One chunk of an outgoing stream, after taking a credit (at most STREAM_WINDOW chunks in flight)."""
+        sem = self._stream_credits.get(sid)
+        if sem is not None:
+            try:
+                await asyncio.wait_for(sem.acquire(), STREAM_CREDIT_TIMEOUT_S)
+            except asyncio.TimeoutError as exc:
+                raise NetworkError(f"{peer} stopped reading stream {sid[:8]}") from exc
+        await self._send_to(peer, {"t": "stream_data", "sid": sid, "data": data, "proto": proto}, proto)
+
     async def _on_stream_open(self, src: str, frame: dict) -> None:
         proto, sid = frame["proto"], frame["sid"]
         if proto == "/hypha-tensor-stream/push":
             q = self._stream_rx.get((proto, frame.get("job"))) or self._stream_rx.get((proto, None))
-            st = IncomingStream(src, proto, frame.get("header"), frame.get("job"), asyncio.Queue(64))
+            st = IncomingStream(src, proto, frame.get("header"), frame.get("job"), asyncio.Queue(STREAM_WINDOW + 1))
+            self._wire_credits(st, sid, proto)
             self._streams[sid] = st
             if q is None:
                 # nobody listens yet: park the stream for a receiver that registers shortly (bounded: a
@@ -901,34 +995,40 @@ class Network:
                 parked.append((now, st))
                 self._early_streams[key] = parked
                 return
-            await q.put(st)
+            try:
+                q.put_nowait(st)                           # never wait here: this is the link's read loop
+            except asyncio.QueueFull:                      # more than STREAM_ACCEPT_LIMIT unaccepted streams
+                self._streams.pop(sid, None)
+                st.discard()
         elif proto == "/hypha-tensor-stream/pull":
             handler = self._pull_handlers.get(proto)
             self._spawn(self._serve_pull(src, sid, frame.get("header"), handler))
 
     async def _serve_pull(self, src: str, sid: str, header: Any, handler) -> None:
         proto = "/hypha-tensor-stream/pull"
+        self._stream_credits[sid] = asyncio.Semaphore(STREAM_WINDOW)
         try:
             if handler is None:
                 raise NetworkError("no pull handler")
             res = await handler(src, header)
             if isinstance(res, (bytes, bytearray)):
                 for i in range(0, len(res), STREAM_CHUNK):
-                    await self._send_to(src, {"t": "stream_data", "sid": sid, "data": bytes(res[i:i + STREAM_CHUNK]),
-                                              "proto": proto}, proto)
+                    await self._send_chunk(src, sid, proto, bytes(res[i:i + STREAM_CHUNK]))
             else:
                 with open(res, "rb") as f:
                     while True:
                         c = f.read(STREAM_CHUNK)
                         if not c:
                             break
-                        await self._send_to(src, {"t": "stream_data", "sid": sid, "data": c, "proto": proto}, proto)
+                        await self._send_chunk(src, sid, proto, c)
             await self._send_to(src, {"t": "stream_close", "sid": sid, "proto": proto}, proto)
         except Exception as exc:
             try:
                 await self._send_to(src, {"t": "stream_close", "sid": sid, "error": str(exc), "proto": proto}, proto)
             except NetworkError:
                 pass
+        finally:
+            self._stream_credits.pop(sid, None)
 
     async def stream_push(self, peer: str, source, job_id: Optional[str] = None, header: Any = None) -> int:
         """Push ``source`` (bytes or a file path) to ``peer``; returns bytes sent."""
@@ -937,20 +1037,24 @@ class Network:
         await self._send_to(peer, {"t": "stream_open", "sid": sid, "proto": proto, "job": job_id, "header": header},
                             proto)
         n = 0
-        if isinstance(source, (bytes, bytearray)):
-            for i in range(0, len(source), STREAM_CHUNK):
-                c = bytes(source[i:i + STREAM_CHUNK])
-                await self._send_to(peer, {"t": "stream_data", "sid": sid, "data": c, "proto": proto}, proto)
-                n += len(c)
-        else:
-            with open(source, "rb") as f:
-                while True:
-                    c = f.read(STREAM_CHUNK)
-                    if not c:
-                        break
-                    await self._send_to(peer, {"t": "stream_data", "sid": sid, "data": c, "proto": proto}, proto)
+        self._stream_credits[sid] = asyncio.Semaphore(STREAM_WINDOW)
+        try:
+            if isinstance(source, (bytes, bytearray)):
+                for i in range(0, len(source), STREAM_CHUNK):
+                    c = bytes(source[i:i + STREAM_CHUNK])
+                    await self._send_chunk(peer, sid, proto, c)
                     n += len(c)
-        await self._send_to(peer, {"t": "stream_close", "sid": sid, "proto": proto}, proto)
+            else:
+                with open(source, "rb") as f:
+                    while True:
+                        c = f.read(STREAM_CHUNK)
+                        if not c:
+                            break
+                        await self._send_chunk(peer, sid, proto, c)
+                        n += len(c)
+            await self._send_to(peer, {"t": "stream_close", "sid": sid, "proto": proto}, proto)
+        finally:
+            self._stream_credits.pop(sid, None)
         return n
 
     async def stream_pull(self, peer: str, header: Any) -> IncomingStream:
@@ -960,7 +1064,8 @@ class Network:
         hdr = header.to_wire() if hasattr(header, "to_wire") else header
         if len(cbor2.dumps(hdr)) > MAX_STREAM_HEADER:          # stream_pull.rs:28: resource headers stay below 1 MiB
             raise NetworkError("pull-stream header larger than 1 MiB")
-        st = IncomingStream(peer, proto, hdr, None, asyncio.Queue(64))
+        st = IncomingStream(peer, proto, hdr, None, asyncio.Queue(STREAM_WINDOW + 1))
+        self._wire_credits(st, sid, proto)
         self._streams[sid] = st
         await self._send_to(peer, {"t": "stream_open", "sid": sid, "proto": proto, "header": hdr}, proto)
         return st

@@ -75,6 +75,28 @@ class Batched:
                 batch, deadline = [], None
 
 
+def peer_id_from_public_bytes(pub: bytes) -> str:
+    """The peer id of a raw Ed25519 public key (one scheme for private keys and certificates)."""
+    import base64
+
+    return "12D3Koo" + base64.b32encode(hashlib.sha256(pub).digest()).decode().rstrip("=")[:40]
+
+
+def peer_id_from_cert_der(der: bytes) -> str:
+    """Peer id bound to a TLS peer certificate: derived from the certificate's subject public key, so a node
+    can only ever speak under the id of the key its CA-issued certificate was made for (the reference binds
+    the libp2p PeerId to the certificate key the same way, crates/network/src/cert.rs:30-80)."""
+    from cryptography import x509
+    from cryptography.hazmat.primitives import serialization
+
+    pub = x509.load_der_x509_certificate(der).public_key()
+    try:
+        raw = pub.public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
+    except ValueError:       # not an Ed25519/X25519-style key: fall back to the DER SubjectPublicKeyInfo
+        raw = pub.public_bytes(serialization.Encoding.DER, serialization.PublicFormat.SubjectPublicKeyInfo)
+    return peer_id_from_public_bytes(raw)
+
+
 def peer_id_from_key_pem(path: str) -> str:
     """Stable peer id derived from the node's Ed25519 public key (``12D3Koo``-style prefix,
     base32 of sha256(pubkey)); the reference derives the libp2p PeerId the same way from the

@@ -102,7 +102,8 @@ class Connector:
         for fn in ref.filenames:
             local = None
             if self.hf_local:
-                cand = os.path.join(self.hf_local, ref.repository, fn)
+                # repository and file name come from the scheduler's job spec: they must stay inside the registry
+                cand = safe_join(self.hf_local, f"{ref.repository}/{fn}")
                 if os.path.exists(cand):
                     local = cand
             if local is None:
@@ -168,11 +169,7 @@ class Connector:
             while True:
                 st: IncomingStream = await q.get()
                 if st.peer not in allowed:
-                    try:
-                        async for _ in st.chunks():      # drain + drop
-                            pass
-                    except NetworkError:
-                        pass
+                    st.discard()      # not on the allow-list: its sender runs out of flow-control credit and stops
                     continue
                 yield st
         finally:
@@ -261,8 +258,12 @@ class Bridge:
     async def _fetch(self, request: web.Request) -> web.Response:
         try:
             ref = M.Fetch.from_wire(await request.json())
-            if ref.type == "uri" and urlparse(ref.value or "").scheme not in ("http", "https", "file"):
-                raise InvalidResource("uri fetch supports http/https")       # bridge.rs:350-377
+            scheme = urlparse(ref.value or "").scheme if ref.type == "uri" else ""
+            if ref.type == "uri" and scheme not in ("http", "https") and not (
+                    scheme == "file" and os.environ.get("HYPHA_ALLOW_FILE_URI") == "1"):
+                # bridge.rs:350-377.  file:// would let a remote scheduler's job spec copy any local file into the
+                # job directory; it exists for offline tests only, behind an explicit worker-side switch
+                raise InvalidResource("uri fetch supports http/https")
             if ref.type == "peers":
                 raise InvalidResource("peers references cannot be fetched through the bridge")
             out = []

@@ -292,7 +292,8 @@ class ParameterServerExecutor:
                             st = nxt.result()
                             nxt = None
                             if st.peer not in workers:
-                                continue                               # late file from a removed worker
+                                st.discard()                           # late file from a removed worker: its sender
+                                continue                               # runs out of credit, the link stays usable
                             path = os.path.join(work_dir, hashlib.sha256(st.peer.encode()).hexdigest())
                             try:
                                 await st.save(path)

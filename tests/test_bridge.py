@@ -89,6 +89,13 @@ def test_bridge_rejects_bad_requests(tmp_path):
 
         code, err = status_of(lambda: session.fetch({"type": "uri", "value": "ftp://example.org/x"}))
         assert code >= 400 and "http/https" in err
+        code, err = status_of(lambda: session.fetch({"type": "uri", "value": "file:///etc/passwd"}))
+        assert code >= 400 and "http/https" in err                     # a job spec cannot read local files
+        for repo in ("../../etc", "/etc", "org/../../../etc"):         # ... nor leave the offline model registry
+            code, err = status_of(lambda repo=repo: session.fetch(
+                M.Fetch.huggingface(repo, None, ["passwd"], None).to_wire()))
+            assert code >= 400, repo
+        assert not os.path.exists(os.path.join(ctx["work"], "artifacts", "passwd"))
         code, err = status_of(lambda: session.fetch(M.Fetch.data_peer("peer", M.DataSlice("d", 0)).to_wire()))
         assert code >= 400 and "peers" in err
         code, err = status_of(lambda: session.fetch({"type": "telepathy"}))

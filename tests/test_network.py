@@ -350,10 +350,14 @@ def test_tcp_links_use_mutual_tls(tmp_path):
     c, k, t = certutil.make_node(oc2, ok2, "mallory", out_dir=d2)
     evil = {"cert_pem": c, "key_pem": k, "trust_pem": t}
 
+    from hypha_b200.transport.utils import peer_id_from_key_pem as pid
+
     async def main():
-        a = Network("alpha", tls=paths["alpha"])
-        b = Network("beta", tls=paths["beta"])
-        m = Network("mallory", tls=evil)
+        # a node's peer id IS its key (roles.start_node derives it the same way)
+        ida, idb = pid(paths["alpha"]["key_pem"]), pid(paths["beta"]["key_pem"])
+        a = Network(ida, tls=paths["alpha"])
+        b = Network(idb, tls=paths["beta"])
+        m = Network(pid(evil["key_pem"]), tls=evil)
         plain = Network("plain")
         addr = await a.listen("tcp://127.0.0.1:0")
 
@@ -362,13 +366,65 @@ def test_tcp_links_use_mutual_tls(tmp_path):
 
         a.on("/test/echo", None, echo)
         peer = await b.dial(addr)
-        assert peer == "alpha"
-        resp = await b.request("alpha", "/test/echo", {"x": 1})
-        assert resp == {"echo": {"x": 1}, "from": "beta"}
+        assert peer == ida
+        resp = await b.request(ida, "/test/echo", {"x": 1})
+        assert resp == {"echo": {"x": 1}, "from": idb}
         for bad in (m, plain):
             with pytest.raises(DialError):
                 await bad.dial(addr, timeout=2.0)
         for n in (a, b, m, plain):
+            await n.close()
+
+    asyncio.run(main())
+
+
+def test_peer_identity_is_bound_to_the_certificate(tmp_path):
+    """A node with a VALID certificate of the trusted CA cannot speak under another node's peer id: its hello
+    is refused (the id must be the one derived from its certificate key), a relay stamps the id it
+    authenticated on relayed frames, and DHT records are only accepted under the sender's own id."""
+    from hypha_b200 import certutil
+    from hypha_b200.transport.network import DialError, Network
+    from hypha_b200.transport.utils import peer_id_from_key_pem as pid
+
+    d = str(tmp_path)
+    rc, rk = certutil.make_root("Acme", out_dir=d)
+    oc, ok = certutil.make_org(rc, rk, "Acme", name="acme-org", out_dir=d)
+    tls = {}
+    for n in ("gw", "sched", "worker", "mallory"):
+        c, k, t = certutil.make_node(oc, ok, n, sans=("127.0.0.1",), out_dir=d)
+        tls[n] = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+    ids = {n: pid(v["key_pem"]) for n, v in tls.items()}
+
+    async def main():
+        gw = Network(ids["gw"], tls=tls["gw"], relay_server=True, dht_server=True)
+        gw.enable_dht_handlers()
+        sched = Network(ids["sched"], tls=tls["sched"])
+        addr = await gw.listen("tcp://127.0.0.1:0")
+        assert await sched.dial(addr) == ids["gw"]
+        # 1. mallory holds a certificate of the same CA but claims the scheduler's id
+        imp = Network(ids["sched"], tls=tls["mallory"])
+        with pytest.raises(DialError):
+            await imp.dial(addr, timeout=2.0)
+        assert gw.identity_rejections == 1 and gw.links[ids["sched"]] is not None
+        assert await sched.ping(ids["gw"]) is not None      # the honest link is unaffected
+        # 2. under her own id she connects, but cannot publish a record or relay a frame in somebody else's name
+        mal = Network(ids["mallory"], tls=tls["mallory"])
+        assert await mal.dial(addr) == ids["gw"]
+        link = mal.links[ids["gw"]]
+        await link.send({"t": "dht_put", "key": "dataset", "value": b"x", "publisher": ids["sched"]})
+        got = []
+
+        async def whoami(peer, msg):
+            got.append(peer)
+            return {"peer": peer}
+
+        sched.on("/test/whoami", None, whoami)
+        await link.send({"t": "relay", "dst": ids["sched"], "src": ids["worker"],
+                         "inner": {"t": "req", "id": "r1", "proto": "/test/whoami", "payload": __import__("cbor2").dumps({})}})
+        await asyncio.sleep(0.3)
+        assert "dataset" not in gw._records and gw.identity_rejections == 2
+        assert got == [ids["mallory"]]                 # the relay vouched for the id IT authenticated, not the claimed one
+        for n in (gw, sched, imp, mal):
             await n.close()
 
     asyncio.run(main())
@@ -540,15 +596,56 @@ def test_revoked_node_certificate_is_refused(tmp_path):
     crl = certutil.make_crl(oc, ok, (tls["beta"]["cert_pem"],), out_dir=d)
     tls["alpha"]["crls_pem"] = crl
 
+    from hypha_b200.transport.utils import peer_id_from_key_pem as pid
+
     async def main():
-        a = Network("alpha", tls=tls["alpha"])
-        b = Network("beta", tls=tls["beta"])
-        g = Network("gamma", tls=tls["gamma"])
+        ids = {n: pid(tls[n]["key_pem"]) for n in tls}
+        a = Network(ids["alpha"], tls=tls["alpha"])
+        b = Network(ids["beta"], tls=tls["beta"])
+        g = Network(ids["gamma"], tls=tls["gamma"])
         addr = await a.listen("tcp://127.0.0.1:0")
-        assert await g.dial(addr) == "alpha"                      # same CA, not revoked
+        assert await g.dial(addr) == ids["alpha"]                 # same CA, not revoked
         with pytest.raises(DialError):
             await b.dial(addr, timeout=2.0)
-        assert "beta" not in a.links and "gamma" in a.links
+        assert ids["beta"] not in a.links and ids["gamma"] in a.links
         for n in (a, b, g):
             await n.close()
+    asyncio.run(main())
+
+
+def test_unconsumed_stream_does_not_stall_the_link(tmp_path):
+    """Flow control is per stream (credits), not per link: a push stream that nobody reads stops after its
+    window, while requests, pings and a second stream on the SAME socket link keep flowing.  (Round-1 defect:
+    the link's read loop awaited the stream's bounded queue, so one ignored stream wedged the peer's link.)"""
+    import hypha_b200.transport.network as N
+
+    async def main():
+        a, b = N.Network("a"), N.Network("b")
+        addr = await a.listen(f"unix://{tmp_path}/a.sock")
+        await b.dial(addr)
+
+        async def echo(peer, msg):
+            return {"echo": msg}
+
+        a.on("/test/echo", None, echo)
+        ignored = a.streams_push("job-ignored")        # registered, never consumed
+        wanted = a.streams_push("job-wanted")
+        big = bytes(N.STREAM_CHUNK) * (N.STREAM_WINDOW + 40)         # more than one window
+        stuck = asyncio.ensure_future(b.stream_push(a.peer_id, big, job_id="job-ignored"))
+        await asyncio.sleep(0.5)
+        assert not stuck.done()                          # out of credit after STREAM_WINDOW chunks
+        for i in range(5):                               # the link itself is alive
+            assert await asyncio.wait_for(b.request(a.peer_id, "/test/echo", {"i": i}), 2.0) == {"echo": {"i": i}}
+        assert await asyncio.wait_for(b.ping(a.peer_id), 2.0) >= 0
+        payload = os.urandom(3 * N.STREAM_CHUNK + 17)
+        push = asyncio.ensure_future(b.stream_push(a.peer_id, payload, job_id="job-wanted"))
+        st = await asyncio.wait_for(wanted.get(), 2.0)
+        assert await asyncio.wait_for(st.read_all(), 5.0) == payload and await push == len(payload)
+        # the consumer finally looks at the ignored stream and refuses it: the sender gives up
+        st2 = await asyncio.wait_for(ignored.get(), 2.0)
+        st2.discard()
+        stuck.cancel()
+        for n in (a, b):
+            await n.close()
+
     asyncio.run(main())
