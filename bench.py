@@ -449,6 +449,7 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     ops.reset_launch_count()
+    ops.reset_fallback_counts()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -456,7 +457,12 @@ def main():
     ev1.record()
     barrier()
     launches = ops.launch_count()
+    fallbacks = ops.fallback_counts()
     clocks = sampler.stop()
+    if fallbacks and args.impl == "ours":
+        # the number this script reports is the hand-written kernels' or nothing
+        print(f"bench.py: library fallbacks inside the timed region: {fallbacks}", file=sys.stderr)
+        return 3
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     ms_per_step = ms_total / args.steps
     value = tokens_per_step * args.steps / (ms_total / 1e3)
@@ -516,7 +522,8 @@ def main():
                 "l2": "no flush needed: >16 GB of weights/activations streamed per step >> 126 MB L2",
             },
             "model_tflops_per_gpu": value / world * cfg.flops_per_token(S) / 1e12,
-            "outer_step_ms": outer_ms, "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e,
+            "outer_step_ms": outer_ms, "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches),
+            "library_fallbacks": fallbacks, "e2e": e2e,
         }
         if drill is not None:
             out["fault_drill"] = drill

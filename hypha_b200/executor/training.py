@@ -420,6 +420,59 @@ class _TrainerEngine:
         print(f"membership generation {mem['generation']}: ranks {new} admitted into the fused engine", flush=True)
         self._pending, self.joining = [], False
 
+    # -- job checkpoint through the scheduler (`[scheduler.job.checkpoint]`; the reference has none) --------
+    @torch.no_grad()
+    def save_checkpoint(self, ckpt_dir: str, round_no: int, work_dir: str) -> Optional[str]:
+        """Right after an outer step every rank holds the same bf16 parameters, and rank r the fp32 theta_outer +
+        momentum of shard r (ZeRO-1).  Rank 0 writes the parameters, every rank its outer shard; rank 0 announces
+        the round once all pieces are on disk.  As in the other aggregation modes the inner AdamW state is not
+        part of a job checkpoint (`DiLoCoTrainer.save_checkpoint` is the full-state, per-rank variant)."""
+        from safetensors.torch import save_file
+
+        from ..worker.jobs import publish_sharded_checkpoint
+
+        outer = self.trainer.outer
+        if outer.backend == "fused" and outer.members() != list(range(outer.world)):
+            print(f"checkpoint of round {round_no} skipped: membership is not full ({outer.members()})", flush=True)
+            return None
+        torch.cuda.synchronize()
+        world, rank = outer.world, outer.rank
+        names = ["collective_params"] + [f"outer_shard_{r}" for r in range(world)]
+        tmp = os.path.join(work_dir, f"outer_shard_{rank}.tmp")
+        save_file({"theta_outer": outer.theta_outer.detach().cpu(), "momentum": outer.momentum.detach().cpu(),
+                   "meta": torch.tensor([outer.round, outer.shard_begin, outer.shard_len, world], dtype=torch.int64)}, tmp)
+        where = publish_sharded_checkpoint(ckpt_dir, round_no, f"outer_shard_{rank}", tmp,
+                                           expect=None)
+        os.unlink(tmp)
+        if rank == 0:
+            tmp = os.path.join(work_dir, "collective_params.tmp")
+            save_file({"params": self.trainer.model.flat.data.detach().cpu()}, tmp)
+            where = publish_sharded_checkpoint(ckpt_dir, round_no, "collective_params", tmp, expect=names)
+            os.unlink(tmp)
+        return where
+
+    @torch.no_grad()
+    def load_checkpoint(self, path: str) -> None:
+        from safetensors.torch import load_file
+
+        tr, outer = self.trainer, self.trainer.outer
+        dev = str(tr.device)
+        tr.model.flat.data.copy_(load_file(os.path.join(path, "collective_params"), device=dev)["params"])
+        tr.opt.master.copy_(tr.model.flat.data)                    # fp32 master restarts from the bf16 weights
+        sh = load_file(os.path.join(path, f"outer_shard_{outer.rank}"), device=dev)
+        rnd, begin, length, world = (int(x) for x in sh["meta"].tolist())
+        if (begin, length, world) != (outer.shard_begin, outer.shard_len, outer.world):
+            raise RuntimeError(f"checkpoint shard {outer.rank} covers [{begin}, +{length}) of a {world}-rank job; this job "
+                               f"needs [{outer.shard_begin}, +{outer.shard_len}) of {outer.world}")
+        outer.theta_outer.copy_(sh["theta_outer"])
+        outer.momentum.copy_(sh["momentum"])
+        outer.round = rnd
+        if outer.backend == "fused":
+            outer.anchor_buf.local.copy_(tr.model.flat.data)
+        from ..ops.functional import bump_fp8_weight_version
+
+        bump_fp8_weight_version()
+
     def outer_step(self, round_no: int = -1, samples: Optional[int] = None) -> None:
         # `samples` is ignored: the fused kernel takes the mean over ranks (equal shares on a homogeneous box)
         outer = self.trainer.outer
@@ -597,9 +650,6 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     joining = bool(coll.get("join"))        # a replacement rank: no training before its first barrier
     ckpt = coll.get("checkpoint") or {}
     if ckpt.get("resume_round"):
-        if not hasattr(engine, "load_checkpoint"):
-            raise RuntimeError("resuming a collective job from a job checkpoint is implemented for the CPU (gloo) "
-                               "engine; the GPU trainer has DiLoCoTrainer.save_checkpoint / load_checkpoint")
         engine.load_checkpoint(os.path.join(ckpt["dir"], f"round-{int(ckpt['resume_round'])}"))
         round_no = int(ckpt["resume_round"]) + 1
         print(f"resumed from the collective checkpoint of round {round_no - 1}", flush=True)

@@ -43,6 +43,34 @@ def get_gemm_backend() -> str:
     return _GEMM_BACKEND
 
 
+# Library fallbacks are counted, never silent: a CUDA tensor that reaches torch.mm / cuDNN although the
+# hand-written backend was requested bumps a counter (and logs once per reason); bench.py refuses to report a
+# number if any happened inside its timed region, and HYPHA_STRICT_KERNELS=1 turns them into errors.
+_FALLBACKS: dict = {}
+_FALLBACK_LOGGED: set = set()
+
+
+def _note_fallback(op: str, why: str) -> None:
+    key = f"{op}: {why}"
+    _FALLBACKS[key] = _FALLBACKS.get(key, 0) + 1
+    if os.environ.get("HYPHA_STRICT_KERNELS") == "1":
+        raise RuntimeError(f"library fallback refused (HYPHA_STRICT_KERNELS=1): {key}")
+    if key not in _FALLBACK_LOGGED:
+        _FALLBACK_LOGGED.add(key)
+        import logging
+
+        logging.getLogger("hypha.ops").warning("library fallback: %s", key)
+
+
+def fallback_counts() -> dict:
+    """``{"op: reason": count}`` of CUDA calls that ran a library kernel instead of the requested sm_100a one."""
+    return dict(_FALLBACKS)
+
+
+def reset_fallback_counts() -> None:
+    _FALLBACKS.clear()
+
+
 def _ptr(t: Optional[torch.Tensor]) -> int:
     return 0 if t is None else t.data_ptr()
 
@@ -76,6 +104,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
                            b.stride(0), out.stride(0), int(a_kmajor), int(b_kmajor),
                            int(accumulate), cuda_stream())
         return out
+    if a.is_cuda and _GEMM_BACKEND == "tcgen05":
+        _note_fallback("gemm", f"operands not 16-byte aligned / multiple of 8 (M={M} N={N} K={K}, dtypes "
+                               f"{a.dtype}/{b.dtype}/{out.dtype})")
     A = a if a_kmajor else a.t()
     B = b.t() if b_kmajor else b
     if accumulate:
@@ -783,6 +814,9 @@ def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: i
         return _TcgenAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "flash2":
         return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+    if _ATTN_BACKEND == "tcgen05":
+        _note_fallback("attention", f"tcgen05 kernels cover head_dim 128 and seq % 128 == 0 "
+                                    f"(got head_dim={head_dim}, seq={seq}): cuDNN used")
     return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)      # cudnn, or a shape tcgen05 does not cover
 
 

@@ -21,6 +21,7 @@ import torch
 from .models.llama import LlamaConfig, LlamaForCausalLM, get_config
 from .parallel.diloco import AdamWConfig, DiLoCoConfig, DiLoCoOuter, FlatAdamW, make_lr_lambda
 from .parallel.peer_memory import PeerGroup
+from .telemetry import DeviceTimer, nvtx_range
 
 
 @dataclass
@@ -50,6 +51,8 @@ class DiLoCoTrainer:
             model.grad_ready_hook = self._on_grad_ready
         self.last_loss: Optional[torch.Tensor] = None
         self.h2d_bytes = 0
+        self.time_outer = os.environ.get("HYPHA_TIME_OUTER", "0") == "1"
+        self.last_outer_ms: Optional[float] = None
 
     # -- construction -------------------------------------------------------------------
     @classmethod
@@ -127,18 +130,25 @@ class DiLoCoTrainer:
         self._opt_done.append((begin, end))
 
     def inner_step(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
-        ids = self._to_device(input_ids)
-        lab = self._to_device(labels)
+        # NVTX ranges (hypha.h2d / fwd / bwd / opt / outer) mark the phases of a step in ncu / nsys timelines
+        with nvtx_range("hypha.h2d"):
+            ids = self._to_device(input_ids)
+            lab = self._to_device(labels)
         self.model.set_grad_accumulate(False)
         if not self.overlap_optimizer:
-            loss = self.model(ids, lab)
-            loss.backward()
-            self.opt.step()
+            with nvtx_range("hypha.fwd"):
+                loss = self.model(ids, lab)
+            with nvtx_range("hypha.bwd"):
+                loss.backward()
+            with nvtx_range("hypha.opt"):
+                self.opt.step()
         else:
             self.opt.begin_step()
             self._opt_done.clear()
-            loss = self.model(ids, lab)
-            loss.backward()
+            with nvtx_range("hypha.fwd"):
+                loss = self.model(ids, lab)
+            with nvtx_range("hypha.bwd+opt"):          # each layer's AdamW slice runs under the remaining backward
+                loss.backward()
             # whatever backward did not cover (the embedding table, or everything if no hook fired)
             done = sorted(self._opt_done)
             cur, n = 0, self.opt.params.numel()
@@ -157,7 +167,15 @@ class DiLoCoTrainer:
         return self.last_loss
 
     def outer_step(self) -> None:
-        self.outer.step()
+        """One DiLoCo outer step; its device time (CUDA events on the launching stream) is kept in
+        ``last_outer_ms`` when ``time_outer`` is set (costs one event synchronisation)."""
+        with nvtx_range("hypha.outer"):
+            if self.time_outer and self.device.type == "cuda":
+                with DeviceTimer() as t:
+                    self.outer.step()
+                self.last_outer_ms = t.ms
+            else:
+                self.outer.step()
 
     def step(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One DiLoCo inner step; runs the outer step when ``inner_steps`` are complete."""

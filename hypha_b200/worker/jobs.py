@@ -19,6 +19,7 @@ import hashlib
 import json
 import os
 import shutil
+import time
 import signal
 import sys
 import uuid
@@ -176,6 +177,8 @@ def latest_checkpoint(ckpt_dir: str) -> Optional[dict]:
             return {"round": int(meta["round"]), "path": path, "kind": "parameter-server"}
         if os.path.isfile(os.path.join(path, "collective_state")):
             return {"round": int(meta["round"]), "path": path, "kind": "collective"}
+        if os.path.isfile(os.path.join(path, "collective_params")):     # fused GPU engine: params + one outer shard per rank
+            return {"round": int(meta["round"]), "path": path, "kind": "collective"}
     except (OSError, ValueError, KeyError):
         pass
     return None
@@ -185,6 +188,34 @@ def save_job_checkpoint(ckpt_dir: str, round_no: int, cum_path: str, momentum_pa
     """Copy the aggregate job's outer state (cumulative update U + momentum) to ``<dir>/round-<n>`` and flip
     ``latest.json`` atomically; older checkpoints beyond ``keep`` are removed."""
     return publish_checkpoint(ckpt_dir, round_no, {"cumulative_update": cum_path, "momentum": momentum_path}, keep)
+
+
+def publish_sharded_checkpoint(ckpt_dir: str, round_no: int, name: str, src: str, *, expect: Optional[List[str]] = None,
+                               wait_s: float = 120.0, keep: int = 2) -> Optional[str]:
+    """Several processes of one box write ONE checkpoint: each moves its own file into ``round-<n>/`` atomically
+    (``name.tmp`` -> ``name``).  The process that passes ``expect`` (the complete list of file names: rank 0)
+    waits until all of them exist, flips ``latest.json`` -- the round is never announced half-written -- and prunes
+    old rounds.  Returns the round directory for that process, None for the others."""
+    dst = os.path.join(ckpt_dir, f"round-{round_no}")
+    os.makedirs(dst, exist_ok=True)
+    tmp = os.path.join(dst, name + ".tmp")
+    shutil.copyfile(src, tmp)
+    os.replace(tmp, os.path.join(dst, name))
+    if expect is None:
+        return None
+    deadline = time.monotonic() + wait_s
+    while not all(os.path.isfile(os.path.join(dst, n)) for n in expect):
+        if time.monotonic() > deadline:
+            missing = [n for n in expect if not os.path.isfile(os.path.join(dst, n))]
+            raise TimeoutError(f"checkpoint of round {round_no}: still missing {missing}")
+        time.sleep(0.05)
+    meta_tmp = os.path.join(ckpt_dir, "latest.json.tmp")
+    json.dump({"round": round_no}, open(meta_tmp, "w"))
+    os.replace(meta_tmp, os.path.join(ckpt_dir, "latest.json"))
+    rounds = sorted(int(d.split("-")[1]) for d in os.listdir(ckpt_dir) if d.startswith("round-") and d.split("-")[1].isdigit())
+    for r in rounds[:-keep]:
+        shutil.rmtree(os.path.join(ckpt_dir, f"round-{r}"), ignore_errors=True)
+    return dst
 
 
 def publish_checkpoint(ckpt_dir: str, round_no: int, files: Dict[str, str], keep: int = 2) -> str:

@@ -107,7 +107,8 @@ def test_hypha_box_runs_a_collective_job_on_cpu(capsys):
     out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert rc == 0 and out["finished"] and out["rounds"] == 2 and out["aggregation"] == "collective"
     assert sorted(out["metrics"]) == ["worker-a", "worker-b"]
-    assert set(out["metrics"]["worker-a"]["2"]) == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms"}
+    assert set(out["metrics"]["worker-a"]["2"]) == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms",
+                                                     "inner_steps", "tokens"}
 
 
 def test_worker_init_detects_resources_and_pins_a_device(tmp_path):

@@ -115,3 +115,62 @@ def test_replacement_process_joins_the_fused_engine():
                        capture_output=True, text=True, timeout=550, cwd=ROOT)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert '"correct": true' in r.stdout
+
+
+@pytest.mark.timeout(900)
+def test_gpu_collective_job_checkpoint_and_resume(tmp_path):
+    """`[scheduler.job.checkpoint]` on the fused GPU engine (round-1 gap: the job checkpoint stopped at the CPU
+    engine).  Run A: 2 GPUs, 2 rounds, a checkpoint after every outer step = the bf16 parameters (written by rank
+    0) + one fp32 theta_outer / momentum shard per rank.  Run B with `resume = true` and new executor processes
+    loads them on every rank, starts at round 3 and finishes round 4."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import asyncio
+    import json
+
+    from safetensors.torch import load_file
+
+    from hypha_b200.executor.dataset import write_synthetic_token_slices
+    from hypha_b200.local_cluster import run_loopback_job
+    from hypha_b200.models.llama import get_config
+
+    cfg = get_config("llama-tiny")
+    ckpt = str(tmp_path / "ckpt")
+
+    def job(rounds, resume):
+        return {
+            "model": {"repository": "local/llama-tiny", "filenames": ["config.json"], "type": "causal-lm",
+                      "input_names": ["input_ids", "labels"]},
+            "preprocessor": None, "dataset": {"dataset": "toyset"},
+            "rounds": {"avg_samples_between_updates": 24, "update_rounds": rounds, "max_batch_size": 2},
+            "inner_optimizer": {"learning-rate": 3e-3}, "outer_optimizer": {"learning-rate": 0.7, "momentum": 0.9},
+            "aggregation": {"mode": "collective"}, "checkpoint": {"dir": ckpt, "every": 1, "resume": resume},
+            "resources": {"num_workers": 2, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
+                          "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
+        }
+
+    def run(sub, j):
+        d = str(tmp_path / sub)
+        os.makedirs(d)
+        return asyncio.run(run_loopback_job(
+            d, repo="local/llama-tiny", write_model_config=lambda p: cfg.to_hf_json(p, seed=3), job=j, timeout_s=400,
+            write_dataset=lambda p: write_synthetic_token_slices(p, num_slices=8, samples_per_slice=16, seq_len=128,
+                                                                 vocab_size=cfg.vocab_size)))
+
+    a, _, logs_a, _ = run("a", job(2, False))
+    assert a.finished and a.rounds == 2, logs_a[-30:]
+    assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 2}
+    files = sorted(os.listdir(os.path.join(ckpt, "round-2")))
+    assert files == ["collective_params", "outer_shard_0", "outer_shard_1"], files
+    p2 = load_file(os.path.join(ckpt, "round-2", "collective_params"))["params"]
+    sh = load_file(os.path.join(ckpt, "round-2", "outer_shard_1"))
+    assert int(sh["meta"][0]) == 2 and int(sh["meta"][3]) == 2 and float(sh["momentum"].abs().max()) > 0
+
+    b, sink_b, logs_b, _ = run("b", job(4, True))
+    assert b.finished and b.rounds == 4, logs_b[-30:]
+    assert sum("resumed from the collective checkpoint of round 2" in l for l in logs_b) == 2
+    assert {r["round"] for r in sink_b.records} == {3, 4}
+    assert json.load(open(os.path.join(ckpt, "latest.json"))) == {"round": 4}
+    p4 = load_file(os.path.join(ckpt, "round-4", "collective_params"))["params"]
+    assert not bool((p2 == p4).all())                       # training went on from the restored state
