@@ -317,9 +317,11 @@ class ReplicatedNesterov:
 
 
 def gpu_join_enabled() -> bool:
-    """Replacement processes may join the fused GPU engine (`_TrainerEngine._admit`).  Off by default until
-    the path has run on a multi-GPU box; the host-side protocol is covered by tests/test_peer_rebind.py."""
-    return os.environ.get("HYPHA_GPU_JOIN", "0") == "1"
+    """Replacement processes may join the fused GPU engine (`_TrainerEngine._admit`): on by default since the
+    path ran on hardware (tests/mgpu_join_check.py and tests/mgpu_box_fault_check.py: `kill -9` of an executor,
+    replacement leased, admitted over CUDA IPC / VMM descriptors, weights pulled over NVLink);
+    ``HYPHA_GPU_JOIN=0`` turns it off (the job then continues with the survivors only)."""
+    return os.environ.get("HYPHA_GPU_JOIN", "1") == "1"
 
 
 class _TrainerEngine:
@@ -613,8 +615,7 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     device = f"cuda:{dev_index}" if use_cuda else "cpu"
     gpu_join = bool(coll.get("join")) and use_cuda
     if gpu_join and not gpu_join_enabled():
-        raise RuntimeError("joining a running collective job on GPUs is experimental: set HYPHA_GPU_JOIN=1 on every "
-                           "worker of the job (and HYPHA_NVLS=0); the CPU (gloo) engine joins without it")
+        raise RuntimeError("joining a running collective job on GPUs is switched off (HYPHA_GPU_JOIN=0)")
     if world > 1 and use_cuda and not gpu_join:
         from datetime import timedelta
 

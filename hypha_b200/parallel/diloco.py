@@ -364,10 +364,16 @@ class DiLoCoOuter:
     def readmit(self, rank: int, handback: bool = True) -> None:
         """A (re)joined rank takes its shard back at a round boundary (collective: every rank of the new
         membership calls it).  With ``handback`` the holder's fp32 theta_outer / momentum of that shard travel
-        back to the owner first (`handback`); the segment is dropped by the holder afterwards."""
-        if handback and self.backend == "fused" and self.group is not None and self.group._exchange is not None \
-                and self.owners().get(rank, rank) != rank:
-            self.handback(self.group._exchange, [rank])
+        back to the owner first (`handback`); the segment is dropped by the holder afterwards.  The returning rank
+        missed the membership events of its absence, so the owner map is re-agreed first."""
+        if handback and self.backend == "fused" and self.group is not None and self.group._exchange is not None:
+            returning = rank == self.rank and getattr(self, "_returning", False)
+            maps = self.group._exchange(None if returning else {int(k): int(v) for k, v in self.owners().items()})
+            if returning:
+                self._owner = {int(k): int(v) for k, v in next(m for m in maps if m is not None).items()}
+                self._returning = False
+            if self.owners().get(rank, rank) != rank:
+                self.handback(self.group._exchange, [rank])
         if rank != self.rank:
             self.segments.pop(rank, None)
         self.owners()[rank] = rank
@@ -395,6 +401,7 @@ class DiLoCoOuter:
         if joining:
             self._owner = {int(k): int(v) for k, v in next(m for m in maps if m is not None).items()}
             self.reseed_from(survivors[0])      # parameters over NVLink; theta_outer / momentum placeholders
+            self._returning = False             # the owner map came with `maps` above
             torch.cuda.synchronize()
         self.handback(exchange, new)            # the holders' fp32 theta_outer + momentum go to the newcomers
         if joining:
@@ -419,6 +426,7 @@ class DiLoCoOuter:
         sl = slice(self.shard_begin, self.shard_begin + self.shard_len)
         self.theta_outer.copy_(self.opt.master[sl])
         self.momentum.zero_()
+        self._returning = True          # `readmit` fetches the owner map (and the shard's state) from the others
 
     def step_resilient(self, max_retries: int = 2) -> tuple:
         """``step()`` that survives ranks that never show up: on a barrier-1 timeout the missing
@@ -457,7 +465,7 @@ class DiLoCoOuter:
     def _multicast_ptrs(self) -> tuple:
         """(mc_delta, mc_param) when both buffers are NVLS-bound and every rank participates; the
         switch cannot skip a member, so a shrunk membership falls back to P2P loads/stores."""
-        full = self.member_mask == (1 << self.world) - 1
+        full = self.member_mask == (1 << self.world) - 1 and not getattr(getattr(self, "group", None), "multicast_broken", False)
         md = getattr(self.delta_buf, "mc_ptr", 0)
         mp = getattr(self.param_buf, "mc_ptr", 0)
         if full and md and mp and self.use_nvls:

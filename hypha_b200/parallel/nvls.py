@@ -87,6 +87,16 @@ class NvlsBuffer(SymmetricBuffer):
     mc_ptr: int = 0                 # multicast virtual address (0 if multicast could not be set up)
     nbytes_mapped: int = 0
     _handles: Optional[list] = None  # driver handles to release in close(): [(va, size, handle), ...]
+    _h_local: object = None          # the local physical allocation (exportable as a POSIX fd: `export_fd`)
+    _gran: int = 0
+
+    def export_fd(self) -> int:
+        """A POSIX file descriptor of the local allocation for a process that was not part of the original team
+        (a replacement rank): it imports + maps it with `map_peer_fd` and reaches this rank's copy with plain
+        P2P loads/stores.  The caller closes the descriptor after sending it."""
+        cu = _cu()
+        H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+        return int(_ck(cu.cuMemExportToShareableHandle(self._h_local, H, 0), "cuMemExportToShareableHandle"))
 
     def close(self) -> None:
         """Unmap every view and release the allocation handles (idempotent; errors are ignored: the
@@ -166,6 +176,41 @@ def nvls_usable(device: int, world: int) -> bool:
                 cu.cuMemRelease(h)
             except Exception:
                 pass
+
+
+def map_peer_fd(fd: int, nbytes_mapped: int, device: int) -> tuple:
+    """Import a peer's VMM allocation from its file descriptor and map it read/write on ``device``.
+    Returns ``(device pointer, (va, size, handle))``; the tuple goes to `unmap_peer`."""
+    cu = _cu()
+    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
+    h = _ck(cu.cuMemImportFromShareableHandle(fd, H), "cuMemImportFromShareableHandle")
+    try:
+        va = _ck(cu.cuMemAddressReserve(nbytes_mapped, 0, 0, 0), "cuMemAddressReserve")
+        try:
+            _ck(cu.cuMemMap(va, nbytes_mapped, 0, h, 0), "cuMemMap")
+        except Exception:
+            cu.cuMemAddressFree(va, nbytes_mapped)
+            raise
+        access = cu.CUmemAccessDesc()
+        access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
+        access.location.id = device
+        access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
+        _ck(cu.cuMemSetAccess(va, nbytes_mapped, [access], 1), "cuMemSetAccess")
+    except Exception:
+        cu.cuMemRelease(h)
+        raise
+    return int(va), (va, nbytes_mapped, h)
+
+
+def unmap_peer(mapping: tuple) -> None:
+    cu = _cu()
+    va, size, h = mapping
+    try:
+        cu.cuMemUnmap(va, size)
+        cu.cuMemAddressFree(va, size)
+        cu.cuMemRelease(h)
+    except Exception:
+        pass
 
 
 def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock_dir: Optional[str] = None) -> NvlsBuffer:
@@ -363,6 +408,6 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     stage(s_view)
     agree()
     buf = NvlsBuffer(name, numel, dtype, st["local"], ptrs, mc_ptr=st["mc_ptr"], nbytes_mapped=st["size"],
-                     _handles=list(st["mapped"]))
+                     _handles=list(st["mapped"]), _h_local=st["h_local"], _gran=st["gran"])
     group.buffers[name] = buf
     return buf

@@ -125,6 +125,8 @@ class PeerGroup:
         self.counters = BandwidthCounters()
         self._opened: List[int] = []
         self._owned: List[int] = []
+        self._vmm_peer_maps: List[tuple] = []     # VMM mappings of survivors' NVLS buffers (replacement process)
+        self.multicast_broken = False             # a member of the multicast team was replaced: P2P only
 
     # -- constructors ---------------------------------------------------------------------
     @classmethod
@@ -189,18 +191,25 @@ class PeerGroup:
         their mappings of the dead processes' buffers and open the newcomers', newcomers open everybody's.
         Mappings between two survivors are left alone.  Kernels pick the new addresses up at their next
         launch (pointer tables are read from ``SymmetricBuffer.peer_ptrs``).  ``members`` = the ranks that
-        take part (default: all ``world``; ranks whose slot is vacant are skipped).  NVLS buffers cannot be
-        re-bound (the multicast team is fixed): run elastic GPU jobs with ``HYPHA_NVLS=0``."""
+        take part (default: all ``world``; ranks whose slot is vacant are skipped).  Survivors' NVLS buffers (VMM
+        allocations: no CUDA-IPC handle exists for them) reach a newcomer as POSIX file descriptors over AF_UNIX
+        and are mapped there for plain P2P access; the multicast team itself is fixed at creation, so the group
+        runs the P2P variant of the outer step from then on (``multicast_broken``)."""
         C = load_C()
         replaced = sorted(set(int(r) for r in replaced))
         self._exchange = exchange
         names = sorted(self.buffers)
-        for n in names:
-            if getattr(self.buffers[n], "mc_ptr", 0):
-                raise RebindError(f"buffer {n!r} is bound to an NVSwitch multicast object and cannot be re-bound")
-        mine = {n: (self.buffers[n].numel, str(self.buffers[n].dtype), C.ipc_export(self.buffers[n].local.data_ptr()))
-                for n in names}
-        table = dict(exchange((self.rank, mine)))
+        i_am_new = self.rank in replaced
+
+        def describe(n):
+            buf = self.buffers[n]
+            if getattr(buf, "mc_ptr", 0) or getattr(buf, "_h_local", None) is not None:
+                # VMM allocation (NVLS buffer): no CUDA-IPC handle exists for it; newcomers get a file descriptor
+                return (buf.numel, str(buf.dtype), "vmm", int(getattr(buf, "nbytes_mapped", 0)))
+            return (buf.numel, str(buf.dtype), C.ipc_export(buf.local.data_ptr()), 0)
+
+        mine = {n: describe(n) for n in names}
+        table = {int(r): m for r, m in exchange((self.rank, mine))}
         expect = sorted(int(m) for m in members) if members is not None else list(range(self.world))
         if sorted(table) != expect:
             raise RebindError(f"membership exchange returned ranks {sorted(table)}, expected {expect}")
@@ -217,7 +226,53 @@ class PeerGroup:
         bad = [p for v in verdicts for p in v]
         if bad:
             raise RebindError("; ".join(bad[:3]))
-        i_am_new = self.rank in replaced
+        # ---- VMM (NVLS) buffers of survivors reach the newcomers as file descriptors over AF_UNIX -----------------
+        survivors = [r for r in expect if r not in replaced]
+        vmm_names = [n for n in names if any(table[r][n][2] == "vmm" for r in survivors)]
+        fd_maps: Dict[int, Dict[str, int]] = {}          # on a newcomer: survivor rank -> {buffer name: fd}
+        if vmm_names and replaced:
+            import os
+            import socket
+            import tempfile
+            import threading
+
+            from . import nvls as _nvls
+
+            tag = exchange(os.getpid() if self.rank == expect[0] else None)[0]
+            paths = {r: os.path.join(tempfile.gettempdir(), f"hb-rebind-{tag}-{r}.sock") for r in replaced if r in expect}
+            server = None
+            if i_am_new:
+                if os.path.exists(paths[self.rank]):
+                    os.unlink(paths[self.rank])
+                server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
+                server.bind(paths[self.rank])
+                server.listen(len(expect))
+                server.settimeout(60)
+            exchange("listening")
+            err = None
+            try:
+                if i_am_new:
+                    got = _nvls._recv_fds(server, len(survivors), len(vmm_names))
+                    for r, fds in got.items():
+                        fd_maps[int(r)] = dict(zip(vmm_names, fds))
+                else:
+                    fds = [self.buffers[n].export_fd() for n in vmm_names]
+                    try:
+                        for r in paths:
+                            _nvls._send_fds(paths[r], self.rank, fds)
+                    finally:
+                        for fd in fds:
+                            os.close(fd)
+            except Exception as exc:                      # noqa: BLE001 - agreed on below
+                err = f"rank {self.rank}: {type(exc).__name__}: {exc}"
+            finally:
+                if server is not None:
+                    server.close()
+                    if os.path.exists(paths[self.rank]):
+                        os.unlink(paths[self.rank])
+            errs = [e for e in exchange(err) if e]
+            if errs:
+                raise RebindError("; ".join(errs[:3]))
         for r in expect:
             if r == self.rank or not (i_am_new or r in replaced):
                 continue
@@ -230,10 +285,25 @@ class PeerGroup:
                     except Exception:
                         pass
                     self._opened.remove(old)
-                with torch.cuda.device(self.device):
-                    p = C.ipc_open(table[r][n][2])
-                self._opened.append(p)
+                kind = table[r][n][2]
+                if kind == "vmm":
+                    from . import nvls as _nvls
+
+                    with torch.cuda.device(self.device):
+                        p, mapping = _nvls.map_peer_fd(fd_maps[r][n], int(table[r][n][3]), self.device)
+                    import os
+
+                    os.close(fd_maps[r][n])
+                    self._vmm_peer_maps.append(mapping)
+                else:
+                    with torch.cuda.device(self.device):
+                        p = C.ipc_open(kind)
+                    self._opened.append(p)
                 buf.peer_ptrs[r] = p
+        if vmm_names and replaced:
+            # the NVSwitch multicast team is fixed at creation: with a replaced member the multimem path is off
+            # for good (plain P2P loads/stores go on working); DiLoCoOuter checks this flag
+            self.multicast_broken = True
         self.deferred = False
         exchange(self.rank)                           # nobody launches before every mapping exists
 
@@ -255,6 +325,12 @@ class PeerGroup:
             except Exception:
                 pass
         self._opened.clear()
+        if self._vmm_peer_maps:
+            from . import nvls as _nvls
+
+            for mp in self._vmm_peer_maps:
+                _nvls.unmap_peer(mp)
+            self._vmm_peer_maps.clear()
         for b in self.buffers.values():
             if hasattr(b, "close"):          # NVLS (VMM + multicast) buffers release their own mappings
                 b.close()

@@ -95,10 +95,17 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
     tel = Telemetry.from_config(f"hypha-{role}", cfg)
     C.load_tls(cfg)                         # validates that the configured PEM files are readable
     tls = {k: getattr(cfg, k, "") for k in ("cert_pem", "key_pem", "trust_pem", "crls_pem")}
-    if peer_id is None and getattr(cfg, "key_pem", ""):
+    if getattr(cfg, "key_pem", ""):
         from .transport.utils import peer_id_from_key_pem
 
-        peer_id = peer_id_from_key_pem(cfg.key_pem)      # identity = public key, like the reference
+        derived = peer_id_from_key_pem(cfg.key_pem)      # identity = public key, like the reference
+        if peer_id is not None and peer_id != derived and any(
+                str(a).startswith("tcp://") for a in list(cfg.listen_addresses) + list(getattr(cfg, "gateway_addresses", []) or [])):
+            # peers check the claimed id against the TLS certificate: a chosen name would be refused on every link
+            tel.logger.warning("--peer-id %s ignored: with mTLS the peer id is the one of the node's key (%s)", peer_id, derived)
+            peer_id = derived
+        elif peer_id is None:
+            peer_id = derived
     net = Network(peer_id or f"{role}-{M.new_id()[:8]}", agent=f"hypha-{role}", relay_server=relay_server,
                   dht_server=dht_server, tls=tls)          # mTLS applies to tcp:// links only
     if any(a.startswith("tcp://") for a in cfg.listen_addresses) and net.tls is None:
@@ -136,7 +143,12 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
 async def probe(addr: str, timeout: float = 5.0, tls: Optional[dict] = None) -> bool:
     """``probe <addr>``: dial, send ``health::Request``, true iff healthy
     (hypha-scheduler.rs:494-535)."""
-    net = Network(f"probe-{M.new_id()[:8]}", tls=tls)
+    pid = f"probe-{M.new_id()[:8]}"
+    if tls and tls.get("key_pem"):
+        from .transport.utils import peer_id_from_key_pem
+
+        pid = peer_id_from_key_pem(tls["key_pem"])       # under mTLS a node speaks under the id of its key only
+    net = Network(pid, tls=tls)
     try:
         peer = await net.dial(addr, timeout=timeout)
         resp = await net.request(peer, M.HEALTH_PROTOCOL, M.HealthRequest(), timeout=timeout)

@@ -84,7 +84,7 @@ def test_gpt2_diloco_collective_mode_loopback(tmp_path):
     assert outcome.parameter_server == "collective"
     assert sum("outer step via all-reduce" in l for l in logs) == 2
     names = {r["metric_name"] for r in sink.records}
-    assert names == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms"}
+    assert names == {"loss", "samples_or_tokens_per_s", "inner_step_ms", "outer_step_ms", "inner_steps", "tokens"}
     assert all(r["value"] > 0 for r in sink.records)
     losses = {}
     for r in sink.records:

@@ -109,7 +109,12 @@ def test_roles_as_separate_processes_over_tcp_with_mtls(tmp_path):
         assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:] + tail
         res_line = json.loads(out.stdout.strip().splitlines()[-1])
         assert res_line["finished"] and res_line["rounds"] == 2
-        assert sorted(res_line["workers"]) == ["worker-1", "worker-2"] and res_line["parameter_server"] == "worker-ps"
+        # under mTLS every node speaks under the peer id of its own key (the --peer-id names are ignored)
+        from hypha_b200.transport.utils import peer_id_from_key_pem as pid
+
+        ids = {n: pid(tls[n][3]) for n in tls}
+        assert sorted(res_line["workers"]) == sorted([ids["worker-1"], ids["worker-2"]])
+        assert res_line["parameter_server"] == ids["worker-ps"]
     finally:
         for p in procs:
             try:

@@ -163,12 +163,53 @@ def test_mismatched_newcomer_is_refused_by_all_ranks_before_any_mapping_changes(
     assert [list(g.buffers["model.params"].peer_ptrs) for g in members] == before and not C.closed
 
 
-def test_nvls_buffers_cannot_be_rebound(fake):
-    g = pm.PeerGroup(0, 2, 0, lambda o: [o, o])
-    g.buffers["model.params"] = types.SimpleNamespace(mc_ptr=0xdead, numel=4, dtype=torch.bfloat16)
-    with pytest.raises(pm.RebindError, match="multicast"):
-        g.rebind(lambda o: [o, o], [1])
+def test_nvls_buffers_reach_a_newcomer_as_file_descriptors(fake, monkeypatch):
+    """Survivors whose buffers are NVLS (VMM) allocations have no CUDA-IPC handle to offer: a replacement process
+    receives one POSIX file descriptor per buffer and survivor over AF_UNIX (real sockets, pipe fds standing in
+    for `cuMemExportToShareableHandle`), maps them, and the group marks its multicast team as broken so the outer
+    step runs the P2P variant from then on.  The newcomer's own buffers are plain IPC and are opened as before."""
+    import os
 
+    from hypha_b200.parallel import nvls
+
+    C, world, dead = fake, 3, 1
+    groups = _group_of(world, C, SHAPES)
+    pipes = {}
+    for g in groups:
+        for name, b in g.buffers.items():
+            b.mc_ptr, b._h_local, b.nbytes_mapped = 0xabc000 + g.rank, object(), b.numel * 2
+
+            def export_fd(g=g, name=name):
+                r, w = os.pipe()
+                os.write(w, f"{g.rank}:{name}".encode())
+                os.close(w)
+                pipes[(g.rank, name)] = r
+                return r
+            b.export_fd = export_fd
+    for name in SHAPES:
+        C.allocs[groups[dead].buffers[name].local.data_ptr()] = False
+    new = pm.PeerGroup.joining(dead, world, dead)
+    for name, (n, dt) in SHAPES.items():
+        new.alloc(name, n, dt)
+    mapped = []
+
+    def fake_map(fd, nbytes, device):
+        what = os.read(fd, 64).decode()
+        mapped.append((what, nbytes, device))
+        return 0x7000000 + len(mapped), ("va", nbytes, what)
+    monkeypatch.setattr(nvls, "map_peer_fd", fake_map)
+    monkeypatch.setattr(nvls, "unmap_peer", lambda m: None)
+    members = [groups[0], new, groups[2]]
+    make = _barrier_exchange(world)
+    res = _in_threads([lambda g=g: g.rebind(make(g.rank), [dead]) for g in members])
+    assert res == [None] * 3, res
+    assert sorted(m[0] for m in mapped) == sorted(f"{r}:{n}" for r in (0, 2) for n in SHAPES)
+    assert all(m[2] == dead for m in mapped)
+    assert all(g.multicast_broken for g in members)
+    for r in (0, 2):                                   # survivors opened the newcomer's plain IPC buffers
+        for name in SHAPES:
+            assert _resolve(C, groups[r], name, dead) == new.buffers[name].local.data_ptr()
+    assert len(new._vmm_peer_maps) == 4 and not new.deferred
 
 def test_store_exchange_over_a_tcp_store():
     """All-gather rounds over a TCPStore: no process group, usable by a later membership generation."""
