@@ -89,13 +89,18 @@ void rmsnorm_fwd(const bf16* x, const bf16* res_in, bf16* res_out, const bf16* w
 //   xhat = x*rstd ; g = dy*w ; c = mean(g*xhat)
 //   dx = rstd*(g - xhat*c) (+ dres_in) ; dW += dy*xhat
 // =============================================================================
-template <int kThr, int kMaxVec>
+// kRows rows are in flight per block iteration: their loads are all issued before the (single, kRows-wide)
+// block reduction, so one DRAM round trip and one pair of __syncthreads is paid per kRows rows instead of per
+// row (round 1: one row per iteration ran at 0.40 of the measured HBM copy rate).
+template <int kThr, int kMaxVec, int kRows>
 __global__ void __launch_bounds__(kThr) rmsnorm_bwd_kernel(
     const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
     const float* __restrict__ rstd, const bf16* __restrict__ dres_in, bf16* __restrict__ dx,
     float* __restrict__ dw_partial, int rows, int cols) {
-  __shared__ float red[32];
+  __shared__ float red[kRows][32];
   const int nvec = cols >> 3;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int kWarps = kThr / 32;
   float wv[kMaxVec][8], dwacc[kMaxVec][8];
 #pragma unroll
   for (int j = 0; j < kMaxVec; ++j) {
@@ -104,43 +109,71 @@ __global__ void __launch_bounds__(kThr) rmsnorm_bwd_kernel(
     for (int e = 0; e < 8; ++e) { dwacc[j][e] = 0.f; wv[j][e] = 0.f; }
     if (i < nvec) unpack8(ld_bf16x8(w + (size_t)i * 8), wv[j]);
   }
-  for (int row = blockIdx.x; row < rows; row += gridDim.x) {
-    const size_t base = (size_t)row * cols;
-    const float rs = rstd[row];
-    float g[kMaxVec][8], xh[kMaxVec][8];
-    float dot = 0.f;
+  for (int row0 = blockIdx.x * kRows; row0 < rows; row0 += gridDim.x * kRows) {
+    bf16x8 dyr[kRows][kMaxVec], xr[kRows][kMaxVec];
+    float rs[kRows], dot[kRows];
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int i = threadIdx.x + j * kThr;
-      if (i < nvec) {
-        float dyv[8], xv[8];
-        unpack8(ld_stream_bf16x8(dy + base + (size_t)i * 8), dyv);
-        unpack8(ld_stream_bf16x8(x + base + (size_t)i * 8), xv);
+    for (int r = 0; r < kRows; ++r) {
+      const int row = row0 + r;
+      rs[r] = row < rows ? rstd[row] : 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          xh[j][e] = xv[e] * rs;
-          g[j][e] = dyv[e] * wv[j][e];
-          dot += g[j][e] * xh[j][e];
-          dwacc[j][e] += dyv[e] * xh[j][e];
+      for (int j = 0; j < kMaxVec; ++j) {
+        const int i = threadIdx.x + j * kThr;
+        if (row < rows && i < nvec) {
+          dyr[r][j] = ld_stream_bf16x8(dy + (size_t)row * cols + (size_t)i * 8);
+          xr[r][j] = ld_stream_bf16x8(x + (size_t)row * cols + (size_t)i * 8);
+        } else {
+          dyr[r][j] = bf16x8{};
+          xr[r][j] = bf16x8{};
         }
       }
     }
-    dot = block_sum(dot, red);
-    const float c = dot / (float)cols;
 #pragma unroll
-    for (int j = 0; j < kMaxVec; ++j) {
-      const int i = threadIdx.x + j * kThr;
-      if (i < nvec) {
-        float o[8];
+    for (int r = 0; r < kRows; ++r) {
+      float d = 0.f;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) o[e] = rs * (g[j][e] - xh[j][e] * c);
-        if (dres_in != nullptr) {
-          float r[8];
-          unpack8(ld_stream_bf16x8(dres_in + base + (size_t)i * 8), r);
+      for (int j = 0; j < kMaxVec; ++j) {
+        float dyv[8], xv[8];
+        unpack8(dyr[r][j], dyv);
+        unpack8(xr[r][j], xv);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) o[e] += r[e];
+        for (int e = 0; e < 8; ++e) {
+          const float xh = xv[e] * rs[r];
+          d += dyv[e] * wv[j][e] * xh;
+          dwacc[j][e] += dyv[e] * xh;
         }
-        st_bf16x8(dx + base + (size_t)i * 8, pack8(o));
+      }
+      d = warp_sum(d);
+      if (lane == 0) red[r][wid] = d;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      float v = lane < kWarps ? red[r][lane] : 0.f;
+      dot[r] = warp_sum(v) / (float)cols;
+    }
+    __syncthreads();                                   // `red` is rewritten by the next iteration
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const int row = row0 + r;
+      if (row >= rows) break;
+#pragma unroll
+      for (int j = 0; j < kMaxVec; ++j) {
+        const int i = threadIdx.x + j * kThr;
+        if (i < nvec) {
+          float dyv[8], xv[8], o[8];
+          unpack8(dyr[r][j], dyv);
+          unpack8(xr[r][j], xv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[e] = rs[r] * (dyv[e] * wv[j][e] - xv[e] * rs[r] * dot[r]);
+          if (dres_in != nullptr) {
+            float rr[8];
+            unpack8(ld_stream_bf16x8(dres_in + (size_t)row * cols + (size_t)i * 8), rr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += rr[e];
+          }
+          st_bf16x8(dx + (size_t)row * cols + (size_t)i * 8, pack8(o));
+        }
       }
     }
   }
@@ -158,7 +191,7 @@ __global__ void __launch_bounds__(kThr) rmsnorm_bwd_kernel(
 }
 
 int rmsnorm_bwd_num_partials(int rows) {
-  const int cap = kNumSMs * 4;
+  const int cap = kNumSMs;        // the kernel holds kRows rows in registers: one 512-thread block per SM
   return rows < cap ? (rows > 0 ? rows : 1) : cap;
 }
 
@@ -168,32 +201,43 @@ void rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd
   const int grid = rmsnorm_bwd_num_partials(rows);
   const int nvec = cols / 8;
   if (nvec <= 256) {
-    rmsnorm_bwd_kernel<256, 1><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<256, 1, 4><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else if (nvec <= 512) {
-    rmsnorm_bwd_kernel<512, 1><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<512, 1, 4><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else if (nvec <= 1024) {
-    rmsnorm_bwd_kernel<512, 2><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<512, 2, 2><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else {
-    rmsnorm_bwd_kernel<512, 4><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
+    rmsnorm_bwd_kernel<512, 4, 1><<<grid, 512, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   }
   count_launch();
 }
 
-// out[c] (+)= sum_p partial[p, c]
+// out[c] (+)= sum_p partial[p, c].  One block = 32 columns x 8 warps: every warp reads whole 128-byte lines of
+// every 8th partial row, the 8 warp sums meet in shared memory (round 1: cols/256 blocks -> 16 blocks for a
+// 4096-wide norm took as long as the backward kernel's own tail).
 __global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial,
                                                               int nparts, int cols,
                                                               bf16* __restrict__ out,
                                                               int accumulate) {
-  const int c = blockIdx.x * 256 + threadIdx.x;
-  if (c >= cols) return;
+  __shared__ float part[8][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += partial[(size_t)p * cols + c];
-  if (accumulate) acc += __bfloat162float(out[c]);
-  out[c] = __float2bfloat16_rn(acc);
+  if (c < cols)
+    for (int p = wid; p < nparts; p += 8) acc += partial[(size_t)p * cols + c];
+  part[wid][lane] = acc;
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][lane];
+    if (accumulate) t += __bfloat162float(out[c]);
+    out[c] = __float2bfloat16_rn(t);
+  }
 }
 void colsum_partials(const float* partial, int nparts, int cols, bf16* out, int accumulate,
                      cudaStream_t s) {
-  colsum_partials_kernel<<<(cols + 255) / 256, 256, 0, s>>>(partial, nparts, cols, out, accumulate);
+  colsum_partials_kernel<<<(cols + 31) / 32, 256, 0, s>>>(partial, nparts, cols, out, accumulate);
   count_launch();
 }
 
