@@ -81,12 +81,24 @@ def main():
     T = int(os.environ.get("KB_TOKENS", "8192"))
     h, inter, qkv, V = 4096, 14336, 6144, 128256
     shapes = [("qkv", qkv, h), ("wo", h, h), ("gate_up", 2 * inter, h), ("down", h, inter)]
-    for nm, n_out, k_in in shapes:
+    for nm, n_out, k_in in ([] if os.environ.get("KB_SKIP_GEMM") == "1" else shapes):
         gemm_case(f"{nm}.fwd", T, n_out, k_in, True, True, res["gemm"], hbm, tf)
         gemm_case(f"{nm}.dgrad", T, k_in, n_out, True, False, res["gemm"], hbm, tf)
         gemm_case(f"{nm}.wgrad", n_out, k_in, T, False, False, res["gemm"], hbm, tf)
-    gemm_case("lm_head.fwd(chunk4096)", 4096, V, h, True, True, res["gemm"], hbm, tf)
-    gemm_case("square8192", 8192, 8192, 8192, True, True, res["gemm"], hbm, tf)
+    if os.environ.get("KB_SKIP_GEMM") != "1":
+        gemm_case("lm_head.fwd(chunk4096)", 4096, V, h, True, True, res["gemm"], hbm, tf)
+        gemm_case("square8192", 8192, 8192, 8192, True, True, res["gemm"], hbm, tf)
+    # gate_up forward with and without the fused SwiGLU epilogue (vs GEMM + stand-alone SwiGLU kernel)
+    xa = torch.randn(T, h, device="cuda", dtype=torch.bfloat16)
+    wgu = (0.02 * torch.randn(2 * inter, h, device="cuda")).to(torch.bfloat16)
+    gu_o = torch.empty(T, 2 * inter, device="cuda", dtype=torch.bfloat16)
+    act_o = torch.empty(T, inter, device="cuda", dtype=torch.bfloat16)
+    ms_plain = time_fn(lambda i: ops.gemm(xa, wgu, out=gu_o))
+    ms_sep = time_fn(lambda i: (ops.gemm(xa, wgu, out=gu_o), C.swiglu_fwd(gu_o.data_ptr(), act_o.data_ptr(), T, inter,
+                                                                          torch.cuda.current_stream().cuda_stream)))
+    ms_fused = time_fn(lambda i: ops.gemm(xa, wgu, out=gu_o, swiglu_out=act_o))
+    res["swiglu_epilogue"] = {"gemm_ms": ms_plain, "gemm_plus_swiglu_kernel_ms": ms_sep, "fused_ms": ms_fused}
+    print(json.dumps(res["swiglu_epilogue"]), flush=True)
     ops.set_gemm_backend("tcgen05")
 
     # ---- memory-bound kernels ---------------------------------------------------------------
@@ -108,6 +120,9 @@ def main():
                                          dx.data_ptr(), part.data_ptr(), T, h, s))
     res["elementwise"].append({"name": "rmsnorm_bwd", "ms": ms, "gbs": bytes_ / ms / 1e6,
                                "frac_of_hbm": bytes_ / ms / 1e6 / hbm})
+    wg = torch.zeros(h, device="cuda", dtype=torch.bfloat16)
+    ms = time_fn(lambda i: C.colsum_partials(part.data_ptr(), nparts, h, wg.data_ptr(), 0, s))
+    res["elementwise"].append({"name": f"colsum_partials[{nparts}x{h}]", "ms": ms})
     gu = torch.randn(T, 2 * inter, device="cuda", dtype=torch.bfloat16)
     act = torch.empty(T, inter, device="cuda", dtype=torch.bfloat16)
     ms = time_fn(lambda i: C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), T, inter, s))

@@ -167,11 +167,13 @@ PYBIND11_MODULE(_C, m) {
   });
 
   m.def("gemm_bf16", [](u64 A, u64 B, u64 D, int M, int N, int K, int lda, int ldb, int ldd,
-                        int a_kmajor, int b_kmajor, int accumulate, u64 s) {
+                        int a_kmajor, int b_kmajor, int accumulate, u64 s, u64 act, int ld_act) {
     int rc = hb::gemm_bf16_tcgen05(P<const bf16>(A), P<const bf16>(B), P<bf16>(D), M, N, K, lda,
-                                   ldb, ldd, a_kmajor, b_kmajor, accumulate, S(s));
+                                   ldb, ldd, a_kmajor, b_kmajor, accumulate, S(s), P<bf16>(act), ld_act);
     if (rc != 0) throw std::runtime_error(std::string("gemm_bf16_tcgen05: ") + hb::gemm_last_error());
-  });
+  }, py::arg("A"), py::arg("B"), py::arg("D"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("lda"),
+     py::arg("ldb"), py::arg("ldd"), py::arg("a_kmajor"), py::arg("b_kmajor"), py::arg("accumulate"), py::arg("s"),
+     py::arg("act") = 0, py::arg("ld_act") = 0);
 
   m.def("attention_fwd", [](u64 qkv, u64 out, u64 lse, int batch, int seq, int n_heads, int n_kv, int head_dim,
                             int qkv_stride, int out_stride, float scale, u64 s) {
@@ -203,12 +205,14 @@ PYBIND11_MODULE(_C, m) {
       throw std::runtime_error(std::string("attention_bwd_fused_tcgen05: ") + hb::attention_bwd_fused_last_error());
   });
   m.def("gemm_fp8", [](u64 A, u64 B, u64 D, int M, int N, int K, int lda, int ldb, int ldd, int a_kmajor,
-                       int b_kmajor, int a_fmt, int b_fmt, u64 dq_a, u64 dq_b, int accumulate, u64 s) {
+                       int b_kmajor, int a_fmt, int b_fmt, u64 dq_a, u64 dq_b, int accumulate, u64 s, u64 act, int ld_act) {
     int rc = hb::gemm_fp8_tcgen05(P<const uint8_t>(A), P<const uint8_t>(B), P<bf16>(D), M, N, K, lda, ldb, ldd,
                                   a_kmajor, b_kmajor, a_fmt, b_fmt, P<const float>(dq_a), P<const float>(dq_b),
-                                  accumulate, S(s));
+                                  accumulate, S(s), P<bf16>(act), ld_act);
     if (rc != 0) throw std::runtime_error(std::string("gemm_fp8_tcgen05: ") + hb::gemm_last_error());
-  });
+  }, py::arg("A"), py::arg("B"), py::arg("D"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("lda"),
+     py::arg("ldb"), py::arg("ldd"), py::arg("a_kmajor"), py::arg("b_kmajor"), py::arg("a_fmt"), py::arg("b_fmt"),
+     py::arg("dq_a"), py::arg("dq_b"), py::arg("accumulate"), py::arg("s"), py::arg("act") = 0, py::arg("ld_act") = 0);
   m.def("amax_bf16", [](u64 x, int64_t n, u64 amax, u64 s) {
     hb::amax_bf16(P<const bf16>(x), n, P<float>(amax), S(s));
     check_last("amax_bf16");

@@ -7,6 +7,7 @@
 // (reference: executors/accelerate/src/hypha/accelerate_executor/training.py:108-112).
 #include "common.cuh"
 #include "kernels.h"
+#include "tcgen05.cuh"
 
 namespace hb {
 
@@ -65,10 +66,135 @@ __global__ void __launch_bounds__(kThr) rmsnorm_fwd_kernel(
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------
+// Row-streaming variants (the default for hidden sizes that fit: 16-byte aligned rows of <= 16 KB): rows arrive in
+// a 4-deep shared-memory ring through `cp.async.bulk` (the TMA engine, completion on an mbarrier), so HBM reads of
+// the next rows are in flight while the block reduces / writes the current one; every thread owns fixed columns
+// (weights and, in backward, the dW accumulators stay in registers).  The block-per-row kernels above leave the
+// memory system idle during their reduction and ran at 0.40-0.67 of the measured HBM copy rate.
+// -----------------------------------------------------------------------------------------------------------
+constexpr int kNormStages = 4;
+constexpr int kNormThr = 256;
+
+__device__ __forceinline__ bf16x8 lds_bf16x8(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return *reinterpret_cast<bf16x8*>(&r);
+}
+
+template <int kVec, bool kRes>
+__global__ void __launch_bounds__(kNormThr, 2) rmsnorm_fwd_stream_kernel(
+    const bf16* __restrict__ x, const bf16* __restrict__ res_in, bf16* __restrict__ res_out,
+    const bf16* __restrict__ w, bf16* __restrict__ y, float* __restrict__ rstd_out, int rows, int cols, float eps) {
+  using namespace sm100;
+  extern __shared__ __align__(128) uint8_t norm_smem[];
+  __shared__ float red[2][kNormThr / 32];
+  __shared__ __align__(8) uint64_t bars[kNormStages];
+  const uint32_t row_bytes = (uint32_t)cols * 2;
+  const uint32_t stage_bytes = row_bytes * (kRes ? 2 : 1);
+  const uint32_t smem0 = smem_u32(norm_smem);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nvec = cols >> 3;
+  const int my_rows = (rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int k) {                      // thread 0: fetch this block's k-th row into stage k % kNormStages
+    const int st = k % kNormStages;
+    const size_t off = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * cols;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_arrive_expect_tx(bar, stage_bytes);
+    bulk_load_1d(smem0 + st * stage_bytes, x + off, row_bytes, bar);
+    if (kRes) bulk_load_1d(smem0 + st * stage_bytes + row_bytes, res_in + off, row_bytes, bar);
+  };
+  if (tid == 0) {
+    for (int st = 0; st < kNormStages; ++st) mbar_init(smem_u32(&bars[st]), 1);
+    fence_barrier_init();
+    for (int k = 0; k < kNormStages && k < my_rows; ++k) issue(k);
+  }
+  float wv[kVec][8];
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const int i = tid + j * kNormThr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wv[j][e] = 0.f;
+    if (i < nvec) unpack8(ld_bf16x8(w + (size_t)i * 8), wv[j]);
+  }
+  __syncthreads();
+  for (int k = 0; k < my_rows; ++k) {
+    const int st = k % kNormStages;
+    const size_t base = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * cols;
+    mbar_wait(smem_u32(&bars[st]), (uint32_t)(k / kNormStages) & 1u);
+    float h[kVec][8];
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int i = tid + j * kNormThr;
+      if (i < nvec) {
+        unpack8(lds_bf16x8(smem0 + st * stage_bytes + (uint32_t)i * 16), h[j]);
+        if (kRes) {
+          float r[8];
+          unpack8(lds_bf16x8(smem0 + st * stage_bytes + row_bytes + (uint32_t)i * 16), r);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) h[j][e] += r[e];
+          const bf16x8 hv = pack8(h[j]);
+          st_bf16x8(res_out + base + (size_t)i * 8, hv);
+          unpack8(hv, h[j]);                     // normalise exactly what backward will re-read
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) ss += h[j][e] * h[j][e];
+      }
+    }
+    ss = warp_sum(ss);
+    if (lane == 0) red[k & 1][wid] = ss;
+    __syncthreads();                             // also: every thread has read stage st -> it can be refilled
+    if (tid == 0 && k + kNormStages < my_rows) issue(k + kNormStages);
+    float tot = lane < kNormThr / 32 ? red[k & 1][lane] : 0.f;
+    tot = warp_sum(tot);
+    const float rstd = rsqrtf(tot / (float)cols + eps);
+    if (tid == 0 && rstd_out != nullptr) rstd_out[(size_t)blockIdx.x + (size_t)k * gridDim.x] = rstd;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int i = tid + j * kNormThr;
+      if (i < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = h[j][e] * rstd * wv[j][e];
+        st_bf16x8(y + base + (size_t)i * 8, pack8(o));
+      }
+    }
+  }
+}
+
+static bool norm_stream_ok(int cols, const void* a, const void* b) {
+  return cols % 8 == 0 && cols / 8 <= kNormThr * 4 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) == 0;
+}
+static int norm_stream_grid(int rows) {
+  const int cap = kNumSMs * 2;
+  return rows < cap ? rows : cap;
+}
+
 void rmsnorm_fwd(const bf16* x, const bf16* res_in, bf16* res_out, const bf16* w, bf16* y,
                  float* rstd, int rows, int cols, float eps, cudaStream_t s) {
   if (rows == 0) return;
   const int nvec = cols / 8;
+  if (norm_stream_ok(cols, x, res_in)) {
+    const int grid = norm_stream_grid(rows);
+    const int kv = (nvec + kNormThr - 1) / kNormThr;
+    const size_t smem = (size_t)kNormStages * cols * 2 * (res_in != nullptr ? 2 : 1);
+#define HB_FWD_STREAM(KV, RES)                                                                                  \
+    do {                                                                                                        \
+      static bool attr = false;                                                                                 \
+      if (!attr) { cudaFuncSetAttribute(rmsnorm_fwd_stream_kernel<KV, RES>,                                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 16384 * 2); attr = true; } \
+      rmsnorm_fwd_stream_kernel<KV, RES><<<grid, kNormThr, smem, s>>>(x, res_in, res_out, w, y, rstd, rows, cols, eps); \
+    } while (0)
+    if (res_in != nullptr) {
+      if (kv == 1) HB_FWD_STREAM(1, true); else if (kv == 2) HB_FWD_STREAM(2, true); else HB_FWD_STREAM(4, true);
+    } else {
+      if (kv == 1) HB_FWD_STREAM(1, false); else if (kv == 2) HB_FWD_STREAM(2, false); else HB_FWD_STREAM(4, false);
+    }
+#undef HB_FWD_STREAM
+    count_launch();
+    return;
+  }
   // one 16-byte vector per thread whenever possible: small register footprint -> full occupancy
   if (nvec <= 256) {
     rmsnorm_fwd_kernel<256, 1><<<rows, 256, 0, s>>>(x, res_in, res_out, w, y, rstd, cols, eps);
@@ -190,8 +316,102 @@ __global__ void __launch_bounds__(kThr) rmsnorm_bwd_kernel(
   }
 }
 
+template <int kVec, bool kRes>
+__global__ void __launch_bounds__(kNormThr, 2) rmsnorm_bwd_stream_kernel(
+    const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+    const float* __restrict__ rstd, const bf16* __restrict__ dres_in, bf16* __restrict__ dx,
+    float* __restrict__ dw_partial, int rows, int cols) {
+  using namespace sm100;
+  extern __shared__ __align__(128) uint8_t norm_smem[];
+  __shared__ float red[2][kNormThr / 32];
+  __shared__ __align__(8) uint64_t bars[kNormStages];
+  const uint32_t row_bytes = (uint32_t)cols * 2;
+  const uint32_t stage_bytes = row_bytes * (kRes ? 3 : 2);
+  const uint32_t smem0 = smem_u32(norm_smem);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nvec = cols >> 3;
+  const int my_rows = (rows - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto issue = [&](int k) {
+    const int st = k % kNormStages;
+    const size_t off = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * cols;
+    const uint32_t bar = smem_u32(&bars[st]);
+    mbar_arrive_expect_tx(bar, stage_bytes);
+    bulk_load_1d(smem0 + st * stage_bytes, dy + off, row_bytes, bar);
+    bulk_load_1d(smem0 + st * stage_bytes + row_bytes, x + off, row_bytes, bar);
+    if (kRes) bulk_load_1d(smem0 + st * stage_bytes + 2 * row_bytes, dres_in + off, row_bytes, bar);
+  };
+  if (tid == 0) {
+    for (int st = 0; st < kNormStages; ++st) mbar_init(smem_u32(&bars[st]), 1);
+    fence_barrier_init();
+    for (int k = 0; k < kNormStages && k < my_rows; ++k) issue(k);
+  }
+  float wv[kVec][8], dwacc[kVec][8];
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const int i = tid + j * kNormThr;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { dwacc[j][e] = 0.f; wv[j][e] = 0.f; }
+    if (i < nvec) unpack8(ld_bf16x8(w + (size_t)i * 8), wv[j]);
+  }
+  __syncthreads();
+  for (int k = 0; k < my_rows; ++k) {
+    const int st = k % kNormStages;
+    const size_t row = (size_t)blockIdx.x + (size_t)k * gridDim.x;
+    const size_t base = row * cols;
+    const float rs = rstd[row];
+    mbar_wait(smem_u32(&bars[st]), (uint32_t)(k / kNormStages) & 1u);
+    float g[kVec][8], xh[kVec][8], rr[kVec][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int i = tid + j * kNormThr;
+      if (i < nvec) {
+        float dyv[8], xv[8];
+        unpack8(lds_bf16x8(smem0 + st * stage_bytes + (uint32_t)i * 16), dyv);
+        unpack8(lds_bf16x8(smem0 + st * stage_bytes + row_bytes + (uint32_t)i * 16), xv);
+        if (kRes) unpack8(lds_bf16x8(smem0 + st * stage_bytes + 2 * row_bytes + (uint32_t)i * 16), rr[j]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          xh[j][e] = xv[e] * rs;
+          g[j][e] = dyv[e] * wv[j][e];
+          dot += g[j][e] * xh[j][e];
+          dwacc[j][e] += dyv[e] * xh[j][e];
+        }
+      }
+    }
+    dot = warp_sum(dot);
+    if (lane == 0) red[k & 1][wid] = dot;
+    __syncthreads();                             // every thread has read stage st: refill it
+    if (tid == 0 && k + kNormStages < my_rows) issue(k + kNormStages);
+    float tot = lane < kNormThr / 32 ? red[k & 1][lane] : 0.f;
+    const float c = warp_sum(tot) / (float)cols;
+#pragma unroll
+    for (int j = 0; j < kVec; ++j) {
+      const int i = tid + j * kNormThr;
+      if (i < nvec) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          o[e] = rs * (g[j][e] - xh[j][e] * c);
+          if (kRes) o[e] += rr[j][e];
+        }
+        st_bf16x8(dx + base + (size_t)i * 8, pack8(o));
+      }
+    }
+  }
+  float* out = dw_partial + (size_t)blockIdx.x * cols;
+#pragma unroll
+  for (int j = 0; j < kVec; ++j) {
+    const int i = tid + j * kNormThr;
+    if (i < nvec) {
+      *reinterpret_cast<float4*>(out + (size_t)i * 8) = make_float4(dwacc[j][0], dwacc[j][1], dwacc[j][2], dwacc[j][3]);
+      *reinterpret_cast<float4*>(out + (size_t)i * 8 + 4) = make_float4(dwacc[j][4], dwacc[j][5], dwacc[j][6], dwacc[j][7]);
+    }
+  }
+}
+
 int rmsnorm_bwd_num_partials(int rows) {
-  const int cap = kNumSMs;        // the kernel holds kRows rows in registers: one 512-thread block per SM
+  const int cap = kNumSMs * 2;    // both backward variants launch at most this many blocks (one partial row each)
   return rows < cap ? (rows > 0 ? rows : 1) : cap;
 }
 
@@ -200,6 +420,22 @@ void rmsnorm_bwd(const bf16* dy, const bf16* x, const bf16* w, const float* rstd
                  cudaStream_t s) {
   const int grid = rmsnorm_bwd_num_partials(rows);
   const int nvec = cols / 8;
+  if (norm_stream_ok(cols, dy, x) && (reinterpret_cast<uintptr_t>(dres_in) & 15) == 0 && nvec <= kNormThr * 2) {
+    const int kv = (nvec + kNormThr - 1) / kNormThr;
+    const size_t smem = (size_t)kNormStages * cols * 2 * (dres_in != nullptr ? 3 : 2);
+#define HB_BWD_STREAM(KV, RES)                                                                                  \
+    do {                                                                                                        \
+      static bool attr = false;                                                                                 \
+      if (!attr) { cudaFuncSetAttribute(rmsnorm_bwd_stream_kernel<KV, RES>,                                     \
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 8192 * 2 * 3); attr = true; } \
+      rmsnorm_bwd_stream_kernel<KV, RES><<<grid, kNormThr, smem, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols); \
+    } while (0)
+    if (dres_in != nullptr) { if (kv == 1) HB_BWD_STREAM(1, true); else HB_BWD_STREAM(2, true); }
+    else { if (kv == 1) HB_BWD_STREAM(1, false); else HB_BWD_STREAM(2, false); }
+#undef HB_BWD_STREAM
+    count_launch();
+    return;
+  }
   if (nvec <= 256) {
     rmsnorm_bwd_kernel<256, 1, 4><<<grid, 256, 0, s>>>(dy, x, w, rstd, dres_in, dx, dw_partial, rows, cols);
   } else if (nvec <= 512) {
@@ -296,49 +532,55 @@ void rope_inplace(bf16* qkv, const float* cos, const float* sin, int tokens, int
 // =============================================================================
 // SwiGLU on the fused gate|up activation: out = silu(g) * u
 // =============================================================================
+// gate/up are INTERLEAVED along the row: gu[r, 2i] = gate_i, gu[r, 2i+1] = up_i (the rows of the fused gate_up
+// weight are interleaved the same way), so that one 256-wide GEMM output tile holds both halves of 128 pairs and
+// the GEMM epilogue can emit silu(gate) * up itself (gemm_tcgen05.cu, `swiglu` epilogue).
+__device__ __forceinline__ float silu_mul(float g, float u) {
+  const float sg = __fdividef(1.f, 1.f + __expf(-g));
+  return g * sg * u;
+}
+// One thread = one 16-byte chunk of gu (4 (gate, up) pairs) and the matching 8 bytes of the [rows, inter] side:
+// consecutive lanes touch consecutive chunks, so every load / store instruction of a warp covers whole 32-byte
+// sectors (a 32-byte-per-thread split made each instruction use half of every sector it touched: 611 us instead of
+// 180 us for the backward at 8192 x 14336).
 __global__ void __launch_bounds__(256) swiglu_fwd_kernel(const bf16* __restrict__ gu,
                                                          bf16* __restrict__ out, int rows,
                                                          int inter) {
-  // grid.y strides over rows, grid.x over 8-element vectors of a row: no per-element div/mod
-  const int vec_per_row = inter >> 3;
-  const int v = blockIdx.x * 256 + threadIdx.x;
-  if (v >= vec_per_row) return;
+  const int chunks = inter >> 2;                       // 16-byte chunks per gu row
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= chunks) return;
   for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    const bf16* gp = gu + (int64_t)r * 2 * inter + (int64_t)v * 8;
-    float g[8], u[8], o[8];
-    unpack8(ld_stream_bf16x8(gp), g);
-    unpack8(ld_stream_bf16x8(gp + inter), u);
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
-      o[e] = g[e] * sg * u[e];
-    }
-    st_bf16x8(out + (int64_t)r * inter + (int64_t)v * 8, pack8(o));
+    float a[8];
+    unpack8(ld_stream_bf16x8(gu + (int64_t)r * 2 * inter + (int64_t)c * 8), a);      // g0 u0 g1 u1 g2 u2 g3 u3
+    __nv_bfloat162 o[2];
+    o[0] = __floats2bfloat162_rn(silu_mul(a[0], a[1]), silu_mul(a[2], a[3]));
+    o[1] = __floats2bfloat162_rn(silu_mul(a[4], a[5]), silu_mul(a[6], a[7]));
+    *reinterpret_cast<uint2*>(out + (int64_t)r * inter + (int64_t)c * 4) = *reinterpret_cast<uint2*>(o);
   }
 }
 __global__ void __launch_bounds__(256) swiglu_bwd_kernel(const bf16* __restrict__ dout,
                                                          const bf16* __restrict__ gu,
                                                          bf16* __restrict__ dgu, int rows,
                                                          int inter) {
-  const int vec_per_row = inter >> 3;
-  const int v = blockIdx.x * 256 + threadIdx.x;
-  if (v >= vec_per_row) return;
+  const int chunks = inter >> 2;
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= chunks) return;
   for (int r = blockIdx.y; r < rows; r += gridDim.y) {
-    const bf16* gp = gu + (int64_t)r * 2 * inter + (int64_t)v * 8;
-    float g[8], u[8], d[8], dg[8], du[8];
-    unpack8(ld_stream_bf16x8(gp), g);
-    unpack8(ld_stream_bf16x8(gp + inter), u);
-    unpack8(ld_stream_bf16x8(dout + (int64_t)r * inter + (int64_t)v * 8), d);
+    float a[8], o[8];
+    unpack8(ld_stream_bf16x8(gu + (int64_t)r * 2 * inter + (int64_t)c * 8), a);
+    const uint2 dv = *reinterpret_cast<const uint2*>(dout + (int64_t)r * inter + (int64_t)c * 4);
+    const __nv_bfloat162* d2 = reinterpret_cast<const __nv_bfloat162*>(&dv);
+    const float2 d01 = __bfloat1622float2(d2[0]), d23 = __bfloat1622float2(d2[1]);
+    const float d[4] = {d01.x, d01.y, d23.x, d23.y};
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float sg = __fdividef(1.f, 1.f + __expf(-g[e]));
-      const float silu = g[e] * sg;
-      du[e] = d[e] * silu;
-      dg[e] = d[e] * u[e] * (sg + silu * (1.f - sg));
+    for (int e = 0; e < 4; ++e) {
+      const float g = a[2 * e], u = a[2 * e + 1];
+      const float sg = __fdividef(1.f, 1.f + __expf(-g));
+      const float silu = g * sg;
+      o[2 * e] = d[e] * u * (sg + silu * (1.f - sg));
+      o[2 * e + 1] = d[e] * silu;
     }
-    bf16* op = dgu + (int64_t)r * 2 * inter + (int64_t)v * 8;
-    st_bf16x8(op, pack8(dg));
-    st_bf16x8(op + inter, pack8(du));
+    st_bf16x8(dgu + (int64_t)r * 2 * inter + (int64_t)c * 8, pack8(o));
   }
 }
 static int ew_grid(int64_t total) {
@@ -347,7 +589,7 @@ static int ew_grid(int64_t total) {
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 static dim3 swiglu_grid(int rows, int inter) {
-  const int gx = (inter / 8 + 255) / 256;
+  const int gx = (inter / 4 + 255) / 256;
   int gy = rows < 8192 ? rows : 8192;
   if (gy < 1) gy = 1;
   return dim3(gx, gy);

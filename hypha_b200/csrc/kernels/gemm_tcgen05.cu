@@ -61,6 +61,7 @@ struct GemmParams {
   int a_fmt, b_fmt;        // fp8 only: 0 = e4m3, 1 = e5m2
   const float* scale;      // fp8 only: device dequantisation factor of A
   const float* scale_b;    // fp8 only: device dequantisation factor of B
+  int swiglu;              // 2-CTA kernel: the output columns interleave gate/up; ALSO store silu(gate)*up through tma_e
 };
 
 __device__ __forceinline__ void tile_coords(int t, const GemmParams& p, int& tm, int& tn) {
@@ -313,7 +314,9 @@ template <bool kFp8>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                               const __grid_constant__ CUtensorMap tma_b,
-                              const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
+                              const __grid_constant__ CUtensorMap tma_d,
+                              const __grid_constant__ CUtensorMap tma_e,      // second output [M, N/2] (swiglu epilogue)
+                              const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -447,7 +450,8 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
       const int row = m0 + ew * 32 + lane;
-#pragma unroll 1
+uint32_t actp[32];
+      #pragma unroll 2
       for (int c = 0; c < BN / 64; ++c) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_addr + c * 64, r0);
@@ -506,6 +510,41 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           tma_store_commit();
         }
         buf ^= 1;
+        if (p.swiglu) {
+          // Fused SwiGLU: the 64 columns of this chunk are 32 (gate, up) pairs.  The activation is computed from
+          // the bf16-ROUNDED pair, i.e. bit-for-bit what `swiglu_fwd_kernel` re-derives from `gu` in backward.
+          // Two chunks make one 64-column (128-byte) row of the second output; it leaves through the same
+          // two staging buffers as the main output (a buffer is rewritten once the store before last has read it).
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i]));
+            const float2 b2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&packed[i + 1]));
+            const float o0 = a.x * __fdividef(1.f, 1.f + __expf(-a.x)) * a.y;
+            const float o1 = b2.x * __fdividef(1.f, 1.f + __expf(-b2.x)) * b2.y;
+            __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+            actp[(c & 1) * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&h);
+          }
+          if (c & 1) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t abuf = epi_smem + buf * kEpiWarpBuf;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = abuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(actp[4 * j]),
+                           "r"(actp[4 * j + 1]), "r"(actp[4 * j + 2]), "r"(actp[4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              const int acol = (n0 + (c - 1) * 64) >> 1;
+              if (2 * acol < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_e, abuf, acol, m0 + ew * 32);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+        }
       }
     }
     if (lane == 0) tma_store_wait_all<0>();
@@ -579,7 +618,7 @@ int gemm_get_cta_mode() { std::call_once(g_once, init_once); return g_mode; }
 
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
-                      cudaStream_t s) {
+                      cudaStream_t s, bf16* act, int ld_act) {
   std::call_once(g_once, init_once);
   if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
   if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
@@ -591,14 +630,20 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   if ((a_kmajor || b_kmajor) && (K % 8)) { g_err = "K must be a multiple of 8"; return 3; }
   if (!a_kmajor && (M % 8)) { g_err = "MN-major A needs M % 8 == 0"; return 3; }
 
-  const bool two = (g_mode == 2);
+  if (act != nullptr && (accumulate || !al16(act) || (ld_act % 8) || (N % 128))) {
+    g_err = "swiglu epilogue: needs N % 128 == 0, a 16-byte aligned second output and no accumulation";
+    return 3;
+  }
+  const bool two = (g_mode == 2) || act != nullptr;       // the fused epilogue lives in the 2-CTA kernel
   const uint32_t b_rows = two ? 128 : BN;       // rows of the K-major B box each CTA loads
-  CUtensorMap ta, tb, td;
+  CUtensorMap ta, tb, td, te;
   bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)
                      : make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, b_rows)
                        : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK));
   ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
+  ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
+                             : make_tmap(&te, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32));
   if (!ok) return 4;
 
   GemmParams p;
@@ -607,6 +652,7 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   p.b_mn = b_kmajor ? 0 : 1;
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
+  p.swiglu = act != nullptr ? 1 : 0;
   p.a_fmt = p.b_fmt = 0; p.scale = nullptr; p.scale_b = nullptr;
   p.tiles_n = (N + BN - 1) / BN;
   if (two) {
@@ -614,7 +660,7 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
     p.num_tiles = p.tiles_m * p.tiles_n;
     int clusters = g_num_sms / 2;
     if (p.num_tiles < clusters) clusters = p.num_tiles;
-    gemm_tcgen05_2cta_kernel<false><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
+    gemm_tcgen05_2cta_kernel<false><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, te, p);
   } else {
     p.tiles_m = (M + BM - 1) / BM;
     p.num_tiles = p.tiles_m * p.tiles_n;
@@ -631,7 +677,8 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
 // D[M,N] (+)= scale * (A . B) with fp8 (e4m3 / e5m2) operands, fp32 accumulation, bf16 output.
 int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, int K, int lda,
                      int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,
-                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s) {
+                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s,
+                     bf16* act, int ld_act) {
   std::call_once(g_once, init_once);
   if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
   if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
@@ -641,12 +688,18 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
     g_err = "fp8 operands need 16-byte aligned pointers / leading dimensions and M,N,K % 16 == 0";
     return 3;
   }
-  CUtensorMap ta, tb, td;
+  if (act != nullptr && (accumulate || !al16(act) || (ld_act % 8) || (N % 128))) {
+    g_err = "swiglu epilogue: needs N % 128 == 0, a 16-byte aligned second output and no accumulation";
+    return 3;
+  }
+  CUtensorMap ta, tb, td, te;
   bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 128, 128, 1)
                      : make_tmap(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 128, 1);
   ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 128, 128, 1)
                        : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 128, 128, 1));
   ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
+  ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
+                             : make_tmap(&te, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32));
   if (!ok) return 4;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -654,13 +707,14 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
   p.b_mn = b_kmajor ? 0 : 1;
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
+  p.swiglu = act != nullptr ? 1 : 0;
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = dequant_a; p.scale_b = dequant_b;
   p.tiles_n = (N + BN - 1) / BN;
   p.tiles_m = (M + 255) / 256;
   p.num_tiles = p.tiles_m * p.tiles_n;
   int clusters = g_num_sms / 2;
   if (p.num_tiles < clusters) clusters = p.num_tiles;
-  gemm_tcgen05_2cta_kernel<true><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, p);
+  gemm_tcgen05_2cta_kernel<true><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, te, p);
   count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }

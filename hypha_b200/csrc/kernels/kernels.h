@@ -94,13 +94,16 @@ void bf16_to_master(const bf16* p, float* master, int64_t n, cudaStream_t s);
 //  a_kmajor: A stored [M,K] (K contiguous) else stored [K,M]
 //  b_kmajor: B stored [N,K] (K contiguous) else stored [K,N]
 // lda/ldb/ldd are row strides (elements) of the stored matrices.
+// `act` (optional): SwiGLU epilogue -- the N output columns interleave (gate, up) pairs and the kernel ALSO writes
+// silu(gate) * up to act[M, N/2] (row stride ld_act), computed from the bf16-rounded pair.
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
-                      cudaStream_t s);
+                      cudaStream_t s, bf16* act = nullptr, int ld_act = 0);
 // fp8 (kind::f8f6f4): D (+)= (*dequant_a * *dequant_b) * (A . B); formats 0 = e4m3, 1 = e5m2.
 int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, int K, int lda,
                      int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,
-                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s);
+                     const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s,
+                     bf16* act = nullptr, int ld_act = 0);
 void amax_bf16(const bf16* x, int64_t n, float* amax, cudaStream_t s);
 void quantize_fp8(const bf16* x, uint8_t* out, int64_t n, const float* amax, float* dequant, int fmt,
                   cudaStream_t s);

@@ -179,8 +179,10 @@ class LlamaBlock(nn.Module):
         qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim, grad_inplace=True)
         att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
         o = ops.linear(att, self.wo)
-        gu, res = ops.add_norm_linear(o, res, self.norm2, self.wgu, c.rms_eps)
-        down = ops.swiglu_linear(gu, self.wdown)
+        # the gate_up GEMM's epilogue emits silu(gate) * up next to gate|up (interleaved columns)
+        act = torch.empty((o.shape[0], c.intermediate_size), dtype=o.dtype, device=o.device) if o.is_cuda else None
+        gu, res = ops.add_norm_linear(o, res, self.norm2, self.wgu, c.rms_eps, swiglu_out=act)
+        down = ops.swiglu_linear(gu, self.wdown, act=act)
         return down, res
 
 
@@ -296,8 +298,8 @@ class LlamaForCausalLM(nn.Module):
                                                    sd[pre + "self_attn.k_proj.weight"],
                                                    sd[pre + "self_attn.v_proj.weight"]], 0))
             P[f"layers.{l}.wo"].copy_(sd[pre + "self_attn.o_proj.weight"])
-            P[f"layers.{l}.wgu"].copy_(torch.cat([sd[pre + "mlp.gate_proj.weight"],
-                                                  sd[pre + "mlp.up_proj.weight"]], 0))
+            P[f"layers.{l}.wgu"].copy_(ops.interleave_gate_up(sd[pre + "mlp.gate_proj.weight"],
+                                                              sd[pre + "mlp.up_proj.weight"]))
             P[f"layers.{l}.wdown"].copy_(sd[pre + "mlp.down_proj.weight"])
             P[f"layers.{l}.norm1"].copy_(sd[pre + "input_layernorm.weight"])
             P[f"layers.{l}.norm2"].copy_(sd[pre + "post_attention_layernorm.weight"])
@@ -314,8 +316,7 @@ class LlamaForCausalLM(nn.Module):
             sd[pre + "self_attn.k_proj.weight"] = wqkv[qd: qd + kd]
             sd[pre + "self_attn.v_proj.weight"] = wqkv[qd + kd:]
             sd[pre + "self_attn.o_proj.weight"] = P[f"layers.{l}.wo"].detach()
-            sd[pre + "mlp.gate_proj.weight"] = wgu[: c.intermediate_size]
-            sd[pre + "mlp.up_proj.weight"] = wgu[c.intermediate_size:]
+            sd[pre + "mlp.gate_proj.weight"], sd[pre + "mlp.up_proj.weight"] = ops.split_gate_up(wgu)
             sd[pre + "mlp.down_proj.weight"] = P[f"layers.{l}.wdown"].detach()
             sd[pre + "input_layernorm.weight"] = P[f"layers.{l}.norm1"].detach()
             sd[pre + "post_attention_layernorm.weight"] = P[f"layers.{l}.norm2"].detach()

@@ -79,11 +79,14 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
 # GEMM
 # -----------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
-         out: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, accumulate: bool = False,
+         swiglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``D[M,N] (+)= A . B`` without materialising transposes.
 
     ``a_kmajor``: ``a`` is stored ``[M, K]`` else ``[K, M]``;
     ``b_kmajor``: ``b`` is stored ``[N, K]`` else ``[K, N]`` (row-major, unit inner stride).
+    ``swiglu_out`` ``[M, N/2]``: the GEMM epilogue also writes ``silu(D[:, 2i]) * D[:, 2i+1]`` there (fused
+    SwiGLU on interleaved gate/up columns; tcgen05 2-CTA kernel, N % 128 == 0).
     """
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
@@ -99,10 +102,14 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
                   and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and out.stride(0) % 8 == 0
                   and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
                   and out.data_ptr() % 16 == 0)
+    fuse = swiglu_out is not None and use_native and N % 128 == 0 and not accumulate
     if use_native:
         load_C().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0),
                            b.stride(0), out.stride(0), int(a_kmajor), int(b_kmajor),
-                           int(accumulate), cuda_stream())
+                           int(accumulate), cuda_stream(), swiglu_out.data_ptr() if fuse else 0,
+                           swiglu_out.stride(0) if fuse else 0)
+        if swiglu_out is not None and not fuse:
+            load_C().swiglu_fwd(out.data_ptr(), swiglu_out.data_ptr(), M, N // 2, cuda_stream())
         return out
     if a.is_cuda and _GEMM_BACKEND == "tcgen05":
         _note_fallback("gemm", f"operands not 16-byte aligned / multiple of 8 (M={M} N={N} K={K}, dtypes "
@@ -113,6 +120,8 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
         out.addmm_(A, B)
     else:
         torch.mm(A, B, out=out)
+    if swiglu_out is not None:
+        swiglu_out.copy_(swiglu(out))
     return out
 
 
@@ -172,8 +181,8 @@ def _weight_fp8(weight: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def gemm_fp8(aq: torch.Tensor, a_dq: torch.Tensor, bq: torch.Tensor, b_dq: torch.Tensor, *, a_kmajor: bool = True,
              b_kmajor: bool = True, a_fmt: int = E4M3, b_fmt: int = E4M3, out: Optional[torch.Tensor] = None,
-             accumulate: bool = False) -> torch.Tensor:
-    """``D (+)= dq_a*dq_b * (A . B)`` with uint8-stored fp8 operands -> bf16."""
+             accumulate: bool = False, swiglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``D (+)= dq_a*dq_b * (A . B)`` with uint8-stored fp8 operands -> bf16 (``swiglu_out``: see `gemm`)."""
     M, K = (aq.shape[0], aq.shape[1]) if a_kmajor else (aq.shape[1], aq.shape[0])
     N, Kb = (bq.shape[0], bq.shape[1]) if b_kmajor else (bq.shape[1], bq.shape[0])
     assert K == Kb
@@ -182,7 +191,11 @@ def gemm_fp8(aq: torch.Tensor, a_dq: torch.Tensor, bq: torch.Tensor, b_dq: torch
         accumulate = False
     load_C().gemm_fp8(aq.data_ptr(), bq.data_ptr(), out.data_ptr(), M, N, K, aq.stride(0), bq.stride(0),
                       out.stride(0), int(a_kmajor), int(b_kmajor), a_fmt, b_fmt, a_dq.data_ptr(), b_dq.data_ptr(),
-                      int(accumulate), cuda_stream())
+                      int(accumulate), cuda_stream(),
+                      swiglu_out.data_ptr() if (swiglu_out is not None and N % 128 == 0 and not accumulate) else 0,
+                      swiglu_out.stride(0) if swiglu_out is not None else 0)
+    if swiglu_out is not None and not (N % 128 == 0 and not accumulate):
+        load_C().swiglu_fwd(out.data_ptr(), swiglu_out.data_ptr(), M, N // 2, cuda_stream())
     return out
 
 
@@ -191,13 +204,13 @@ def _fp8_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
             and x2.shape[1] % 16 == 0 and weight.shape[0] % 16 == 0)
 
 
-def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """y = x2 @ weight.T on the bf16 or fp8 tensor-core path."""
+def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor, swiglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x2 @ weight.T on the bf16 or fp8 tensor-core path (``swiglu_out``: fused SwiGLU epilogue, see `gemm`)."""
     if _fp8_ok(x2, weight):
         xq, xdq = quantize_fp8(x2, E4M3)
         wq, wdq = _weight_fp8(weight)
-        return gemm_fp8(xq, xdq, wq, wdq)
-    return gemm(x2, weight)
+        return gemm_fp8(xq, xdq, wq, wdq, swiglu_out=swiglu_out)
+    return gemm(x2, weight, swiglu_out=swiglu_out)
 
 
 def _mm_bwd(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor, need_dx: bool = True,
@@ -364,7 +377,7 @@ def add_rmsnorm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor,
     return _AddRMSNorm.apply(x, residual, weight, eps)
 
 
-def _norm_linear_fwd(x, residual, norm_w, weight, eps):
+def _norm_linear_fwd(x, residual, norm_w, weight, eps, act_out=None):
     C = load_C()
     rows, cols = x.shape
     n = torch.empty_like(x)
@@ -377,7 +390,7 @@ def _norm_linear_fwd(x, residual, norm_w, weight, eps):
         h = x
         C.rmsnorm_fwd(x.data_ptr(), 0, 0, norm_w.data_ptr(), n.data_ptr(), rstd.data_ptr(), rows, cols, eps,
                       cuda_stream())
-    return _mm_fwd(n, weight), h, rstd
+    return _mm_fwd(n, weight, act_out), h, rstd
 
 
 def _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, eps):
@@ -410,8 +423,8 @@ class _AddNormLinear(torch.autograd.Function):
     norm per layer.  Returns ``(y, h)``."""
 
     @staticmethod
-    def forward(ctx, x, residual, norm_w, weight, eps):
-        y, h, rstd = _norm_linear_fwd(x, residual, norm_w, weight, eps)
+    def forward(ctx, x, residual, norm_w, weight, eps, act_out=None):
+        y, h, rstd = _norm_linear_fwd(x, residual, norm_w, weight, eps, act_out)
         ctx.save_for_backward(h, rstd, norm_w, weight)
         ctx.eps = eps
         return y, h
@@ -420,15 +433,15 @@ class _AddNormLinear(torch.autograd.Function):
     def backward(ctx, dy, dh):
         h, rstd, norm_w, weight = ctx.saved_tensors
         dx, dnw, dw = _norm_linear_bwd(dy, dh, h, rstd, norm_w, weight, ctx.eps)
-        return dx, dx, dnw, dw, None
+        return dx, dx, dnw, dw, None, None
 
 
 class _NormLinear(torch.autograd.Function):
     """``y = rmsnorm(x) @ W^T`` (no residual input); same recompute policy as ``_AddNormLinear``."""
 
     @staticmethod
-    def forward(ctx, x, norm_w, weight, eps):
-        y, _, rstd = _norm_linear_fwd(x, None, norm_w, weight, eps)
+    def forward(ctx, x, norm_w, weight, eps, act_out=None):
+        y, _, rstd = _norm_linear_fwd(x, None, norm_w, weight, eps, act_out)
         ctx.save_for_backward(x, rstd, norm_w, weight)
         ctx.eps = eps
         return y
@@ -437,29 +450,38 @@ class _NormLinear(torch.autograd.Function):
     def backward(ctx, dy):
         x, rstd, norm_w, weight = ctx.saved_tensors
         dx, dnw, dw = _norm_linear_bwd(dy, None, x, rstd, norm_w, weight, ctx.eps)
-        return dx, dnw, dw, None
+        return dx, dnw, dw, None, None
 
 
 def add_norm_linear(x: torch.Tensor, residual: Optional[torch.Tensor], norm_w: torch.Tensor,
-                    weight: torch.Tensor, eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
-    """``h = x + residual`` (or ``x``), ``y = rmsnorm(h) * norm_w @ weight.T``; returns ``(y, h)``."""
+                    weight: torch.Tensor, eps: float = 1e-5, swiglu_out: Optional[torch.Tensor] = None
+                    ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``h = x + residual`` (or ``x``), ``y = rmsnorm(h) * norm_w @ weight.T``; returns ``(y, h)``.
+
+    ``swiglu_out`` (``[rows, out_features/2]``, no autograd): when ``weight`` is an interleaved gate_up
+    projection the GEMM epilogue also writes ``silu(gate) * up`` there, which `swiglu_linear(..., act=...)`
+    then consumes instead of launching the SwiGLU kernel (the gradient still flows through ``y``)."""
     if not x.is_cuda:
         h = x if residual is None else (x.float() + residual.float()).to(x.dtype)
-        return F.linear(_rmsnorm_ref(h, norm_w, eps), weight), h
+        y = F.linear(_rmsnorm_ref(h, norm_w, eps), weight)
+        if swiglu_out is not None:
+            swiglu_out.copy_(swiglu(y.detach()))
+        return y, h
     assert x.dim() == 2 and x.is_contiguous()
     if residual is None:
-        return _NormLinear.apply(x, norm_w, weight, eps), x
-    return _AddNormLinear.apply(x, residual, norm_w, weight, eps)
+        return _NormLinear.apply(x, norm_w, weight, eps, swiglu_out), x
+    return _AddNormLinear.apply(x, residual, norm_w, weight, eps, swiglu_out)
 
 
 class _SwiGLULinear(torch.autograd.Function):
     """``y = (silu(g) * u) @ W^T`` on a fused gate|up activation, saving only ``gu``."""
 
     @staticmethod
-    def forward(ctx, gu, weight):
+    def forward(ctx, gu, weight, act=None):
         rows, two_i = gu.shape
-        act = torch.empty((rows, two_i // 2), dtype=gu.dtype, device=gu.device)
-        load_C().swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, two_i // 2, cuda_stream())
+        if act is None:            # not produced by the gate_up GEMM's epilogue: one memory-bound launch
+            act = torch.empty((rows, two_i // 2), dtype=gu.dtype, device=gu.device)
+            load_C().swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, two_i // 2, cuda_stream())
         y = _mm_fwd(act, weight)
         ctx.save_for_backward(gu, weight)
         return y
@@ -480,15 +502,25 @@ class _SwiGLULinear(torch.autograd.Function):
             dact, dw = _mm_bwd(dy2, act, weight, dx_out=act)
         dgu = torch.empty_like(gu)
         C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
-        return dgu, dw
+        return dgu, dw, None
 
 
-def swiglu_linear(gu: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
-    """``(silu(gate) * up) @ weight.T`` with the activation recomputed in backward."""
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor) -> torch.Tensor:
+    """``[2I, H]`` fused weight with rows ``gate_0, up_0, gate_1, up_1, ...`` from HF-style gate / up ``[I, H]``."""
+    return torch.stack([gate, up], dim=1).reshape(2 * gate.shape[0], *gate.shape[1:])
+
+
+def split_gate_up(wgu: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    return wgu[0::2], wgu[1::2]
+
+
+def swiglu_linear(gu: torch.Tensor, weight: torch.Tensor, act: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``(silu(gate) * up) @ weight.T`` with the activation recomputed in backward.  ``act``: the activation
+    already computed by the producing GEMM's epilogue (`add_norm_linear(..., swiglu_out=act)`)."""
     if not gu.is_cuda:
         return F.linear(swiglu(gu), weight)
     assert gu.dim() == 2 and gu.is_contiguous()
-    return _SwiGLULinear.apply(gu, weight)
+    return _SwiGLULinear.apply(gu, weight, act)
 
 
 # -----------------------------------------------------------------------------
@@ -571,9 +603,12 @@ class _SwiGLU(torch.autograd.Function):
 
 
 def swiglu(gu: torch.Tensor) -> torch.Tensor:
-    """``silu(gate) * up`` on a fused ``[rows, 2*I]`` (gate | up) activation."""
+    """``silu(gate) * up`` on a fused ``[rows, 2*I]`` activation whose columns INTERLEAVE gate and up
+    (``gu[:, 2i] = gate_i``, ``gu[:, 2i+1] = up_i``; the rows of the fused gate_up weight are interleaved the
+    same way -- ``interleave_gate_up`` -- so that a 256-wide GEMM tile holds whole pairs and the GEMM epilogue
+    can apply the activation itself)."""
     if not gu.is_cuda:
-        g, u = gu.chunk(2, dim=-1)
+        g, u = gu[..., 0::2], gu[..., 1::2]
         return (F.silu(g.float()) * u.float()).to(gu.dtype)
     assert gu.dim() == 2 and gu.is_contiguous()
     return _SwiGLU.apply(gu)

@@ -59,6 +59,26 @@ def test_gemm_accumulate(C):
     assert _rel(out, ref) < 5e-3
 
 
+def test_gemm_swiglu_epilogue(C):
+    """The gate_up GEMM's fused epilogue: silu(gate) * up on interleaved columns, computed from the bf16-rounded
+    pair -> bit-identical to the stand-alone SwiGLU kernel applied to the GEMM's own output."""
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    for M, N, K in ((512, 1024, 256), (300, 256, 128), (8192, 28672, 4096)):
+        a = (0.5 * torch.randn(M, K, device="cuda")).to(torch.bfloat16)
+        w = (0.05 * torch.randn(N, K, device="cuda")).to(torch.bfloat16)
+        act = torch.full((M, N // 2), 7.0, device="cuda", dtype=torch.bfloat16)
+        gu = ops.gemm(a, w, swiglu_out=act)
+        ref_gu = ops.gemm(a, w)
+        assert torch.equal(gu, ref_gu)
+        ref_act = ops.swiglu(ref_gu)
+        assert torch.equal(act, ref_act), (M, N, K, (act.float() - ref_act.float()).abs().max().item())
+        if M * N < 1e7:
+            g, u = ref_gu.float()[:, 0::2], ref_gu.float()[:, 1::2]
+            assert _rel(act, torch.nn.functional.silu(g) * u) < 1e-2
+
+
 def test_gemm_strided_views(C):
     """lda/ldb/ldd larger than the logical width (views into fused buffers)."""
     from hypha_b200 import ops
@@ -139,7 +159,7 @@ def test_add_norm_linear_and_swiglu_linear(C):
     do = torch.randn_like(out)
     out.backward(do)
     gf, Wdf = gu.detach().float().requires_grad_(True), Wd.detach().float().requires_grad_(True)
-    g, u = gf.chunk(2, -1)
+    g, u = gf[..., 0::2], gf[..., 1::2]           # interleaved gate | up columns
     of = (torch.nn.functional.silu(g) * u) @ Wdf.t()
     of.backward(do.float())
     assert _rel(out, of) < 2e-2 and _rel(gu.grad, gf.grad) < 2e-2 and _rel(Wd.grad, Wdf.grad) < 2e-2
@@ -174,7 +194,7 @@ def test_swiglu(C):
     d = torch.randn_like(out)
     out.backward(d)
     gf = gu.detach().float().requires_grad_(True)
-    g, u = gf.chunk(2, -1)
+    g, u = gf[..., 0::2], gf[..., 1::2]           # interleaved gate | up columns
     of = torch.nn.functional.silu(g) * u
     of.backward(d.float())
     assert _rel(out, of) < 1e-2 and _rel(gu.grad, gf.grad) < 1e-2
