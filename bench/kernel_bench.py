@@ -99,6 +99,17 @@ def main():
     ms_fused = time_fn(lambda i: ops.gemm(xa, wgu, out=gu_o, swiglu_out=act_o))
     res["swiglu_epilogue"] = {"gemm_ms": ms_plain, "gemm_plus_swiglu_kernel_ms": ms_sep, "fused_ms": ms_fused}
     print(json.dumps(res["swiglu_epilogue"]), flush=True)
+    # down-projection dgrad with and without the fused SwiGLU-backward epilogue
+    dyd = torch.randn(T, h, device="cuda", dtype=torch.bfloat16)
+    wd = (0.02 * torch.randn(h, inter, device="cuda")).to(torch.bfloat16)
+    dgu_o = torch.empty_like(gu_o)
+    sb = torch.cuda.current_stream().cuda_stream
+    ms_plain = time_fn(lambda i: ops.gemm(dyd, wd, a_kmajor=True, b_kmajor=False, out=act_o))
+    ms_sep = time_fn(lambda i: (ops.gemm(dyd, wd, a_kmajor=True, b_kmajor=False, out=act_o),
+                                C.swiglu_bwd(act_o.data_ptr(), gu_o.data_ptr(), dgu_o.data_ptr(), T, inter, sb)))
+    ms_fused = time_fn(lambda i: ops.gemm(dyd, wd, a_kmajor=True, b_kmajor=False, out=act_o, dswiglu=(gu_o, dgu_o)))
+    res["dswiglu_epilogue"] = {"dgrad_ms": ms_plain, "dgrad_plus_swiglu_bwd_kernel_ms": ms_sep, "fused_ms": ms_fused}
+    print(json.dumps(res["dswiglu_epilogue"]), flush=True)
     ops.set_gemm_backend("tcgen05")
 
     # ---- memory-bound kernels ---------------------------------------------------------------

@@ -167,13 +167,14 @@ PYBIND11_MODULE(_C, m) {
   });
 
   m.def("gemm_bf16", [](u64 A, u64 B, u64 D, int M, int N, int K, int lda, int ldb, int ldd,
-                        int a_kmajor, int b_kmajor, int accumulate, u64 s, u64 act, int ld_act) {
+                        int a_kmajor, int b_kmajor, int accumulate, u64 s, u64 act, int ld_act, u64 gu, int ld_gu) {
     int rc = hb::gemm_bf16_tcgen05(P<const bf16>(A), P<const bf16>(B), P<bf16>(D), M, N, K, lda,
-                                   ldb, ldd, a_kmajor, b_kmajor, accumulate, S(s), P<bf16>(act), ld_act);
+                                   ldb, ldd, a_kmajor, b_kmajor, accumulate, S(s), P<bf16>(act), ld_act,
+                                   P<const bf16>(gu), ld_gu);
     if (rc != 0) throw std::runtime_error(std::string("gemm_bf16_tcgen05: ") + hb::gemm_last_error());
   }, py::arg("A"), py::arg("B"), py::arg("D"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("lda"),
      py::arg("ldb"), py::arg("ldd"), py::arg("a_kmajor"), py::arg("b_kmajor"), py::arg("accumulate"), py::arg("s"),
-     py::arg("act") = 0, py::arg("ld_act") = 0);
+     py::arg("act") = 0, py::arg("ld_act") = 0, py::arg("gu") = 0, py::arg("ld_gu") = 0);
 
   m.def("attention_fwd", [](u64 qkv, u64 out, u64 lse, int batch, int seq, int n_heads, int n_kv, int head_dim,
                             int qkv_stride, int out_stride, float scale, u64 s) {

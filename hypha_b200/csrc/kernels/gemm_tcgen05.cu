@@ -62,6 +62,8 @@ struct GemmParams {
   const float* scale;      // fp8 only: device dequantisation factor of A
   const float* scale_b;    // fp8 only: device dequantisation factor of B
   int swiglu;              // 2-CTA kernel: the output columns interleave gate/up; ALSO store silu(gate)*up through tma_e
+  const bf16* gu;          // 2-CTA kernel, dswiglu epilogue: D is NOT written; instead the [M, N] accumulator is taken as
+  int ld_gu;               // d(act) and d(gate|up)[M, 2N] = swiglu'(gu) * d(act) leaves through tma_e (interleaved columns)
 };
 
 __device__ __forceinline__ void tile_coords(int t, const GemmParams& p, int& tm, int& tn) {
@@ -463,6 +465,59 @@ uint32_t actp[32];
           if (lane == 0) mbar_arrive_remote(mapa_shared(tempty_bar(acc), 0));
         }
         const int col0 = n0 + c * 64;
+        if (p.gu != nullptr) {
+          // Fused SwiGLU backward (down-projection dgrad): this chunk holds d(act) for 64 activations of 32 rows;
+          // with the (gate, up) pairs read straight from gu (256 contiguous bytes per row and chunk) it becomes
+          // 128 interleaved d(gate), d(up) columns -- two 64-column stores through tma_e.  d(act) is rounded to
+          // bf16 first, so the result equals the stand-alone `swiglu_bwd_kernel` applied to the bf16 dgrad.
+          const bool row_ok = row < p.M;
+          const bf16* gp = p.gu + (size_t)row * p.ld_gu + 2 * (size_t)col0;
+          if (row_ok && c + 1 < BN / 64 && 2 * (col0 + 64) + 128 <= 2 * p.N) {
+            // the next chunk's (gate, up) pairs: start them on their way from HBM to L2 now
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 128));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 192));
+          }
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t outp[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {                       // 8 x 16 bytes of gu = 4 pairs each
+              float a[8];
+              bf16x8 gv = bf16x8{};
+              if (row_ok && 2 * col0 + hh * 64 + j * 8 + 8 <= 2 * p.N) gv = ld_bf16x8(gp + hh * 64 + j * 8);
+              unpack8(gv, a);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = hh * 32 + j * 4 + e;              // activation index inside the chunk (0..63)
+                const float dacc = __uint_as_float(i < 32 ? r0[i & 31] : r1[i & 31]) * out_scale;
+                const float d = __bfloat162float(__float2bfloat16_rn(dacc));
+                const float g = a[2 * e], u = a[2 * e + 1];
+                const float sg = __fdividef(1.f, 1.f + __expf(-g));
+                const float silu = g * sg;
+                __nv_bfloat162 h = __floats2bfloat162_rn(d * u * (sg + silu * (1.f - sg)), d * silu);
+                outp[j * 4 + e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+            }
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+            const uint32_t sbuf = epi_smem + buf * kEpiWarpBuf;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint32_t dst = sbuf + lane * 128 + ((j ^ (lane & 7)) << 4);
+              asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst), "r"(outp[4 * j]),
+                           "r"(outp[4 * j + 1]), "r"(outp[4 * j + 2]), "r"(outp[4 * j + 3])
+                           : "memory");
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (col0 < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_e, sbuf, 2 * col0 + hh * 64, m0 + ew * 32);
+              tma_store_commit();
+            }
+            buf ^= 1;
+          }
+          continue;
+        }
         uint32_t packed[32];
         if (p.accumulate) {
           const bool row_ok = row < p.M;
@@ -618,7 +673,7 @@ int gemm_get_cta_mode() { std::call_once(g_once, init_once); return g_mode; }
 
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
-                      cudaStream_t s, bf16* act, int ld_act) {
+                      cudaStream_t s, bf16* act, int ld_act, const bf16* gu, int ld_gu) {
   std::call_once(g_once, init_once);
   if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
   if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
@@ -630,11 +685,15 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   if ((a_kmajor || b_kmajor) && (K % 8)) { g_err = "K must be a multiple of 8"; return 3; }
   if (!a_kmajor && (M % 8)) { g_err = "MN-major A needs M % 8 == 0"; return 3; }
 
-  if (act != nullptr && (accumulate || !al16(act) || (ld_act % 8) || (N % 128))) {
+  if (act != nullptr && gu == nullptr && (accumulate || !al16(act) || (ld_act % 8) || (N % 128))) {
     g_err = "swiglu epilogue: needs N % 128 == 0, a 16-byte aligned second output and no accumulation";
     return 3;
   }
-  const bool two = (g_mode == 2) || act != nullptr;       // the fused epilogue lives in the 2-CTA kernel
+  if (gu != nullptr && (act == nullptr || accumulate || !al16(gu) || (ld_gu % 8) || (N % 64))) {
+    g_err = "dswiglu epilogue: needs the [M, 2N] output in `act`, N % 64 == 0, 16-byte aligned gu and no accumulation";
+    return 3;
+  }
+  const bool two = (g_mode == 2) || act != nullptr;       // the fused epilogues live in the 2-CTA kernel
   const uint32_t b_rows = two ? 128 : BN;       // rows of the K-major B box each CTA loads
   CUtensorMap ta, tb, td, te;
   bool ok = a_kmajor ? make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BK, BM)
@@ -642,7 +701,7 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   ok = ok && (b_kmajor ? make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BK, b_rows)
                        : make_tmap(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK));
   ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
-  ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
+  ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(gu != nullptr ? 2 * N : N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
                              : make_tmap(&te, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32));
   if (!ok) return 4;
 
@@ -652,7 +711,8 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
   p.b_mn = b_kmajor ? 0 : 1;
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
-  p.swiglu = act != nullptr ? 1 : 0;
+  p.swiglu = (act != nullptr && gu == nullptr) ? 1 : 0;
+  p.gu = gu; p.ld_gu = ld_gu;
   p.a_fmt = p.b_fmt = 0; p.scale = nullptr; p.scale_b = nullptr;
   p.tiles_n = (N + BN - 1) / BN;
   if (two) {
@@ -708,6 +768,7 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
   p.accumulate = accumulate;
   p.D = D; p.ldd = ldd;
   p.swiglu = act != nullptr ? 1 : 0;
+  p.gu = nullptr; p.ld_gu = 0;
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = dequant_a; p.scale_b = dequant_b;
   p.tiles_n = (N + BN - 1) / BN;
   p.tiles_m = (M + 255) / 256;

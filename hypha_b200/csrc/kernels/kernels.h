@@ -98,7 +98,9 @@ void bf16_to_master(const bf16* p, float* master, int64_t n, cudaStream_t s);
 // silu(gate) * up to act[M, N/2] (row stride ld_act), computed from the bf16-rounded pair.
 int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K, int lda,
                       int ldb, int ldd, int a_kmajor, int b_kmajor, int accumulate,
-                      cudaStream_t s, bf16* act = nullptr, int ld_act = 0);
+                      cudaStream_t s, bf16* act = nullptr, int ld_act = 0, const bf16* gu = nullptr, int ld_gu = 0);
+// `gu` (with `act`): SwiGLU-BACKWARD epilogue -- the [M, N] product is d(act); D is not written, act[M, 2N] receives
+// d(gate|up) = swiglu'(gu) * d(act) with interleaved columns (gu[M, 2N] is the forward's gate|up activation).
 // fp8 (kind::f8f6f4): D (+)= (*dequant_a * *dequant_b) * (A . B); formats 0 = e4m3, 1 = e5m2.
 int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, int K, int lda,
                      int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,

@@ -80,13 +80,16 @@ def _ptr(t: Optional[torch.Tensor]) -> int:
 # -----------------------------------------------------------------------------
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: bool = True,
          out: Optional[torch.Tensor] = None, accumulate: bool = False,
-         swiglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         swiglu_out: Optional[torch.Tensor] = None, dswiglu: Optional[Tuple[torch.Tensor, torch.Tensor]] = None
+         ) -> torch.Tensor:
     """``D[M,N] (+)= A . B`` without materialising transposes.
 
     ``a_kmajor``: ``a`` is stored ``[M, K]`` else ``[K, M]``;
     ``b_kmajor``: ``b`` is stored ``[N, K]`` else ``[K, N]`` (row-major, unit inner stride).
     ``swiglu_out`` ``[M, N/2]``: the GEMM epilogue also writes ``silu(D[:, 2i]) * D[:, 2i+1]`` there (fused
     SwiGLU on interleaved gate/up columns; tcgen05 2-CTA kernel, N % 128 == 0).
+    ``dswiglu = (gu, dgu)``: SwiGLU BACKWARD epilogue -- the product is d(act) (rounded to bf16, not stored unless
+    the fallback runs) and ``dgu[M, 2N] = swiglu'(gu) * d(act)`` is written instead; returns ``dgu``.
     """
     assert a.dim() == 2 and b.dim() == 2 and a.stride(1) == 1 and b.stride(1) == 1
     M, K = (a.shape[0], a.shape[1]) if a_kmajor else (a.shape[1], a.shape[0])
@@ -102,6 +105,21 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
                   and a.stride(0) % 8 == 0 and b.stride(0) % 8 == 0 and out.stride(0) % 8 == 0
                   and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
                   and out.data_ptr() % 16 == 0)
+    if dswiglu is not None:
+        gu_t, dgu_t = dswiglu
+        if (use_native and N % 64 == 0 and not accumulate and gu_t.stride(1) == 1 and gu_t.stride(0) % 8 == 0
+                and dgu_t.stride(1) == 1 and dgu_t.stride(0) % 8 == 0 and gu_t.data_ptr() % 16 == 0
+                and dgu_t.data_ptr() % 16 == 0):
+            load_C().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0), b.stride(0),
+                               out.stride(0), int(a_kmajor), int(b_kmajor), 0, cuda_stream(), dgu_t.data_ptr(),
+                               dgu_t.stride(0), gu_t.data_ptr(), gu_t.stride(0))
+            return dgu_t
+        dact = gemm(a, b, a_kmajor=a_kmajor, b_kmajor=b_kmajor, out=out, accumulate=accumulate)
+        if dact.is_cuda:
+            load_C().swiglu_bwd(dact.data_ptr(), gu_t.data_ptr(), dgu_t.data_ptr(), M, N, cuda_stream())
+        else:
+            raise RuntimeError("dswiglu epilogue is a CUDA path")
+        return dgu_t
     fuse = swiglu_out is not None and use_native and N % 128 == 0 and not accumulate
     if use_native:
         load_C().gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, a.stride(0),
@@ -496,12 +514,15 @@ class _SwiGLULinear(torch.autograd.Function):
         act = torch.empty((rows, inter), dtype=gu.dtype, device=gu.device)
         C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, inter, s)
         dy2 = dy if dy.is_contiguous() else dy.contiguous()
+        dgu = torch.empty_like(gu)
         if _fp8_ok(act, weight):
             dact, dw = _mm_bwd(dy2, act, weight)
+            C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
         else:
-            dact, dw = _mm_bwd(dy2, act, weight, dx_out=act)
-        dgu = torch.empty_like(gu)
-        C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
+            # wgrad consumes the recomputed activation; the dgrad GEMM's epilogue then turns its own product
+            # d(act) into d(gate|up) on the way out (no [rows, inter] round trip, no SwiGLU-backward launch)
+            _, dw = _mm_bwd(dy2, act, weight, need_dx=False)
+            gemm(dy2, weight, a_kmajor=True, b_kmajor=False, out=act, dswiglu=(gu, dgu))
         return dgu, dw, None
 
 

@@ -79,6 +79,25 @@ def test_gemm_swiglu_epilogue(C):
             assert _rel(act, torch.nn.functional.silu(g) * u) < 1e-2
 
 
+def test_gemm_dswiglu_epilogue(C):
+    """The down-projection dgrad with the fused SwiGLU-backward epilogue == dgrad GEMM + `swiglu_bwd` kernel."""
+    from hypha_b200 import ops
+    from hypha_b200.ops.native import cuda_stream
+
+    torch.manual_seed(0)
+    for T, I, H in ((512, 1024, 256), (300, 192, 128), (8192, 14336, 4096)):
+        dy = torch.randn(T, H, device="cuda").to(torch.bfloat16)
+        w = (0.05 * torch.randn(H, I, device="cuda")).to(torch.bfloat16)       # down projection [H, I]
+        gu = torch.randn(T, 2 * I, device="cuda").to(torch.bfloat16)
+        dact = ops.gemm(dy, w, a_kmajor=True, b_kmajor=False)
+        ref = torch.empty_like(gu)
+        C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), ref.data_ptr(), T, I, cuda_stream())
+        got = torch.full_like(gu, 3.0)
+        scratch = torch.empty(T, I, device="cuda", dtype=torch.bfloat16)
+        ops.gemm(dy, w, a_kmajor=True, b_kmajor=False, out=scratch, dswiglu=(gu, got))
+        assert torch.equal(got, ref), (T, I, H, (got.float() - ref.float()).abs().max().item())
+
+
 def test_gemm_strided_views(C):
     """lda/ldb/ldd larger than the logical width (views into fused buffers)."""
     from hypha_b200 import ops
