@@ -382,3 +382,41 @@ def test_process_executor_escalates_from_sigterm_to_sigkill(tmp_path, monkeypatc
     monkeypatch.setattr(J, "KILL_GRACE_S", 5.0)
     status, dt, logs, wd = asyncio.run(run(polite))
     assert dt < 3.0 and not os.path.exists(wd)                 # SIGTERM was enough: the grace period was not spent
+
+
+def test_binary_release_roundtrip(tmp_path):
+    """`tools/make_release.py` -> `install.sh --from-release`: the artefact carries the prebuilt extensions (no
+    sources of the native code), the installer verifies sha256 + manifest, unpacks and links launchers that run
+    WITHOUT the checkout on the path; a tampered archive is refused."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import tarfile
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "make_release.py"), "--out", str(tmp_path / "dist"),
+                          "--skip-cuda"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    info = json.loads(out.stdout.strip().splitlines()[-1])
+    names = tarfile.open(info["artefact"]).getnames()
+    assert any(n.endswith("MANIFEST.json") for n in names) and any("_core" in n and n.endswith(".so") for n in names)
+    assert not any("/csrc/" in n for n in names)
+    home = tmp_path / "home"
+    env = dict(os.environ, HOME=str(home), HYPHA_NO_MODIFY_PATH="1", HYPHA_PYTHON=sys.executable)
+    env.pop("PYTHONPATH", None)
+    r = subprocess.run(["sh", os.path.join(root, "install.sh"), "--from-release", info["artefact"]], env=env,
+                       capture_output=True, text=True, timeout=300, cwd=str(tmp_path))
+    assert r.returncode == 0 and "sha256 verified" in r.stdout, r.stdout + r.stderr
+    gw = home / ".local" / "bin" / "hypha-gateway"
+    r = subprocess.run([str(gw), "init", "-o", str(tmp_path / "gw.toml")], env=env, capture_output=True, text=True,
+                       timeout=120, cwd=str(tmp_path))
+    assert r.returncode == 0 and (tmp_path / "gw.toml").exists(), r.stderr
+    bad = tmp_path / "bad.tar.gz"
+    blob = bytearray(open(info["artefact"], "rb").read())
+    blob[len(blob) // 2] ^= 0xFF
+    bad.write_bytes(bytes(blob))
+    open(str(bad) + ".sha256", "w").write(open(info["artefact"] + ".sha256").read())
+    r = subprocess.run(["sh", os.path.join(root, "install.sh"), "--from-release", str(bad)], env=env, capture_output=True,
+                       text=True, timeout=120, cwd=str(tmp_path))
+    assert r.returncode != 0 and "sha256 mismatch" in (r.stdout + r.stderr)
