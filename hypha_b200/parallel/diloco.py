@@ -212,6 +212,9 @@ class DiLoCoOuter:
             self.theta_outer = opt.master.clone()
             self.momentum = torch.zeros(self.n, dtype=torch.float32, device=dev)
         elif backend == "fused":
+            if world > 8:
+                raise ValueError(f"the fused outer step covers one NVSwitch box (<= 8 ranks); got world = {world}: use "
+                                 f"backend='nccl' across boxes")
             assert group is not None and param_buf is not None and delta_buf is not None
             assert param_buf.local.data_ptr() == opt.params.data_ptr(), \
                 "fused outer step needs the model parameters in the symmetric buffer"

@@ -395,6 +395,24 @@ class Network:
         # rfc/2025-05-30_mtls.md): {"cert_pem": chain file, "key_pem": key file, "trust_pem": CA file,
         # "crls_pem": optional}.  memory:// and unix:// links rely on process / file-system isolation.
         self.tls = tls if tls and tls.get("cert_pem") and tls.get("key_pem") and tls.get("trust_pem") else None
+        # Signed gossip (the reference's gossipsub runs MessageAuthenticity::Signed, crates/scheduler/src/network.rs:133):
+        # a node with a key signs what it publishes; a node in strict mode (= mTLS configured) drops messages that are
+        # unsigned, signed by a key that is not the claimed origin's, or altered -- a relaying peer cannot forge an ad.
+        self._sign_key = None
+        self._pub_raw = b""
+        self.gossip_rejections = 0
+        if tls and tls.get("key_pem"):
+            try:
+                from cryptography.hazmat.primitives import serialization
+                from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PrivateKey
+
+                key = serialization.load_pem_private_key(open(tls["key_pem"], "rb").read(), password=None)
+                if isinstance(key, Ed25519PrivateKey):
+                    self._sign_key = key
+                    self._pub_raw = key.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
+            except Exception:
+                self._sign_key = None
+        self.strict_gossip = self.tls is not None and self._sign_key is not None
         self.agent = agent
         self.relay_server = relay_server
         self.dht_server = dht_server
@@ -821,6 +839,9 @@ class Network:
         (an isolated peer cannot publish, gossipsub_test.rs:297)."""
         frame = {"t": "pub", "topic": topic, "mid": uuid.uuid4().hex, "origin": self.peer_id, "data": data,
                  "proto": "/meshsub/1.1.0"}
+        if self._sign_key is not None:
+            frame["key"] = self._pub_raw
+            frame["sig"] = self._sign_key.sign(self._gossip_digest(frame))
         self._seen_msgs[frame["mid"]] = time.monotonic()
         n = await self._forward_pub(frame, exclude=None)
         if n == 0:
@@ -841,9 +862,42 @@ class Network:
                     pass
         return sent
 
+    @staticmethod
+    def _gossip_digest(frame: dict) -> bytes:
+        import hashlib
+
+        h = hashlib.sha256()
+        for part in (b"hypha-gossip-v1", frame["topic"].encode(), frame["mid"].encode(), frame["origin"].encode(),
+                     bytes(frame["data"])):
+            h.update(len(part).to_bytes(4, "little"))
+            h.update(part)
+        return h.digest()
+
+    def _gossip_authentic(self, frame: dict) -> bool:
+        """True iff the message carries a valid Ed25519 signature by the key the claimed origin's peer id is
+        derived from.  Unsigned messages pass only outside strict mode (no PKI configured: loopback boxes)."""
+        sig, key = frame.get("sig"), frame.get("key")
+        if not sig or not key:
+            return not self.strict_gossip
+        try:
+            from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PublicKey
+
+            from .utils import peer_id_from_public_bytes
+
+            if peer_id_from_public_bytes(bytes(key)) != frame["origin"]:
+                return False
+            Ed25519PublicKey.from_public_bytes(bytes(key)).verify(bytes(sig), self._gossip_digest(frame))
+            return True
+        except Exception:
+            return False
+
     async def _on_publish(self, frame: dict, src: str) -> None:
         mid = frame["mid"]
         if mid in self._seen_msgs:
+            return
+        if not self._gossip_authentic(frame):
+            self.gossip_rejections += 1
+            self._seen_msgs[mid] = time.monotonic()      # do not verify (or forward) the same forgery again
             return
         now = time.monotonic()
         self._seen_msgs[mid] = now

@@ -649,3 +649,49 @@ def test_unconsumed_stream_does_not_stall_the_link(tmp_path):
             await n.close()
 
     asyncio.run(main())
+
+
+def test_gossip_is_signed_and_forgeries_are_dropped(tmp_path):
+    """Gossip carries an Ed25519 signature of (topic, id, origin, payload) by the origin's key (the reference runs
+    gossipsub with MessageAuthenticity::Signed).  A relaying peer that alters the payload, or publishes in
+    somebody else's name, is ignored by nodes with a PKI; honest messages still arrive through the relay."""
+    from hypha_b200 import certutil
+    from hypha_b200.transport.network import Network
+    from hypha_b200.transport.utils import peer_id_from_key_pem as pid
+
+    d = str(tmp_path)
+    rc, rk = certutil.make_root("Acme", out_dir=d)
+    oc, ok = certutil.make_org(rc, rk, "Acme", name="acme-org", out_dir=d)
+    tls = {}
+    for n in ("gw", "sched", "worker", "mallory"):
+        c, k, t = certutil.make_node(oc, ok, n, sans=("127.0.0.1",), out_dir=d)
+        tls[n] = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+    ids = {n: pid(v["key_pem"]) for n, v in tls.items()}
+
+    async def main():
+        gw = Network(ids["gw"], tls=tls["gw"], relay_server=True, dht_server=True)
+        addr = await gw.listen("tcp://127.0.0.1:0")
+        sched, worker, mal = (Network(ids[n], tls=tls[n]) for n in ("sched", "worker", "mallory"))
+        for n in (sched, worker, mal):
+            await n.dial(addr)
+        sub = await worker.subscribe("hypha/worker")
+        await asyncio.sleep(0.2)
+        assert await sched.publish("hypha/worker", b"ad-1") >= 1
+        assert await sub.get(timeout=2.0) == (ids["sched"], b"ad-1")
+        # mallory (a legitimate member of the PKI) forges an ad in the scheduler's name ...
+        link = mal.links[ids["gw"]]
+        forged = {"t": "pub", "topic": "hypha/worker", "mid": "f" * 32, "origin": ids["sched"], "data": b"ad-forged",
+                  "proto": "/meshsub/1.1.0", "key": mal._pub_raw}
+        forged["sig"] = mal._sign_key.sign(Network._gossip_digest(forged))
+        await link.send(forged)
+        # ... replays a signed ad with another payload, and sends an unsigned one
+        await link.send({"t": "pub", "topic": "hypha/worker", "mid": "e" * 32, "origin": ids["mallory"], "data": b"unsigned",
+                         "proto": "/meshsub/1.1.0"})
+        await asyncio.sleep(0.4)
+        assert gw.gossip_rejections == 2 and sub.q.empty()
+        assert await mal.publish("hypha/worker", b"honest") >= 1            # her own signed messages are fine
+        assert await sub.get(timeout=2.0) == (ids["mallory"], b"honest")
+        for n in (gw, sched, worker, mal):
+            await n.close()
+
+    asyncio.run(main())
