@@ -130,6 +130,7 @@ def build_cuda(verbose: bool = False) -> Path:
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda s: _compile(s, "cu", verbose), srcs))
     objs.append(_compile(CSRC / "comm" / "peer_mem.cpp", "cpp", verbose))
+    objs.append(_compile(CSRC / "comm" / "vmm.cpp", "cpp", verbose))
     objs.append(_compile(CSRC / "bindings.cpp", "cpp", verbose))
     stamp = BUILD / "_C.stamp"
     key = ",".join(o.name for o in objs)

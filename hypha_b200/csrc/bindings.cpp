@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "comm/peer_mem.h"
+#include "comm/vmm.h"
 #include "kernels/kernels.h"
 
 namespace py = pybind11;
@@ -214,6 +215,20 @@ PYBIND11_MODULE(_C, m) {
   }, py::arg("A"), py::arg("B"), py::arg("D"), py::arg("M"), py::arg("N"), py::arg("K"), py::arg("lda"),
      py::arg("ldb"), py::arg("ldd"), py::arg("a_kmajor"), py::arg("b_kmajor"), py::arg("a_fmt"), py::arg("b_fmt"),
      py::arg("dq_a"), py::arg("dq_b"), py::arg("accumulate"), py::arg("s"), py::arg("act") = 0, py::arg("ld_act") = 0);
+  m.def("gemm_mxfp8", [](u64 A, u64 sfa, u64 B, u64 sfb, u64 D, int M, int N, int K, int lda, int ldb, int ldd, int a_fmt,
+                         int b_fmt, int accumulate, u64 s, u64 act, int ld_act, u64 gu, int ld_gu) {
+    int rc = hb::gemm_mxfp8_tcgen05(P<const uint8_t>(A), P<const uint8_t>(sfa), P<const uint8_t>(B), P<const uint8_t>(sfb),
+                                    P<bf16>(D), M, N, K, lda, ldb, ldd, a_fmt, b_fmt, accumulate, S(s), P<bf16>(act),
+                                    ld_act, P<const bf16>(gu), ld_gu);
+    if (rc != 0) throw std::runtime_error(std::string("gemm_mxfp8_tcgen05: ") + hb::gemm_last_error());
+    check_last("gemm_mxfp8");
+  });
+  m.def("quantize_mxfp8", [](u64 x, int ldx, u64 q, int ldq, u64 sf, u64 qT, int ldqT, u64 sfT, int R, int C, u64 s) {
+    int rc = hb::quantize_mxfp8(P<const bf16>(x), ldx, P<uint8_t>(q), ldq, P<uint8_t>(sf), P<uint8_t>(qT), ldqT,
+                                P<uint8_t>(sfT), R, C, S(s));
+    if (rc != 0) throw std::runtime_error("quantize_mxfp8: needs R, C % 128 == 0, 16-byte aligned pitches, an output pair");
+    check_last("quantize_mxfp8");
+  });
   m.def("amax_bf16", [](u64 x, int64_t n, u64 amax, u64 s) {
     hb::amax_bf16(P<const bf16>(x), n, P<float>(amax), S(s));
     check_last("amax_bf16");
@@ -235,4 +250,49 @@ PYBIND11_MODULE(_C, m) {
   m.def("sym_bytes_allocated", &hb::comm::bytes_allocated);
   m.def("memcpy_d2d_async", &hb::comm::memcpy_d2d_async);
   m.def("memset_async", &hb::comm::memset_async);
+
+  // ---- VMM / NVSwitch multicast / descriptor passing / membership epochs (csrc/comm/vmm.cpp) ----
+  {
+    namespace vm = hb::comm::vmm;
+    static py::exception<vm::Unavailable> unavailable(m, "VmmUnavailable", PyExc_RuntimeError);
+    m.def("vmm_driver_available", &vm::driver_available);
+    m.def("vmm_multicast_supported", &vm::multicast_supported);
+    m.def("vmm_usable", &vm::usable, py::call_guard<py::gil_scoped_release>());
+    m.def("vmm_granularity", &vm::granularity);
+    m.def("vmm_create", [](int device, size_t bytes, int world) {
+      vm::AllocInfo a = vm::create(device, bytes, world);
+      return py::make_tuple(a.id, a.size, a.gran);
+    });
+    m.def("vmm_export_fd", &vm::export_fd);
+    m.def("vmm_import_fd", &vm::import_fd, py::arg("fd"), py::arg("multicast") = false);
+    m.def("vmm_map", &vm::map);
+    m.def("vmm_unmap", &vm::unmap);
+    m.def("vmm_release", &vm::release);
+    m.def("vmm_live_handles", &vm::live_handles);
+    m.def("vmm_mc_create", &vm::mc_create);
+    m.def("vmm_mc_add_device", &vm::mc_add_device);
+    m.def("vmm_mc_bind", &vm::mc_bind);
+    m.def("uds_listen", &vm::uds_listen);
+    m.def("uds_close", &vm::uds_close);
+    m.def("uds_send_fds", &vm::uds_send_fds, py::call_guard<py::gil_scoped_release>());
+    m.def("uds_recv_fds", &vm::uds_recv_fds, py::call_guard<py::gil_scoped_release>());
+    m.def("epoch_stress", &vm::epoch_stress, py::call_guard<py::gil_scoped_release>());
+    py::class_<vm::EpochTable>(m, "EpochTable")
+        .def(py::init<int>())
+        .def("snapshot", [](const vm::EpochTable& t) {
+          const vm::EpochSnapshot s = t.snapshot();
+          py::dict d;
+          d["epoch"] = s.epoch;
+          d["flag_epoch"] = s.flag_epoch;
+          d["mask"] = s.mask;
+          d["world"] = s.world;
+          d["owner"] = std::vector<int>(s.owner, s.owner + s.world);
+          return d;
+        })
+        .def("drop", &vm::EpochTable::drop, py::arg("rank"), py::arg("adopter") = -1)
+        .def("set_mask", &vm::EpochTable::set_mask)
+        .def("set_owner", &vm::EpochTable::set_owner)
+        .def("admit", &vm::EpochTable::admit, py::arg("rank"), py::arg("take_back_shard") = true)
+        .def("set_flag_epoch", &vm::EpochTable::set_flag_epoch);
+  }
 }

@@ -285,19 +285,37 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tma_a,
 // barriers the MMA thread waits on (full / tmem_empty); MMA completion is multicast to both
 // CTAs' empty / tmem_full barriers; each CTA's epilogue drains its own 128 TMEM lanes.
 // =====================================================================================
-constexpr int kStages2 = 6;
-constexpr int kAStage2 = 128 * BK * 2;  // 16 KB: this CTA's 128 rows of A
-constexpr int kBStage2 = 128 * BK * 2;  // 16 KB: this CTA's 128 rows of B (half of N = 256)
 constexpr int kGroupM2 = 8;
 
-struct SmemLayout2 {
+// kMode 0: bf16 operands (kind::f16, 64-element K blocks, UMMA_K = 16), 256x256 tiles
+// kMode 1: fp8 e4m3/e5m2 operands, per-tensor scales (kind::f8f6f4, 128-element K blocks, UMMA_K = 32);
+//          the fp32 accumulator is multiplied by the two dequantisation factors in the epilogue
+// kMode 2: MXFP8 -- fp8 operands with one UE8M0 scale per 32 K-elements of every row of A and B
+//          (kind::mxf8f6f4.block_scale).  The scale factors of a K block travel with the operands (one more
+//          TMA box per operand and stage), are copied shared -> tensor memory by tcgen05.cp right before the
+//          four MMAs that consume them, and are applied inside the tensor core.  Both operands K-major.
+//          256x128 tiles: two 128-column accumulators + 8 scale-factor columns fit the 512 TMEM columns with the
+//          epilogue of tile i still overlapping the main loop of tile i+1 (a 256-wide tile would have to share
+//          columns between the scale factors and the accumulator being drained).
+template <int kMode>
+struct Cfg2 {
+  static constexpr bool kFp8 = kMode != 0;
+  static constexpr bool kMx = kMode == 2;
+  static constexpr int TN = kMx ? 128 : 256;           // tile columns
+  static constexpr int stages = kMx ? 7 : 6;
+  static constexpr int a_stage = 128 * BK * 2;          // 16 KB: this CTA's 128 rows of A
+  static constexpr int b_stage = (TN / 2) * BK * 2;     // this CTA's half of the B rows
+  static constexpr int sf_stage = kMx ? 1024 : 0;       // SFA (this CTA's 128 rows) + SFB (all TN columns), 512 B each
   static constexpr int a_off = 0;
-  static constexpr int b_off = a_off + kStages2 * kAStage2;
-  static constexpr int epi_off = b_off + kStages2 * kBStage2;
+  static constexpr int b_off = a_off + stages * a_stage;
+  static constexpr int sf_off = b_off + stages * b_stage;
+  static constexpr int epi_off = sf_off + stages * sf_stage;
   static constexpr int bar_off = epi_off + kEpiBytes;
-  static constexpr int total = bar_off + (2 * kStages2 + 4) * 8 + 16;
+  static constexpr int total = bar_off + (2 * stages + 4) * 8 + 16;
+  static constexpr int smem_bytes = total + 1024;
+  static constexpr int sf_tmem_col = 2 * TN;            // first column after the two accumulators
 };
-constexpr int kSmemBytes2 = SmemLayout2::total + 1024;
+static_assert(Cfg2<0>::smem_bytes <= 232448 && Cfg2<2>::smem_bytes <= 232448, "shared memory budget");
 
 __device__ __forceinline__ void tile_coords2(int t, const GemmParams& p, int& tm, int& tn) {
   const int per_group = kGroupM2 * p.tiles_n;
@@ -309,30 +327,37 @@ __device__ __forceinline__ void tile_coords2(int t, const GemmParams& p, int& tm
   tn = r / gsz;
 }
 
-// kFp8 = false: bf16 operands (kind::f16, 64-element K blocks, UMMA_K = 16)
-// kFp8 = true : fp8 e4m3/e5m2 operands (kind::f8f6f4, 128-element K blocks, UMMA_K = 32), the
-//               fp32 accumulator is multiplied by *p.scale (dequantisation) in the epilogue.
-template <bool kFp8>
+template <int kMode>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
                               const __grid_constant__ CUtensorMap tma_b,
                               const __grid_constant__ CUtensorMap tma_d,
                               const __grid_constant__ CUtensorMap tma_e,      // second output [M, N/2] (swiglu epilogue)
+                              const __grid_constant__ CUtensorMap tma_sfa,    // MXFP8: scale factors of A, [row block x K block] x 512 B
+                              const __grid_constant__ CUtensorMap tma_sfb,    // MXFP8: scale factors of B
                               const GemmParams p) {
+  using C2 = Cfg2<kMode>;
+  constexpr bool kFp8 = C2::kFp8;
+  constexpr bool kMx = C2::kMx;
+  constexpr int TN = C2::TN;
+  constexpr int kStages2 = C2::stages;
+  constexpr int kAStage2 = C2::a_stage;
+  constexpr int kBStage2 = C2::b_stage;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
 
-  const uint32_t a_smem = smem_base + SmemLayout2::a_off;
-  const uint32_t b_smem = smem_base + SmemLayout2::b_off;
-  const uint32_t bars = smem_base + SmemLayout2::bar_off;
+  const uint32_t a_smem = smem_base + C2::a_off;
+  const uint32_t b_smem = smem_base + C2::b_off;
+  const uint32_t sf_smem = smem_base + C2::sf_off;
+  const uint32_t bars = smem_base + C2::bar_off;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (kStages2 + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages2 + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 2 + s); };
   const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages2 + 4);
   volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + SmemLayout2::bar_off + 8 * (2 * kStages2 + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C2::bar_off + 8 * (2 * kStages2 + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -351,6 +376,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     tma_prefetch_desc(&tma_a);
     tma_prefetch_desc(&tma_b);
     tma_prefetch_desc(&tma_d);
+    if constexpr (kMx) {
+      tma_prefetch_desc(&tma_sfa);
+      tma_prefetch_desc(&tma_sfb);
+    }
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages2; ++s) {
@@ -377,10 +406,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       int tm, tn;
       tile_coords2(t, p, tm, tn);
       const int m0 = tm * 256 + (int)cta_rank * 128;
-      const int n0 = tn * 256 + (int)cta_rank * 128;
+      const int n0 = tn * TN + (int)cta_rank * (TN / 2);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(empty_bar(stage), phase ^ 1u);
-        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * (kAStage2 + kBStage2));
+        if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * (kAStage2 + kBStage2 + C2::sf_stage));
         const uint32_t lbar = mapa_shared(full_bar(stage), 0);   // the leader's barrier
         const int k0 = kb * BKE;
         const uint32_t sa = a_smem + stage * kAStage2;
@@ -393,19 +422,27 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
             tma_load_2d_2cta(sa + i * kChunk, &tma_a, lbar, m0 + i * kMnPerChunk, k0);
         }
         if (!p.b_mn) {
-          tma_load_2d_2cta(sb, &tma_b, lbar, k0, n0);            // box {128 B of k, 128 n}
+          tma_load_2d_2cta(sb, &tma_b, lbar, k0, n0);            // box {128 B of k, TN / 2 n}
         } else {
 #pragma unroll
           for (int i = 0; i < 128 / kMnPerChunk; ++i)
             tma_load_2d_2cta(sb + i * kChunk, &tma_b, lbar, n0 + i * kMnPerChunk, k0);
+        }
+        if constexpr (kMx) {
+          // 512 B per (128-row block, 128-element K block): row tm*2 + rank of A's table, row tn of B's table
+          const uint32_t ssf = sf_smem + stage * C2::sf_stage;
+          tma_load_2d_2cta(ssf, &tma_sfa, lbar, 0, (tm * 2 + (int)cta_rank) * num_kb + kb);
+          tma_load_2d_2cta(ssf + 512, &tma_sfb, lbar, 0, tn * num_kb + kb);
         }
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1 && lane == 0 && leader) {
     // ============================ MMA issuer (leader CTA) ==================
-    const uint32_t idesc = kFp8 ? umma_idesc_fp8(256, BN, p.a_mn, p.b_mn, p.a_fmt, p.b_fmt)
-                                : umma_idesc_bf16(256, BN, p.a_mn, p.b_mn);
+    const uint32_t idesc = kMx ? umma_idesc_mxfp8(256, TN, p.a_fmt, p.b_fmt)
+                           : kFp8 ? umma_idesc_fp8(256, TN, p.a_mn, p.b_mn, p.a_fmt, p.b_fmt)
+                                  : umma_idesc_bf16(256, TN, p.a_mn, p.b_mn);
+    const uint32_t tsfa = tmem_base + (uint32_t)C2::sf_tmem_col, tsfb = tsfa + 4u;
     const uint32_t a_lbo = p.a_mn ? kChunk : 16, b_lbo = p.b_mn ? kChunk : 16;
     const uint32_t a_kadv = p.a_mn ? UK * 128 : 32;   // MN-major: UK k-rows of 128 B; K-major: 32 B
     const uint32_t b_kadv = p.b_mn ? UK * 128 : 32;
@@ -417,17 +454,26 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(full_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = a_smem + stage * kAStage2;
         const uint32_t sb = b_smem + stage * kBStage2;
+        if constexpr (kMx) {
+          // scale factors of this K block: shared -> tensor memory of BOTH CTAs (each from its own shared memory);
+          // tcgen05.cp and tcgen05.mma execute in issue order, so the previous block's MMAs have read theirs
+          const uint32_t ssf = sf_smem + stage * C2::sf_stage;
+          tmem_cp_sf_2cta(tsfa, umma_sf_desc(ssf));
+          tmem_cp_sf_2cta(tsfb, umma_sf_desc(ssf + 512));
+        }
 #pragma unroll
         for (int k = 0; k < BKE / UK; ++k) {
           const uint64_t ad = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024);
           const uint64_t bd = umma_smem_desc(sb + k * b_kadv, b_lbo, 1024);
-          if constexpr (kFp8) umma_fp8_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (kMx) umma_mxfp8_ss_2cta(d_tmem, ad, bd, idesc | ((uint32_t)k << 29) | ((uint32_t)k << 4), tsfa, tsfb,
+                                                (kb | k) != 0 ? 1u : 0u);
+          else if constexpr (kFp8) umma_fp8_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           else umma_bf16_ss_2cta(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
         }
         umma_commit_2cta(empty_bar(stage), 0x3);   // frees the slot in BOTH CTAs
@@ -438,28 +484,28 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp >= 4) {
     // ============================ epilogue (both CTAs) =====================
     const int ew = warp - 4;
-    const uint32_t epi_smem = smem_base + SmemLayout2::epi_off + ew * 2 * kEpiWarpBuf;
-    const float out_scale = (kFp8 && p.scale != nullptr) ? __ldg(p.scale) * __ldg(p.scale_b) : 1.f;
+    const uint32_t epi_smem = smem_base + C2::epi_off + ew * 2 * kEpiWarpBuf;
+    const float out_scale = (kFp8 && !kMx && p.scale != nullptr) ? __ldg(p.scale) * __ldg(p.scale_b) : 1.f;
     int it = 0;
     int buf = 0;
     for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++it) {
       int tm, tn;
       tile_coords2(t, p, tm, tn);
-      const int m0 = tm * 256 + (int)cta_rank * 128, n0 = tn * 256;
+      const int m0 = tm * 256 + (int)cta_rank * 128, n0 = tn * TN;
       const int acc = it & 1;
       const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * TN);
       const int row = m0 + ew * 32 + lane;
 uint32_t actp[32];
       #pragma unroll 2
-      for (int c = 0; c < BN / 64; ++c) {
+      for (int c = 0; c < TN / 64; ++c) {
         uint32_t r0[32], r1[32];
         tmem_ld_32x32(t_addr + c * 64, r0);
         tmem_ld_32x32(t_addr + c * 64 + 32, r1);
         tmem_ld_wait();
-        if (c == BN / 64 - 1) {
+        if (c == TN / 64 - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_remote(mapa_shared(tempty_bar(acc), 0));
@@ -472,7 +518,7 @@ uint32_t actp[32];
           // bf16 first, so the result equals the stand-alone `swiglu_bwd_kernel` applied to the bf16 dgrad.
           const bool row_ok = row < p.M;
           const bf16* gp = p.gu + (size_t)row * p.ld_gu + 2 * (size_t)col0;
-          if (row_ok && c + 1 < BN / 64 && 2 * (col0 + 64) + 128 <= 2 * p.N) {
+          if (row_ok && c + 1 < TN / 64 && 2 * (col0 + 64) + 128 <= 2 * p.N) {
             // the next chunk's (gate, up) pairs: start them on their way from HBM to L2 now
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 128));
             asm volatile("prefetch.global.L2 [%0];" ::"l"(gp + 192));
@@ -639,10 +685,12 @@ void init_once() {
   cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                        kSmemBytes);
-  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       kSmemBytes2);
-  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                       kSmemBytes2);
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Cfg2<0>::smem_bytes);
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Cfg2<1>::smem_bytes);
+  cudaFuncSetAttribute(gemm_tcgen05_2cta_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       Cfg2<2>::smem_bytes);
   if (const char* e = getenv("HYPHA_GEMM_CTAS")) g_mode = (e[0] == '1') ? 1 : 2;
 }
 
@@ -660,6 +708,22 @@ bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, 
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     g_err = "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r);
+    return false;
+  }
+  return true;
+}
+
+// Scale-factor table of an MXFP8 operand: `rows` = (128-row blocks) x (128-element K blocks), 512 bytes each.
+bool make_tmap_sf(CUtensorMap* m, const void* ptr, uint64_t rows) {
+  cuuint64_t dims[2] = {128, rows};
+  cuuint64_t strides[1] = {512};
+  cuuint32_t box[2] = {128, 1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    g_err = "cuTensorMapEncodeTiled (scale factors) failed with code " + std::to_string((int)r);
     return false;
   }
   return true;
@@ -720,7 +784,7 @@ int gemm_bf16_tcgen05(const bf16* A, const bf16* B, bf16* D, int M, int N, int K
     p.num_tiles = p.tiles_m * p.tiles_n;
     int clusters = g_num_sms / 2;
     if (p.num_tiles < clusters) clusters = p.num_tiles;
-    gemm_tcgen05_2cta_kernel<false><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, te, p);
+    gemm_tcgen05_2cta_kernel<0><<<clusters * 2, kThreads, Cfg2<0>::smem_bytes, s>>>(ta, tb, td, te, td, td, p);
   } else {
     p.tiles_m = (M + BM - 1) / BM;
     p.num_tiles = p.tiles_m * p.tiles_n;
@@ -775,7 +839,61 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
   p.num_tiles = p.tiles_m * p.tiles_n;
   int clusters = g_num_sms / 2;
   if (p.num_tiles < clusters) clusters = p.num_tiles;
-  gemm_tcgen05_2cta_kernel<true><<<clusters * 2, kThreads, kSmemBytes2, s>>>(ta, tb, td, te, p);
+  gemm_tcgen05_2cta_kernel<1><<<clusters * 2, kThreads, Cfg2<1>::smem_bytes, s>>>(ta, tb, td, te, td, td, p);
+  count_launch();
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }
+  return 0;
+}
+
+
+// D[M,N] (+)= A . B^T with MXFP8 operands: A [M,K] and B [N,K] fp8 (K contiguous), one UE8M0 scale per 32 consecutive
+// K-elements of every row, the scales in the tensor-core atom layout (see `quantize_mxfp8`): table[row block of 128]
+// [K block of 128][(r % 32) * 16 + (r / 32 % 4) * 4 + (k / 32 % 4)].  fp32 accumulation, bf16 output.
+int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, const uint8_t* sfb, bf16* D, int M, int N,
+                       int K, int lda, int ldb, int ldd, int a_fmt, int b_fmt, int accumulate, cudaStream_t s,
+                       bf16* act, int ld_act, const bf16* gu, int ld_gu) {
+  std::call_once(g_once, init_once);
+  if (g_encode == nullptr) { g_err = "cuTensorMapEncodeTiled unavailable"; return 1; }
+  if (M <= 0 || N <= 0 || K <= 0) { g_err = "empty problem"; return 2; }
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  if (!al16(A) || !al16(B) || !al16(D) || !al16(sfa) || !al16(sfb) || (lda % 16) || (ldb % 16) || (ldd % 8) ||
+      (M % 128) || (N % 128) || (K % 128)) {
+    g_err = "mxfp8 operands need 16-byte aligned pointers / leading dimensions and M, N, K % 128 == 0";
+    return 3;
+  }
+  if (act != nullptr && gu == nullptr && (accumulate || !al16(act) || (ld_act % 8))) {
+    g_err = "swiglu epilogue: needs a 16-byte aligned second output and no accumulation";
+    return 3;
+  }
+  if (gu != nullptr && (act == nullptr || accumulate || !al16(gu) || (ld_gu % 8))) {
+    g_err = "dswiglu epilogue: needs the [M, 2N] output in `act`, 16-byte aligned gu and no accumulation";
+    return 3;
+  }
+  constexpr int TN = Cfg2<2>::TN;
+  const int num_kb = K / 128;
+  CUtensorMap ta, tb, td, te, tsa, tsb;
+  bool ok = make_tmap(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 128, 128, 1);
+  ok = ok && make_tmap(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 128, TN / 2, 1);
+  ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
+  ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(gu != nullptr ? 2 * N : N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
+                             : make_tmap(&te, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32));
+  ok = ok && make_tmap_sf(&tsa, sfa, (uint64_t)(M / 128) * num_kb) && make_tmap_sf(&tsb, sfb, (uint64_t)(N / 128) * num_kb);
+  if (!ok) return 4;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.a_mn = 0; p.b_mn = 0;
+  p.accumulate = accumulate;
+  p.D = D; p.ldd = ldd;
+  p.swiglu = (act != nullptr && gu == nullptr) ? 1 : 0;
+  p.gu = gu; p.ld_gu = ld_gu;
+  p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = nullptr; p.scale_b = nullptr;
+  p.tiles_n = N / TN;
+  p.tiles_m = (M + 255) / 256;
+  p.num_tiles = p.tiles_m * p.tiles_n;
+  int clusters = g_num_sms / 2;
+  if (p.num_tiles < clusters) clusters = p.num_tiles;
+  gemm_tcgen05_2cta_kernel<2><<<clusters * 2, kThreads, Cfg2<2>::smem_bytes, s>>>(ta, tb, td, te, tsa, tsb, p);
   count_launch();
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) { g_err = cudaGetErrorString(e); return 5; }

@@ -106,6 +106,13 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
                      int ldb, int ldd, int a_kmajor, int b_kmajor, int a_fmt, int b_fmt,
                      const float* dequant_a, const float* dequant_b, int accumulate, cudaStream_t s,
                      bf16* act = nullptr, int ld_act = 0);
+// MXFP8 (kind::mxf8f6f4.block_scale): both operands K-major, UE8M0 scales per 32 K-elements in the atom layout
+// `quantize_mxfp8` writes; optional fused SwiGLU / SwiGLU-backward epilogues as in gemm_bf16_tcgen05.
+int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, const uint8_t* sfb, bf16* D, int M, int N,
+                       int K, int lda, int ldb, int ldd, int a_fmt, int b_fmt, int accumulate, cudaStream_t s,
+                       bf16* act = nullptr, int ld_act = 0, const bf16* gu = nullptr, int ld_gu = 0);
+int quantize_mxfp8(const bf16* x, int ldx, uint8_t* q, int ldq, uint8_t* sf, uint8_t* qT, int ldqT, uint8_t* sfT, int R,
+                   int C, cudaStream_t s);
 void amax_bf16(const bf16* x, int64_t n, float* amax, cudaStream_t s);
 void quantize_fp8(const bf16* x, uint8_t* out, int64_t n, const float* amax, float* dequant, int fmt,
                   cudaStream_t s);

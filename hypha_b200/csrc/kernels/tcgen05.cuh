@@ -273,6 +273,43 @@ __device__ __forceinline__ void umma_fp8_ss_2cta(uint32_t d_tmem, uint64_t a_des
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- MXFP8: block-scaled MMA (kind::mxf8f6f4.block_scale, one UE8M0 scale per 32 K-elements) -----------------
+// Instruction descriptor of the block-scaled form (no c_format field: the accumulator is fp32):
+//   [4,6) b_sf_id  [7,10) a_format  [10,13) b_format  [15] a_major  [16] b_major  [17,23) N >> 3
+//   [23] scale format (1 = UE8M0)  [24,29) M >> 4  [29,31) a_sf_id  [31] K size (0 = 32)
+// a_sf_id / b_sf_id select the byte of the 32-bit scale-factor column an MMA uses: with 128-element K blocks the
+// four scales of a row sit in one TMEM column and MMA k of the block takes byte k.  Operands K-major.
+__host__ __device__ constexpr uint32_t umma_idesc_mxfp8(int m, int n, int a_fmt, int b_fmt) {
+  return ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// Shared-memory descriptor of one scale-factor atom for tcgen05.cp: 32 rows x 16 bytes, no swizzle, K-major;
+// 8-row core matrices of 128 contiguous bytes, 128 bytes apart.
+__device__ __forceinline__ uint64_t umma_sf_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(128u >> 4) << 32;   // stride byte offset
+  d |= (uint64_t)1 << 46;             // sm_100 descriptor version
+  return d;
+}
+// 32 rows x 128 bits of shared memory -> 32 lanes x 4 columns of tensor memory, replicated into the four 32-lane
+// sub-partitions (every warp quadrant of the MMA reads the scales of "its" rows locally); each CTA of the pair
+// copies from its own shared memory into its own tensor memory.
+__device__ __forceinline__ void tmem_cp_sf_2cta(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void tmem_cp_sf(uint32_t taddr, uint64_t sdesc) {
+  asm volatile("tcgen05.cp.cta_group::1.32x128b.warpx4 [%0], %1;" ::"r"(taddr), "l"(sdesc) : "memory");
+}
+__device__ __forceinline__ void umma_mxfp8_ss_2cta(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                   uint32_t sfa_tmem, uint32_t sfb_tmem, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
+      : "memory");
+}
 // Arrive (once) on the same-offset mbarrier of every CTA in `cta_mask` when prior MMAs retire.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile(

@@ -144,19 +144,31 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_kmajor: bool = True, b_kmajor: b
 
 
 # -----------------------------------------------------------------------------
-# fp8 (kind::f8f6f4) path: per-tensor current scaling, e4m3 forward operands, e5m2 gradients
+# fp8 paths.  "mx" (default): MXFP8 -- e4m3 values, one UE8M0 scale per 32 elements along the contraction
+# dimension, applied inside the tensor core (tcgen05.mma.kind::mxf8f6f4.block_scale).  "tensor": per-tensor current
+# scaling on kind::f8f6f4 (e4m3 forward operands, e5m2 gradients), the round-1 path.
 # -----------------------------------------------------------------------------
 _FP8 = os.environ.get("HYPHA_FP8", "0") == "1"
+_FP8_MODE = os.environ.get("HYPHA_FP8_MODE", "mx")
 _FP8_WEIGHT_VERSION = 0
 E4M3, E5M2 = 0, 1
 
 
-def set_fp8(enabled: bool) -> None:
-    """Run Linear-layer GEMMs (fwd, dgrad, wgrad) in fp8 on the tcgen05 ``kind::f8f6f4`` kernel.
+def set_fp8(enabled: bool, mode: Optional[str] = None) -> None:
+    """Run Linear-layer GEMMs (fwd, dgrad, wgrad) in fp8 on the tcgen05 kernels: ``mode="mx"`` block-scaled MXFP8
+    (``kind::mxf8f6f4.block_scale``), ``mode="tensor"`` per-tensor scaling (``kind::f8f6f4``).
     Master weights, gradients written to ``main_grad``, the optimizer and the DiLoCo outer step stay
     bf16/fp32 (BASELINE config 3: fp8 inner steps, bf16 outer all-reduce)."""
-    global _FP8
+    global _FP8, _FP8_MODE
     _FP8 = bool(enabled)
+    if mode is not None:
+        if mode not in ("mx", "tensor"):
+            raise ValueError(mode)
+        _FP8_MODE = mode
+
+
+def fp8_mode() -> str:
+    return _FP8_MODE
 
 
 def fp8_enabled() -> bool:
@@ -217,13 +229,114 @@ def gemm_fp8(aq: torch.Tensor, a_dq: torch.Tensor, bq: torch.Tensor, b_dq: torch
     return out
 
 
+# ---- MXFP8 ---------------------------------------------------------------------------------------------------
+def mx_sf_shape(rows: int, k: int) -> Tuple[int, int, int]:
+    """Shape of the scale table of a ``[rows, k]`` operand: one 512-byte atom per (128 rows, 128 K-elements)."""
+    return (rows // 128, k // 128, 512)
+
+
+def quantize_mxfp8(x: torch.Tensor, rowwise: bool = True, transposed: bool = False):
+    """``(q, sf, qT, sfT)`` of a bf16 matrix ``x[R, C]`` in ONE pass (`csrc/kernels/fp8.cu`):
+
+    ``q[R, C]`` e4m3 (uint8) scaled per 32 elements along ``C`` with table ``sf`` -- the operand of a GEMM that
+    contracts over ``C``; ``qT[C, R]`` = ``x^T`` scaled along ``R`` with ``sfT`` -- the operand when the GEMM
+    contracts over ``R`` (wgrad, dgrad's weight).  Pairs not requested are ``None``.  ``R, C % 128 == 0``."""
+    assert x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 2 and x.stride(1) == 1
+    R, C = x.shape
+    q = sf = qT = sfT = None
+    if rowwise:
+        q = torch.empty((R, C), dtype=torch.uint8, device=x.device)
+        sf = torch.empty(mx_sf_shape(R, C), dtype=torch.uint8, device=x.device)
+    if transposed:
+        qT = torch.empty((C, R), dtype=torch.uint8, device=x.device)
+        sfT = torch.empty(mx_sf_shape(C, R), dtype=torch.uint8, device=x.device)
+    load_C().quantize_mxfp8(x.data_ptr(), x.stride(0), _ptr(q), C, _ptr(sf), _ptr(qT), R, _ptr(sfT), R, C, cuda_stream())
+    return q, sf, qT, sfT
+
+
+def mxfp8_quantize_ref(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Plain-torch model of the row-wise quantiser: ``(q as float8_e4m3fn [R, C], biased exponents uint8 [R, C/32])``."""
+    R, C = x.shape
+    xb = x.float().reshape(R, C // 32, 32)
+    amax = xb.abs().amax(dim=-1)
+    u = (amax * (1.0 / 448.0)).view(torch.int32)
+    e = ((u >> 23) & 0xFF) + ((u & 0x7FFFFF) != 0).to(torch.int32)
+    e = e.clamp(max=254)
+    inv = ((254 - e) << 23).view(torch.float32)
+    q = (xb * inv[..., None]).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).reshape(R, C)
+    return q, e.to(torch.uint8)
+
+
+def mxfp8_sf_to_table(e: torch.Tensor) -> torch.Tensor:
+    """Biased exponents ``[rows, k/32]`` -> the atom-layout table ``[rows/128, k/128, 512]`` the kernels use."""
+    rows, kb = e.shape
+    t = e.reshape(rows // 128, 4, 32, kb // 4, 4)        # [row block, r/32, r%32, k block, k/32]
+    return t.permute(0, 3, 2, 1, 4).reshape(rows // 128, kb // 4, 512).contiguous()
+
+
+def mxfp8_dequant_ref(q: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
+    """fp32 matrix an MXFP8 operand stands for (uint8-stored e4m3 + atom-layout scale table)."""
+    rows, k = q.shape
+    e = table.reshape(rows // 128, k // 128, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(rows, k // 32)
+    scale = torch.exp2(e.float() - 127.0)
+    return (q.view(torch.float8_e4m3fn).float().reshape(rows, k // 32, 32) * scale[..., None]).reshape(rows, k)
+
+
+def gemm_mxfp8(aq: torch.Tensor, asf: torch.Tensor, bq: torch.Tensor, bsf: torch.Tensor, *,
+               out: Optional[torch.Tensor] = None, accumulate: bool = False, swiglu_out: Optional[torch.Tensor] = None,
+               dswiglu: Optional[Tuple[torch.Tensor, torch.Tensor]] = None) -> torch.Tensor:
+    """``D[M,N] (+)= A[M,K] . B[N,K]^T`` with MXFP8 operands (both K-major, scale tables from `quantize_mxfp8`);
+    block scales applied by ``tcgen05.mma.kind::mxf8f6f4.block_scale``, fp32 accumulation, bf16 output.
+    ``swiglu_out`` / ``dswiglu``: the fused epilogues of `gemm`."""
+    M, K = aq.shape
+    N, Kb = bq.shape
+    assert K == Kb and aq.stride(1) == 1 and bq.stride(1) == 1
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=aq.device)
+        accumulate = False
+    act, ld_act, gu, ld_gu = 0, 0, 0, 0
+    if dswiglu is not None:
+        gu_t, dgu_t = dswiglu
+        act, ld_act, gu, ld_gu = dgu_t.data_ptr(), dgu_t.stride(0), gu_t.data_ptr(), gu_t.stride(0)
+    elif swiglu_out is not None:
+        act, ld_act = swiglu_out.data_ptr(), swiglu_out.stride(0)
+    load_C().gemm_mxfp8(aq.data_ptr(), asf.data_ptr(), bq.data_ptr(), bsf.data_ptr(), out.data_ptr(), M, N, K,
+                        aq.stride(0), bq.stride(0), out.stride(0), E4M3, E4M3, int(accumulate), cuda_stream(),
+                        act, ld_act, gu, ld_gu)
+    return dswiglu[1] if dswiglu is not None else out
+
+
+def _weight_mx(weight: torch.Tensor):
+    """``(q, sf, qT, sfT)`` of a weight ``[N, K]``: the forward operand and the dgrad operand (W^T scaled along N),
+    cached until the optimizer rewrites the weights (2 bytes / parameter)."""
+    cache = getattr(weight, "_mx_cache", None)
+    if _FP8_CACHE_WEIGHTS and cache is not None and cache[0] == _FP8_WEIGHT_VERSION:
+        return cache[1]
+    quad = quantize_mxfp8(weight.detach(), rowwise=True, transposed=True)
+    if _FP8_CACHE_WEIGHTS:
+        weight._mx_cache = (_FP8_WEIGHT_VERSION, quad)
+    return quad
+
+
+def _mx_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
+    return (_FP8 and _FP8_MODE == "mx" and x2.is_cuda and x2.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+            and x2.shape[0] % 128 == 0 and x2.shape[1] % 128 == 0 and weight.shape[0] % 128 == 0
+            and x2.stride(1) == 1 and x2.stride(0) % 8 == 0 and weight.is_contiguous())
+
+
 def _fp8_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
+    if _FP8 and _FP8_MODE == "mx":
+        return _mx_ok(x2, weight)
     return (_FP8 and x2.is_cuda and x2.dtype == torch.bfloat16 and x2.shape[0] % 16 == 0
             and x2.shape[1] % 16 == 0 and weight.shape[0] % 16 == 0)
 
 
 def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor, swiglu_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """y = x2 @ weight.T on the bf16 or fp8 tensor-core path (``swiglu_out``: fused SwiGLU epilogue, see `gemm`)."""
+    if _mx_ok(x2, weight):
+        xq, xsf, _, _ = quantize_mxfp8(x2, rowwise=True, transposed=False)
+        wq, wsf, _, _ = _weight_mx(weight)
+        return gemm_mxfp8(xq, xsf, wq, wsf, swiglu_out=swiglu_out)
     if _fp8_ok(x2, weight):
         xq, xdq = quantize_fp8(x2, E4M3)
         wq, wdq = _weight_fp8(weight)
@@ -232,10 +345,22 @@ def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor, swiglu_out: Optional[torch.T
 
 
 def _mm_bwd(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor, need_dx: bool = True,
-            dx_out: Optional[torch.Tensor] = None):
-    """(dx, dW) for y = x2 @ weight.T.  dW goes to ``weight.main_grad`` when present (returns None)."""
+            dx_out: Optional[torch.Tensor] = None, dswiglu: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+    """(dx, dW) for y = x2 @ weight.T.  dW goes to ``weight.main_grad`` when present (returns None).
+    ``dswiglu = (gu, dgu)`` (MXFP8 only): the dgrad epilogue writes d(gate|up) into ``dgu`` and returns it as dx."""
     mg = getattr(weight, "main_grad", None)
     acc = bool(getattr(weight, "grad_accumulate", False)) if mg is not None else False
+    if _mx_ok(x2, weight):
+        # every operand K-major: dW[N,K] = dy^T[N,T] . (x^T[K,T])^T, dx[T,K] = dy[T,N] . (W^T[K,N])^T
+        dyq, dysf, dyTq, dyTsf = quantize_mxfp8(dy2, rowwise=need_dx, transposed=True)
+        _, _, xTq, xTsf = quantize_mxfp8(x2, rowwise=False, transposed=True)
+        dw = gemm_mxfp8(dyTq, dyTsf, xTq, xTsf, out=mg, accumulate=acc)
+        dx = None
+        if need_dx:
+            _, _, wTq, wTsf = _weight_mx(weight)
+            dx = gemm_mxfp8(dyq, dysf, wTq, wTsf, out=dx_out, dswiglu=dswiglu)
+        return dx, (None if mg is not None else dw)
+    assert dswiglu is None, "the fused SwiGLU-backward epilogue of _mm_bwd is an MXFP8 path"
     if _fp8_ok(x2, weight) and dy2.shape[1] % 16 == 0:
         dyq, dydq = quantize_fp8(dy2, E5M2)
         xq, xdq = quantize_fp8(x2, E4M3)
@@ -515,7 +640,10 @@ class _SwiGLULinear(torch.autograd.Function):
         C.swiglu_fwd(gu.data_ptr(), act.data_ptr(), rows, inter, s)
         dy2 = dy if dy.is_contiguous() else dy.contiguous()
         dgu = torch.empty_like(gu)
-        if _fp8_ok(act, weight):
+        if _mx_ok(act, weight):
+            # one quantisation of dy feeds wgrad and dgrad; the dgrad epilogue turns d(act) into d(gate|up)
+            _, dw = _mm_bwd(dy2, act, weight, dx_out=act, dswiglu=(gu, dgu))
+        elif _fp8_ok(act, weight):
             dact, dw = _mm_bwd(dy2, act, weight)
             C.swiglu_bwd(dact.data_ptr(), gu.data_ptr(), dgu.data_ptr(), rows, inter, s)
         else:

@@ -187,6 +187,75 @@ def shard_bounds(n: int, world: int, rank: int, align: int = 1024):
     return b, max(0, e - b)
 
 
+class _PyEpochTable:
+    """Plain-Python stand-in for the native epoch table when the group spans more than one box (world > 8:
+    NCCL backend, no fused kernel launches to keep consistent)."""
+
+    def __init__(self, world: int):
+        self._s = {"epoch": 0, "flag_epoch": 0, "mask": (1 << world) - 1, "world": world, "owner": list(range(world))}
+
+    def snapshot(self) -> dict:
+        return dict(self._s, owner=list(self._s["owner"]))
+
+    def _bump(self) -> int:
+        self._s["epoch"] += 1
+        return self._s["epoch"]
+
+    def set_mask(self, mask: int) -> int:
+        self._s["mask"] = int(mask)
+        return self._bump()
+
+    def set_owner(self, shard: int, rank: int) -> int:
+        self._s["owner"][shard] = int(rank)
+        return self._bump()
+
+    def set_flag_epoch(self, v: int) -> int:
+        self._s["flag_epoch"] = int(v)
+        return self._bump()
+
+
+class _OwnerMap:
+    """``{shard: rank}`` view of the epoch table's ownership column with the dict operations the membership code
+    uses (every rank applies the same events in the same order, so the tables agree without communication)."""
+
+    def __init__(self, table, world: int):
+        self._t, self._world = table, world
+
+    def _col(self) -> List[int]:
+        return [int(x) for x in self._t.snapshot()["owner"]]
+
+    def __getitem__(self, k: int) -> int:
+        return self._col()[int(k)]
+
+    def __setitem__(self, k: int, v: int) -> None:
+        self._t.set_owner(int(k), int(v))
+
+    def get(self, k, default=None):
+        k = int(k)
+        return self._col()[k] if 0 <= k < self._world else default
+
+    def keys(self):
+        return range(self._world)
+
+    def values(self):
+        return self._col()
+
+    def items(self):
+        return list(enumerate(self._col()))
+
+    def __iter__(self):
+        return iter(range(self._world))
+
+    def __len__(self) -> int:
+        return self._world
+
+    def __eq__(self, other) -> bool:
+        return dict(self.items()) == dict(other.items()) if hasattr(other, "items") else NotImplemented
+
+    def __repr__(self) -> str:
+        return repr(dict(self.items()))
+
+
 class DiLoCoOuter:
     """Outer Nesterov optimizer, ZeRO-1 sharded across the participating ranks."""
 
@@ -205,7 +274,9 @@ class DiLoCoOuter:
         self.backend = backend
         self.world, self.rank = world, (group.rank if group is not None else 0)
         self.round = 0
-        self.member_mask = (1 << world) - 1
+        # membership, shard ownership and the flag-token epoch live in the native epoch table (`csrc/comm/vmm.cpp`:
+        # writers publish under a sequence lock, a launch reads a consistent snapshot); one box = 8 ranks at most
+        self._table.snapshot()
         self.last_status = (0, 0)
         if backend == "local":
             self.shard_begin, self.shard_len = 0, self.n
@@ -229,7 +300,6 @@ class DiLoCoOuter:
             # segments owned by this rank: its shard + shards adopted from dropped ranks
             self.segments = {self.rank: (self.shard_begin, self.shard_len, self.theta_outer, self.momentum)}
             self.layout = [shard_bounds(self.n, world, r) for r in range(world)]
-            self.attempt = 0
             # multimem path when the buffers carry a multicast address; measured slower than P2P at
             # N=2 (nothing to save: one peer) and 12-19 % faster at N=8
             self.use_nvls = world >= 4
@@ -243,6 +313,43 @@ class DiLoCoOuter:
             raise ValueError(backend)
 
     # -- membership (fault tolerance: SURVEY 5.3, BASELINE config 4) ------------------------
+    @property
+    def _table(self):
+        t = self.__dict__.get("_table_obj")
+        if t is None:
+            world = self.world
+            t = self.__dict__["_table_obj"] = load_C().EpochTable(world) if world <= 8 else _PyEpochTable(world)
+            self.__dict__["_owner_map"] = _OwnerMap(t, world)
+        return t
+
+    @property
+    def member_mask(self) -> int:
+        return int(self._table.snapshot()["mask"])
+
+    @member_mask.setter
+    def member_mask(self, mask: int) -> None:
+        self._table.set_mask(int(mask))
+
+    @property
+    def attempt(self) -> int:
+        """Flag-token epoch of the device-side barriers (bumped by every launch)."""
+        return int(self._table.snapshot()["flag_epoch"])
+
+    @attempt.setter
+    def attempt(self, v: int) -> None:
+        self._table.set_flag_epoch(int(v))
+
+    @property
+    def _owner(self) -> "_OwnerMap":
+        self._table
+        return self.__dict__["_owner_map"]
+
+    @_owner.setter
+    def _owner(self, value) -> None:
+        om = self._owner                            # a plain {shard: rank} map agreed over the control plane
+        for k, v in value.items():
+            om[int(k)] = int(v)
+
     def set_members(self, ranks: List[int]) -> None:
         mask = 0
         for r in ranks:
@@ -262,17 +369,18 @@ class DiLoCoOuter:
                                  first, 1.0, s)
         elif self.backend == "fused":
             self.attempt += 1                      # flag tokens must be unique per launch
+            snap = self._table.snapshot()          # ONE consistent (members, flag epoch) pair for this launch
             segs = [self.segments[k] for k in sorted(self.segments)]
             C.diloco_outer_step_fused(self.delta_buf.peer_ptrs, self.param_buf.peer_ptrs,
                                       self.anchor_buf.peer_ptrs, self.flag_buf.peer_ptrs,
                                       opt.master.data_ptr(), [b for b, _, _, _ in segs],
                                       [l for _, l, _, _ in segs], [t.data_ptr() for _, _, t, _ in segs],
                                       [m.data_ptr() for _, _, _, m in segs], self.n, self.rank,
-                                      self.member_mask, self.attempt, cfg.outer_lr, cfg.outer_momentum,
+                                      int(snap["mask"]), int(snap["flag_epoch"]), cfg.outer_lr, cfg.outer_momentum,
                                       first, cfg.num_ctas, *self._multicast_ptrs(),
                                       [b for b, _ in self.layout], [l for _, l in self.layout],
                                       *self._pipeline_shape(), s)
-            nmem = bin(self.member_mask).count("1")
+            nmem = bin(int(snap["mask"])).count("1")
             wire = 2 * sum(l for _, l, _, _ in segs) * (nmem - 1)
             self.group.counters.add("/hypha-peer-memory/outer-step", inbound=wire, outbound=wire)
         else:
@@ -315,10 +423,7 @@ class DiLoCoOuter:
     def owners(self) -> Dict[int, int]:
         """shard -> rank that currently runs its outer update.  Replicated bookkeeping: every rank applies the
         same membership events in the same order, so the maps agree without communication."""
-        own = getattr(self, "_owner", None)
-        if own is None:
-            own = self._owner = {r: r for r in range(self.world)}
-        return own
+        return self._owner
 
     def drop_ranks(self, dead: List[int]) -> None:
         """Shrink the membership; orphaned shards are adopted with theta_outer re-derived from the

@@ -3,7 +3,9 @@ plain P2P loads/stores and (c) bound to an NVSwitch *multicast object*, so a ker
 ``multimem.ld_reduce`` (the switch sums the N copies in flight) and ``multimem.st`` (the switch
 replicates one store to all N copies).
 
-Set-up (driver API through ``cuda.bindings``; no NCCL, no torch symmetric-memory):
+Set-up (CUDA driver API from C++, `csrc/comm/vmm.cpp`: allocation, export / import, mapping, multicast objects and
+the SCM_RIGHTS descriptor passing are native; this module only sequences the stages between control-plane exchanges;
+no NCCL, no torch symmetric-memory, no cuda-python):
   1. ``cuMemCreate`` a POSIX-fd-exportable physical allocation per rank,
   2. swap the fds between the rank processes over AF_UNIX sockets (``SCM_RIGHTS``),
   3. import + ``cuMemMap`` every peer's allocation (unicast view, for flags / fallback P2P),
@@ -16,14 +18,13 @@ This is the B200-native replacement of the reference's parameter-server fan-in /
 from __future__ import annotations
 
 import os
-import socket
 import tempfile
-import time
 from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
 
+from ..ops.native import load_C
 from .peer_memory import _DT_SIZE, PeerGroup, SymmetricBuffer, tensor_from_ptr
 
 
@@ -31,99 +32,55 @@ class NvlsUnavailable(RuntimeError):
     pass
 
 
-def _cu():
+def _native(fn, *args):
+    """Call into `csrc/comm/vmm.cpp`; its `Unavailable` (and any driver error) becomes `NvlsUnavailable`."""
     try:
-        from cuda.bindings import driver as cu
-    except ImportError:  # older cuda-python
-        from cuda import cuda as cu
-    return cu
-
-
-def _ck(res, what: str):
-    cu = _cu()
-    err, *rest = res if isinstance(res, tuple) else (res,)
-    if err != cu.CUresult.CUDA_SUCCESS:
-        raise NvlsUnavailable(f"{what} failed: {err}")
-    return rest[0] if len(rest) == 1 else (tuple(rest) if rest else None)
+        return fn(*args)
+    except RuntimeError as exc:          # VmmUnavailable derives from RuntimeError
+        raise NvlsUnavailable(str(exc)) from exc
 
 
 def _send_fds(path: str, rank: int, fds: List[int]) -> None:
-    deadline = time.time() + 30
-    while True:
-        try:
-            s = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-            s.connect(path)
-            break
-        except (FileNotFoundError, ConnectionRefusedError):
-            s.close()
-            if time.time() > deadline:
-                raise NvlsUnavailable(f"peer socket {path} never appeared")
-            time.sleep(0.02)
-    with s:
-        s.settimeout(60)    # a receiver that failed before accepting must not hang the sender
-        try:
-            socket.send_fds(s, [rank.to_bytes(4, "little")], fds)
-            s.recv(1)       # ack: the receiver has dup'ed the descriptors
-        except (socket.timeout, OSError) as exc:
-            raise NvlsUnavailable(f"peer at {path} did not take the memory handles: {exc}") from exc
+    """Hand ``fds`` to the process listening on ``path`` (SCM_RIGHTS); waits up to 30 s for the socket to appear and
+    up to 60 s for the receiver's acknowledgement."""
+    _native(load_C().uds_send_fds, path, int(rank), [int(f) for f in fds], 30.0, 60.0)
 
 
-def _recv_fds(server: socket.socket, count: int, nfds: int):
-    got = {}
-    for _ in range(count):
-        try:
-            conn, _ = server.accept()
-        except socket.timeout as exc:
-            raise NvlsUnavailable("timed out waiting for a peer's memory handle") from exc
-        with conn:
-            msg, fds, _, _ = socket.recv_fds(conn, 4, nfds)
-            got[int.from_bytes(msg, "little")] = list(fds)
-            conn.send(b"k")
-    return got
+def _recv_fds(server, count: int, nfds: int):
+    """``{sender rank: [fd, ...]}`` from ``count`` peers; ``server`` is a listening socket (object or descriptor)."""
+    fd = server if isinstance(server, int) else server.fileno()
+    got = _native(load_C().uds_recv_fds, fd, int(count), int(nfds), 60.0)
+    return {int(r): list(f) for r, f in got.items()}
 
 
 @dataclass
 class NvlsBuffer(SymmetricBuffer):
     mc_ptr: int = 0                 # multicast virtual address (0 if multicast could not be set up)
     nbytes_mapped: int = 0
-    _handles: Optional[list] = None  # driver handles to release in close(): [(va, size, handle), ...]
-    _h_local: object = None          # the local physical allocation (exportable as a POSIX fd: `export_fd`)
+    _handles: Optional[list] = None  # native registry ids to release in close()
+    _h_local: int = 0                # the local physical allocation (exportable as a POSIX fd: `export_fd`)
     _gran: int = 0
 
     def export_fd(self) -> int:
         """A POSIX file descriptor of the local allocation for a process that was not part of the original team
         (a replacement rank): it imports + maps it with `map_peer_fd` and reaches this rank's copy with plain
         P2P loads/stores.  The caller closes the descriptor after sending it."""
-        cu = _cu()
-        H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
-        return int(_ck(cu.cuMemExportToShareableHandle(self._h_local, H, 0), "cuMemExportToShareableHandle"))
+        return int(_native(load_C().vmm_export_fd, self._h_local))
 
     def close(self) -> None:
         """Unmap every view and release the allocation handles (idempotent; errors are ignored: the
         peers may already be gone at shutdown)."""
         if not self._handles:
             return
-        cu = _cu()
-        for va, size, handle in self._handles:
-            try:
-                cu.cuMemUnmap(va, size)
-                cu.cuMemAddressFree(va, size)
-                cu.cuMemRelease(handle)
-            except Exception:
-                pass
+        C = load_C()
+        for hid in self._handles:
+            C.vmm_release(hid)               # noexcept on the native side
         self._handles = None
         self.mc_ptr = 0
 
 
 def multicast_supported(device: int) -> bool:
-    cu = _cu()
-    try:
-        (err,) = cu.cuInit(0)
-        err, dev = cu.cuDeviceGet(device)
-        err, val = cu.cuDeviceGetAttribute(cu.CUdevice_attribute.CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev)
-        return err == cu.CUresult.CUDA_SUCCESS and bool(val)
-    except Exception:
-        return False
+    return bool(load_C().vmm_multicast_supported(int(device)))
 
 
 def nvls_usable(device: int, world: int) -> bool:
@@ -132,85 +89,27 @@ def nvls_usable(device: int, world: int) -> bool:
     object for ``world`` devices and add its own device to it.  Any failure (fabric manager not running,
     multicast not permitted in this container, out of handles, ...) returns False, so that all ranks can
     agree on plain CUDA-IPC buffers *before* anyone enters the collective set-up in ``alloc_nvls``."""
-    if not multicast_supported(device):
-        return False
-    cu = _cu()
-    handles = []
-    fds = []
     try:
-        dev = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
-        H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
-        prop = cu.CUmemAllocationProp()
-        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
-        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-        prop.location.id = device
-        prop.requestedHandleTypes = H
-        mcprop = cu.CUmulticastObjectProp()
-        mcprop.numDevices = max(1, int(world))
-        mcprop.handleTypes = H
-        mcprop.flags = 0
-        mcprop.size = 1
-        gran = max(int(_ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
-                           "cuMulticastGetGranularity")),
-                   int(_ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
-                           "cuMemGetAllocationGranularity")))
-        mcprop.size = gran
-        h = _ck(cu.cuMemCreate(gran, prop, 0), "cuMemCreate")
-        handles.append(h)
-        fds.append(int(_ck(cu.cuMemExportToShareableHandle(h, H, 0), "cuMemExportToShareableHandle")))
-        mc = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
-        handles.append(mc)
-        fds.append(int(_ck(cu.cuMemExportToShareableHandle(mc, H, 0), "export multicast handle")))
-        _ck(cu.cuMulticastAddDevice(mc, dev), "cuMulticastAddDevice")
-        return True
+        return bool(load_C().vmm_usable(int(device), max(1, int(world))))
     except Exception:
         return False
-    finally:
-        for fd in fds:
-            try:
-                os.close(fd)
-            except OSError:
-                pass
-        for h in reversed(handles):
-            try:
-                cu.cuMemRelease(h)
-            except Exception:
-                pass
 
 
 def map_peer_fd(fd: int, nbytes_mapped: int, device: int) -> tuple:
     """Import a peer's VMM allocation from its file descriptor and map it read/write on ``device``.
-    Returns ``(device pointer, (va, size, handle))``; the tuple goes to `unmap_peer`."""
-    cu = _cu()
-    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
-    h = _ck(cu.cuMemImportFromShareableHandle(fd, H), "cuMemImportFromShareableHandle")
+    Returns ``(device pointer, mapping)``; the mapping goes to `unmap_peer`."""
+    C = load_C()
+    hid = _native(C.vmm_import_fd, int(fd), False)
     try:
-        va = _ck(cu.cuMemAddressReserve(nbytes_mapped, 0, 0, 0), "cuMemAddressReserve")
-        try:
-            _ck(cu.cuMemMap(va, nbytes_mapped, 0, h, 0), "cuMemMap")
-        except Exception:
-            cu.cuMemAddressFree(va, nbytes_mapped)
-            raise
-        access = cu.CUmemAccessDesc()
-        access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-        access.location.id = device
-        access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
-        _ck(cu.cuMemSetAccess(va, nbytes_mapped, [access], 1), "cuMemSetAccess")
+        ptr = _native(C.vmm_map, hid, int(nbytes_mapped), 0, int(device))
     except Exception:
-        cu.cuMemRelease(h)
+        C.vmm_release(hid)
         raise
-    return int(va), (va, nbytes_mapped, h)
+    return int(ptr), hid
 
 
-def unmap_peer(mapping: tuple) -> None:
-    cu = _cu()
-    va, size, h = mapping
-    try:
-        cu.cuMemUnmap(va, size)
-        cu.cuMemAddressFree(va, size)
-        cu.cuMemRelease(h)
-    except Exception:
-        pass
+def unmap_peer(mapping) -> None:
+    load_C().vmm_release(int(mapping))
 
 
 def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock_dir: Optional[str] = None) -> NvlsBuffer:
@@ -223,10 +122,9 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     same on every path, so the caller can go on using the group (``trainer.py`` falls back to CUDA-IPC)."""
     import threading
 
-    cu = _cu()
+    C = load_C()
     rank, world, device = group.rank, group.world, group.device
-    H = cu.CUmemAllocationHandleType.CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR
-    st = {"err": None, "fds": [], "mapped": [], "loose": [], "server": None, "path": None}
+    st = {"err": None, "fds": [], "ids": [], "server": -1, "path": None}
 
     def stage(fn) -> None:
         if st["err"] is None:
@@ -242,24 +140,12 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
             except OSError:
                 pass
         st["fds"].clear()
-        if st["server"] is not None:
-            st["server"].close()
-            st["server"] = None
-        if st["path"] and os.path.exists(st["path"]):
-            os.unlink(st["path"])
-        for va, size, h in st["mapped"]:
-            try:
-                cu.cuMemUnmap(va, size)
-                cu.cuMemAddressFree(va, size)
-            except Exception:
-                pass
-        for h in [m[2] for m in st["mapped"]] + st["loose"]:
-            try:
-                cu.cuMemRelease(h)
-            except Exception:
-                pass
-        st["mapped"].clear()
-        st["loose"].clear()
+        if st["server"] >= 0:
+            C.uds_close(st["server"], st["path"] or "")
+            st["server"] = -1
+        for hid in st["ids"]:
+            C.vmm_release(hid)
+        st["ids"].clear()
 
     def agree(extra=None) -> list:
         got = group._exchange((st["err"], extra))
@@ -273,36 +159,17 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     def s_create() -> None:
         torch.cuda.set_device(device)
         torch.cuda.current_stream().synchronize()     # make sure the primary context exists
-        if not multicast_supported(device):
+        if not C.vmm_multicast_supported(device):
             raise NvlsUnavailable("device does not report CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED")
-        _ck(cu.cuInit(0), "cuInit")
-        st["dev"] = _ck(cu.cuDeviceGet(device), "cuDeviceGet")
-        prop = cu.CUmemAllocationProp()
-        prop.type = cu.CUmemAllocationType.CU_MEM_ALLOCATION_TYPE_PINNED
-        prop.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-        prop.location.id = device
-        prop.requestedHandleTypes = H
-        mcprop = cu.CUmulticastObjectProp()
-        mcprop.numDevices = world
-        mcprop.handleTypes = H
-        mcprop.flags = 0
         nbytes = numel * _DT_SIZE[dtype]
-        mcprop.size = nbytes
-        gran_mc = _ck(cu.cuMulticastGetGranularity(mcprop, cu.CUmulticastGranularity_flags.CU_MULTICAST_GRANULARITY_RECOMMENDED),
-                      "cuMulticastGetGranularity")
-        gran_mem = _ck(cu.cuMemGetAllocationGranularity(prop, cu.CUmemAllocationGranularity_flags.CU_MEM_ALLOC_GRANULARITY_RECOMMENDED),
-                       "cuMemGetAllocationGranularity")
-        st["gran"] = gran = max(int(gran_mc), int(gran_mem))
-        st["size"] = size = (nbytes + gran - 1) // gran * gran
-        mcprop.size = size
-        st["h_local"] = _ck(cu.cuMemCreate(size, prop, 0), "cuMemCreate")
-        st["loose"].append(st["h_local"])
-        st["fd_local"] = int(_ck(cu.cuMemExportToShareableHandle(st["h_local"], H, 0), "cuMemExportToShareableHandle"))
+        st["h_local"], st["size"], st["gran"] = _native(C.vmm_create, device, nbytes, world)
+        st["ids"].append(st["h_local"])
+        st["fd_local"] = int(_native(C.vmm_export_fd, st["h_local"]))
         st["fds"].append(st["fd_local"])
         if rank == 0:
-            st["mc"] = _ck(cu.cuMulticastCreate(mcprop), "cuMulticastCreate")
-            st["loose"].append(st["mc"])
-            st["fd_mc"] = int(_ck(cu.cuMemExportToShareableHandle(st["mc"], H, 0), "export multicast handle"))
+            st["mc"] = _native(C.vmm_mc_create, world, st["size"])
+            st["ids"].append(st["mc"])
+            st["fd_mc"] = int(_native(C.vmm_export_fd, st["mc"]))
             st["fds"].append(st["fd_mc"])
 
     stage(s_create)
@@ -313,33 +180,13 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
     paths = [os.path.join(base, f"hb-nvls-{tag}-{name.replace('.', '_')}-{r}.sock") for r in range(world)]
 
     def s_listen() -> None:
-        if os.path.exists(paths[rank]):
-            os.unlink(paths[rank])
         st["path"] = paths[rank]
-        server = socket.socket(socket.AF_UNIX, socket.SOCK_STREAM)
-        st["server"] = server
-        server.bind(paths[rank])
-        server.listen(world)
-        server.settimeout(60)                      # a peer that dies mid-way must not hang this rank forever
+        st["server"] = int(_native(C.uds_listen, paths[rank], world))
 
     stage(s_listen)
     agree()                                        # everyone is listening
 
     # ---- stage 3: descriptors travel (SCM_RIGHTS), peers' memory is mapped, the device joins the team --------------
-    def map_handle(h) -> int:
-        size = st["size"]
-        va = _ck(cu.cuMemAddressReserve(size, st["gran"], 0, 0), "cuMemAddressReserve")
-        try:
-            _ck(cu.cuMemMap(va, size, 0, h, 0), "cuMemMap")
-        except Exception:
-            cu.cuMemAddressFree(va, size)
-            raise
-        st["mapped"].append((va, size, h))
-        if h in st["loose"]:
-            st["loose"].remove(h)
-        _ck(cu.cuMemSetAccess(va, size, [st["access"]], 1), "cuMemSetAccess")
-        return int(va)
-
     ptrs = [0] * world
 
     def s_swap() -> None:
@@ -348,7 +195,7 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
 
         def receiver() -> None:
             try:
-                recv_box.update(_recv_fds(st["server"], world - 1, 2))
+                recv_box.update(_recv_fds(st["server"], world - 1, 2))   # a peer that dies must not hang us: 60 s
             except Exception as exc:     # noqa: BLE001
                 recv_err.append(exc)
 
@@ -362,44 +209,39 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
                 except Exception as exc:     # noqa: BLE001 - keep serving the other peers
                     send_err = send_err or exc
         t.join()
-        st["server"].close()
-        st["server"] = None
-        os.unlink(paths[rank])
+        C.uds_close(st["server"], paths[rank])
+        st["server"] = -1
         for fds in recv_box.values():
             st["fds"].extend(fds)
         if send_err or recv_err:
             raise send_err or recv_err[0]
 
-        access = cu.CUmemAccessDesc()
-        access.location.type = cu.CUmemLocationType.CU_MEM_LOCATION_TYPE_DEVICE
-        access.location.id = device
-        access.flags = cu.CUmemAccess_flags.CU_MEM_ACCESS_FLAGS_PROT_READWRITE
-        st["access"] = access
-        ptrs[rank] = map_handle(st["h_local"])
+        size, gran = st["size"], st["gran"]
+        ptrs[rank] = int(_native(C.vmm_map, st["h_local"], size, gran, device))
         for p in range(world):
             if p == rank:
                 continue
-            hp = _ck(cu.cuMemImportFromShareableHandle(recv_box[p][0], H), "cuMemImportFromShareableHandle")
-            st["loose"].append(hp)
-            ptrs[p] = map_handle(hp)
+            hp = _native(C.vmm_import_fd, recv_box[p][0], False)
+            st["ids"].append(hp)
+            ptrs[p] = int(_native(C.vmm_map, hp, size, gran, device))
         if rank != 0:
-            st["mc"] = _ck(cu.cuMemImportFromShareableHandle(recv_box[0][1], H), "import multicast handle")
-            st["loose"].append(st["mc"])
+            st["mc"] = _native(C.vmm_import_fd, recv_box[0][1], True)
+            st["ids"].append(st["mc"])
         for fd in st["fds"]:
             os.close(fd)
         st["fds"].clear()
-        _ck(cu.cuMulticastAddDevice(st["mc"], st["dev"]), "cuMulticastAddDevice")
+        _native(C.vmm_mc_add_device, st["mc"], device)
 
     stage(s_swap)
     agree()                                        # every device is part of the team before anyone binds
 
     # ---- stage 4: bind the local memory to the multicast object -------------------------------------------------------
-    stage(lambda: _ck(cu.cuMulticastBindMem(st["mc"], 0, st["h_local"], 0, st["size"], 0), "cuMulticastBindMem"))
+    stage(lambda: _native(C.vmm_mc_bind, st["mc"], st["h_local"], st["size"]))
     agree()
 
     # ---- stage 5: map the multicast view, zero the local slice ----------------------------------------------------------
     def s_view() -> None:
-        st["mc_ptr"] = map_handle(st["mc"])
+        st["mc_ptr"] = int(_native(C.vmm_map, st["mc"], st["size"], st["gran"], device))
         local = tensor_from_ptr(ptrs[rank], numel, dtype, device)
         local.zero_()
         torch.cuda.synchronize()
@@ -407,7 +249,9 @@ def alloc_nvls(group: PeerGroup, name: str, numel: int, dtype: torch.dtype, sock
 
     stage(s_view)
     agree()
+    # release order: the multicast view and the peers' mappings first, the local allocation last
+    ids = [st["mc"]] + [h for h in st["ids"] if h not in (st["mc"], st["h_local"])] + [st["h_local"]]
     buf = NvlsBuffer(name, numel, dtype, st["local"], ptrs, mc_ptr=st["mc_ptr"], nbytes_mapped=st["size"],
-                     _handles=list(st["mapped"]), _h_local=st["h_local"], _gran=st["gran"])
+                     _handles=ids, _h_local=st["h_local"], _gran=st["gran"])
     group.buffers[name] = buf
     return buf

@@ -443,6 +443,108 @@ def test_quantize_fp8_roundtrip(C):
         assert abs(dq.item() - x.abs().max().item() / (448.0 if fmt == ops.E4M3 else 57344.0)) < 1e-6 * max(1, dq.item())
 
 
+@pytest.mark.parametrize("R,Cc", [(128, 128), (256, 384), (1024, 4096)])
+def test_quantize_mxfp8_matches_reference(C, R, Cc):
+    """One-pass MXFP8 quantiser (row-wise operand + transposed operand, UE8M0 scales in the tcgen05.cp atom layout)
+    vs the plain-torch model: bytes and scale tables must be identical."""
+    from hypha_b200 import ops
+
+    torch.manual_seed(1)
+    x = (torch.randn(R, Cc, device="cuda") * torch.exp(torch.randn(R, 1, device="cuda") * 3)).to(torch.bfloat16)
+    x[5, 32:64] = 0                                   # an all-zero block
+    x[7, 0] = 448.0                                   # exactly representable maximum: scale 2^0, no saturation
+    q, sf, qT, sfT = ops.quantize_mxfp8(x, rowwise=True, transposed=True)
+    qr, er = ops.mxfp8_quantize_ref(x)
+    assert torch.equal(q, qr.view(torch.uint8))
+    assert torch.equal(sf, ops.mxfp8_sf_to_table(er))
+    qtr, etr = ops.mxfp8_quantize_ref(x.t().contiguous())
+    assert torch.equal(qT, qtr.view(torch.uint8))
+    assert torch.equal(sfT, ops.mxfp8_sf_to_table(etr))
+    back = ops.mxfp8_dequant_ref(q, sf)
+    assert _rel(back, x) < 0.04
+    # single-output variants write the same bytes
+    q1, sf1, _, _ = ops.quantize_mxfp8(x, rowwise=True, transposed=False)
+    _, _, qT1, sfT1 = ops.quantize_mxfp8(x, rowwise=False, transposed=True)
+    assert torch.equal(q1, q) and torch.equal(sf1, sf) and torch.equal(qT1, qT) and torch.equal(sfT1, sfT)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 128, 256), (384, 640, 512), (1024, 4096, 4096),
+                                   (4096, 1024, 8192)])
+def test_gemm_mxfp8(C, M, N, K):
+    """Block-scaled tcgen05.mma (kind::mxf8f6f4.block_scale, scales staged by tcgen05.cp) vs an fp32 matmul of the
+    de-quantised operands; rows carry very different magnitudes so a misplaced scale factor cannot hide."""
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    A = (torch.randn(M, K, device="cuda") * torch.exp2(torch.randint(-6, 7, (M, K // 32), device="cuda").float())
+         .repeat_interleave(32, dim=1)).to(torch.bfloat16)
+    B = (torch.randn(N, K, device="cuda") * torch.exp2(torch.randint(-6, 7, (N, K // 32), device="cuda").float())
+         .repeat_interleave(32, dim=1)).to(torch.bfloat16)
+    aq, asf, _, _ = ops.quantize_mxfp8(A)
+    bq, bsf, _, _ = ops.quantize_mxfp8(B)
+    out = ops.gemm_mxfp8(aq, asf, bq, bsf)
+    ref_q = ops.mxfp8_dequant_ref(aq, asf) @ ops.mxfp8_dequant_ref(bq, bsf).t()
+    assert _rel(out, ref_q) < 5e-3, _rel(out, ref_q)
+    assert _rel(out, A.float() @ B.float().t()) < 0.06
+    D0 = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    o2 = D0.clone()
+    ops.gemm_mxfp8(aq, asf, bq, bsf, out=o2, accumulate=True)
+    assert _rel(o2, D0.float() + ref_q) < 5e-3
+
+
+def test_gemm_mxfp8_fused_swiglu_epilogues(C):
+    from hypha_b200 import ops
+
+    torch.manual_seed(0)
+    M, I, H = 512, 1024, 512
+    x = torch.randn(M, H, device="cuda", dtype=torch.bfloat16)
+    wgu = (torch.randn(2 * I, H, device="cuda") * 0.05).to(torch.bfloat16)
+    xq, xsf, _, _ = ops.quantize_mxfp8(x)
+    wq, wsf, _, _ = ops.quantize_mxfp8(wgu)
+    act = torch.empty(M, I, device="cuda", dtype=torch.bfloat16)
+    gu = ops.gemm_mxfp8(xq, xsf, wq, wsf, swiglu_out=act)
+    g, u = gu[:, 0::2].float(), gu[:, 1::2].float()
+    assert _rel(act, torch.nn.functional.silu(g) * u) < 5e-3
+    # dgrad of the down projection with the SwiGLU-backward epilogue
+    wd = (torch.randn(H, I, device="cuda") * 0.05).to(torch.bfloat16)
+    dy = torch.randn(M, H, device="cuda", dtype=torch.bfloat16)
+    dyq, dysf, _, _ = ops.quantize_mxfp8(dy)
+    _, _, wTq, wTsf = ops.quantize_mxfp8(wd, rowwise=False, transposed=True)
+    dact = ops.gemm_mxfp8(dyq, dysf, wTq, wTsf)
+    dgu = torch.empty_like(gu)
+    ops.gemm_mxfp8(dyq, dysf, wTq, wTsf, out=torch.empty_like(dact), dswiglu=(gu, dgu))
+    sg = torch.sigmoid(g)
+    d = dact.float()
+    ref = torch.stack([d * u * (sg + g * sg * (1 - sg)), d * g * sg], dim=2).reshape(M, 2 * I)
+    assert _rel(dgu, ref) < 5e-3
+
+
+def test_llama_mxfp8_step_close_to_bf16(C):
+    """A Llama whose every GEMM dimension is a multiple of 128 runs all Linear GEMMs (fwd, dgrad, wgrad) on the
+    block-scaled kernel; loss and gradients stay close to the bf16 run."""
+    from hypha_b200 import ops
+    from hypha_b200.models.llama import LlamaForCausalLM, get_config
+
+    torch.manual_seed(0)
+    cfg = get_config("llama-tiny", hidden_size=256, intermediate_size=512, num_heads=2, num_kv_heads=1, head_dim=128)
+    ids = torch.randint(0, cfg.vocab_size, (2, 128), device="cuda")
+    lab = torch.roll(ids, -1, 1)
+    losses, grads, launches = [], [], []
+    for fp8 in (False, True):
+        ops.set_fp8(fp8, mode="mx")
+        net = LlamaForCausalLM(cfg, device="cuda", seed=5)
+        ops.reset_launch_count()
+        loss = net(ids, lab)
+        loss.backward()
+        launches.append(ops.launch_count())
+        losses.append(loss.item())
+        grads.append(net.flat.grad.float().clone())
+    ops.set_fp8(False)
+    assert launches[1] > launches[0], "the MXFP8 run must add quantiser launches (it silently ran bf16 otherwise)"
+    assert abs(losses[0] - losses[1]) < 0.05, losses
+    assert _rel(grads[1], grads[0]) < 0.12, _rel(grads[1], grads[0])
+
+
 def test_llama_fp8_step_close_to_bf16(C):
     from hypha_b200 import ops
     from hypha_b200.models.llama import LlamaForCausalLM, get_config
@@ -453,7 +555,7 @@ def test_llama_fp8_step_close_to_bf16(C):
     lab = torch.roll(ids, -1, 1)
     losses, grads = [], []
     for fp8 in (False, True):
-        ops.set_fp8(fp8)
+        ops.set_fp8(fp8, mode="tensor")
         net = LlamaForCausalLM(cfg, device="cuda", seed=5)
         loss = net(ids, lab)
         loss.backward()
