@@ -49,6 +49,8 @@ def parse_args():
                     help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
                          "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
+    ap.add_argument("--fp8-mode", choices=["mx", "tensor"], default="mx",
+                    help="mx: MXFP8 block scaling (tcgen05.mma.kind::mxf8f6f4.block_scale); tensor: per-tensor scaling")
     ap.add_argument("--via-box", action="store_true",
                     help="measure through the Hypha API instead of the trainer API: gateway + data node + one worker per "
                          "GPU + scheduler in this process, leases, one executor process per GPU, per-step status RPCs, "
@@ -331,7 +333,7 @@ def main():
             and not any(a == "--attn" or a.startswith("--attn=") for a in sys.argv)):
         args.attn = "cudnn"              # the stock-components arm: library GEMMs, library attention, NCCL
     ops.set_attention_backend(args.attn)
-    ops.set_fp8(args.fp8)
+    ops.set_fp8(args.fp8, mode=args.fp8_mode)
     if args.impl == "baseline":
         ops.set_gemm_backend("cublas")
     base_cfg = get_config(args.model)
@@ -505,7 +507,9 @@ def main():
             "value": value, "unit": "tokens/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None,
-            "dtype": "fp8 GEMMs (e4m3 fwd / e5m2 grad, per-tensor scaling), bf16 elsewhere" if args.fp8 else "bf16",
+            "dtype": (("MXFP8 GEMMs (e4m3, UE8M0 scale per 32 K-elements, block-scaled tcgen05.mma), bf16 elsewhere"
+                       if args.fp8_mode == "mx" else "fp8 GEMMs (e4m3 fwd / e5m2 grad, per-tensor scaling), bf16 elsewhere")
+                      if args.fp8 else "bf16"),
             "data": "synthetic tokens, random-init weights", "impl": args.impl,
             "config": {
                 "model": cfg.name, "params": cfg.num_params(), "global_batch": B * world,

@@ -82,9 +82,10 @@ void quantize_fp8(const bf16* x, uint8_t* out, int64_t n, const float* amax, flo
 //   q  [R, C]  scaled along C (the operand when the GEMM contracts over C), scale table sf
 //   qT [C, R]  = x^T scaled along R (the operand when the GEMM contracts over R), scale table sfT
 // so every GEMM of a Linear layer (fwd: x, W; dgrad: dy, W^T; wgrad: dy^T, x^T) reads K-major operands.
-// A scale table is laid out the way tcgen05.cp wants to find it in shared memory -- per (128-row block, 128-element
-// K block) one 512-byte atom with byte (r % 32) * 16 + (r / 32) * 4 + (k / 32) -- so the GEMM fetches one contiguous
-// 512-byte box per operand and stage and needs no shuffle.
+// A scale table is laid out the way tcgen05.cp wants to find it in shared memory -- per (128-element K block, 128-row
+// block) one 512-byte atom with byte (r % 32) * 16 + (r / 32) * 4 + (k / 32), K blocks outermost -- so the GEMM
+// fetches one contiguous box per operand and stage (the two row blocks of a 256-wide tile are adjacent) and needs no
+// shuffle.
 //
 // Scale of a block: 2^e with e = ceil(log2(amax / 448)), i.e. the smallest power of two that keeps the block inside
 // the e4m3 range without saturating; stored biased (e + 127), amax = 0 stores 0.
@@ -180,11 +181,12 @@ __global__ void __launch_bounds__(256) quant_mxfp8_kernel(const bf16* __restrict
     sf_col[(c1 & 31) * 16 + (c1 >> 5) * 4 + rb] = (uint8_t)e1;
     __syncthreads();
   }
+  // tables are [K block][128-row block][512]: for q the K blocks run along C (tc), for qT along R (tr)
   if (kRow && threadIdx.x < 32)
-    reinterpret_cast<uint4*>(sf + ((size_t)tr * gridDim.x + tc) * 512)[threadIdx.x] =
+    reinterpret_cast<uint4*>(sf + ((size_t)tc * gridDim.y + tr) * 512)[threadIdx.x] =
         reinterpret_cast<const uint4*>(sf_row)[threadIdx.x];
   if (kCol && threadIdx.x >= 32 && threadIdx.x < 64)
-    reinterpret_cast<uint4*>(sfT + ((size_t)tc * gridDim.y + tr) * 512)[threadIdx.x - 32] =
+    reinterpret_cast<uint4*>(sfT + ((size_t)tr * gridDim.x + tc) * 512)[threadIdx.x - 32] =
         reinterpret_cast<const uint4*>(sf_col)[threadIdx.x - 32];
 }
 

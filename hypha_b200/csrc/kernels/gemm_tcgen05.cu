@@ -61,6 +61,7 @@ struct GemmParams {
   int a_fmt, b_fmt;        // fp8 only: 0 = e4m3, 1 = e5m2
   const float* scale;      // fp8 only: device dequantisation factor of A
   const float* scale_b;    // fp8 only: device dequantisation factor of B
+  int sf_ahead;            // MXFP8: copy the scale factors of K block kb+1 before issuing the MMAs of block kb
   int swiglu;              // 2-CTA kernel: the output columns interleave gate/up; ALSO store silu(gate)*up through tma_e
   const bf16* gu;          // 2-CTA kernel, dswiglu epilogue: D is NOT written; instead the [M, N] accumulator is taken as
   int ld_gu;               // d(act) and d(gate|up)[M, 2N] = swiglu'(gu) * d(act) leaves through tma_e (interleaved columns)
@@ -294,28 +295,36 @@ constexpr int kGroupM2 = 8;
 //          (kind::mxf8f6f4.block_scale).  The scale factors of a K block travel with the operands (one more
 //          TMA box per operand and stage), are copied shared -> tensor memory by tcgen05.cp right before the
 //          four MMAs that consume them, and are applied inside the tensor core.  Both operands K-major.
-//          256x128 tiles: two 128-column accumulators + 8 scale-factor columns fit the 512 TMEM columns with the
-//          epilogue of tile i still overlapping the main loop of tile i+1 (a 256-wide tile would have to share
-//          columns between the scale factors and the accumulator being drained).
+//          256x256 tiles like the other modes (a 256x128 tile measured 1.5 PFLOP/s against 2.8 of the per-tensor
+//          kernel: its 171 FLOP per operand byte runs into the ~6.3 KB/clk the L2 can feed the SMs).  Two 256-column
+//          accumulators fill the 512 TMEM columns, so the scale-factor columns of tile i (4 slots of 4 + 8) live in
+//          the first 64 columns of the OTHER accumulator: the epilogue of tile i-1 reads those columns first and says so (sf_free), the rest
+//          of its drain still overlaps the main loop of tile i.
 template <int kMode>
 struct Cfg2 {
   static constexpr bool kFp8 = kMode != 0;
   static constexpr bool kMx = kMode == 2;
-  static constexpr int TN = kMx ? 128 : 256;           // tile columns
-  static constexpr int stages = kMx ? 7 : 6;
+  static constexpr int TN = 256;                        // tile columns
+  // MXFP8: the scale factors cost 1.5 KB per stage; a sixth stage fits once every epilogue warp stages its stores
+  // through ONE buffer instead of two (5 stages measured 2.4 PFLOP/s against 2.9 of the 6-stage per-tensor kernel:
+  // with operands coming from HBM, ~190 KB must be in flight per SM to cover the latency at this rate)
+  static constexpr int stages = 6;
+  static constexpr int epi_bufs = kMx ? 1 : 2;
   static constexpr int a_stage = 128 * BK * 2;          // 16 KB: this CTA's 128 rows of A
   static constexpr int b_stage = (TN / 2) * BK * 2;     // this CTA's half of the B rows
-  static constexpr int sf_stage = kMx ? 1024 : 0;       // SFA (this CTA's 128 rows) + SFB (all TN columns), 512 B each
+  static constexpr int sf_stage = kMx ? 1536 : 0;       // SFA (this CTA's 128 rows, 512 B) + SFB (all 256 columns, 1024 B)
   static constexpr int a_off = 0;
   static constexpr int b_off = a_off + stages * a_stage;
   static constexpr int sf_off = b_off + stages * b_stage;
-  static constexpr int epi_off = sf_off + stages * sf_stage;
-  static constexpr int bar_off = epi_off + kEpiBytes;
-  static constexpr int total = bar_off + (2 * stages + 4) * 8 + 16;
+  // the epilogue staging buffers are written with the 128-byte swizzle pattern of a 1024-byte aligned tile
+  static constexpr int epi_off = (sf_off + stages * sf_stage + 1023) / 1024 * 1024;
+  static constexpr int bar_off = epi_off + 4 * epi_bufs * kEpiWarpBuf;
+  static constexpr int total = bar_off + (2 * stages + 6) * 8 + 16;
   static constexpr int smem_bytes = total + 1024;
-  static constexpr int sf_tmem_col = 2 * TN;            // first column after the two accumulators
 };
 static_assert(Cfg2<0>::smem_bytes <= 232448 && Cfg2<2>::smem_bytes <= 232448, "shared memory budget");
+static_assert(Cfg2<0>::epi_off % 1024 == 0 && Cfg2<1>::epi_off % 1024 == 0 && Cfg2<2>::epi_off % 1024 == 0 &&
+              Cfg2<2>::b_off % 1024 == 0, "swizzled tiles need 1024-byte alignment");
 
 __device__ __forceinline__ void tile_coords2(int t, const GemmParams& p, int& tm, int& tn) {
   const int per_group = kGroupM2 * p.tiles_n;
@@ -343,6 +352,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   constexpr int kStages2 = C2::stages;
   constexpr int kAStage2 = C2::a_stage;
   constexpr int kBStage2 = C2::b_stage;
+  constexpr int kEB = C2::epi_bufs;               // staging buffers per epilogue warp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -355,9 +365,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   auto empty_bar = [&](int s) { return bars + 8u * (kStages2 + s); };
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages2 + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 2 + s); };
-  const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages2 + 4);
+  auto sffree_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 4 + s); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages2 + 6);
   volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C2::bar_off + 8 * (2 * kStages2 + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C2::bar_off + 8 * (2 * kStages2 + 6));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -389,6 +400,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
       mbar_init(tempty_bar(s), 8);  // 4 epilogue warps x 2 CTAs (used on the leader only)
+      mbar_init(sffree_bar(s), 8);  // MXFP8: the first columns of accumulator s have been read
     }
     fence_barrier_init();
   }
@@ -428,12 +440,27 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
           for (int i = 0; i < 128 / kMnPerChunk; ++i)
             tma_load_2d_2cta(sb + i * kChunk, &tma_b, lbar, n0 + i * kMnPerChunk, k0);
         }
-        if constexpr (kMx) {
-          // 512 B per (128-row block, 128-element K block): row tm*2 + rank of A's table, row tn of B's table
-          const uint32_t ssf = sf_smem + stage * C2::sf_stage;
-          tma_load_2d_2cta(ssf, &tma_sfa, lbar, 0, (tm * 2 + (int)cta_rank) * num_kb + kb);
-          tma_load_2d_2cta(ssf + 512, &tma_sfb, lbar, 0, tn * num_kb + kb);
-        }
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (kMx && warp == 3 && lane == 0) {
+    // ============================ scale-factor producer (both CTAs) =========
+    // A second TMA-issuing thread: with the three extra boxes per stage on the operand producer, the single thread's
+    // issue rate (5 TMA instructions per 512 tensor-core cycles) was what the block-scaled kernel ran at.
+    // Tables are [K block][128-row block][512 B]: this CTA's 128 rows of A, and the two adjacent blocks of the tile's
+    // 256 columns of B in one box.  The bytes land on the same full barrier the leader's operand producer armed.
+    const int mblocks = (p.M + 127) >> 7, nblocks = (p.N + 127) >> 7;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters) {
+      int tm, tn;
+      tile_coords2(t, p, tm, tn);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        const uint32_t lbar = mapa_shared(full_bar(stage), 0);
+        const uint32_t ssf = sf_smem + stage * C2::sf_stage;
+        tma_load_2d_2cta(ssf, &tma_sfa, lbar, 0, kb * mblocks + tm * 2 + (int)cta_rank);
+        tma_load_2d_2cta(ssf + 512, &tma_sfb, lbar, 0, kb * nblocks + tn * 2);
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
       }
     }
@@ -442,7 +469,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     const uint32_t idesc = kMx ? umma_idesc_mxfp8(256, TN, p.a_fmt, p.b_fmt)
                            : kFp8 ? umma_idesc_fp8(256, TN, p.a_mn, p.b_mn, p.a_fmt, p.b_fmt)
                                   : umma_idesc_bf16(256, TN, p.a_mn, p.b_mn);
-    const uint32_t tsfa = tmem_base + (uint32_t)C2::sf_tmem_col, tsfb = tsfa + 4u;
+
     const uint32_t a_lbo = p.a_mn ? kChunk : 16, b_lbo = p.b_mn ? kChunk : 16;
     const uint32_t a_kadv = p.a_mn ? UK * 128 : 32;   // MN-major: UK k-rows of 128 B; K-major: 32 B
     const uint32_t b_kadv = p.b_mn ? UK * 128 : 32;
@@ -455,17 +482,41 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
+      // MXFP8: this tile's scale factors sit in the first 64 columns of the other accumulator
+      const uint32_t tsf0 = tmem_base + (uint32_t)((acc ^ 1) * TN);
+      if constexpr (kMx) {
+        if (it > 0) {                      // ... which tile it-1's epilogue must have read (it reads them first)
+          mbar_wait(sffree_bar(acc ^ 1), (uint32_t)((it - 1) >> 1) & 1u);
+          tc_fence_after();
+        }
+      }
+      // MXFP8: copy the scale factors of K block `kb` (stage `st`) shared -> tensor memory of BOTH CTAs (each from
+      // its own shared memory) into slot kb % 4.  Four 16-column slots fill exactly the first 64-column chunk; the
+      // copy for block kb+1 is issued BEFORE the MMAs of block kb (ncu: with the copy in front of its own MMAs the
+      // tensor pipe sat idle ~300 cycles per K block waiting for it, 64 % active against 96 % of the unscaled kernel).
+      auto cp_sf = [&](int st, int kb) {
+        const uint32_t ssf = sf_smem + st * C2::sf_stage;
+        const uint32_t ta = tsf0 + (uint32_t)((kb & 3) * 16);
+        tmem_cp_sf_2cta(ta, umma_sf_desc(ssf));
+        tmem_cp_sf_2cta(ta + 4u, umma_sf_desc(ssf + 512));
+        tmem_cp_sf_2cta(ta + 8u, umma_sf_desc(ssf + 1024));
+      };
       for (int kb = 0; kb < num_kb; ++kb) {
-        mbar_wait(full_bar(stage), phase);
-        tc_fence_after();
+        if (!kMx || !p.sf_ahead || kb == 0) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+        }
         const uint32_t sa = a_smem + stage * kAStage2;
         const uint32_t sb = b_smem + stage * kBStage2;
+        const uint32_t tsfa = tsf0 + (uint32_t)((kb & 3) * 16), tsfb = tsfa + 4u;
         if constexpr (kMx) {
-          // scale factors of this K block: shared -> tensor memory of BOTH CTAs (each from its own shared memory);
-          // tcgen05.cp and tcgen05.mma execute in issue order, so the previous block's MMAs have read theirs
-          const uint32_t ssf = sf_smem + stage * C2::sf_stage;
-          tmem_cp_sf_2cta(tsfa, umma_sf_desc(ssf));
-          tmem_cp_sf_2cta(tsfb, umma_sf_desc(ssf + 512));
+          if (kb == 0 || !p.sf_ahead) cp_sf(stage, kb);
+          if (p.sf_ahead && kb + 1 < num_kb) {
+            const int ns = stage + 1 == kStages2 ? 0 : stage + 1;
+            mbar_wait(full_bar(ns), ns == 0 ? phase ^ 1u : phase);
+            tc_fence_after();
+            cp_sf(ns, kb + 1);
+          }
         }
 #pragma unroll
         for (int k = 0; k < BKE / UK; ++k) {
@@ -484,7 +535,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   } else if (warp >= 4) {
     // ============================ epilogue (both CTAs) =====================
     const int ew = warp - 4;
-    const uint32_t epi_smem = smem_base + C2::epi_off + ew * 2 * kEpiWarpBuf;
+    const uint32_t epi_smem = smem_base + C2::epi_off + ew * kEB * kEpiWarpBuf;
     const float out_scale = (kFp8 && !kMx && p.scale != nullptr) ? __ldg(p.scale) * __ldg(p.scale_b) : 1.f;
     int it = 0;
     int buf = 0;
@@ -505,6 +556,12 @@ uint32_t actp[32];
         tmem_ld_32x32(t_addr + c * 64, r0);
         tmem_ld_32x32(t_addr + c * 64 + 32, r1);
         tmem_ld_wait();
+        if (kMx && c == 0) {
+          // the next tile's scale factors go into columns [0, 64) of this accumulator: they are in registers now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(mapa_shared(sffree_bar(acc), 0));
+        }
         if (c == TN / 64 - 1) {
           tc_fence_before();
           __syncwarp();
@@ -544,7 +601,7 @@ uint32_t actp[32];
                 outp[j * 4 + e] = *reinterpret_cast<uint32_t*>(&h);
               }
             }
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<kEB - 1>();
             __syncwarp();
             const uint32_t sbuf = epi_smem + buf * kEpiWarpBuf;
 #pragma unroll
@@ -560,7 +617,7 @@ uint32_t actp[32];
               if (col0 < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_e, sbuf, 2 * col0 + hh * 64, m0 + ew * 32);
               tma_store_commit();
             }
-            buf ^= 1;
+            buf = (kEB == 2) ? (buf ^ 1) : 0;
           }
           continue;
         }
@@ -594,7 +651,7 @@ uint32_t actp[32];
             packed[16 + i] = *reinterpret_cast<uint32_t*>(&h1);
           }
         }
-        if (lane == 0) tma_store_wait_read<1>();
+        if (lane == 0) tma_store_wait_read<kEB - 1>();
         __syncwarp();
         const uint32_t sbuf = epi_smem + buf * kEpiWarpBuf;
 #pragma unroll
@@ -610,7 +667,7 @@ uint32_t actp[32];
           if (col0 < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_d, sbuf, col0, m0 + ew * 32);
           tma_store_commit();
         }
-        buf ^= 1;
+        buf = (kEB == 2) ? (buf ^ 1) : 0;
         if (p.swiglu) {
           // Fused SwiGLU: the 64 columns of this chunk are 32 (gate, up) pairs.  The activation is computed from
           // the bf16-ROUNDED pair, i.e. bit-for-bit what `swiglu_fwd_kernel` re-derives from `gu` in backward.
@@ -626,7 +683,7 @@ uint32_t actp[32];
             actp[(c & 1) * 16 + (i >> 1)] = *reinterpret_cast<uint32_t*>(&h);
           }
           if (c & 1) {
-            if (lane == 0) tma_store_wait_read<1>();
+            if (lane == 0) tma_store_wait_read<kEB - 1>();
             __syncwarp();
             const uint32_t abuf = epi_smem + buf * kEpiWarpBuf;
 #pragma unroll
@@ -643,7 +700,7 @@ uint32_t actp[32];
               if (2 * acol < p.N && m0 + ew * 32 < p.M) tma_store_2d(&tma_e, abuf, acol, m0 + ew * 32);
               tma_store_commit();
             }
-            buf ^= 1;
+            buf = (kEB == 2) ? (buf ^ 1) : 0;
           }
         }
       }
@@ -714,10 +771,10 @@ bool make_tmap(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, 
 }
 
 // Scale-factor table of an MXFP8 operand: `rows` = (128-row blocks) x (128-element K blocks), 512 bytes each.
-bool make_tmap_sf(CUtensorMap* m, const void* ptr, uint64_t rows) {
+bool make_tmap_sf(CUtensorMap* m, const void* ptr, uint64_t rows, uint32_t box_rows) {
   cuuint64_t dims[2] = {128, rows};
   cuuint64_t strides[1] = {512};
-  cuuint32_t box[2] = {128, 1};
+  cuuint32_t box[2] = {128, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -848,8 +905,8 @@ int gemm_fp8_tcgen05(const uint8_t* A, const uint8_t* B, bf16* D, int M, int N, 
 
 
 // D[M,N] (+)= A . B^T with MXFP8 operands: A [M,K] and B [N,K] fp8 (K contiguous), one UE8M0 scale per 32 consecutive
-// K-elements of every row, the scales in the tensor-core atom layout (see `quantize_mxfp8`): table[row block of 128]
-// [K block of 128][(r % 32) * 16 + (r / 32 % 4) * 4 + (k / 32 % 4)].  fp32 accumulation, bf16 output.
+// K-elements of every row, the scales in the tensor-core atom layout (see `quantize_mxfp8`): table[K block of 128]
+// [row block of 128][(r % 32) * 16 + (r / 32 % 4) * 4 + (k / 32 % 4)].  fp32 accumulation, bf16 output.
 int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, const uint8_t* sfb, bf16* D, int M, int N,
                        int K, int lda, int ldb, int ldd, int a_fmt, int b_fmt, int accumulate, cudaStream_t s,
                        bf16* act, int ld_act, const bf16* gu, int ld_gu) {
@@ -878,7 +935,7 @@ int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, c
   ok = ok && make_tmap(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32);
   ok = ok && (act != nullptr ? make_tmap(&te, act, (uint64_t)(gu != nullptr ? 2 * N : N / 2), (uint64_t)M, (uint64_t)ld_act, 64, 32)
                              : make_tmap(&te, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, 32));
-  ok = ok && make_tmap_sf(&tsa, sfa, (uint64_t)(M / 128) * num_kb) && make_tmap_sf(&tsb, sfb, (uint64_t)(N / 128) * num_kb);
+  ok = ok && make_tmap_sf(&tsa, sfa, (uint64_t)(M / 128) * num_kb, 1) && make_tmap_sf(&tsb, sfb, (uint64_t)(N / 128) * num_kb, 2);
   if (!ok) return 4;
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
@@ -888,7 +945,9 @@ int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, c
   p.swiglu = (act != nullptr && gu == nullptr) ? 1 : 0;
   p.gu = gu; p.ld_gu = ld_gu;
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = nullptr; p.scale_b = nullptr;
-  p.tiles_n = N / TN;
+  static const int sf_ahead = getenv("HYPHA_MX_SF_AHEAD") ? atoi(getenv("HYPHA_MX_SF_AHEAD")) : 0;
+  p.sf_ahead = sf_ahead;
+  p.tiles_n = (N + TN - 1) / TN;
   p.tiles_m = (M + 255) / 256;
   p.num_tiles = p.tiles_m * p.tiles_n;
   int clusters = g_num_sms / 2;

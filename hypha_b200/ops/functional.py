@@ -231,8 +231,9 @@ def gemm_fp8(aq: torch.Tensor, a_dq: torch.Tensor, bq: torch.Tensor, b_dq: torch
 
 # ---- MXFP8 ---------------------------------------------------------------------------------------------------
 def mx_sf_shape(rows: int, k: int) -> Tuple[int, int, int]:
-    """Shape of the scale table of a ``[rows, k]`` operand: one 512-byte atom per (128 rows, 128 K-elements)."""
-    return (rows // 128, k // 128, 512)
+    """Shape of the scale table of a ``[rows, k]`` operand: one 512-byte atom per (128 K-elements, 128 rows),
+    K blocks outermost."""
+    return (k // 128, rows // 128, 512)
 
 
 def quantize_mxfp8(x: torch.Tensor, rowwise: bool = True, transposed: bool = False):
@@ -268,16 +269,16 @@ def mxfp8_quantize_ref(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 
 def mxfp8_sf_to_table(e: torch.Tensor) -> torch.Tensor:
-    """Biased exponents ``[rows, k/32]`` -> the atom-layout table ``[rows/128, k/128, 512]`` the kernels use."""
+    """Biased exponents ``[rows, k/32]`` -> the atom-layout table ``[k/128, rows/128, 512]`` the kernels use."""
     rows, kb = e.shape
     t = e.reshape(rows // 128, 4, 32, kb // 4, 4)        # [row block, r/32, r%32, k block, k/32]
-    return t.permute(0, 3, 2, 1, 4).reshape(rows // 128, kb // 4, 512).contiguous()
+    return t.permute(3, 0, 2, 1, 4).reshape(kb // 4, rows // 128, 512).contiguous()
 
 
 def mxfp8_dequant_ref(q: torch.Tensor, table: torch.Tensor) -> torch.Tensor:
     """fp32 matrix an MXFP8 operand stands for (uint8-stored e4m3 + atom-layout scale table)."""
     rows, k = q.shape
-    e = table.reshape(rows // 128, k // 128, 32, 4, 4).permute(0, 3, 2, 1, 4).reshape(rows, k // 32)
+    e = table.reshape(k // 128, rows // 128, 32, 4, 4).permute(1, 3, 2, 0, 4).reshape(rows, k // 32)
     scale = torch.exp2(e.float() - 127.0)
     return (q.view(torch.float8_e4m3fn).float().reshape(rows, k // 32, 32) * scale[..., None]).reshape(rows, k)
 
@@ -306,16 +307,22 @@ def gemm_mxfp8(aq: torch.Tensor, asf: torch.Tensor, bq: torch.Tensor, bsf: torch
     return dswiglu[1] if dswiglu is not None else out
 
 
-def _weight_mx(weight: torch.Tensor):
-    """``(q, sf, qT, sfT)`` of a weight ``[N, K]``: the forward operand and the dgrad operand (W^T scaled along N),
-    cached until the optimizer rewrites the weights (2 bytes / parameter)."""
-    cache = getattr(weight, "_mx_cache", None)
-    if _FP8_CACHE_WEIGHTS and cache is not None and cache[0] == _FP8_WEIGHT_VERSION:
-        return cache[1]
-    quad = quantize_mxfp8(weight.detach(), rowwise=True, transposed=True)
-    if _FP8_CACHE_WEIGHTS:
-        weight._mx_cache = (_FP8_WEIGHT_VERSION, quad)
-    return quad
+_MX_CACHE_WEIGHTS = os.environ.get("HYPHA_MX_CACHE", "0") == "1"
+
+
+def _weight_mx(weight: torch.Tensor, transposed: bool):
+    """MXFP8 operand of a weight ``[N, K]``: ``(q, sf)`` for the forward GEMM, or ``(qT, sfT)`` (W^T scaled along N)
+    for dgrad.  Quantised where it is used: one read of the bf16 weight and one fp8 write per use is ~1 % of the
+    step, while keeping both copies resident costs 2 bytes / parameter -- 16 GB on the 8B model, i.e. more layers to
+    recompute.  ``HYPHA_MX_CACHE=1`` keeps them until the optimizer rewrites the weights."""
+    if _MX_CACHE_WEIGHTS:
+        cache = getattr(weight, "_mx_cache", None)
+        if cache is None or cache[0] != _FP8_WEIGHT_VERSION:
+            cache = weight._mx_cache = (_FP8_WEIGHT_VERSION, quantize_mxfp8(weight.detach(), rowwise=True, transposed=True))
+        quad = cache[1]
+        return (quad[2], quad[3]) if transposed else (quad[0], quad[1])
+    quad = quantize_mxfp8(weight.detach(), rowwise=not transposed, transposed=transposed)
+    return (quad[2], quad[3]) if transposed else (quad[0], quad[1])
 
 
 def _mx_ok(x2: torch.Tensor, weight: torch.Tensor) -> bool:
@@ -335,7 +342,7 @@ def _mm_fwd(x2: torch.Tensor, weight: torch.Tensor, swiglu_out: Optional[torch.T
     """y = x2 @ weight.T on the bf16 or fp8 tensor-core path (``swiglu_out``: fused SwiGLU epilogue, see `gemm`)."""
     if _mx_ok(x2, weight):
         xq, xsf, _, _ = quantize_mxfp8(x2, rowwise=True, transposed=False)
-        wq, wsf, _, _ = _weight_mx(weight)
+        wq, wsf = _weight_mx(weight, transposed=False)
         return gemm_mxfp8(xq, xsf, wq, wsf, swiglu_out=swiglu_out)
     if _fp8_ok(x2, weight):
         xq, xdq = quantize_fp8(x2, E4M3)
@@ -357,7 +364,7 @@ def _mm_bwd(dy2: torch.Tensor, x2: torch.Tensor, weight: torch.Tensor, need_dx: 
         dw = gemm_mxfp8(dyTq, dyTsf, xTq, xTsf, out=mg, accumulate=acc)
         dx = None
         if need_dx:
-            _, _, wTq, wTsf = _weight_mx(weight)
+            wTq, wTsf = _weight_mx(weight, transposed=True)
             dx = gemm_mxfp8(dyq, dysf, wTq, wTsf, out=dx_out, dswiglu=dswiglu)
         return dx, (None if mg is not None else dw)
     assert dswiglu is None, "the fused SwiGLU-backward epilogue of _mm_bwd is an MXFP8 path"
