@@ -60,8 +60,9 @@ def main():
             res["quantize"].append({"shape": [R, Cc], "outputs": tag, "ms": ms, "gbs": b / ms / 1e6,
                                     "frac_of_hbm": b / ms / 1e6 / hbm})
             print(json.dumps(res["quantize"][-1]), flush=True)
-    os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(res, open("gpurun_out/fp8_bench.json", "w"), indent=1)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump(res, open(os.path.join(out, "fp8_bench.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":

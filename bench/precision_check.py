@@ -11,7 +11,11 @@ times from the same initial weights and data order:
   torch     stock torch.optim.AdamW (fp32 master copy of the flat buffer, fp32 moments) driven by the same
             forward/backward -- the reference's optimizer (executors/accelerate/.../utils.py:56-64)
 
-and reports the loss curves (EMA-smoothed) and their relative distance.  -> gpurun_out/precision_check.json"""
+and reports the loss curves (EMA-smoothed) and their relative distance.  -> gpurun_out/precision_check.json
+
+``--kinds bf16sr,mxfp8,fp8tensor`` compares the fp8 GEMM paths against the bf16 run instead (same optimizer):
+  mxfp8      every Linear GEMM (fwd, dgrad, wgrad) on tcgen05.mma.kind::mxf8f6f4.block_scale (e4m3 + UE8M0 / 32)
+  fp8tensor  per-tensor current scaling on kind::f8f6f4 (e4m3 forward, e5m2 gradients)"""
 import argparse
 import json
 import os
@@ -41,7 +45,10 @@ def make_stream(vocab, batch, seq, steps, seed=0):
 
 
 def run(kind, cfg, stream, lr, init):
-    tr = DiLoCoTrainer.create(cfg, adamw=AdamWConfig(lr=lr, state_dtype="fp32" if kind != "bf16sr" else "bf16"),
+    from hypha_b200 import ops
+
+    ops.set_fp8(kind in ("mxfp8", "fp8tensor"), mode="mx" if kind == "mxfp8" else "tensor")
+    tr = DiLoCoTrainer.create(cfg, adamw=AdamWConfig(lr=lr, state_dtype="fp32" if kind in ("fp32", "torch") else "bf16"),
                               diloco=DiLoCoConfig(inner_steps=1 << 60), device=0, seed=11)
     if init is not None:
         tr.model.flat.data.copy_(init)
@@ -67,6 +74,7 @@ def run(kind, cfg, stream, lr, init):
             losses.append(float(tr.step(ids.pin_memory()).item()))
     del tr
     torch.cuda.empty_cache()
+    ops.set_fp8(False)
     return losses, init
 
 
@@ -84,22 +92,26 @@ def main():
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--seq", type=int, default=512)
     ap.add_argument("--lr", type=float, default=3e-4)
+    ap.add_argument("--kinds", default="fp32,bf16sr,torch")
+    ap.add_argument("--out", default="gpurun_out/precision_check.json")
     a = ap.parse_args()
+    kinds = a.kinds.split(",")
     cfg = get_config("llama-small", max_seq_len=a.seq)
     stream = make_stream(cfg.vocab_size, a.batch, a.seq, a.steps)
     curves, init = {}, None
-    for kind in ("fp32", "bf16sr", "torch"):
+    for kind in kinds:
         curves[kind], init = run(kind, cfg, stream, a.lr, init)
         print(kind, [round(curves[kind][i], 4) for i in (0, a.steps // 4, a.steps // 2, a.steps - 1)], flush=True)
     sm = {k: ema(v) for k, v in curves.items()}
     tail = slice(a.steps // 3, None)
-    rel = {f"{x}_vs_{y}": max(abs(p - q) / q for p, q in zip(sm[x][tail], sm[y][tail]))
-           for x, y in (("bf16sr", "fp32"), ("fp32", "torch"), ("bf16sr", "torch"))}
+    pairs = [(x, y) for x, y in (("bf16sr", "fp32"), ("fp32", "torch"), ("bf16sr", "torch"), ("mxfp8", "bf16sr"),
+                                 ("fp8tensor", "bf16sr")) if x in sm and y in sm]
+    rel = {f"{x}_vs_{y}": max(abs(p - q) / q for p, q in zip(sm[x][tail], sm[y][tail])) for x, y in pairs}
     out = {"model": "llama-small", "steps": a.steps, "batch": a.batch, "seq": a.seq, "lr": a.lr,
            "loss_at": {k: {str(i): v[i] for i in (0, 49, 99, 199, a.steps - 1) if i < a.steps} for k, v in sm.items()},
            "max_rel_diff_of_smoothed_loss_after_first_third": rel, "curves": curves}
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/precision_check.json", "w"))
+    json.dump(out, open(a.out, "w"))
     print(json.dumps({k: v for k, v in out.items() if k != "curves"}))
 
 

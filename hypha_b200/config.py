@@ -76,7 +76,7 @@ class NetworkMixin(TelemetryMixin):
     key_pem: str = doc("path to this node's private key (PEM, PKCS#8 Ed25519)", "")
     trust_pem: str = doc("path to the trusted CA bundle (PEM)", "")
     crls_pem: Optional[str] = doc("optional certificate revocation lists (PEM)", None)
-    listen_addresses: List[str] = doc("addresses to listen on (memory://, unix://, tcp://host:port)",
+    listen_addresses: List[str] = doc("addresses to listen on (memory://, unix://, tcp://host:port, udp://host:port)",
                                       factory=lambda: ["tcp://127.0.0.1:0"])
     external_addresses: List[str] = doc("addresses advertised to peers", factory=list)
     exclude_cidr: List[str] = doc("CIDR ranges never added to the routing table",

@@ -61,7 +61,6 @@ struct GemmParams {
   int a_fmt, b_fmt;        // fp8 only: 0 = e4m3, 1 = e5m2
   const float* scale;      // fp8 only: device dequantisation factor of A
   const float* scale_b;    // fp8 only: device dequantisation factor of B
-  int sf_ahead;            // MXFP8: copy the scale factors of K block kb+1 before issuing the MMAs of block kb
   int swiglu;              // 2-CTA kernel: the output columns interleave gate/up; ALSO store silu(gate)*up through tma_e
   const bf16* gu;          // 2-CTA kernel, dswiglu epilogue: D is NOT written; instead the [M, N] accumulator is taken as
   int ld_gu;               // d(act) and d(gate|up)[M, 2N] = swiglu'(gu) * d(act) leaves through tma_e (interleaved columns)
@@ -293,11 +292,12 @@ constexpr int kGroupM2 = 8;
 //          the fp32 accumulator is multiplied by the two dequantisation factors in the epilogue
 // kMode 2: MXFP8 -- fp8 operands with one UE8M0 scale per 32 K-elements of every row of A and B
 //          (kind::mxf8f6f4.block_scale).  The scale factors of a K block travel with the operands (one more
-//          TMA box per operand and stage), are copied shared -> tensor memory by tcgen05.cp right before the
-//          four MMAs that consume them, and are applied inside the tensor core.  Both operands K-major.
+//          TMA box per operand and stage), are copied shared -> tensor memory by tcgen05.cp from a thread of their own
+//          (in order with the MMAs the copies cost the tensor pipe a third of its time), and are applied inside the
+//          tensor core.  Both operands K-major.
 //          256x256 tiles like the other modes (a 256x128 tile measured 1.5 PFLOP/s against 2.8 of the per-tensor
 //          kernel: its 171 FLOP per operand byte runs into the ~6.3 KB/clk the L2 can feed the SMs).  Two 256-column
-//          accumulators fill the 512 TMEM columns, so the scale-factor columns of tile i (4 slots of 4 + 8) live in
+//          accumulators fill the 512 TMEM columns, so the scale-factor columns of tile i (one 12-column slot per stage) live in
 //          the first 64 columns of the OTHER accumulator: the epilogue of tile i-1 reads those columns first and says so (sf_free), the rest
 //          of its drain still overlaps the main loop of tile i.
 template <int kMode>
@@ -305,11 +305,9 @@ struct Cfg2 {
   static constexpr bool kFp8 = kMode != 0;
   static constexpr bool kMx = kMode == 2;
   static constexpr int TN = 256;                        // tile columns
-  // MXFP8: the scale factors cost 1.5 KB per stage; a sixth stage fits once every epilogue warp stages its stores
-  // through ONE buffer instead of two (5 stages measured 2.4 PFLOP/s against 2.9 of the 6-stage per-tensor kernel:
-  // with operands coming from HBM, ~190 KB must be in flight per SM to cover the latency at this rate)
-  static constexpr int stages = 6;
-  static constexpr int epi_bufs = kMx ? 1 : 2;
+  // MXFP8: the scale factors cost 1.5 KB per stage -> 5 stages; TMEM slot s (12 columns) belongs to stage s
+  static constexpr int stages = kMx ? 5 : 6;
+  static constexpr int epi_bufs = 2;
   static constexpr int a_stage = 128 * BK * 2;          // 16 KB: this CTA's 128 rows of A
   static constexpr int b_stage = (TN / 2) * BK * 2;     // this CTA's half of the B rows
   static constexpr int sf_stage = kMx ? 1536 : 0;       // SFA (this CTA's 128 rows, 512 B) + SFB (all 256 columns, 1024 B)
@@ -319,7 +317,7 @@ struct Cfg2 {
   // the epilogue staging buffers are written with the 128-byte swizzle pattern of a 1024-byte aligned tile
   static constexpr int epi_off = (sf_off + stages * sf_stage + 1023) / 1024 * 1024;
   static constexpr int bar_off = epi_off + 4 * epi_bufs * kEpiWarpBuf;
-  static constexpr int total = bar_off + (2 * stages + 6) * 8 + 16;
+  static constexpr int total = bar_off + (3 * stages + 6) * 8 + 16;
   static constexpr int smem_bytes = total + 1024;
 };
 static_assert(Cfg2<0>::smem_bytes <= 232448 && Cfg2<2>::smem_bytes <= 232448, "shared memory budget");
@@ -366,9 +364,10 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
   auto tfull_bar = [&](int s) { return bars + 8u * (2 * kStages2 + s); };
   auto tempty_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 2 + s); };
   auto sffree_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 4 + s); };
-  const uint32_t tmem_ptr_smem = bars + 8u * (2 * kStages2 + 6);
+  auto sfready_bar = [&](int s) { return bars + 8u * (2 * kStages2 + 6 + s); };
+  const uint32_t tmem_ptr_smem = bars + 8u * (3 * kStages2 + 6);
   volatile uint32_t* tmem_ptr_gen =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + C2::bar_off + 8 * (2 * kStages2 + 6));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + C2::bar_off + 8 * (3 * kStages2 + 6));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -396,6 +395,7 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
     for (int s = 0; s < kStages2; ++s) {
       mbar_init(full_bar(s), 1);    // leader's arrive.expect_tx (bytes of BOTH CTAs land here)
       mbar_init(empty_bar(s), 1);   // one multicast tcgen05.commit per phase
+      mbar_init(sfready_bar(s), 1); // MXFP8: the scale factors of this stage are in tensor memory (leader only)
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar(s), 1);
@@ -464,6 +464,34 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
         if (++stage == kStages2) { stage = 0; phase ^= 1u; }
       }
     }
+  } else if (kMx && warp == 2 && lane == 0 && leader) {
+    // ============================ scale-factor copier (leader CTA) ==========
+    // tcgen05.cp issued by the MMA thread executes in order WITH its MMAs: ncu showed the tensor pipe 64 % active
+    // against 96 % of the unscaled kernel, ~100 idle cycles per copy and three copies per 512 cycles of MMAs.  Issued
+    // from another thread the copies are ordered with the MMAs only through sfready (tcgen05.commit -> mbarrier).
+    // Slot s = 12 TMEM columns of stage s, inside the first 64-column chunk of the accumulator NOT being written.
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = cluster_id; t < p.num_tiles; t += num_clusters, ++it) {
+      const int acc = it & 1;
+      const uint32_t tsf0 = tmem_base + (uint32_t)((acc ^ 1) * TN);
+      if (it > 0) {                        // tile it-1's epilogue reads those columns first and says so
+        mbar_wait(sffree_bar(acc ^ 1), (uint32_t)((it - 1) >> 1) & 1u);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(full_bar(stage), phase);          // operands AND scale factors of both CTAs have landed
+        tc_fence_after();
+        const uint32_t ssf = sf_smem + stage * C2::sf_stage;
+        const uint32_t ta = tsf0 + (uint32_t)(stage * 12);
+        tmem_cp_sf_2cta(ta, umma_sf_desc(ssf));
+        tmem_cp_sf_2cta(ta + 4u, umma_sf_desc(ssf + 512));
+        tmem_cp_sf_2cta(ta + 8u, umma_sf_desc(ssf + 1024));
+        umma_commit_1of2(sfready_bar(stage));       // arrives on the leader's barrier when the copies are done
+        if (++stage == kStages2) { stage = 0; phase ^= 1u; }
+      }
+    }
   } else if (warp == 1 && lane == 0 && leader) {
     // ============================ MMA issuer (leader CTA) ==================
     const uint32_t idesc = kMx ? umma_idesc_mxfp8(256, TN, p.a_fmt, p.b_fmt)
@@ -482,42 +510,15 @@ gemm_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tma_a,
       mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
-      // MXFP8: this tile's scale factors sit in the first 64 columns of the other accumulator
+      // MXFP8: this tile's scale factors sit in the first 64 columns of the other accumulator (see the copier)
       const uint32_t tsf0 = tmem_base + (uint32_t)((acc ^ 1) * TN);
-      if constexpr (kMx) {
-        if (it > 0) {                      // ... which tile it-1's epilogue must have read (it reads them first)
-          mbar_wait(sffree_bar(acc ^ 1), (uint32_t)((it - 1) >> 1) & 1u);
-          tc_fence_after();
-        }
-      }
-      // MXFP8: copy the scale factors of K block `kb` (stage `st`) shared -> tensor memory of BOTH CTAs (each from
-      // its own shared memory) into slot kb % 4.  Four 16-column slots fill exactly the first 64-column chunk; the
-      // copy for block kb+1 is issued BEFORE the MMAs of block kb (ncu: with the copy in front of its own MMAs the
-      // tensor pipe sat idle ~300 cycles per K block waiting for it, 64 % active against 96 % of the unscaled kernel).
-      auto cp_sf = [&](int st, int kb) {
-        const uint32_t ssf = sf_smem + st * C2::sf_stage;
-        const uint32_t ta = tsf0 + (uint32_t)((kb & 3) * 16);
-        tmem_cp_sf_2cta(ta, umma_sf_desc(ssf));
-        tmem_cp_sf_2cta(ta + 4u, umma_sf_desc(ssf + 512));
-        tmem_cp_sf_2cta(ta + 8u, umma_sf_desc(ssf + 1024));
-      };
       for (int kb = 0; kb < num_kb; ++kb) {
-        if (!kMx || !p.sf_ahead || kb == 0) {
-          mbar_wait(full_bar(stage), phase);
-          tc_fence_after();
-        }
+        if constexpr (kMx) mbar_wait(sfready_bar(stage), phase);     // implies full_bar(stage)
+        else mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
         const uint32_t sa = a_smem + stage * kAStage2;
         const uint32_t sb = b_smem + stage * kBStage2;
-        const uint32_t tsfa = tsf0 + (uint32_t)((kb & 3) * 16), tsfb = tsfa + 4u;
-        if constexpr (kMx) {
-          if (kb == 0 || !p.sf_ahead) cp_sf(stage, kb);
-          if (p.sf_ahead && kb + 1 < num_kb) {
-            const int ns = stage + 1 == kStages2 ? 0 : stage + 1;
-            mbar_wait(full_bar(ns), ns == 0 ? phase ^ 1u : phase);
-            tc_fence_after();
-            cp_sf(ns, kb + 1);
-          }
-        }
+        const uint32_t tsfa = tsf0 + (uint32_t)(stage * 12), tsfb = tsfa + 4u;
 #pragma unroll
         for (int k = 0; k < BKE / UK; ++k) {
           const uint64_t ad = umma_smem_desc(sa + k * a_kadv, a_lbo, 1024);
@@ -945,8 +946,6 @@ int gemm_mxfp8_tcgen05(const uint8_t* A, const uint8_t* sfa, const uint8_t* B, c
   p.swiglu = (act != nullptr && gu == nullptr) ? 1 : 0;
   p.gu = gu; p.ld_gu = ld_gu;
   p.a_fmt = a_fmt; p.b_fmt = b_fmt; p.scale = nullptr; p.scale_b = nullptr;
-  static const int sf_ahead = getenv("HYPHA_MX_SF_AHEAD") ? atoi(getenv("HYPHA_MX_SF_AHEAD")) : 0;
-  p.sf_ahead = sf_ahead;
   p.tiles_n = (N + TN - 1) / TN;
   p.tiles_m = (M + 255) / 256;
   p.num_tiles = p.tiles_m * p.tiles_n;

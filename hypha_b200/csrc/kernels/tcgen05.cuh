@@ -310,6 +310,10 @@ __device__ __forceinline__ void umma_mxfp8_ss_2cta(uint32_t d_tmem, uint64_t a_d
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(sfa_tmem), "r"(sfb_tmem)
       : "memory");
 }
+// Arrive on an mbarrier of THIS CTA when the tcgen05 operations this thread issued (cta_group::2 form) have completed.
+__device__ __forceinline__ void umma_commit_1of2(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
 // Arrive (once) on the same-offset mbarrier of every CTA in `cta_mask` when prior MMAs retire.
 __device__ __forceinline__ void umma_commit_2cta(uint32_t bar, uint16_t cta_mask) {
   asm volatile(

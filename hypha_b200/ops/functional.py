@@ -828,8 +828,8 @@ class _TcgenAttnQKV(torch.autograd.Function):
     ``HYPHA_ATTN_BWD=flash2`` routes the backward through flash-attn 2 (library) for A/B runs."""
 
     @staticmethod
-    def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim):
-        scale = 1.0 / math.sqrt(head_dim)
+    def forward(ctx, qkv, batch, seq, n_heads, n_kv, head_dim, scale=None):
+        scale = 1.0 / math.sqrt(head_dim) if scale is None else float(scale)
         out = torch.empty((batch * seq, n_heads * head_dim), dtype=qkv.dtype, device=qkv.device)
         lse = torch.empty((batch, n_heads, seq), dtype=torch.float32, device=qkv.device)
         load_C().attention_fwd(qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), batch, seq, n_heads, n_kv, head_dim,
@@ -847,7 +847,7 @@ class _TcgenAttnQKV(torch.autograd.Function):
             dout = dout if dout.stride(-1) == 1 and dout.stride(0) % 8 == 0 else dout.contiguous()
             variant = os.environ.get("HYPHA_ATTN_BWD", "fused")
             return attention_bwd_tcgen05(qkv, out, dout, lse, batch, seq, n_heads, n_kv, head_dim, dqkv,
-                                         "split" if variant == "tcgen05" else variant), None, None, None, None, None
+                                         "split" if variant == "tcgen05" else variant, scale=scale), None, None, None, None, None, None
         from flash_attn.flash_attn_interface import _flash_attn_backward
 
         sl = lambda t, a, b, hh: t[:, a * head_dim: b * head_dim].view(batch, seq, hh, head_dim)
@@ -857,14 +857,15 @@ class _TcgenAttnQKV(torch.autograd.Function):
         rng = torch.zeros(2, dtype=torch.int64, device=qkv.device)
         _flash_attn_backward(do, q, k, v, out.view(batch, seq, n_heads, head_dim), lse, dq, dk, dv, 0.0, scale, True,
                              -1, -1, 0.0, None, False, rng)
-        return dqkv, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None
 
 
 _ATTN_BWD_WS: dict = {}
 
 
 def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: int, n_kv: int, head_dim: int,
-                          dqkv: Optional[torch.Tensor] = None, variant: Optional[str] = None) -> torch.Tensor:
+                          dqkv: Optional[torch.Tensor] = None, variant: Optional[str] = None,
+                          scale: Optional[float] = None) -> torch.Tensor:
     """Raw backward: returns ``dqkv [tokens, (Hq+2Hkv)*D]`` given the forward's (qkv, out, lse) and dout.
 
     ``variant`` (default ``HYPHA_ATTN_BWD`` or ``fused``): ``fused`` = one kernel, 5 GEMMs per tile pair, dQ
@@ -876,7 +877,7 @@ def attention_bwd_tcgen05(qkv, out, dout, lse, batch: int, seq: int, n_heads: in
         dqkv = torch.empty_like(qkv)
     C = load_C()
     args = (batch, seq, n_heads, n_kv, head_dim, qkv.stride(0), out.stride(0), dout.stride(0), dqkv.stride(0),
-            1.0 / math.sqrt(head_dim), cuda_stream())
+            1.0 / math.sqrt(head_dim) if scale is None else float(scale), cuda_stream())
     if variant == "fused":
         # the workspace (D, lse2 and the fp32 dQ accumulator: 4 bytes per q element) is cached per shape and
         # stream-ordered, so a 32-layer backward reuses one allocation instead of 32 x 134 MB
@@ -995,6 +996,23 @@ def _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim):
     return o.transpose(1, 2).reshape(batch * seq, n_heads * head_dim)
 
 
+def _attention_tcgen05_padded(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int,
+                              head_dim: int) -> torch.Tensor:
+    """Shapes the tcgen05 kernels are not specialised for -- head_dim < 128 (GPT-2, llama3-1b: 64) and sequences
+    that are not a multiple of 128 -- run on them all the same, zero-padded to the kernels' tile: head_dim -> 128
+    (zero q/k columns add nothing to a score, zero v columns give zero outputs that are sliced off; the softmax
+    scale stays 1/sqrt(head_dim)) and seq -> the next multiple of 128 (under the causal mask no real query sees a
+    padded key; padded queries are discarded and receive zero gradient, so they contribute nothing to dK / dV).
+    Exact, at the price of the padding's FLOPs and two copies -- no library kernel on the default path."""
+    H = n_heads + 2 * n_kv
+    S2 = (seq + 127) // 128 * 128
+    x = qkv.reshape(batch, seq, H, head_dim)
+    xp = torch.zeros((batch, S2, H, 128), dtype=qkv.dtype, device=qkv.device)
+    xp[:, :seq, :, :head_dim] = x
+    out = _TcgenAttnQKV.apply(xp.view(batch * S2, H * 128), batch, S2, n_heads, n_kv, 128, 1.0 / math.sqrt(head_dim))
+    return out.view(batch, S2, n_heads, 128)[:, :seq, :, :head_dim].reshape(batch * seq, n_heads * head_dim)
+
+
 def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: int,
                   head_dim: int) -> torch.Tensor:
     """Causal self-attention on a fused (already RoPE'd) qkv activation -> ``[tokens, Hq*D]``."""
@@ -1003,11 +1021,14 @@ def attention_qkv(qkv: torch.Tensor, batch: int, seq: int, n_heads: int, n_kv: i
     if (_ATTN_BACKEND == "tcgen05" and head_dim == 128 and seq % 128 == 0 and qkv.dtype == torch.bfloat16
             and n_heads % n_kv == 0 and qkv.stride(-1) == 1 and qkv.stride(0) % 8 == 0):
         return _TcgenAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
+    if (_ATTN_BACKEND == "tcgen05" and qkv.dtype == torch.bfloat16 and n_heads % n_kv == 0 and 0 < head_dim <= 128
+            and head_dim % 8 == 0):
+        return _attention_tcgen05_padded(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "flash2":
         return _FlashAttnQKV.apply(qkv, batch, seq, n_heads, n_kv, head_dim)
     if _ATTN_BACKEND == "tcgen05":
-        _note_fallback("attention", f"tcgen05 kernels cover head_dim 128 and seq % 128 == 0 "
-                                    f"(got head_dim={head_dim}, seq={seq}): cuDNN used")
+        _note_fallback("attention", f"tcgen05 kernels cover bf16, head_dim <= 128 (multiple of 8) and an integral GQA ratio "
+                                    f"(got head_dim={head_dim}, {qkv.dtype}, heads {n_heads}/{n_kv}): cuDNN used")
     return _attention_sdpa(qkv, batch, seq, n_heads, n_kv, head_dim)      # cudnn, or a shape tcgen05 does not cover
 
 

@@ -536,13 +536,43 @@ class DiLoCoOuter:
         self.momentum.zero_()
         self._returning = True          # `readmit` fetches the owner map (and the shard's state) from the others
 
-    def step_resilient(self, max_retries: int = 2) -> tuple:
+    @staticmethod
+    def merge_verdicts(verdicts: List[tuple]) -> tuple:
+        """One verdict for all survivors from their per-rank ``(status, missing mask)`` of a fused step.
+
+        The barrier time-outs are per rank, so the ranks of one launch can disagree: a slow rank may arrive inside one
+        survivor's window and after another's.  A rank that PASSED barrier 1 has run phase B -- it changed its
+        theta_outer / momentum and stored new parameters into its peers' buffers -- so a mix of "completed" (0) or
+        "failed mid-broadcast" (2) with "timed out at barrier 1" (1) cannot be retried by dropping ranks: every rank
+        must abort and restore.  Only when NOBODY got past barrier 1 is the state untouched everywhere; the missing
+        ranks are then the union of what the survivors saw."""
+        if not verdicts:
+            return (0, 0)
+        sts = [int(v[0]) for v in verdicts]
+        missing = 0
+        for v in verdicts:
+            missing |= int(v[1])
+        if all(s == 0 for s in sts):
+            return (0, 0)
+        if all(s == 1 for s in sts):
+            return (1, missing)
+        return (2, missing)
+
+    def step_resilient(self, max_retries: int = 2, agree=None) -> tuple:
         """``step()`` that survives ranks that never show up: on a barrier-1 timeout the missing
-        ranks are dropped, their shards adopted, and the step is retried with the survivors."""
+        ranks are dropped, their shards adopted, and the step is retried with the survivors.
+
+        ``agree``: a control-plane all-gather among the ranks that are still alive (``agree(obj) -> [obj of every
+        rank that answered]``, e.g. the executor's membership exchange).  With it the survivors settle on ONE verdict
+        (`merge_verdicts`) before anyone retries, so that a rank which saw the step fail mid-broadcast stops all of
+        them; without it each rank acts on its own status (single-process drills)."""
         for _ in range(max_retries + 1):
             rnd = self.round
             self.step()
             st, missing = self.check()
+            if agree is not None:
+                st, missing = self.merge_verdicts([tuple(v) for v in agree((int(st), int(missing)))])
+                self.last_status = (st, missing)
             if st == 0:
                 return (0, 0)
             self.round = rnd                       # the failed attempt did not advance the round
@@ -596,7 +626,8 @@ class DiLoCoOuter:
 
     def state_dict(self) -> Dict[str, torch.Tensor]:
         sd = {"theta_outer": self.theta_outer, "momentum": self.momentum,
-              "round": torch.tensor(self.round), "shard_begin": torch.tensor(self.shard_begin)}
+              "round": torch.tensor(self.round), "shard_begin": torch.tensor(self.shard_begin),
+              "world": torch.tensor(self.world)}
         if self.backend == "fused":
             # the pseudo-gradient is theta - anchor, anchor = the weights right after the last outer step (bf16,
             # full length, one copy per rank): part of the state unless the checkpoint is taken exactly at a
@@ -605,6 +636,16 @@ class DiLoCoOuter:
         return sd
 
     def load_state_dict(self, sd) -> None:
+        # a shard only makes sense at the place and team size it was saved for
+        if "world" in sd and int(sd["world"]) != self.world:
+            raise ValueError(f"outer state was saved by a team of {int(sd['world'])}, this one has {self.world} ranks")
+        if "shard_begin" in sd and int(sd["shard_begin"]) != self.shard_begin:
+            raise ValueError(f"outer state belongs to the shard at {int(sd['shard_begin'])}, this rank owns "
+                             f"{self.shard_begin} (rank order changed?)")
+        if tuple(sd["theta_outer"].shape) != tuple(self.theta_outer.shape):
+            raise ValueError(f"outer shard has {tuple(sd['theta_outer'].shape)} elements, expected {tuple(self.theta_outer.shape)}")
+        if self.backend == "fused" and len(getattr(self, "segments", {})) > 1:
+            raise ValueError("cannot load outer state while this rank holds adopted shards: restore with the full membership")
         self.theta_outer.copy_(sd["theta_outer"])
         self.momentum.copy_(sd["momentum"])
         self.round = int(sd["round"])

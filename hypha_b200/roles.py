@@ -100,16 +100,19 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
 
         derived = peer_id_from_key_pem(cfg.key_pem)      # identity = public key, like the reference
         if peer_id is not None and peer_id != derived and any(
-                str(a).startswith("tcp://") for a in list(cfg.listen_addresses) + list(getattr(cfg, "gateway_addresses", []) or [])):
+                str(a).startswith(("tcp://", "udp://")) for a in list(cfg.listen_addresses) + list(getattr(cfg, "gateway_addresses", []) or [])):
             # peers check the claimed id against the TLS certificate: a chosen name would be refused on every link
             tel.logger.warning("--peer-id %s ignored: with mTLS the peer id is the one of the node's key (%s)", peer_id, derived)
             peer_id = derived
         elif peer_id is None:
             peer_id = derived
     net = Network(peer_id or f"{role}-{M.new_id()[:8]}", agent=f"hypha-{role}", relay_server=relay_server,
-                  dht_server=dht_server, tls=tls)          # mTLS applies to tcp:// links only
+                  dht_server=dht_server, tls=tls,         # certificates authenticate tcp:// (mTLS) and udp:// links
+                  exclude_cidrs=tuple(getattr(cfg, "exclude_cidr", []) or []))   # kept out of the Kademlia routing table
     if any(a.startswith("tcp://") for a in cfg.listen_addresses) and net.tls is None:
         tel.logger.warning("tcp:// listener without cert_pem/key_pem/trust_pem: the link is NOT encrypted")
+    if any(a.startswith("udp://") for a in cfg.listen_addresses) and net.tls is None:
+        tel.logger.warning("udp:// listener without cert_pem/key_pem/trust_pem: the link is encrypted but peers are NOT authenticated")
     tel.register_bandwidth(net.counters)
     node = Node(role, net, tel)
     net.enable_dht_handlers()

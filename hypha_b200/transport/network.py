@@ -309,6 +309,8 @@ class SocketLink(Link):
 
 
 _MEMORY_LISTENERS: Dict[str, "Network"] = {}
+DCUTR_PROTOCOL = "/libp2p/dcutr"
+DCUTR_RETRY_S = 30.0
 
 
 # ---------------------------------------------------------------------------------------------
@@ -389,8 +391,13 @@ class Network:
     """Per-role network handle (what the reference calls ``Network`` + ``NetworkDriver``)."""
 
     def __init__(self, peer_id: Optional[str] = None, *, agent: str = "hypha-b200",
-                 relay_server: bool = False, dht_server: bool = False, tls: Optional[Dict[str, str]] = None):
+                 relay_server: bool = False, dht_server: bool = False, tls: Optional[Dict[str, str]] = None,
+                 exclude_cidrs: Tuple[str, ...] = (), allow_cidrs: Tuple[str, ...] = ()):
+        from .kad import CidrFilter, RoutingTable
+
         self.peer_id = peer_id or new_peer_id()
+        # Kademlia routing table: DHT servers learnt through identify, filtered by CIDR (kad.rs:394-432)
+        self.kad = RoutingTable(self.peer_id, cidr=CidrFilter(exclude_cidrs, allow_cidrs))
         # mutual TLS on tcp:// links (the reference's mTLS, crates/network/src/cert.rs:30-80,
         # rfc/2025-05-30_mtls.md): {"cert_pem": chain file, "key_pem": key file, "trust_pem": CA file,
         # "crls_pem": optional}.  memory:// and unix:// links rely on process / file-system isolation.
@@ -422,6 +429,9 @@ class Network:
         self.listen_addrs: List[str] = []
         self.external_addrs: List[str] = []
         self._servers: List[asyncio.AbstractServer] = []
+        self._udp: List[Any] = []             # UdpEndpoint objects: the first one also carries outgoing udp:// dials
+        self.relayed_frames = 0               # frames this node forwarded as a relay server
+        self._dcutr_last: Dict[str, float] = {}
         self._handlers: Dict[str, List[HandlerRegistration]] = {}
         self._hid = itertools.count(1)
         self._pending: Dict[str, asyncio.Future] = {}
@@ -472,7 +482,10 @@ class Network:
 
     # -- listen / dial -----------------------------------------------------------------------
     async def listen(self, addr: str) -> str:
-        """``memory://name`` | ``unix:///path`` | ``tcp://host:port`` (port 0 = ephemeral)."""
+        """``memory://name`` | ``unix:///path`` | ``tcp://host:port`` | ``udp://host:port`` (port 0 = ephemeral).
+
+        ``udp://`` is the encrypted reliable datagram transport of `transport/udplink.py` (the reference's QUIC
+        listener); one socket serves every connection of this node, incoming and outgoing."""
         if addr.startswith("memory://"):
             if addr in _MEMORY_LISTENERS and not _MEMORY_LISTENERS[addr].closed:
                 raise NetworkError(f"address in use: {addr}")
@@ -491,10 +504,26 @@ class Network:
             port = srv.sockets[0].getsockname()[1]
             addr = f"tcp://{host}:{port}"
             self._servers.append(srv)
+        elif addr.startswith("udp://"):
+            host, port = addr[len("udp://"):].rsplit(":", 1)
+            ep = await self._udp_endpoint(host, int(port))
+            addr = f"udp://{host}:{ep.local_addr[1]}"
         else:
             raise NetworkError(f"unsupported address {addr!r}")
         self.listen_addrs.append(addr)
         return addr
+
+    async def _udp_endpoint(self, host: Optional[str] = None, port: int = 0):
+        """The node's UDP endpoint (created on first use; a listen address creates it on that port)."""
+        from .udplink import UdpEndpoint
+
+        if host is None and self._udp:
+            return self._udp[0]
+        ep = UdpEndpoint(self.tls, lambda link: self._spawn(self._socket_loop(link)))
+        await asyncio.get_running_loop().create_datagram_endpoint(lambda: ep, local_addr=(host or "0.0.0.0", port))
+        self._udp.append(ep)
+        self._enable_dcutr()
+        return ep
 
     def add_external_address(self, addr: str) -> None:
         if addr not in self.external_addrs:
@@ -516,8 +545,12 @@ class Network:
 
     async def _drop_link(self, link: Link) -> None:
         await link.close()
+        hf = getattr(link, "_hello_fut", None)
+        if hf is not None and not hf.done():          # the other side hung up during identify: fail the dial now
+            hf.set_exception(DialError("connection closed during identify"))
         if link.peer_id and self.links.get(link.peer_id) is link:
             del self.links[link.peer_id]
+            self.kad.mark_disconnected(link.peer_id)
             self._peer_topics.pop(link.peer_id, None)
             for sid, st in list(self._streams.items()):
                 if st.peer == link.peer_id:          # half-received files must not look complete
@@ -531,7 +564,8 @@ class Network:
         return {"t": "hello", "peer": self.peer_id, "agent": self.agent,
                 "addrs": list(self.external_addrs or self.listen_addrs),
                 "topics": list(self._subs.keys()), "relay": self.relay_server, "dht": self.dht_server,
-                "known": {p: a for p, a in self.peer_addrs.items()} if self.relay_server else {}}
+                "known": {p: a for p, a in self.peer_addrs.items()} if self.relay_server else {},
+                "servers": {p: self.kad.addrs(p) for p in self.kad.peers()[:64]} if self.dht_server else {}}
 
     async def dial(self, addr: str, timeout: float = 5.0) -> str:
         """Connect to ``addr``; returns the remote peer id once identify completed."""
@@ -555,6 +589,16 @@ class Network:
                     asyncio.get_running_loop().create_connection(_FrameProtocol, host, int(port),
                                                                  ssl=self._ssl_context(False)), timeout)
                 link = SocketLink(proto)
+                self._spawn(self._socket_loop(link))
+            elif addr.startswith("udp://"):
+                from .udplink import UdpError
+
+                host, port = addr[len("udp://"):].rsplit(":", 1)
+                ep = await self._udp_endpoint()
+                try:
+                    link = await ep.connect(host, int(port), timeout)
+                except UdpError as exc:
+                    raise DialError(f"dial {addr} failed: {exc}") from exc
                 self._spawn(self._socket_loop(link))
             else:
                 raise DialError(f"unsupported address {addr!r}")
@@ -596,6 +640,8 @@ class Network:
         self.links.clear()
         for s in self._servers:
             s.close()
+        for ep in self._udp:
+            ep.close()
         for t in list(self._tasks):
             t.cancel()
         for fut in self._pending.values():
@@ -620,8 +666,84 @@ class Network:
                 continue
         for p, l in self.links.items():
             if getattr(l, "is_relay", False) and not l.closed:
+                # traffic for this peer goes through the gateway: try to replace the detour by a direct link in the
+                # background (hole punching over the node's UDP socket, the reference's dcutr behaviour)
+                if self._udp and time.monotonic() - self._dcutr_last.get(peer, -1e9) > DCUTR_RETRY_S:
+                    self._dcutr_last[peer] = time.monotonic()
+                    self._spawn(self._upgrade_quietly(peer))
                 return l, True
         raise RequestFailed(f"no route to {peer}")
+
+    # -- direct connection upgrade through relay (dcutr) ----------------------------------------------------------------
+    def _dcutr_addrs(self) -> List[str]:
+        addrs = [a for a in (self.external_addrs or self.listen_addrs) if a.startswith(("udp://", "tcp://"))]
+        return sorted(addrs, key=lambda a: not a.startswith("udp://"))            # udp first: it can be hole-punched
+
+    def _enable_dcutr(self) -> None:
+        if getattr(self, "_dcutr_on", False):
+            return
+        self._dcutr_on = True
+
+        async def serve(peer: str, msg: Any):
+            theirs = [a for a in (msg.get("connect") or []) if isinstance(a, str)][:8]
+            ep = self._udp[0] if self._udp else None
+            for a in theirs:
+                if ep is not None and a.startswith("udp://"):
+                    host, port = a[len("udp://"):].rsplit(":", 1)
+                    ep.punch(host, int(port))          # opens OUR mapping for their dial
+            self._spawn(self._dcutr_dial(peer, theirs, delay=0.05))
+            return {"addrs": self._dcutr_addrs()}
+
+        self.on(DCUTR_PROTOCOL, lambda m: isinstance(m, dict) and "connect" in m, serve)
+
+    async def _dcutr_dial(self, peer: str, addrs: List[str], delay: float = 0.0, timeout: float = 2.0) -> bool:
+        if delay:
+            await asyncio.sleep(delay)
+        for a in addrs:
+            link = self.links.get(peer)
+            if link is not None and not link.closed:
+                return True
+            try:
+                if await self.dial(a, timeout=timeout) == peer:
+                    return True
+            except DialError:
+                continue
+        link = self.links.get(peer)
+        return link is not None and not link.closed
+
+    async def upgrade_direct(self, peer: str, timeout: float = 5.0) -> bool:
+        """Replace a relayed path to ``peer`` by a direct link (libp2p dcutr, crates/scheduler/src/network.rs:56):
+        the two nodes swap their addresses THROUGH the relay, each sends a datagram towards the other's UDP address
+        from the socket it listens on (so both NATs hold a mapping for the pair), then both dial at the same time.
+        True when a direct link exists afterwards; the relay stays the fallback."""
+        link = self.links.get(peer)
+        if link is not None and not link.closed:
+            return True
+        ep = await self._udp_endpoint()
+        self._enable_dcutr()
+        try:
+            r = await self.request(peer, DCUTR_PROTOCOL, {"connect": self._dcutr_addrs()}, timeout=timeout)
+        except NetworkError:
+            return False
+        theirs = [a for a in (r.get("addrs") or []) if isinstance(a, str)][:8]
+        for a in theirs:
+            if a.startswith("udp://"):
+                host, port = a[len("udp://"):].rsplit(":", 1)
+                ep.punch(host, int(port))
+        ok = await self._dcutr_dial(peer, theirs, timeout=min(2.0, timeout))
+        if not ok:                                   # their simultaneous dial may still be completing
+            for _ in range(10):
+                await asyncio.sleep(0.05)
+                link = self.links.get(peer)
+                if link is not None and not link.closed:
+                    return True
+        return ok
+
+    async def _upgrade_quietly(self, peer: str) -> None:
+        try:
+            await self.upgrade_direct(peer)
+        except Exception:       # noqa: BLE001 - best effort: the relayed path keeps working
+            pass
 
     async def _send_to(self, peer: str, frame: dict, protocol: str) -> None:
         link, relayed = await self._link_to(peer)
@@ -668,6 +790,11 @@ class Network:
             self._peer_topics[peer] = set(frame.get("topics", []))
             if frame.get("dht"):
                 self._bootstrapped.set()
+                self.kad.add(peer, list(frame.get("addrs") or []), connected=True)
+            for p, a in (frame.get("servers") or {}).items():      # other DHT servers the peer routes to
+                if p != self.peer_id and p not in self.links:
+                    if self.kad.add(p, list(a), connected=False):
+                        self.peer_addrs.setdefault(p, self.kad.addrs(p))
             fut = getattr(link, "_hello_fut", None)
             if fut is not None and not fut.done():
                 fut.set_result(peer)
@@ -685,6 +812,7 @@ class Network:
                 else:
                     self.identity_rejections += 1
             elif self.relay_server and dst in self.links and link.peer_id is not None:
+                self.relayed_frames += 1
                 await self._send(self.links[dst], dict(frame, src=link.peer_id), "/hypha-relay")
             # else: drop (no route / unidentified sender)
         elif t == "req":
@@ -706,11 +834,26 @@ class Network:
         elif t == "dht_put":
             if frame["publisher"] == src:            # a record is published under the sender's own id only
                 self._records[frame["key"]] = (frame["value"], frame["publisher"])
+                if self.dht_server:
+                    self._spawn(self._replicate(frame, {src}))
             else:
                 self.identity_rejections += 1
         elif t == "dht_provide":
             if frame["provider"] == src:
                 self._providers.setdefault(frame["key"], set()).add(frame["provider"])
+                if self.dht_server:
+                    self._spawn(self._replicate({"key": frame["key"], "value": b"", "publisher": frame["provider"],
+                                                 "kind": "provider"}, {src}))
+            else:
+                self.identity_rejections += 1
+        elif t == "dht_replicate":
+            # server-to-server copy of a record whose publisher the SENDING server authenticated on its own link;
+            # accepted from DHT servers only and never forwarded again
+            if self.dht_server and src in self.kad:
+                if frame.get("kind") == "provider":
+                    self._providers.setdefault(frame["key"], set()).add(frame["publisher"])
+                else:
+                    self._records[frame["key"]] = (frame["value"], frame["publisher"])
             else:
                 self.identity_rejections += 1
         elif t == "stream_open":
@@ -916,68 +1059,127 @@ class Network:
             await self._forward_pub(frame, exclude=src)
 
     # -- DHT -----------------------------------------------------------------------------------------------------------
+    def _dht_targets(self, key: str, n: int) -> List[str]:
+        """The ``n`` DHT servers closest to ``key`` this node can route to (the routing table; before any server has
+        identified itself -- loopback set-ups -- every connected peer)."""
+        servers = [p for p in self.kad.closest(key, n * 2) if p in self.links or self.peer_addrs.get(p) or self.kad.addrs(p)]
+        return servers[:n] if servers else list(self.links.keys())
+
     async def put_record(self, key: str, value: bytes) -> None:
-        """Store locally and replicate to connected peers (Quorum::One)."""
+        """Store locally and on the `kad.REPLICATION` DHT servers closest to the key (Quorum::One: one
+        acknowledged send is enough); the receiving servers replicate to the closest servers THEY know."""
+        from .kad import REPLICATION
+
         self._records[key] = (value, self.peer_id)
         frame = {"t": "dht_put", "key": key, "value": value, "publisher": self.peer_id, "proto": "/ipfs/kad/1.0.0"}
         ok = 0
-        for link in list(self.links.values()):
+        for peer in self._dht_targets(key, REPLICATION):
             try:
-                await self._send(link, frame, "/ipfs/kad/1.0.0")
+                await self._send_to(peer, dict(frame), "/ipfs/kad/1.0.0")
                 ok += 1
             except NetworkError:
                 pass
         if ok == 0 and not self.dht_server:
             raise NetworkError("put_record: quorum failed (no peers)")
 
+    async def _replicate(self, frame: dict, exclude: Set[str]) -> None:
+        """A server that accepted a record from its publisher hands it to the other closest servers it knows."""
+        from .kad import REPLICATION
+
+        rep = {"t": "dht_replicate", "key": frame["key"], "value": frame["value"], "publisher": frame["publisher"],
+               "kind": frame.get("kind", "record")}
+        for peer in self.kad.closest(frame["key"], REPLICATION):
+            if peer in exclude or peer == self.peer_id:
+                continue
+            try:
+                await self._send_to(peer, dict(rep), "/ipfs/kad/1.0.0")
+            except NetworkError:
+                pass
+
+    async def _lookup(self, key: str, ask: str, timeout: float):
+        """Iterative lookup towards ``key``: query the closest known servers, follow the closer ones they name.
+        ``ask``: "get" | "providers" | "closest".  Yields ``(peer, response)`` for every server that answered."""
+        from .kad import ALPHA, K, key_id
+
+        t = key_id(key)
+        cand = self._dht_targets(key, K)
+        for p in self.links:
+            if p not in cand:
+                cand.append(p)
+        seen: Set[str] = set()
+        while True:
+            batch = [p for p in sorted(cand, key=lambda p: key_id(p) ^ t) if p not in seen][:ALPHA]
+            if not batch or len(seen) >= 4 * K:
+                return
+            seen.update(batch)
+            rs = await asyncio.gather(*(self.request(p, "/ipfs/kad/1.0.0", {ask: key}, timeout=timeout) for p in batch),
+                                      return_exceptions=True)
+            for p, r in zip(batch, rs):
+                if isinstance(r, Exception) or not isinstance(r, dict):
+                    continue
+                for q, addrs in (r.get("closer") or []):
+                    if q != self.peer_id and q not in seen and q not in cand:
+                        if self.kad.add(q, list(addrs), connected=False) or q in self.kad:
+                            self.peer_addrs.setdefault(q, self.kad.addrs(q))
+                            cand.append(q)
+                yield p, r
+
     async def get_record(self, key: str, timeout: float = 5.0) -> Tuple[bytes, str]:
-        """(value, publisher).  Local store first, then every connected peer."""
+        """(value, publisher).  Local store first, then an iterative lookup over the DHT servers."""
         if key in self._records:
             return self._records[key]
-        for peer in list(self.links.keys()):
-            try:
-                r = await self.request(peer, "/ipfs/kad/1.0.0", {"get": key}, timeout=timeout)
-            except NetworkError:
-                continue
-            if r and r.get("found"):
+        async for _, r in self._lookup(key, "get", timeout):
+            if r.get("found"):
                 return r["value"], r["publisher"]
         raise RecordNotFound(key)
 
     async def provide(self, key: str) -> None:
+        from .kad import REPLICATION
+
         self._providers.setdefault(key, set()).add(self.peer_id)
-        for link in list(self.links.values()):
+        for peer in self._dht_targets(key, REPLICATION):
             try:
-                await self._send(link, {"t": "dht_provide", "key": key, "provider": self.peer_id}, "/ipfs/kad/1.0.0")
+                await self._send_to(peer, {"t": "dht_provide", "key": key, "provider": self.peer_id}, "/ipfs/kad/1.0.0")
             except NetworkError:
                 pass
 
     async def find_providers(self, key: str, timeout: float = 5.0) -> List[str]:
         found = set(self._providers.get(key, set()))
-        for peer in list(self.links.keys()):
-            try:
-                r = await self.request(peer, "/ipfs/kad/1.0.0", {"providers": key}, timeout=timeout)
-                found.update(r.get("providers", []))
-            except NetworkError:
-                continue
+        async for _, r in self._lookup(key, "providers", timeout):
+            found.update(r.get("providers", []))
         return sorted(found)
 
     def closest_peers(self, key: str, k: int = 20) -> List[str]:
-        """Peers ordered by XOR distance of hashed ids to the hashed key."""
-        import hashlib
+        """Known peers ordered by XOR distance of hashed ids to the hashed key (routing table + connected peers)."""
+        from .kad import key_id
 
-        def h(s: str) -> int:
-            return int.from_bytes(hashlib.sha256(s.encode()).digest(), "big")
+        target = key_id(key)
+        return sorted(set(self.kad.peers()) | set(self.links.keys()), key=lambda p: key_id(p) ^ target)[:k]
 
-        target = h(key)
-        return sorted(self.links.keys(), key=lambda p: h(p) ^ target)[:k]
+    async def find_closest_peers(self, key: str, k: int = 20, timeout: float = 5.0) -> List[str]:
+        """Iterative FIND_NODE: walk the DHT servers towards ``key`` and return the ``k`` closest peers found."""
+        from .kad import key_id
+
+        async for _ in self._lookup(key, "closest", timeout):
+            pass
+        return self.closest_peers(key, k)
 
     def enable_dht_handlers(self) -> None:
+        from .kad import K
+
+        def closer(key: str) -> list:
+            return [[p, self.kad.addrs(p) or self.peer_addrs.get(p, [])] for p in self.kad.closest(key, K)]
+
         async def serve(peer, msg):
             if "get" in msg:
                 rec = self._records.get(msg["get"])
-                return {"found": rec is not None, "value": rec[0] if rec else b"", "publisher": rec[1] if rec else ""}
+                if rec is not None:
+                    return {"found": True, "value": rec[0], "publisher": rec[1]}
+                return {"found": False, "value": b"", "publisher": "", "closer": closer(msg["get"])}
             if "providers" in msg:
-                return {"providers": sorted(self._providers.get(msg["providers"], set()))}
+                return {"providers": sorted(self._providers.get(msg["providers"], set())), "closer": closer(msg["providers"])}
+            if "closest" in msg:
+                return {"closer": closer(msg["closest"])}
             return {}
 
         self.on("/ipfs/kad/1.0.0", None, serve)

@@ -29,7 +29,7 @@ from typing import Any, Callable, Dict, List, Optional
 from .. import messages as M
 from ..transport import Network, NetworkError
 from .bridge import Bridge, Connector
-from .ps_round import outer_round
+from .ps_round import SafetensorsFormatError, outer_round, read_header
 
 KILL_GRACE_S = 5.0
 
@@ -346,6 +346,18 @@ class ParameterServerExecutor:
                     # true mean + momentum + Nesterov + cumulative update in ONE pass over the mmapped files
                     # (C++ core, all cores; torch fallback for non-F32 tensors), OFF the event loop: the worker
                     # must keep answering RenewLease / health RPCs while GBs are being reduced
+                    # a worker file is untrusted input: one with a malformed header costs that worker its
+                    # contribution to this round, not everybody the round
+                    for peer, path in list(got.items()):
+                        try:
+                            read_header(path)
+                        except (SafetensorsFormatError, OSError) as exc:
+                            self.log(f"[ps {spec.job_id[:8]}] round {rnd}: dropping the file of {peer}: {exc}")
+                            got.pop(peer)
+                            if os.path.exists(path):
+                                os.unlink(path)
+                    if not got:
+                        raise RuntimeError(f"round {rnd}: no usable pseudo-gradient file")
                     paths = list(got.values())
                     stats = await asyncio.get_event_loop().run_in_executor(
                         None, lambda: outer_round(paths, work_dir, cfg.optimizer.learning_rate, cfg.optimizer.momentum))

@@ -42,15 +42,31 @@ def read_header(path: str) -> Tuple[Dict[str, dict], int]:
             header = json.loads(f.read(n))
         except ValueError as exc:
             raise SafetensorsFormatError(f"{path}: header is not JSON ({exc})") from exc
+    if not isinstance(header, dict):
+        raise SafetensorsFormatError(f"{path}: header is not a JSON object")
     header.pop("__metadata__", None)
     start = 8 + n
+    spans = []
     for name, e in header.items():
-        a, b = e["data_offsets"]
+        # worker-supplied and untrusted: every field is checked before anything indexes or maps the file
+        if not isinstance(e, dict) or not all(k in e for k in ("dtype", "shape", "data_offsets")):
+            raise SafetensorsFormatError(f"{path}: tensor {name!r} lacks dtype / shape / data_offsets")
+        off, shape, dtype = e["data_offsets"], e["shape"], e["dtype"]
+        if (not isinstance(off, list) or len(off) != 2 or not all(isinstance(x, int) and not isinstance(x, bool) for x in off)
+                or not isinstance(shape, list) or not all(isinstance(d, int) and not isinstance(d, bool) and d >= 0 for d in shape)
+                or dtype not in _DT_BYTES):
+            raise SafetensorsFormatError(f"{path}: tensor {name!r} has a malformed entry")
+        a, b = off
         numel = 1
-        for d in e["shape"]:
-            numel *= int(d)
-        if b < a or start + b > size or (b - a) != numel * _DT_BYTES.get(e["dtype"], 0):
+        for d in shape:
+            numel *= d
+        if a < 0 or b < a or start + b > size or (b - a) != numel * _DT_BYTES[dtype]:
             raise SafetensorsFormatError(f"{path}: tensor {name!r} has inconsistent offsets")
+        spans.append((a, b, name))
+    spans.sort()
+    for (a0, b0, n0), (a1, b1, n1) in zip(spans, spans[1:]):
+        if a1 < b0:
+            raise SafetensorsFormatError(f"{path}: tensors {n0!r} and {n1!r} overlap")
     return dict(sorted(header.items(), key=lambda kv: kv[1]["data_offsets"][0])), start
 
 
@@ -89,7 +105,9 @@ def read_samples(path: str, header: Dict[str, dict], start: int) -> Optional[flo
     with open(path, "rb") as f:
         f.seek(start + e["data_offsets"][0])
         (v,) = struct.unpack("<f", f.read(4))
-    return float(v)
+    import math
+
+    return float(v) if math.isfinite(v) else None      # inf / nan would turn every weight into nan
 
 
 def sample_weights(paths: List[str], heads=None) -> Optional[List[float]]:

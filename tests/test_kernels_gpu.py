@@ -629,6 +629,33 @@ def test_attention_tcgen05_backend_grad(C):
     assert _rel(out, of) < 2e-2 and _rel(qkv.grad, qf.grad) < 3e-2
 
 
+@pytest.mark.parametrize("B,S,Hq,Hk,D", [(2, 256, 4, 2, 64), (1, 200, 4, 4, 128), (2, 136, 6, 2, 64), (1, 64, 2, 1, 96)])
+def test_attention_tcgen05_padded_shapes(C, B, S, Hq, Hk, D):
+    """head_dim < 128 and seq % 128 != 0 run on the hand-written kernels through exact zero padding: forward and
+    backward match the fp32 reference, no library fallback is counted."""
+    from hypha_b200 import ops
+    from hypha_b200.ops.functional import _attention_ref
+
+    prev = ops.get_attention_backend()
+    ops.set_attention_backend("tcgen05")
+    ops.reset_fallback_counts()
+    torch.manual_seed(0)
+    qkv = torch.randn(B * S, (Hq + 2 * Hk) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    try:
+        n0 = ops.launch_count()
+        out = ops.attention_qkv(qkv, B, S, Hq, Hk, D)
+        d = torch.randn_like(out)
+        out.backward(d)
+        assert ops.launch_count() > n0 and not ops.fallback_counts(), ops.fallback_counts()
+    finally:
+        ops.set_attention_backend(prev)
+    qf = qkv.detach().float().requires_grad_(True)
+    of = _attention_ref(qf, B, S, Hq, Hk, D)
+    of.backward(d.float())
+    assert out.shape == of.shape
+    assert _rel(out, of) < 2e-2 and _rel(qkv.grad, qf.grad) < 3e-2, (_rel(out, of), _rel(qkv.grad, qf.grad))
+
+
 def test_attention_production_shape(C):
     """The shape the benchmark runs (S=4096, GQA 4:1, D=128; 8 q heads to keep the fp32 reference small):
     forward (default kernel), fused backward and split backward against the fp32 reference."""

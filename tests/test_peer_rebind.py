@@ -447,7 +447,7 @@ def test_fused_outer_state_includes_the_anchor():
 
     def outer(params, anchor, backend="fused"):
         o = object.__new__(DiLoCoOuter)
-        o.backend, o.round, o.shard_begin = backend, 7, 0
+        o.backend, o.round, o.shard_begin, o.world, o.rank = backend, 7, 0, 1, 0
         o.theta_outer, o.momentum = torch.randn(n), torch.randn(n)
         o.opt = types.SimpleNamespace(params=params)
         o.anchor_buf = types.SimpleNamespace(local=anchor)

@@ -194,3 +194,43 @@ def test_sample_weighted_mean(tmp_path):
     rc = ps_round.outer_round(files(c, (True, False, True)), c, 1.0, 0.0)
     assert rc["native"] and rc["weights"] is None
     torch.testing.assert_close(load_file(rc["path"])["w"], torch.full((3, 5), 5.0))
+
+
+def test_read_header_rejects_hostile_entries(tmp_path):
+    """Worker files are untrusted: every malformed header ends as SafetensorsFormatError (never KeyError / TypeError /
+    a mapped region outside the file), and a non-finite sample count is ignored instead of poisoning the weights."""
+    import json
+    import struct
+
+    from hypha_b200.worker import ps_round as P
+
+    def write(header, data=b"\0" * 64):
+        blob = json.dumps(header).encode()
+        p = tmp_path / f"f{abs(hash(blob)) % 10**8}.safetensors"
+        p.write_bytes(struct.pack("<Q", len(blob)) + blob + data)
+        return str(p)
+
+    ok = {"w": {"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 64]}}
+    assert list(P.read_header(write(ok))[0]) == ["w"]
+    bad = [
+        {"w": {"dtype": "F32", "shape": [4, 4]}},                                        # no offsets
+        {"w": {"shape": [4, 4], "data_offsets": [0, 64]}},                               # no dtype
+        {"w": {"dtype": "F32", "shape": [-4, -4], "data_offsets": [0, 64]}},             # negative dims (product 16)
+        {"w": {"dtype": "F32", "shape": [4, 4], "data_offsets": [-64, 0]}},              # negative offset
+        {"w": {"dtype": "F32", "shape": [4, 4], "data_offsets": [0, 64.0]}},             # float offset
+        {"w": {"dtype": "F32", "shape": "16", "data_offsets": [0, 64]}},                 # shape not a list
+        {"w": {"dtype": "F31", "shape": [16], "data_offsets": [0, 64]}},                 # unknown dtype
+        {"w": {"dtype": "F32", "shape": [16], "data_offsets": [0, 64, 128]}},
+        {"w": {"dtype": "F32", "shape": [8], "data_offsets": [0, 32]}, "v": {"dtype": "F32", "shape": [8], "data_offsets": [16, 48]}},
+        {"w": [1, 2, 3]},
+        [1, 2],
+        {"w": {"dtype": "F32", "shape": [1 << 40], "data_offsets": [0, 1 << 42]}},       # beyond the file
+    ]
+    for h in bad:
+        with pytest.raises(P.SafetensorsFormatError):
+            P.read_header(write(h))
+    for v in (float("inf"), float("nan")):
+        h = {"__samples__": {"dtype": "F32", "shape": [1], "data_offsets": [0, 4]}}
+        path = write(h, struct.pack("<f", v) + b"\0" * 60)
+        head, start = P.read_header(path)
+        assert P.read_samples(path, head, start) is None

@@ -1,0 +1,208 @@
+"""`udp://` links (the reference's QUIC listener), direct-connection upgrade through the relay (dcutr) and the
+Kademlia routing table / record replication (crates/network/src/kad.rs; Cargo.toml:48,54,106)."""
+import asyncio
+import os
+import tempfile
+
+import pytest
+
+from hypha_b200.transport.kad import RESERVED_CIDRS, CidrFilter, RoutingTable, key_id
+from hypha_b200.transport.network import DialError, Network, RecordNotFound
+
+
+def run(coro):
+    return asyncio.run(coro)
+
+
+async def _echo_node(name, **kw):
+    n = Network(name, **kw)
+
+    async def echo(peer, m):
+        return {"echo": m, "from": peer}
+
+    n.on("/echo", None, echo)
+    return n
+
+
+def test_udp_link_request_and_lossy_stream():
+    async def main():
+        a, b = await _echo_node("a"), await _echo_node("b")
+        addr = await b.listen("udp://127.0.0.1:0")
+        assert addr.startswith("udp://127.0.0.1:") and not addr.endswith(":0")
+        assert await a.dial(addr) == "b"
+        assert (await a.request("b", "/echo", {"x": [1, 2, 3]})) == {"echo": {"x": [1, 2, 3]}, "from": "a"}
+        assert (await b.request("a", "/echo", "back")) == {"echo": "back", "from": "b"}     # same connection, other way
+        # a 3 MiB tensor stream with one datagram in seven dropped 40 times: every byte arrives, in order
+        q = b.streams_push()
+        blob = os.urandom(3 << 20)
+        ep = a._udp[0]
+        ep.drop_next, ep.drop_every = 40, 7
+        push = asyncio.ensure_future(a.stream_push("b", blob))
+        st = await asyncio.wait_for(q.get(), 20)
+        got = await asyncio.wait_for(st.read_all(), 30)
+        await push
+        assert got == blob
+        link = a.links["b"]
+        assert 40 <= link.retransmits < 400 and ep.drop_next == 0
+        assert sum(a.counters.outbound.values()) > len(blob)            # outbound bytes are accounted like on tcp links
+        for n in (a, b):
+            await n.close()
+
+    run(main())
+
+
+def _pki(names):
+    from hypha_b200 import certutil
+
+    d = tempfile.mkdtemp(prefix="hbu", dir="/tmp")
+    rc, rk = certutil.make_root("acme", out_dir=d)
+    oc, ok = certutil.make_org(rc, rk, "acme", out_dir=d)
+    out = {}
+    for n in names:
+        c, k, t = certutil.make_node(oc, ok, n, out_dir=d)
+        out[n] = {"cert_pem": c, "key_pem": k, "trust_pem": t}
+    return d, oc, ok, out
+
+
+def test_udp_link_mutual_authentication_and_identity_binding():
+    from hypha_b200 import certutil
+    from hypha_b200.transport.utils import peer_id_from_key_pem
+
+    async def main():
+        d, oc, ok, tls = _pki(["n1", "n2", "n3"])
+        ids = {n: peer_id_from_key_pem(t["key_pem"]) for n, t in tls.items()}
+        n2 = await _echo_node(ids["n2"], tls=tls["n2"])
+        addr = await n2.listen("udp://127.0.0.1:0")
+        n1 = await _echo_node(ids["n1"], tls=tls["n1"])
+        assert await n1.dial(addr) == ids["n2"]
+        assert n1.links[ids["n2"]].cert_peer_id() == ids["n2"] and n2.links[ids["n1"]].cert_peer_id() == ids["n1"]
+        assert (await n1.request(ids["n2"], "/echo", 7))["from"] == ids["n1"]
+        # a CA-issued certificate entitles its holder to ITS key's peer id only
+        imp = Network(ids["n2"], tls=tls["n1"])
+        with pytest.raises(DialError):
+            await imp.dial(addr, timeout=2.0)
+        # no certificate: refused during the handshake, quickly
+        anon = Network("anon")
+        t0 = asyncio.get_event_loop().time()
+        with pytest.raises(DialError):
+            await anon.dial(addr, timeout=5.0)
+        assert asyncio.get_event_loop().time() - t0 < 2.0
+        # a certificate from another PKI
+        _, _, _, other = _pki(["x"])
+        stranger = Network(peer_id_from_key_pem(other["x"]["key_pem"]), tls=other["x"])
+        with pytest.raises(DialError):
+            await stranger.dial(addr, timeout=2.0)
+        # a revoked node
+        crl = certutil.make_crl(oc, ok, revoked=(tls["n3"]["cert_pem"],), out_dir=d)
+        strict = await _echo_node(ids["n2"], tls=dict(tls["n2"], crls_pem=crl))
+        saddr = await strict.listen("udp://127.0.0.1:0")
+        n3 = Network(ids["n3"], tls=tls["n3"])
+        with pytest.raises(DialError):
+            await n3.dial(saddr, timeout=2.0)
+        assert await n1.dial(saddr) == ids["n2"]             # the others are still welcome
+        for n in (n1, n2, imp, anon, stranger, strict, n3):
+            await n.close()
+
+    run(main())
+
+
+def test_dcutr_replaces_the_relayed_path_by_a_direct_udp_link():
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        gaddr = await gw.listen("tcp://127.0.0.1:0")
+        a, b = await _echo_node("a"), await _echo_node("b")
+        for n in (a, b):
+            await n.listen("udp://127.0.0.1:0")
+            n._udp[0].nat_filter = True       # unsolicited handshakes are dropped, like behind an address-restricted NAT
+            await n.dial(gaddr)
+        # behind the NAT a plain dial does not get through ...
+        with pytest.raises(DialError):
+            await a.dial(b.listen_addrs[0], timeout=0.5)
+        a.peer_addrs.pop("b", None)
+        b.peer_addrs.pop("a", None)
+        a._udp[0]._contacted.clear()
+        # ... so traffic goes through the gateway
+        a._dcutr_last["b"] = 1e18             # keep the automatic upgrade out of this part of the test
+        assert (await a.request("b", "/echo", 1))["from"] == "a"
+        assert gw.relayed_frames >= 2 and "b" not in a.links
+        # the upgrade: addresses swapped through the relay, both sides punch and dial
+        assert await a.upgrade_direct("b")
+        assert type(a.links["b"]).__name__ == "UdpLink" and b._udp[0].punches + a._udp[0].punches >= 1
+        before = gw.relayed_frames
+        assert (await a.request("b", "/echo", 2))["echo"] == 2
+        assert (await b.request("a", "/echo", 3))["echo"] == 3
+        assert gw.relayed_frames == before                   # the gateway is out of the data path
+        # a peer that cannot be reached at all: the upgrade reports failure and the relay keeps working
+        c = await _echo_node("c")
+        await c.dial(gaddr)                                  # no listener at all
+        a._dcutr_last["c"] = 1e18
+        assert not await a.upgrade_direct("c", timeout=1.0)
+        assert (await a.request("c", "/echo", 4))["echo"] == 4
+        for n in (a, b, c, gw):
+            await n.close()
+
+    run(main())
+
+
+def test_routing_table_buckets_cidr_filter_and_closest():
+    t = RoutingTable("me", k=2)
+    peers = [f"p{i}" for i in range(200)]
+    for p in peers:
+        t.add(p, [f"tcp://8.8.{len(p)}.{int(p[1:]) % 250}:1"])
+    assert 2 <= len(t) <= 2 * 256 and all(len(b) <= 2 for b in t.buckets)
+    # full buckets prefer their old, live entries; a stale entry makes room
+    b = next(b for b in t.buckets if len(b) == 2)
+    old = list(b)
+    newcomer = next(p for p in (f"q{i}" for i in range(100000)) if t._bucket(p) is b and p not in b)
+    assert not t.add(newcomer, ["tcp://8.8.8.8:1"]) and list(b) == old
+    t.mark_disconnected(old[0])
+    assert t.add(newcomer, ["tcp://8.8.8.8:1"]) and old[0] not in b and newcomer in b
+    # closest() is the XOR order
+    want = sorted(t.peers(), key=lambda p: key_id(p) ^ key_id("some-key"))[:5]
+    assert t.closest("some-key", 5) == want
+    # strict mode: reserved ranges never enter the table, an allow-list re-admits a site's own range
+    strict = RoutingTable("me", cidr=CidrFilter(RESERVED_CIDRS, allow=("10.1.0.0/16",)))
+    assert not strict.add("lo", ["tcp://127.0.0.1:1", "udp://192.168.1.5:2"]) and strict.rejected_by_cidr == 1
+    assert strict.add("pub", ["tcp://127.0.0.1:1", "tcp://93.184.216.34:1"]) and strict.addrs("pub") == ["tcp://93.184.216.34:1"]
+    assert strict.add("site", ["udp://10.1.2.3:9"]) and not strict.add("site2", ["udp://10.2.2.3:9"])
+    assert strict.add("v6", ["tcp://[2a00:1450::1]:1"]) and not strict.add("v6lo", ["tcp://[::1]:1"])
+    assert strict.add("dns", ["tcp://gateway.example.org:1"])
+
+
+def test_two_gateways_replicate_records_and_lookups_walk_the_table():
+    async def main():
+        g1 = Network("g1", relay_server=True, dht_server=True)
+        g2 = Network("g2", relay_server=True, dht_server=True)
+        for g in (g1, g2):
+            g.enable_dht_handlers()
+        a1 = await g1.listen("tcp://127.0.0.1:0")
+        a2 = await g2.listen("tcp://127.0.0.1:0")
+        await g1.dial(a2)                                    # the gateways know each other
+        assert "g2" in g1.kad and "g1" in g2.kad
+        data, sched = Network("data"), Network("sched")
+        await data.dial(a1)                                  # the data node only knows gateway 1 ...
+        await sched.dial(a2)                                 # ... the scheduler only gateway 2
+        # the scheduler learnt about gateway 1 from gateway 2's identify (other DHT servers it routes to); a record
+        # only gateway 1 holds is found by walking there: no link to g1 existed before the lookup
+        assert "g1" not in sched.links and "g1" in sched.kad and sched.kad.addrs("g1") == [a1]
+        g1._records["only-g1"] = (b"v", "data")
+        assert (await sched.get_record("only-g1")) == (b"v", "data")
+        assert "g1" in sched.links
+        await data.put_record("dataset", b'{"num_slices": 4}')
+        await data.provide("dataset")
+        await asyncio.sleep(0.2)
+        assert g1._records["dataset"][1] == "data" and g2._records["dataset"] == g1._records["dataset"]
+        assert (await sched.get_record("dataset")) == (b'{"num_slices": 4}', "data")
+        assert await sched.find_providers("dataset") == ["data"]
+        with pytest.raises(RecordNotFound):
+            await sched.get_record("nobody-has-this", timeout=1.0)
+        assert set(await sched.find_closest_peers("whatever")) >= {"g1", "g2"}
+        # replication frames are taken from DHT servers only
+        before = g2.identity_rejections
+        await sched._send(sched.links["g2"], {"t": "dht_replicate", "key": "forged", "value": b"x", "publisher": "data"}, "/ipfs/kad/1.0.0")
+        await asyncio.sleep(0.1)
+        assert "forged" not in g2._records and g2.identity_rejections == before + 1
+        for n in (data, sched, g1, g2):
+            await n.close()
+
+    run(main())
