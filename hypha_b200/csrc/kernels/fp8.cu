@@ -169,13 +169,26 @@ __global__ void __launch_bounds__(256) quant_mxfp8_kernel(const bf16* __restrict
       o0[g] = cvt4_e4m3(a[0], a[1], a[2], a[3]);
       o1[g] = cvt4_e4m3(b[0], b[1], b[2], b[3]);
     }
-    // row (tc*128 + 2cp [+1]) of qT, 32 consecutive bytes at column tr*128 + rb*32: two full sectors per thread
-    uint8_t* d0 = qT + (size_t)(tc * kQT + 2 * cp) * ldqT + tr * kQT + rb * 32;
-    uint8_t* d1 = d0 + ldqT;
-    *reinterpret_cast<uint4*>(d0) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
-    *reinterpret_cast<uint4*>(d0 + 16) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
-    *reinterpret_cast<uint4*>(d1) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
-    *reinterpret_cast<uint4*>(d1 + 16) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+    // Transposed tile through shared memory (the bf16 staging tile is dead once every thread holds its words), so
+    // that a warp stores four 128-byte rows of qT per instruction instead of 32 scattered 16-byte pieces (the direct
+    // stores ran at 0.46 of the HBM rate).  Row pitch 144 B keeps the 16-byte column writes at 2-way conflicts.
+    __syncthreads();
+    constexpr int kTP = kQT + 16;
+    {
+      uint8_t* r0p = tile + (2 * cp) * kTP + rb * 32;
+      uint8_t* r1p = r0p + kTP;
+      *reinterpret_cast<uint4*>(r0p) = make_uint4(o0[0], o0[1], o0[2], o0[3]);
+      *reinterpret_cast<uint4*>(r0p + 16) = make_uint4(o0[4], o0[5], o0[6], o0[7]);
+      *reinterpret_cast<uint4*>(r1p) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+      *reinterpret_cast<uint4*>(r1p + 16) = make_uint4(o1[4], o1[5], o1[6], o1[7]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = threadIdx.x + 256 * i, row = j >> 3, part = j & 7;
+      const uint4 vq = *reinterpret_cast<const uint4*>(tile + row * kTP + part * 16);
+      *reinterpret_cast<uint4*>(qT + (size_t)(tc * kQT + row) * ldqT + tr * kQT + part * 16) = vq;
+    }
     const int c0 = 2 * cp, c1 = 2 * cp + 1;
     sf_col[(c0 & 31) * 16 + (c0 >> 5) * 4 + rb] = (uint8_t)e0;
     sf_col[(c1 & 31) * 16 + (c1 >> 5) * 4 + rb] = (uint8_t)e1;
