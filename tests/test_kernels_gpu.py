@@ -720,11 +720,11 @@ def test_library_fallbacks_are_counted(C):
     a = torch.randn(64, 36, device="cuda", dtype=torch.bfloat16)       # K = 36: not a multiple of 8
     b = torch.randn(48, 36, device="cuda", dtype=torch.bfloat16)
     ops.gemm(a, b)
-    qkv = torch.randn(128, (2 + 2) * 64, device="cuda", dtype=torch.bfloat16)
+    qkv = torch.randn(128, (2 + 2) * 160, device="cuda", dtype=torch.bfloat16)
     prev = ops.get_attention_backend()
     ops.set_attention_backend("tcgen05")
     try:
-        ops.attention_qkv(qkv, 1, 128, 2, 1, 64)                        # head_dim 64
+        ops.attention_qkv(qkv, 1, 128, 2, 1, 160)                       # head_dim > 128: beyond the kernels' tile
         counts = ops.fallback_counts()
         assert sum(counts.values()) == 2 and any(k.startswith("gemm") for k in counts) and any(k.startswith("attention") for k in counts)
         os.environ["HYPHA_STRICT_KERNELS"] = "1"
