@@ -250,6 +250,13 @@ class AggregationSection:
 
 
 @dataclass
+class PrecisionSection:
+    gemm: str = doc("precision of the Linear-layer GEMMs of the inner steps on GPU executors: `bf16` (default), "
+                    "`mxfp8` (e4m3 with one UE8M0 scale per 32 elements, block-scaled tensor-core MMA) or `fp8` "
+                    "(per-tensor scaling); master weights, optimizer and the outer step are unaffected", "bf16")
+
+
+@dataclass
 class DiLoCoJob:
     type: str = doc("job type (only `diloco`)", "diloco")
     model: ModelSource = doc("model source", factory=ModelSource)
@@ -262,6 +269,7 @@ class DiLoCoJob:
     aggregation: AggregationSection = doc("how the outer step is carried out", factory=AggregationSection)
     elastic: ElasticSection = doc("behaviour on worker failure", factory=ElasticSection)
     checkpoint: CheckpointSection = doc("job-level checkpoint / resume (parameter-server mode)", factory=CheckpointSection)
+    precision: PrecisionSection = doc("numeric precision of the inner steps", factory=PrecisionSection)
 
 
 @dataclass
@@ -578,6 +586,9 @@ def validate(cfg: Any) -> Any:
         if job.aggregation.mode not in ("parameter-server", "collective"):
             raise _err(meta, "scheduler.job.aggregation.mode",
                        f"unknown aggregation mode `{job.aggregation.mode}` (parameter-server | collective)")
+        if job.precision.gemm not in ("bf16", "mxfp8", "fp8"):
+            raise _err(meta, "scheduler.job.precision.gemm",
+                       f"unknown GEMM precision `{job.precision.gemm}` (bf16 | mxfp8 | fp8)")
         if job.aggregation.weighting not in ("uniform", "samples"):
             raise _err(meta, "scheduler.job.aggregation.weighting",
                        f"unknown weighting `{job.aggregation.weighting}` (uniform | samples)")

@@ -744,6 +744,21 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
             pass
 
 
+def apply_precision(precision: Optional[str], device: str) -> str:
+    """Job-level GEMM precision (`[scheduler.job.precision] gemm`): ``mxfp8`` / ``fp8`` switch the Linear GEMMs of
+    the sm_100a models to the block-scaled / per-tensor fp8 tensor-core kernels; on a CPU executor (and for models
+    that do not run on the hand-written kernels) the setting has nothing to act on and bf16 / fp32 stays."""
+    precision = precision or "bf16"
+    if precision not in ("bf16", "mxfp8", "fp8"):
+        raise ValueError(f"unknown GEMM precision {precision!r}")
+    if precision != "bf16" and device.startswith("cuda"):
+        from .. import ops
+
+        ops.set_fp8(True, mode="mx" if precision == "mxfp8" else "tensor")
+        return precision
+    return "bf16"
+
+
 def main(socket_path: str, work_dir: str, job_json: str) -> None:
     from safetensors.torch import load_file, save_file
 
@@ -759,6 +774,7 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
         executor = job["executor"]
         assert executor["class"] == "train"
         config = executor["config"]
+        apply_precision(config.get("precision"), device)
         if config.get("collective"):
             return main_collective(session, config, work_dir)
         prepare_files(config, session)

@@ -364,6 +364,8 @@ class TrainExecutorConfig:
     # B200 extension: "samples" -> the executor reports the samples it processed with its pseudo-gradient and the
     # mean is taken over samples instead of over workers (absent / "uniform": the reference's 1/N intent)
     weighting: Optional[str] = None
+    # B200 extension: GEMM precision of the inner steps on GPU executors ("mxfp8" | "fp8"; absent / "bf16": bf16)
+    precision: Optional[str] = None
 
     def to_wire(self) -> dict:
         d = {"model": self.model.to_wire(), "data": self.data.to_wire(), "updates": self.updates.to_wire(),
@@ -379,6 +381,8 @@ class TrainExecutorConfig:
             d["join"] = dict(self.join)
         if self.weighting and self.weighting != "uniform":
             d["weighting"] = self.weighting
+        if self.precision and self.precision != "bf16":
+            d["precision"] = self.precision
         return d
 
     @classmethod
@@ -389,7 +393,8 @@ class TrainExecutorConfig:
                    LRScheduler.from_wire(d["scheduler"]) if d.get("scheduler") else None,
                    dict(d["collective"]) if d.get("collective") else None,
                    dict(d["join"]) if d.get("join") else None,
-                   str(d["weighting"]) if d.get("weighting") else None)
+                   str(d["weighting"]) if d.get("weighting") else None,
+                   str(d["precision"]) if d.get("precision") else None)
 
 
 @dataclass

@@ -144,7 +144,8 @@ class DiLoCoJobRun:
                                      updates=M.Send.to_peers([self.ps.peer_id]),
                                      results=M.Receive.from_peers([self.ps.peer_id]),
                                      optimizer=self.adam, batch_size=bs, preprocessor=self.pre,
-                                     weighting=self.job.aggregation.weighting)
+                                     weighting=self.job.aggregation.weighting,
+                                     precision=self.job.precision.gemm)
 
     async def _dispatch_train(self, w: WorkerHandle, tcfg: M.TrainExecutorConfig) -> None:
         spec = M.JobSpec(self.job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))

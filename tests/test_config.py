@@ -185,3 +185,31 @@ def test_aggregation_weighting_is_validated_and_travels_to_the_executor(tmp_path
     assert t.weighting == "samples" and t.to_wire()["weighting"] == "samples"
     del wire["weighting"]
     assert "weighting" not in M.TrainExecutorConfig.from_wire(wire).to_wire()      # reference job JSON unchanged
+
+
+def test_job_precision_is_validated_and_travels_to_the_executor(tmp_path):
+    """`[scheduler.job.precision] gemm = "mxfp8"` (BASELINE config 3 through the product path): validated, carried in
+    the train executor's job JSON only when it differs from bf16, applied by the executor on GPUs only."""
+    from hypha_b200 import messages as M
+    from hypha_b200.executor.training import apply_precision
+
+    p = tmp_path / "s.toml"
+    p.write_text('[scheduler.job.precision]\ngemm = "mxfp8"\n')
+    cfg = C.builder(C.SchedulerConfig).with_toml(str(p)).build()
+    assert cfg.scheduler.job.precision.gemm == "mxfp8"
+    C.validate(cfg)
+    assert C.builder(C.SchedulerConfig).build().scheduler.job.precision.gemm == "bf16"
+    p.write_text('[scheduler.job.precision]\ngemm = "int3"\n')
+    with pytest.raises(C.ConfigError, match="precision"):
+        C.validate(C.builder(C.SchedulerConfig).with_toml(str(p)).build())
+    wire = {"model": M.Model("causal-lm", M.Fetch.uri("file:///m"), ["input_ids"]).to_wire(),
+            "data": M.Fetch.scheduler("s", "d").to_wire(), "updates": M.Send.to_peers(["ps"]).to_wire(),
+            "results": M.Receive.from_peers(["ps"]).to_wire(), "optimizer": M.Adam(1e-3).to_wire(), "batch_size": 4,
+            "precision": "mxfp8"}
+    t = M.TrainExecutorConfig.from_wire(wire)
+    assert t.precision == "mxfp8" and t.to_wire()["precision"] == "mxfp8"
+    wire["precision"] = "bf16"
+    assert "precision" not in M.TrainExecutorConfig.from_wire(wire).to_wire()     # reference job JSON unchanged
+    assert apply_precision("mxfp8", "cpu") == "bf16" and apply_precision(None, "cuda:0") == "bf16"
+    with pytest.raises(ValueError):
+        apply_precision("int3", "cpu")
