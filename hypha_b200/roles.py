@@ -116,6 +116,7 @@ async def start_node(role: str, cfg: Any, *, peer_id: Optional[str] = None, rela
     tel.register_bandwidth(net.counters)
     node = Node(role, net, tel)
     net.enable_dht_handlers()
+    net.start_dht_maintenance(float(os.environ.get("HYPHA_DHT_REFRESH_S", "300")))
     for addr in cfg.listen_addresses:
         await net.listen(addr)
     for addr in getattr(cfg, "external_addresses", []) or []:

@@ -440,6 +440,8 @@ class Network:
         self._peer_topics: Dict[str, Set[str]] = {}
         self._seen_msgs: Dict[str, float] = {}
         self._records: Dict[str, Tuple[bytes, str]] = {}
+        self._published: Dict[str, bytes] = {}        # records THIS node published (republished by the maintenance loop)
+        self._provided: Set[str] = set()
         self._providers: Dict[str, Set[str]] = {}
         self._stream_rx: Dict[Tuple[str, Optional[str]], asyncio.Queue] = {}
         self._early_streams: Dict[Tuple[str, Optional[str]], List[Tuple[float, IncomingStream]]] = {}
@@ -1071,6 +1073,7 @@ class Network:
         from .kad import REPLICATION
 
         self._records[key] = (value, self.peer_id)
+        self._published[key] = value
         frame = {"t": "dht_put", "key": key, "value": value, "publisher": self.peer_id, "proto": "/ipfs/kad/1.0.0"}
         ok = 0
         for peer in self._dht_targets(key, REPLICATION):
@@ -1137,6 +1140,7 @@ class Network:
         from .kad import REPLICATION
 
         self._providers.setdefault(key, set()).add(self.peer_id)
+        self._provided.add(key)
         for peer in self._dht_targets(key, REPLICATION):
             try:
                 await self._send_to(peer, {"t": "dht_provide", "key": key, "provider": self.peer_id}, "/ipfs/kad/1.0.0")
@@ -1163,6 +1167,39 @@ class Network:
         async for _ in self._lookup(key, "closest", timeout):
             pass
         return self.closest_peers(key, k)
+
+    async def dht_maintain_once(self, timeout: float = 2.0) -> dict:
+        """One round of Kademlia upkeep (kad.rs runs these on timers): a lookup of our own id fills the buckets
+        around us with servers we have only heard of, then everything this node published is stored again on the
+        servers that are closest NOW -- a gateway that joined or restarted since gets its copy without the publisher
+        noticing.  Returns counters for logs and tests."""
+        before = len(self.kad)
+        try:
+            await self.find_closest_peers(self.peer_id, timeout=timeout)
+        except NetworkError:
+            pass
+        republished = 0
+        for key, value in list(self._published.items()):
+            try:
+                await self.put_record(key, value)
+                republished += 1
+            except NetworkError:
+                pass
+        for key in list(self._provided):
+            await self.provide(key)
+        return {"servers_known": len(self.kad), "servers_learnt": len(self.kad) - before, "republished": republished,
+                "provided": len(self._provided)}
+
+    def start_dht_maintenance(self, interval_s: float = 300.0) -> asyncio.Task:
+        async def loop():
+            while not self.closed:
+                await asyncio.sleep(interval_s)
+                try:
+                    await self.dht_maintain_once()
+                except Exception:       # noqa: BLE001 - upkeep must never take the node down
+                    pass
+
+        return self._spawn(loop())
 
     def enable_dht_handlers(self) -> None:
         from .kad import K

@@ -206,3 +206,35 @@ def test_two_gateways_replicate_records_and_lookups_walk_the_table():
             await n.close()
 
     run(main())
+
+
+def test_dht_maintenance_republishes_to_a_gateway_that_joined_later():
+    async def main():
+        g1 = Network("g1", relay_server=True, dht_server=True)
+        g1.enable_dht_handlers()
+        a1 = await g1.listen("tcp://127.0.0.1:0")
+        data = Network("data")
+        await data.dial(a1)
+        await data.put_record("dataset", b"v1")
+        await data.provide("dataset")
+        # a second gateway appears and meets the first one; the data node has never heard of it
+        g2 = Network("g2", relay_server=True, dht_server=True)
+        g2.enable_dht_handlers()
+        a2 = await g2.listen("tcp://127.0.0.1:0")
+        await g2.dial(a1)
+        assert "dataset" not in g2._records and "g2" not in data.kad
+        out = await data.dht_maintain_once()
+        await asyncio.sleep(0.2)
+        assert out["republished"] == 1 and out["servers_learnt"] >= 1 and "g2" in data.kad
+        assert g2._records["dataset"] == (b"v1", "data") and "data" in g2._providers["dataset"]
+        # the timer variant
+        await data.put_record("dataset", b"v2")
+        g2._records.clear()
+        t = data.start_dht_maintenance(0.1)
+        await asyncio.sleep(0.5)
+        assert g2._records["dataset"] == (b"v2", "data")
+        t.cancel()
+        for n in (data, g1, g2):
+            await n.close()
+
+    run(main())
