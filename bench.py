@@ -49,6 +49,8 @@ def parse_args():
                     help="BASELINE config 4: after the timed regions, stall one rank, let the survivors time out, "
                          "adopt its shard and continue, then re-seed it over peer memory and re-admit it")
     ap.add_argument("--fp8", action="store_true", help="BASELINE config 3: fp8 inner-step GEMMs, bf16 outer step")
+    ap.add_argument("--no-outer-kernel-list", action="store_true",
+                    help="skip the CUPTI capture of one outer step (its kernel names go into the JSON line)")
     ap.add_argument("--fp8-mode", choices=["mx", "tensor"], default="mx",
                     help="mx: MXFP8 block scaling (tcgen05.mma.kind::mxf8f6f4.block_scale); tensor: per-tensor scaling")
     ap.add_argument("--via-box", action="store_true",
@@ -496,6 +498,26 @@ def main():
         barrier()
         outer_ms = max_over_ranks(o0.elapsed_time(o1)) / 2
 
+    # ---- which kernels an outer step launches (proof that the fused path issues no NCCL kernel) -----------------
+    outer_kernels = None
+    if world > 1 and not args.no_outer_kernel_list:
+        try:
+            from torch.profiler import ProfilerActivity, profile
+
+            barrier()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                trainer.outer_step()
+                torch.cuda.synchronize()
+            names = {}
+            for ev in prof.events():
+                if ev.device_type == torch.autograd.DeviceType.CUDA:
+                    names[ev.name] = names.get(ev.name, 0) + 1
+            outer_kernels = {"kernels": {k[:96]: v for k, v in sorted(names.items())},
+                             "nccl_kernels": sum(v for k, v in names.items() if "nccl" in k.lower())}
+            barrier()
+        except Exception as exc:       # noqa: BLE001 - evidence only: never costs the run its number
+            outer_kernels = {"error": repr(exc)[:200]}
+
     memdbg("before drill")
     drill = None
     if args.fault_drill and world > 1 and trainer.outer.backend == "fused":
@@ -527,7 +549,7 @@ def main():
             },
             "model_tflops_per_gpu": value / world * cfg.flops_per_token(S) / 1e12,
             "outer_step_ms": outer_ms, "loss": loss_val, "clocks": clocks, "gpu_launches": int(launches),
-            "library_fallbacks": fallbacks, "e2e": e2e,
+            "library_fallbacks": fallbacks, "e2e": e2e, "outer_step_launches": outer_kernels,
         }
         if drill is not None:
             out["fault_drill"] = drill
