@@ -845,13 +845,13 @@ class Network:
                 self._providers.setdefault(frame["key"], set()).add(frame["provider"])
                 if self.dht_server:
                     self._spawn(self._replicate({"key": frame["key"], "value": b"", "publisher": frame["provider"],
-                                                 "kind": "provider"}, {src}))
+                                                 "kind": "provider", "sig": frame.get("sig"), "pub": frame.get("pub")}, {src}))
             else:
                 self.identity_rejections += 1
         elif t == "dht_replicate":
             # server-to-server copy of a record whose publisher the SENDING server authenticated on its own link;
             # accepted from DHT servers only and never forwarded again
-            if self.dht_server and src in self.kad:
+            if self.dht_server and src in self.kad and self._record_authentic(frame):
                 if frame.get("kind") == "provider":
                     self._providers.setdefault(frame["key"], set()).add(frame["publisher"])
                 else:
@@ -1061,6 +1061,45 @@ class Network:
             await self._forward_pub(frame, exclude=src)
 
     # -- DHT -----------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def _record_digest(kind: str, key: str, value: bytes, publisher: str) -> bytes:
+        import hashlib
+
+        h = hashlib.sha256()
+        for part in (b"hypha-dht-v1", kind.encode(), key.encode(), bytes(value), publisher.encode()):
+            h.update(len(part).to_bytes(4, "little"))
+            h.update(part)
+        return h.digest()
+
+    def _sign_record(self, frame: dict) -> dict:
+        """A node with a key signs what it publishes: the copies DHT servers hand to each other stay verifiable."""
+        if self._sign_key is not None:
+            frame["pub"] = self._pub_raw
+            frame["sig"] = self._sign_key.sign(self._record_digest(frame.get("kind", "record"), frame["key"],
+                                                                   frame.get("value", b""), frame["publisher"]))
+        return frame
+
+    def _record_authentic(self, frame: dict) -> bool:
+        """Replicated records reach us from a server that is NOT their publisher.  With a PKI (strict mode) such a
+        copy is accepted only with a valid Ed25519 signature by the key the publisher's peer id derives from;
+        without one (loopback boxes) the sending server is trusted, as before."""
+        sig, pub = frame.get("sig"), frame.get("pub")
+        if not sig or not pub:
+            return not self.strict_gossip
+        try:
+            from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PublicKey
+
+            from .utils import peer_id_from_public_bytes
+
+            if peer_id_from_public_bytes(bytes(pub)) != frame["publisher"]:
+                return False
+            Ed25519PublicKey.from_public_bytes(bytes(pub)).verify(
+                bytes(sig), self._record_digest(frame.get("kind", "record"), frame["key"], frame.get("value", b""),
+                                                frame["publisher"]))
+            return True
+        except Exception:
+            return False
+
     def _dht_targets(self, key: str, n: int) -> List[str]:
         """The ``n`` DHT servers closest to ``key`` this node can route to (the routing table; before any server has
         identified itself -- loopback set-ups -- every connected peer)."""
@@ -1074,7 +1113,8 @@ class Network:
 
         self._records[key] = (value, self.peer_id)
         self._published[key] = value
-        frame = {"t": "dht_put", "key": key, "value": value, "publisher": self.peer_id, "proto": "/ipfs/kad/1.0.0"}
+        frame = self._sign_record({"t": "dht_put", "key": key, "value": value, "publisher": self.peer_id,
+                                   "proto": "/ipfs/kad/1.0.0"})
         ok = 0
         for peer in self._dht_targets(key, REPLICATION):
             try:
@@ -1091,6 +1131,8 @@ class Network:
 
         rep = {"t": "dht_replicate", "key": frame["key"], "value": frame["value"], "publisher": frame["publisher"],
                "kind": frame.get("kind", "record")}
+        if frame.get("sig") and frame.get("pub"):
+            rep["sig"], rep["pub"] = frame["sig"], frame["pub"]
         for peer in self.kad.closest(frame["key"], REPLICATION):
             if peer in exclude or peer == self.peer_id:
                 continue
@@ -1143,7 +1185,9 @@ class Network:
         self._provided.add(key)
         for peer in self._dht_targets(key, REPLICATION):
             try:
-                await self._send_to(peer, {"t": "dht_provide", "key": key, "provider": self.peer_id}, "/ipfs/kad/1.0.0")
+                f = self._sign_record({"t": "dht_provide", "key": key, "provider": self.peer_id, "publisher": self.peer_id,
+                                       "kind": "provider", "value": b""})
+                await self._send_to(peer, f, "/ipfs/kad/1.0.0")
             except NetworkError:
                 pass
 

@@ -609,6 +609,12 @@ class UdpEndpoint(asyncio.DatagramProtocol):
         if half is not None:                                   # retransmitted INIT: repeat our answer
             self.sendto(half.hs["resp"], addr)
             return
+        # half-open connections older than 10 s are forgotten (an INIT flood must not pin memory)
+        now = time.monotonic()
+        for k, v in list(self._pending_init.items()):
+            if now - v.hs.get("t0", now) > 10.0:
+                self._pending_init.pop(k, None)
+                v._fail("handshake never completed", notify=False)
         scid = os.urandom(8)
         link = UdpLink(self, addr, scid, False)
         link.dcid = ccid
@@ -619,7 +625,7 @@ class UdpEndpoint(asyncio.DatagramProtocol):
         hk, c2s, s2c = self._keys(shared, transcript)
         blob = self._aead(hk).encrypt(b"\0" * 11 + b"\1", self._auth_blob(transcript, b"server"), transcript)
         resp = struct.pack("<B8s8s", RESP, ccid, scid) + e_pub + blob
-        link.hs = {"hk": hk, "transcript": transcript, "c2s": c2s, "s2c": s2c, "resp": resp}
+        link.hs = {"hk": hk, "transcript": transcript, "c2s": c2s, "s2c": s2c, "resp": resp, "t0": now}
         self.conns[scid] = link
         self._pending_init[(addr, ccid)] = link
         if len(self._pending_init) > 1024:

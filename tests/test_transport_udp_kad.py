@@ -238,3 +238,38 @@ def test_dht_maintenance_republishes_to_a_gateway_that_joined_later():
             await n.close()
 
     run(main())
+
+
+def test_replicated_records_are_verifiable_under_a_pki():
+    """With certificates every record carries its publisher's Ed25519 signature: a DHT server cannot plant a record
+    under somebody else's name through the server-to-server replication path."""
+    from hypha_b200.transport.utils import peer_id_from_key_pem
+
+    async def main():
+        _, _, _, tls = _pki(["g1", "g2", "data", "rogue"])
+        ids = {n: peer_id_from_key_pem(t["key_pem"]) for n, t in tls.items()}
+        g1 = Network(ids["g1"], relay_server=True, dht_server=True, tls=tls["g1"])
+        g2 = Network(ids["g2"], relay_server=True, dht_server=True, tls=tls["g2"])
+        for g in (g1, g2):
+            g.enable_dht_handlers()
+        a1 = await g1.listen("udp://127.0.0.1:0")
+        a2 = await g2.listen("udp://127.0.0.1:0")
+        await g1.dial(a2)
+        data = Network(ids["data"], tls=tls["data"])
+        await data.dial(a1)
+        await data.put_record("dataset", b"real")
+        await asyncio.sleep(0.3)
+        assert g2._records["dataset"] == (b"real", ids["data"])          # replicated, signature verified
+        # a rogue DHT server (valid certificate of its own) forges a record in the data node's name
+        rogue = Network(ids["rogue"], dht_server=True, tls=tls["rogue"])
+        await rogue.dial(a2)
+        before = g2.identity_rejections
+        forged = {"t": "dht_replicate", "key": "dataset", "value": b"poison", "publisher": ids["data"], "kind": "record"}
+        await rogue._send(rogue.links[ids["g2"]], dict(forged), "/ipfs/kad/1.0.0")                       # unsigned
+        await rogue._send(rogue.links[ids["g2"]], rogue._sign_record(dict(forged)) | {"publisher": ids["data"]}, "/ipfs/kad/1.0.0")
+        await asyncio.sleep(0.2)
+        assert g2._records["dataset"] == (b"real", ids["data"]) and g2.identity_rejections == before + 2
+        for n in (data, rogue, g1, g2):
+            await n.close()
+
+    run(main())
