@@ -16,7 +16,7 @@ import hashlib
 import ipaddress
 import time
 from collections import OrderedDict
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Iterable, List, Optional, Sequence, Tuple
 
 K = 20                  # bucket size
 ALPHA = 3               # parallelism of an iterative lookup
