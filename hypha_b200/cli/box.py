@@ -41,6 +41,8 @@ def build_parser() -> argparse.ArgumentParser:
     r.add_argument("--outer-lr", type=float, default=0.7)
     r.add_argument("--outer-momentum", type=float, default=0.9)
     r.add_argument("--aggregation", choices=["collective", "parameter-server"], default="collective")
+    r.add_argument("--precision", choices=["bf16", "mxfp8", "fp8"], default="bf16",
+                   help="GEMM precision of the inner steps on GPU executors ([scheduler.job.precision] gemm)")
     r.add_argument("--job", default=None, help="extra [scheduler.job] keys as JSON (merged last)")
     r.add_argument("--work-dir", default=None, help="scratch directory (default: a temporary one, removed at exit)")
     r.add_argument("--timeout", type=float, default=3600.0)
@@ -92,6 +94,7 @@ def run(args) -> int:
         "inner_optimizer": {"learning-rate": args.lr},
         "outer_optimizer": {"learning-rate": args.outer_lr, "momentum": args.outer_momentum},
         "aggregation": {"mode": args.aggregation},
+        "precision": {"gemm": args.precision},
         "resources": {"num_workers": workers, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
@@ -123,7 +126,7 @@ def run(args) -> int:
     for rec in sink.records:
         by_worker.setdefault(rec["worker_id"], {}).setdefault(str(rec["round"]), {})[rec["metric_name"]] = rec["value"]
     print(json.dumps({"finished": outcome.finished, "rounds": outcome.rounds, "workers": outcome.workers,
-                      "removed_workers": outcome.removed_workers, "aggregation": args.aggregation,
+                      "removed_workers": outcome.removed_workers, "aggregation": args.aggregation, "precision": args.precision,
                       "device": "cuda" if use_cuda else "cpu", "metrics": by_worker}))
     if not outcome.finished:
         print("\n".join(logs[-30:]), file=sys.stderr)

@@ -755,6 +755,8 @@ def apply_precision(precision: Optional[str], device: str) -> str:
         from .. import ops
 
         ops.set_fp8(True, mode="mx" if precision == "mxfp8" else "tensor")
+        print(f"inner-step GEMMs in {precision} ({'block-scaled tcgen05.mma.kind::mxf8f6f4' if precision == 'mxfp8' else 'kind::f8f6f4, per-tensor scales'})",
+              flush=True)
         return precision
     return "bf16"
 
