@@ -47,40 +47,8 @@ void uds_send_fds(const std::string& path, int rank, const std::vector<int>& fds
                   double io_timeout_s);
 std::map<int, std::vector<int>> uds_recv_fds(int server_fd, int count, int nfds, double timeout_s);
 
-constexpr int kMaxRanks = 8;   // one NVSwitch box; `outer_step.cu` carries 8 peer pointers
-
-struct EpochSnapshot {
-  uint64_t epoch = 0;        // bumps on every membership / ownership / flag-epoch change
-  uint64_t flag_epoch = 0;   // token base of the device-side flag barriers
-  uint32_t mask = 0;         // members
-  int world = 0;
-  int owner[kMaxRanks] = {}; // shard -> rank that holds its fp32 theta_outer + momentum
-};
-
-class EpochTable {
- public:
-  explicit EpochTable(int world);
-  EpochSnapshot snapshot() const;                    // lock-free, consistent
-  // member leaves; every shard it held goes to `adopter`, or (adopter < 0) to the next live rank after the shard
-  uint64_t drop(int rank, int adopter = -1);
-  uint64_t set_mask(uint32_t mask);                  // membership as decided by the control plane
-  uint64_t set_owner(int shard, int rank);
-  uint64_t admit(int rank, bool take_back_shard);    // member (re)joins; optionally owns its own shard again
-  uint64_t set_flag_epoch(uint64_t v);
-
- private:
-  void publish_begin();
-  void publish_end();
-  mutable std::mutex mu_;
-  std::atomic<uint64_t> seq_{0};
-  std::atomic<uint64_t> epoch_{0}, flag_epoch_{0};
-  std::atomic<uint32_t> mask_{0};
-  std::atomic<int> world_{0};
-  std::atomic<int> owner_[kMaxRanks];
-};
-
-uint64_t epoch_stress(int world, int readers, int iters);
-
 }  // namespace vmm
 }  // namespace comm
 }  // namespace hb
+
+#include "epoch_table.hpp"

@@ -3,8 +3,9 @@
 #
 #   tools/sanitize.sh core      ASAN+UBSAN build of the C++ control-plane core, runs tests/test_core.py and
 #                               tests/test_ps_round.py against it (CPU)
-#   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model and of the
-#                               parameter-server reducer (+ ASAN/UBSAN over the latter) (CPU)
+#   tools/sanitize.sh tsan      ThreadSanitizer run of the cross-GPU flag-barrier protocol model, of the
+#                               parameter-server reducer (+ ASAN/UBSAN over the latter) and of the membership-epoch
+#                               table under concurrent re-binds (CPU)
 #   tools/sanitize.sh memcheck  compute-sanitizer --tool memcheck  over the kernel numerics tests (GPU box)
 #   tools/sanitize.sh racecheck compute-sanitizer --tool racecheck (shared-memory hazards; GPU box)
 #   tools/sanitize.sh synccheck compute-sanitizer --tool synccheck (barrier misuse; GPU box)
@@ -42,6 +43,10 @@ case "${1:-core}" in
     $SCXX -O1 -g -std=c++17 -fsanitize=thread -fno-omit-frame-pointer -I hypha_b200/csrc \
         tools/tsan_ps_reduce.cpp -o "$OUT/tsan_ps_reduce" -pthread
     "$OUT/tsan_ps_reduce"
+    # membership-epoch table of the fused outer step: snapshots under concurrent re-binds
+    $SCXX -O1 -g -std=c++17 -fsanitize=thread -fno-omit-frame-pointer -I hypha_b200/csrc \
+        tools/tsan_epoch_table.cpp -o "$OUT/tsan_epoch_table" -pthread
+    "$OUT/tsan_epoch_table"
     # the same driver under ASAN+UBSAN: mmap bounds and unaligned tensor data
     $SCXX -O1 -g -std=c++17 -fsanitize=address,undefined -fno-omit-frame-pointer -I hypha_b200/csrc \
         tools/tsan_ps_reduce.cpp -o "$OUT/asan_ps_reduce" -pthread
