@@ -27,7 +27,10 @@ def _spawn(args, env, log):
 
 
 @pytest.mark.timeout(300)
-def test_roles_as_separate_processes_over_tcp_with_mtls(tmp_path):
+@pytest.mark.parametrize("scheme", ["tcp", "udp"])
+def test_roles_as_separate_processes_over_tcp_with_mtls(tmp_path, scheme):
+    """``tcp``: TLS 1.3 links.  ``udp``: the same deployment over the encrypted datagram transport (the reference's
+    QUIC listeners) -- every role listens on and dials udp:// addresses, certificates authenticate the handshake."""
     from hypha_b200 import certutil
     from hypha_b200.executor.dataset import write_synthetic_token_slices
     from hypha_b200.models.gpt2 import GPT2Config
@@ -46,7 +49,7 @@ def test_roles_as_separate_processes_over_tcp_with_mtls(tmp_path):
     ds = os.path.join(tmp, "toyset")
     write_synthetic_token_slices(ds, num_slices=6, samples_per_slice=16, seq_len=32, vocab_size=512)
     port = _free_port()
-    gw = f"tcp://127.0.0.1:{port}"
+    gw = f"{scheme}://127.0.0.1:{port}"
     env = dict(os.environ, HYPHA_HF_LOCAL=os.path.join(tmp, "registry"), OMP_NUM_THREADS="2",
                HYPHA_EXECUTOR_DEVICE="cpu", PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
 
@@ -54,6 +57,8 @@ def test_roles_as_separate_processes_over_tcp_with_mtls(tmp_path):
         p = os.path.join(tmp, f"{name}.toml")
         t = tls[name]
         head = "".join(f'{t[i]} = "{t[i + 1]}"\n' for i in range(0, 6, 2)) + 'exclude_cidr = ["0.0.0.0/32"]\n'
+        if "listen_addresses" not in body:
+            head += f'listen_addresses = ["{scheme}://127.0.0.1:0"]\n'
         open(p, "w").write(head + body)
         return p
 
