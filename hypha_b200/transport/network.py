@@ -428,6 +428,7 @@ class Network:
         self.peer_addrs: Dict[str, List[str]] = {}
         self.listen_addrs: List[str] = []
         self.external_addrs: List[str] = []
+        self.observed_addrs: List[str] = []       # our udp address as peers see it (identify), newest last
         self._servers: List[asyncio.AbstractServer] = []
         self._udp: List[Any] = []             # UdpEndpoint objects: the first one also carries outgoing udp:// dials
         self.relayed_frames = 0               # frames this node forwarded as a relay server
@@ -678,7 +679,11 @@ class Network:
 
     # -- direct connection upgrade through relay (dcutr) ----------------------------------------------------------------
     def _dcutr_addrs(self) -> List[str]:
-        addrs = [a for a in (self.external_addrs or self.listen_addrs) if a.startswith(("udp://", "tcp://"))]
+        addrs = [a for a in (self.external_addrs or self.listen_addrs) if a.startswith(("udp://", "tcp://"))
+                 and "://0.0.0.0:" not in a and "://[::]:" not in a]              # a wildcard bind is not an address
+        for a in self.observed_addrs:                                            # what a peer saw us as (behind a NAT)
+            if a not in addrs:
+                addrs.append(a)
         return sorted(addrs, key=lambda a: not a.startswith("udp://"))            # udp first: it can be hole-punched
 
     def _enable_dcutr(self) -> None:
@@ -801,7 +806,19 @@ class Network:
             if fut is not None and not fut.done():
                 fut.set_result(peer)
             elif first:
-                await self._send(link, self._hello(), "/hypha-identify/0.0.1")
+                reply = self._hello()
+                # identify's observed address: on a udp:// link the source of the peer's datagrams IS the public
+                # mapping of the socket it listens on (one socket per node) -- what a node behind a NAT needs to know
+                # about itself before it can be hole-punched
+                obs = getattr(link, "addr", None)
+                if obs is not None and type(link).__name__ == "UdpLink":
+                    host = f"[{obs[0]}]" if ":" in obs[0] else obs[0]
+                    reply["observed"] = f"udp://{host}:{obs[1]}"
+                await self._send(link, reply, "/hypha-identify/0.0.1")
+            if isinstance(frame.get("observed"), str) and frame["observed"].startswith("udp://") \
+                    and self._udp and frame["observed"] not in self.observed_addrs:
+                self.observed_addrs.append(frame["observed"])
+                del self.observed_addrs[:-4]                  # a few recent ones (several gateways, re-mappings)
             if self.dht_server:      # replicate our records to the newcomer lazily on get; nothing to do
                 pass
         elif t == "relay":

@@ -273,3 +273,30 @@ def test_replicated_records_are_verifiable_under_a_pki():
             await n.close()
 
     run(main())
+
+
+def test_observed_address_makes_a_wildcard_listener_reachable_for_hole_punching():
+    """A node that binds udp://0.0.0.0 does not know an address others can use; the gateway tells it how its
+    datagrams arrive (identify's observed address), and the direct-connection upgrade works with that."""
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        gaddr = await gw.listen("udp://127.0.0.1:0")
+        a, b = await _echo_node("a"), await _echo_node("b")
+        for n in (a, b):
+            await n.listen("udp://0.0.0.0:0")
+            n._udp[0].nat_filter = True
+            await n.dial(gaddr)                       # over the node's one UDP socket
+        port_b = b._udp[0].local_addr[1]
+        assert b.observed_addrs == [f"udp://127.0.0.1:{port_b}"] and a.observed_addrs
+        assert b._dcutr_addrs() == [f"udp://127.0.0.1:{port_b}"]          # the wildcard bind is not advertised
+        a.peer_addrs.pop("b", None)
+        b.peer_addrs.pop("a", None)
+        a._dcutr_last["b"] = 1e18
+        assert (await a.request("b", "/echo", 1))["from"] == "a" and "b" not in a.links      # relayed
+        assert await a.upgrade_direct("b")
+        before = gw.relayed_frames
+        assert (await a.request("b", "/echo", 2))["echo"] == 2 and gw.relayed_frames == before
+        for n in (a, b, gw):
+            await n.close()
+
+    run(main())
