@@ -523,7 +523,7 @@ class Network:
         if host is None and self._udp:
             return self._udp[0]
         ep = UdpEndpoint(self.tls, lambda link: self._spawn(self._socket_loop(link)))
-        await asyncio.get_running_loop().create_datagram_endpoint(lambda: ep, local_addr=(host or "0.0.0.0", port))
+        ep.open(host or "0.0.0.0", port)
         self._udp.append(ep)
         self._enable_dcutr()
         return ep

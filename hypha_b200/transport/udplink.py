@@ -189,6 +189,11 @@ class UdpLink:
         if not self.closed or recs[:1] == b"C":
             self.ep.sendto(self._seal(recs), self.addr)
 
+    def flush_ack(self) -> None:
+        if self._ack_due and not self.closed and self._tx_key is not None:
+            self._ack_due = False
+            self._send_records(self._ack_record())
+
     def _ack_record(self) -> bytes:
         self._segs_since_ack = 0
         wnd = max(0, RWND - self._ooo_bytes - len(self._stream))
@@ -352,9 +357,7 @@ class UdpLink:
                 self._rcv_nxt += len(s)
             self._parse()
             self._segs_since_ack += 1
-            if self._segs_since_ack >= 2:                    # every second segment at once, a lone one after 10 ms
-                self._ack_due = False
-                self._send_records(self._ack_record())
+            self.ep._dirty.add(self)                         # one ACK per batch of datagrams read (`_on_readable`)
         elif off > self._rcv_nxt:
             if off not in self._ooo and self._ooo_bytes + len(seg) <= RWND:
                 self._ooo[off] = seg
@@ -435,12 +438,13 @@ class UdpLink:
         self._fail("closed")
 
 
-class UdpEndpoint(asyncio.DatagramProtocol):
+class UdpEndpoint:
     """One UDP socket, many connections (demultiplexed by the 8-byte destination connection id)."""
 
     def __init__(self, tls: Optional[dict], on_accept):
         self.tls, self.on_accept = tls, on_accept
-        self.transport: Optional[asyncio.DatagramTransport] = None
+        self.sock = None
+        self._dirty: set = set()                  # links that received in-order data in the current read batch
         self.conns: Dict[bytes, UdpLink] = {}
         self._pending_init: Dict[Tuple, UdpLink] = {}      # (addr, client cid) -> half-open server connection
         self.local_addr: Optional[Tuple[str, int]] = None
@@ -459,20 +463,43 @@ class UdpEndpoint(asyncio.DatagramProtocol):
             self._chain = [c.public_bytes(serialization.Encoding.DER)
                            for c in x509.load_pem_x509_certificates(open(tls["cert_pem"], "rb").read())]
 
-    def connection_made(self, transport) -> None:
+    def open(self, host: str, port: int) -> None:
+        """Bind the node's one UDP socket.  Reads are drained in batches (up to 64 datagrams per wake-up of the event
+        loop instead of one callback per datagram -- the loop iteration was the largest per-packet cost), and every
+        connection acknowledges once per batch."""
         import socket
 
-        self.transport = transport
-        self.local_addr = transport.get_extra_info("sockname")[:2]
-        sock = transport.get_extra_info("socket")
+        fam = socket.AF_INET6 if ":" in host else socket.AF_INET
+        sock = socket.socket(fam, socket.SOCK_DGRAM)
+        sock.setblocking(False)
         for opt in (socket.SO_RCVBUF, socket.SO_SNDBUF):         # as much as the kernel grants (rmem_max / wmem_max)
             try:
                 sock.setsockopt(socket.SOL_SOCKET, opt, 4 << 20)
             except OSError:
                 pass
+        sock.bind((host, port))
+        self.sock = sock
+        self.local_addr = sock.getsockname()[:2]
+        asyncio.get_running_loop().add_reader(sock.fileno(), self._on_readable)
+
+    def _on_readable(self) -> None:
+        sock = self.sock
+        if sock is None:
+            return
+        for _ in range(64):
+            try:
+                data, addr = sock.recvfrom(2048)
+            except (BlockingIOError, InterruptedError):
+                break
+            except OSError:
+                break
+            self.datagram_received(data, addr)
+        dirty, self._dirty = self._dirty, set()
+        for link in dirty:
+            link.flush_ack()
 
     def sendto(self, data: bytes, addr) -> None:
-        if self.transport is None or self.transport.is_closing():
+        if self.sock is None:
             return
         if self.drop_next > 0 and data[:1] == bytes([DATA]):
             self._drop_ctr += 1
@@ -480,13 +507,23 @@ class UdpEndpoint(asyncio.DatagramProtocol):
                 self.drop_next -= 1
                 return
         self._contacted.add(tuple(addr[:2]))
-        self.transport.sendto(data, addr)
+        try:
+            self.sock.sendto(data, addr)
+        except (BlockingIOError, InterruptedError):
+            pass                                   # a full send buffer is a lost datagram: the sender retransmits
+        except OSError:
+            pass
 
     def close(self) -> None:
         for c in list(self.conns.values()):
             c._fail("endpoint closed")
-        if self.transport is not None:
-            self.transport.close()
+        if self.sock is not None:
+            try:
+                asyncio.get_event_loop().remove_reader(self.sock.fileno())
+            except Exception:
+                pass
+            self.sock.close()
+            self.sock = None
 
     # -- handshake -------------------------------------------------------------------------------------------------------
     @staticmethod
