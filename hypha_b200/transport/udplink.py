@@ -33,6 +33,7 @@ INIT, RESP, FIN, DATA, CLOSE, PUNCH = 1, 2, 3, 4, 5, 6
 MSS = 1150                      # stream bytes per datagram (fits a 1280-byte path MTU with headers + tag)
 CWND = 1024 * 1024              # upper bound of the congestion window (bytes in flight)
 INIT_CWND = 16 * 1150
+INIT_MIN = 1200                 # smallest INIT datagram a server answers
 RWND = 4 * 1024 * 1024          # reassembly buffer the receiver advertises
 MIN_RTO, MAX_RTO = 0.05, 2.0
 MAX_FRAME = 16 << 20
@@ -460,8 +461,11 @@ class UdpEndpoint:
             from cryptography.hazmat.primitives import serialization
 
             self._key = serialization.load_pem_private_key(open(tls["key_pem"], "rb").read(), password=None)
-            self._chain = [c.public_bytes(serialization.Encoding.DER)
-                           for c in x509.load_pem_x509_certificates(open(tls["cert_pem"], "rb").read())]
+            # leaf first; the self-signed root stays home (the peer holds it as its trust anchor), which keeps the
+            # handshake datagrams of a three-level PKI under a 1280-byte MTU
+            certs = x509.load_pem_x509_certificates(open(tls["cert_pem"], "rb").read())
+            self._chain = [c.public_bytes(serialization.Encoding.DER) for i, c in enumerate(certs)
+                           if i == 0 or c.issuer != c.subject]
 
     def open(self, host: str, port: int) -> None:
         """Bind the node's one UDP socket.  Reads are drained in batches (up to 64 datagrams per wake-up of the event
@@ -575,7 +579,11 @@ class UdpEndpoint:
         e_pub = e.public_key().public_bytes(serialization.Encoding.Raw, serialization.PublicFormat.Raw)
         link.hs = {"e": e, "e_pub": e_pub}
         self.conns[scid] = link
+        # padded to INIT_MIN bytes: the server answers an INIT with ~1 KB (certificates) before the client has shown
+        # that it can receive at its source address, so the request must not be smaller than the answer (QUIC's rule
+        # against reflection amplification)
         init = struct.pack("<B8s8s", INIT, b"\0" * 8, scid) + e_pub
+        init += b"\0" * max(0, INIT_MIN - len(init))
         deadline = time.monotonic() + timeout
         delay = 0.1
         while not link.established.done():
@@ -639,8 +647,8 @@ class UdpEndpoint:
         from cryptography.hazmat.primitives import serialization
         from cryptography.hazmat.primitives.asymmetric.x25519 import X25519PrivateKey, X25519PublicKey
 
-        if len(data) < 17 + 32:
-            return
+        if len(data) < INIT_MIN:
+            return                                             # see `connect`: no amplification for spoofed sources
         ccid, e_c = data[9:17], data[17:49]
         half = self._pending_init.get((addr, ccid))
         if half is not None:                                   # retransmitted INIT: repeat our answer

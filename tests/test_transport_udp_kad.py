@@ -300,3 +300,39 @@ def test_observed_address_makes_a_wildcard_listener_reachable_for_hole_punching(
             await n.close()
 
     run(main())
+
+
+def test_udp_handshake_gives_no_amplification_and_fits_small_mtus():
+    """An INIT shorter than 1200 bytes is not answered (a spoofed source cannot turn 49 bytes into a kilobyte of
+    certificates aimed at a victim), and with a three-level PKI the handshake datagrams stay under 1280 bytes."""
+    import socket
+    import struct
+
+    from hypha_b200.transport import udplink
+    from hypha_b200.transport.utils import peer_id_from_key_pem
+
+    async def main():
+        _, _, _, tls = _pki(["s", "c"])
+        srv = Network(peer_id_from_key_pem(tls["s"]["key_pem"]), tls=tls["s"])
+        addr = await srv.listen("udp://127.0.0.1:0")
+        port = int(addr.rsplit(":", 1)[1])
+        probe = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        probe.setblocking(False)
+        probe.bind(("127.0.0.1", 0))
+        short = struct.pack("<B8s8s", udplink.INIT, b"\0" * 8, b"12345678") + b"\1" * 32
+        probe.sendto(short, ("127.0.0.1", port))
+        await asyncio.sleep(0.2)
+        with pytest.raises(BlockingIOError):
+            probe.recvfrom(4096)                                  # silence
+        probe.sendto(short + b"\0" * (udplink.INIT_MIN - len(short)), ("127.0.0.1", port))
+        await asyncio.sleep(0.2)
+        resp, _ = probe.recvfrom(4096)
+        assert resp[0] == udplink.RESP and len(resp) <= 1280 and len(resp) <= udplink.INIT_MIN + 80
+        probe.close()
+        assert len(srv._udp[0]._chain) == 2                       # node + organisation CA; the root is not sent
+        cli = Network(peer_id_from_key_pem(tls["c"]["key_pem"]), tls=tls["c"])
+        assert await cli.dial(addr) == srv.peer_id                # and the real handshake still verifies the chain
+        for n in (cli, srv):
+            await n.close()
+
+    run(main())
