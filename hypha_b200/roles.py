@@ -241,12 +241,17 @@ async def run_worker(cfg: C.WorkerConfig, *, peer_id: Optional[str] = None,
                       strategy=cfg.offer.strategy.type, log=log)
     node.arbiter = arbiter  # type: ignore[attr-defined]
     node.jobs = jobs  # type: ignore[attr-defined]
+    from .telemetry.gpu_monitor import start_for_worker
+
+    node.gpu_monitor = start_for_worker(cfg, node.telemetry, log)  # type: ignore[attr-defined]  # hypha.gpu.* gauges
     node.ready.set()                         # listening + bootstrapped (hypha-worker.rs:84-87,200)
     if started is not None and not started.done():
         started.set_result(node)
     try:
         await arbiter.run(node.stop)
     finally:
+        if node.gpu_monitor is not None:  # type: ignore[attr-defined]
+            node.gpu_monitor.stop()  # type: ignore[attr-defined]
         await jobs.shutdown()
         await node.shutdown()
 

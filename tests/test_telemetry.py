@@ -139,3 +139,67 @@ def test_otlp_http_export_reaches_a_collector():
     assert all(ct == "application/x-protobuf" and key == "secret" and size > 0 for p, ct, key, size in got
                if p in ("/v1/traces", "/v1/metrics"))
     assert "/v1/logs" in paths          # the log bridge exported the warning
+
+
+def test_gpu_monitor_samples_exports_and_raises_the_alarm():
+    """Worker resource monitor against a fake NVML: samples become hypha.gpu.* gauges with a gpu attribute, power-cap
+    throttling is normal, a hardware / thermal slowdown is reported once per change."""
+    import types
+
+    from opentelemetry.sdk.metrics.export import InMemoryMetricReader
+
+    from hypha_b200.telemetry.gpu_monitor import GpuMonitor, decode_reasons
+
+    state = {"mask": 0x4, "temp": 61}
+
+    class FakeNvml:
+        NVML_TEMPERATURE_GPU, NVML_CLOCK_SM = 0, 1
+        calls = []
+
+        def nvmlInit(self): self.calls.append("init")
+        def nvmlShutdown(self): self.calls.append("shutdown")
+        def nvmlDeviceGetCount(self): return 2
+        def nvmlDeviceGetHandleByIndex(self, i): return i
+        def nvmlDeviceGetUtilizationRates(self, h): return types.SimpleNamespace(gpu=97 - h, memory=40)
+        def nvmlDeviceGetMemoryInfo(self, h): return types.SimpleNamespace(used=(100 + h) << 30, total=180 << 30)
+        def nvmlDeviceGetTemperature(self, h, kind): return state["temp"] + h
+        def nvmlDeviceGetPowerUsage(self, h): return 995_000
+        def nvmlDeviceGetClockInfo(self, h, kind): return 1455
+        def nvmlDeviceGetCurrentClocksEventReasons(self, h): return state["mask"] if h == 1 else 0x4
+
+    assert decode_reasons(0x4 | 0x40) == ["sw_power_cap", "hw_thermal_slowdown"]
+    logs = []
+    reader = InMemoryMetricReader()
+    tel = T.Telemetry("gpu", metric_reader=reader)
+    mon = GpuMonitor(nvml=FakeNvml(), log=logs.append)
+    assert mon.devices == [0, 1]
+    mon.register(tel)
+    mon._tick()
+    s = mon.last()
+    assert s[0]["utilization_pct"] == 97 and s[1]["memory_used"] == 101 << 30 and s[0]["power_w"] == 995.0
+    assert s[0]["throttle_reasons"] == ["sw_power_cap"] and mon.health() == {"healthy": True, "throttled": {}} and not logs
+    data = reader.get_metrics_data()
+    got = {}
+    for rm in data.resource_metrics:
+        for sm in rm.scope_metrics:
+            for m in sm.metrics:
+                if m.name.startswith("hypha.gpu."):
+                    got[m.name] = {dp.attributes["gpu"]: dp.value for dp in m.data.data_points}
+    assert got["hypha.gpu.utilization"] == {"0": 97.0, "1": 96.0} and got["hypha.gpu.clock.sm"]["1"] == 1455.0
+    assert got["hypha.gpu.temperature"] == {"0": 61.0, "1": 62.0} and got["hypha.gpu.throttled"] == {"0": 0, "1": 0}
+    # GPU 1 overheats: one log line, the gauge flips, health says which device and why; then it recovers
+    state["mask"], state["temp"] = 0x4 | 0x40 | 0x8, 91
+    mon._tick()
+    mon._tick()
+    assert len(logs) == 1 and "gpu 1" in logs[0] and "hw_thermal_slowdown" in logs[0] and "hw_slowdown" in logs[0]
+    assert mon.health() == {"healthy": False, "throttled": {1: ["hw_slowdown", "hw_thermal_slowdown"]}}
+    state["mask"] = 0x4
+    mon._tick()
+    assert len(logs) == 2 and "normal clocks" in logs[1] and mon.health()["healthy"]
+    mon.stop()
+    assert "shutdown" in FakeNvml.calls
+    # a machine without NVML: the worker simply has no monitor
+    from hypha_b200.telemetry.gpu_monitor import start_for_worker
+
+    cfg = types.SimpleNamespace(resources=types.SimpleNamespace(gpu=0.0), device=None)
+    assert start_for_worker(cfg, tel, logs.append) is None
