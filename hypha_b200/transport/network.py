@@ -692,7 +692,7 @@ class Network:
         self._dcutr_on = True
 
         async def serve(peer: str, msg: Any):
-            theirs = [a for a in (msg.get("connect") or []) if isinstance(a, str)][:8]
+            theirs = self.kad.cidr.filter([a for a in (msg.get("connect") or []) if isinstance(a, str)][:8])
             ep = self._udp[0] if self._udp else None
             for a in theirs:
                 if ep is not None and a.startswith("udp://"):
@@ -732,7 +732,7 @@ class Network:
             r = await self.request(peer, DCUTR_PROTOCOL, {"connect": self._dcutr_addrs()}, timeout=timeout)
         except NetworkError:
             return False
-        theirs = [a for a in (r.get("addrs") or []) if isinstance(a, str)][:8]
+        theirs = self.kad.cidr.filter([a for a in (r.get("addrs") or []) if isinstance(a, str)][:8])
         for a in theirs:
             if a.startswith("udp://"):
                 host, port = a[len("udp://"):].rsplit(":", 1)
@@ -789,11 +789,13 @@ class Network:
             link.peer_id = peer
             link.is_relay = bool(frame.get("relay"))  # type: ignore[attr-defined]
             self.links[peer] = link
+            # addresses a peer tells us about are dialled later: they pass the same CIDR filter as the routing table
+            # (a peer must not be able to point this node at an address range the operator excluded)
             if frame.get("addrs"):
-                self.peer_addrs[peer] = list(frame["addrs"])
+                self.peer_addrs[peer] = self.kad.cidr.filter([a for a in frame["addrs"] if isinstance(a, str)][:16])
             for p, a in (frame.get("known") or {}).items():
-                if p != self.peer_id:
-                    self.peer_addrs.setdefault(p, list(a))
+                if p != self.peer_id and isinstance(a, (list, tuple)):
+                    self.peer_addrs.setdefault(p, self.kad.cidr.filter([x for x in a if isinstance(x, str)][:16]))
             self._peer_topics[peer] = set(frame.get("topics", []))
             if frame.get("dht"):
                 self._bootstrapped.set()

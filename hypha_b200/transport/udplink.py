@@ -673,8 +673,9 @@ class UdpEndpoint:
         link.hs = {"hk": hk, "transcript": transcript, "c2s": c2s, "s2c": s2c, "resp": resp, "t0": now}
         self.conns[scid] = link
         self._pending_init[(addr, ccid)] = link
-        if len(self._pending_init) > 1024:
-            self._pending_init.pop(next(iter(self._pending_init)))
+        if len(self._pending_init) > 1024:                      # a flood: the oldest half-open connection goes
+            k = next(iter(self._pending_init))
+            self._pending_init.pop(k)._fail("too many half-open connections", notify=False)
         self.sendto(resp, addr)
 
     def _on_resp(self, data: bytes, addr) -> None:

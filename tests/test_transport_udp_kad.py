@@ -336,3 +336,23 @@ def test_udp_handshake_gives_no_amplification_and_fits_small_mtus():
             await n.close()
 
     run(main())
+
+
+def test_addresses_learnt_from_peers_pass_the_cidr_filter():
+    """What a peer says about itself (or, as a relay, about others) is dialled later: with `exclude_cidr` set such
+    addresses are dropped, so a peer cannot point this node at a range the operator ruled out."""
+    async def main():
+        gw = Network("gw", relay_server=True, dht_server=True)
+        gaddr = await gw.listen("tcp://127.0.0.1:0")
+        liar = Network("liar")
+        liar.add_external_address("tcp://10.0.0.7:22")
+        liar.add_external_address("tcp://93.184.216.34:4001")
+        await liar.dial(gaddr)
+        strict = Network("strict", exclude_cidrs=("10.0.0.0/8",))
+        await strict.dial(gaddr)
+        assert strict.peer_addrs["liar"] == ["tcp://93.184.216.34:4001"]          # via the gateway's peer table
+        assert gw.peer_addrs["liar"] == ["tcp://10.0.0.7:22", "tcp://93.184.216.34:4001"]     # no filter configured
+        for n in (liar, strict, gw):
+            await n.close()
+
+    run(main())
