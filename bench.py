@@ -504,6 +504,8 @@ def main():
         try:
             from torch.profiler import ProfilerActivity, profile
 
+            with profile(activities=[ProfilerActivity.CUDA]):       # CUPTI start-up (seconds, differs per rank) happens here,
+                torch.cuda.synchronize()                            # not between the ranks' entries into the fused kernel
             barrier()
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
                 trainer.outer_step()
