@@ -4,6 +4,7 @@
 #include <pybind11/stl.h>
 
 #include "core.hpp"
+#include "kad.hpp"
 #include "flag_barrier_model.hpp"
 #include "ps_reduce.hpp"
 
@@ -190,6 +191,24 @@ PYBIND11_MODULE(_core, m) {
       .def_readonly("violations", &FlagBarrierReport::violations)
       .def_readonly("timeouts", &FlagBarrierReport::timeouts)
       .def_readonly("missing_union", &FlagBarrierReport::missing_union);
+  // ---- Kademlia routing table (kad.hpp) ----
+  m.def("sha256", [](const std::string& s) {
+    const hb::kad::Id d = hb::kad::sha256(s);
+    return py::bytes(reinterpret_cast<const char*>(d.data()), d.size());
+  });
+  py::class_<hb::kad::RoutingTable>(m, "KadTable")
+      .def(py::init<const std::string&, int>(), py::arg("self_id"), py::arg("k") = 20)
+      .def("add", &hb::kad::RoutingTable::add, py::arg("peer"), py::arg("addrs"), py::arg("connected") = true)
+      .def("mark_disconnected", &hb::kad::RoutingTable::mark_disconnected)
+      .def("remove", &hb::kad::RoutingTable::remove)
+      .def("contains", &hb::kad::RoutingTable::contains)
+      .def("addrs", &hb::kad::RoutingTable::addrs)
+      .def("peers", &hb::kad::RoutingTable::peers)
+      .def("bucket", &hb::kad::RoutingTable::bucket)
+      .def("bucket_index", &hb::kad::RoutingTable::bucket_index)
+      .def("closest", &hb::kad::RoutingTable::closest, py::arg("key"), py::arg("n") = 20, py::arg("include_self") = false)
+      .def("__len__", &hb::kad::RoutingTable::size);
+
   m.def("flag_barrier_stress",
         [](int world, uint32_t member_mask, int epochs, int stages, uint32_t seed, int dead_rank, int timeout_ms,
            uint32_t first_epoch) {

@@ -4,7 +4,8 @@ towards the key `:482-737`; reserved address ranges crates/network/src/lib.rs:57
 
 * ids: ``sha256(peer id)`` / ``sha256(key)``, distance = XOR, 256 buckets by the length of the common prefix with our
   own id, `K` entries per bucket in least-recently-seen order; a full bucket keeps its old, still connected entries and
-  replaces a stale one (Kademlia's preference for long-lived nodes);
+  replaces a stale one (Kademlia's preference for long-lived nodes) -- implemented in the C++ core
+  (`csrc/core/kad.hpp`, bound as `_core.KadTable`), like the reference's table is native;
 * only peers that announce themselves as DHT servers are routable, and only with addresses that pass the CIDR filter:
   in strict mode an address inside a reserved range (loopback, RFC 1918, link-local, CGNAT, multicast, documentation
   nets, ...) is not learnt, and a peer with no acceptable address does not enter the table;
@@ -14,8 +15,6 @@ from __future__ import annotations
 
 import hashlib
 import ipaddress
-import time
-from collections import OrderedDict
 from typing import Iterable, List, Optional, Sequence, Tuple
 
 K = 20                  # bucket size
@@ -67,16 +66,24 @@ class CidrFilter:
 
 
 class RoutingTable:
+    """Policy layer over the native table (`csrc/core/kad.hpp`: sha256 ids, XOR metric, k-buckets, closest): this
+    class only decides WHICH addresses of a peer may be learnt (CIDR filter) and counts what it turned away."""
+
     def __init__(self, self_id: str, k: int = K, cidr: Optional[CidrFilter] = None):
+        from ..ops.native import load_core
+
         self.self_id, self.k = self_id, k
-        self._self = key_id(self_id)
         self.cidr = cidr or CidrFilter()
-        self.buckets: List["OrderedDict[str, dict]"] = [OrderedDict() for _ in range(256)]
+        self._t = load_core().KadTable(self_id, k)
         self.rejected_by_cidr = 0
 
-    def _bucket(self, peer: str) -> "OrderedDict[str, dict]":
-        d = key_id(peer) ^ self._self
-        return self.buckets[255 - (d.bit_length() - 1) if d else 255]
+    @property
+    def buckets(self) -> List[List[str]]:
+        """Peers per bucket (index = length of the id prefix shared with this node), least recently seen first."""
+        return [self._t.bucket(i) for i in range(256)]
+
+    def _bucket(self, peer: str) -> List[str]:
+        return self._t.bucket(self._t.bucket_index(peer))
 
     def add(self, peer: str, addrs: Sequence[str], connected: bool = True) -> bool:
         """Learn (or refresh) a DHT server.  False when the CIDR filter leaves it without an address or its bucket is
@@ -87,44 +94,25 @@ class RoutingTable:
         if addrs and not ok:
             self.rejected_by_cidr += 1
             return False
-        b = self._bucket(peer)
-        ent = {"addrs": list(ok), "seen": time.monotonic(), "connected": connected}
-        if peer in b:
-            if not ok:
-                ent["addrs"] = b[peer]["addrs"]
-            b.pop(peer)
-            b[peer] = ent
-            return True
-        if len(b) >= self.k:
-            stale = next((p for p, e in b.items() if not e["connected"]), None)
-            if stale is None:
-                return False
-            b.pop(stale)
-        b[peer] = ent
-        return True
+        return bool(self._t.add(peer, list(ok), connected))
 
     def mark_disconnected(self, peer: str) -> None:
-        b = self._bucket(peer)
-        if peer in b:
-            b[peer]["connected"] = False
+        self._t.mark_disconnected(peer)
 
     def remove(self, peer: str) -> None:
-        self._bucket(peer).pop(peer, None)
+        self._t.remove(peer)
 
     def addrs(self, peer: str) -> List[str]:
-        e = self._bucket(peer).get(peer)
-        return list(e["addrs"]) if e else []
+        return list(self._t.addrs(peer))
 
     def peers(self) -> List[str]:
-        return [p for b in self.buckets for p in b]
+        return list(self._t.peers())
 
     def __len__(self) -> int:
-        return sum(len(b) for b in self.buckets)
+        return len(self._t)
 
     def __contains__(self, peer: str) -> bool:
-        return peer in self._bucket(peer)
+        return bool(self._t.contains(peer))
 
     def closest(self, key: str, n: int = K, include_self: bool = False) -> List[str]:
-        t = key_id(key)
-        cand = self.peers() + ([self.self_id] if include_self else [])
-        return sorted(cand, key=lambda p: key_id(p) ^ t)[:n]
+        return list(self._t.closest(key, n, include_self))

@@ -337,3 +337,40 @@ def test_updated_is_idempotent_within_one_synchronisation():
         acks = [sched.handle(w, K.UpdateReceived, 0, t + 5) for w in ("w0", "w1")]
         assert all(a.kind == (R.Done if rnd == 1 else R.Continue) for a in acks)
     assert acks[-1].all_done and sched.tracker.training_finished()
+
+
+def test_native_kad_table_matches_the_xor_metric():
+    """`_core.KadTable` (csrc/core/kad.hpp): native SHA-256 ids, XOR ordering, bucket index = shared prefix length,
+    least-recently-seen order, live entries win -- checked against hashlib / big-integer arithmetic."""
+    import hashlib
+
+    from hypha_b200.ops.native import load_core
+
+    core = load_core()
+    for m in ("", "abc", "a" * 55, "b" * 56, "c" * 64, "d" * 1000):
+        assert core.sha256(m) == hashlib.sha256(m.encode()).digest()
+
+    def h(s):
+        return int.from_bytes(hashlib.sha256(s.encode()).digest(), "big")
+
+    t = core.KadTable("self", 3)
+    peers = [f"peer-{i}" for i in range(300)]
+    accepted = [p for p in peers if t.add(p, [f"tcp://1.2.3.{i % 250}:1" for i in range(2)], True)]
+    assert len(t) == len(accepted) and not t.add("self", [], True)
+    for p in peers[:40]:
+        assert t.bucket_index(p) == 256 - (h(p) ^ h("self")).bit_length()
+    assert all(len(t.bucket(i)) <= 3 for i in range(256)) and sum(len(t.bucket(i)) for i in range(256)) == len(t)
+    for key in ("k1", "dataset", "another key"):
+        want = sorted(accepted, key=lambda p: h(p) ^ h(key))
+        assert t.closest(key, 7, False) == want[:7]
+        with_self = sorted(accepted + ["self"], key=lambda p: h(p) ^ h(key))
+        assert t.closest(key, len(accepted) + 5, True) == with_self
+    assert t.closest("k", 0, False) == []
+    full = next(i for i in range(256) if len(t.bucket(i)) == 3)
+    rejected = next(p for p in peers if p not in accepted and t.bucket_index(p) == full)
+    assert not t.add(rejected, ["tcp://9.9.9.9:1"], True)
+    victim = t.bucket(full)[1]
+    t.mark_disconnected(victim)
+    assert t.add(rejected, ["tcp://9.9.9.9:1"], True) and not t.contains(victim) and t.bucket(full)[-1] == rejected
+    t.remove(rejected)
+    assert not t.contains(rejected) and t.addrs(rejected) == [] and len(t.bucket(full)) == 2

@@ -151,12 +151,23 @@ def test_routing_table_buckets_cidr_filter_and_closest():
         t.add(p, [f"tcp://8.8.{len(p)}.{int(p[1:]) % 250}:1"])
     assert 2 <= len(t) <= 2 * 256 and all(len(b) <= 2 for b in t.buckets)
     # full buckets prefer their old, live entries; a stale entry makes room
-    b = next(b for b in t.buckets if len(b) == 2)
-    old = list(b)
-    newcomer = next(p for p in (f"q{i}" for i in range(100000)) if t._bucket(p) is b and p not in b)
-    assert not t.add(newcomer, ["tcp://8.8.8.8:1"]) and list(b) == old
+    bi = next(i for i, b in enumerate(t.buckets) if len(b) == 2)
+    old = t.buckets[bi]
+    newcomer = next(p for p in (f"q{i}" for i in range(100000)) if t._t.bucket_index(p) == bi and p not in old)
+    assert not t.add(newcomer, ["tcp://8.8.8.8:1"]) and t.buckets[bi] == old
     t.mark_disconnected(old[0])
-    assert t.add(newcomer, ["tcp://8.8.8.8:1"]) and old[0] not in b and newcomer in b
+    assert t.add(newcomer, ["tcp://8.8.8.8:1"]) and old[0] not in t.buckets[bi] and newcomer in t.buckets[bi]
+    # refreshing an entry moves it to the most-recently-seen end and keeps its addresses when none are given
+    first = t.buckets[bi][0]
+    assert t.add(first, []) and t.buckets[bi][-1] == first and t.addrs(first)
+    # the bucket index is the length of the id prefix shared with our own id
+    import hashlib
+
+    def lz(p):
+        d = int.from_bytes(hashlib.sha256(p.encode()).digest(), "big") ^ int.from_bytes(hashlib.sha256(b"me").digest(), "big")
+        return 256 - d.bit_length()
+
+    assert all(t._t.bucket_index(p) == lz(p) for p in peers[:50])
     # closest() is the XOR order
     want = sorted(t.peers(), key=lambda p: key_id(p) ^ key_id("some-key"))[:5]
     assert t.closest("some-key", 5) == want
