@@ -34,6 +34,11 @@ MSS = 1150                      # stream bytes per datagram (fits a 1280-byte pa
 CWND = 1024 * 1024              # upper bound of the congestion window (bytes in flight)
 INIT_CWND = 16 * 1150
 INIT_MIN = 1200                 # smallest INIT datagram a server answers
+# Path-MTU discovery (the socket sets DF): after the handshake each side probes larger datagrams and raises its
+# segment size to the largest one the peer acknowledged -- 1150 bytes suit the internet, a jumbo-frame fabric carries
+# 8.9 KB, loopback 60 KB, and the per-datagram cost (crypto, syscall, bookkeeping) is what bounds the stream rate.
+PROBE_SIZES = (1400, 4000, 8900, 16000, 32000, 60000)
+OVERHEAD = 17 + 16 + 11         # packet header + AEAD tag + segment record header
 RWND = 4 * 1024 * 1024          # reassembly buffer the receiver advertises
 MIN_RTO, MAX_RTO = 0.05, 2.0
 MAX_FRAME = 16 << 20
@@ -157,6 +162,9 @@ class UdpLink:
         self._segs_since_ack = 0
         self._timer: Optional[asyncio.TimerHandle] = None
         self.retransmits = 0
+        self.mss = MSS                                  # raised by `_probe_mtu`, dropped back by repeated time-outs
+        self._probe_acked = 0
+        self._probe_task: Optional[asyncio.Task] = None
         self.hs: dict = {}
 
     # -- identity ---------------------------------------------------------------------------------------------------
@@ -204,8 +212,8 @@ class UdpLink:
     def _pump(self) -> None:
         now = time.monotonic()
         while self._snd_buf and self._inflight < min(self._cwnd, self._peer_wnd):
-            seg = bytes(self._snd_buf[:MSS])
-            del self._snd_buf[:MSS]
+            seg = bytes(self._snd_buf[:self.mss])
+            del self._snd_buf[:self.mss]
             off = self._snd_nxt
             self._snd_nxt += len(seg)
             self._unacked[off] = [seg, now, 0]
@@ -239,6 +247,8 @@ class UdpLink:
                 if ent[2] >= 12:
                     self._fail("peer unreachable")
                     return
+                if ent[2] >= 2 and self.mss > MSS:
+                    self._shrink_mss()                       # the path may have stopped carrying large datagrams
                 rto = self._rto
                 self._rto = min(MAX_RTO, self._rto * 2)
                 self._recover = self._snd_nxt                # what follows the hole may be lost as well
@@ -290,6 +300,36 @@ class UdpLink:
                 self._retransmit_first(now)
         self._pump()
 
+    def _shrink_mss(self) -> None:
+        """Back to the conservative segment size; what is in flight is re-cut so that retransmissions fit."""
+        self.mss = MSS
+        cut: "collections.OrderedDict[int, list]" = collections.OrderedDict()
+        for off, (data, t_sent, retx) in self._unacked.items():
+            for i in range(0, len(data), MSS):
+                cut[off + i] = [data[i:i + MSS], t_sent, retx]
+        self._unacked = cut
+
+    async def _probe_mtu(self) -> None:
+        try:
+            for size in PROBE_SIZES:
+                ok = False
+                for _ in range(2):
+                    if self.closed:
+                        return
+                    rec = b"P" + struct.pack("<I", size)
+                    rec += b"\0" * max(0, size - 17 - 16 - len(rec))
+                    if not self.ep.sendto(self._seal(rec), self.addr):
+                        break                                # EMSGSIZE: larger than the interface MTU
+                    await asyncio.sleep(0.05 + 2 * (self._srtt or 0.05))
+                    if self._probe_acked >= size:
+                        ok = True
+                        break
+                if not ok:
+                    return
+                self.mss = max(self.mss, size - OVERHEAD)
+        except Exception:               # noqa: BLE001 - discovery is an optimisation
+            return
+
     def _retransmit_first(self, now: float) -> None:
         off, ent = next(iter(self._unacked.items()))
         ent[1], ent[2] = now, ent[2] + 1
@@ -340,6 +380,14 @@ class UdpLink:
                 ack, wnd = struct.unpack_from("<QI", pt, i + 1)
                 i += 13
                 self._on_ack(ack, wnd)
+            elif k == b"P" and i + 5 <= n:                  # MTU probe: the rest of the datagram is padding
+                (size,) = struct.unpack_from("<I", pt, i + 1)
+                self._send_records(b"Q" + struct.pack("<I", size))
+                return
+            elif k == b"Q" and i + 5 <= n:
+                (size,) = struct.unpack_from("<I", pt, i + 1)
+                self._probe_acked = max(self._probe_acked, int(size))
+                i += 5
             elif k == b"C":
                 self._fail("closed by peer", notify=False)
                 return
@@ -426,6 +474,8 @@ class UdpLink:
         if self._timer is not None:
             self._timer.cancel()
             self._timer = None
+        if self._probe_task is not None:
+            self._probe_task.cancel()
         self._space.set()
         if not self.established.done():
             self.established.set_exception(UdpError(why))
@@ -454,6 +504,7 @@ class UdpEndpoint:
         self.drop_every = 1           # ... one out of every `drop_every`
         self._drop_ctr = 0
         self.nat_filter = False       # test hook: behave like an address-restricted NAT (INITs only from punched peers)
+        self.mtu_limit = 0            # test hook: refuse datagrams above this size, like an interface MTU
         self._contacted: set = set()
         self._key = self._chain = None
         if tls:
@@ -481,6 +532,13 @@ class UdpEndpoint:
                 sock.setsockopt(socket.SOL_SOCKET, opt, 4 << 20)
             except OSError:
                 pass
+        try:                                                      # DF: an oversized probe fails instead of fragmenting
+            if fam == socket.AF_INET:
+                sock.setsockopt(socket.IPPROTO_IP, getattr(socket, "IP_MTU_DISCOVER", 10), getattr(socket, "IP_PMTUDISC_DO", 2))
+            else:
+                sock.setsockopt(socket.IPPROTO_IPV6, getattr(socket, "IPV6_MTU_DISCOVER", 23), getattr(socket, "IPV6_PMTUDISC_DO", 2))
+        except OSError:
+            pass
         sock.bind((host, port))
         self.sock = sock
         self.local_addr = sock.getsockname()[:2]
@@ -492,7 +550,7 @@ class UdpEndpoint:
             return
         for _ in range(64):
             try:
-                data, addr = sock.recvfrom(2048)
+                data, addr = sock.recvfrom(65535)
             except (BlockingIOError, InterruptedError):
                 break
             except OSError:
@@ -502,21 +560,25 @@ class UdpEndpoint:
         for link in dirty:
             link.flush_ack()
 
-    def sendto(self, data: bytes, addr) -> None:
+    def sendto(self, data: bytes, addr) -> bool:
+        """False when the datagram could not even be handed to the kernel (EMSGSIZE for an MTU probe, no socket)."""
         if self.sock is None:
-            return
+            return False
         if self.drop_next > 0 and data[:1] == bytes([DATA]):
             self._drop_ctr += 1
             if self._drop_ctr % self.drop_every == 0:
                 self.drop_next -= 1
-                return
+                return True
+        if self.mtu_limit and len(data) > self.mtu_limit:
+            return False                           # test hook: an interface with a smaller MTU
         self._contacted.add(tuple(addr[:2]))
         try:
             self.sock.sendto(data, addr)
         except (BlockingIOError, InterruptedError):
             pass                                   # a full send buffer is a lost datagram: the sender retransmits
         except OSError:
-            pass
+            return False
+        return True
 
     def close(self) -> None:
         for c in list(self.conns.values()):
@@ -704,6 +766,7 @@ class UdpEndpoint:
         self.sendto(link.hs["fin"], addr)
         if not link.established.done():
             link.established.set_result(link)
+            link._probe_task = asyncio.ensure_future(link._probe_mtu())
 
     def _on_fin(self, data: bytes, addr) -> None:
         link = self.conns.get(data[1:9])
@@ -719,6 +782,7 @@ class UdpEndpoint:
         self._pending_init = {k: v for k, v in self._pending_init.items() if v is not link}
         if not link.established.done():
             link.established.set_result(link)
+            link._probe_task = asyncio.ensure_future(link._probe_mtu())
         self.on_accept(link)
 
     def punch(self, host: str, port: int) -> None:

@@ -36,6 +36,9 @@ def test_udp_link_request_and_lossy_stream():
         q = b.streams_push()
         blob = os.urandom(3 << 20)
         ep = a._udp[0]
+        a.links["b"]._shrink_mss()                       # internet-sized segments (loopback would carry 60 KB ones)
+        if a.links["b"]._probe_task is not None:
+            a.links["b"]._probe_task.cancel()
         ep.drop_next, ep.drop_every = 40, 7
         push = asyncio.ensure_future(a.stream_push("b", blob))
         st = await asyncio.wait_for(q.get(), 20)
@@ -364,6 +367,40 @@ def test_addresses_learnt_from_peers_pass_the_cidr_filter():
         assert strict.peer_addrs["liar"] == ["tcp://93.184.216.34:4001"]          # via the gateway's peer table
         assert gw.peer_addrs["liar"] == ["tcp://10.0.0.7:22", "tcp://93.184.216.34:4001"]     # no filter configured
         for n in (liar, strict, gw):
+            await n.close()
+
+    run(main())
+
+
+def test_udp_path_mtu_discovery_and_fallback():
+    """Segments grow to what the path carries (probes with DF set, acknowledged sizes only) and fall back to the
+    conservative size when large datagrams stop getting through."""
+    async def main():
+        a, b = Network("a"), Network("b")
+        addr = await b.listen("udp://127.0.0.1:0")
+        await a.listen("udp://127.0.0.1:0")
+        a._udp[0].mtu_limit = b._udp[0].mtu_limit = 9000          # a jumbo-frame fabric
+        await a.dial(addr)
+        await asyncio.sleep(1.0)
+        la, lb = a.links["b"], b.links["a"]
+        assert la.mss == 8900 - 44 and lb.mss == 8900 - 44          # 8.9 KB probe acknowledged, 16 KB refused
+        q = b.streams_push()
+        blob = os.urandom(4 << 20)
+        push = asyncio.ensure_future(a.stream_push("b", blob))
+        st = await asyncio.wait_for(q.get(), 10)
+        assert await asyncio.wait_for(st.read_all(), 20) == blob
+        await push
+        sent_before = la._pn
+        assert sent_before < 1200                                   # ~500 data packets instead of ~3700 at 1150 bytes
+        # the route changes to a 1500-byte path while a transfer is on its way
+        a._udp[0].mtu_limit = b._udp[0].mtu_limit = 1500
+        blob2 = os.urandom(1 << 20)
+        push = asyncio.ensure_future(a.stream_push("b", blob2))
+        st = await asyncio.wait_for(q.get(), 20)
+        assert await asyncio.wait_for(st.read_all(), 40) == blob2
+        await push
+        assert la.mss == 1150 and la.retransmits > 0
+        for n in (a, b):
             await n.close()
 
     run(main())
