@@ -164,64 +164,10 @@ async def probe(addr: str, timeout: float = 5.0, tls: Optional[dict] = None) -> 
 
 
 # ---------------------------------------------------------------------------------------------
-# gateway
+# gateway and data node: `hypha_b200/gateway`, `hypha_b200/data` (re-exported here)
 # ---------------------------------------------------------------------------------------------
-async def run_gateway(cfg: C.GatewayConfig, *, peer_id: Optional[str] = None,
-                      started: Optional[asyncio.Future] = None) -> None:
-    node = await start_node("gateway", cfg, peer_id=peer_id, relay_server=True, dht_server=True,
-                            need_bootstrap=False)
-    node.ready.set()                        # gateway readiness == listening (hypha-gateway.rs:78,121)
-    node.telemetry.logger.info("gateway %s listening on %s", node.peer_id, node.network.listen_addrs)
-    if started is not None and not started.done():
-        started.set_result(node)
-    try:
-        await node.stop.wait()
-    finally:
-        await node.shutdown()
-
-
-# ---------------------------------------------------------------------------------------------
-# data node
-# ---------------------------------------------------------------------------------------------
-def dataset_files(path: str) -> List[str]:
-    """Slices of a dataset directory in SORTED order (the reference indexes ``read_dir()`` order,
-    which is unspecified: quirk Q5)."""
-    return sorted(os.path.join(path, f) for f in os.listdir(path) if os.path.isfile(os.path.join(path, f)))
-
-
-async def run_data(cfg: C.DataConfig, *, peer_id: Optional[str] = None,
-                   started: Optional[asyncio.Future] = None) -> None:
-    C.validate(cfg)
-    node = await start_node("data", cfg, peer_id=peer_id)
-    name = os.path.basename(os.path.normpath(cfg.dataset_path))
-    files = dataset_files(cfg.dataset_path)
-    if not files:
-        raise RoleError(f"dataset directory {cfg.dataset_path} is empty")
-
-    async def serve(peer: str, header: Any):
-        sl = M.DataSlice.from_wire(header)
-        if sl.dataset != name:
-            raise RoleError(f"unknown dataset {sl.dataset!r}")
-        if not (0 <= sl.index < len(files)):            # correct bounds (reference uses `>`: Q5)
-            raise RoleError(f"slice {sl.index} out of range 0..{len(files) - 1}")
-        return files[sl.index]
-
-    node.network.serve_pull(serve)
-
-    async def announce(*_):
-        await node.network.put_record(name, json.dumps(M.DataRecord(len(files)).to_wire()).encode())
-        await node.network.provide(name)
-
-    await announce()
-    node.on_gateway_reconnect.append(announce)       # a restarted gateway has an empty DHT
-    node.ready.set()
-    node.telemetry.logger.info("data node %s announces %s (%d slices)", node.peer_id, name, len(files))
-    if started is not None and not started.done():
-        started.set_result(node)
-    try:
-        await node.stop.wait()
-    finally:
-        await node.shutdown()
+from .data import dataset_files, run_data  # noqa: E402,F401
+from .gateway import run_gateway  # noqa: E402,F401
 
 
 # ---------------------------------------------------------------------------------------------
