@@ -381,8 +381,11 @@ def test_udp_path_mtu_discovery_and_fallback():
         await a.listen("udp://127.0.0.1:0")
         a._udp[0].mtu_limit = b._udp[0].mtu_limit = 9000          # a jumbo-frame fabric
         await a.dial(addr)
-        await asyncio.sleep(1.0)
         la, lb = a.links["b"], b.links["a"]
+        for _ in range(100):                                        # discovery runs in the background
+            if la.mss == lb.mss == 8900 - 44 and la._probe_task.done() and lb._probe_task.done():
+                break
+            await asyncio.sleep(0.05)
         assert la.mss == 8900 - 44 and lb.mss == 8900 - 44          # 8.9 KB probe acknowledged, 16 KB refused
         q = b.streams_push()
         blob = os.urandom(4 << 20)
