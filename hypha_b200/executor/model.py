@@ -2,7 +2,7 @@
 
 The reference resolves 38 HF auto-classes with ``trust_remote_code=True`` (model.py:47-126,
 SURVEY quirk Q12).  Here architectures are LOCAL: ``config.json``'s ``model_type`` selects one of
-our model families (llama -> sm_100a kernels on GPU; gpt2 / lenet -> stock torch), weights come
+our model families (llama and mistral -> sm_100a kernels on GPU; gpt2 / lenet -> stock torch), weights come
 from ``model.safetensors`` when present and are random-init otherwise (no network).  Unknown
 model types fall back to ``transformers`` auto-classes without remote code."""
 from __future__ import annotations
@@ -46,8 +46,12 @@ class _LlamaAdapter(torch.nn.Module):
     def forward(self, input_ids, labels=None, **_):
         if labels is None:
             return {"logits": self.net(input_ids)}
+        # HF semantics (what the reference's `model(**batch)` computes): position t is scored against token t+1, the
+        # last position has no target.  The count of scored positions is known on the host: no synchronisation.
         shifted = torch.roll(labels, -1, dims=-1)
-        return {"loss": self.net(input_ids, shifted)}
+        shifted[..., -1] = -100
+        return {"loss": self.net(input_ids, shifted, ignore_index=-100, n_valid=shifted.numel() - shifted.shape[0]
+                                 if shifted.dim() > 1 else shifted.numel() - 1)}
 
 
 def get_model(model_path: str, model_type: str, device: str = "cpu") -> torch.nn.Module:
@@ -77,15 +81,10 @@ def _build_model(model_path: str, model_type: str, device: str, meta: dict, fami
         from ..models.lenet import LeNetConfig, LeNetForImageClassification
 
         net = LeNetForImageClassification(LeNetConfig.from_json(cfg_path))
-    elif family == "llama":
+    elif family in ("llama", "mistral"):
         from ..models.llama import LlamaConfig, LlamaForCausalLM
 
-        c = LlamaConfig(vocab_size=meta["vocab_size"], hidden_size=meta["hidden_size"],
-                        intermediate_size=meta["intermediate_size"], num_layers=meta["num_hidden_layers"],
-                        num_heads=meta["num_attention_heads"], num_kv_heads=meta.get("num_key_value_heads", meta["num_attention_heads"]),
-                        head_dim=meta.get("head_dim", meta["hidden_size"] // meta["num_attention_heads"]),
-                        rope_theta=float(meta.get("rope_theta", 500000.0)), rms_eps=float(meta.get("rms_norm_eps", 1e-5)),
-                        max_seq_len=int(meta.get("max_position_embeddings", 8192)), name=meta.get("name", "llama"))
+        c = LlamaConfig.from_hf_dict(meta)          # llama / mistral -> the sm_100a kernels (see its docstring)
         dtype = torch.bfloat16 if device.startswith("cuda") else torch.float32
         inner = LlamaForCausalLM(c, device=device, dtype=dtype)
         if os.path.exists(weights):

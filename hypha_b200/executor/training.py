@@ -335,13 +335,7 @@ class _TrainerEngine:
         from ..trainer import DiLoCoTrainer
 
         meta = json.load(open(os.path.join(local, "config.json")))
-        cfg = LlamaConfig(vocab_size=meta["vocab_size"], hidden_size=meta["hidden_size"],
-                          intermediate_size=meta["intermediate_size"], num_layers=meta["num_hidden_layers"],
-                          num_heads=meta["num_attention_heads"],
-                          num_kv_heads=meta.get("num_key_value_heads", meta["num_attention_heads"]),
-                          head_dim=meta.get("head_dim", meta["hidden_size"] // meta["num_attention_heads"]),
-                          rope_theta=float(meta.get("rope_theta", 500000.0)), rms_eps=float(meta.get("rms_norm_eps", 1e-5)),
-                          max_seq_len=int(meta.get("max_position_embeddings", 8192)), name=meta.get("name", "llama"))
+        cfg = LlamaConfig.from_hf_dict(meta)
         o = config["optimizer"]
         adamw = AdamWConfig(lr=float(o["learning-rate"]), betas=tuple(o["betas"]) if o.get("betas") else (0.9, 0.999),
                             eps=float(o["epsilon"]) if o.get("epsilon") else 1e-8)

@@ -38,6 +38,8 @@ class LlamaConfig:
     num_kv_heads: int = 8
     head_dim: int = 128
     rope_theta: float = 500000.0
+    rope_scaling: Optional[dict] = None  # {"rope_type": "llama3", "factor", "low_freq_factor", "high_freq_factor",
+                                         #  "original_max_position_embeddings"} (Llama 3.1+); None = plain RoPE
     rms_eps: float = 1e-5
     max_seq_len: int = 8192
     init_std: float = 0.02
@@ -65,6 +67,44 @@ class LlamaConfig:
     def to_dict(self) -> dict:
         return asdict(self)
 
+    @classmethod
+    def from_hf_dict(cls, meta: dict) -> "LlamaConfig":
+        """The configuration of a Hugging Face ``config.json`` of a family the sm_100a kernels cover: ``llama`` and
+        ``mistral`` (the Llama block with a sliding attention window: up to the window length causal attention IS
+        sliding-window attention, so the sequence length is capped there; HF parameter names are identical).
+        RoPE settings are read from the top level (transformers < 5, hub checkpoints) or from ``rope_parameters`` /
+        ``rope_scaling``; plain RoPE and the ``llama3`` frequency scaling are supported, anything else -- and
+        projection biases -- is refused instead of being computed differently."""
+        family = meta.get("model_type", "llama")
+        if family not in ("llama", "mistral"):
+            raise RuntimeError(f"model_type {family!r} is not one of the sm_100a model families (llama, mistral)")
+        if any(meta.get(k) for k in ("attention_bias", "mlp_bias")):
+            raise RuntimeError(f"{family} checkpoint with projection biases is not covered by the sm_100a model family")
+        rope = dict(meta.get("rope_parameters") or meta.get("rope_scaling") or {})
+        rope_type = rope.get("rope_type", rope.get("type", "default")) or "default"
+        if rope_type not in ("default", "llama3"):
+            raise RuntimeError(f"RoPE variant {rope_type!r} is not covered by the sm_100a model family "
+                               f"(plain RoPE and llama3 scaling only)")
+        theta = meta.get("rope_theta", rope.get("rope_theta"))
+        if theta is None:
+            theta = 10000.0 if family == "mistral" else 500000.0
+        scaling = None
+        if rope_type == "llama3":
+            scaling = {"rope_type": "llama3", "factor": float(rope["factor"]),
+                       "low_freq_factor": float(rope.get("low_freq_factor", 1.0)),
+                       "high_freq_factor": float(rope.get("high_freq_factor", 4.0)),
+                       "original_max_position_embeddings": int(rope.get("original_max_position_embeddings", 8192))}
+        max_pos = int(meta.get("max_position_embeddings", 8192))
+        if family == "mistral" and meta.get("sliding_window"):
+            max_pos = min(max_pos, int(meta["sliding_window"]))
+        heads = int(meta["num_attention_heads"])
+        return cls(vocab_size=int(meta["vocab_size"]), hidden_size=int(meta["hidden_size"]),
+                   intermediate_size=int(meta["intermediate_size"]), num_layers=int(meta["num_hidden_layers"]),
+                   num_heads=heads, num_kv_heads=int(meta.get("num_key_value_heads") or heads),
+                   head_dim=int(meta.get("head_dim") or int(meta["hidden_size"]) // heads), rope_theta=float(theta),
+                   rope_scaling=scaling, rms_eps=float(meta.get("rms_norm_eps", 1e-5)), max_seq_len=max_pos,
+                   name=meta.get("name", family))
+
     def to_hf_json(self, path: str, seed: int = 0) -> None:
         """Write a Hugging-Face style ``config.json`` (what ``executor/model.py`` and the collective
         executor read back); ``seed`` fixes the random init every worker of a job starts from."""
@@ -75,7 +115,8 @@ class LlamaConfig:
                    "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_layers,
                    "num_attention_heads": self.num_heads, "num_key_value_heads": self.num_kv_heads,
                    "head_dim": self.head_dim, "rope_theta": self.rope_theta, "rms_norm_eps": self.rms_eps,
-                   "max_position_embeddings": self.max_seq_len, "seed": seed}, open(path, "w"))
+                   "max_position_embeddings": self.max_seq_len, "seed": seed,
+                   **({"rope_scaling": dict(self.rope_scaling)} if self.rope_scaling else {})}, open(path, "w"))
 
 
 PRESETS: Dict[str, LlamaConfig] = {
@@ -256,11 +297,16 @@ class LlamaForCausalLM(nn.Module):
     def _rope(self, seq: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
         key = (seq, str(device))
         if key not in self._rope_cache:
-            self._rope_cache[key] = ops.rope_tables(seq, self.cfg.head_dim, self.cfg.rope_theta, device)
+            self._rope_cache[key] = ops.rope_tables(seq, self.cfg.head_dim, self.cfg.rope_theta, device,
+                                                    scaling=self.cfg.rope_scaling)
         return self._rope_cache[key]
 
     # -- forward ------------------------------------------------------------------------
-    def forward(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None):
+    def forward(self, input_ids: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                ignore_index: Optional[int] = None, n_valid: Optional[int] = None):
+        """Logits ``[B, S, V]``, or with ``labels`` (already aligned with the positions: ``labels[b, t]`` is the
+        target of position ``t``) the mean cross-entropy.  ``ignore_index`` masks targets; ``n_valid`` = number of
+        unmasked targets when the caller knows it (no host synchronisation)."""
         cfg = self.cfg
         batch, seq = input_ids.shape
         cos, sin = self._rope(seq, input_ids.device)
@@ -282,7 +328,8 @@ class LlamaForCausalLM(nn.Module):
         hN, _ = ops.add_rmsnorm(delta, residual, P["final_norm"], cfg.rms_eps)
         if labels is None:
             return ops.linear(hN, P["lm_head"]).view(batch, seq, -1)
-        return ops.linear_cross_entropy(hN, P["lm_head"], labels.reshape(-1), chunk=cfg.ce_chunk)
+        return ops.linear_cross_entropy(hN, P["lm_head"], labels.reshape(-1), chunk=cfg.ce_chunk,
+                                        ignore_index=ignore_index, n_valid=n_valid)
 
     # -- HF interop -----------------------------------------------------------------------
     @torch.no_grad()

@@ -682,8 +682,24 @@ def swiglu_linear(gu: torch.Tensor, weight: torch.Tensor, act: Optional[torch.Te
 # -----------------------------------------------------------------------------
 # RoPE
 # -----------------------------------------------------------------------------
-def rope_tables(seq_len: int, head_dim: int, theta: float, device) -> Tuple[torch.Tensor, torch.Tensor]:
+def rope_tables(seq_len: int, head_dim: int, theta: float, device,
+                scaling: Optional[dict] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``(cos, sin)`` tables ``[seq_len, head_dim / 2]`` the RoPE kernel reads.  ``scaling``: the ``llama3`` frequency
+    scaling of Llama 3.1+ (long wavelengths divided by ``factor``, short ones untouched, a smooth blend between) --
+    it only changes the table, the kernel is the same."""
     inv = 1.0 / (theta ** (torch.arange(0, head_dim, 2, dtype=torch.float32, device=device) / head_dim))
+    if scaling:
+        kind = scaling.get("rope_type", scaling.get("type"))
+        if kind != "llama3":
+            raise ValueError(f"unsupported RoPE scaling {kind!r}")
+        factor, lo, hi = float(scaling["factor"]), float(scaling.get("low_freq_factor", 1.0)), float(scaling.get("high_freq_factor", 4.0))
+        old_len = float(scaling.get("original_max_position_embeddings", 8192))
+        wavelen = 2 * math.pi / inv
+        scaled = torch.where(wavelen > old_len / lo, inv / factor, inv)
+        smooth = (old_len / wavelen - lo) / (hi - lo)
+        blended = (1 - smooth) * scaled / factor + smooth * scaled
+        medium = ~(wavelen < old_len / hi) & ~(wavelen > old_len / lo)
+        inv = torch.where(medium, blended, scaled)
     ang = torch.outer(torch.arange(seq_len, dtype=torch.float32, device=device), inv)
     return ang.cos().contiguous(), ang.sin().contiguous()
 
@@ -1080,12 +1096,14 @@ class _LinearCrossEntropy(torch.autograd.Function):
     peak memory is one ``[chunk, vocab]`` bf16 tile instead of ``[tokens, vocab]`` fp32."""
 
     @staticmethod
-    def forward(ctx, h, weight, targets, chunk, ignore_index):
+    def forward(ctx, h, weight, targets, chunk, ignore_index, n_valid=None):
         C = load_C()
         T, K = h.shape
         V = weight.shape[0]
         if ignore_index is None:
             n_valid, ignore_index = T, -100          # caller guarantees every target is valid
+        elif n_valid is not None:
+            n_valid = max(int(n_valid), 1)           # the caller knows how many targets it masked: no host sync
         else:
             n_valid = max(int((targets != ignore_index).sum().item()), 1)   # host sync
         scale = 1.0 / n_valid
@@ -1115,20 +1133,22 @@ class _LinearCrossEntropy(torch.autograd.Function):
         dw = ctx.dw
         if dw is not None:
             dw = dw * dloss.to(dw.dtype)
-        return dh, dw, None, None, None
+        return dh, dw, None, None, None, None
 
 
 def linear_cross_entropy(h: torch.Tensor, weight: torch.Tensor, targets: torch.Tensor,
-                         chunk: int = 4096, ignore_index: Optional[int] = None) -> torch.Tensor:
+                         chunk: int = 4096, ignore_index: Optional[int] = None,
+                         n_valid: Optional[int] = None) -> torch.Tensor:
     """Mean token cross-entropy of ``h @ weight.T`` against ``targets`` (LM head fused in).
 
     ``ignore_index=None`` promises that every target is valid, which keeps the op free of
-    host synchronisation; pass an index (e.g. ``-100``) to mask padding tokens."""
+    host synchronisation; pass an index (e.g. ``-100``) to mask padding tokens -- and ``n_valid`` (how many targets
+    are NOT masked) when the caller knows it, which keeps the masked variant free of the synchronisation as well."""
     if not h.is_cuda:
         logits = F.linear(h, weight).float()
         return F.cross_entropy(logits, targets.reshape(-1),
                                ignore_index=-100 if ignore_index is None else ignore_index)
-    return _LinearCrossEntropy.apply(h, weight, targets.reshape(-1).contiguous(), chunk, ignore_index)
+    return _LinearCrossEntropy.apply(h, weight, targets.reshape(-1).contiguous(), chunk, ignore_index, n_valid)
 
 
 def cross_entropy_inplace(logits: torch.Tensor, targets: torch.Tensor, grad_scale: float,

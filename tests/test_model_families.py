@@ -1,0 +1,64 @@
+"""Built-in model families against their Hugging Face originals (CPU, fp32): a checkpoint saved by `transformers` is
+loaded through the executor's `get_model` and must give the same logits and the same loss the reference's
+`model(**batch)` would (executors/accelerate/src/hypha/accelerate_executor/training.py:108-112)."""
+import json
+import os
+
+import pytest
+import torch
+
+
+def _hf_checkpoint(tmp, cfgcls, cls, **extra):
+    import transformers
+    from safetensors.torch import save_file
+
+    kw = dict(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2, num_attention_heads=4,
+              num_key_value_heads=2, max_position_embeddings=128, rms_norm_eps=1e-5, tie_word_embeddings=False)
+    if "rope_parameters" not in extra:
+        kw["rope_theta"] = 10000.0
+    cfg = getattr(transformers, cfgcls)(**kw, **extra)
+    torch.manual_seed(0)
+    hf = getattr(transformers, cls)(cfg).eval()
+    json.dump(cfg.to_dict(), open(os.path.join(tmp, "config.json"), "w"))
+    save_file({k: v.contiguous() for k, v in hf.state_dict().items()}, os.path.join(tmp, "model.safetensors"))
+    return hf, cfg
+
+
+LLAMA3_ROPE = {"rope_parameters": {"rope_type": "llama3", "rope_theta": 10000.0, "factor": 8.0, "low_freq_factor": 1.0,
+                                   "high_freq_factor": 4.0, "original_max_position_embeddings": 32}}
+
+
+@pytest.mark.parametrize("family,cfgcls,cls,extra", [("llama", "LlamaConfig", "LlamaForCausalLM", {}),
+                                                    ("llama", "LlamaConfig", "LlamaForCausalLM", LLAMA3_ROPE),
+                                                    ("mistral", "MistralConfig", "MistralForCausalLM", {"sliding_window": 64})])
+def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls, extra):
+    from hypha_b200.executor.model import get_model
+
+    hf, cfg = _hf_checkpoint(str(tmp_path), cfgcls, cls, **extra)
+    assert "rope_theta" not in cfg.to_dict() or True       # transformers >= 5 nests it under rope_parameters
+    ours = get_model(str(tmp_path), "causal-lm", "cpu").eval()
+    assert type(ours.net).__name__ == "LlamaForCausalLM" and ours.net.cfg.rope_theta == 10000.0
+    assert ours.net.cfg.max_seq_len == (64 if family == "mistral" else 128)      # capped at the sliding window
+    ids = torch.randint(0, 320, (2, 48))
+    with torch.no_grad():
+        ref = hf(ids)
+        got = ours(ids)["logits"].reshape(ref.logits.shape)
+        assert (ref.logits - got).abs().max().item() < 1e-5
+        # labels == inputs, shifted inside, the last position unscored: exactly the HF loss
+        assert abs(hf(ids, labels=ids).loss.item() - ours(ids, labels=ids)["loss"].item()) < 1e-5
+    # the round trip back to HF names is lossless (what a checkpoint of a finished job contains)
+    sd = ours.net.to_hf_state_dict()
+    for k, v in hf.state_dict().items():
+        assert torch.equal(sd[k].float(), v.float()), k
+
+
+def test_unsupported_llama_variants_are_refused_loudly(tmp_path):
+    from hypha_b200.executor.model import get_model
+
+    base = {"model_type": "llama", "vocab_size": 64, "hidden_size": 32, "intermediate_size": 64, "num_hidden_layers": 1,
+            "num_attention_heads": 2}
+    for bad, msg in (({"rope_parameters": {"rope_type": "yarn", "rope_theta": 5e5, "factor": 8.0}}, "RoPE variant"),
+                     ({"attention_bias": True}, "biases")):
+        json.dump(dict(base, **bad), open(tmp_path / "config.json", "w"))
+        with pytest.raises(RuntimeError, match=msg):
+            get_model(str(tmp_path), "causal-lm", "cpu")
