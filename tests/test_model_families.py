@@ -62,3 +62,28 @@ def test_unsupported_llama_variants_are_refused_loudly(tmp_path):
         json.dump(dict(base, **bad), open(tmp_path / "config.json", "w"))
         with pytest.raises(RuntimeError, match=msg):
             get_model(str(tmp_path), "causal-lm", "cpu")
+
+
+def test_gpt2_checkpoint_matches_transformers(tmp_path):
+    """The plumbing config's model (BASELINE config 1: GPT-2 small): same parameter names, logits and loss as
+    `transformers.GPT2LMHeadModel` (tied LM head)."""
+    import transformers
+    from safetensors.torch import save_file
+
+    from hypha_b200.executor.model import get_model
+
+    cfg = transformers.GPT2Config(vocab_size=320, n_positions=64, n_embd=64, n_layer=2, n_head=4)
+    torch.manual_seed(0)
+    hf = transformers.GPT2LMHeadModel(cfg).eval()
+    json.dump(cfg.to_dict(), open(tmp_path / "config.json", "w"))
+    save_file({k: v.contiguous() for k, v in hf.state_dict().items() if k != "lm_head.weight"},
+              str(tmp_path / "model.safetensors"))
+    ours = get_model(str(tmp_path), "causal-lm", "cpu").eval()
+    ids = torch.randint(0, 320, (2, 32))
+    with torch.no_grad():
+        ref = hf(ids, labels=ids)
+        got = ours(input_ids=ids, labels=ids)
+    logits = got["logits"] if isinstance(got, dict) else got.logits
+    loss = got["loss"] if isinstance(got, dict) else got.loss
+    assert (ref.logits - logits).abs().max().item() < 1e-5 and abs(ref.loss.item() - loss.item()) < 1e-5
+    assert set(ours.state_dict()) <= set(hf.state_dict())
