@@ -36,6 +36,19 @@ AUTO_CLASS = {
 }
 
 
+def hf_shift_labels(labels: torch.Tensor) -> tuple:
+    """Hugging Face causal-LM convention -> per-position targets.  A dataset hands ``labels`` that are ALIGNED with
+    ``input_ids`` (usually a copy of them); the model scores position ``t`` against ``labels[t + 1]`` and the last
+    position of every sequence against nothing.  Returns ``(targets, n_valid)``: the shifted targets with ``-100`` in
+    the last position (and wherever the dataset masked with ``-100``) and the number of scored positions (counted
+    here for host tensors -- what a data loader hands out; ``None`` for device tensors, the loss then counts itself)."""
+    shifted = torch.roll(labels, -1, dims=-1)
+    shifted[..., -1] = -100
+    if shifted.is_cuda:
+        return shifted, None                         # counted on the device by the loss (one host synchronisation)
+    return shifted, int((shifted != -100).sum())     # host tensor (what the data loader hands out): counting is free
+
+
 class _LlamaAdapter(torch.nn.Module):
     """Gives ``LlamaForCausalLM`` the HF calling convention (``labels`` == inputs, shift inside)."""
 
@@ -48,10 +61,8 @@ class _LlamaAdapter(torch.nn.Module):
             return {"logits": self.net(input_ids)}
         # HF semantics (what the reference's `model(**batch)` computes): position t is scored against token t+1, the
         # last position has no target.  The count of scored positions is known on the host: no synchronisation.
-        shifted = torch.roll(labels, -1, dims=-1)
-        shifted[..., -1] = -100
-        return {"loss": self.net(input_ids, shifted, ignore_index=-100, n_valid=shifted.numel() - shifted.shape[0]
-                                 if shifted.dim() > 1 else shifted.numel() - 1)}
+        shifted, n_valid = hf_shift_labels(labels)
+        return {"loss": self.net(input_ids, shifted, ignore_index=-100, n_valid=n_valid)}
 
 
 def get_model(model_path: str, model_type: str, device: str = "cpu") -> torch.nn.Module:

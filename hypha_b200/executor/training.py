@@ -362,8 +362,13 @@ class _TrainerEngine:
         self.backend = self.trainer.outer.backend
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        # the dataset follows the Hugging Face convention (labels aligned with input_ids, the shift happens in the
+        # model): same targets as the CPU path's `_LlamaAdapter` and as the reference's `model(**batch)`
+        from .model import hf_shift_labels
+
         ids = batch["input_ids"]
-        return self.trainer.inner_step(ids, batch.get("labels", torch.roll(ids, -1, dims=-1)))
+        targets, n_valid = hf_shift_labels(batch.get("labels", ids))
+        return self.trainer.inner_step(ids, targets, ignore_index=-100, n_valid=n_valid)
 
     def regroup(self, membership: dict, coll: dict, **_) -> None:
         """The scheduler dropped ranks: shrink the fused kernel's membership and adopt orphaned shards now

@@ -129,7 +129,10 @@ class DiLoCoTrainer:
             self.opt.step_range(begin, end)
         self._opt_done.append((begin, end))
 
-    def inner_step(self, input_ids: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def inner_step(self, input_ids: torch.Tensor, labels: torch.Tensor, ignore_index: Optional[int] = None,
+                   n_valid: Optional[int] = None) -> torch.Tensor:
+        """``labels[b, t]`` is the target of position ``t`` (already shifted); ``ignore_index`` / ``n_valid``: masked
+        targets and the number of unmasked ones (see `LlamaForCausalLM.forward`)."""
         # NVTX ranges (hypha.h2d / fwd / bwd / opt / outer) mark the phases of a step in ncu / nsys timelines
         with nvtx_range("hypha.h2d"):
             ids = self._to_device(input_ids)
@@ -137,7 +140,7 @@ class DiLoCoTrainer:
         self.model.set_grad_accumulate(False)
         if not self.overlap_optimizer:
             with nvtx_range("hypha.fwd"):
-                loss = self.model(ids, lab)
+                loss = self.model(ids, lab, ignore_index=ignore_index, n_valid=n_valid)
             with nvtx_range("hypha.bwd"):
                 loss.backward()
             with nvtx_range("hypha.opt"):
@@ -146,7 +149,7 @@ class DiLoCoTrainer:
             self.opt.begin_step()
             self._opt_done.clear()
             with nvtx_range("hypha.fwd"):
-                loss = self.model(ids, lab)
+                loss = self.model(ids, lab, ignore_index=ignore_index, n_valid=n_valid)
             with nvtx_range("hypha.bwd+opt"):          # each layer's AdamW slice runs under the remaining backward
                 loss.backward()
             # whatever backward did not cover (the embedding table, or everything if no hook fired)

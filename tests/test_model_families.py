@@ -87,3 +87,16 @@ def test_gpt2_checkpoint_matches_transformers(tmp_path):
     loss = got["loss"] if isinstance(got, dict) else got.loss
     assert (ref.logits - logits).abs().max().item() < 1e-5 and abs(ref.loss.item() - loss.item()) < 1e-5
     assert set(ours.state_dict()) <= set(hf.state_dict())
+
+
+def test_hf_label_shift():
+    """Labels aligned with the inputs (the dataset convention) become per-position targets: position t <- token t+1,
+    the last position unscored, dataset masks (-100) preserved; the input tensor is not modified."""
+    from hypha_b200.executor.model import hf_shift_labels
+
+    ids = torch.tensor([[5, 6, 7, 8], [1, 2, -100, 4]])
+    keep = ids.clone()
+    tgt, n = hf_shift_labels(ids)
+    assert tgt.tolist() == [[6, 7, 8, -100], [2, -100, 4, -100]] and n == 5 and torch.equal(ids, keep)
+    ref = torch.nn.functional.cross_entropy(torch.zeros(8, 10), tgt.reshape(-1), ignore_index=-100)
+    assert abs(ref.item() - torch.log(torch.tensor(10.0)).item()) < 1e-6
