@@ -100,3 +100,37 @@ def test_hf_label_shift():
     assert tgt.tolist() == [[6, 7, 8, -100], [2, -100, 4, -100]] and n == 5 and torch.equal(ids, keep)
     ref = torch.nn.functional.cross_entropy(torch.zeros(8, 10), tgt.reshape(-1), ignore_index=-100)
     assert abs(ref.item() - torch.log(torch.tensor(10.0)).item()) < 1e-6
+
+
+def test_lr_schedules_match_transformers():
+    """`make_lr_lambda` (folded into the fused AdamW's launch arguments) against the Hugging Face schedulers the
+    reference builds (executors/accelerate/.../utils.py:90-102), step for step over the schedule's length."""
+    import transformers
+
+    from hypha_b200.parallel.diloco import make_lr_lambda
+
+    p = torch.nn.Parameter(torch.zeros(1))
+
+    def hf_curve(make, n):
+        opt = torch.optim.SGD([p], lr=1.0)
+        sch = make(opt)
+        out = []
+        for _ in range(n):
+            out.append(opt.param_groups[0]["lr"])
+            opt.step()
+            sch.step()
+        return out
+
+    cases = [({"type": "cosine-with-warmup", "warmup_steps": 5, "training_steps": 50}, 51,
+              lambda o: transformers.get_cosine_schedule_with_warmup(o, 5, 50)),
+             ({"type": "linear-with-warmup", "warmup_steps": 5, "training_steps": 50}, 60,
+              lambda o: transformers.get_linear_schedule_with_warmup(o, 5, 50)),
+             ({"type": "wsd", "warmup_steps": 5, "decay_steps": 10, "training_steps": 40}, 45,
+              lambda o: transformers.get_wsd_schedule(o, 5, 10, num_training_steps=40)),
+             ({}, 10, lambda o: transformers.get_constant_schedule(o))]
+    for cfg, n, make in cases:
+        f = make_lr_lambda(cfg)
+        assert max(abs(f(s) - r) for s, r in enumerate(hf_curve(make, n))) < 1e-12, cfg
+    # past the end the cosine stays at zero (the Hugging Face lambda would climb again)
+    f = make_lr_lambda({"type": "cosine-with-warmup", "warmup_steps": 5, "training_steps": 50})
+    assert f(55) == 0.0 and f(500) == 0.0
