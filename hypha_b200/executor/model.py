@@ -56,11 +56,16 @@ class _LlamaAdapter(torch.nn.Module):
         super().__init__()
         self.net = net
 
-    def forward(self, input_ids, labels=None, **_):
+    def forward(self, input_ids, labels=None, targets=None, n_valid=None, **_):
+        """``labels``: Hugging Face convention (aligned with the inputs, shifted here).  ``targets`` / ``n_valid``: the
+        already shifted targets and their count, prepared on the host by the caller (`InnerLoop.step`) so that the
+        masked loss needs no device-side count."""
+        if targets is not None:
+            return {"loss": self.net(input_ids, targets, ignore_index=-100, n_valid=n_valid)}
         if labels is None:
             return {"logits": self.net(input_ids)}
         # HF semantics (what the reference's `model(**batch)` computes): position t is scored against token t+1, the
-        # last position has no target.  The count of scored positions is known on the host: no synchronisation.
+        # last position has no target.
         shifted, n_valid = hf_shift_labels(labels)
         return {"loss": self.net(input_ids, shifted, ignore_index=-100, n_valid=n_valid)}
 

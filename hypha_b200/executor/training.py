@@ -66,10 +66,17 @@ class InnerLoop:
             self.prev = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        extra = {}
+        if self.flat and batch.get("labels") is not None and not batch["labels"].is_cuda:
+            # shift the labels while they are still on the host: the count of scored positions comes for free there
+            from .model import hf_shift_labels
+
+            targets, extra["n_valid"] = hf_shift_labels(batch["labels"])
+            batch = dict({k: v for k, v in batch.items() if k != "labels"}, targets=targets)
         batch = {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
         if not self.flat:
             self.opt.zero_grad(set_to_none=True)
-        out = self.model(**batch)
+        out = self.model(**batch, **extra)
         loss = out if isinstance(out, torch.Tensor) else out["loss"]
         loss.backward()
         self.opt.step()

@@ -102,6 +102,25 @@ def test_hf_label_shift():
     assert abs(ref.item() - torch.log(torch.tensor(10.0)).item()) < 1e-6
 
 
+def test_adapter_accepts_host_shifted_targets():
+    """`InnerLoop.step` shifts the labels on the host (where counting the scored positions is free) and hands the
+    adapter ``targets`` + ``n_valid``; that path gives the same loss as handing it Hugging Face style ``labels``."""
+    from hypha_b200.executor.model import _LlamaAdapter, hf_shift_labels
+    from hypha_b200.models.llama import LlamaConfig, LlamaForCausalLM
+
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=64, hidden_size=32, intermediate_size=64, num_layers=1, num_heads=2, num_kv_heads=2,
+                      max_seq_len=16)
+    net = _LlamaAdapter(LlamaForCausalLM(cfg, device="cpu", dtype=torch.float32))
+    ids = torch.randint(0, 64, (2, 16))
+    labels = ids.clone()
+    labels[1, 5:9] = -100
+    tgt, n = hf_shift_labels(labels)
+    a = net(input_ids=ids, labels=labels)["loss"]
+    b = net(input_ids=ids, targets=tgt, n_valid=n)["loss"]
+    assert torch.isfinite(a) and abs(a.item() - b.item()) < 1e-6
+
+
 def test_lr_schedules_match_transformers():
     """`make_lr_lambda` (folded into the fused AdamW's launch arguments) against the Hugging Face schedulers the
     reference builds (executors/accelerate/.../utils.py:90-102), step for step over the schedule's length."""
