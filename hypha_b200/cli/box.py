@@ -43,6 +43,10 @@ def build_parser() -> argparse.ArgumentParser:
     r.add_argument("--aggregation", choices=["collective", "parameter-server"], default="collective")
     r.add_argument("--precision", choices=["bf16", "mxfp8", "fp8"], default="bf16",
                    help="GEMM precision of the inner steps on GPU executors ([scheduler.job.precision] gemm)")
+    r.add_argument("--micro-batches", type=int, default=1,
+                   help="gradient accumulation: micro-batches per inner step ([scheduler.job.precision] micro_batches)")
+    r.add_argument("--main-grad", choices=["fp32", "bf16"], default="fp32",
+                   help="where micro-batch gradients are summed ([scheduler.job.precision] main_grad)")
     r.add_argument("--job", default=None, help="extra [scheduler.job] keys as JSON (merged last)")
     r.add_argument("--work-dir", default=None, help="scratch directory (default: a temporary one, removed at exit)")
     r.add_argument("--timeout", type=float, default=3600.0)
@@ -94,7 +98,7 @@ def run(args) -> int:
         "inner_optimizer": {"learning-rate": args.lr},
         "outer_optimizer": {"learning-rate": args.outer_lr, "momentum": args.outer_momentum},
         "aggregation": {"mode": args.aggregation},
-        "precision": {"gemm": args.precision},
+        "precision": {"gemm": args.precision, "micro_batches": args.micro_batches, "main_grad": args.main_grad},
         "resources": {"num_workers": workers, "worker": {"gpu": 1.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},

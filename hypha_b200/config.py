@@ -254,6 +254,12 @@ class PrecisionSection:
     gemm: str = doc("precision of the Linear-layer GEMMs of the inner steps on GPU executors: `bf16` (default), "
                     "`mxfp8` (e4m3 with one UE8M0 scale per 32 elements, block-scaled tensor-core MMA) or `fp8` "
                     "(per-tensor scaling); master weights, optimizer and the outer step are unaffected", "bf16")
+    micro_batches: int = doc("gradient accumulation: every batch of an inner step is split into this many "
+                             "micro-batches whose mean gradient feeds ONE optimizer step (1 = off, the reference's "
+                             "behaviour); the worker's batch size must be a multiple of it", 1)
+    main_grad: str = doc("where the micro-batch gradients are summed when `micro_batches` > 1: `fp32` (an fp32 "
+                         "buffer, rounded to bf16 once; +4 bytes per parameter) or `bf16` (in the bf16 gradient "
+                         "buffer by the wgrad GEMM epilogues; no extra memory, one rounding per micro-batch)", "fp32")
 
 
 @dataclass
@@ -589,6 +595,11 @@ def validate(cfg: Any) -> Any:
         if job.precision.gemm not in ("bf16", "mxfp8", "fp8"):
             raise _err(meta, "scheduler.job.precision.gemm",
                        f"unknown GEMM precision `{job.precision.gemm}` (bf16 | mxfp8 | fp8)")
+        if not isinstance(job.precision.micro_batches, int) or job.precision.micro_batches < 1:
+            raise _err(meta, "scheduler.job.precision.micro_batches", "must be a positive integer")
+        if job.precision.main_grad not in ("fp32", "bf16"):
+            raise _err(meta, "scheduler.job.precision.main_grad",
+                       f"unknown main-gradient type `{job.precision.main_grad}` (fp32 | bf16)")
         if job.aggregation.weighting not in ("uniform", "samples"):
             raise _err(meta, "scheduler.job.aggregation.weighting",
                        f"unknown weighting `{job.aggregation.weighting}` (uniform | samples)")

@@ -20,7 +20,7 @@ import argparse
 import json
 import os
 import time
-from typing import Any, Dict, Iterator, List, Optional
+from typing import Any, Dict, Iterator, List, Optional, Tuple
 
 import torch
 
@@ -43,13 +43,39 @@ def fetch_data(session: Session, data: Any, work_dir: str) -> Iterator[str]:
         yield os.path.join(work_dir, got[0]["path"])
 
 
+def accumulation_of(config: dict) -> Tuple[int, str]:
+    """(micro-batches per inner step, main-gradient type) of a train executor's job config
+    (`[scheduler.job.precision] micro_batches / main_grad`; absent: one micro-batch, the reference's behaviour)."""
+    a = config.get("accumulation") or {}
+    k, main_grad = int(a.get("micro_batches", 1)), str(a.get("main_grad", "fp32"))
+    if k < 1 or main_grad not in ("fp32", "bf16"):
+        raise ValueError(f"bad accumulation spec {a!r}")
+    return k, main_grad
+
+
+def split_batch(batch: Dict[str, torch.Tensor], k: int) -> List[Dict[str, torch.Tensor]]:
+    """``k`` equal micro-batches along the sample dimension.  A batch whose size is not a multiple of ``k`` (the
+    tail of a data slice) is cut into the largest number of EQUAL parts <= k instead, so that the mean over
+    micro-batches stays the mean over samples."""
+    n = int(next(iter(batch.values())).shape[0])
+    k = max(1, min(k, n))
+    while n % k:
+        k -= 1
+    if k == 1:
+        return [batch]
+    return [{key: v[i * (n // k):(i + 1) * (n // k)] for key, v in batch.items()} for i in range(k)]
+
+
 class InnerLoop:
     """Model + inner optimizer + the bookkeeping DiLoCo needs (snapshot / delta / merge)."""
 
-    def __init__(self, model: torch.nn.Module, opt_cfg: dict, sched_cfg: Optional[dict], device: str):
+    def __init__(self, model: torch.nn.Module, opt_cfg: dict, sched_cfg: Optional[dict], device: str,
+                 accumulation: Tuple[int, str] = (1, "fp32")):
         from ..parallel.diloco import AdamWConfig, FlatAdamW, make_lr_lambda
 
         self.model, self.device = model, device
+        self.micro_batches, self.main_grad_type = accumulation
+        self._main_grad = None
         self.flat = isinstance(model, _LlamaAdapter) and device.startswith("cuda")
         lr = float(opt_cfg["learning-rate"])
         betas = tuple(opt_cfg["betas"]) if opt_cfg.get("betas") else (0.9, 0.999)
@@ -65,7 +91,7 @@ class InnerLoop:
             self.sched = torch.optim.lr_scheduler.LambdaLR(self.opt, lam)
             self.prev = {k: v.detach().clone() for k, v in model.state_dict().items()}
 
-    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+    def _loss(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         extra = {}
         if self.flat and batch.get("labels") is not None and not batch["labels"].is_cuda:
             # shift the labels while they are still on the host: the count of scored positions comes for free there
@@ -74,15 +100,59 @@ class InnerLoop:
             targets, extra["n_valid"] = hf_shift_labels(batch["labels"])
             batch = dict({k: v for k, v in batch.items() if k != "labels"}, targets=targets)
         batch = {k: v.to(self.device, non_blocking=True) for k, v in batch.items()}
+        out = self.model(**batch, **extra)
+        return out if isinstance(out, torch.Tensor) else out["loss"]
+
+    def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        micro = split_batch(batch, self.micro_batches) if self.micro_batches > 1 else [batch]
+        if len(micro) > 1:
+            return self._step_accumulated(micro)
         if not self.flat:
             self.opt.zero_grad(set_to_none=True)
-        out = self.model(**batch, **extra)
-        loss = out if isinstance(out, torch.Tensor) else out["loss"]
+        loss = self._loss(batch)
         loss.backward()
         self.opt.step()
         if not self.flat:
             self.sched.step()
         return loss.detach()
+
+    def _step_accumulated(self, micro: List[Dict[str, torch.Tensor]]) -> torch.Tensor:
+        """One optimizer step on the mean gradient of the micro-batches (`[scheduler.job.precision]
+        micro_batches`).  torch models: autograd sums ``loss / k`` into the fp32 ``.grad``.  Flat sm_100a model:
+        the bf16 gradient buffer is summed in fp32 (`parallel.main_grad.MainGrad`) or, with ``main_grad =
+        "bf16"``, by the accumulate mode of the wgrad GEMM epilogues with 1/k folded into the AdamW launch."""
+        k = len(micro)
+        total = None
+        if not self.flat:
+            self.opt.zero_grad(set_to_none=True)
+            for mb in micro:
+                loss = self._loss(mb)
+                (loss / k).backward()
+                total = loss.detach() if total is None else total + loss.detach()
+            self.opt.step()
+            self.sched.step()
+            return total / k
+        net, fp32 = self.model.net, self.main_grad_type == "fp32"
+        if fp32 and self._main_grad is None:
+            from ..parallel.main_grad import MainGrad
+
+            self._main_grad = MainGrad(net.flat.grad)
+        try:
+            for i, mb in enumerate(micro):
+                net.set_grad_accumulate(not fp32 and i > 0)
+                loss = self._loss(mb)
+                loss.backward()
+                if fp32:
+                    self._main_grad.add()
+                total = loss.detach() if total is None else total + loss.detach()
+        finally:
+            net.set_grad_accumulate(False)
+        if fp32:
+            self._main_grad.finalize()
+            self.opt.step()
+        else:
+            self.opt.step(grad_scale=1.0 / k)
+        return total / k
 
     def delta_state_dict(self) -> Dict[str, torch.Tensor]:
         """theta - theta_prev per tensor, fp32 on CPU (utils.py:118-123)."""
@@ -367,14 +437,21 @@ class _TrainerEngine:
             self.trainer.model.load_hf_state_dict(load_file(weights))
             self.trainer.opt.master.copy_(self.trainer.model.flat.data)
         self.backend = self.trainer.outer.backend
+        self.micro_batches, self.main_grad_type = accumulation_of(config)
 
     def step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         # the dataset follows the Hugging Face convention (labels aligned with input_ids, the shift happens in the
         # model): same targets as the CPU path's `_LlamaAdapter` and as the reference's `model(**batch)`
         from .model import hf_shift_labels
 
+        batch = {"input_ids": batch["input_ids"], "labels": batch.get("labels", batch["input_ids"])}
+        micro = split_batch(batch, self.micro_batches) if self.micro_batches > 1 else [batch]
+        if len(micro) > 1:
+            return self.trainer.inner_step_accumulated(
+                [(mb["input_ids"],) + hf_shift_labels(mb["labels"]) for mb in micro],
+                main_grad=self.main_grad_type, ignore_index=-100)
         ids = batch["input_ids"]
-        targets, n_valid = hf_shift_labels(batch.get("labels", ids))
+        targets, n_valid = hf_shift_labels(batch["labels"])
         return self.trainer.inner_step(ids, targets, ignore_index=-100, n_valid=n_valid)
 
     def regroup(self, membership: dict, coll: dict, **_) -> None:
@@ -503,7 +580,7 @@ class _TrainerEngine:
 class _GenericEngine:
     def __init__(self, local: str, config: dict, coll: dict, device: str, group: _Group):
         model = get_model(local, config["model"]["task"], device)
-        self.loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device)
+        self.loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device, accumulation_of(config))
         outer = coll.get("outer") or {}
         self.outer = ReplicatedNesterov(float(outer.get("learning-rate", 0.7)), float(outer.get("momentum", 0.9)))
         self.group = group
@@ -788,7 +865,7 @@ def main(socket_path: str, work_dir: str, job_json: str) -> None:
         prepare_files(config, session)
         local = os.path.join(work_dir, FETCH_PATH)
         model = get_model(local, config["model"]["task"], device)
-        loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device)
+        loop = InnerLoop(model, config["optimizer"], config.get("scheduler"), device, accumulation_of(config))
         pre_cfg = config.get("preprocessor")
         loader = torch.utils.data.DataLoader(
             IterableStreamDataSet(fetch_data(session, config["data"], work_dir), config["model"]["input-names"],

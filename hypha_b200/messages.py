@@ -366,6 +366,16 @@ class TrainExecutorConfig:
     weighting: Optional[str] = None
     # B200 extension: GEMM precision of the inner steps on GPU executors ("mxfp8" | "fp8"; absent / "bf16": bf16)
     precision: Optional[str] = None
+    # B200 extension: gradient accumulation inside an inner step, {"micro_batches": k, "main_grad": "fp32" | "bf16"}
+    # (absent: one micro-batch per step, as the reference)
+    accumulation: Optional[dict] = None
+
+    def __post_init__(self):
+        if self.accumulation is not None:
+            k, mg = self.accumulation.get("micro_batches", 1), self.accumulation.get("main_grad", "fp32")
+            if not isinstance(k, int) or isinstance(k, bool) or k < 1 or mg not in ("fp32", "bf16"):
+                raise MessageError(f"bad accumulation spec {self.accumulation!r}")
+            self.accumulation = {"micro_batches": k, "main_grad": mg} if k > 1 else None
 
     def to_wire(self) -> dict:
         d = {"model": self.model.to_wire(), "data": self.data.to_wire(), "updates": self.updates.to_wire(),
@@ -383,6 +393,8 @@ class TrainExecutorConfig:
             d["weighting"] = self.weighting
         if self.precision and self.precision != "bf16":
             d["precision"] = self.precision
+        if self.accumulation is not None:
+            d["accumulation"] = dict(self.accumulation)
         return d
 
     @classmethod
@@ -394,7 +406,8 @@ class TrainExecutorConfig:
                    dict(d["collective"]) if d.get("collective") else None,
                    dict(d["join"]) if d.get("join") else None,
                    str(d["weighting"]) if d.get("weighting") else None,
-                   str(d["precision"]) if d.get("precision") else None)
+                   str(d["precision"]) if d.get("precision") else None,
+                   dict(d["accumulation"]) if d.get("accumulation") else None)
 
 
 @dataclass

@@ -145,7 +145,9 @@ class DiLoCoJobRun:
                                      results=M.Receive.from_peers([self.ps.peer_id]),
                                      optimizer=self.adam, batch_size=bs, preprocessor=self.pre,
                                      weighting=self.job.aggregation.weighting,
-                                     precision=self.job.precision.gemm)
+                                     precision=self.job.precision.gemm,
+                                     accumulation={"micro_batches": self.job.precision.micro_batches,
+                                                   "main_grad": self.job.precision.main_grad})
 
     async def _dispatch_train(self, w: WorkerHandle, tcfg: M.TrainExecutorConfig) -> None:
         spec = M.JobSpec(self.job_id, M.Executor.train(M.TRAIN_EXECUTOR_NAME, tcfg))

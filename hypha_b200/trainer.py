@@ -50,6 +50,7 @@ class DiLoCoTrainer:
         if self.overlap_optimizer:
             model.grad_ready_hook = self._on_grad_ready
         self.last_loss: Optional[torch.Tensor] = None
+        self._main_grad = None              # fp32 gradient sum, created by the first inner_step_accumulated("fp32")
         self.h2d_bytes = 0
         self.time_outer = os.environ.get("HYPHA_TIME_OUTER", "0") == "1"
         self.last_outer_ms: Optional[float] = None
@@ -167,6 +168,56 @@ class DiLoCoTrainer:
             torch.cuda.current_stream().wait_stream(self._opt_stream)
             self.opt.finish_step()
         self.last_loss = loss.detach()
+        return self.last_loss
+
+    def inner_step_accumulated(self, micro_batches, main_grad: str = "fp32", ignore_index: Optional[int] = None
+                               ) -> torch.Tensor:
+        """One inner step whose gradient is the mean over several micro-batches (``[(input_ids, labels), ...]`` or
+        ``[(input_ids, labels, n_valid), ...]``, labels already shifted as in `inner_step`).  ``main_grad``:
+
+        * ``"fp32"`` -- each micro-batch writes its bf16 gradients in overwrite mode and they are summed in an fp32
+          buffer (`parallel.main_grad.MainGrad`), rounded to bf16 once before the fused AdamW;
+        * ``"bf16"`` -- the wgrad GEMM epilogues add into the bf16 gradient buffer (no extra memory or traffic, one
+          rounding per micro-batch), the 1/k goes into the AdamW launch as ``grad_scale``.
+
+        The optimizer cannot start before the last micro-batch, so this path does not use the optimizer-in-backward
+        overlap.  Returns the mean loss (on the device)."""
+        if main_grad not in ("fp32", "bf16"):
+            raise ValueError(f"main_grad must be 'fp32' or 'bf16', not {main_grad!r}")
+        micro_batches = list(micro_batches)
+        if not micro_batches:
+            raise ValueError("inner_step_accumulated needs at least one micro-batch")
+        k = len(micro_batches)
+        if main_grad == "fp32" and self._main_grad is None:
+            from .parallel.main_grad import MainGrad
+
+            self._main_grad = MainGrad(self.model.flat.grad)
+        hook, self.model.grad_ready_hook = self.model.grad_ready_hook, None
+        total = None
+        try:
+            for i, mb in enumerate(micro_batches):
+                input_ids, labels = mb[0], mb[1]
+                n_valid = mb[2] if len(mb) > 2 else None       # known count of unmasked targets: no host sync
+                with nvtx_range("hypha.h2d"):
+                    ids, lab = self._to_device(input_ids), self._to_device(labels)
+                self.model.set_grad_accumulate(main_grad == "bf16" and i > 0)
+                with nvtx_range("hypha.fwd"):
+                    loss = self.model(ids, lab, ignore_index=ignore_index, n_valid=n_valid)
+                with nvtx_range("hypha.bwd"):
+                    loss.backward()
+                if main_grad == "fp32":
+                    self._main_grad.add()
+                total = loss.detach() if total is None else total + loss.detach()
+        finally:
+            self.model.grad_ready_hook = hook
+            self.model.set_grad_accumulate(False)
+        with nvtx_range("hypha.opt"):
+            if main_grad == "fp32":
+                self._main_grad.finalize()
+                self.opt.step()
+            else:
+                self.opt.step(grad_scale=1.0 / k)
+        self.last_loss = total / k
         return self.last_loss
 
     def outer_step(self) -> None:
