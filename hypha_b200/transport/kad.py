@@ -116,3 +116,168 @@ class RoutingTable:
 
     def closest(self, key: str, n: int = K, include_self: bool = False) -> List[str]:
         return list(self._t.closest(key, n, include_self))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# record store of a DHT node
+# ---------------------------------------------------------------------------------------------------------------------
+RECORD_TTL_S = 3600.0           # a record nobody republishes disappears (publishers republish every few minutes)
+MAX_RECORD_VALUE = 64 * 1024    # bytes; the reference's records are a few dozen bytes (DataRecord{num_slices})
+MAX_RECORD_KEY = 256
+MAX_RECORDS = 16384             # per node
+MAX_RECORDS_PER_PUBLISHER = 1024
+MAX_PROVIDERS_PER_KEY = 64
+
+
+class StoredRecord(tuple):
+    """``(value, publisher)`` -- what `get_record` hands out -- with the bookkeeping as attributes."""
+
+    def __new__(cls, value: bytes, publisher: str, seq: int = 0, sig: bytes = b"", pub: bytes = b"",
+                expires: float = float("inf")):
+        self = super().__new__(cls, (value, publisher))
+        self.seq, self.sig, self.pub, self.expires = int(seq), bytes(sig or b""), bytes(pub or b""), expires
+        return self
+
+    value = property(lambda self: self[0])
+    publisher = property(lambda self: self[1])
+
+
+class RecordStore:
+    """Records and provider sets a node keeps for the DHT, with the limits a node reachable by strangers needs:
+
+    * size: values <= 64 KiB, keys <= 256 bytes, <= 16384 records per node and <= 1024 per publisher -- a peer cannot
+      grow the store without bound; a full store evicts expired entries first and then refuses;
+    * lifetime: an entry lives `RECORD_TTL_S` after it was last stored (the publisher's upkeep timer stores it again
+      every few minutes), so what a departed peer left behind goes away;
+    * ownership (``enforce_owner``, on under a PKI): while a key's record is alive only its publisher can replace it
+      -- another certificate holder cannot take over a dataset's key and point the schedulers at its own data node;
+    * order: a publisher's records carry a sequence number (its clock in ms) under its signature; an older copy --
+      a replay by a server that kept one -- does not roll a newer one back.
+
+    Reads like a dict of ``key -> (value, publisher)``."""
+
+    def __init__(self, ttl_s: float = RECORD_TTL_S, enforce_owner: bool = False, clock=None):
+        import time
+
+        self.ttl_s, self.enforce_owner = ttl_s, enforce_owner
+        self._clock = clock or time.monotonic
+        self._recs: dict = {}
+        self._per_pub: dict = {}
+        self._provs: dict = {}                # key -> {provider: expires}
+        self.refused: dict = {}               # reason -> count
+
+    # -- records ------------------------------------------------------------------------------------------------------
+    def _no(self, why: str) -> str:
+        self.refused[why] = self.refused.get(why, 0) + 1
+        return why
+
+    def _drop(self, key: str) -> None:
+        rec = self._recs.pop(key, None)
+        if rec is not None:
+            n = self._per_pub.get(rec.publisher, 0) - 1
+            if n > 0:
+                self._per_pub[rec.publisher] = n
+            else:
+                self._per_pub.pop(rec.publisher, None)
+
+    def expire(self) -> int:
+        now, n = self._clock(), 0
+        for key in [k for k, r in self._recs.items() if r.expires <= now]:
+            self._drop(key)
+            n += 1
+        for key in list(self._provs):
+            live = {p: e for p, e in self._provs[key].items() if e > now}
+            n += len(self._provs[key]) - len(live)
+            if live:
+                self._provs[key] = live
+            else:
+                del self._provs[key]
+        return n
+
+    def put(self, key: str, value: bytes, publisher: str, seq: int = 0, sig: bytes = b"", pub: bytes = b"",
+            local: bool = False) -> str:
+        """"stored", or why not ("too-large" | "owned" | "stale" | "full").  ``local``: this node's own record (no
+        quota, never expires while the node republishes it)."""
+        if not isinstance(key, str) or not isinstance(publisher, str) or len(key.encode()) > MAX_RECORD_KEY \
+                or len(value) > MAX_RECORD_VALUE or len(publisher) > MAX_RECORD_KEY:
+            return self._no("too-large")
+        now = self._clock()
+        cur = self._recs.get(key)
+        if cur is not None and cur.expires <= now:
+            self._drop(key)
+            cur = None
+        if cur is not None:
+            if cur.publisher != publisher:
+                if self.enforce_owner and not local:
+                    return self._no("owned")
+            elif int(seq) < cur.seq:
+                return self._no("stale")
+        if not local and (cur is None or cur.publisher != publisher):
+            if self._per_pub.get(publisher, 0) >= MAX_RECORDS_PER_PUBLISHER or len(self._recs) >= MAX_RECORDS:
+                self.expire()
+                if self._per_pub.get(publisher, 0) >= MAX_RECORDS_PER_PUBLISHER or len(self._recs) >= MAX_RECORDS:
+                    return self._no("full")
+        if cur is not None:
+            self._drop(key)
+        self._recs[key] = StoredRecord(bytes(value), publisher, seq, sig, pub,
+                                       float("inf") if local else now + self.ttl_s)
+        self._per_pub[publisher] = self._per_pub.get(publisher, 0) + 1
+        return "stored"
+
+    def get(self, key: str, default=None):
+        rec = self._recs.get(key)
+        if rec is None:
+            return default
+        if rec.expires <= self._clock():
+            self._drop(key)
+            return default
+        return rec
+
+    def __getitem__(self, key: str):
+        rec = self.get(key)
+        if rec is None:
+            raise KeyError(key)
+        return rec
+
+    def __setitem__(self, key: str, vp) -> None:
+        self._drop(key)
+        self._recs[key] = StoredRecord(vp[0], vp[1], expires=self._clock() + self.ttl_s)
+        self._per_pub[vp[1]] = self._per_pub.get(vp[1], 0) + 1
+
+    def __contains__(self, key) -> bool:
+        return self.get(key) is not None
+
+    def __len__(self) -> int:
+        return len(self._recs)
+
+    def keys(self):
+        return list(self._recs)
+
+    def clear(self) -> None:
+        self._recs.clear()
+        self._per_pub.clear()
+        self._provs.clear()
+
+    # -- providers ----------------------------------------------------------------------------------------------------
+    def add_provider(self, key: str, provider: str) -> str:
+        if not isinstance(key, str) or len(key.encode()) > MAX_RECORD_KEY or len(provider) > MAX_RECORD_KEY:
+            return self._no("too-large")
+        now = self._clock()
+        cur = self._provs.get(key)
+        if cur is None:
+            if len(self._provs) >= MAX_RECORDS:
+                self.expire()
+                if len(self._provs) >= MAX_RECORDS:
+                    return self._no("full")
+            cur = self._provs[key] = {}
+        if provider not in cur and len(cur) >= MAX_PROVIDERS_PER_KEY:
+            for p in [p for p, e in cur.items() if e <= now]:
+                del cur[p]
+            if len(cur) >= MAX_PROVIDERS_PER_KEY:
+                return self._no("full")
+        cur[provider] = now + self.ttl_s
+        return "stored"
+
+    def providers(self, key: str) -> set:
+        now = self._clock()
+        return {p for p, e in self._provs.get(key, {}).items() if e > now}

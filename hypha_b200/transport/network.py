@@ -387,6 +387,23 @@ class IncomingStream:
 # ---------------------------------------------------------------------------------------------
 # the node
 # ---------------------------------------------------------------------------------------------
+class _ProviderView:
+    """``net._providers[key]`` / ``.get(key, default)``: the live provider set of a key in the record store."""
+
+    def __init__(self, store):
+        self._store = store
+
+    def __getitem__(self, key: str) -> Set[str]:
+        return self._store.providers(key)
+
+    def get(self, key: str, default=None):
+        got = self._store.providers(key)
+        return got if got else (set() if default is None else default)
+
+    def __contains__(self, key: str) -> bool:
+        return bool(self._store.providers(key))
+
+
 class Network:
     """Per-role network handle (what the reference calls ``Network`` + ``NetworkDriver``)."""
 
@@ -407,6 +424,7 @@ class Network:
         # unsigned, signed by a key that is not the claimed origin's, or altered -- a relaying peer cannot forge an ad.
         self._sign_key = None
         self._pub_raw = b""
+        self._last_seq = 0
         self.gossip_rejections = 0
         if tls and tls.get("key_pem"):
             try:
@@ -440,10 +458,14 @@ class Network:
         self._subs: Dict[str, List[asyncio.Queue]] = {}
         self._peer_topics: Dict[str, Set[str]] = {}
         self._seen_msgs: Dict[str, float] = {}
-        self._records: Dict[str, Tuple[bytes, str]] = {}
+        from .kad import RecordStore
+
+        # bounded, expiring; under a PKI a live key belongs to its publisher (see `kad.RecordStore`)
+        self._records = RecordStore(enforce_owner=self.strict_gossip)
+        self.record_refusals = 0                       # dht_put / dht_provide / replicas the store did not take
         self._published: Dict[str, bytes] = {}        # records THIS node published (republished by the maintenance loop)
         self._provided: Set[str] = set()
-        self._providers: Dict[str, Set[str]] = {}
+        self._providers = _ProviderView(self._records)
         self._stream_rx: Dict[Tuple[str, Optional[str]], asyncio.Queue] = {}
         self._early_streams: Dict[Tuple[str, Optional[str]], List[Tuple[float, IncomingStream]]] = {}
         self._streams: Dict[str, IncomingStream] = {}
@@ -853,18 +875,21 @@ class Network:
         elif t == "pub":
             await self._on_publish(frame, src)
         elif t == "dht_put":
-            if frame["publisher"] == src:            # a record is published under the sender's own id only
-                self._records[frame["key"]] = (frame["value"], frame["publisher"])
-                if self.dht_server:
+            # a record is published under the sender's own id only; what is kept (and handed on) carries a signature
+            # that checks out, so that nobody downstream is given a copy it has to refuse
+            if frame["publisher"] == src and (not frame.get("sig") or self._record_authentic(frame)):
+                if self._store_record(frame) and self.dht_server:
                     self._spawn(self._replicate(frame, {src}))
             else:
                 self.identity_rejections += 1
         elif t == "dht_provide":
             if frame["provider"] == src:
-                self._providers.setdefault(frame["key"], set()).add(frame["provider"])
-                if self.dht_server:
+                if self._records.add_provider(frame["key"], frame["provider"]) != "stored":
+                    self.record_refusals += 1
+                elif self.dht_server:
                     self._spawn(self._replicate({"key": frame["key"], "value": b"", "publisher": frame["provider"],
-                                                 "kind": "provider", "sig": frame.get("sig"), "pub": frame.get("pub")}, {src}))
+                                                 "kind": "provider", "seq": frame.get("seq", 0),
+                                                 "sig": frame.get("sig"), "pub": frame.get("pub")}, {src}))
             else:
                 self.identity_rejections += 1
         elif t == "dht_replicate":
@@ -872,9 +897,10 @@ class Network:
             # accepted from DHT servers only and never forwarded again
             if self.dht_server and src in self.kad and self._record_authentic(frame):
                 if frame.get("kind") == "provider":
-                    self._providers.setdefault(frame["key"], set()).add(frame["publisher"])
+                    if self._records.add_provider(frame["key"], frame["publisher"]) != "stored":
+                        self.record_refusals += 1
                 else:
-                    self._records[frame["key"]] = (frame["value"], frame["publisher"])
+                    self._store_record(frame)
             else:
                 self.identity_rejections += 1
         elif t == "stream_open":
@@ -1081,22 +1107,36 @@ class Network:
 
     # -- DHT -----------------------------------------------------------------------------------------------------------
     @staticmethod
-    def _record_digest(kind: str, key: str, value: bytes, publisher: str) -> bytes:
+    def _record_digest(kind: str, key: str, value: bytes, publisher: str, seq: int = 0) -> bytes:
         import hashlib
 
         h = hashlib.sha256()
-        for part in (b"hypha-dht-v1", kind.encode(), key.encode(), bytes(value), publisher.encode()):
+        for part in (b"hypha-dht-v2", kind.encode(), key.encode(), bytes(value), publisher.encode(),
+                     int(seq).to_bytes(8, "little")):
             h.update(len(part).to_bytes(4, "little"))
             h.update(part)
         return h.digest()
 
     def _sign_record(self, frame: dict) -> dict:
-        """A node with a key signs what it publishes: the copies DHT servers hand to each other stay verifiable."""
+        """Every published record carries a sequence number (this node's clock in ms: a later publication of the same
+        key outranks an earlier one, a replayed old copy does not roll it back); a node with a key signs key, value,
+        publisher and sequence number, so the copies DHT servers hand to each other -- and to readers -- stay
+        verifiable."""
+        frame["seq"] = max(int(time.time() * 1000), self._last_seq + 1)
+        self._last_seq = frame["seq"]
         if self._sign_key is not None:
             frame["pub"] = self._pub_raw
             frame["sig"] = self._sign_key.sign(self._record_digest(frame.get("kind", "record"), frame["key"],
-                                                                   frame.get("value", b""), frame["publisher"]))
+                                                                   frame.get("value", b""), frame["publisher"],
+                                                                   frame["seq"]))
         return frame
+
+    def _store_record(self, frame: dict) -> bool:
+        why = self._records.put(frame["key"], frame["value"], frame["publisher"], int(frame.get("seq") or 0),
+                                frame.get("sig") or b"", frame.get("pub") or b"")
+        if why != "stored":
+            self.record_refusals += 1
+        return why == "stored"
 
     def _record_authentic(self, frame: dict) -> bool:
         """Replicated records reach us from a server that is NOT their publisher.  With a PKI (strict mode) such a
@@ -1114,7 +1154,7 @@ class Network:
                 return False
             Ed25519PublicKey.from_public_bytes(bytes(pub)).verify(
                 bytes(sig), self._record_digest(frame.get("kind", "record"), frame["key"], frame.get("value", b""),
-                                                frame["publisher"]))
+                                                frame["publisher"], int(frame.get("seq") or 0)))
             return True
         except Exception:
             return False
@@ -1130,10 +1170,13 @@ class Network:
         acknowledged send is enough); the receiving servers replicate to the closest servers THEY know."""
         from .kad import REPLICATION
 
-        self._records[key] = (value, self.peer_id)
-        self._published[key] = value
         frame = self._sign_record({"t": "dht_put", "key": key, "value": value, "publisher": self.peer_id,
                                    "proto": "/ipfs/kad/1.0.0"})
+        why = self._records.put(key, value, self.peer_id, frame["seq"], frame.get("sig", b""), frame.get("pub", b""),
+                                local=True)
+        if why != "stored":
+            raise NetworkError(f"put_record: {why}")
+        self._published[key] = value
         ok = 0
         for peer in self._dht_targets(key, REPLICATION):
             try:
@@ -1149,7 +1192,7 @@ class Network:
         from .kad import REPLICATION
 
         rep = {"t": "dht_replicate", "key": frame["key"], "value": frame["value"], "publisher": frame["publisher"],
-               "kind": frame.get("kind", "record")}
+               "kind": frame.get("kind", "record"), "seq": int(frame.get("seq") or 0)}
         if frame.get("sig") and frame.get("pub"):
             rep["sig"], rep["pub"] = frame["sig"], frame["pub"]
         for peer in self.kad.closest(frame["key"], REPLICATION):
@@ -1190,17 +1233,26 @@ class Network:
 
     async def get_record(self, key: str, timeout: float = 5.0) -> Tuple[bytes, str]:
         """(value, publisher).  Local store first, then an iterative lookup over the DHT servers."""
-        if key in self._records:
-            return self._records[key]
-        async for _, r in self._lookup(key, "get", timeout):
-            if r.get("found"):
-                return r["value"], r["publisher"]
+        rec = self._records.get(key)
+        if rec is not None:
+            return rec[0], rec[1]
+        async for server, r in self._lookup(key, "get", timeout):
+            if not r.get("found"):
+                continue
+            # the answering server is rarely the publisher: under a PKI its copy must carry the publisher's signature
+            # (a server cannot invent a dataset record and send the scheduler to a data node of its choosing)
+            if r.get("publisher") != server and not self._record_authentic(
+                    {"key": key, "value": r.get("value", b""), "publisher": r.get("publisher", ""),
+                     "seq": r.get("seq", 0), "sig": r.get("sig"), "pub": r.get("pub")}):
+                self.identity_rejections += 1
+                continue
+            return r["value"], r["publisher"]
         raise RecordNotFound(key)
 
     async def provide(self, key: str) -> None:
         from .kad import REPLICATION
 
-        self._providers.setdefault(key, set()).add(self.peer_id)
+        self._records.add_provider(key, self.peer_id)
         self._provided.add(key)
         for peer in self._dht_targets(key, REPLICATION):
             try:
@@ -1274,7 +1326,8 @@ class Network:
             if "get" in msg:
                 rec = self._records.get(msg["get"])
                 if rec is not None:
-                    return {"found": True, "value": rec[0], "publisher": rec[1]}
+                    return {"found": True, "value": rec[0], "publisher": rec[1], "seq": rec.seq, "sig": rec.sig,
+                            "pub": rec.pub}
                 return {"found": False, "value": b"", "publisher": "", "closer": closer(msg["get"])}
             if "providers" in msg:
                 return {"providers": sorted(self._providers.get(msg["providers"], set())), "closer": closer(msg["providers"])}

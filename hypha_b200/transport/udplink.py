@@ -29,7 +29,10 @@ from typing import Dict, List, Optional, Tuple
 
 import cbor2
 
-INIT, RESP, FIN, DATA, CLOSE, PUNCH = 1, 2, 3, 4, 5, 6
+INIT, RESP, FIN, DATA, CLOSE, PUNCH, RETRY = 1, 2, 3, 4, 5, 6, 7
+COOKIE_LEN = 24                 # 8-byte timestamp + 16 bytes of HMAC-SHA256 over (source address, client cid, timestamp)
+COOKIE_AFTER = 64               # half-open connections beyond which an INIT must echo a cookie (QUIC's Retry)
+COOKIE_TTL_S = 10.0
 MSS = 1150                      # stream bytes per datagram (fits a 1280-byte path MTU with headers + tag)
 CWND = 1024 * 1024              # upper bound of the congestion window (bytes in flight)
 INIT_CWND = 16 * 1150
@@ -157,6 +160,10 @@ class UdpLink:
         self._ooo_bytes = 0
         self._stream = bytearray()
         self._frames: collections.deque = collections.deque()
+        self._queued = 0                            # bytes of complete frames nobody has `recv()`-ed yet
+        self._adv_wnd = RWND                        # the window last advertised
+        self._in_order = 0
+        self._persist, self._persist_at = 0.2, 0.0  # zero-window probing (sender side)
         self._frame_waiter: Optional[asyncio.Future] = None
         self._ack_due = False
         self._segs_since_ack = 0
@@ -203,10 +210,16 @@ class UdpLink:
             self._ack_due = False
             self._send_records(self._ack_record())
 
+    def _window(self) -> int:
+        """What the receiver can still take: the reassembly budget minus what is parked out of order and minus the
+        complete frames the application has not read yet.  The frame under assembly does not count -- it is bounded by
+        `MAX_FRAME` on its own, and counting it would close the window on any frame larger than the window."""
+        return max(0, RWND - self._ooo_bytes - self._queued)
+
     def _ack_record(self) -> bytes:
         self._segs_since_ack = 0
-        wnd = max(0, RWND - self._ooo_bytes - len(self._stream))
-        return b"A" + struct.pack("<QI", self._rcv_nxt, wnd)
+        self._adv_wnd = self._window()
+        return b"A" + struct.pack("<QI", self._rcv_nxt, self._adv_wnd)
 
     # -- sending -------------------------------------------------------------------------------------------------------
     def _pump(self) -> None:
@@ -223,14 +236,14 @@ class UdpLink:
                 rec += self._ack_record()
                 self._ack_due = False
             self._send_records(rec)
-        if self._inflight < min(self._cwnd, self._peer_wnd) and len(self._snd_buf) < CWND:
+        if len(self._snd_buf) < CWND:                 # `send` parks at most ~2 windows here, whatever the peer's window
             self._space.set()
         else:
             self._space.clear()
         self._arm()
 
     def _arm(self) -> None:
-        if self._timer is None and (self._unacked or self._ack_due) and not self.closed:
+        if self._timer is None and (self._unacked or self._ack_due or self._snd_buf) and not self.closed:
             self._timer = asyncio.get_event_loop().call_later(0.01 if self._ack_due else min(self._rto, 0.05), self._tick)
 
     def _tick(self) -> None:
@@ -241,7 +254,19 @@ class UdpLink:
         if self._ack_due:
             self._ack_due = False
             self._send_records(self._ack_record())
-        if self._unacked:
+        if self._snd_buf and not self._unacked and self._peer_wnd < self.mss and now >= self._persist_at:
+            # zero-window probe: the receiver's window update may have been lost, and nothing else is in flight whose
+            # ACK would bring a new one.  One segment, at a doubling interval; its ACK carries the current window.
+            seg = bytes(self._snd_buf[:self.mss])
+            del self._snd_buf[:self.mss]
+            off = self._snd_nxt
+            self._snd_nxt += len(seg)
+            self._unacked[off] = [seg, now, 0]
+            self._inflight += len(seg)
+            self._send_records(b"S" + struct.pack("<QH", off, len(seg)) + seg)
+            self._persist = min(2.0, self._persist * 2)
+            self._persist_at = now + self._persist
+        elif self._unacked:
             off, ent = next(iter(self._unacked.items()))
             if now - ent[1] > self._rto:
                 if ent[2] >= 12:
@@ -267,6 +292,10 @@ class UdpLink:
     def _on_ack(self, ack: int, wnd: int) -> None:
         self._peer_wnd = wnd
         now = time.monotonic()
+        if wnd >= self.mss:
+            self._persist, self._persist_at = 0.2, 0.0
+        elif self._persist_at == 0.0:
+            self._persist_at = now + self._persist
         if ack > self._snd_una:
             self._snd_una = ack
             self._dup_acks = 0
@@ -404,6 +433,12 @@ class UdpLink:
                 self._ooo_bytes -= len(s)
                 self._stream += s
                 self._rcv_nxt += len(s)
+            self._in_order += 1
+            if self._ooo and self._in_order % 256 == 0:
+                # segments parked under offsets the stream has passed by other cuts (the sender re-cuts what is in
+                # flight when it lowers its segment size) would hold window space for good
+                for o in [o for o in self._ooo if o < self._rcv_nxt]:
+                    self._ooo_bytes -= len(self._ooo.pop(o))
             self._parse()
             self._segs_since_ack += 1
             self.ep._dirty.add(self)                         # one ACK per batch of datagrams read (`_on_readable`)
@@ -429,6 +464,7 @@ class UdpLink:
             if len(buf) < 4 + n:
                 break
             self._frames.append((bytearray(buf[4:4 + n]), split))
+            self._queued += n
             del buf[:4 + n]
         w, self._frame_waiter = self._frame_waiter, None
         if w is not None and not w.done():
@@ -444,6 +480,9 @@ class UdpLink:
             await self._frame_waiter
         body, split = self._frames.popleft()
         n, m = len(body), 0
+        self._queued -= n
+        if self._adv_wnd < RWND // 4 and self._window() >= RWND // 2 and not self.closed and self._tx_key is not None:
+            self._send_records(self._ack_record())           # window update: the sender was (nearly) stopped
         if split:
             if n < 4:
                 raise NetworkError("malformed bulk frame")
@@ -506,6 +545,9 @@ class UdpEndpoint:
         self.nat_filter = False       # test hook: behave like an address-restricted NAT (INITs only from punched peers)
         self.mtu_limit = 0            # test hook: refuse datagrams above this size, like an interface MTU
         self._contacted: set = set()
+        self._cookie_secret = os.urandom(32)
+        self._swept_at = 0.0
+        self.retries_sent = 0
         self._key = self._chain = None
         if tls:
             from cryptography import x509
@@ -644,15 +686,16 @@ class UdpEndpoint:
         # padded to INIT_MIN bytes: the server answers an INIT with ~1 KB (certificates) before the client has shown
         # that it can receive at its source address, so the request must not be smaller than the answer (QUIC's rule
         # against reflection amplification)
-        init = struct.pack("<B8s8s", INIT, b"\0" * 8, scid) + e_pub
-        init += b"\0" * max(0, INIT_MIN - len(init))
+        head = struct.pack("<B8s8s", INIT, b"\0" * 8, scid) + e_pub
         deadline = time.monotonic() + timeout
         delay = 0.1
         while not link.established.done():
             if "fin" in link.hs:
                 self.sendto(link.hs["fin"], link.addr)            # our FIN may have been lost: the RESP came again
             else:
-                self.sendto(init, link.addr)
+                # a busy server first answers RETRY with a cookie bound to our address; the INIT then carries it
+                init = head + link.hs.get("cookie", b"\0" * COOKIE_LEN)
+                self.sendto(init + b"\0" * max(0, INIT_MIN - len(init)), link.addr)
             left = deadline - time.monotonic()
             if left <= 0:
                 link._fail("handshake timed out", notify=False)
@@ -694,6 +737,13 @@ class UdpEndpoint:
                 # only a handshake can be refused in clear: nothing authenticated has arrived on this connection yet
                 if c is not None and (not c.established.done() or (c.initiator and not c._rx_seen)):
                     c._fail("refused by peer: " + data[9:].decode(errors="replace"), notify=False)
+            elif typ == RETRY:
+                c = self.conns.get(dcid)
+                if c is not None and c.initiator and not c.established.done() and "fin" not in c.hs \
+                        and len(data) >= 9 + COOKIE_LEN and "cookie" not in c.hs:
+                    c.hs["cookie"] = data[9:9 + COOKIE_LEN]
+                    init = struct.pack("<B8s8s", INIT, b"\0" * 8, c.scid) + c.hs["e_pub"] + c.hs["cookie"]
+                    self.sendto(init + b"\0" * max(0, INIT_MIN - len(init)), c.addr)
             elif typ == PUNCH:
                 self.punches += 1
         except UdpError as exc:
@@ -704,6 +754,24 @@ class UdpEndpoint:
                 c._fail(str(exc), notify=False)
         except Exception:
             return
+
+    def _cookie(self, addr, ccid: bytes, ts: Optional[int] = None) -> bytes:
+        import hashlib
+        import hmac
+
+        ts = int(time.time()) if ts is None else ts
+        msg = repr(tuple(addr[:2])).encode() + ccid + struct.pack("<Q", ts)
+        return struct.pack("<Q", ts) + hmac.new(self._cookie_secret, msg, hashlib.sha256).digest()[:16]
+
+    def _cookie_ok(self, cookie: bytes, addr, ccid: bytes) -> bool:
+        import hmac
+
+        if len(cookie) != COOKIE_LEN:
+            return False
+        (ts,) = struct.unpack_from("<Q", cookie, 0)
+        if abs(time.time() - ts) > COOKIE_TTL_S:
+            return False
+        return hmac.compare_digest(cookie, self._cookie(addr, ccid, ts))
 
     def _on_init(self, data: bytes, addr) -> None:
         from cryptography.hazmat.primitives import serialization
@@ -718,10 +786,19 @@ class UdpEndpoint:
             return
         # half-open connections older than 10 s are forgotten (an INIT flood must not pin memory)
         now = time.monotonic()
-        for k, v in list(self._pending_init.items()):
-            if now - v.hs.get("t0", now) > 10.0:
-                self._pending_init.pop(k, None)
-                v._fail("handshake never completed", notify=False)
+        if now - self._swept_at > 1.0:
+            self._swept_at = now
+            for k, v in list(self._pending_init.items()):
+                if now - v.hs.get("t0", now) > 10.0:
+                    self._pending_init.pop(k, None)
+                    v._fail("handshake never completed", notify=False)
+        if len(self._pending_init) >= COOKIE_AFTER and not self._cookie_ok(data[49:49 + COOKIE_LEN], addr, ccid):
+            # many half-open connections: before spending a key exchange and a signature on this one, make the
+            # client show that it receives at the address it claims (QUIC's Retry; 33 bytes back for 1200 in)
+            self.retries_sent += 1
+            self.sendto(struct.pack("<B8s", RETRY, ccid) + self._cookie(addr, ccid), addr)
+            return
+        now = time.monotonic()
         scid = os.urandom(8)
         link = UdpLink(self, addr, scid, False)
         link.dcid = ccid

@@ -54,6 +54,106 @@ def test_udp_link_request_and_lossy_stream():
     run(main())
 
 
+async def _udp_pair():
+    from hypha_b200.transport.udplink import UdpEndpoint
+
+    accepted = asyncio.get_event_loop().create_future()
+    sep = UdpEndpoint(None, lambda link: accepted.set_result(link))
+    sep.open("127.0.0.1", 0)
+    cep = UdpEndpoint(None, lambda link: None)
+    cep.open("127.0.0.1", 0)
+    c = await cep.connect(*sep.local_addr)
+    return sep, cep, await asyncio.wait_for(accepted, 5), c
+
+
+def test_udp_receive_window_is_bounded_and_never_wedges():
+    """Flow control of a udp link: (a) a frame larger than the receive window still arrives (the frame being assembled
+    does not count against the window), (b) frames nobody reads stop the SENDER at about one window instead of piling
+    up in the receiver, (c) when the reader returns the window update restarts the flow -- even when that update is
+    lost (zero-window probe)."""
+    from hypha_b200.transport import udplink
+
+    async def main():
+        sep, cep, s, c = await _udp_pair()
+        big = os.urandom(udplink.RWND + (2 << 20))
+        await asyncio.wait_for(c.send({"t": "stream_data", "sid": "x", "data": big}), 30)
+        frame, _ = await asyncio.wait_for(s.recv(), 30)
+        assert bytes(frame["data"]) == big
+        chunk, n = os.urandom(256 << 10), 48                               # 12 MiB, three windows
+
+        async def pour():
+            for i in range(n):
+                await c.send({"t": "stream_data", "sid": "y", "i": i, "data": chunk})
+
+        task = asyncio.ensure_future(pour())
+        await asyncio.sleep(1.5)
+        assert not task.done()                                              # the sender is waiting for window
+        assert s._queued <= udplink.RWND + 2 * len(chunk) and s._queued >= udplink.RWND // 2
+        held = s._queued
+        await asyncio.sleep(0.5)
+        assert s._queued <= held + 64 * 1024                                # and it stays put (probes trickle at most)
+        sep.drop_next, sep.drop_every = 4, 1                                # the window updates get lost
+        for i in range(n):
+            frame, _ = await asyncio.wait_for(s.recv(), 20)
+            assert frame["i"] == i and bytes(frame["data"]) == chunk
+        await asyncio.wait_for(task, 20)
+        assert s._queued == 0 and sep.drop_next == 0
+        cep.close()
+        sep.close()
+
+    run(main())
+
+
+def test_udp_busy_server_asks_for_a_retry_cookie():
+    """With many half-open connections an INIT is answered by a 33-byte RETRY carrying a cookie bound to the source
+    address; the key exchange and the signature are spent only on an INIT that echoes it.  A client goes through this
+    transparently; a flood from spoofed addresses costs the server one HMAC per datagram."""
+    import socket
+    import struct
+
+    from hypha_b200.transport import udplink
+
+    async def main():
+        accepted = []
+        sep = udplink.UdpEndpoint(None, accepted.append)
+        sep.open("127.0.0.1", 0)
+        # a flood: distinct (spoofable) client ids, no cookie
+        raw = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+        raw.bind(("127.0.0.1", 0))
+        raw.setblocking(False)
+        for i in range(udplink.COOKIE_AFTER + 8):
+            init = struct.pack("<B8s8s", udplink.INIT, b"\0" * 8, struct.pack("<Q", i + 1)) + os.urandom(32)
+            raw.sendto(init + b"\0" * (udplink.INIT_MIN - len(init)), sep.local_addr)
+            await asyncio.sleep(0.002)
+        await asyncio.sleep(0.2)
+        assert len(sep._pending_init) == udplink.COOKIE_AFTER and sep.retries_sent == 8
+        kinds = []
+        while True:
+            try:
+                kinds.append(raw.recv(65535))
+            except BlockingIOError:
+                break
+        assert sum(1 for d in kinds if d[0] == udplink.RETRY and len(d) == 9 + udplink.COOKIE_LEN) == 8
+        # a cookie issued to another address (or made up) is not accepted
+        init = struct.pack("<B8s8s", udplink.INIT, b"\0" * 8, b"spoofer!") + os.urandom(32) + os.urandom(udplink.COOKIE_LEN)
+        raw.sendto(init + b"\0" * (udplink.INIT_MIN - len(init)), sep.local_addr)
+        await asyncio.sleep(0.1)
+        assert len(sep._pending_init) == udplink.COOKIE_AFTER and sep.retries_sent == 9
+        # a real client still gets in, one round trip later
+        cep = udplink.UdpEndpoint(None, lambda link: None)
+        cep.open("127.0.0.1", 0)
+        c = await asyncio.wait_for(cep.connect(*sep.local_addr), 5)
+        await asyncio.sleep(0.1)
+        assert sep.retries_sent == 10 and len(accepted) == 1 and "cookie" in c.hs
+        await c.send({"t": "hello"})
+        assert (await asyncio.wait_for(accepted[0].recv(), 5))[0] == {"t": "hello"}
+        raw.close()
+        cep.close()
+        sep.close()
+
+    run(main())
+
+
 def _pki(names):
     from hypha_b200 import certutil
 
@@ -284,6 +384,96 @@ def test_replicated_records_are_verifiable_under_a_pki():
         await asyncio.sleep(0.2)
         assert g2._records["dataset"] == (b"real", ids["data"]) and g2.identity_rejections == before + 2
         for n in (data, rogue, g1, g2):
+            await n.close()
+
+    run(main())
+
+
+def test_record_store_limits_lifetime_ownership_and_order():
+    """`kad.RecordStore`: bounded (value / key size, per-publisher and per-node counts, providers per key), expiring,
+    a live key belongs to its publisher when ownership is enforced, and an older sequence number does not replace a
+    newer one."""
+    from hypha_b200.transport import kad
+
+    now = [0.0]
+    st = kad.RecordStore(ttl_s=100.0, enforce_owner=True, clock=lambda: now[0])
+    assert st.put("k", b"v1", "alice", seq=5) == "stored" and st["k"] == (b"v1", "alice") and st["k"].seq == 5
+    assert st.put("k", b"old", "alice", seq=4) == "stale" and st["k"][0] == b"v1"          # replayed older copy
+    assert st.put("k", b"v2", "alice", seq=6) == "stored" and st["k"][0] == b"v2"
+    assert st.put("k", b"mine now", "mallory", seq=99) == "owned" and st["k"] == (b"v2", "alice")
+    now[0] = 101.0                                                                           # nobody republished it
+    assert "k" not in st and st.get("k") is None
+    assert st.put("k", b"m", "mallory", seq=1) == "stored"                                   # the key is free again
+    assert st.put("big", b"x" * (kad.MAX_RECORD_VALUE + 1), "alice") == "too-large"
+    assert st.put("k" * 300, b"", "alice") == "too-large"
+    for i in range(kad.MAX_RECORDS_PER_PUBLISHER):
+        assert st.put(f"bulk-{i}", b"", "spammer") == "stored"
+    assert st.put("one-more", b"", "spammer") == "full" and st.put("other", b"", "alice") == "stored"
+    assert st.put("bulk-0", b"again", "spammer", seq=1) == "stored"                          # refreshing is not growth
+    now[0] = 250.0
+    assert st.put("one-more", b"", "spammer") == "stored" and len(st) == 1                   # expired entries made room
+    assert st.put("mine", b"", "me", local=True) == "stored"
+    now[0] = 1e9
+    assert "mine" in st and "one-more" not in st                                             # own records stay
+    # providers
+    for i in range(kad.MAX_PROVIDERS_PER_KEY):
+        assert st.add_provider("file", f"p{i}") == "stored"
+    assert st.add_provider("file", "p-extra") == "full" and st.add_provider("file", "p0") == "stored"
+    assert len(st.providers("file")) == kad.MAX_PROVIDERS_PER_KEY
+    now[0] += 101.0
+    assert st.providers("file") == set() and st.add_provider("file", "p-extra") == "stored"
+    assert st.refused["owned"] == 1 and st.refused["stale"] == 1 and st.refused["full"] >= 2
+    # without ownership (no PKI: peer ids are per process, a restarted data node must be able to publish again)
+    loose = kad.RecordStore(clock=lambda: 0.0)
+    assert loose.put("k", b"a", "x") == "stored" and loose.put("k", b"b", "y") == "stored" and loose["k"] == (b"b", "y")
+
+
+def test_pki_dht_keys_are_owned_and_reads_are_verified():
+    """Under a PKI (a) another certificate holder cannot take over a live key -- the dataset record keeps pointing at
+    the data node that published it -- and (b) a reader checks the publisher's signature on the copy a server hands
+    out, so a rogue DHT server cannot answer a lookup with a record of its own making."""
+    from hypha_b200.transport.utils import peer_id_from_key_pem
+
+    async def main():
+        _, _, _, tls = _pki(["g1", "data", "mallory", "rogue", "sched"])
+        ids = {n: peer_id_from_key_pem(t["key_pem"]) for n, t in tls.items()}
+        g1 = Network(ids["g1"], relay_server=True, dht_server=True, tls=tls["g1"])
+        g1.enable_dht_handlers()
+        a1 = await g1.listen("tcp://127.0.0.1:0")
+        data = Network(ids["data"], tls=tls["data"])
+        await data.dial(a1)
+        await data.put_record("dataset", b"real")
+        mallory = Network(ids["mallory"], tls=tls["mallory"])
+        await mallory.dial(a1)
+        await mallory.put_record("dataset", b"mine")              # accepted by the link, refused by the store
+        await asyncio.sleep(0.2)
+        assert g1._records["dataset"] == (b"real", ids["data"]) and g1.record_refusals == 1
+        await data.put_record("dataset", b"real-v2")              # the owner itself can update it
+        await asyncio.sleep(0.2)
+        assert g1._records["dataset"] == (b"real-v2", ids["data"])
+        # an old signed copy replayed by its publisher's link (or a server that kept it) does not roll v2 back
+        old = data._sign_record({"t": "dht_put", "key": "dataset", "value": b"real", "publisher": ids["data"]})
+        old["seq"] = 1
+        old["sig"] = data._sign_key.sign(data._record_digest("record", "dataset", b"real", ids["data"], 1))
+        await data._send(data.links[ids["g1"]], old, "/ipfs/kad/1.0.0")
+        await asyncio.sleep(0.2)
+        assert g1._records["dataset"][0] == b"real-v2"
+        # a scheduler reads through an honest server: verified
+        sched = Network(ids["sched"], tls=tls["sched"])
+        await sched.dial(a1)
+        assert await sched.get_record("dataset") == (b"real-v2", ids["data"])
+        # ... and through a rogue server that answers with a forged record: refused, the lookup goes on and fails
+        rogue = Network(ids["rogue"], relay_server=True, dht_server=True, tls=tls["rogue"])
+        rogue.enable_dht_handlers()
+        ar = await rogue.listen("tcp://127.0.0.1:0")
+        rogue._records["dataset"] = (b"poison", ids["data"])      # no signature of the data node exists for this
+        s2 = Network(ids["sched"], tls=tls["sched"])
+        await s2.dial(ar)
+        before = s2.identity_rejections
+        with pytest.raises(RecordNotFound):
+            await s2.get_record("dataset", timeout=1.0)
+        assert s2.identity_rejections == before + 1
+        for n in (data, mallory, sched, s2, rogue, g1):
             await n.close()
 
     run(main())
