@@ -311,6 +311,9 @@ class SocketLink(Link):
 _MEMORY_LISTENERS: Dict[str, "Network"] = {}
 DCUTR_PROTOCOL = "/libp2p/dcutr"
 DCUTR_RETRY_S = 30.0
+MAX_LEARNT_PEERS = 4096          # peers known by hearsay only (addresses from a relay's table)
+MAX_LEARNT_PER_HELLO = 512
+MAX_TOPICS_PER_PEER = 256
 
 
 # ---------------------------------------------------------------------------------------------
@@ -425,6 +428,7 @@ class Network:
         self._sign_key = None
         self._pub_raw = b""
         self._last_seq = 0
+        self._dcutr_served: Dict[str, float] = {}
         self.gossip_rejections = 0
         if tls and tls.get("key_pem"):
             try:
@@ -592,8 +596,13 @@ class Network:
                 "known": {p: a for p, a in self.peer_addrs.items()} if self.relay_server else {},
                 "servers": {p: self.kad.addrs(p) for p in self.kad.peers()[:64]} if self.dht_server else {}}
 
-    async def dial(self, addr: str, timeout: float = 5.0) -> str:
-        """Connect to ``addr``; returns the remote peer id once identify completed."""
+    async def dial(self, addr: str, timeout: float = 5.0, *, trust_relay: bool = True) -> str:
+        """Connect to ``addr``; returns the remote peer id once identify completed.
+
+        ``trust_relay``: whether the peer, should it announce itself as a relay server, may forward traffic in other
+        peers' names to this node.  A relay vouches for the ``src`` of what it forwards, so that role is granted only
+        on links the APPLICATION dialled (configured gateways); links this node opens on its own to addresses it learnt
+        from others (routing, hole punching, DHT walks) and inbound links never get it."""
         try:
             if addr.startswith("memory://"):
                 other = _MEMORY_LISTENERS.get(addr)
@@ -631,6 +640,7 @@ class Network:
             raise DialError(f"dial {addr} failed: {exc}") from exc
         fut = asyncio.get_event_loop().create_future()
         link._hello_fut = fut  # type: ignore[attr-defined]
+        link._relay_ok = trust_relay  # type: ignore[attr-defined]
         await self._send(link, self._hello(), "/hypha-identify/0.0.1")
         try:
             peer = await asyncio.wait_for(fut, timeout)
@@ -684,7 +694,7 @@ class Network:
             return link, False
         for addr in self.peer_addrs.get(peer, []):
             try:
-                got = await self.dial(addr)
+                got = await self.dial(addr, trust_relay=False)
                 if got == peer and peer in self.links:
                     return self.links[peer], False
             except DialError:
@@ -698,6 +708,22 @@ class Network:
                     self._spawn(self._upgrade_quietly(peer))
                 return l, True
         raise RequestFailed(f"no route to {peer}")
+
+    def _learn_addrs(self, peer: str, addrs: List[str]) -> None:
+        """Addresses of a peer this node is NOT connected to, as told by a third party (a relay's peer table): they
+        pass the CIDR filter, never replace what is known already, and the table of such hearsay is bounded -- when it
+        is full the oldest entries of peers without a link make room."""
+        if peer in self.peer_addrs or len(peer) > 256:
+            return
+        good = self.kad.cidr.filter(addrs)
+        if not good:
+            return
+        if len(self.peer_addrs) >= MAX_LEARNT_PEERS:
+            for p in [p for p in self.peer_addrs if p not in self.links][:max(1, MAX_LEARNT_PEERS // 16)]:
+                del self.peer_addrs[p]
+            if len(self.peer_addrs) >= MAX_LEARNT_PEERS:
+                return
+        self.peer_addrs[peer] = good
 
     # -- direct connection upgrade through relay (dcutr) ----------------------------------------------------------------
     def _dcutr_addrs(self) -> List[str]:
@@ -714,6 +740,13 @@ class Network:
         self._dcutr_on = True
 
         async def serve(peer: str, msg: Any):
+            # one upgrade attempt per peer per second: every request makes this node send datagrams and dial
+            now = time.monotonic()
+            if now - self._dcutr_served.get(peer, -1e9) < 1.0:
+                return {"addrs": []}
+            if len(self._dcutr_served) > 4096:
+                self._dcutr_served.clear()
+            self._dcutr_served[peer] = now
             theirs = self.kad.cidr.filter([a for a in (msg.get("connect") or []) if isinstance(a, str)][:8])
             ep = self._udp[0] if self._udp else None
             for a in theirs:
@@ -733,7 +766,7 @@ class Network:
             if link is not None and not link.closed:
                 return True
             try:
-                if await self.dial(a, timeout=timeout) == peer:
+                if await self.dial(a, timeout=timeout, trust_relay=False) == peer:
                     return True
             except DialError:
                 continue
@@ -809,16 +842,21 @@ class Network:
                 return
             first = link.peer_id is None
             link.peer_id = peer
-            link.is_relay = bool(frame.get("relay"))  # type: ignore[attr-defined]
+            # a relay speaks for others (see `dial`): only a peer this node chose to dial can hold that role
+            link.is_relay = bool(frame.get("relay")) and bool(getattr(link, "_relay_ok", False))  # type: ignore[attr-defined]
             self.links[peer] = link
             # addresses a peer tells us about are dialled later: they pass the same CIDR filter as the routing table
             # (a peer must not be able to point this node at an address range the operator excluded)
             if frame.get("addrs"):
                 self.peer_addrs[peer] = self.kad.cidr.filter([a for a in frame["addrs"] if isinstance(a, str)][:16])
-            for p, a in (frame.get("known") or {}).items():
-                if p != self.peer_id and isinstance(a, (list, tuple)):
-                    self.peer_addrs.setdefault(p, self.kad.cidr.filter([x for x in a if isinstance(x, str)][:16]))
-            self._peer_topics[peer] = set(frame.get("topics", []))
+            known = frame.get("known") or {}
+            if isinstance(known, dict) and link.is_relay:           # a relay's peer table; nobody else's is wanted
+                for p, a in itertools.islice(known.items(), MAX_LEARNT_PER_HELLO):
+                    if isinstance(p, str) and p != self.peer_id and isinstance(a, (list, tuple)):
+                        self._learn_addrs(p, [x for x in a if isinstance(x, str)][:16])
+            topics = frame.get("topics", [])
+            self._peer_topics[peer] = {t_ for t_ in topics[:MAX_TOPICS_PER_PEER] if isinstance(t_, str)} \
+                if isinstance(topics, (list, tuple)) else set()
             if frame.get("dht"):
                 self._bootstrapped.set()
                 self.kad.add(peer, list(frame.get("addrs") or []), connected=True)
@@ -869,7 +907,9 @@ class Network:
                     err = frame.get("error", "request failed")
                     fut.set_exception(NoHandler(err) if frame.get("nohandler") else RequestFailed(err))
         elif t == "sub":
-            self._peer_topics.setdefault(src, set()).add(frame["topic"])
+            mine = self._peer_topics.setdefault(src, set())
+            if isinstance(frame.get("topic"), str) and len(frame["topic"]) <= 256 and len(mine) < MAX_TOPICS_PER_PEER:
+                mine.add(frame["topic"])
         elif t == "unsub":
             self._peer_topics.setdefault(src, set()).discard(frame["topic"])
         elif t == "pub":

@@ -378,6 +378,57 @@ def test_tcp_links_use_mutual_tls(tmp_path):
     asyncio.run(main())
 
 
+def test_only_a_dialled_gateway_can_relay_in_other_peers_names():
+    """A relay vouches for the `src` of what it forwards, so a peer does not get that role by saying "relay": it must
+    be a peer the application dialled (a configured gateway).  An inbound peer that claims to be a relay -- and a
+    peer this node dialled on its own at an address it learnt from others -- cannot inject frames in somebody
+    else's name; nor is a stranger's peer table (`known`) taken in."""
+    import cbor2
+
+    async def main():
+        victim = Network("victim")
+        addr = await victim.listen("memory://victim")
+        got = []
+
+        async def whoami(peer, msg):
+            got.append(peer)
+            return {"peer": peer}
+
+        victim.on("/test/whoami", None, whoami)
+        rogue = Network("rogue", relay_server=True)              # announces "relay": true in its hello
+        rogue.peer_addrs["ghost"] = ["tcp://203.0.113.9:1"]       # ... and a peer table
+        raddr = await rogue.listen("memory://rogue")
+        await rogue.dial(addr)
+        assert not victim.links["rogue"].is_relay and "ghost" not in victim.peer_addrs
+        forged = {"t": "relay", "dst": "victim", "src": "scheduler",
+                  "inner": {"t": "req", "id": "r1", "proto": "/test/whoami", "payload": cbor2.dumps({})}}
+        before = victim.identity_rejections
+        await rogue.links["victim"].send(dict(forged))
+        await asyncio.sleep(0.1)
+        assert got == [] and victim.identity_rejections == before + 1
+        # the node reaches the rogue through an address it learnt (routing), not through configuration
+        await victim.disconnect("rogue")
+        await asyncio.sleep(0.05)
+        victim.peer_addrs["rogue"] = [raddr]
+        link, relayed = await victim._link_to("rogue")
+        assert not relayed and not link.is_relay
+        await rogue.links["victim"].send(dict(forged))
+        await asyncio.sleep(0.1)
+        assert got == [] and victim.identity_rejections == before + 2
+        # a gateway the application dials keeps the role
+        gw = Network("gw", relay_server=True)
+        gaddr = await gw.listen("memory://gw")
+        await victim.dial(gaddr)
+        other = Network("other")
+        await other.dial(gaddr)
+        assert victim.links["gw"].is_relay
+        assert (await other.request("victim", "/test/whoami", {}))["peer"] == "other" and got == ["other"]
+        for n in (victim, rogue, gw, other):
+            await n.close()
+
+    asyncio.run(main())
+
+
 def test_peer_identity_is_bound_to_the_certificate(tmp_path):
     """A node with a VALID certificate of the trusted CA cannot speak under another node's peer id: its hello
     is refused (the id must be the one derived from its certificate key), a relay stamps the id it
