@@ -429,6 +429,8 @@ class Network:
         self._pub_raw = b""
         self._last_seq = 0
         self._dcutr_served: Dict[str, float] = {}
+        self._seen_swept = 0.0
+        self._pulls_active: Dict[str, int] = {}
         self.gossip_rejections = 0
         if tls and tls.get("key_pem"):
             try:
@@ -1131,10 +1133,14 @@ class Network:
             return
         now = time.monotonic()
         self._seen_msgs[mid] = now
-        if len(self._seen_msgs) > 4096:
+        if len(self._seen_msgs) > 4096 and now - self._seen_swept > 1.0:
+            self._seen_swept = now
             for k, v in list(self._seen_msgs.items()):
                 if now - v > 60:
                     del self._seen_msgs[k]
+        if len(self._seen_msgs) > 65536:                  # a flood inside the window: the oldest ids go
+            for k in list(itertools.islice(self._seen_msgs, 32768)):
+                del self._seen_msgs[k]
         for q in self._subs.get(frame["topic"], []):
             if q.full():            # bounded fan-out like broadcast::channel(5): drop the oldest
                 try:
@@ -1451,6 +1457,16 @@ class Network:
                 st.discard()
         elif proto == "/hypha-tensor-stream/pull":
             handler = self._pull_handlers.get(proto)
+            # at most STREAM_ACCEPT_LIMIT pulls in service per peer (stream_pull.rs:71): each holds a task, an open
+            # file and a window of chunks
+            if self._pulls_active.get(src, 0) >= STREAM_ACCEPT_LIMIT:
+                try:
+                    await self._send_to(src, {"t": "stream_close", "sid": sid, "proto": proto,
+                                              "error": f"more than {STREAM_ACCEPT_LIMIT} pull streams at once"}, proto)
+                except NetworkError:
+                    pass
+                return
+            self._pulls_active[src] = self._pulls_active.get(src, 0) + 1
             self._spawn(self._serve_pull(src, sid, frame.get("header"), handler))
 
     async def _serve_pull(self, src: str, sid: str, header: Any, handler) -> None:
@@ -1478,6 +1494,11 @@ class Network:
                 pass
         finally:
             self._stream_credits.pop(sid, None)
+            left = self._pulls_active.get(src, 1) - 1
+            if left > 0:
+                self._pulls_active[src] = left
+            else:
+                self._pulls_active.pop(src, None)
 
     async def stream_push(self, peer: str, source, job_id: Optional[str] = None, header: Any = None) -> int:
         """Push ``source`` (bytes or a file path) to ``peer``; returns bytes sent."""

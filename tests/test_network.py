@@ -283,6 +283,36 @@ def test_pull_stream():
     run(main())
 
 
+def test_pull_streams_in_service_are_limited_per_peer():
+    """A data node serves at most `STREAM_ACCEPT_LIMIT` pull streams of one peer at a time (stream_pull.rs:71); the
+    next one is refused with a reason, and the slot is free again when one of them finishes."""
+    from hypha_b200.transport.network import STREAM_ACCEPT_LIMIT, StreamAborted
+
+    async def main():
+        a, b = await pair()
+        gate = asyncio.Event()
+
+        async def serve(peer, header):
+            await gate.wait()
+            return b"x" * 10
+
+        a.serve_pull(serve)
+        held = [await b.stream_pull("A", {"i": i}) for i in range(STREAM_ACCEPT_LIMIT)]
+        await asyncio.sleep(0.05)
+        assert a._pulls_active == {"B": STREAM_ACCEPT_LIMIT}
+        extra = await b.stream_pull("A", {"i": "one too many"})
+        with pytest.raises(StreamAborted, match="pull streams at once"):
+            await extra.read_all()
+        gate.set()
+        for st in held:
+            assert await st.read_all() == b"x" * 10
+        await asyncio.sleep(0.05)
+        assert a._pulls_active == {}
+        assert await (await b.stream_pull("A", {"i": "again"})).read_all() == b"x" * 10
+        await a.close(); await b.close()
+    run(main())
+
+
 def test_batched_count_and_time_windows():
     from hypha_b200.transport.utils import Batched
 
