@@ -20,6 +20,7 @@ from typing import Iterable, List, Optional, Sequence, Tuple
 K = 20                  # bucket size
 ALPHA = 3               # parallelism of an iterative lookup
 REPLICATION = 3         # servers a record is stored on
+REFRESH_BUCKETS = 8     # buckets refreshed by a lookup of their own (the 8 far ones hold 255/256 of all ids)
 
 RESERVED_CIDRS: Tuple[str, ...] = (
     "0.0.0.0/8", "10.0.0.0/8", "100.64.0.0/10", "127.0.0.0/8", "169.254.0.0/16", "172.16.0.0/12", "192.0.0.0/24",
@@ -76,6 +77,7 @@ class RoutingTable:
         self.cidr = cidr or CidrFilter()
         self._t = load_core().KadTable(self_id, k)
         self.rejected_by_cidr = 0
+        self._refresh: List[str] = []
 
     @property
     def buckets(self) -> List[List[str]]:
@@ -116,6 +118,31 @@ class RoutingTable:
 
     def closest(self, key: str, n: int = K, include_self: bool = False) -> List[str]:
         return list(self._t.closest(key, n, include_self))
+
+    def refresh_keys(self, buckets: int = REFRESH_BUCKETS) -> List[str]:
+        """One lookup key per bucket ``0 .. buckets-1``: a string whose hashed id shares exactly ``i`` leading bits with
+        this node's id, i.e. falls into bucket ``i``'s range.  Kademlia refreshes a bucket by looking up a random id
+        inside it; ids here are hashes of strings, so the string is found by trial (2^(i+1) hashes on average -- the
+        far buckets, which hold almost all of a network, cost a handful; the near ones are covered by the lookup of
+        the node's own id).  Computed once per node."""
+        if len(self._refresh) < buckets:
+            me = key_id(self.self_id)
+            want = set(range(len(self._refresh), buckets))
+            found: dict = {}
+            n = 0
+            while want and n < (1 << (buckets + 4)):
+                s = f"hypha-kad-refresh/{self.self_id}/{n}"
+                n += 1
+                x = key_id(s) ^ me
+                i = 256 - x.bit_length()               # length of the common prefix
+                if i in want:
+                    want.discard(i)
+                    found[i] = s
+            for i in range(len(self._refresh), buckets):
+                if i not in found:
+                    break
+                self._refresh.append(found[i])
+        return list(self._refresh[:buckets])
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -1335,10 +1335,14 @@ class Network:
         servers that are closest NOW -- a gateway that joined or restarted since gets its copy without the publisher
         noticing.  Returns counters for logs and tests."""
         before = len(self.kad)
-        try:
-            await self.find_closest_peers(self.peer_id, timeout=timeout)
-        except NetworkError:
-            pass
+        refreshed = 0
+        # the node's own id (its neighbourhood), then one id inside each of the far buckets (kad's bucket refresh)
+        for key in [self.peer_id] + self.kad.refresh_keys():
+            try:
+                await self.find_closest_peers(key, timeout=timeout)
+                refreshed += 1
+            except NetworkError:
+                pass
         republished = 0
         for key, value in list(self._published.items()):
             try:
@@ -1349,6 +1353,7 @@ class Network:
         for key in list(self._provided):
             await self.provide(key)
         return {"servers_known": len(self.kad), "servers_learnt": len(self.kad) - before, "republished": republished,
+                "lookups": refreshed,
                 "provided": len(self._provided)}
 
     def start_dht_maintenance(self, interval_s: float = 300.0) -> asyncio.Task:

@@ -340,6 +340,10 @@ def test_dht_maintenance_republishes_to_a_gateway_that_joined_later():
         out = await data.dht_maintain_once()
         await asyncio.sleep(0.2)
         assert out["republished"] == 1 and out["servers_learnt"] >= 1 and "g2" in data.kad
+        # own id + one id inside each of the far buckets (bucket refresh)
+        keys = data.kad.refresh_keys()
+        assert out["lookups"] == 1 + len(keys) and [data.kad._t.bucket_index(k) for k in keys] == list(range(len(keys)))
+        assert len(keys) == len(set(keys)) >= 8 and data.kad.refresh_keys() == keys
         assert g2._records["dataset"] == (b"v1", "data") and "data" in g2._providers["dataset"]
         # the timer variant
         await data.put_record("dataset", b"v2")
