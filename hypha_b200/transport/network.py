@@ -430,6 +430,8 @@ class Network:
         self._last_seq = 0
         self._dcutr_served: Dict[str, float] = {}
         self._seen_swept = 0.0
+        self._relay_ctr = 0
+        self._relay_seen: Dict[str, list] = {}           # sender -> [floor, counters seen] of signed relayed frames
         self._pulls_active: Dict[str, int] = {}
         self.gossip_rejections = 0
         if tls and tls.get("key_pem"):
@@ -812,8 +814,76 @@ class Network:
     async def _send_to(self, peer: str, frame: dict, protocol: str) -> None:
         link, relayed = await self._link_to(peer)
         if relayed:
-            frame = {"t": "relay", "dst": peer, "src": self.peer_id, "inner": frame}
+            frame = self._seal_relayed(peer, frame)
         await self._send(link, frame, protocol)
+
+    # -- frames that travel through a relay ------------------------------------------------------------------------------
+    @staticmethod
+    def _relay_digest(src: str, dst: str, ctr: int, raw: bytes) -> bytes:
+        import hashlib
+
+        h = hashlib.sha256()
+        for part in (b"hypha-relay-v1", src.encode(), dst.encode(), int(ctr).to_bytes(8, "little"), bytes(raw)):
+            h.update(len(part).to_bytes(4, "little"))
+            h.update(part)
+        return h.digest()
+
+    def _seal_relayed(self, dst: str, frame: dict) -> dict:
+        """The envelope of a frame that goes through a relay.  A node with a key signs sender, receiver, a counter
+        and the encoded frame: the receiver then knows who sent it without having to believe the relay (in the
+        reference a relayed connection is a libp2p circuit with its own end-to-end handshake).  The counter is the
+        sender's clock in microseconds, strictly increasing -- it survives a restart of the sender."""
+        if self._sign_key is None:
+            return {"t": "relay", "dst": dst, "src": self.peer_id, "inner": frame}
+        raw = cbor2.dumps(frame)
+        self._relay_ctr = max(int(time.time() * 1e6), self._relay_ctr + 1)
+        return {"t": "relay", "dst": dst, "src": self.peer_id, "raw": raw, "ctr": self._relay_ctr, "pub": self._pub_raw,
+                "sig": self._sign_key.sign(self._relay_digest(self.peer_id, dst, self._relay_ctr, raw))}
+
+    def _open_relayed(self, frame: dict, link: Link) -> Optional[dict]:
+        """The inner frame of a relayed envelope addressed to this node, or None when it is not to be believed.
+
+        Signed envelope: valid iff the key's peer id is the claimed sender, the signature covers (sender, this node,
+        counter, frame) and the counter was not seen before (a window of the 1024 most recent per sender: concurrent
+        sends may overtake each other).  It may arrive over any identified link.  Unsigned envelope: only outside
+        strict mode (no PKI), and only from a relay this node trusts (`dial(trust_relay=True)`), which vouches for
+        the sender id it authenticated on its own link."""
+        src = frame.get("src")
+        if not isinstance(src, str) or link.peer_id is None:
+            return None
+        if frame.get("raw") is not None and frame.get("sig") and frame.get("pub"):
+            try:
+                from cryptography.hazmat.primitives.asymmetric.ed25519 import Ed25519PublicKey
+
+                from .utils import peer_id_from_public_bytes
+
+                raw, ctr = bytes(frame["raw"]), int(frame["ctr"])
+                if peer_id_from_public_bytes(bytes(frame["pub"])) != src:
+                    return None
+                Ed25519PublicKey.from_public_bytes(bytes(frame["pub"])).verify(
+                    bytes(frame["sig"]), self._relay_digest(src, self.peer_id, ctr, raw))
+            except Exception:
+                return None
+            seen = self._relay_seen.get(src)
+            if seen is None:
+                if len(self._relay_seen) >= 4096:
+                    self._relay_seen.pop(next(iter(self._relay_seen)))
+                seen = self._relay_seen[src] = [0, set()]              # [floor, recent counters]
+            if ctr <= seen[0] or ctr in seen[1]:
+                return None                                             # replayed
+            seen[1].add(ctr)
+            if len(seen[1]) > 1024:
+                keep = sorted(seen[1])[-512:]
+                seen[0], seen[1] = keep[0] - 1, set(keep)
+            try:
+                inner = cbor2.loads(raw)
+            except Exception:
+                return None
+            return inner if isinstance(inner, dict) else None
+        if self.strict_gossip or not getattr(link, "is_relay", False):
+            return None
+        inner = frame.get("inner")
+        return inner if isinstance(inner, dict) else None
 
     # -- frame dispatch -------------------------------------------------------------------------------
     async def _on_frame(self, frame: dict, link: Link, src_override: Optional[str] = None,
@@ -888,10 +958,11 @@ class Network:
         elif t == "relay":
             dst = frame["dst"]
             if dst == self.peer_id:
-                # only a relay server may speak for somebody else, and what it vouches for is the id it
-                # authenticated on ITS link (it overwrites `src` below); anything else is dropped
-                if getattr(link, "is_relay", False) and link.peer_id is not None:
-                    await self._on_frame(frame["inner"], link, frame["src"], size)
+                # who sent it: the sender's own signature under a PKI, else the word of a relay this node trusts
+                # (which stamps the id it authenticated on ITS link, see below); anything else is dropped
+                inner = self._open_relayed(frame, link)
+                if inner is not None:
+                    await self._on_frame(inner, link, frame["src"], size)
                 else:
                     self.identity_rejections += 1
             elif self.relay_server and dst in self.links and link.peer_id is not None:

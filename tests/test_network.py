@@ -504,7 +504,24 @@ def test_peer_identity_is_bound_to_the_certificate(tmp_path):
                          "inner": {"t": "req", "id": "r1", "proto": "/test/whoami", "payload": __import__("cbor2").dumps({})}})
         await asyncio.sleep(0.3)
         assert "dataset" not in gw._records and gw.identity_rejections == 2
-        assert got == [ids["mallory"]]                 # the relay vouched for the id IT authenticated, not the claimed one
+        # under a PKI the receiver believes the SENDER's signature, not the relay: an unsigned envelope is dropped
+        # (the relay had stamped mallory's id on it) ...
+        assert got == [] and sched.identity_rejections == 1
+        # ... even a relay that plays along cannot pass her envelope off as the worker's: her signature does not
+        # cover that name ...
+        forged = mal._seal_relayed(ids["sched"], {"t": "req", "id": "r2", "proto": "/test/whoami",
+                                                  "payload": __import__("cbor2").dumps({})})
+        await gw.links[ids["sched"]].send(dict(forged, src=ids["worker"]))
+        await asyncio.sleep(0.2)
+        assert got == [] and sched.identity_rejections == 2
+        # ... her own request through the relay is served under her own id, once: a replayed copy is dropped
+        assert (await mal.request(ids["sched"], "/test/whoami", {}))["peer"] == ids["mallory"]
+        sealed = mal._seal_relayed(ids["sched"], {"t": "req", "id": "r3", "proto": "/test/whoami",
+                                                  "payload": __import__("cbor2").dumps({})})
+        await link.send(dict(sealed))
+        await link.send(dict(sealed))
+        await asyncio.sleep(0.3)
+        assert got == [ids["mallory"]] * 2 and sched.identity_rejections == 3
         for n in (gw, sched, imp, mal):
             await n.close()
 
