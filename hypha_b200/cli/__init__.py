@@ -55,6 +55,22 @@ def build_parser(role: str) -> argparse.ArgumentParser:
         r.add_argument("--status-bridge", default=None)
     if role == "data":
         r.add_argument("--dataset-path", default=None)
+    if role == "data":
+        pp = sub.add_parser("prepare", help="cut a token corpus into the slice files a data node serves",
+                            description="Pack a pre-tokenised corpus (.npy | .bin | .safetensors) or text (.txt | "
+                                        ".jsonl with a local tokenizer) into samples of --seq-len ids and write "
+                                        "them as safetensors slices of --samples-per-slice rows into --output; "
+                                        "point `dataset_path` of a data node at that directory.")
+        pp.add_argument("source", help="corpus file")
+        pp.add_argument("-o", "--output", required=True, help="slice directory to create (its name = dataset name)")
+        pp.add_argument("--seq-len", type=int, required=True)
+        pp.add_argument("--samples-per-slice", type=int, default=1024)
+        pp.add_argument("--dtype", default="uint16", help="id type of a .bin corpus (uint16 | uint32 | int32 | int64)")
+        pp.add_argument("--tokenizer", default=None, help="local directory of a Hugging Face tokenizer (text input)")
+        pp.add_argument("--vocab-size", type=int, default=None, help="refuse ids outside 0..vocab-1")
+        pp.add_argument("--shuffle-seed", type=int, default=None, help="permute the samples before slicing")
+        pp.add_argument("--no-labels", action="store_true", help="write input_ids only")
+        pp.add_argument("--drop-last", action="store_true", help="drop a final slice shorter than the others")
     return p
 
 
@@ -117,6 +133,19 @@ def main(role: str, argv: Optional[List[str]] = None) -> int:
         with open(ns.output, "w") as f:
             f.write(C.to_toml(cfg))
         print(f"wrote {ns.output}")
+        return 0
+    if ns.command == "prepare":
+        from ..executor.dataset import load_token_corpus, write_token_slices
+
+        try:
+            tokens = load_token_corpus(ns.source, dtype=ns.dtype, tokenizer=ns.tokenizer)
+            summary = write_token_slices(tokens, ns.output, ns.seq_len, ns.samples_per_slice,
+                                         with_labels=not ns.no_labels, vocab_size=ns.vocab_size,
+                                         shuffle_seed=ns.shuffle_seed, drop_last=ns.drop_last)
+        except (ValueError, OSError) as exc:
+            print(f"hypha-data prepare: {exc}", file=sys.stderr)
+            return 2
+        print(json.dumps(summary))
         return 0
     if ns.command == "probe":
         ok = asyncio.run(roles.probe(ns.address, ns.timeout))

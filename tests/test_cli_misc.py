@@ -420,3 +420,68 @@ def test_binary_release_roundtrip(tmp_path):
     r = subprocess.run(["sh", os.path.join(root, "install.sh"), "--from-release", str(bad)], env=env, capture_output=True,
                        text=True, timeout=120, cwd=str(tmp_path))
     assert r.returncode != 0 and "sha256 mismatch" in (r.stdout + r.stderr)
+
+
+def test_hypha_data_prepare_cuts_a_corpus_into_slices(tmp_path, capsys):
+    """`hypha-data prepare`: a flat token stream (.bin / .npy), packed samples or text become the slice directory a
+    data node serves -- rows of `seq_len` ids, `samples_per_slice` per file, labels = inputs, ids range-checked."""
+    import json
+
+    import numpy as np
+    import torch
+    from safetensors.torch import load_file
+
+    from hypha_b200.cli import main
+    from hypha_b200.data import dataset_files
+    from hypha_b200.executor.dataset import IterableStreamDataSet
+
+    stream = np.arange(10 * 16 + 5, dtype=np.uint16) % 50
+    src = tmp_path / "corpus.bin"
+    stream.tofile(src)
+    out = tmp_path / "toyset"
+    assert main("data", ["prepare", str(src), "-o", str(out), "--seq-len", "16", "--samples-per-slice", "4",
+                         "--vocab-size", "50"]) == 0
+    summary = json.loads(capsys.readouterr().out)
+    assert summary == {"dataset": "toyset", "num_slices": 3, "samples": 10, "seq_len": 16, "samples_per_slice": 4,
+                       "tokens": 160, "max_token_id": 49, "inputs": ["input_ids", "labels"]}
+    assert json.load(open(str(out) + ".json")) == summary
+    files = dataset_files(str(out))
+    assert [os.path.basename(f) for f in files] == ["slice-00000.safetensors", "slice-00001.safetensors",
+                                                    "slice-00002.safetensors"]
+    rows = list(IterableStreamDataSet(iter(files), ["input_ids", "labels"]))
+    assert len(rows) == 10 and all(r["input_ids"].shape == (16,) and torch.equal(r["input_ids"], r["labels"]) for r in rows)
+    assert torch.equal(torch.cat([r["input_ids"] for r in rows]), torch.from_numpy(stream[:160].astype(np.int64)))
+    # refusals: a directory that already holds files, ids outside the vocabulary, a corpus shorter than one sample
+    assert main("data", ["prepare", str(src), "-o", str(out), "--seq-len", "16"]) == 2
+    assert main("data", ["prepare", str(src), "-o", str(tmp_path / "v"), "--seq-len", "16", "--vocab-size", "10"]) == 2
+    assert main("data", ["prepare", str(src), "-o", str(tmp_path / "s"), "--seq-len", "4096"]) == 2
+    err = capsys.readouterr().err
+    assert "not empty" in err and "outside the vocabulary" in err and "shorter than one sample" in err
+    # packed .npy samples, shuffled deterministically, last short slice dropped, no labels
+    packed = np.arange(9 * 8, dtype=np.int64).reshape(9, 8)
+    np.save(tmp_path / "packed.npy", packed)
+    out2 = tmp_path / "packedset"
+    assert main("data", ["prepare", str(tmp_path / "packed.npy"), "-o", str(out2), "--seq-len", "8",
+                         "--samples-per-slice", "4", "--shuffle-seed", "1", "--no-labels", "--drop-last"]) == 0
+    s2 = json.loads(capsys.readouterr().out)
+    assert s2["num_slices"] == 2 and s2["samples"] == 8 and s2["inputs"] == ["input_ids"]
+    got = torch.cat([load_file(f)["input_ids"] for f in dataset_files(str(out2))])
+    assert sorted(got[:, 0].tolist()) != got[:, 0].tolist() and set(got[:, 0].tolist()) <= set(packed[:, 0].tolist())
+    assert main("data", ["prepare", str(tmp_path / "packed.npy"), "-o", str(tmp_path / "w"), "--seq-len", "16"]) == 2
+    # text needs a tokenizer (a local directory: nothing is downloaded); documents are joined by the EOS token
+    (tmp_path / "t.txt").write_text("hello world\nworld again hello\n")
+    assert main("data", ["prepare", str(tmp_path / "t.txt"), "-o", str(tmp_path / "t"), "--seq-len", "4"]) == 2
+    capsys.readouterr()
+    from tokenizers import Tokenizer, models, pre_tokenizers
+    from transformers import PreTrainedTokenizerFast
+
+    tk = Tokenizer(models.WordLevel({"<eos>": 0, "hello": 1, "world": 2, "again": 3, "[UNK]": 4}, unk_token="[UNK]"))
+    tk.pre_tokenizer = pre_tokenizers.Whitespace()
+    PreTrainedTokenizerFast(tokenizer_object=tk, eos_token="<eos>", unk_token="[UNK]").save_pretrained(str(tmp_path / "tok"))
+    (tmp_path / "t.jsonl").write_text('{"text": "hello world"}\n\n{"text": "world again hello"}\n')
+    for name in ("t.txt", "t.jsonl"):
+        dst = tmp_path / ("text-" + name.split(".")[1])
+        assert main("data", ["prepare", str(tmp_path / name), "-o", str(dst), "--seq-len", "7", "--tokenizer",
+                             str(tmp_path / "tok")]) == 0
+        assert json.loads(capsys.readouterr().out)["samples"] == 1
+        assert load_file(dataset_files(str(dst))[0])["input_ids"].tolist() == [[1, 2, 0, 2, 3, 1, 0]]
