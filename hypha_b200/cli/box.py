@@ -47,10 +47,27 @@ def build_parser() -> argparse.ArgumentParser:
                    help="gradient accumulation: micro-batches per inner step ([scheduler.job.precision] micro_batches)")
     r.add_argument("--main-grad", choices=["fp32", "bf16"], default="fp32",
                    help="where micro-batch gradients are summed ([scheduler.job.precision] main_grad)")
+    r.add_argument("--checkpoint-dir", default=None,
+                   help="write a job checkpoint after every --checkpoint-every-th round ([scheduler.job.checkpoint] dir)")
+    r.add_argument("--checkpoint-every", type=int, default=1)
+    r.add_argument("--resume", action="store_true", help="continue from the newest checkpoint in --checkpoint-dir")
+    r.add_argument("--export", default=None, metavar="DIR",
+                   help="after the run, write the trained model as a Hugging Face directory (needs --checkpoint-dir)")
     r.add_argument("--job", default=None, help="extra [scheduler.job] keys as JSON (merged last)")
     r.add_argument("--work-dir", default=None, help="scratch directory (default: a temporary one, removed at exit)")
     r.add_argument("--timeout", type=float, default=3600.0)
     r.add_argument("--verbose", action="store_true", help="echo executor output")
+    e = sub.add_parser("export", help="turn a job checkpoint into a model directory `transformers` loads",
+                       description="Rebuild the global model of a job checkpoint ([scheduler.job.checkpoint] dir) -- "
+                                   "theta_0 + cumulative update of a parameter-server job, theta_prev of a collective "
+                                   "job, flat parameters + fp32 shards of the fused GPU engine -- and write "
+                                   "model.safetensors under Hugging Face names next to config.json.")
+    e.add_argument("--checkpoint", required=True, help="checkpoint directory of the job")
+    e.add_argument("--model", required=True, help="model directory the job trained (config.json [+ model.safetensors])")
+    e.add_argument("-o", "--output", required=True)
+    e.add_argument("--round", type=int, default=None, help="round to export (default: the newest)")
+    e.add_argument("--dtype", choices=["bf16", "fp16", "fp32"], default=None)
+    e.add_argument("--type", default="causal-lm", help="model type of the job ([scheduler.job.model] type)")
     return p
 
 
@@ -103,6 +120,13 @@ def run(args) -> int:
                       "parameter_server": {"gpu": 0.0, "cpu": 1.0, "memory": 1.0, "storage": 0.0},
                       "worker_price": {"bid": 1.0, "max": 2.0}, "parameter_server_price": {"bid": 1.0, "max": 2.0}},
     }
+    if args.export and not args.checkpoint_dir:
+        print("hypha-box: --export needs --checkpoint-dir (the model is rebuilt from the job checkpoint)", file=sys.stderr)
+        return 2
+    if args.checkpoint_dir:
+        os.makedirs(args.checkpoint_dir, exist_ok=True)
+        job["checkpoint"] = {"dir": os.path.abspath(args.checkpoint_dir), "every": args.checkpoint_every,
+                             "resume": bool(args.resume)}
     if args.job:
         _deep_merge(job, json.loads(args.job))
     tmp = args.work_dir or tempfile.mkdtemp(prefix="hypha-box-")
@@ -119,10 +143,21 @@ def run(args) -> int:
                                      seq_len=args.seq_len, vocab_size=vocab)
 
     log = (lambda m: print(m, file=sys.stderr, flush=True)) if args.verbose else None
+    exported = None
     try:
         outcome, sink, logs, _ = asyncio.run(run_loopback_job(
             tmp, repo=repo, write_model_config=writer, write_dataset=write_dataset, job=job, num_workers=workers,
             timeout_s=args.timeout, log=log))
+        if args.export and outcome.finished:
+            from ..export import ExportError, export_checkpoint
+
+            mdir = os.path.join(tmp, "export-model")
+            os.makedirs(mdir, exist_ok=True)
+            writer(os.path.join(mdir, "config.json"))
+            try:
+                exported = export_checkpoint(args.checkpoint_dir, mdir, args.export)
+            except ExportError as exc:
+                print(f"hypha-box: export failed: {exc}", file=sys.stderr)
     finally:
         if not args.work_dir:
             shutil.rmtree(tmp, ignore_errors=True)
@@ -131,7 +166,8 @@ def run(args) -> int:
         by_worker.setdefault(rec["worker_id"], {}).setdefault(str(rec["round"]), {})[rec["metric_name"]] = rec["value"]
     print(json.dumps({"finished": outcome.finished, "rounds": outcome.rounds, "workers": outcome.workers,
                       "removed_workers": outcome.removed_workers, "aggregation": args.aggregation, "precision": args.precision,
-                      "device": "cuda" if use_cuda else "cpu", "metrics": by_worker}))
+                      "device": "cuda" if use_cuda else "cpu", "metrics": by_worker,
+                      **({"exported": exported} if exported else {})}))
     if not outcome.finished:
         print("\n".join(logs[-30:]), file=sys.stderr)
     return 0 if outcome.finished else 1
@@ -139,6 +175,17 @@ def run(args) -> int:
 
 def main(argv: Optional[List[str]] = None) -> int:
     args = build_parser().parse_args(argv)
+    if args.command == "export":
+        from ..export import ExportError, export_checkpoint
+
+        try:
+            info = export_checkpoint(args.checkpoint, args.model, args.output, model_type=args.type, round_no=args.round,
+                                     dtype=args.dtype)
+        except (ExportError, OSError) as exc:
+            print(f"hypha-box export: {exc}", file=sys.stderr)
+            return 2
+        print(json.dumps(info))
+        return 0
     return run(args)
 
 

@@ -151,15 +151,45 @@ def test_replicated_nesterov_matches_the_reference_vector():
     assert torch.equal(loop.prev["weight"], loop.model.weight)
 
 
-def test_hypha_box_single_worker_on_cpu(capsys):
+def test_hypha_box_single_worker_on_cpu(capsys, tmp_path):
+    """... and the way out: `--checkpoint-dir` + `--export` leave a model directory that `transformers` loads, holding
+    weights that moved away from the seeded initialisation; `hypha-box export` does the same from the checkpoint."""
     import json
 
-    from hypha_b200.cli import box
+    import torch
+    import transformers
 
+    from hypha_b200.cli import box
+    from hypha_b200.models.gpt2 import GPT2Config
+
+    ck, out_dir = str(tmp_path / "ckpt"), str(tmp_path / "trained")
     rc = box.main(["run", "--model", "gpt2-tiny", "--workers", "1", "--device", "cpu", "--rounds", "2",
-                   "--samples-per-round", "16", "--batch-size", "4", "--seq-len", "32", "--timeout", "240"])
+                   "--samples-per-round", "16", "--batch-size", "4", "--seq-len", "32", "--timeout", "240",
+                   "--lr", "1e-2", "--checkpoint-dir", ck, "--export", out_dir])
     out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
     assert rc == 0 and out["finished"] and out["rounds"] == 2 and list(out["metrics"]) == ["worker-a"]
+    assert out["exported"]["round"] == 2 and out["exported"]["kind"] == "collective"
+    hf = transformers.GPT2LMHeadModel.from_pretrained(out_dir).eval()
+    with torch.no_grad():
+        assert torch.isfinite(hf(torch.randint(0, 100, (1, 16))).logits).all()
+    # the same through the stand-alone command, from the checkpoint and the model config
+    mdir = tmp_path / "model"
+    mdir.mkdir()
+    GPT2Config.tiny().to_json(str(mdir / "config.json"))
+    assert box.main(["export", "--checkpoint", ck, "--model", str(mdir), "-o", str(tmp_path / "again"), "--dtype", "fp32"]) == 0
+    info = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert info["round"] == 2 and info["parameters"] == sum(p.numel() for p in hf.parameters())
+    again = transformers.GPT2LMHeadModel.from_pretrained(str(tmp_path / "again"))
+    from hypha_b200.executor.model import get_model
+
+    init = get_model(str(mdir), "causal-lm", "cpu").state_dict()
+    moved = 0
+    for k, v in hf.state_dict().items():
+        assert torch.equal(v, again.state_dict()[k]), k
+        moved += int(k in init and not torch.allclose(v, init[k].float(), atol=1e-6))
+    assert moved > 10                                   # training happened to what was exported
+    assert box.main(["export", "--checkpoint", str(tmp_path / "nowhere"), "--model", str(mdir), "-o", str(tmp_path / "x")]) == 2
+    assert box.main(["run", "--model", "gpt2-tiny", "--device", "cpu", "--export", str(tmp_path / "y")]) == 2
 
 
 def test_status_pipe_runs_exactly_the_projected_number_of_batches(monkeypatch):
