@@ -30,6 +30,9 @@ def build_parser() -> argparse.ArgumentParser:
     r.add_argument("--model", default="llama-tiny",
                    help="preset (llama3-8b, llama3-1b, llama-small, llama-tiny, gpt2-tiny, gpt2-small)")
     r.add_argument("--model-config", default=None, help="path to a Hugging-Face style config.json (overrides --model)")
+    r.add_argument("--model-dir", default=None,
+                   help="Hugging Face model directory (config.json + model.safetensors or its shards + tokenizer files): "
+                        "training starts from these weights (overrides --model / --model-config)")
     r.add_argument("--workers", type=int, default=0, help="train workers (default: one per visible GPU, 2 on CPU)")
     r.add_argument("--device", choices=["auto", "cuda", "cpu"], default="auto")
     r.add_argument("--rounds", type=int, default=2, help="DiLoCo outer rounds")
@@ -71,8 +74,38 @@ def build_parser() -> argparse.ArgumentParser:
     return p
 
 
+MODEL_DIR_FILES = ("model.safetensors", "model.safetensors.index.json", "generation_config.json", "tokenizer.json",
+                   "tokenizer_config.json", "tokenizer.model", "special_tokens_map.json", "vocab.json", "merges.txt")
+
+
+def model_dir_files(model_dir: str) -> List[str]:
+    """What a job over ``model_dir`` lists as its model `filenames`: the config, the weights (one file or every shard of
+    the index) and the tokenizer files that are there."""
+    if not os.path.isfile(os.path.join(model_dir, "config.json")):
+        raise FileNotFoundError(f"{model_dir} has no config.json")
+    names = ["config.json"] + [n for n in MODEL_DIR_FILES if os.path.isfile(os.path.join(model_dir, n))]
+    index = os.path.join(model_dir, "model.safetensors.index.json")
+    if os.path.isfile(index):
+        names += sorted(set(json.load(open(index)).get("weight_map", {}).values()))
+    return names
+
+
 def _write_model_config(args) -> tuple:
     """Returns (repo name, writer(path), vocab_size)."""
+    if getattr(args, "model_dir", None):
+        src = os.path.abspath(args.model_dir)
+        meta = json.load(open(os.path.join(src, "config.json")))
+
+        def link_all(cfg_path: str) -> None:
+            # the registry entry of the job's model: links, not copies (an 8B checkpoint is 16 GB)
+            dst = os.path.dirname(cfg_path)
+            for n in model_dir_files(src):
+                target = os.path.join(dst, n)
+                if os.path.lexists(target):
+                    os.unlink(target)
+                os.symlink(os.path.join(src, n), target)
+
+        return f"local/{os.path.basename(src.rstrip('/')) or 'model'}", link_all, int(meta.get("vocab_size", 32000))
     if args.model_config:
         meta = json.load(open(args.model_config))
         return "local/custom", (lambda p: shutil.copyfile(args.model_config, p)), int(meta.get("vocab_size", 32000))
@@ -107,7 +140,8 @@ def run(args) -> int:
     os.environ["HYPHA_EXECUTOR_DEVICE"] = "cuda" if use_cuda else "cpu"
     repo, writer, vocab = _write_model_config(args)
     job = {
-        "model": {"repository": repo, "filenames": ["config.json"], "type": "causal-lm", "input_names": ["input_ids", "labels"]},
+        "model": {"repository": repo, "filenames": model_dir_files(args.model_dir) if args.model_dir else ["config.json"],
+                  "type": "causal-lm", "input_names": ["input_ids", "labels"]},
         "preprocessor": None,
         "dataset": {"dataset": os.path.basename(os.path.normpath(args.dataset_path)) if args.dataset_path else "synthetic-tokens"},
         "rounds": {"avg_samples_between_updates": args.samples_per_round, "update_rounds": args.rounds,
@@ -153,7 +187,7 @@ def run(args) -> int:
 
             mdir = os.path.join(tmp, "export-model")
             os.makedirs(mdir, exist_ok=True)
-            writer(os.path.join(mdir, "config.json"))
+            writer(os.path.join(mdir, "config.json"))        # --model-dir: links to the weights the job started from
             try:
                 exported = export_checkpoint(args.checkpoint_dir, mdir, args.export)
             except ExportError as exc:

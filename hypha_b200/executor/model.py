@@ -70,6 +70,36 @@ class _LlamaAdapter(torch.nn.Module):
         return {"loss": self.net(input_ids, shifted, ignore_index=-100, n_valid=n_valid)}
 
 
+def weight_files(model_path: str) -> list:
+    """The safetensors files of a model directory: ``model.safetensors``, or the shards named by
+    ``model.safetensors.index.json`` (how checkpoints beyond a few GB are published)."""
+    single = os.path.join(model_path, "model.safetensors")
+    if os.path.exists(single):
+        return [single]
+    index = os.path.join(model_path, "model.safetensors.index.json")
+    if os.path.exists(index):
+        names = sorted(set(json.load(open(index)).get("weight_map", {}).values()))
+        missing = [n for n in names if not os.path.exists(os.path.join(model_path, n))]
+        if missing:
+            raise FileNotFoundError(f"{index} names {missing[:3]} which are not in {model_path}: list every shard in "
+                                    "the job's model `filenames`")
+        return [os.path.join(model_path, n) for n in names]
+    return []
+
+
+def load_weights(model_path: str):
+    """State dict of a model directory (all shards merged), or None when it holds no weights."""
+    files = weight_files(model_path)
+    if not files:
+        return None
+    from safetensors.torch import load_file
+
+    sd: dict = {}
+    for f in files:
+        sd.update(load_file(f))
+    return sd
+
+
 def get_model(model_path: str, model_type: str, device: str = "cpu") -> torch.nn.Module:
     cfg_path = os.path.join(model_path, "config.json")
     if not os.path.exists(cfg_path):
@@ -103,10 +133,9 @@ def _build_model(model_path: str, model_type: str, device: str, meta: dict, fami
         c = LlamaConfig.from_hf_dict(meta)          # llama / mistral -> the sm_100a kernels (see its docstring)
         dtype = torch.bfloat16 if device.startswith("cuda") else torch.float32
         inner = LlamaForCausalLM(c, device=device, dtype=dtype)
-        if os.path.exists(weights):
-            from safetensors.torch import load_file
-
-            inner.load_hf_state_dict(load_file(weights))
+        sd = load_weights(model_path)
+        if sd is not None:
+            inner.load_hf_state_dict(sd)
         return _LlamaAdapter(inner)
     else:
         import transformers
@@ -115,10 +144,9 @@ def _build_model(model_path: str, model_type: str, device: str, meta: dict, fami
         if cls_name is None:
             raise RuntimeError(f"model type {model_type!r} not supported")
         return getattr(transformers, cls_name).from_pretrained(model_path)
-    if os.path.exists(weights):
-        from safetensors.torch import load_file
-
-        net.load_state_dict(load_file(weights), strict=False)
+    sd = load_weights(model_path)
+    if sd is not None:
+        net.load_state_dict(sd, strict=False)
     return net.to(device)
 
 

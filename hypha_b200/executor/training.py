@@ -430,12 +430,13 @@ class _TrainerEngine:
             group = PeerGroup.from_torch_distributed(dev_index) if coll["world"] > 1 else None
         self.trainer = DiLoCoTrainer.create(cfg, adamw=adamw, diloco=diloco, group=group, device=dev_index,
                                             seed=int(meta.get("seed", 0)), scheduler=config.get("scheduler"))
-        weights = os.path.join(local, "model.safetensors")
-        if os.path.exists(weights):
-            from safetensors.torch import load_file
+        from .model import load_weights
 
-            self.trainer.model.load_hf_state_dict(load_file(weights))
+        sd = load_weights(local)                    # model.safetensors, or the shards of its index
+        if sd is not None:
+            self.trainer.model.load_hf_state_dict(sd)
             self.trainer.opt.master.copy_(self.trainer.model.flat.data)
+            del sd
         self.backend = self.trainer.outer.backend
         self.micro_batches, self.main_grad_type = accumulation_of(config)
 

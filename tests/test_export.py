@@ -154,3 +154,49 @@ def test_parameter_server_update_in_flat_layout_names(tmp_path):
     save_job_checkpoint(ck, 2, str(tmp_path / "cum"), str(tmp_path / "mom"))
     with pytest.raises(ExportError, match="match neither"):
         export_checkpoint(ck, mdir, out)
+
+
+def test_box_fine_tunes_a_sharded_hf_checkpoint_and_exports_it(tmp_path, capsys):
+    """`hypha-box run --model-dir`: the job starts from the weights of a Hugging Face directory -- here published as
+    two shards with an index, the way large checkpoints are -- and `--export` writes the result back: after one
+    round at a tiny learning rate the exported weights are the originals plus a small step, not a re-initialisation."""
+    import transformers
+    from safetensors.torch import save_file
+
+    from hypha_b200.cli import box
+    from hypha_b200.executor.model import get_model, weight_files
+
+    mdir = tmp_path / "tiny-llama"
+    mdir.mkdir()
+    cfg = transformers.LlamaConfig(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                                   rms_norm_eps=1e-5, tie_word_embeddings=False)
+    torch.manual_seed(5)
+    hf = transformers.LlamaForCausalLM(cfg)
+    json.dump(cfg.to_dict(), open(mdir / "config.json", "w"))
+    sd = {k: v.contiguous() for k, v in hf.state_dict().items()}
+    keys = sorted(sd)
+    parts = {"model-00001-of-00002.safetensors": keys[: len(keys) // 2], "model-00002-of-00002.safetensors": keys[len(keys) // 2:]}
+    for name, ks in parts.items():
+        save_file({k: sd[k] for k in ks}, str(mdir / name))
+    json.dump({"metadata": {}, "weight_map": {k: n for n, ks in parts.items() for k in ks}},
+              open(mdir / "model.safetensors.index.json", "w"))
+    json.dump({"model_max_length": 64}, open(mdir / "tokenizer_config.json", "w"))
+    assert [os.path.basename(f) for f in weight_files(str(mdir))] == sorted(parts)
+    assert box.model_dir_files(str(mdir)) == ["config.json", "model.safetensors.index.json", "tokenizer_config.json"] + sorted(parts)
+    loaded = get_model(str(mdir), "causal-lm", "cpu")
+    assert torch.equal(loaded.net.to_hf_state_dict()["model.embed_tokens.weight"], sd["model.embed_tokens.weight"])
+    out = tmp_path / "tuned"
+    rc = box.main(["run", "--model-dir", str(mdir), "--workers", "1", "--device", "cpu", "--rounds", "1",
+                   "--samples-per-round", "8", "--batch-size", "4", "--seq-len", "32", "--lr", "1e-5", "--timeout", "240",
+                   "--checkpoint-dir", str(tmp_path / "ck"), "--export", str(out)])
+    res = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rc == 0 and res["finished"] and res["exported"]["round"] == 1
+    tuned = transformers.LlamaForCausalLM.from_pretrained(str(out)).state_dict()
+    worst = max((tuned[k].float() - v.float()).abs().max().item() for k, v in sd.items())
+    assert 0 < worst < 5e-3                       # the original weights, moved a little
+    assert os.path.isfile(out / "tokenizer_config.json")
+    # an index that names a shard which is not there is an error, not a silent random initialisation
+    os.unlink(mdir / "model-00002-of-00002.safetensors")
+    with pytest.raises(FileNotFoundError, match="not in"):
+        get_model(str(mdir), "causal-lm", "cpu")
