@@ -71,6 +71,16 @@ def build_parser() -> argparse.ArgumentParser:
     e.add_argument("--round", type=int, default=None, help="round to export (default: the newest)")
     e.add_argument("--dtype", choices=["bf16", "fp16", "fp32"], default=None)
     e.add_argument("--type", default="causal-lm", help="model type of the job ([scheduler.job.model] type)")
+    v = sub.add_parser("eval", help="next-token loss / perplexity of a model directory over a slice directory",
+                       description="Run the model of --model (a Hugging Face directory, e.g. the output of `export`) "
+                                   "over the slices of --dataset-path with the executors' model code and print "
+                                   "loss and perplexity as one JSON line.")
+    v.add_argument("--model", required=True)
+    v.add_argument("--dataset-path", required=True)
+    v.add_argument("--device", choices=["auto", "cuda", "cpu"], default="auto")
+    v.add_argument("--batch-size", type=int, default=4)
+    v.add_argument("--max-samples", type=int, default=None)
+    v.add_argument("--type", default="causal-lm")
     return p
 
 
@@ -219,6 +229,19 @@ def main(argv: Optional[List[str]] = None) -> int:
             print(f"hypha-box export: {exc}", file=sys.stderr)
             return 2
         print(json.dumps(info))
+        return 0
+    if args.command == "eval":
+        import torch
+
+        from ..export import ExportError, evaluate_model
+
+        dev = "cuda" if args.device == "cuda" or (args.device == "auto" and torch.cuda.is_available()) else "cpu"
+        try:
+            print(json.dumps(evaluate_model(args.model, args.dataset_path, model_type=args.type, device=dev,
+                                            batch_size=args.batch_size, max_samples=args.max_samples)))
+        except (ExportError, OSError) as exc:
+            print(f"hypha-box eval: {exc}", file=sys.stderr)
+            return 2
         return 0
     return run(args)
 

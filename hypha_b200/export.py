@@ -151,3 +151,43 @@ def export_checkpoint(ckpt_dir: str, model_dir: str, out_dir: str, model_type: s
             "parameters": int(sum(v.numel() for v in out.values())), "dtype": dtype or "as stored",
             "output": os.path.join(out_dir, "model.safetensors")}
     return info
+
+
+@torch.no_grad()
+def evaluate_model(model_dir: str, dataset_path: str, model_type: str = "causal-lm", device: str = "cpu",
+                   batch_size: int = 4, max_samples: Optional[int] = None) -> dict:
+    """Mean next-token loss and perplexity of the model in ``model_dir`` over the slices of ``dataset_path`` (the files a
+    data node serves), through the same model code the executors train with -- the sm_100a kernels on ``cuda``.  The loss
+    is the Hugging Face one (labels aligned with the inputs, shifted inside, -100 ignored), weighted by the number of
+    scored tokens of each batch."""
+    from .data import dataset_files
+    from .executor.dataset import IterableStreamDataSet
+    from .executor.model import get_model
+
+    files = dataset_files(dataset_path)
+    if not files:
+        raise ExportError(f"{dataset_path} holds no slices")
+    model = get_model(model_dir, model_type, device).eval()
+    loader = torch.utils.data.DataLoader(IterableStreamDataSet(iter(files), ["input_ids", "labels"]),
+                                         batch_size=batch_size)
+    total, scored, samples = 0.0, 0, 0
+    for batch in loader:
+        if max_samples is not None and samples >= max_samples:
+            break
+        if max_samples is not None:
+            batch = {k: v[: max_samples - samples] for k, v in batch.items()}
+        n = int((batch["labels"][:, 1:] != -100).sum())
+        if n == 0:
+            continue
+        out = model(**{k: v.to(device) for k, v in batch.items()})
+        loss = out["loss"] if isinstance(out, dict) else out.loss
+        total += float(loss) * n
+        scored += n
+        samples += int(batch["input_ids"].shape[0])
+    if scored == 0:
+        raise ExportError("no scored tokens in the dataset")
+    import math
+
+    mean = total / scored
+    return {"loss": mean, "perplexity": math.exp(min(mean, 50.0)), "tokens_scored": scored, "samples": samples,
+            "device": device}

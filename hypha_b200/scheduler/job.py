@@ -75,6 +75,11 @@ class DiLoCoJobRun:
         self.telemetry, self.log, self.stop = telemetry, telemetry.logger, stop
         self.get_data_provider = data_provider
         self.sink = metrics_connector or (AimConnector(status_bridge) if status_bridge else NoOpConnector())
+        if telemetry is not None and getattr(telemetry, "enabled", False):
+            # an OTLP endpoint is configured: training metrics go there as well (hypha.job.* gauges)
+            from .scheduling import FanOutConnector, OtelConnector
+
+            self.sink = FanOutConnector(self.sink, OtelConnector(telemetry))
         self.allocation_pause_s = allocation_pause_s
         self.collective = job.aggregation.mode == "collective"
         self.allocator = GreedyWorkerAllocator(net)

@@ -249,6 +249,39 @@ class AimConnector(Connector):
                 r.raise_for_status()
 
 
+class OtelConnector(Connector):
+    """Training metrics as OpenTelemetry gauges ``hypha.job.<metric>`` (attributes: ``worker``, ``round``) on the
+    scheduler's meter, next to the bandwidth counters: a deployment that ships OTLP to a collector
+    (`telemetry_endpoint`) sees loss / throughput / step times per worker without running the AIM driver.  The
+    reference forwards training metrics to AIM only (metrics_bridge.rs:126-145) and exports system metrics over OTLP
+    (metrics.rs:33-75); this joins the two."""
+
+    def __init__(self, telemetry: Any):
+        self.meter = telemetry.meter
+        self._gauges: Dict[str, Any] = {}
+
+    async def send(self, worker_id, round, name, value) -> None:
+        g = self._gauges.get(name)
+        if g is None:
+            safe = "".join(c if c.isalnum() or c in "._-" else "_" for c in str(name))[:63]
+            g = self._gauges[name] = self.meter.create_gauge(f"hypha.job.{safe}")
+        g.set(float(value), {"worker": str(worker_id), "round": int(round)})
+
+
+class FanOutConnector(Connector):
+    """Every metric to every sink; a sink that fails does not starve the others."""
+
+    def __init__(self, *sinks: Connector):
+        self.sinks = [s for s in sinks if s is not None]
+
+    async def send(self, worker_id, round, name, value) -> None:
+        for s in self.sinks:
+            try:
+                await s.send(worker_id, round, name, value)
+            except Exception:      # noqa: BLE001 - a broken sink must not stop the others
+                pass
+
+
 class MetricsBridge:
     """Fan-in of ``(peer, Metrics)`` queues -> a connector."""
 

@@ -200,3 +200,41 @@ def test_box_fine_tunes_a_sharded_hf_checkpoint_and_exports_it(tmp_path, capsys)
     os.unlink(mdir / "model-00002-of-00002.safetensors")
     with pytest.raises(FileNotFoundError, match="not in"):
         get_model(str(mdir), "causal-lm", "cpu")
+
+
+def test_eval_reports_the_hf_loss_over_a_slice_directory(tmp_path, capsys):
+    """`hypha-box eval`: token-weighted mean of the Hugging Face loss over the slices, equal to what `transformers`
+    computes for the same checkpoint and data."""
+    import math
+
+    import transformers
+    from safetensors.torch import save_file
+
+    from hypha_b200.cli import box
+    from hypha_b200.executor.dataset import write_synthetic_token_slices
+
+    mdir = tmp_path / "m"
+    mdir.mkdir()
+    cfg = transformers.LlamaConfig(vocab_size=320, hidden_size=64, intermediate_size=128, num_hidden_layers=2,
+                                   num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                                   rms_norm_eps=1e-5, tie_word_embeddings=False)
+    torch.manual_seed(9)
+    hf = transformers.LlamaForCausalLM(cfg).eval()
+    json.dump(cfg.to_dict(), open(mdir / "config.json", "w"))
+    save_file({k: v.contiguous() for k, v in hf.state_dict().items()}, str(mdir / "model.safetensors"))
+    files = write_synthetic_token_slices(str(tmp_path / "ds"), num_slices=2, samples_per_slice=5, seq_len=32, vocab_size=320)
+    assert box.main(["eval", "--model", str(mdir), "--dataset-path", str(tmp_path / "ds"), "--device", "cpu",
+                     "--batch-size", "4"]) == 0
+    got = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    from safetensors.torch import load_file
+
+    ids = torch.cat([load_file(f)["input_ids"] for f in files])
+    with torch.no_grad():
+        ref = hf(ids, labels=ids).loss.item()
+    assert got["samples"] == 10 and got["tokens_scored"] == 10 * 31
+    assert abs(got["loss"] - ref) < 1e-4 and abs(got["perplexity"] - math.exp(ref)) < 1e-1
+    assert box.main(["eval", "--model", str(mdir), "--dataset-path", str(tmp_path / "ds"), "--device", "cpu",
+                     "--max-samples", "3"]) == 0
+    assert json.loads(capsys.readouterr().out.strip().splitlines()[-1])["samples"] == 3
+    (tmp_path / "empty").mkdir()
+    assert box.main(["eval", "--model", str(mdir), "--dataset-path", str(tmp_path / "empty"), "--device", "cpu"]) == 2

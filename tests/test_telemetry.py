@@ -203,3 +203,45 @@ def test_gpu_monitor_samples_exports_and_raises_the_alarm():
 
     cfg = types.SimpleNamespace(resources=types.SimpleNamespace(gpu=0.0), device=None)
     assert start_for_worker(cfg, tel, logs.append) is None
+
+
+def test_training_metrics_become_otel_gauges():
+    """With an OTLP endpoint the scheduler's metrics bridge also records `hypha.job.<metric>` gauges (worker and round
+    as attributes); a sink that fails does not keep the others from getting the metric."""
+    import asyncio
+
+    from opentelemetry.sdk.metrics.export import InMemoryMetricReader
+
+    from hypha_b200.scheduler import FanOutConnector, MemoryConnector, OtelConnector
+    from hypha_b200.scheduler.scheduling import Connector
+
+    class Broken(Connector):
+        async def send(self, *a):
+            raise RuntimeError("sink down")
+
+    reader = InMemoryMetricReader()
+    tel = T.Telemetry("sched", metric_reader=reader)
+    mem = MemoryConnector()
+    sink = FanOutConnector(Broken(), mem, OtelConnector(tel))
+
+    async def main():
+        await sink.send("worker-a", 1, "loss", 2.5)
+        await sink.send("worker-b", 1, "loss", 2.75)
+        await sink.send("worker-a", 2, "loss", 2.0)
+        await sink.send("worker-a", 2, "samples_or_tokens_per_s", 21940.0)
+        await sink.send("worker-a", 2, "odd name/with spaces", 1.0)
+
+    asyncio.run(main())
+    got = {}
+    for rm in reader.get_metrics_data().resource_metrics:
+        for sm in rm.scope_metrics:
+            for m in sm.metrics:
+                for p in m.data.data_points:
+                    if m.name.startswith("hypha.job."):
+                        got[(m.name, p.attributes["worker"], p.attributes["round"])] = p.value
+    assert got[("hypha.job.loss", "worker-a", 1)] == 2.5 and got[("hypha.job.loss", "worker-b", 1)] == 2.75
+    assert got[("hypha.job.loss", "worker-a", 2)] == 2.0
+    assert got[("hypha.job.samples_or_tokens_per_s", "worker-a", 2)] == 21940.0
+    assert ("hypha.job.odd_name_with_spaces", "worker-a", 2) in got
+    assert len(mem.records) == 5
+    tel.shutdown()
