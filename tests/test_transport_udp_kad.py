@@ -659,3 +659,53 @@ def test_udp_reassembly_survives_any_arrival_order():
         asyncio.run(main())
 
     prop()
+
+
+def test_record_store_invariants_under_random_operations():
+    """Property: whatever sequence of puts, provider announcements and clock jumps a store sees, it stays within its
+    bounds, its per-publisher accounting matches its contents, an owner's record is never replaced by somebody else
+    while it is alive, and a publisher's sequence numbers never go backwards."""
+    from hypothesis import given, settings, strategies as st
+
+    from hypha_b200.transport import kad
+
+    ops = st.lists(st.one_of(
+        st.tuples(st.just("put"), st.integers(0, 5), st.integers(0, 3), st.integers(0, 50), st.booleans()),
+        st.tuples(st.just("prov"), st.integers(0, 5), st.integers(0, 3)),
+        st.tuples(st.just("tick"), st.floats(0.0, 80.0))), max_size=60)
+
+    @settings(max_examples=80, deadline=None)
+    @given(ops)
+    def prop(seq):
+        now = [0.0]
+        s = kad.RecordStore(ttl_s=100.0, enforce_owner=True, clock=lambda: now[0])
+        for op in seq:
+            if op[0] == "put":
+                _, k, p, sq, local = op
+                key, pub = f"k{k}", f"p{p}"
+                before = s.get(key)
+                res = s.put(key, b"v%d" % sq, pub, seq=sq, local=local)
+                after = s.get(key)
+                if before is not None and before.publisher != pub and not local:
+                    assert res == "owned" and after == before
+                if before is not None and before.publisher == pub and sq < before.seq:
+                    assert res == "stale" and after.seq == before.seq
+                if res == "stored":
+                    assert after == (b"v%d" % sq, pub) and after.seq == sq
+            elif op[0] == "prov":
+                s.add_provider(f"k{op[1]}", f"p{op[2]}")
+            else:
+                now[0] += op[1]
+            live = [s.get(k) for k in s.keys()]
+            live = [r for r in live if r is not None]
+            assert len(s) <= kad.MAX_RECORDS
+            counts = {}
+            for r in live:
+                counts[r.publisher] = counts.get(r.publisher, 0) + 1
+            for p, n in counts.items():
+                assert s._per_pub.get(p, 0) >= n          # expired-but-unswept entries may still be counted
+            s.expire()
+            assert {p: n for p, n in s._per_pub.items()} == counts
+            assert all(len(s.providers(f"k{k}")) <= kad.MAX_PROVIDERS_PER_KEY for k in range(6))
+
+    prop()
