@@ -46,7 +46,7 @@ class DiLoCoConfig:
     inner_steps: int = 100              # H
     outer_lr: float = 0.7               # scheduler_config.rs:89-92 defaults
     outer_momentum: float = 0.9
-    backend: str = "auto"               # auto | fused | nccl | local
+    backend: str = "auto"               # auto | fused | sharded | nccl | local
     num_ctas: int = 0                   # 0 = one CTA per SM
     pipeline_chunks: int = 0            # fused backend: 0 = auto (by size), 1 = plain A|B|C, K = K-deep pipeline
     link_ctas: int = 0                  # CTAs driving NVLink while the others stream HBM (0 = auto)
@@ -269,10 +269,27 @@ class DiLoCoOuter:
         dev = opt.params.device
         world = group.world if group is not None else 1
         backend = cfg.backend
+        if world == 1 and process_group is not None and backend in ("auto", "sharded"):
+            import torch.distributed as dist
+
+            world = dist.get_world_size(process_group)        # a team without peer memory: several boxes
         if backend == "auto":
-            backend = "local" if world == 1 else ("fused" if param_buf is not None else "nccl")
+            if world == 1:
+                backend = "local"
+            elif param_buf is not None and world <= 8:
+                backend = "fused"
+            else:
+                # across boxes there is no peer memory: stock collectives, outer state sharded like the fused path
+                import torch.distributed as dist
+
+                backend = "sharded" if (world > 8 and dist.is_available() and dist.is_initialized()) else "nccl"
         self.backend = backend
         self.world, self.rank = world, (group.rank if group is not None else 0)
+        if backend == "sharded":
+            import torch.distributed as dist
+
+            self.world, self.rank = dist.get_world_size(process_group), dist.get_rank(process_group)
+            world = self.world
         self.round = 0
         # membership, shard ownership and the flag-token epoch live in the native epoch table (`csrc/comm/vmm.cpp`:
         # writers publish under a sequence lock, a launch reads a consistent snapshot); one box = 8 ranks at most
@@ -285,7 +302,7 @@ class DiLoCoOuter:
         elif backend == "fused":
             if world > 8:
                 raise ValueError(f"the fused outer step covers one NVSwitch box (<= 8 ranks); got world = {world}: use "
-                                 f"backend='nccl' across boxes")
+                                 f"backend='sharded' (or 'auto') across boxes")
             assert group is not None and param_buf is not None and delta_buf is not None
             assert param_buf.local.data_ptr() == opt.params.data_ptr(), \
                 "fused outer step needs the model parameters in the symmetric buffer"
@@ -304,6 +321,19 @@ class DiLoCoOuter:
             # N=2 (nothing to save: one peer) and 12-19 % faster at N=8
             self.use_nvls = world >= 4
             load_C().set_outer_timeout_ms(int(cfg.timeout_ms))
+        elif backend == "sharded":
+            # more than one NVSwitch box (or no peer memory): reduce-scatter / all-gather of the process group, with
+            # the fp32 outer state sharded over ALL ranks as on the fused path (8 bytes x n / world per rank instead
+            # of the 8 bytes x n of the replicated "nccl" baseline) and the same numerics: the round starts from the
+            # bf16 weights every rank holds (the anchor), theta_outer / momentum stay fp32 on the shard's owner
+            self._per = (self.n + world - 1) // world
+            self._per = (self._per + 1023) // 1024 * 1024           # equal shards; the tail past n is padding
+            self.shard_begin = min(self.n, self.rank * self._per)
+            self.shard_len = max(0, min(self.n, self.shard_begin + self._per) - self.shard_begin)
+            sl = slice(self.shard_begin, self.shard_begin + self.shard_len)
+            self.theta_outer = opt.master[sl].clone()
+            self.momentum = torch.zeros(self.shard_len, dtype=torch.float32, device=dev)
+            self.anchor = opt.params.clone()
         elif backend == "nccl":
             # baseline: replicated outer state, stock collectives + unfused torch ops
             self.shard_begin, self.shard_len = 0, self.n
@@ -358,10 +388,11 @@ class DiLoCoOuter:
 
     def step(self) -> None:
         """Run one outer step; all participating ranks must call it."""
-        C = load_C()
         opt, cfg = self.opt, self.cfg
         first = int(self.round == 0)
-        s = cuda_stream()
+        if self.backend in ("local", "fused"):         # the collective backends are stream-ordered torch ops
+            C = load_C()
+            s = cuda_stream()
         if self.backend == "local":
             C.diloco_outer_local(opt.master.data_ptr(), 0, 0, self.theta_outer.data_ptr(),
                                  self.momentum.data_ptr(), opt.master.data_ptr(),
@@ -383,6 +414,8 @@ class DiLoCoOuter:
             nmem = bin(int(snap["mask"])).count("1")
             wire = 2 * sum(l for _, l, _, _ in segs) * (nmem - 1)
             self.group.counters.add("/hypha-peer-memory/outer-step", inbound=wire, outbound=wire)
+        elif self.backend == "sharded":
+            self._step_sharded(bool(first))
         else:
             import torch.distributed as dist
 
@@ -407,6 +440,60 @@ class DiLoCoOuter:
         from ..ops.functional import bump_fp8_weight_version
 
         bump_fp8_weight_version()
+
+    def _step_sharded(self, first: bool) -> None:
+        """The outer step over stock collectives with ZeRO-1 sharded outer state (the multi-box path).
+
+        Per piece of every shard: delta = master - anchor (bf16 on the wire) -> ``reduce_scatter`` -> the owner's
+        Nesterov update in fp32 -> new bf16 weights -> ``all_gather`` -> parameters, master weights and the anchor
+        of every rank.  Staging is bounded (two buffers of <= 2^28 elements), so it fits next to an 8B model."""
+        import torch.distributed as dist
+
+        opt, cfg, W, pg, n, per = self.opt, self.cfg, self.world, self.process_group, self.n, self._per
+        dev = opt.master.device
+        # gloo (the CPU plumbing configuration) reduces fp32; NCCL carries the pseudo-gradient in bf16 like the kernel
+        wire = torch.bfloat16 if dev.type == "cuda" else torch.float32
+        piece = min(per, max(1024, ((1 << 28) // W) // 1024 * 1024))
+        send = torch.empty(W * piece, dtype=wire, device=dev)
+        mine = torch.empty(piece, dtype=wire, device=dev)
+        new = torch.empty(piece, dtype=torch.bfloat16, device=dev)
+        gathered = torch.empty(W * piece, dtype=torch.bfloat16, device=dev)
+        for off in range(0, per, piece):
+            ln = min(piece, per - off)
+            spans = []
+            for r in range(W):
+                a = min(n, r * per + off)
+                b = min(n, a + ln, (r + 1) * per)
+                spans.append((a, b))
+                view = send[r * ln:(r + 1) * ln]
+                if b > a:
+                    view[:b - a] = (opt.master[a:b] - self.anchor[a:b].float()).to(wire)
+                view[max(0, b - a):].zero_()
+            try:
+                dist.reduce_scatter_tensor(mine[:ln], send[:W * ln], group=pg)
+            except (RuntimeError, NotImplementedError):        # gloo has no reduce-scatter: all-reduce, keep a slice
+                dist.all_reduce(send[:W * ln], group=pg)
+                mine[:ln].copy_(send[self.rank * ln:(self.rank + 1) * ln])
+            a, b = spans[self.rank]
+            k = b - a
+            if k > 0:
+                lo = a - self.shard_begin
+                g = mine[:k].float().div_(W)
+                m = self.momentum[lo:lo + k]
+                if first:
+                    m.copy_(g)
+                else:
+                    m.mul_(cfg.outer_momentum).add_(g)
+                self.theta_outer[lo:lo + k].add_((m * cfg.outer_momentum).add_(g).mul_(cfg.outer_lr))
+                new[:k].copy_(self.theta_outer[lo:lo + k])
+            new[max(0, k):ln].zero_()
+            dist.all_gather_into_tensor(gathered[:W * ln], new[:ln], group=pg)
+            for r, (a, b) in enumerate(spans):
+                if b > a:
+                    fresh = gathered[r * ln:r * ln + (b - a)]
+                    opt.params[a:b].copy_(fresh)
+                    self.anchor[a:b].copy_(fresh)
+                    opt.master[a:b].copy_(fresh)               # every replica starts the round from the same bf16 weights
 
     # -- fault tolerance ------------------------------------------------------------------------
     def members(self) -> List[int]:
@@ -633,6 +720,8 @@ class DiLoCoOuter:
             # full length, one copy per rank): part of the state unless the checkpoint is taken exactly at a
             # round boundary.  Shards adopted from dropped ranks are NOT saved: checkpoint with full membership.
             sd["anchor"] = self.anchor_buf.local
+        elif self.backend == "sharded":
+            sd["anchor"] = self.anchor
         return sd
 
     def load_state_dict(self, sd) -> None:
@@ -654,3 +743,5 @@ class DiLoCoOuter:
                 self.anchor_buf.local.copy_(sd["anchor"])
             else:       # checkpoint written before the anchor was saved: only right at a round boundary
                 self.anchor_buf.local.copy_(self.opt.params)
+        elif self.backend == "sharded":
+            self.anchor.copy_(sd["anchor"] if "anchor" in sd else self.opt.params)

@@ -67,7 +67,10 @@ class DiLoCoTrainer:
         dev = torch.cuda.current_device() if device is None else device
         torch.cuda.set_device(dev)
         param_buf = grad_buf = None
-        want_fused = group is not None and group.world > 1 and diloco.backend in ("auto", "fused")
+        # peer memory (and with it the fused outer step) ends at the NVSwitch box: a larger team trains with the
+        # sharded outer step over the process group (`DiLoCoOuter._step_sharded`)
+        want_fused = group is not None and group.world > 1 and (
+            diloco.backend == "fused" or (diloco.backend == "auto" and group.world <= 8))
         if want_fused:
             holders = {}
             nvls_mode = os.environ.get("HYPHA_NVLS", "1")      # "0" off | "1" after a local pre-flight | "force"
