@@ -47,6 +47,25 @@ def free_tcp_port() -> int:
         return int(sk.getsockname()[1])
 
 
+def rendezvous_series(first: str):
+    """Addresses for the successive process groups of one collective job (a new generation forms after every
+    membership change).  On one box each is a free loopback port.  With a configured ``rendezvous`` on another host
+    (a team across boxes: the store is hosted by rank 0 THERE, so this process cannot probe for free ports) the host is
+    kept and the port counts up from the configured one -- reserve a small range."""
+    from urllib.parse import urlparse
+
+    u = urlparse(first)
+    if u.hostname in (None, "127.0.0.1", "localhost", "::1"):
+        return lambda: f"tcp://127.0.0.1:{free_tcp_port()}"
+    state = {"port": int(u.port or 29400)}
+
+    def nxt() -> str:
+        state["port"] += 1
+        host = f"[{u.hostname}]" if ":" in u.hostname else u.hostname
+        return f"tcp://{host}:{state['port']}"
+    return nxt
+
+
 def worker_batch_size(offered_gpu: float, required_gpu: float, max_batch: Optional[int]) -> int:
     """``floor(offered.gpu / required.gpu).min(max_batch_size)`` (hypha-scheduler.rs:320-322)."""
     bs = int(offered_gpu // required_gpu) if required_gpu > 0 else 1
@@ -199,7 +218,7 @@ class DiLoCoJobRun:
                 self.log.warning("checkpoint.resume is set but %s holds no checkpoint: starting at round 0", ck.dir)
         rendezvous = job.aggregation.rendezvous or f"tcp://127.0.0.1:{free_tcp_port()}"
         if self.collective:
-            self.batch.enable_collective(self.live, rendezvous, lambda: f"tcp://127.0.0.1:{free_tcp_port()}")
+            self.batch.enable_collective(self.live, rendezvous, rendezvous_series(rendezvous))
         for i, w in enumerate(self.workers):
             tcfg = self.train_config(w)
             if self.collective:

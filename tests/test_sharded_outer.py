@@ -52,3 +52,15 @@ def test_auto_backend_picks_by_team_size():
     src = inspect.getsource(trainer.DiLoCoTrainer.create)
     assert "group.world <= 8" in src
     assert "sharded" in inspect.getsource(diloco.DiLoCoOuter.__init__)
+
+
+def test_rendezvous_of_later_generations_stays_on_the_configured_host():
+    from hypha_b200.scheduler.job import rendezvous_series
+
+    local = rendezvous_series("tcp://127.0.0.1:29400")
+    a, b = local(), local()
+    assert a.startswith("tcp://127.0.0.1:") and b.startswith("tcp://127.0.0.1:")
+    far = rendezvous_series("tcp://node-a.cluster:29400")
+    assert [far(), far()] == ["tcp://node-a.cluster:29401", "tcp://node-a.cluster:29402"]
+    v6 = rendezvous_series("tcp://[fd00::1]:4000")
+    assert v6() == "tcp://[fd00::1]:4001"
