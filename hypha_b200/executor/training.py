@@ -710,7 +710,9 @@ def main_collective(session: Session, config: dict, work_dir: str) -> None:
     prepare_files(config, session)
     local = os.path.join(work_dir, FETCH_PATH)
     family = json.load(open(os.path.join(local, "config.json"))).get("model_type", "")
-    if use_cuda and family == "llama":
+    from ..models.llama import SM100_FAMILIES
+
+    if use_cuda and family in SM100_FAMILIES:
         engine = _TrainerEngine(local, config, coll, dev_index, joining=gpu_join)
     elif coll.get("join"):
         engine = _GenericEngine(local, config, coll, device, _Group("solo", None, 0, 1))   # regrouped at its first barrier

@@ -40,6 +40,7 @@ class LlamaConfig:
     rope_theta: float = 500000.0
     rope_scaling: Optional[dict] = None  # {"rope_type": "llama3", "factor", "low_freq_factor", "high_freq_factor",
                                          #  "original_max_position_embeddings"} (Llama 3.1+); None = plain RoPE
+    qkv_bias: bool = False          # Qwen2: a bias on the fused q|k|v projection (and nowhere else)
     rms_eps: float = 1e-5
     max_seq_len: int = 8192
     init_std: float = 0.02
@@ -76,10 +77,14 @@ class LlamaConfig:
         ``rope_scaling``; plain RoPE and the ``llama3`` frequency scaling are supported, anything else -- and
         projection biases -- is refused instead of being computed differently."""
         family = meta.get("model_type", "llama")
-        if family not in ("llama", "mistral"):
-            raise RuntimeError(f"model_type {family!r} is not one of the sm_100a model families (llama, mistral)")
-        if any(meta.get(k) for k in ("attention_bias", "mlp_bias")):
+        if family not in SM100_FAMILIES:
+            raise RuntimeError(f"model_type {family!r} is not one of the sm_100a model families {SM100_FAMILIES}")
+        # qwen2 is the Llama block with a bias on q / k / v only (fixed by the architecture, not a config switch)
+        if family != "qwen2" and any(meta.get(k) for k in ("attention_bias", "mlp_bias")):
             raise RuntimeError(f"{family} checkpoint with projection biases is not covered by the sm_100a model family")
+        if family == "qwen2" and meta.get("use_sliding_window"):
+            raise RuntimeError("qwen2 with use_sliding_window (a window on the upper layers only) is not covered by "
+                               "the sm_100a model family")
         rope = dict(meta.get("rope_parameters") or meta.get("rope_scaling") or {})
         rope_type = rope.get("rope_type", rope.get("type", "default")) or "default"
         if rope_type not in ("default", "llama3"):
@@ -87,7 +92,7 @@ class LlamaConfig:
                                f"(plain RoPE and llama3 scaling only)")
         theta = meta.get("rope_theta", rope.get("rope_theta"))
         if theta is None:
-            theta = 10000.0 if family == "mistral" else 500000.0
+            theta = 500000.0 if family == "llama" else 10000.0
         scaling = None
         if rope_type == "llama3":
             scaling = {"rope_type": "llama3", "factor": float(rope["factor"]),
@@ -102,7 +107,8 @@ class LlamaConfig:
                    intermediate_size=int(meta["intermediate_size"]), num_layers=int(meta["num_hidden_layers"]),
                    num_heads=heads, num_kv_heads=int(meta.get("num_key_value_heads") or heads),
                    head_dim=int(meta.get("head_dim") or int(meta["hidden_size"]) // heads), rope_theta=float(theta),
-                   rope_scaling=scaling, rms_eps=float(meta.get("rms_norm_eps", 1e-5)), max_seq_len=max_pos,
+                   rope_scaling=scaling, qkv_bias=family == "qwen2",
+                   rms_eps=float(meta.get("rms_norm_eps", 1e-6 if family == "qwen2" else 1e-5)), max_seq_len=max_pos,
                    name=meta.get("name", family))
 
     def to_hf_json(self, path: str, seed: int = 0) -> None:
@@ -110,7 +116,8 @@ class LlamaConfig:
         executor read back); ``seed`` fixes the random init every worker of a job starts from."""
         import json
 
-        json.dump({"model_type": "llama", "architectures": ["LlamaForCausalLM"], "name": self.name,
+        family, arch = ("qwen2", "Qwen2ForCausalLM") if self.qkv_bias else ("llama", "LlamaForCausalLM")
+        json.dump({"model_type": family, "architectures": [arch], "name": self.name,
                    "vocab_size": self.vocab_size, "hidden_size": self.hidden_size,
                    "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_layers,
                    "num_attention_heads": self.num_heads, "num_key_value_heads": self.num_kv_heads,
@@ -118,6 +125,9 @@ class LlamaConfig:
                    "max_position_embeddings": self.max_seq_len, "seed": seed,
                    **({"rope_scaling": dict(self.rope_scaling)} if self.rope_scaling else {})}, open(path, "w"))
 
+
+# config.json `model_type`s that run on the sm_100a kernels through `LlamaForCausalLM` (`LlamaConfig.from_hf_dict`)
+SM100_FAMILIES = ("llama", "mistral", "qwen2")
 
 PRESETS: Dict[str, LlamaConfig] = {
     "llama3-8b": LlamaConfig(name="llama3-8b"),
@@ -127,6 +137,9 @@ PRESETS: Dict[str, LlamaConfig] = {
     "llama-tiny": LlamaConfig(vocab_size=1024, hidden_size=256, intermediate_size=512,
                               num_layers=2, num_heads=4, num_kv_heads=2, head_dim=64,
                               max_seq_len=256, ce_chunk=128, name="llama-tiny"),
+    "qwen2.5-7b": LlamaConfig(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
+                              num_heads=28, num_kv_heads=4, head_dim=128, rope_theta=1000000.0, qkv_bias=True,
+                              rms_eps=1e-6, max_seq_len=32768, name="qwen2.5-7b"),
     "llama-small": LlamaConfig(vocab_size=32000, hidden_size=1024, intermediate_size=4096,
                                num_layers=4, num_heads=8, num_kv_heads=4, head_dim=128,
                                max_seq_len=2048, ce_chunk=2048, name="llama-small"),
@@ -208,15 +221,18 @@ class _CheckpointPair(torch.autograd.Function):
 
 
 class LlamaBlock(nn.Module):
-    def __init__(self, cfg: LlamaConfig, wqkv, wo, wgu, wdown, norm1, norm2):
+    def __init__(self, cfg: LlamaConfig, wqkv, wo, wgu, wdown, norm1, norm2, bqkv=None):
         super().__init__()
         self.cfg = cfg
         self.wqkv, self.wo, self.wgu, self.wdown = wqkv, wo, wgu, wdown
         self.norm1, self.norm2 = norm1, norm2
+        self.bqkv = bqkv
 
     def forward(self, delta, residual, cos, sin, batch: int, seq: int):
         c = self.cfg
         qkv, res = ops.add_norm_linear(delta, residual, self.norm1, self.wqkv, c.rms_eps)
+        if self.bqkv is not None:
+            qkv = ops.add_bias(qkv, self.bqkv)
         qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim, grad_inplace=True)
         att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
         o = ops.linear(att, self.wo)
@@ -240,6 +256,7 @@ class LlamaForCausalLM(nn.Module):
             shapes += [
                 (f"layers.{l}.norm1", (h,)),
                 (f"layers.{l}.wqkv", (cfg.qkv_dim, h)),
+                *([(f"layers.{l}.bqkv", (cfg.qkv_dim,))] if cfg.qkv_bias else []),
                 (f"layers.{l}.wo", (h, cfg.num_heads * cfg.head_dim)),
                 (f"layers.{l}.norm2", (h,)),
                 (f"layers.{l}.wgu", (2 * i, h)),
@@ -257,7 +274,8 @@ class LlamaForCausalLM(nn.Module):
         P = self._params
         self.blocks = nn.ModuleList([
             LlamaBlock(cfg, P[f"layers.{l}.wqkv"], P[f"layers.{l}.wo"], P[f"layers.{l}.wgu"],
-                       P[f"layers.{l}.wdown"], P[f"layers.{l}.norm1"], P[f"layers.{l}.norm2"])
+                       P[f"layers.{l}.wdown"], P[f"layers.{l}.norm1"], P[f"layers.{l}.norm2"],
+                       P.get(f"layers.{l}.bqkv"))
             for l in range(cfg.num_layers)
         ])
         self._rope_cache: Dict[Tuple[int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -281,6 +299,8 @@ class LlamaForCausalLM(nn.Module):
         for name, view in self.flat.named_views():
             if "norm" in name:
                 view.fill_(1.0)
+            elif name.endswith("bqkv"):
+                view.zero_()
             else:
                 std = cfg.init_std
                 if name.endswith("wo") or name.endswith("wdown"):
@@ -344,6 +364,10 @@ class LlamaForCausalLM(nn.Module):
             P[f"layers.{l}.wqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.weight"],
                                                    sd[pre + "self_attn.k_proj.weight"],
                                                    sd[pre + "self_attn.v_proj.weight"]], 0))
+            if self.cfg.qkv_bias:
+                P[f"layers.{l}.bqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.bias"],
+                                                       sd[pre + "self_attn.k_proj.bias"],
+                                                       sd[pre + "self_attn.v_proj.bias"]], 0))
             P[f"layers.{l}.wo"].copy_(sd[pre + "self_attn.o_proj.weight"])
             P[f"layers.{l}.wgu"].copy_(ops.interleave_gate_up(sd[pre + "mlp.gate_proj.weight"],
                                                               sd[pre + "mlp.up_proj.weight"]))
@@ -362,6 +386,10 @@ class LlamaForCausalLM(nn.Module):
             sd[pre + "self_attn.q_proj.weight"] = wqkv[:qd]
             sd[pre + "self_attn.k_proj.weight"] = wqkv[qd: qd + kd]
             sd[pre + "self_attn.v_proj.weight"] = wqkv[qd + kd:]
+            if c.qkv_bias:
+                b = P[f"layers.{l}.bqkv"].detach()
+                sd[pre + "self_attn.q_proj.bias"], sd[pre + "self_attn.k_proj.bias"] = b[:qd], b[qd: qd + kd]
+                sd[pre + "self_attn.v_proj.bias"] = b[qd + kd:]
             sd[pre + "self_attn.o_proj.weight"] = P[f"layers.{l}.wo"].detach()
             sd[pre + "mlp.gate_proj.weight"], sd[pre + "mlp.up_proj.weight"] = ops.split_gate_up(wgu)
             sd[pre + "mlp.down_proj.weight"] = P[f"layers.{l}.wdown"].detach()

@@ -740,6 +740,36 @@ class _RoPE(torch.autograd.Function):
         return dqkv, None, None, None, None, None, None
 
 
+class _AddBias(torch.autograd.Function):
+    """``y = x + bias`` over the rows of ``x [T, N]`` (Qwen2's bias on the fused q|k|v projection).  The bias gradient
+    is the fp32 column sum of ``dy``, written to ``bias.main_grad`` under the same overwrite / accumulate convention as
+    the weight gradients.  Plain elementwise + reduction kernels: 2 x T x N bytes next to the GEMM that produced x."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        ctx.bias = bias
+        return x + bias.to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        bias = ctx.bias
+        db = dy.reshape(-1, dy.shape[-1]).sum(0, dtype=torch.float32)
+        mg = getattr(bias, "main_grad", None)
+        if mg is None:
+            return dy, db.to(bias.dtype)
+        if getattr(bias, "grad_accumulate", False):
+            mg.add_(db.to(mg.dtype))
+        else:
+            mg.copy_(db)
+        return dy, None
+
+
+def add_bias(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    if not x.is_cuda:
+        return x + bias.to(x.dtype)          # CPU plumbing path: plain autograd (`.grad`), like every other op here
+    return _AddBias.apply(x, bias)
+
+
 def rope_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int,
              n_rot_heads: int, head_dim: int, grad_inplace: bool = False) -> torch.Tensor:
     """Rotate the q and k heads of a fused ``[tokens, (Hq+2Hkv)*D]`` activation in place.

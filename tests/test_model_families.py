@@ -19,6 +19,10 @@ def _hf_checkpoint(tmp, cfgcls, cls, **extra):
     cfg = getattr(transformers, cfgcls)(**kw, **extra)
     torch.manual_seed(0)
     hf = getattr(transformers, cls)(cfg).eval()
+    with torch.no_grad():
+        for name, p in hf.named_parameters():
+            if name.endswith(".bias"):
+                p.normal_(0.0, 0.5)                 # biases start at zero: make them count
     json.dump(cfg.to_dict(), open(os.path.join(tmp, "config.json"), "w"))
     save_file({k: v.contiguous() for k, v in hf.state_dict().items()}, os.path.join(tmp, "model.safetensors"))
     return hf, cfg
@@ -30,7 +34,8 @@ LLAMA3_ROPE = {"rope_parameters": {"rope_type": "llama3", "rope_theta": 10000.0,
 
 @pytest.mark.parametrize("family,cfgcls,cls,extra", [("llama", "LlamaConfig", "LlamaForCausalLM", {}),
                                                     ("llama", "LlamaConfig", "LlamaForCausalLM", LLAMA3_ROPE),
-                                                    ("mistral", "MistralConfig", "MistralForCausalLM", {"sliding_window": 64})])
+                                                    ("mistral", "MistralConfig", "MistralForCausalLM", {"sliding_window": 64}),
+                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {})])
 def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls, extra):
     from hypha_b200.executor.model import get_model
 
@@ -39,6 +44,7 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
     ours = get_model(str(tmp_path), "causal-lm", "cpu").eval()
     assert type(ours.net).__name__ == "LlamaForCausalLM" and ours.net.cfg.rope_theta == 10000.0
     assert ours.net.cfg.max_seq_len == (64 if family == "mistral" else 128)      # capped at the sliding window
+    assert ours.net.cfg.qkv_bias == (family == "qwen2")
     ids = torch.randint(0, 320, (2, 48))
     with torch.no_grad():
         ref = hf(ids)
@@ -50,6 +56,18 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
     sd = ours.net.to_hf_state_dict()
     for k, v in hf.state_dict().items():
         assert torch.equal(sd[k].float(), v.float()), k
+    # gradients: the fused q|k|v weight (and Qwen2's bias) against the three HF projections
+    hf.zero_grad()
+    hf(ids, labels=ids).loss.backward()
+    ours.zero_grad()
+    ours(ids, labels=ids)["loss"].backward()
+    att = hf.model.layers[0].self_attn
+    named = dict(ours.net.named_flat_parameters())
+    want = torch.cat([att.q_proj.weight.grad, att.k_proj.weight.grad, att.v_proj.weight.grad], 0)
+    assert (named["layers.0.wqkv"].grad - want).abs().max().item() < 1e-5
+    if family == "qwen2":
+        want_b = torch.cat([att.q_proj.bias.grad, att.k_proj.bias.grad, att.v_proj.bias.grad], 0)
+        assert want_b.abs().max().item() > 0 and (named["layers.0.bqkv"].grad - want_b).abs().max().item() < 1e-5
 
 
 def test_unsupported_llama_variants_are_refused_loudly(tmp_path):
@@ -153,3 +171,39 @@ def test_lr_schedules_match_transformers():
     # past the end the cosine stays at zero (the Hugging Face lambda would climb again)
     f = make_lr_lambda({"type": "cosine-with-warmup", "warmup_steps": 5, "training_steps": 50})
     assert f(55) == 0.0 and f(500) == 0.0
+
+
+def test_bias_gradient_follows_the_main_grad_convention():
+    """The GPU form of `ops.add_bias` (an autograd Function that writes the bias gradient into the flat gradient
+    buffer, overwrite or accumulate) -- its arithmetic is device independent, so it is checked here on host tensors."""
+    from hypha_b200.ops.functional import _AddBias
+
+    x = torch.randn(6, 8, requires_grad=True)
+    b = torch.nn.Parameter(torch.randn(8))
+    b.main_grad = torch.zeros(8)
+    w = torch.randn(6, 8)
+    (_AddBias.apply(x, b) * w).sum().backward()
+    assert b.grad is None and torch.allclose(b.main_grad, w.sum(0)) and torch.allclose(x.grad, w)
+    b.grad_accumulate = True
+    (_AddBias.apply(x, b) * w).sum().backward()
+    assert torch.allclose(b.main_grad, 2 * w.sum(0))
+    b.grad_accumulate = False
+    (_AddBias.apply(x.detach().requires_grad_(), b) * (3 * w)).sum().backward()
+    assert torch.allclose(b.main_grad, 3 * w.sum(0))                  # overwritten, not added
+    plain = torch.nn.Parameter(torch.randn(8))                        # no flat buffer: the ordinary `.grad`
+    (_AddBias.apply(x.detach(), plain) * w).sum().backward()
+    assert torch.allclose(plain.grad, w.sum(0))
+
+
+def test_qwen2_preset_and_config_round_trip(tmp_path):
+    from hypha_b200.models.llama import LlamaConfig, get_config
+
+    c = get_config("qwen2.5-7b", num_layers=1, vocab_size=512)
+    assert c.qkv_bias and c.head_dim * c.num_heads == c.hidden_size
+    c.to_hf_json(str(tmp_path / "config.json"), seed=3)
+    meta = json.load(open(tmp_path / "config.json"))
+    assert meta["model_type"] == "qwen2"
+    back = LlamaConfig.from_hf_dict(meta)
+    assert back.qkv_bias and back.rope_theta == 1000000.0 and back.rms_eps == 1e-6
+    with pytest.raises(RuntimeError, match="use_sliding_window"):
+        LlamaConfig.from_hf_dict(dict(meta, use_sliding_window=True))
