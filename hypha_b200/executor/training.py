@@ -555,6 +555,8 @@ class _TrainerEngine:
         outer.round = rnd
         if outer.backend == "fused":
             outer.anchor_buf.local.copy_(tr.model.flat.data)
+        elif outer.backend == "sharded":
+            outer.anchor.copy_(tr.model.flat.data)
         from ..ops.functional import bump_fp8_weight_version
 
         bump_fp8_weight_version()

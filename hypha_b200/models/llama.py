@@ -41,6 +41,7 @@ class LlamaConfig:
     rope_scaling: Optional[dict] = None  # {"rope_type": "llama3", "factor", "low_freq_factor", "high_freq_factor",
                                          #  "original_max_position_embeddings"} (Llama 3.1+); None = plain RoPE
     qkv_bias: bool = False          # Qwen2: a bias on the fused q|k|v projection (and nowhere else)
+    tie_embeddings: bool = False    # the LM head IS the embedding table (Llama-3.2-1B/3B, small Qwen2 models)
     rms_eps: float = 1e-5
     max_seq_len: int = 8192
     init_std: float = 0.02
@@ -108,6 +109,7 @@ class LlamaConfig:
                    num_heads=heads, num_kv_heads=int(meta.get("num_key_value_heads") or heads),
                    head_dim=int(meta.get("head_dim") or int(meta["hidden_size"]) // heads), rope_theta=float(theta),
                    rope_scaling=scaling, qkv_bias=family == "qwen2",
+                   tie_embeddings=bool(meta.get("tie_word_embeddings", False)),
                    rms_eps=float(meta.get("rms_norm_eps", 1e-6 if family == "qwen2" else 1e-5)), max_seq_len=max_pos,
                    name=meta.get("name", family))
 
@@ -123,6 +125,7 @@ class LlamaConfig:
                    "num_attention_heads": self.num_heads, "num_key_value_heads": self.num_kv_heads,
                    "head_dim": self.head_dim, "rope_theta": self.rope_theta, "rms_norm_eps": self.rms_eps,
                    "max_position_embeddings": self.max_seq_len, "seed": seed,
+                   "tie_word_embeddings": self.tie_embeddings,
                    **({"rope_scaling": dict(self.rope_scaling)} if self.rope_scaling else {})}, open(path, "w"))
 
 
@@ -140,6 +143,9 @@ PRESETS: Dict[str, LlamaConfig] = {
     "qwen2.5-7b": LlamaConfig(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
                               num_heads=28, num_kv_heads=4, head_dim=128, rope_theta=1000000.0, qkv_bias=True,
                               rms_eps=1e-6, max_seq_len=32768, name="qwen2.5-7b"),
+    "qwen2-tiny": LlamaConfig(vocab_size=1024, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
+                              num_kv_heads=2, head_dim=64, rope_theta=1000000.0, qkv_bias=True, rms_eps=1e-6,
+                              max_seq_len=256, ce_chunk=128, name="qwen2-tiny"),
     "llama-small": LlamaConfig(vocab_size=32000, hidden_size=1024, intermediate_size=4096,
                                num_layers=4, num_heads=8, num_kv_heads=4, head_dim=128,
                                max_seq_len=2048, ce_chunk=2048, name="llama-small"),
@@ -262,7 +268,7 @@ class LlamaForCausalLM(nn.Module):
                 (f"layers.{l}.wgu", (2 * i, h)),
                 (f"layers.{l}.wdown", (h, i)),
             ]
-        shapes += [("final_norm", (h,)), ("lm_head", (v, h))]
+        shapes += [("final_norm", (h,))] + ([] if cfg.tie_embeddings else [("lm_head", (v, h))])
         self.flat = FlatParams(shapes, device, dtype, alloc=alloc, grad_alloc=grad_alloc)
         self._params: Dict[str, nn.Parameter] = {}
         for name, view in self.flat.named_views():
@@ -272,6 +278,12 @@ class LlamaForCausalLM(nn.Module):
             self._params[name] = p
             self.register_parameter(name.replace(".", "_"), p)
         P = self._params
+        if cfg.tie_embeddings:
+            # ONE parameter used twice: the head's weight gradient (written by the fused LM-head + cross-entropy op
+            # in overwrite mode) and the embedding's scatter-add meet in the same slice of the flat gradient buffer,
+            # so the embedding backward must add to what it finds (`ops.functional._Embedding.backward`)
+            P["lm_head"] = P["embed"]
+            P["embed"].tied_head = True
         self.blocks = nn.ModuleList([
             LlamaBlock(cfg, P[f"layers.{l}.wqkv"], P[f"layers.{l}.wo"], P[f"layers.{l}.wgu"],
                        P[f"layers.{l}.wdown"], P[f"layers.{l}.norm1"], P[f"layers.{l}.norm2"],
@@ -358,7 +370,8 @@ class LlamaForCausalLM(nn.Module):
         P = self._params
         P["embed"].copy_(sd["model.embed_tokens.weight"])
         P["final_norm"].copy_(sd["model.norm.weight"])
-        P["lm_head"].copy_(sd.get("lm_head.weight", sd["model.embed_tokens.weight"]))
+        if not self.cfg.tie_embeddings:
+            P["lm_head"].copy_(sd.get("lm_head.weight", sd["model.embed_tokens.weight"]))
         for l in range(self.cfg.num_layers):
             pre = f"model.layers.{l}."
             P[f"layers.{l}.wqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.weight"],
@@ -378,8 +391,9 @@ class LlamaForCausalLM(nn.Module):
     def to_hf_state_dict(self) -> Dict[str, torch.Tensor]:
         c, P = self.cfg, self._params
         qd, kd = c.num_heads * c.head_dim, c.num_kv_heads * c.head_dim
-        sd = {"model.embed_tokens.weight": P["embed"].detach(), "model.norm.weight": P["final_norm"].detach(),
-              "lm_head.weight": P["lm_head"].detach()}
+        sd = {"model.embed_tokens.weight": P["embed"].detach(), "model.norm.weight": P["final_norm"].detach()}
+        if not c.tie_embeddings:                    # a tied head is not stored: `transformers` re-ties it on load
+            sd["lm_head.weight"] = P["lm_head"].detach()
         for l in range(c.num_layers):
             pre = f"model.layers.{l}."
             wqkv, wgu = P[f"layers.{l}.wqkv"].detach(), P[f"layers.{l}.wgu"].detach()

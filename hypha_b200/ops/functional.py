@@ -1099,7 +1099,8 @@ class _Embedding(torch.autograd.Function):
         table = ctx.table
         mg = getattr(table, "main_grad", None)
         if mg is not None:
-            if not getattr(table, "grad_accumulate", False):
+            # a table that doubles as the LM head (`tied_head`) already holds the head's weight gradient here
+            if not (getattr(table, "grad_accumulate", False) or getattr(table, "tied_head", False)):
                 mg.zero_()
             target, ret = mg, None
         else:

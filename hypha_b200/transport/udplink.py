@@ -463,7 +463,8 @@ class UdpLink:
                 return
             if len(buf) < 4 + n:
                 break
-            self._frames.append((bytearray(buf[4:4 + n]), split))
+            with memoryview(buf) as mv:                      # one copy out of the stream buffer, not two
+                self._frames.append((bytearray(mv[4:4 + n]), split))
             self._queued += n
             del buf[:4 + n]
         w, self._frame_waiter = self._frame_waiter, None

@@ -16,7 +16,8 @@ def _hf_checkpoint(tmp, cfgcls, cls, **extra):
               num_key_value_heads=2, max_position_embeddings=128, rms_norm_eps=1e-5, tie_word_embeddings=False)
     if "rope_parameters" not in extra:
         kw["rope_theta"] = 10000.0
-    cfg = getattr(transformers, cfgcls)(**kw, **extra)
+    kw.update(extra)
+    cfg = getattr(transformers, cfgcls)(**kw)
     torch.manual_seed(0)
     hf = getattr(transformers, cls)(cfg).eval()
     with torch.no_grad():
@@ -24,7 +25,9 @@ def _hf_checkpoint(tmp, cfgcls, cls, **extra):
             if name.endswith(".bias"):
                 p.normal_(0.0, 0.5)                 # biases start at zero: make them count
     json.dump(cfg.to_dict(), open(os.path.join(tmp, "config.json"), "w"))
-    save_file({k: v.contiguous() for k, v in hf.state_dict().items()}, os.path.join(tmp, "model.safetensors"))
+    save_file({k: v.contiguous() for k, v in hf.state_dict().items()
+               if not (kw.get("tie_word_embeddings") and k == "lm_head.weight")},     # a tied head is stored once
+              os.path.join(tmp, "model.safetensors"))
     return hf, cfg
 
 
@@ -35,7 +38,9 @@ LLAMA3_ROPE = {"rope_parameters": {"rope_type": "llama3", "rope_theta": 10000.0,
 @pytest.mark.parametrize("family,cfgcls,cls,extra", [("llama", "LlamaConfig", "LlamaForCausalLM", {}),
                                                     ("llama", "LlamaConfig", "LlamaForCausalLM", LLAMA3_ROPE),
                                                     ("mistral", "MistralConfig", "MistralForCausalLM", {"sliding_window": 64}),
-                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {})])
+                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {}),
+                                                    ("llama", "LlamaConfig", "LlamaForCausalLM", {"tie_word_embeddings": True}),
+                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {"tie_word_embeddings": True})])
 def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls, extra):
     from hypha_b200.executor.model import get_model
 
@@ -54,7 +59,11 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
         assert abs(hf(ids, labels=ids).loss.item() - ours(ids, labels=ids)["loss"].item()) < 1e-5
     # the round trip back to HF names is lossless (what a checkpoint of a finished job contains)
     sd = ours.net.to_hf_state_dict()
+    tied = bool(extra.get("tie_word_embeddings"))
+    assert ours.net.cfg.tie_embeddings == tied and ("lm_head.weight" in sd) == (not tied)
     for k, v in hf.state_dict().items():
+        if tied and k == "lm_head.weight":
+            continue                                   # stored once, as the embedding table
         assert torch.equal(sd[k].float(), v.float()), k
     # gradients: the fused q|k|v weight (and Qwen2's bias) against the three HF projections
     hf.zero_grad()
@@ -65,6 +74,10 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
     named = dict(ours.net.named_flat_parameters())
     want = torch.cat([att.q_proj.weight.grad, att.k_proj.weight.grad, att.v_proj.weight.grad], 0)
     assert (named["layers.0.wqkv"].grad - want).abs().max().item() < 1e-5
+    if tied:        # one parameter, two uses: the head's gradient and the embedding's scatter-add are summed
+        assert named["lm_head"] is named["embed"]
+        assert (named["embed"].grad - hf.model.embed_tokens.weight.grad).abs().max().item() < 1e-5
+        assert sum(p.numel() for p in ours.net.parameters()) == sum(p.numel() for p in hf.parameters())
     if family == "qwen2":
         want_b = torch.cat([att.q_proj.bias.grad, att.k_proj.bias.grad, att.v_proj.bias.grad], 0)
         assert want_b.abs().max().item() > 0 and (named["layers.0.bqkv"].grad - want_b).abs().max().item() < 1e-5
@@ -207,3 +220,24 @@ def test_qwen2_preset_and_config_round_trip(tmp_path):
     assert back.qkv_bias and back.rope_theta == 1000000.0 and back.rms_eps == 1e-6
     with pytest.raises(RuntimeError, match="use_sliding_window"):
         LlamaConfig.from_hf_dict(dict(meta, use_sliding_window=True))
+
+
+def test_qwen2_job_through_the_box_exports_a_transformers_checkpoint(capsys, tmp_path):
+    """The whole stack on a Qwen2-shaped model (CPU): scheduler -> lease -> executor -> rounds -> export; the exported
+    directory loads as `transformers.Qwen2ForCausalLM` and its q/k/v biases were trained (they start at zero)."""
+    import transformers
+
+    from hypha_b200.cli import box
+
+    out_dir = str(tmp_path / "trained")
+    rc = box.main(["run", "--model", "qwen2-tiny", "--workers", "1", "--device", "cpu", "--rounds", "2",
+                   "--samples-per-round", "16", "--batch-size", "4", "--seq-len", "32", "--timeout", "240",
+                   "--lr", "1e-2", "--checkpoint-dir", str(tmp_path / "ckpt"), "--export", out_dir])
+    out = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert rc == 0 and out["finished"] and out["rounds"] == 2
+    assert json.load(open(os.path.join(out_dir, "config.json")))["model_type"] == "qwen2"
+    hf = transformers.Qwen2ForCausalLM.from_pretrained(out_dir).eval()
+    with torch.no_grad():
+        assert torch.isfinite(hf(torch.randint(0, 1024, (1, 16))).logits).all()
+    bias = hf.model.layers[0].self_attn.q_proj.bias
+    assert bias is not None and bias.abs().max().item() > 0
