@@ -127,7 +127,7 @@ def _build_model(model_path: str, model_type: str, device: str, meta: dict, fami
         from ..models.lenet import LeNetConfig, LeNetForImageClassification
 
         net = LeNetForImageClassification(LeNetConfig.from_json(cfg_path))
-    elif family in ("llama", "mistral", "qwen2"):      # models.llama.SM100_FAMILIES
+    elif family in ("llama", "mistral", "qwen2", "qwen3", "phi3"):      # models.llama.SM100_FAMILIES
         from ..models.llama import LlamaConfig, LlamaForCausalLM
 
         c = LlamaConfig.from_hf_dict(meta)          # llama / mistral -> the sm_100a kernels (see its docstring)

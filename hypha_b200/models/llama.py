@@ -42,6 +42,9 @@ class LlamaConfig:
                                          #  "original_max_position_embeddings"} (Llama 3.1+); None = plain RoPE
     qkv_bias: bool = False          # Qwen2: a bias on the fused q|k|v projection (and nowhere else)
     tie_embeddings: bool = False    # the LM head IS the embedding table (Llama-3.2-1B/3B, small Qwen2 models)
+    qk_norm: bool = False           # Qwen3: RMSNorm over head_dim on every q and k head, before RoPE
+    hf_family: str = "llama"        # whose parameter names / config.json a checkpoint uses: llama | mistral | qwen2 |
+                                    # qwen3 | phi3 (phi3 stores q|k|v and gate|up fused, as this model does)
     rms_eps: float = 1e-5
     max_seq_len: int = 8192
     init_std: float = 0.02
@@ -83,9 +86,11 @@ class LlamaConfig:
         # qwen2 is the Llama block with a bias on q / k / v only (fixed by the architecture, not a config switch)
         if family != "qwen2" and any(meta.get(k) for k in ("attention_bias", "mlp_bias")):
             raise RuntimeError(f"{family} checkpoint with projection biases is not covered by the sm_100a model family")
-        if family == "qwen2" and meta.get("use_sliding_window"):
-            raise RuntimeError("qwen2 with use_sliding_window (a window on the upper layers only) is not covered by "
+        if family in ("qwen2", "qwen3") and meta.get("use_sliding_window"):
+            raise RuntimeError(f"{family} with use_sliding_window (a window on the upper layers only) is not covered by "
                                "the sm_100a model family")
+        if family == "phi3" and float(meta.get("partial_rotary_factor", 1.0) or 1.0) != 1.0:
+            raise RuntimeError("phi3 with a partial rotary factor is not covered by the sm_100a model family")
         rope = dict(meta.get("rope_parameters") or meta.get("rope_scaling") or {})
         rope_type = rope.get("rope_type", rope.get("type", "default")) or "default"
         if rope_type not in ("default", "llama3"):
@@ -101,16 +106,17 @@ class LlamaConfig:
                        "high_freq_factor": float(rope.get("high_freq_factor", 4.0)),
                        "original_max_position_embeddings": int(rope.get("original_max_position_embeddings", 8192))}
         max_pos = int(meta.get("max_position_embeddings", 8192))
-        if family == "mistral" and meta.get("sliding_window"):
+        if family in ("mistral", "phi3") and meta.get("sliding_window"):
             max_pos = min(max_pos, int(meta["sliding_window"]))
         heads = int(meta["num_attention_heads"])
         return cls(vocab_size=int(meta["vocab_size"]), hidden_size=int(meta["hidden_size"]),
                    intermediate_size=int(meta["intermediate_size"]), num_layers=int(meta["num_hidden_layers"]),
                    num_heads=heads, num_kv_heads=int(meta.get("num_key_value_heads") or heads),
                    head_dim=int(meta.get("head_dim") or int(meta["hidden_size"]) // heads), rope_theta=float(theta),
-                   rope_scaling=scaling, qkv_bias=family == "qwen2",
+                   rope_scaling=scaling, qkv_bias=family == "qwen2", qk_norm=family == "qwen3", hf_family=family,
                    tie_embeddings=bool(meta.get("tie_word_embeddings", False)),
-                   rms_eps=float(meta.get("rms_norm_eps", 1e-6 if family == "qwen2" else 1e-5)), max_seq_len=max_pos,
+                   rms_eps=float(meta.get("rms_norm_eps", 1e-6 if family in ("qwen2", "qwen3") else 1e-5)),
+                   max_seq_len=max_pos,
                    name=meta.get("name", family))
 
     def to_hf_json(self, path: str, seed: int = 0) -> None:
@@ -118,7 +124,9 @@ class LlamaConfig:
         executor read back); ``seed`` fixes the random init every worker of a job starts from."""
         import json
 
-        family, arch = ("qwen2", "Qwen2ForCausalLM") if self.qkv_bias else ("llama", "LlamaForCausalLM")
+        family = "qwen2" if self.qkv_bias else "qwen3" if self.qk_norm else self.hf_family
+        arch = {"llama": "LlamaForCausalLM", "mistral": "MistralForCausalLM", "qwen2": "Qwen2ForCausalLM",
+                "qwen3": "Qwen3ForCausalLM", "phi3": "Phi3ForCausalLM"}[family]
         json.dump({"model_type": family, "architectures": [arch], "name": self.name,
                    "vocab_size": self.vocab_size, "hidden_size": self.hidden_size,
                    "intermediate_size": self.intermediate_size, "num_hidden_layers": self.num_layers,
@@ -130,7 +138,7 @@ class LlamaConfig:
 
 
 # config.json `model_type`s that run on the sm_100a kernels through `LlamaForCausalLM` (`LlamaConfig.from_hf_dict`)
-SM100_FAMILIES = ("llama", "mistral", "qwen2")
+SM100_FAMILIES = ("llama", "mistral", "qwen2", "qwen3", "phi3")
 
 PRESETS: Dict[str, LlamaConfig] = {
     "llama3-8b": LlamaConfig(name="llama3-8b"),
@@ -227,18 +235,21 @@ class _CheckpointPair(torch.autograd.Function):
 
 
 class LlamaBlock(nn.Module):
-    def __init__(self, cfg: LlamaConfig, wqkv, wo, wgu, wdown, norm1, norm2, bqkv=None):
+    def __init__(self, cfg: LlamaConfig, wqkv, wo, wgu, wdown, norm1, norm2, bqkv=None, qnorm=None, knorm=None):
         super().__init__()
         self.cfg = cfg
         self.wqkv, self.wo, self.wgu, self.wdown = wqkv, wo, wgu, wdown
         self.norm1, self.norm2 = norm1, norm2
         self.bqkv = bqkv
+        self.qnorm, self.knorm = qnorm, knorm
 
     def forward(self, delta, residual, cos, sin, batch: int, seq: int):
         c = self.cfg
         qkv, res = ops.add_norm_linear(delta, residual, self.norm1, self.wqkv, c.rms_eps)
         if self.bqkv is not None:
             qkv = ops.add_bias(qkv, self.bqkv)
+        if self.qnorm is not None:
+            qkv = ops.qk_norm(qkv, self.qnorm, self.knorm, c.num_heads, c.num_kv_heads, c.head_dim, c.rms_eps)
         qkv = ops.rope_qkv(qkv, cos, sin, seq, c.num_heads + c.num_kv_heads, c.head_dim, grad_inplace=True)
         att = ops.attention_qkv(qkv, batch, seq, c.num_heads, c.num_kv_heads, c.head_dim)
         o = ops.linear(att, self.wo)
@@ -263,6 +274,7 @@ class LlamaForCausalLM(nn.Module):
                 (f"layers.{l}.norm1", (h,)),
                 (f"layers.{l}.wqkv", (cfg.qkv_dim, h)),
                 *([(f"layers.{l}.bqkv", (cfg.qkv_dim,))] if cfg.qkv_bias else []),
+                *([(f"layers.{l}.qnorm", (cfg.head_dim,)), (f"layers.{l}.knorm", (cfg.head_dim,))] if cfg.qk_norm else []),
                 (f"layers.{l}.wo", (h, cfg.num_heads * cfg.head_dim)),
                 (f"layers.{l}.norm2", (h,)),
                 (f"layers.{l}.wgu", (2 * i, h)),
@@ -287,7 +299,7 @@ class LlamaForCausalLM(nn.Module):
         self.blocks = nn.ModuleList([
             LlamaBlock(cfg, P[f"layers.{l}.wqkv"], P[f"layers.{l}.wo"], P[f"layers.{l}.wgu"],
                        P[f"layers.{l}.wdown"], P[f"layers.{l}.norm1"], P[f"layers.{l}.norm2"],
-                       P.get(f"layers.{l}.bqkv"))
+                       P.get(f"layers.{l}.bqkv"), P.get(f"layers.{l}.qnorm"), P.get(f"layers.{l}.knorm"))
             for l in range(cfg.num_layers)
         ])
         self._rope_cache: Dict[Tuple[int, str], Tuple[torch.Tensor, torch.Tensor]] = {}
@@ -374,16 +386,23 @@ class LlamaForCausalLM(nn.Module):
             P["lm_head"].copy_(sd.get("lm_head.weight", sd["model.embed_tokens.weight"]))
         for l in range(self.cfg.num_layers):
             pre = f"model.layers.{l}."
-            P[f"layers.{l}.wqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.weight"],
-                                                   sd[pre + "self_attn.k_proj.weight"],
-                                                   sd[pre + "self_attn.v_proj.weight"]], 0))
+            if self.cfg.hf_family == "phi3":                 # already fused: [q; k; v] and [gate; up] row blocks
+                P[f"layers.{l}.wqkv"].copy_(sd[pre + "self_attn.qkv_proj.weight"])
+                gate, up = sd[pre + "mlp.gate_up_proj.weight"].chunk(2, 0)
+            else:
+                P[f"layers.{l}.wqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.weight"],
+                                                       sd[pre + "self_attn.k_proj.weight"],
+                                                       sd[pre + "self_attn.v_proj.weight"]], 0))
+                gate, up = sd[pre + "mlp.gate_proj.weight"], sd[pre + "mlp.up_proj.weight"]
             if self.cfg.qkv_bias:
                 P[f"layers.{l}.bqkv"].copy_(torch.cat([sd[pre + "self_attn.q_proj.bias"],
                                                        sd[pre + "self_attn.k_proj.bias"],
                                                        sd[pre + "self_attn.v_proj.bias"]], 0))
+            if self.cfg.qk_norm:
+                P[f"layers.{l}.qnorm"].copy_(sd[pre + "self_attn.q_norm.weight"])
+                P[f"layers.{l}.knorm"].copy_(sd[pre + "self_attn.k_norm.weight"])
             P[f"layers.{l}.wo"].copy_(sd[pre + "self_attn.o_proj.weight"])
-            P[f"layers.{l}.wgu"].copy_(ops.interleave_gate_up(sd[pre + "mlp.gate_proj.weight"],
-                                                              sd[pre + "mlp.up_proj.weight"]))
+            P[f"layers.{l}.wgu"].copy_(ops.interleave_gate_up(gate, up))
             P[f"layers.{l}.wdown"].copy_(sd[pre + "mlp.down_proj.weight"])
             P[f"layers.{l}.norm1"].copy_(sd[pre + "input_layernorm.weight"])
             P[f"layers.{l}.norm2"].copy_(sd[pre + "post_attention_layernorm.weight"])
@@ -397,15 +416,23 @@ class LlamaForCausalLM(nn.Module):
         for l in range(c.num_layers):
             pre = f"model.layers.{l}."
             wqkv, wgu = P[f"layers.{l}.wqkv"].detach(), P[f"layers.{l}.wgu"].detach()
-            sd[pre + "self_attn.q_proj.weight"] = wqkv[:qd]
-            sd[pre + "self_attn.k_proj.weight"] = wqkv[qd: qd + kd]
-            sd[pre + "self_attn.v_proj.weight"] = wqkv[qd + kd:]
+            gate, up = ops.split_gate_up(wgu)
+            if c.hf_family == "phi3":
+                sd[pre + "self_attn.qkv_proj.weight"] = wqkv
+                sd[pre + "mlp.gate_up_proj.weight"] = torch.cat([gate, up], 0)
+            else:
+                sd[pre + "self_attn.q_proj.weight"] = wqkv[:qd]
+                sd[pre + "self_attn.k_proj.weight"] = wqkv[qd: qd + kd]
+                sd[pre + "self_attn.v_proj.weight"] = wqkv[qd + kd:]
+                sd[pre + "mlp.gate_proj.weight"], sd[pre + "mlp.up_proj.weight"] = gate, up
             if c.qkv_bias:
                 b = P[f"layers.{l}.bqkv"].detach()
                 sd[pre + "self_attn.q_proj.bias"], sd[pre + "self_attn.k_proj.bias"] = b[:qd], b[qd: qd + kd]
                 sd[pre + "self_attn.v_proj.bias"] = b[qd + kd:]
+            if c.qk_norm:
+                sd[pre + "self_attn.q_norm.weight"] = P[f"layers.{l}.qnorm"].detach()
+                sd[pre + "self_attn.k_norm.weight"] = P[f"layers.{l}.knorm"].detach()
             sd[pre + "self_attn.o_proj.weight"] = P[f"layers.{l}.wo"].detach()
-            sd[pre + "mlp.gate_proj.weight"], sd[pre + "mlp.up_proj.weight"] = ops.split_gate_up(wgu)
             sd[pre + "mlp.down_proj.weight"] = P[f"layers.{l}.wdown"].detach()
             sd[pre + "input_layernorm.weight"] = P[f"layers.{l}.norm1"].detach()
             sd[pre + "post_attention_layernorm.weight"] = P[f"layers.{l}.norm2"].detach()

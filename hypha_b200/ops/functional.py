@@ -770,6 +770,43 @@ def add_bias(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
     return _AddBias.apply(x, bias)
 
 
+class _MainGradSink(torch.autograd.Function):
+    """Identity on a parameter whose gradient, computed by plain autograd ops, belongs in the flat gradient buffer
+    (``param.main_grad``, overwrite / accumulate like the kernels' weight gradients) instead of ``param.grad`` --
+    the fused optimizer only reads the flat buffer."""
+
+    @staticmethod
+    def forward(ctx, param):
+        ctx.param = param
+        return param.view_as(param)
+
+    @staticmethod
+    def backward(ctx, g):
+        p = ctx.param
+        mg = getattr(p, "main_grad", None)
+        if mg is None:
+            return g
+        if getattr(p, "grad_accumulate", False):
+            mg.add_(g.to(mg.dtype))
+        else:
+            mg.copy_(g)
+        return None
+
+
+def qk_norm(qkv: torch.Tensor, q_weight: torch.Tensor, k_weight: torch.Tensor, n_heads: int, n_kv: int, head_dim: int,
+            eps: float) -> torch.Tensor:
+    """Qwen3's RMSNorm over ``head_dim`` of every q and k head of the fused ``[T, (Hq + 2 Hkv) D]`` activation (before
+    RoPE).  No sm_100a kernel yet: torch ops on every device, counted as a library fallback on the GPU."""
+    T = qkv.shape[0]
+    qd, kd = n_heads * head_dim, n_kv * head_dim
+    if qkv.is_cuda:
+        _note_fallback("qk_norm", "per-head RMSNorm of q / k (qwen3) runs as torch ops")
+        q_weight, k_weight = _MainGradSink.apply(q_weight), _MainGradSink.apply(k_weight)
+    q = _rmsnorm_ref(qkv[:, :qd].reshape(T, n_heads, head_dim), q_weight, eps).reshape(T, qd)
+    k = _rmsnorm_ref(qkv[:, qd:qd + kd].reshape(T, n_kv, head_dim), k_weight, eps).reshape(T, kd)
+    return torch.cat([q, k, qkv[:, qd + kd:]], 1)
+
+
 def rope_qkv(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, seq_len: int,
              n_rot_heads: int, head_dim: int, grad_inplace: bool = False) -> torch.Tensor:
     """Rotate the q and k heads of a fused ``[tokens, (Hq+2Hkv)*D]`` activation in place.

@@ -24,6 +24,8 @@ def _hf_checkpoint(tmp, cfgcls, cls, **extra):
         for name, p in hf.named_parameters():
             if name.endswith(".bias"):
                 p.normal_(0.0, 0.5)                 # biases start at zero: make them count
+            if name.endswith(("q_norm.weight", "k_norm.weight")):
+                p.uniform_(0.5, 1.5)                # ... and norm weights at one
     json.dump(cfg.to_dict(), open(os.path.join(tmp, "config.json"), "w"))
     save_file({k: v.contiguous() for k, v in hf.state_dict().items()
                if not (kw.get("tie_word_embeddings") and k == "lm_head.weight")},     # a tied head is stored once
@@ -40,7 +42,9 @@ LLAMA3_ROPE = {"rope_parameters": {"rope_type": "llama3", "rope_theta": 10000.0,
                                                     ("mistral", "MistralConfig", "MistralForCausalLM", {"sliding_window": 64}),
                                                     ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {}),
                                                     ("llama", "LlamaConfig", "LlamaForCausalLM", {"tie_word_embeddings": True}),
-                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {"tie_word_embeddings": True})])
+                                                    ("qwen2", "Qwen2Config", "Qwen2ForCausalLM", {"tie_word_embeddings": True}),
+                                                    ("qwen3", "Qwen3Config", "Qwen3ForCausalLM", {"head_dim": 16}),
+                                                    ("phi3", "Phi3Config", "Phi3ForCausalLM", {"pad_token_id": None, "sliding_window": 64})])
 def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls, extra):
     from hypha_b200.executor.model import get_model
 
@@ -48,7 +52,9 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
     assert "rope_theta" not in cfg.to_dict() or True       # transformers >= 5 nests it under rope_parameters
     ours = get_model(str(tmp_path), "causal-lm", "cpu").eval()
     assert type(ours.net).__name__ == "LlamaForCausalLM" and ours.net.cfg.rope_theta == 10000.0
-    assert ours.net.cfg.max_seq_len == (64 if family == "mistral" else 128)      # capped at the sliding window
+    assert ours.net.cfg.head_dim == 16
+    assert ours.net.cfg.max_seq_len == (64 if family in ("mistral", "phi3") else 128)      # capped at the sliding window
+    assert ours.net.cfg.qk_norm == (family == "qwen3") and ours.net.cfg.hf_family == family
     assert ours.net.cfg.qkv_bias == (family == "qwen2")
     ids = torch.randint(0, 320, (2, 48))
     with torch.no_grad():
@@ -72,7 +78,18 @@ def test_llama_like_checkpoints_match_transformers(tmp_path, family, cfgcls, cls
     ours(ids, labels=ids)["loss"].backward()
     att = hf.model.layers[0].self_attn
     named = dict(ours.net.named_flat_parameters())
-    want = torch.cat([att.q_proj.weight.grad, att.k_proj.weight.grad, att.v_proj.weight.grad], 0)
+    if family == "phi3":
+        want = att.qkv_proj.weight.grad
+        gu = hf.model.layers[0].mlp.gate_up_proj.weight.grad
+        from hypha_b200.ops import interleave_gate_up
+
+        assert (named["layers.0.wgu"].grad - interleave_gate_up(*gu.chunk(2, 0))).abs().max().item() < 1e-5
+    else:
+        want = torch.cat([att.q_proj.weight.grad, att.k_proj.weight.grad, att.v_proj.weight.grad], 0)
+    if family == "qwen3":
+        assert att.q_norm.weight.grad.abs().max().item() > 0
+        assert (named["layers.0.qnorm"].grad - att.q_norm.weight.grad).abs().max().item() < 1e-5
+        assert (named["layers.0.knorm"].grad - att.k_norm.weight.grad).abs().max().item() < 1e-5
     assert (named["layers.0.wqkv"].grad - want).abs().max().item() < 1e-5
     if tied:        # one parameter, two uses: the head's gradient and the embedding's scatter-add are summed
         assert named["lm_head"] is named["embed"]
@@ -241,3 +258,21 @@ def test_qwen2_job_through_the_box_exports_a_transformers_checkpoint(capsys, tmp
         assert torch.isfinite(hf(torch.randint(0, 1024, (1, 16))).logits).all()
     bias = hf.model.layers[0].self_attn.q_proj.bias
     assert bias is not None and bias.abs().max().item() > 0
+
+
+def test_gradients_of_plain_torch_ops_reach_the_flat_buffer():
+    """`_MainGradSink`: the identity that routes a parameter's autograd gradient into ``main_grad`` (what the GPU form
+    of `ops.qk_norm` wraps its norm weights in); device independent, checked on host tensors."""
+    from hypha_b200.ops.functional import _MainGradSink
+
+    w = torch.nn.Parameter(torch.randn(5))
+    w.main_grad = torch.zeros(5)
+    x = torch.randn(3, 5)
+    (_MainGradSink.apply(w) * x).sum().backward()
+    assert w.grad is None and torch.allclose(w.main_grad, x.sum(0))
+    w.grad_accumulate = True
+    (_MainGradSink.apply(w) * x).sum().backward()
+    assert torch.allclose(w.main_grad, 2 * x.sum(0))
+    plain = torch.nn.Parameter(torch.randn(5))
+    (_MainGradSink.apply(plain) * x).sum().backward()
+    assert torch.allclose(plain.grad, x.sum(0))
