@@ -74,12 +74,17 @@ class LlamaConfig:
 
     @classmethod
     def from_hf_dict(cls, meta: dict) -> "LlamaConfig":
-        """The configuration of a Hugging Face ``config.json`` of a family the sm_100a kernels cover: ``llama`` and
-        ``mistral`` (the Llama block with a sliding attention window: up to the window length causal attention IS
-        sliding-window attention, so the sequence length is capped there; HF parameter names are identical).
+        """The configuration of a Hugging Face ``config.json`` of a family the sm_100a kernels cover (`SM100_FAMILIES`):
+
+        * ``llama``; ``mistral`` and ``phi3`` = the Llama block with a sliding attention window (up to the window length
+          causal attention IS sliding-window attention, so the sequence length is capped there); ``phi3`` checkpoints
+          store q|k|v and gate|up fused;
+        * ``qwen2`` = the Llama block with a bias on q / k / v; ``qwen3`` = with an RMSNorm over every q and k head.
+
         RoPE settings are read from the top level (transformers < 5, hub checkpoints) or from ``rope_parameters`` /
-        ``rope_scaling``; plain RoPE and the ``llama3`` frequency scaling are supported, anything else -- and
-        projection biases -- is refused instead of being computed differently."""
+        ``rope_scaling``; plain RoPE and the ``llama3`` frequency scaling are supported.  Anything else (other RoPE
+        variants, biases on other projections, partial rotary embeddings, per-layer windows) is refused instead of
+        being computed differently."""
         family = meta.get("model_type", "llama")
         if family not in SM100_FAMILIES:
             raise RuntimeError(f"model_type {family!r} is not one of the sm_100a model families {SM100_FAMILIES}")
@@ -150,10 +155,10 @@ PRESETS: Dict[str, LlamaConfig] = {
                               max_seq_len=256, ce_chunk=128, name="llama-tiny"),
     "qwen2.5-7b": LlamaConfig(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
                               num_heads=28, num_kv_heads=4, head_dim=128, rope_theta=1000000.0, qkv_bias=True,
-                              rms_eps=1e-6, max_seq_len=32768, name="qwen2.5-7b"),
+                              rms_eps=1e-6, max_seq_len=32768, hf_family="qwen2", name="qwen2.5-7b"),
     "qwen2-tiny": LlamaConfig(vocab_size=1024, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
                               num_kv_heads=2, head_dim=64, rope_theta=1000000.0, qkv_bias=True, rms_eps=1e-6,
-                              max_seq_len=256, ce_chunk=128, name="qwen2-tiny"),
+                              max_seq_len=256, ce_chunk=128, hf_family="qwen2", name="qwen2-tiny"),
     "llama-small": LlamaConfig(vocab_size=32000, hidden_size=1024, intermediate_size=4096,
                                num_layers=4, num_heads=8, num_kv_heads=4, head_dim=128,
                                max_seq_len=2048, ce_chunk=2048, name="llama-small"),
