@@ -156,6 +156,20 @@ PRESETS: Dict[str, LlamaConfig] = {
     "qwen2.5-7b": LlamaConfig(vocab_size=152064, hidden_size=3584, intermediate_size=18944, num_layers=28,
                               num_heads=28, num_kv_heads=4, head_dim=128, rope_theta=1000000.0, qkv_bias=True,
                               rms_eps=1e-6, max_seq_len=32768, hf_family="qwen2", name="qwen2.5-7b"),
+    "llama3.2-1b": LlamaConfig(vocab_size=128256, hidden_size=2048, intermediate_size=8192, num_layers=16,
+                               num_heads=32, num_kv_heads=8, head_dim=64, tie_embeddings=True, max_seq_len=131072,
+                               rope_scaling={"rope_type": "llama3", "factor": 32.0, "low_freq_factor": 1.0,
+                                             "high_freq_factor": 4.0, "original_max_position_embeddings": 8192},
+                               name="llama3.2-1b"),
+    "mistral-7b": LlamaConfig(vocab_size=32000, hidden_size=4096, intermediate_size=14336, num_layers=32,
+                              num_heads=32, num_kv_heads=8, head_dim=128, rope_theta=10000.0, max_seq_len=4096,
+                              hf_family="mistral", name="mistral-7b"),          # v0.1: 4096-token sliding window
+    "qwen3-8b": LlamaConfig(vocab_size=151936, hidden_size=4096, intermediate_size=12288, num_layers=36,
+                            num_heads=32, num_kv_heads=8, head_dim=128, rope_theta=1000000.0, qk_norm=True,
+                            rms_eps=1e-6, max_seq_len=40960, hf_family="qwen3", name="qwen3-8b"),
+    "phi3-mini": LlamaConfig(vocab_size=32064, hidden_size=3072, intermediate_size=8192, num_layers=32,
+                             num_heads=32, num_kv_heads=32, head_dim=96, rope_theta=10000.0, max_seq_len=2047,
+                             hf_family="phi3", name="phi3-mini"),               # 4k variant: 2047-token window
     "qwen2-tiny": LlamaConfig(vocab_size=1024, hidden_size=256, intermediate_size=512, num_layers=2, num_heads=4,
                               num_kv_heads=2, head_dim=64, rope_theta=1000000.0, qkv_bias=True, rms_eps=1e-6,
                               max_seq_len=256, ce_chunk=128, hf_family="qwen2", name="qwen2-tiny"),

@@ -276,3 +276,25 @@ def test_gradients_of_plain_torch_ops_reach_the_flat_buffer():
     plain = torch.nn.Parameter(torch.randn(5))
     (_MainGradSink.apply(plain) * x).sum().backward()
     assert torch.allclose(plain.grad, x.sum(0))
+
+
+@pytest.mark.parametrize("preset,family,params_b", [("llama3-8b", "llama", 8.03), ("llama3.2-1b", "llama", 1.24),
+                                                    ("mistral-7b", "mistral", 7.24), ("qwen2.5-7b", "qwen2", 7.62),
+                                                    ("qwen3-8b", "qwen3", 8.19), ("phi3-mini", "phi3", 3.82)])
+def test_presets_have_the_published_parameter_counts(tmp_path, preset, family, params_b):
+    """The presets describe the published models: parameter count from the layout alone (no allocation), and the
+    `config.json` they write is read back as the same family."""
+    from hypha_b200.models.llama import LlamaConfig, get_config
+
+    c = get_config(preset)
+    h, i, v, d = c.hidden_size, c.intermediate_size, c.vocab_size, c.head_dim
+    qkv = (c.num_heads + 2 * c.num_kv_heads) * d
+    per_layer = qkv * h + (qkv if c.qkv_bias else 0) + (2 * d if c.qk_norm else 0) + c.num_heads * d * h + 3 * i * h + 2 * h
+    total = c.num_layers * per_layer + h + v * h * (1 if c.tie_embeddings else 2)
+    assert abs(total / 1e9 - params_b) < 0.01, total / 1e9
+    c.to_hf_json(str(tmp_path / "config.json"))
+    meta = json.load(open(tmp_path / "config.json"))
+    assert meta["model_type"] == family
+    back = LlamaConfig.from_hf_dict(meta)
+    assert (back.qkv_bias, back.qk_norm, back.tie_embeddings, back.hf_family) == (c.qkv_bias, c.qk_norm, c.tie_embeddings, family)
+    assert back.rope_scaling == c.rope_scaling and back.head_dim == c.head_dim
