@@ -86,14 +86,27 @@ def _run(cmd: list[str], verbose: bool) -> None:
         sys.stderr.write(r.stdout + r.stderr)
 
 
-def _compile(src: Path, kind: str, verbose: bool, extra: list[str] | None = None) -> Path:
-    extra = extra or []
+def _flags(kind: str, extra: list[str] | None = None) -> list[str]:
     if kind == "cu":
-        flags = NVCC_FLAGS + ["-I", str(CSRC), "-I", str(CSRC / "kernels")] + extra
-        tool = [NVCC]
-    else:
-        flags = CXX_FLAGS + ["-I", str(CSRC), "-I", os.path.join(CUDA_HOME, "include")] + _py_includes() + extra
-        tool = [CXX]
+        return NVCC_FLAGS + ["-I", str(CSRC), "-I", str(CSRC / "kernels")] + (extra or [])
+    return CXX_FLAGS + ["-I", str(CSRC), "-I", os.path.join(CUDA_HOME, "include")] + _py_includes() + (extra or [])
+
+
+def _up_to_date(out: Path, parts: list[tuple[Path, str]]) -> tuple[bool, Path, str]:
+    """Is the shared object next to the package the build of the current sources?  Its key (the hashes of every
+    source with its flags) is kept IN the package directory, so a copy of the tree that carries the `.so` but not the
+    object cache under ``build/`` (a fresh GPU box) does not compile anything."""
+    stamp = out.with_suffix(".srckey")
+    key = ",".join(f"{src.stem}.{_source_hash(src, _flags(kind))}" for src, kind in parts)
+    try:
+        return out.exists() and stamp.read_text() == key, stamp, key
+    except OSError:
+        return False, stamp, key
+
+
+def _compile(src: Path, kind: str, verbose: bool, extra: list[str] | None = None) -> Path:
+    flags = _flags(kind, extra)
+    tool = [NVCC] if kind == "cu" else [CXX]
     tag = _source_hash(src, flags)
     obj = BUILD / f"{src.stem}.{tag}.o"
     if obj.exists():
@@ -112,12 +125,17 @@ def cuda_sources() -> list[Path]:
 def build_core(verbose: bool = False) -> Path:
     """Build the pure-C++ control-plane core (``hypha_b200/_core*.so``)."""
     out = PKG / f"_core{EXT}"
+    fresh, srckey, key_src = _up_to_date(out, [(CSRC / "core" / "core_bindings.cpp", "cpp")])
+    if fresh:
+        return out
     obj = _compile(CSRC / "core" / "core_bindings.cpp", "cpp", verbose)
     stamp = BUILD / "_core.stamp"
     if out.exists() and stamp.exists() and stamp.read_text() == obj.name:
+        srckey.write_text(key_src)
         return out
     _run([CXX, "-shared", "-o", str(out), str(obj), "-pthread"], verbose)
     stamp.write_text(obj.name)
+    srckey.write_text(key_src)
     return out
 
 
@@ -127,6 +145,10 @@ def build_cuda(verbose: bool = False) -> Path:
         raise RuntimeError(f"nvcc not found at {NVCC}")
     out = PKG / f"_C{EXT}"
     srcs = cuda_sources()
+    cpp = [CSRC / "comm" / "peer_mem.cpp", CSRC / "comm" / "vmm.cpp", CSRC / "bindings.cpp"]
+    fresh, srckey, key_src = _up_to_date(out, [(s, "cu") for s in srcs] + [(c, "cpp") for c in cpp])
+    if fresh:
+        return out
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 4)) as ex:
         objs = list(ex.map(lambda s: _compile(s, "cu", verbose), srcs))
     objs.append(_compile(CSRC / "comm" / "peer_mem.cpp", "cpp", verbose))
@@ -135,10 +157,12 @@ def build_cuda(verbose: bool = False) -> Path:
     stamp = BUILD / "_C.stamp"
     key = ",".join(o.name for o in objs)
     if out.exists() and stamp.exists() and stamp.read_text() == key:
+        srckey.write_text(key_src)
         return out
     _run([NVCC] + ARCH + ["-shared", "-o", str(out)] + [str(o) for o in objs]
          + ["-cudart", "static", "-lpthread", "-ldl", "-lrt"], verbose)
     stamp.write_text(key)
+    srckey.write_text(key_src)
     return out
 
 
